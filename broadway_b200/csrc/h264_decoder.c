@@ -1,0 +1,456 @@
+/* h264_decoder.c — the NAL-level state machine behind h264bsdInit / h264bsdDecode /
+ * h264bsdNextOutputPicture / h264bsdShutdown and the accessors
+ * (reference: h264bsd_decoder.c:99-122, :162-560, :579-618, :642-1006,
+ * h264bsd_byte_stream.c:80-237, h264bsd_nal_unit.c:68-117,
+ * h264bsd_storage.c:298-420 activation, :632-800 access-unit boundary).
+ *
+ * Same call protocol and return codes as the reference: one NAL unit consumed
+ * per call; *readBytes = 0 when the same buffer must be presented again
+ * (H264BSD_HDRS_RDY after a new SPS was activated); H264BSD_PIC_RDY as soon as
+ * the last macroblock of a picture has been parsed.  What differs is what
+ * "decode a slice" means: the slice is parsed into macroblock records and the
+ * finished picture is handed to the backend (CUDA engine) for reconstruction;
+ * pixels exist only on the GPU until h264bsdNextOutputPicture asks for them.
+ * Error concealment (h264bsd_conceal.c) is out of scope: macroblocks of a lost
+ * or corrupt slice are reported through numErrMbs and left unreconstructed.
+ */
+#include <stdlib.h>
+#include <string.h>
+#include <stdio.h>
+#include "h264b200.h"
+#include "h264_internal.h"
+
+static h264_decoder_t *DEC(storage_t *s) { return s ? (h264_decoder_t *)s->impl : NULL; }
+
+/* ------------------------------------------------------------ NAL extraction */
+/* Find the NAL unit at the head of buf: Annex-B (00 00 01 / 00 00 00 prefix) or a
+ * bare NAL.  Removes emulation prevention bytes IN PLACE (the reference does the
+ * same to the caller's buffer, h264bsd_byte_stream.c:192-234).  Returns 0 and sets
+ * nal/nal_len/consumed, or -1. */
+static int extract_nal(uint8_t *buf, uint32_t len, uint8_t **nal, uint32_t *nal_len, uint32_t *consumed)
+{
+    uint32_t start = 0, end = len, trailing = 0, i, zeros;
+    int has_epb = 0, invalid = 0;
+    if (len > 3 && buf[0] == 0 && buf[1] == 0 && (buf[2] & 0xFE) == 0) {
+        /* skip to the byte after the first start code prefix */
+        i = 2; zeros = 2;
+        for (;;) {
+            uint8_t v = buf[i++];
+            if (i == len) { *consumed = len; return -1; }
+            if (!v) zeros++;
+            else if (v == 1 && zeros >= 2) break;
+            else zeros = 0;
+        }
+        start = i;
+        /* the NAL ends at the next start code prefix or at the end of the buffer; trailing
+         * zero bytes are not part of it (runs of zeros are located with memchr) */
+        while (i < len) {
+            const uint8_t *z = (const uint8_t *)memchr(buf + i, 0, len - i);
+            uint32_t j;
+            if (!z) break;
+            i = (uint32_t)(z - buf);
+            for (j = i; j < len && buf[j] == 0; j++) ;
+            zeros = j - i;
+            if (j == len) { end = i; trailing = zeros; break; }
+            if (zeros >= 2 && buf[j] == 1) { end = i; trailing = zeros > 3 ? zeros - 3 : 0; break; }
+            if (zeros == 2 && buf[j] == 3) has_epb = 1;
+            else if (zeros >= 3) invalid = 1;          /* 00 00 00 xx inside a NAL unit */
+            i = j + 1;
+        }
+        *nal = buf + start; *nal_len = end - start; *consumed = end + trailing;
+        if (invalid) return -1;
+    } else {
+        *nal = buf; *nal_len = len; *consumed = len; has_epb = 1;
+    }
+    if (has_epb) {
+        uint8_t *p = *nal, *e = p + *nal_len, *r = p, *w;
+        /* locate the first 00 00 03, then compact the rest byte by byte */
+        while (r < e) {
+            uint8_t *z = (uint8_t *)memchr(r, 0, (size_t)(e - r));
+            if (!z || z + 2 >= e) { r = e; break; }
+            if (z[1] == 0 && z[2] == 3) { r = z; break; }
+            r = z + 1;
+        }
+        if (r < e) {
+            w = r; zeros = 0;
+            while (r < e) {
+                if (zeros == 2 && *r == 3) {
+                    if (r + 1 == e || r[1] > 3) return -1;
+                    r++; zeros = 0; continue;
+                }
+                if (zeros == 2 && *r <= 2) return -1;
+                zeros = *r == 0 ? zeros + 1 : 0;
+                *w++ = *r++;
+            }
+            *nal_len = (uint32_t)(w - p);
+        }
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------- access unit boundary */
+static int check_au_boundary(h264_decoder_t *d, br_t b /* by value, after the NAL header */, int type, int ref_idc, int *boundary)
+{
+    uint32_t pps_id, v, frame_num;
+    const h264_pps_t *pps; const h264_sps_t *sps;
+    *boundary = 0;
+    if ((type > 5 && type < 12) || (type > 12 && type <= 18)) { *boundary = 1; return 0; }
+    if (type != NAL_SLICE && type != NAL_IDR) return 0;
+    if (d->aub.first_call) { *boundary = 1; d->aub.first_call = 0; }
+    if (h264_peek_pps_id(b, &pps_id)) return -1;
+    pps = d->pps[pps_id];
+    if (!pps || !d->sps[pps->sps_id] ||
+        (d->active_sps_id != H264_MAX_SPS && pps->sps_id != d->active_sps_id && type != NAL_IDR)) return -2;
+    sps = d->sps[pps->sps_id];
+    if (d->aub.prev_ref_idc != ref_idc && (d->aub.prev_ref_idc == 0 || ref_idc == 0)) *boundary = 1;
+    if ((d->aub.prev_type == NAL_IDR) != (type == NAL_IDR)) *boundary = 1;
+    v = br_ue(&b); v = br_ue(&b); v = br_ue(&b);     /* first_mb, slice_type, pps_id */
+    (void)v;
+    frame_num = br_get(&b, sps->log2_max_frame_num);
+    if (d->aub.prev_frame_num != frame_num) { d->aub.prev_frame_num = frame_num; *boundary = 1; }
+    if (type == NAL_IDR) {
+        v = br_ue(&b);
+        if (v == 0xffffffffu) return -1;
+        if (d->aub.prev_type == NAL_IDR && d->aub.prev_idr_pic_id != v) *boundary = 1;
+        d->aub.prev_idr_pic_id = v;
+    }
+    if (sps->poc_type == 0) {
+        v = br_get(&b, sps->log2_max_poc_lsb);
+        if (d->aub.prev_poc_lsb != v) { d->aub.prev_poc_lsb = v; *boundary = 1; }
+        if (pps->pic_order_present) {
+            int32_t sv = br_se(&b);
+            if (d->aub.prev_delta_poc_bottom != sv) { d->aub.prev_delta_poc_bottom = sv; *boundary = 1; }
+        }
+    } else if (sps->poc_type == 1 && !sps->delta_pic_order_always_zero) {
+        int32_t sv = br_se(&b);
+        if (d->aub.prev_delta_poc[0] != sv) { d->aub.prev_delta_poc[0] = sv; *boundary = 1; }
+        if (pps->pic_order_present) {
+            sv = br_se(&b);
+            if (d->aub.prev_delta_poc[1] != sv) { d->aub.prev_delta_poc[1] = sv; *boundary = 1; }
+        }
+    }
+    d->aub.prev_ref_idc = (uint8_t)ref_idc; d->aub.prev_type = (uint8_t)type;
+    return br_overrun(&b) ? -1 : 0;
+}
+
+/* --------------------------------------------------------- parameter sets */
+static int sps_equal(const h264_sps_t *a, const h264_sps_t *b) { return memcmp(a, b, sizeof *a) == 0; }
+
+static int store_sps(h264_decoder_t *d, const h264_sps_t *s)
+{
+    int id = s->sps_id;
+    if (!d->sps[id]) { d->sps[id] = (h264_sps_t *)malloc(sizeof *s); if (!d->sps[id]) return -1; }
+    else if (id == d->active_sps_id) {
+        if (sps_equal(s, d->active_sps)) return 0;
+        d->active_sps_id = H264_MAX_SPS + 1; d->active_pps_id = H264_MAX_PPS + 1;
+        d->active_sps = NULL; d->active_pps = NULL;
+    }
+    *d->sps[id] = *s;
+    return 0;
+}
+static int store_pps(h264_decoder_t *d, const h264_pps_t *p)
+{
+    int id = p->pps_id;
+    if (!d->pps[id]) { d->pps[id] = (h264_pps_t *)malloc(sizeof *p); if (!d->pps[id]) return -1; }
+    else if (id == d->active_pps_id) {
+        if (p->sps_id != d->active_sps_id) d->active_pps_id = H264_MAX_PPS + 1;
+    }
+    *d->pps[id] = *p;
+    if (id == d->active_pps_id) d->active_pps = d->pps[id];
+    return 0;
+}
+
+static void select_sets(h264_decoder_t *d, uint32_t pps_id)
+{
+    d->active_pps_id = (int)pps_id; d->active_pps = d->pps[pps_id];
+    d->active_sps_id = d->active_pps->sps_id; d->active_sps = d->sps[d->active_sps_id];
+    d->width_mbs = d->active_sps->width_mbs; d->height_mbs = d->active_sps->height_mbs;
+    d->pic_size_mbs = d->width_mbs * d->height_mbs;
+    d->pending_activation = 1;
+}
+
+/* 0 ok, -1 bad combination, -2 allocation failure (h264bsd_storage.c:298-420) */
+static int activate_param_sets(h264_decoder_t *d, uint32_t pps_id, int is_idr)
+{
+    if (!d->pps[pps_id] || !d->sps[d->pps[pps_id]->sps_id]) return -1;
+    if (d->active_pps_id == H264_MAX_PPS) select_sets(d, pps_id);
+    else if (d->pending_activation) {
+        const h264_sps_t *sps = d->active_sps;
+        int no_reorder;
+        d->pending_activation = 0;
+        free(d->mbctx);
+        d->mbctx = (h264_mbctx_t *)calloc(d->pic_size_mbs, sizeof(h264_mbctx_t));
+        if (!d->mbctx) return -2;
+        no_reorder = d->no_reordering_app || sps->poc_type == 2 ||
+                     (sps->vui_present && sps->bitstream_restriction && !sps->num_reorder_frames);
+        h264_dpb_init(&d->dpb, sps->max_dpb_size, sps->num_ref_frames, sps->max_frame_num, no_reorder);
+        d->n_slots = d->dpb.dpb_size + 1;
+        if (!d->be) d->be = h264_default_backend();   /* CUDA engine; NULL (reason on stderr) without a usable GPU */
+        if (!d->be) return -2;
+        if (d->be_inst) { d->be->inst_destroy(d->be, d->be_inst); d->be_inst = NULL; }
+        d->be_inst = d->be->inst_create(d->be, d->width_mbs, d->height_mbs, d->n_slots);
+        if (!d->be_inst) return -2;
+        d->pic = NULL;
+    } else if ((int)pps_id != d->active_pps_id) {
+        if (d->pps[pps_id]->sps_id != d->active_sps_id) {
+            if (!is_idr) return -1;
+            select_sets(d, pps_id);
+        } else { d->active_pps_id = (int)pps_id; d->active_pps = d->pps[pps_id]; }
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------ picture end */
+static void finish_picture(h264_decoder_t *d)
+{
+    int is_idr = d->pic_nal_type == NAL_IDR;
+    int32_t poc;
+    if (d->pic) {
+        d->pic->cur_slot = h264_dpb_current_slot(&d->dpb);
+        d->be->pic_submit(d->be, d->be_inst, d->pic);
+        d->pic = NULL;
+    }
+    d->num_decoded_mbs = 0; d->slice_id = 0;
+    poc = h264_decode_poc(d, &d->sh, d->pic_nal_type, d->pic_nal_ref_idc);
+    if (d->valid_slice_in_au)
+        h264_dpb_mark(&d->dpb, &d->sh, d->pic_nal_ref_idc != 0, is_idr, poc, d->current_pic_id, d->num_err_mbs);
+    d->pic_started = 0; d->valid_slice_in_au = 0;
+}
+
+static int begin_picture(h264_decoder_t *d)
+{
+    uint32_t i;
+    d->pic = d->be->pic_begin(d->be, d->be_inst);
+    if (!d->pic) return -1;
+    d->pic->coef_used = 0; d->pic->n_intra = d->pic->n_inter = 0; d->pic->any_deblock = 0;
+    memset(d->pic->ref_slots_used, 0, sizeof d->pic->ref_slots_used);
+    memset(d->mbctx, 0, d->pic_size_mbs * sizeof(h264_mbctx_t));
+    for (i = 0; i < d->pic_size_mbs; i++) d->pic->mbs[i].mb_class = H264B200_MB_MISSING;
+    d->num_decoded_mbs = 0; d->slice_id = 0;
+    return 0;
+}
+
+/* ------------------------------------------------------------------ API */
+u32 h264_decoder_create(storage_t *pStorage, u32 noOutputReordering, h264_backend_t *be)
+{
+    h264_decoder_t *d;
+    if (!pStorage) return HANTRO_NOK;
+    memset(pStorage, 0, sizeof *pStorage);
+    d = (h264_decoder_t *)calloc(1, sizeof *d);
+    if (!d) return HANTRO_NOK;
+    h264_cavlc_init();
+    d->be = be;
+    d->active_sps_id = H264_MAX_SPS; d->active_pps_id = H264_MAX_PPS; d->old_sps_id = H264_MAX_SPS + 1;
+    d->aub.first_call = 1;
+    d->no_reordering_app = noOutputReordering ? 1 : 0;
+    pStorage->impl = d;
+    return HANTRO_OK;
+}
+
+u32 h264bsdInit(storage_t *pStorage, u32 noOutputReordering)
+{
+    return h264_decoder_create(pStorage, noOutputReordering, NULL);
+}
+
+u32 h264bsdDecode(storage_t *pStorage, u8 *byteStrm, u32 len, u32 picId, u32 *readBytes)
+{
+    h264_decoder_t *d = DEC(pStorage);
+    uint8_t *nal; uint32_t nal_len, consumed;
+    int type, ref_idc, boundary = 0, pic_ready = 0, rc;
+    br_t b;
+    if (!d || !byteStrm || !len || !readBytes) return H264BSD_ERROR;
+
+    if (d->prev_buf_not_finished && byteStrm == d->prev_buf_ptr) {
+        nal = (uint8_t *)d->nal_data; nal_len = (uint32_t)d->nal_len;
+        *readBytes = d->prev_bytes_consumed;
+    } else {
+        if (extract_nal(byteStrm, len, &nal, &nal_len, &consumed)) { *readBytes = consumed; return H264BSD_ERROR; }
+        *readBytes = consumed;
+        d->nal_data = nal; d->nal_len = nal_len;
+        d->prev_bytes_consumed = consumed; d->prev_buf_ptr = byteStrm;
+    }
+    d->prev_buf_not_finished = 0;
+    if (nal_len < 1) return H264BSD_ERROR;
+    ref_idc = (nal[0] >> 5) & 3; type = nal[0] & 31;
+    if (type == 2 || type == 3 || type == 4) return H264BSD_ERROR;       /* data partitioning: not Baseline decoder scope */
+    if ((type == NAL_SPS || type == NAL_PPS || type == NAL_IDR) && ref_idc == 0) return H264BSD_ERROR;
+    if ((type == NAL_SEI || type == NAL_AUD || type == NAL_EOSEQ || type == NAL_EOSTREAM || type == NAL_FILLER) && ref_idc != 0) return H264BSD_ERROR;
+    if (type == 0 || type >= 13) return H264BSD_RDY;
+    br_init(&b, nal + 1, nal_len - 1);
+
+    rc = check_au_boundary(d, b, type, ref_idc, &boundary);
+    if (rc) return rc == -2 ? H264BSD_PARAM_SET_ERROR : H264BSD_ERROR;
+    if (boundary) {
+        if (d->pic_started && d->active_sps) {
+            /* a new access unit starts while the previous picture is incomplete: the reference
+             * conceals here (h264bsd_decoder.c:236-270). Concealment is out of scope: the missing
+             * macroblocks are counted and the picture is finished as it is. */
+            if (d->pending_activation) return H264BSD_ERROR;
+            if (!d->valid_slice_in_au) {
+                if (begin_picture(d)) return H264BSD_MEMALLOC_ERROR;
+                h264_dpb_init_ref_list(&d->dpb);
+            }
+            d->num_err_mbs = d->pic_size_mbs - d->num_decoded_mbs;
+            pic_ready = 1;
+            *readBytes = 0; d->prev_buf_not_finished = 1;
+        } else d->valid_slice_in_au = 0;
+        d->skip_redundant = 0;
+    }
+
+    if (!pic_ready) switch (type) {
+    case NAL_SPS: {
+        h264_sps_t *sps = (h264_sps_t *)malloc(sizeof *sps);
+        if (!sps) return H264BSD_MEMALLOC_ERROR;
+        rc = h264_parse_sps(&b, sps);
+        if (!rc) rc = store_sps(d, sps);
+        free(sps);
+        if (rc) return H264BSD_ERROR;
+        break; }
+    case NAL_PPS: {
+        h264_pps_t pps;
+        if (h264_parse_pps(&b, &pps)) return H264BSD_ERROR;
+        if (store_pps(d, &pps)) return H264BSD_MEMALLOC_ERROR;
+        break; }
+    case NAL_IDR:
+    case NAL_SLICE: {
+        h264_slice_hdr_t sh;
+        int start_of_pic;
+        if (d->skip_redundant) return H264BSD_RDY;
+        d->pic_started = 1;
+        start_of_pic = !d->valid_slice_in_au;
+        if (start_of_pic) {
+            uint32_t pps_id; int old_sps;
+            d->num_err_mbs = 0; d->current_pic_id = picId;
+            if (h264_peek_pps_id(b, &pps_id)) return H264BSD_ERROR;
+            old_sps = d->active_sps_id;
+            rc = activate_param_sets(d, pps_id, type == NAL_IDR);
+            if (rc) {
+                d->active_pps_id = H264_MAX_PPS; d->active_pps = NULL;
+                d->active_sps_id = H264_MAX_SPS; d->active_sps = NULL;
+                d->pending_activation = 0;
+                return rc == -2 ? H264BSD_MEMALLOC_ERROR : H264BSD_PARAM_SET_ERROR;
+            }
+            if (old_sps != d->active_sps_id) {
+                const h264_sps_t *old = d->old_sps_id < H264_MAX_SPS ? d->sps[d->old_sps_id] : NULL, *nw = d->active_sps;
+                int no_output = 1, ok = 0;
+                *readBytes = 0; d->prev_buf_not_finished = 1;
+                if (type == NAL_IDR) {
+                    h264_slice_hdr_t tmp;
+                    if (!h264_parse_slice_header(&b, &tmp, nw, d->active_pps, type, ref_idc)) { ok = 1; no_output = tmp.no_output_of_prior_pics; }
+                }
+                if (!ok || no_output || d->dpb.no_reordering || !old || old->width_mbs != nw->width_mbs ||
+                    old->height_mbs != nw->height_mbs || old->max_dpb_size != nw->max_dpb_size) d->dpb.flushed = 0;
+                else h264_dpb_flush(&d->dpb);
+                d->old_sps_id = d->active_sps_id;
+                return H264BSD_HDRS_RDY;
+            }
+        }
+        if (d->pending_activation) return H264BSD_ERROR;
+        if (h264_parse_slice_header(&b, &sh, d->active_sps, d->active_pps, type, ref_idc)) return H264BSD_ERROR;
+        if (start_of_pic) {
+            if (type != NAL_IDR && h264_dpb_check_gaps(&d->dpb, sh.frame_num, ref_idc != 0, d->active_sps->gaps_allowed)) return H264BSD_ERROR;
+            if (begin_picture(d)) return H264BSD_MEMALLOC_ERROR;
+        }
+        d->sh = sh; d->valid_slice_in_au = 1;
+        d->pic_nal_type = (uint8_t)type; d->pic_nal_ref_idc = (uint8_t)ref_idc;
+        if (sh.redundant_pic_cnt) break;          /* redundant coded pictures are not decoded */
+        h264_dpb_init_ref_list(&d->dpb);
+        if (h264_dpb_reorder(&d->dpb, &d->sh)) return H264BSD_ERROR;
+        if (h264_decode_slice_data(d, &b, &d->sh)) {
+            /* the reference marks the slice corrupt and conceals at the next access unit
+             * (h264bsd_slice_data.c:302-358); here its macroblocks stay MISSING */
+            return H264BSD_ERROR;
+        }
+        if (d->num_decoded_mbs == d->pic_size_mbs) { pic_ready = 1; d->skip_redundant = 1; }
+        break; }
+    default: break;                                /* SEI, AUD, end of sequence/stream, filler: ignored */
+    }
+
+    if (pic_ready) { finish_picture(d); return H264BSD_PIC_RDY; }
+    return H264BSD_RDY;
+}
+
+u8 *h264bsdNextOutputPicture(storage_t *pStorage, u32 *picId, u32 *isIdrPic, u32 *numErrMbs)
+{
+    h264_decoder_t *d = DEC(pStorage);
+    const h264_out_t *o;
+    uint32_t err = 0;
+    uint8_t *p;
+    if (!d || !d->dpb.allocated || !d->be_inst) return NULL;
+    o = h264_dpb_next_output(&d->dpb);
+    if (!o) return NULL;
+    p = d->be->frame_host(d->be, d->be_inst, o->slot, &err);
+    if (picId) *picId = o->pic_id;
+    if (isIdrPic) *isIdrPic = o->is_idr;
+    if (numErrMbs) *numErrMbs = o->num_err_mbs;
+    return p;
+}
+
+void h264bsdShutdown(storage_t *pStorage)
+{
+    h264_decoder_t *d = DEC(pStorage);
+    int i;
+    if (!d) return;
+    if (d->be_inst) d->be->inst_destroy(d->be, d->be_inst);
+    for (i = 0; i < H264_MAX_SPS; i++) free(d->sps[i]);
+    for (i = 0; i < H264_MAX_PPS; i++) free(d->pps[i]);
+    free(d->mbctx);
+    free(d);
+    pStorage->impl = NULL;
+}
+
+u32 h264bsdPicWidth(storage_t *s)  { h264_decoder_t *d = DEC(s); return d && d->active_sps ? d->active_sps->width_mbs : 0; }
+u32 h264bsdPicHeight(storage_t *s) { h264_decoder_t *d = DEC(s); return d && d->active_sps ? d->active_sps->height_mbs : 0; }
+u32 h264bsdVideoRange(storage_t *s)
+{
+    h264_decoder_t *d = DEC(s);
+    return d && d->active_sps && d->active_sps->vui_present && d->active_sps->video_signal_present && d->active_sps->video_full_range;
+}
+u32 h264bsdMatrixCoefficients(storage_t *s)
+{
+    h264_decoder_t *d = DEC(s);
+    if (d && d->active_sps && d->active_sps->vui_present && d->active_sps->video_signal_present && d->active_sps->colour_desc_present)
+        return d->active_sps->matrix_coefficients;
+    return 2;
+}
+void h264bsdCroppingParams(storage_t *s, u32 *croppingFlag, u32 *left, u32 *width, u32 *top, u32 *height)
+{
+    h264_decoder_t *d = DEC(s);
+    if (d && d->active_sps && d->active_sps->crop_flag) {
+        const h264_sps_t *p = d->active_sps;
+        *croppingFlag = 1;
+        *left = 2 * p->crop_left; *width = 16 * p->width_mbs - 2 * (p->crop_left + p->crop_right);
+        *top = 2 * p->crop_top;   *height = 16 * p->height_mbs - 2 * (p->crop_top + p->crop_bottom);
+    } else { *croppingFlag = 0; *left = 0; *width = 0; *top = 0; *height = 0; }
+}
+void h264bsdSampleAspectRatio(storage_t *s, u32 *sarWidth, u32 *sarHeight)
+{
+    static const uint8_t tab[14][2] = {{0,0},{1,1},{12,11},{10,11},{16,11},{40,33},{24,11},{20,11},{32,11},{80,33},{18,11},{15,11},{64,33},{160,99}};
+    h264_decoder_t *d = DEC(s);
+    u32 w = 1, h = 1;
+    if (d && d->active_sps && d->active_sps->vui_present && d->active_sps->aspect_ratio_present) {
+        const h264_sps_t *p = d->active_sps;
+        if (p->aspect_ratio_idc < 14) { w = tab[p->aspect_ratio_idc][0]; h = tab[p->aspect_ratio_idc][1]; }
+        else if (p->aspect_ratio_idc == 255) { w = p->sar_width; h = p->sar_height; if (!w || !h) w = h = 0; }
+        else w = h = 0;
+    }
+    *sarWidth = w; *sarHeight = h;
+}
+u32 h264bsdCheckValidParamSets(storage_t *s)
+{
+    h264_decoder_t *d = DEC(s);
+    int i;
+    if (!d) return 0;
+    for (i = 0; i < H264_MAX_PPS; i++) if (d->pps[i] && d->sps[d->pps[i]->sps_id]) return 1;
+    return 0;
+}
+void h264bsdFlushBuffer(storage_t *s) { h264_decoder_t *d = DEC(s); if (d) h264_dpb_flush(&d->dpb); }
+u32 h264bsdProfile(storage_t *s) { h264_decoder_t *d = DEC(s); return d && d->active_sps ? d->active_sps->profile_idc : 0; }
+
+/* used by the H264SwDec layer (h264_swdec.c): DPB flags the reference's API pokes directly */
+int h264_decoder_flushed_pending(storage_t *s)
+{
+    h264_decoder_t *d = DEC(s);
+    if (d && d->dpb.flushed && d->dpb.num_out != d->dpb.out_index) { d->dpb.flushed = 0; return 1; }
+    return 0;
+}

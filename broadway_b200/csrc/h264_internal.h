@@ -1,0 +1,213 @@
+/* h264_internal.h — private structures of the host side of the decoder:
+ * parameter sets, slice header, decoded picture buffer bookkeeping, the
+ * per-instance state behind the opaque `storage_t`, and the backend interface
+ * through which finished pictures (macroblock records + coefficient slots) are
+ * handed to the reconstruction engine (CUDA in the product library).
+ */
+#ifndef B200_H264_INTERNAL_H
+#define B200_H264_INTERNAL_H
+#include <stdint.h>
+#include <stddef.h>
+#include "h264b200_records.h"
+#include "h264_bits.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define H264_MAX_SPS 32
+#define H264_MAX_PPS 256
+#define H264_MAX_REFS 16
+#define H264_MAX_SLOTS 18          /* dpbSize(<=16) + current + 1 spare */
+
+enum { NAL_SLICE = 1, NAL_IDR = 5, NAL_SEI = 6, NAL_SPS = 7, NAL_PPS = 8, NAL_AUD = 9, NAL_EOSEQ = 10, NAL_EOSTREAM = 11, NAL_FILLER = 12 };
+
+typedef struct {
+    uint8_t  valid;
+    uint8_t  profile_idc, level_idc, sps_id;
+    uint32_t max_frame_num;            /* 2^(log2_max_frame_num) */
+    uint8_t  log2_max_frame_num;
+    uint8_t  poc_type;
+    uint8_t  log2_max_poc_lsb;
+    uint32_t max_poc_lsb;
+    uint8_t  delta_pic_order_always_zero;
+    int32_t  offset_for_non_ref_pic, offset_for_top_to_bottom;
+    uint32_t num_ref_frames_in_poc_cycle;
+    int32_t  offset_for_ref_frame[256];
+    uint32_t num_ref_frames;
+    uint8_t  gaps_allowed;
+    uint32_t width_mbs, height_mbs;
+    uint8_t  crop_flag;
+    uint32_t crop_left, crop_right, crop_top, crop_bottom;
+    uint32_t max_dpb_size;
+    /* VUI subset the API reports / the DPB uses (h264bsd_vui.c) */
+    uint8_t  vui_present, aspect_ratio_present, aspect_ratio_idc;
+    uint32_t sar_width, sar_height;
+    uint8_t  video_signal_present, video_full_range, colour_desc_present, matrix_coefficients;
+    uint8_t  bitstream_restriction;
+    uint32_t num_reorder_frames, max_dec_frame_buffering;
+} h264_sps_t;
+
+typedef struct {
+    uint8_t  valid;
+    uint8_t  pps_id, sps_id;
+    uint8_t  pic_order_present;
+    uint32_t num_slice_groups;
+    uint32_t num_ref_idx_l0_default;
+    int32_t  pic_init_qp;
+    int32_t  chroma_qp_index_offset;
+    uint8_t  deblocking_control_present, constrained_intra_pred, redundant_pic_cnt_present;
+} h264_pps_t;
+
+typedef struct { uint8_t idc; uint32_t val; } h264_reorder_cmd_t;
+typedef struct { uint8_t op; uint32_t diff_pic_nums, long_term_pic_num, long_term_frame_idx, max_long_term_frame_idx; } h264_mmco_t;
+
+typedef struct {
+    uint32_t first_mb;
+    uint8_t  slice_type;               /* 0 P, 2 I (mod 5) */
+    uint32_t pps_id, frame_num, idr_pic_id, poc_lsb;
+    int32_t  delta_poc_bottom, delta_poc[2];
+    uint32_t redundant_pic_cnt;
+    uint32_t num_ref_idx_active;
+    uint8_t  reorder_flag; uint32_t n_reorder; h264_reorder_cmd_t reorder[H264_MAX_REFS + 2];
+    uint8_t  no_output_of_prior_pics, long_term_reference_flag, adaptive_marking;
+    uint32_t n_mmco; h264_mmco_t mmco[36];
+    int32_t  slice_qp;
+    uint8_t  disable_deblocking_idc; int8_t alpha_off, beta_off;   /* offsets already *2 */
+} h264_slice_hdr_t;
+
+/* -------------------------------------------------------------------- DPB */
+enum { PIC_UNUSED = 0, PIC_NON_EXISTING, PIC_SHORT, PIC_LONG };
+typedef struct {
+    int      slot;                     /* frame-pool slot (stable id of the frame storage) */
+    int      status;
+    int32_t  pic_num;                  /* PicNum / LongTermPicNum */
+    uint32_t frame_num;
+    int32_t  poc;
+    uint8_t  to_be_displayed;
+    uint32_t pic_id, num_err_mbs, is_idr;
+} h264_dpb_pic_t;
+
+typedef struct { int slot; uint32_t pic_id, num_err_mbs, is_idr; } h264_out_t;
+
+typedef struct {
+    h264_dpb_pic_t buf[H264_MAX_REFS + 1];   /* sorted; buf[dpb_size] is the picture being decoded */
+    h264_dpb_pic_t *list[H264_MAX_REFS + 1]; /* RefPicList0 */
+    h264_out_t out[H264_MAX_REFS + 2];
+    uint32_t num_out, out_index;
+    uint32_t max_ref_frames, dpb_size, max_frame_num, max_long_term_idx;
+    uint32_t num_ref_frames, fullness, prev_ref_frame_num;
+    uint8_t  no_reordering, flushed, last_has_mmco5, allocated;
+} h264_dpb_t;
+
+#define H264_NO_LONG_TERM 0xFFFF
+
+void h264_dpb_init(h264_dpb_t *d, uint32_t dpb_size, uint32_t max_ref_frames, uint32_t max_frame_num, int no_reordering);
+int  h264_dpb_current_slot(h264_dpb_t *d);
+int  h264_dpb_check_gaps(h264_dpb_t *d, uint32_t frame_num, int is_ref, int gaps_allowed);
+void h264_dpb_init_ref_list(h264_dpb_t *d);
+int  h264_dpb_reorder(h264_dpb_t *d, const h264_slice_hdr_t *sh);
+int  h264_dpb_ref_slot(const h264_dpb_t *d, uint32_t ref_idx);  /* -1: missing / non-existing */
+int  h264_dpb_mark(h264_dpb_t *d, const h264_slice_hdr_t *sh, int is_ref, int is_idr, int32_t poc, uint32_t pic_id, uint32_t num_err);
+void h264_dpb_flush(h264_dpb_t *d);
+const h264_out_t *h264_dpb_next_output(h264_dpb_t *d);
+
+/* ---------------------------------------------------------------- backend */
+/* One picture's worth of host-written input for the reconstruction engine. */
+typedef struct {
+    h264b200_mb_t *mbs;        /* width_mbs*height_mbs records (pinned in the CUDA backend) */
+    int16_t  *coef;            /* coefficient slots */
+    uint32_t  coef_cap;        /* capacity in slots */
+    uint32_t  coef_used;       /* slots written */
+    uint32_t  n_intra, n_inter;/* macroblock class counts (lets the engine skip kernels) */
+    uint32_t  any_deblock;     /* some macroblock has filtering enabled */
+    int       cur_slot;
+    uint8_t   ref_slots_used[H264_MAX_SLOTS];
+    void     *priv;
+} h264_pic_input_t;
+
+typedef struct h264_backend h264_backend_t;
+struct h264_backend {
+    /* (re)allocate the frame pool of one decoder instance: n_slots frames of width x height MBs */
+    void *(*inst_create)(h264_backend_t *be, uint32_t width_mbs, uint32_t height_mbs, uint32_t n_slots);
+    void  (*inst_destroy)(h264_backend_t *be, void *inst);
+    /* get a free input buffer for the next picture (may wait for an in-flight one) */
+    h264_pic_input_t *(*pic_begin)(h264_backend_t *be, void *inst);
+    /* grow pic->coef to at least min_slots (contents preserved); 0 on success */
+    int   (*coef_grow)(h264_backend_t *be, void *inst, h264_pic_input_t *pic, uint32_t min_slots);
+    /* picture complete: reconstruct + deblock into frame slot pic->cur_slot (asynchronous) */
+    int   (*pic_submit)(h264_backend_t *be, void *inst, h264_pic_input_t *pic);
+    /* host-visible I420 frame of `slot`, valid once the picture last submitted into it is done */
+    uint8_t *(*frame_host)(h264_backend_t *be, void *inst, int slot, uint32_t *error_flags);
+    void  (*destroy)(h264_backend_t *be);
+    void  *ctx;
+};
+
+/* implemented by whichever backend is linked: the CUDA engine in libh264b200.so */
+h264_backend_t *h264_default_backend(void);
+
+/* ------------------------------------------------------- per-MB host context */
+typedef struct {
+    uint8_t  tc[24];           /* TotalCoeff by luma4x4BlkIdx, Cb 16..19, Cr 20..23 */
+    int8_t   ref_idx[4];       /* refIdxL0 per 8x8 (-1 intra) */
+    uint8_t  kind;             /* H264B200_MB_* */
+    uint8_t  decoded;
+    uint16_t slice_id;         /* 0 = not decoded in this picture */
+} h264_mbctx_t;
+
+/* ------------------------------------------------------- decoder instance */
+typedef struct h264_decoder {
+    h264_backend_t *be;
+    void *be_inst;
+    int   owns_backend;
+    h264_sps_t *sps[H264_MAX_SPS];
+    h264_pps_t *pps[H264_MAX_PPS];
+    int active_sps_id, active_pps_id, old_sps_id;
+    h264_sps_t *active_sps; h264_pps_t *active_pps;
+    int pending_activation;
+    uint32_t width_mbs, height_mbs, pic_size_mbs, n_slots;
+    int no_reordering_app;
+
+    /* NAL / access unit state (h264bsd_storage.c:632-800) */
+    struct { int first_call; uint8_t prev_ref_idc, prev_type; uint32_t prev_frame_num, prev_idr_pic_id, prev_poc_lsb;
+             int32_t prev_delta_poc_bottom, prev_delta_poc[2]; } aub;
+    int pic_started, valid_slice_in_au, skip_redundant;
+    uint8_t *prev_buf_ptr; uint32_t prev_bytes_consumed; int prev_buf_not_finished;
+    const uint8_t *nal_data; size_t nal_len;      /* current RBSP (inside the caller's buffer) */
+    uint8_t cur_nal_type, cur_nal_ref_idc;
+    uint8_t pic_nal_type, pic_nal_ref_idc;        /* of the last valid slice */
+
+    h264_slice_hdr_t sh;                          /* last valid slice header */
+    uint32_t slice_id;                            /* restarts at 1 each picture */
+    uint32_t num_decoded_mbs, num_err_mbs;
+    uint32_t current_pic_id;
+
+    /* POC state (h264bsd_pic_order_cnt.c) */
+    struct { uint32_t prev_poc_lsb; int32_t prev_poc_msb; uint32_t prev_frame_num, prev_frame_num_offset; int contains_mmco5; } poc;
+
+    h264_dpb_t dpb;
+    h264_mbctx_t *mbctx;                          /* pic_size_mbs */
+    h264_pic_input_t *pic;                        /* input buffer of the picture being parsed */
+    int last_output_slot;
+} h264_decoder_t;
+
+/* parameter sets / headers (h264_params.c) */
+int h264_parse_sps(br_t *b, h264_sps_t *sps);
+int h264_parse_pps(br_t *b, h264_pps_t *pps);
+int h264_peek_pps_id(br_t b, uint32_t *pps_id);   /* by value: does not consume */
+int h264_parse_slice_header(br_t *b, h264_slice_hdr_t *sh, const h264_sps_t *sps, const h264_pps_t *pps, int nal_type, int nal_ref_idc);
+int32_t h264_decode_poc(h264_decoder_t *d, const h264_slice_hdr_t *sh, int nal_type, int nal_ref_idc);
+
+/* CAVLC (h264_cavlc.c) */
+void h264_cavlc_init(void);
+/* Decode one residual block into out[scan[i]] (out pre-zeroed). nc < 0: chroma DC.
+ * Returns TotalCoeff, or -1 on a malformed block. */
+int h264_cavlc_block(br_t *b, int nc, int max_coeff, int16_t *out, const uint8_t *scan);
+
+/* slice data (h264_slice.c): parse all macroblocks of one slice into d->pic */
+int h264_decode_slice_data(h264_decoder_t *d, br_t *b, const h264_slice_hdr_t *sh);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
