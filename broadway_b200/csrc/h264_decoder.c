@@ -18,6 +18,7 @@
 #include <string.h>
 #include <stdio.h>
 #include "h264b200.h"
+#include "h264b200_batch.h"
 #include "h264_internal.h"
 
 static h264_decoder_t *DEC(storage_t *s) { return s ? (h264_decoder_t *)s->impl : NULL; }
@@ -384,6 +385,31 @@ u8 *h264bsdNextOutputPicture(storage_t *pStorage, u32 *picId, u32 *isIdrPic, u32
     if (isIdrPic) *isIdrPic = o->is_idr;
     if (numErrMbs) *numErrMbs = o->num_err_mbs;
     return p;
+}
+
+/* non-blocking pop + explicit wait (include/h264b200_batch.h) */
+u8 *h264b200NextOutputPictureAsync(storage_t *pStorage, u32 *picId, u32 *isIdrPic, u32 *numErrMbs, u32 *ticket)
+{
+    h264_decoder_t *d = DEC(pStorage);
+    const h264_out_t *o;
+    uint32_t err = 0;
+    if (!d || !d->dpb.allocated || !d->be_inst || !ticket) return NULL;
+    o = h264_dpb_next_output(&d->dpb);
+    if (!o) return NULL;
+    *ticket = (u32)o->slot;
+    if (picId) *picId = o->pic_id;
+    if (isIdrPic) *isIdrPic = o->is_idr;
+    if (numErrMbs) *numErrMbs = o->num_err_mbs;
+    if (d->be->frame_host_async) return d->be->frame_host_async(d->be, d->be_inst, o->slot);
+    return d->be->frame_host(d->be, d->be_inst, o->slot, &err);
+}
+u32 h264b200PictureWait(storage_t *pStorage, u32 ticket)
+{
+    h264_decoder_t *d = DEC(pStorage);
+    uint32_t err = 0;
+    if (!d || !d->be_inst) return 0xffffffffu;
+    if (!d->be->frame_host(d->be, d->be_inst, (int)ticket, &err)) return 0xffffffffu;
+    return err;
 }
 
 void h264bsdShutdown(storage_t *pStorage)

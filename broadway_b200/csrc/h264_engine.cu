@@ -1,0 +1,603 @@
+/* h264_engine.cu — the CUDA reconstruction engine of libh264b200.so (sm_100a).
+ *
+ * This is the device half of what the reference does inside
+ * h264bsdDecodeMacroblock after the QP update (h264bsd_macroblock_layer.c:
+ * 1099-1129: ProcessResidual, h264bsdIntraPrediction, h264bsdInterPrediction)
+ * and in h264bsdFilterPicture (h264bsd_deblocking.c:574-639), re-organised for
+ * a B200: the host parser (h264_slice.c) hands over WHOLE PICTURES as
+ * macroblock records + coefficient slots (include/h264b200_records.h); the
+ * engine copies them to HBM and runs four kernel families over a BATCH of
+ * pictures (one per attached decoder instance) per launch:
+ *     K1 k1_transform   dequant + inverse transforms          (k1_transform.cuh)
+ *     K2 k2_inter       motion compensation + residual add    (k2_inter.cuh)
+ *     K3 k3_intra       intra prediction wavefront            (k3_intra.cuh)
+ *     K4 k4_deblock     deblocking wavefront                  (k4_deblock.cuh)
+ * then copies each finished frame into a pinned host mirror, which is the
+ * pointer h264bsdNextOutputPicture returns (Decoder.c:113-147 layout).
+ *
+ * HBM layout per decoder instance: n_slots frames back to back, each planar
+ * I420, MB aligned (Y 16wm x 16hm, Cb, Cr; pitch = width) — exactly the
+ * reference's output layout, so D2H needs no repacking.  Records and slots of a
+ * picture live in a ring of NBUF input buffers (pinned host + device twin).
+ *
+ * Streams: s_h2d (records/slots in) -> s_comp (K1..K4) -> s_d2h (frames out),
+ * chained with events, so the copy-in of batch n+1 and the copy-out of batch
+ * n-1 overlap the kernels of batch n.  There is no CPU reconstruction path in
+ * this library: if CUDA is unusable h264_default_backend() returns NULL and
+ * h264bsdDecode reports H264BSD_MEMALLOC_ERROR (reason on stderr).
+ */
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <mutex>
+#include <vector>
+#include "h264b200.h"
+#include "h264b200_batch.h"
+#include "h264_internal.h"
+#include "k1_transform.cuh"
+#include "k2_inter.cuh"
+#include "k3_intra.cuh"
+#include "k4_deblock.cuh"
+
+#define NBUF 3                 /* input buffers in flight per instance */
+#define NSCR 4                 /* batch scratch sets in flight per engine */
+#define CTRL_HEAD 16           /* int32 words before the progress counters: [0] K3 ticket, [1] K4 ticket */
+
+#define CUDA_TRY(call, fail) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { \
+    fprintf(stderr, "h264b200: %s -> %s (%s:%d)\n", #call, cudaGetErrorString(e__), __FILE__, __LINE__); fail; } } while (0)
+
+struct Inst;
+
+struct PicBuf {
+    h264_pic_input_t in;           /* in.mbs / in.coef: pinned host memory */
+    h264b200_mb_t *d_mbs;
+    int16_t *d_coef;
+    uint32_t d_coef_cap;           /* slots */
+    cudaEvent_t done;              /* kernels that read this buffer have finished */
+    int state;                     /* 0 free, 1 being filled by the parser, 2 queued, 3 launched */
+    Inst *inst;
+};
+
+struct Inst {
+    h264b200_engine *e;
+    uint32_t wm, hm, n_mbs, n_slots;
+    size_t frame_bytes;
+    uint8_t *d_frames, *h_frames;
+    cudaEvent_t slot_ready[H264_MAX_SLOTS];   /* the host mirror of the slot is complete */
+    uint8_t slot_flags[H264_MAX_SLOTS];       /* bit 0: picture queued, not launched; bit 1: launched, host has not waited yet */
+    PicBuf bufs[NBUF];
+    int next_buf;
+    int batched;
+    int queued;                               /* pictures of this instance waiting in the engine queue */
+};
+
+struct Retained {                  /* one batch kept resident for replay */
+    std::vector<PicJob> jobs;      /* host copy */
+    PicJob *d_jobs;
+    std::vector<void *> owned;     /* device allocations of this batch */
+    Batch batch;
+    size_t ctrl_words;
+    bool k1, k2, k3, k4;
+    uint64_t bytes[4];             /* algorithmic bytes per kernel family */
+    uint32_t n_pics;
+};
+
+struct Scratch {
+    PicJob *h_jobs, *d_jobs;
+    uint32_t cap_jobs;
+    int32_t *d_ctrl;
+    size_t cap_ctrl;               /* words */
+    cudaEvent_t done;
+    bool used;
+};
+
+struct h264b200_engine {
+    int device, sm_count;
+    cudaStream_t s_h2d, s_comp, s_d2h;
+    cudaEvent_t ev_h2d, ev_comp;
+    std::mutex mu;
+    std::vector<PicBuf *> queue;
+    std::vector<Inst *> insts;
+    Scratch scr[NSCR];
+    int next_scr;
+    uint32_t *d_err, *h_err;
+    h264b200_stats_t st;
+    uint32_t flags;                /* H264B200_ENGINE_* */
+    std::vector<Retained *> retained;
+    int32_t *d_replay_ctrl; size_t replay_ctrl_cap;
+    /* per-kernel timing of replays */
+    std::vector<cudaEvent_t> tev;  /* 5 events per replayed batch */
+    std::vector<int> tev_batch;
+    double k_ms[4]; uint64_t k_bytes[4]; uint64_t k_launches[4];
+    h264_backend_t be;
+};
+
+/* ----------------------------------------------------------------- helpers */
+static void set_device(h264b200_engine *e) { cudaSetDevice(e->device); }
+
+static int picbuf_alloc(PicBuf *p, Inst *in, uint32_t coef_cap)
+{
+    memset(p, 0, sizeof *p);
+    p->inst = in;
+    CUDA_TRY(cudaHostAlloc((void **)&p->in.mbs, (size_t)in->n_mbs * sizeof(h264b200_mb_t), cudaHostAllocDefault), return -1);
+    CUDA_TRY(cudaHostAlloc((void **)&p->in.coef, (size_t)coef_cap * 32, cudaHostAllocDefault), return -1);
+    CUDA_TRY(cudaMalloc((void **)&p->d_mbs, (size_t)in->n_mbs * sizeof(h264b200_mb_t)), return -1);
+    CUDA_TRY(cudaMalloc((void **)&p->d_coef, (size_t)coef_cap * 32), return -1);
+    CUDA_TRY(cudaEventCreateWithFlags(&p->done, cudaEventDisableTiming), return -1);
+    p->in.coef_cap = coef_cap; p->d_coef_cap = coef_cap;
+    p->in.priv = p;
+    return 0;
+}
+static void picbuf_free(PicBuf *p)
+{
+    if (p->in.mbs) cudaFreeHost(p->in.mbs);
+    if (p->in.coef) cudaFreeHost(p->in.coef);
+    if (p->d_mbs) cudaFree(p->d_mbs);
+    if (p->d_coef) cudaFree(p->d_coef);
+    if (p->done) cudaEventDestroy(p->done);
+    memset(p, 0, sizeof *p);
+}
+
+/* algorithmic bytes of one picture per kernel family, as SURVEY.md 8(d) defines them */
+static void count_bytes(const h264_pic_input_t *pic, uint32_t n_mbs, uint64_t out[4], uint32_t *coded_blocks)
+{
+    uint64_t inter = 0, intra = 0, blocks = 0, dc = 0, blk_inter = 0, blk_intra = 0, dbk = 0;
+    for (uint32_t i = 0; i < n_mbs; i++) {
+        const h264b200_mb_t *m = &pic->mbs[i];
+        uint32_t nb = (uint32_t)__builtin_popcount(m->resid_mask & 0xffffffu), nd = (uint32_t)__builtin_popcount(m->resid_mask >> 24);
+        if (m->mb_class == H264B200_MB_MISSING) continue;
+        if (m->mb_class == H264B200_MB_INTER) { inter++; blk_inter += nb; } else { intra++; blk_intra += nb; if (m->mb_class == H264B200_MB_IPCM) blk_intra += 12; }
+        blocks += nb; dc += nd;
+        if (m->dbk_flags) dbk++;
+    }
+    out[0] = blocks * 64 + dc * 64;                         /* K1: 32 B in + 32 B out per coded block / DC block */
+    out[1] = inter * (384 + 384 + 128) + blk_inter * 32;    /* K2 */
+    out[2] = intra * (384 + 64 + 128) + blk_intra * 32;     /* K3 */
+    out[3] = dbk * (384 + 384 + 128);                       /* K4 */
+    if (coded_blocks) *coded_blocks = (uint32_t)blocks;
+}
+
+/* ------------------------------------------------------------ kernel launch */
+struct BatchPlan { bool k1, k2, k3, k4; uint32_t total_mbs; int max_hm; int n_jobs; };
+
+static void launch_kernels(h264b200_engine *e, const Batch &b, const BatchPlan &pl, cudaEvent_t *tev)
+{
+    cudaStream_t s = e->s_comp;
+    if (tev) cudaEventRecord(tev[0], s);
+    if (pl.k1) { uint32_t blocks = (pl.total_mbs * 32 + 255) / 256; k1_transform<<<blocks, 256, 0, s>>>(b); e->st.kernel_launches++; }
+    if (tev) cudaEventRecord(tev[1], s);
+    if (pl.k2) { k2_inter<<<pl.total_mbs, K2_THREADS, 0, s>>>(b); e->st.kernel_launches++; }
+    if (tev) cudaEventRecord(tev[2], s);
+    uint32_t n_tasks = (uint32_t)pl.n_jobs * (uint32_t)pl.max_hm;
+    if (pl.k3) {
+        uint32_t blocks = (n_tasks + K3_WARPS - 1) / K3_WARPS, cap = (uint32_t)e->sm_count * 16;
+        k3_intra<<<blocks < cap ? blocks : cap, K3_WARPS * 32, 0, s>>>(b); e->st.kernel_launches++;
+    }
+    if (tev) cudaEventRecord(tev[3], s);
+    if (pl.k4) {
+        uint32_t blocks = (n_tasks + K4_WARPS - 1) / K4_WARPS, cap = (uint32_t)e->sm_count * 16;
+        k4_deblock<<<blocks < cap ? blocks : cap, K4_WARPS * 32, 0, s>>>(b); e->st.kernel_launches++;
+    }
+    if (tev) cudaEventRecord(tev[4], s);
+}
+
+/* ------------------------------------------------------------------ submit */
+/* engine mutex held.  Launch every queued picture as one batch. */
+static uint32_t submit_locked(h264b200_engine *e)
+{
+    uint32_t n = (uint32_t)e->queue.size();
+    if (!n) return 0;
+    set_device(e);
+    const bool retain = (e->flags & H264B200_ENGINE_RETAIN) != 0;
+    Retained *ret = retain ? new Retained() : nullptr;
+    Scratch &sc = e->scr[e->next_scr];
+    e->next_scr = (e->next_scr + 1) % NSCR;
+    if (sc.used) cudaEventSynchronize(sc.done);
+    size_t ctrl_words = CTRL_HEAD;
+    for (PicBuf *p : e->queue) ctrl_words += 2 * (size_t)p->inst->hm;
+    if (sc.cap_jobs < n) {
+        if (sc.h_jobs) cudaFreeHost(sc.h_jobs);
+        if (sc.d_jobs) cudaFree(sc.d_jobs);
+        sc.cap_jobs = n + 16;
+        CUDA_TRY(cudaHostAlloc((void **)&sc.h_jobs, sc.cap_jobs * sizeof(PicJob), cudaHostAllocDefault), return 0);
+        CUDA_TRY(cudaMalloc((void **)&sc.d_jobs, sc.cap_jobs * sizeof(PicJob)), return 0);
+    }
+    if (sc.cap_ctrl < ctrl_words) {
+        if (sc.d_ctrl) cudaFree(sc.d_ctrl);
+        sc.cap_ctrl = ctrl_words + 1024;
+        CUDA_TRY(cudaMalloc((void **)&sc.d_ctrl, sc.cap_ctrl * sizeof(int32_t)), return 0);
+    }
+    PicJob *d_jobs = sc.d_jobs; int32_t *d_ctrl = sc.d_ctrl;
+    if (retain) {                  /* a retained batch owns its job table and control area */
+        CUDA_TRY(cudaMalloc((void **)&ret->d_jobs, n * sizeof(PicJob)), return 0);
+        ret->owned.push_back(ret->d_jobs);
+        d_jobs = ret->d_jobs;
+        CUDA_TRY(cudaMalloc((void **)&d_ctrl, ctrl_words * sizeof(int32_t)), return 0);
+        ret->owned.push_back(d_ctrl);
+    }
+
+    BatchPlan pl; memset(&pl, 0, sizeof pl);
+    uint32_t mb_base = 0; size_t prog_off = CTRL_HEAD;
+    uint64_t bytes[4] = {0, 0, 0, 0};
+    for (uint32_t i = 0; i < n; i++) {
+        PicBuf *p = e->queue[i]; Inst *in = p->inst; h264_pic_input_t *pic = &p->in;
+        h264b200_mb_t *d_mbs = p->d_mbs; int16_t *d_coef_in = p->d_coef, *d_coef = p->d_coef;
+        size_t coef_bytes = (size_t)pic->coef_used * 32;
+        if (retain) {
+            void *a = nullptr, *b = nullptr, *c = nullptr;
+            CUDA_TRY(cudaMalloc(&a, (size_t)in->n_mbs * sizeof(h264b200_mb_t)), return 0);
+            CUDA_TRY(cudaMalloc(&b, coef_bytes + 32), return 0);
+            CUDA_TRY(cudaMalloc(&c, coef_bytes + 32), return 0);
+            ret->owned.push_back(a); ret->owned.push_back(b); ret->owned.push_back(c);
+            d_mbs = (h264b200_mb_t *)a; d_coef_in = (int16_t *)b; d_coef = (int16_t *)c;
+        } else if (p->d_coef_cap < pic->coef_used) {          /* the host side grew: follow */
+            /* the previous device buffer may still be read by an earlier batch of this ring slot: it is not
+             * (pic_begin waited for `done`), so it can be replaced */
+            cudaFree(p->d_coef);
+            p->d_coef_cap = pic->coef_cap;
+            CUDA_TRY(cudaMalloc((void **)&p->d_coef, (size_t)p->d_coef_cap * 32), return 0);
+            d_coef_in = d_coef = p->d_coef;
+        }
+        CUDA_TRY(cudaMemcpyAsync(d_mbs, pic->mbs, (size_t)in->n_mbs * sizeof(h264b200_mb_t), cudaMemcpyHostToDevice, e->s_h2d), return 0);
+        if (coef_bytes) CUDA_TRY(cudaMemcpyAsync(d_coef_in, pic->coef, coef_bytes, cudaMemcpyHostToDevice, e->s_h2d), return 0);
+        e->st.h2d_bytes += (size_t)in->n_mbs * sizeof(h264b200_mb_t) + coef_bytes;
+
+        PicJob &j = sc.h_jobs[i];
+        j.mbs = d_mbs; j.coef_in = d_coef_in; j.coef = d_coef;
+        j.cur = in->d_frames + (size_t)pic->cur_slot * in->frame_bytes;
+        j.frames = in->d_frames; j.frame_bytes = (uint32_t)in->frame_bytes;
+        j.wm = (int32_t)in->wm; j.hm = (int32_t)in->hm;
+        j.progress = d_ctrl + prog_off; prog_off += 2 * (size_t)in->hm;
+        j.n_intra = pic->n_intra; j.n_inter = pic->n_inter; j.any_deblock = pic->any_deblock;
+        j.mb_base = mb_base; mb_base += in->n_mbs;
+        if (pic->coef_used) pl.k1 = true;
+        if (pic->n_inter) pl.k2 = true;
+        if (pic->n_intra) pl.k3 = true;
+        if (pic->any_deblock) pl.k4 = true;
+        if ((int)in->hm > pl.max_hm) pl.max_hm = (int)in->hm;
+        /* the frame being written may still be on its way to the host from an earlier batch */
+        if (in->slot_flags[pic->cur_slot] & 2) cudaStreamWaitEvent(e->s_comp, in->slot_ready[pic->cur_slot], 0);
+        if (retain) { uint64_t bb[4]; count_bytes(pic, in->n_mbs, bb, nullptr); for (int k = 0; k < 4; k++) bytes[k] += bb[k]; }
+    }
+    pl.total_mbs = mb_base; pl.n_jobs = (int)n;
+
+    Batch b;
+    b.jobs = d_jobs; b.n_jobs = (int32_t)n; b.max_hm = pl.max_hm; b.total_mbs = mb_base;
+    b.tickets = (uint32_t *)d_ctrl; b.error_flags = e->d_err;
+
+    cudaEventRecord(e->ev_h2d, e->s_h2d);
+    cudaStreamWaitEvent(e->s_comp, e->ev_h2d, 0);
+    cudaMemcpyAsync(d_jobs, sc.h_jobs, n * sizeof(PicJob), cudaMemcpyHostToDevice, e->s_comp);
+    cudaMemsetAsync(d_ctrl, 0, ctrl_words * sizeof(int32_t), e->s_comp);
+    launch_kernels(e, b, pl, nullptr);
+    cudaEventRecord(sc.done, e->s_comp); sc.used = true;
+    cudaEventRecord(e->ev_comp, e->s_comp);
+    cudaStreamWaitEvent(e->s_d2h, e->ev_comp, 0);
+    for (uint32_t i = 0; i < n; i++) {
+        PicBuf *p = e->queue[i]; Inst *in = p->inst; int slot = p->in.cur_slot;
+        cudaEventRecord(p->done, e->s_comp);
+        p->state = 3;
+        if (!(e->flags & H264B200_ENGINE_NO_D2H)) {
+            cudaMemcpyAsync(in->h_frames + (size_t)slot * in->frame_bytes, in->d_frames + (size_t)slot * in->frame_bytes,
+                            in->frame_bytes, cudaMemcpyDeviceToHost, e->s_d2h);
+            e->st.d2h_bytes += in->frame_bytes;
+        }
+        cudaEventRecord(in->slot_ready[slot], e->s_d2h);
+        in->slot_flags[slot] = 2;
+        in->queued--;
+    }
+    cudaMemcpyAsync(e->h_err, e->d_err, sizeof(uint32_t), cudaMemcpyDeviceToHost, e->s_d2h);
+    e->st.pictures += n; e->st.batches++;
+    if (retain) {
+        ret->jobs.assign(sc.h_jobs, sc.h_jobs + n);
+        ret->batch = b; ret->ctrl_words = ctrl_words;
+        ret->k1 = pl.k1; ret->k2 = pl.k2; ret->k3 = pl.k3; ret->k4 = pl.k4;
+        for (int k = 0; k < 4; k++) ret->bytes[k] = bytes[k];
+        ret->n_pics = n;
+        e->retained.push_back(ret);
+    }
+    e->queue.clear();
+    cudaError_t le = cudaGetLastError();
+    if (le != cudaSuccess) fprintf(stderr, "h264b200: kernel launch failed: %s\n", cudaGetErrorString(le));
+    return n;
+}
+
+/* ------------------------------------------------------- backend callbacks */
+static void *be_inst_create(h264_backend_t *be, uint32_t wm, uint32_t hm, uint32_t n_slots)
+{
+    h264b200_engine *e = (h264b200_engine *)be->ctx;
+    if (n_slots > H264_MAX_SLOTS) return NULL;
+    set_device(e);
+    Inst *in = (Inst *)calloc(1, sizeof *in);
+    if (!in) return NULL;
+    in->e = e; in->wm = wm; in->hm = hm; in->n_mbs = wm * hm; in->n_slots = n_slots;
+    in->frame_bytes = (size_t)in->n_mbs * 384;
+    in->batched = (e->flags & H264B200_ENGINE_BATCHED) != 0;
+    CUDA_TRY(cudaMalloc((void **)&in->d_frames, in->frame_bytes * n_slots), { free(in); return NULL; });
+    CUDA_TRY(cudaMemset(in->d_frames, 0, in->frame_bytes * n_slots), { free(in); return NULL; });
+    CUDA_TRY(cudaHostAlloc((void **)&in->h_frames, in->frame_bytes * n_slots, cudaHostAllocDefault), { free(in); return NULL; });
+    memset(in->h_frames, 0, in->frame_bytes * n_slots);
+    for (uint32_t i = 0; i < n_slots; i++) CUDA_TRY(cudaEventCreateWithFlags(&in->slot_ready[i], cudaEventDisableTiming), { free(in); return NULL; });
+    for (int i = 0; i < NBUF; i++) if (picbuf_alloc(&in->bufs[i], in, in->n_mbs * 10 + 64)) return NULL;
+    std::lock_guard<std::mutex> lk(e->mu);
+    e->insts.push_back(in);
+    return in;
+}
+
+static void be_inst_destroy(h264_backend_t *be, void *inst)
+{
+    h264b200_engine *e = (h264b200_engine *)be->ctx; Inst *in = (Inst *)inst;
+    {
+        std::lock_guard<std::mutex> lk(e->mu);
+        if (in->queued) submit_locked(e);
+        for (size_t i = 0; i < e->insts.size(); i++) if (e->insts[i] == in) { e->insts.erase(e->insts.begin() + i); break; }
+    }
+    set_device(e);
+    cudaStreamSynchronize(e->s_comp); cudaStreamSynchronize(e->s_d2h);
+    for (int i = 0; i < NBUF; i++) picbuf_free(&in->bufs[i]);
+    for (uint32_t i = 0; i < in->n_slots; i++) cudaEventDestroy(in->slot_ready[i]);
+    cudaFree(in->d_frames); cudaFreeHost(in->h_frames);
+    free(in);
+}
+
+static h264_pic_input_t *be_pic_begin(h264_backend_t *be, void *inst)
+{
+    h264b200_engine *e = (h264b200_engine *)be->ctx; Inst *in = (Inst *)inst;
+    PicBuf *p = &in->bufs[in->next_buf];
+    in->next_buf = (in->next_buf + 1) % NBUF;
+    if (p->state == 2) { std::lock_guard<std::mutex> lk(e->mu); submit_locked(e); }
+    if (p->state == 3) { set_device(e); cudaEventSynchronize(p->done); }
+    p->state = 1;
+    return &p->in;
+}
+
+static int be_coef_grow(h264_backend_t *be, void *inst, h264_pic_input_t *pic, uint32_t min_slots)
+{
+    h264b200_engine *e = (h264b200_engine *)be->ctx; (void)inst;
+    uint32_t cap = pic->coef_cap * 2 > min_slots ? pic->coef_cap * 2 : min_slots;
+    int16_t *n = NULL;
+    set_device(e);
+    CUDA_TRY(cudaHostAlloc((void **)&n, (size_t)cap * 32, cudaHostAllocDefault), return -1);
+    memcpy(n, pic->coef, (size_t)pic->coef_used * 32);
+    cudaFreeHost(pic->coef);
+    pic->coef = n; pic->coef_cap = cap;
+    return 0;
+}
+
+static int be_pic_submit(h264_backend_t *be, void *inst, h264_pic_input_t *pic)
+{
+    h264b200_engine *e = (h264b200_engine *)be->ctx; Inst *in = (Inst *)inst;
+    PicBuf *p = (PicBuf *)pic->priv;
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (in->queued) submit_locked(e);          /* consecutive pictures of one stream depend on each other */
+    p->state = 2;
+    in->slot_flags[pic->cur_slot] |= 1;
+    in->queued++;
+    e->queue.push_back(p);
+    if (!in->batched) submit_locked(e);
+    return 0;
+}
+
+static uint8_t *be_frame_host(h264_backend_t *be, void *inst, int slot, uint32_t *error_flags)
+{
+    h264b200_engine *e = (h264b200_engine *)be->ctx; Inst *in = (Inst *)inst;
+    if (slot < 0 || slot >= (int)in->n_slots) return NULL;
+    if (in->slot_flags[slot] & 1) { std::lock_guard<std::mutex> lk(e->mu); submit_locked(e); }
+    if (in->slot_flags[slot] & 2) {
+        set_device(e);
+        cudaError_t er = cudaEventSynchronize(in->slot_ready[slot]);
+        if (er != cudaSuccess) { fprintf(stderr, "h264b200: reconstruction failed: %s\n", cudaGetErrorString(er)); return NULL; }
+        in->slot_flags[slot] &= (uint8_t)~2;
+    }
+    if (error_flags) *error_flags = *e->h_err;
+    return in->h_frames + (size_t)slot * in->frame_bytes;
+}
+
+static uint8_t *be_frame_host_async(h264_backend_t *be, void *inst, int slot)
+{
+    Inst *in = (Inst *)inst; (void)be;
+    if (slot < 0 || slot >= (int)in->n_slots) return NULL;
+    return in->h_frames + (size_t)slot * in->frame_bytes;
+}
+
+static void be_destroy(h264_backend_t *be) { (void)be; }
+
+/* ------------------------------------------------------------- engine API */
+extern "C" int h264b200Probe(char *msg, size_t cap)
+{
+    int n = 0;
+    cudaError_t er = cudaGetDeviceCount(&n);
+    if (er != cudaSuccess || n == 0) {
+        if (msg && cap) snprintf(msg, cap, "no usable CUDA device: %s", er != cudaSuccess ? cudaGetErrorString(er) : "device count is 0");
+        return -1;
+    }
+    cudaDeviceProp p;
+    cudaGetDeviceProperties(&p, 0);
+    if (msg && cap) snprintf(msg, cap, "%d device(s); device 0: %s sm_%d%d, %d SMs", n, p.name, p.major, p.minor, p.multiProcessorCount);
+    if (p.major != 10) { if (msg && cap) snprintf(msg, cap, "device 0 is sm_%d%d; this library is built for sm_100a only", p.major, p.minor); return -2; }
+    return 0;
+}
+
+extern "C" h264b200_engine_t *h264b200EngineCreateEx(int device, uint32_t flags)
+{
+    char msg[256];
+    if (h264b200Probe(msg, sizeof msg)) { fprintf(stderr, "h264b200: %s\n", msg); return NULL; }
+    if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
+    h264b200_engine *e = new h264b200_engine();
+    e->device = device; e->flags = flags; e->next_scr = 0;
+    memset(&e->st, 0, sizeof e->st); memset(e->scr, 0, sizeof e->scr);
+    memset(e->k_ms, 0, sizeof e->k_ms); memset(e->k_bytes, 0, sizeof e->k_bytes); memset(e->k_launches, 0, sizeof e->k_launches);
+    e->d_replay_ctrl = NULL; e->replay_ctrl_cap = 0;
+    CUDA_TRY(cudaSetDevice(device), { delete e; return NULL; });
+    cudaDeviceProp p;
+    CUDA_TRY(cudaGetDeviceProperties(&p, device), { delete e; return NULL; });
+    e->sm_count = p.multiProcessorCount;
+    CUDA_TRY(cudaStreamCreateWithFlags(&e->s_h2d, cudaStreamNonBlocking), { delete e; return NULL; });
+    CUDA_TRY(cudaStreamCreateWithFlags(&e->s_comp, cudaStreamNonBlocking), { delete e; return NULL; });
+    CUDA_TRY(cudaStreamCreateWithFlags(&e->s_d2h, cudaStreamNonBlocking), { delete e; return NULL; });
+    CUDA_TRY(cudaEventCreateWithFlags(&e->ev_h2d, cudaEventDisableTiming), { delete e; return NULL; });
+    CUDA_TRY(cudaEventCreateWithFlags(&e->ev_comp, cudaEventDisableTiming), { delete e; return NULL; });
+    for (int i = 0; i < NSCR; i++) CUDA_TRY(cudaEventCreateWithFlags(&e->scr[i].done, cudaEventDisableTiming), { delete e; return NULL; });
+    CUDA_TRY(cudaMalloc((void **)&e->d_err, 64), { delete e; return NULL; });
+    CUDA_TRY(cudaMemset(e->d_err, 0, 64), { delete e; return NULL; });
+    CUDA_TRY(cudaHostAlloc((void **)&e->h_err, 64, cudaHostAllocDefault), { delete e; return NULL; });
+    *e->h_err = 0;
+    e->be.inst_create = be_inst_create; e->be.inst_destroy = be_inst_destroy; e->be.pic_begin = be_pic_begin;
+    e->be.coef_grow = be_coef_grow; e->be.pic_submit = be_pic_submit; e->be.frame_host = be_frame_host;
+    e->be.frame_host_async = be_frame_host_async;
+    e->be.destroy = be_destroy; e->be.ctx = e;
+    return e;
+}
+extern "C" h264b200_engine_t *h264b200EngineCreate(int device) { return h264b200EngineCreateEx(device, H264B200_ENGINE_BATCHED); }
+
+static void free_retained(h264b200_engine *e)
+{
+    for (Retained *r : e->retained) { for (void *p : r->owned) cudaFree(p); delete r; }
+    e->retained.clear();
+}
+
+extern "C" void h264b200EngineDestroy(h264b200_engine_t *e)
+{
+    if (!e) return;
+    set_device(e);
+    cudaStreamSynchronize(e->s_h2d); cudaStreamSynchronize(e->s_comp); cudaStreamSynchronize(e->s_d2h);
+    free_retained(e);
+    for (cudaEvent_t ev : e->tev) cudaEventDestroy(ev);
+    for (int i = 0; i < NSCR; i++) {
+        Scratch &s = e->scr[i];
+        if (s.h_jobs) cudaFreeHost(s.h_jobs);
+        if (s.d_jobs) cudaFree(s.d_jobs);
+        if (s.d_ctrl) cudaFree(s.d_ctrl);
+        cudaEventDestroy(s.done);
+    }
+    if (e->d_replay_ctrl) cudaFree(e->d_replay_ctrl);
+    cudaFree(e->d_err); cudaFreeHost(e->h_err);
+    cudaEventDestroy(e->ev_h2d); cudaEventDestroy(e->ev_comp);
+    cudaStreamDestroy(e->s_h2d); cudaStreamDestroy(e->s_comp); cudaStreamDestroy(e->s_d2h);
+    delete e;
+}
+
+extern "C" u32 h264_decoder_create(storage_t *pStorage, u32 noOutputReordering, h264_backend_t *be);
+extern "C" u32 h264b200InitOnEngine(storage_t *pStorage, u32 noOutputReordering, h264b200_engine_t *e)
+{
+    if (!e) return HANTRO_NOK;
+    return h264_decoder_create(pStorage, noOutputReordering, &e->be);
+}
+
+extern "C" u32 h264b200EngineSubmit(h264b200_engine_t *e)
+{
+    if (!e) return 0;
+    std::lock_guard<std::mutex> lk(e->mu);
+    return submit_locked(e);
+}
+
+extern "C" void h264b200EngineSync(h264b200_engine_t *e)
+{
+    if (!e) return;
+    set_device(e);
+    cudaError_t a = cudaStreamSynchronize(e->s_h2d), b = cudaStreamSynchronize(e->s_comp), c = cudaStreamSynchronize(e->s_d2h);
+    if (a != cudaSuccess || b != cudaSuccess || c != cudaSuccess)
+        fprintf(stderr, "h264b200: engine sync failed: %s\n", cudaGetErrorString(a != cudaSuccess ? a : b != cudaSuccess ? b : c));
+}
+
+extern "C" void h264b200EngineStats(h264b200_engine_t *e, h264b200_stats_t *out) { if (e && out) { std::lock_guard<std::mutex> lk(e->mu); *out = e->st; } }
+extern "C" u32 h264b200EngineErrorFlags(h264b200_engine_t *e) { return e ? *e->h_err : 0; }
+extern "C" void h264b200EngineSetFlags(h264b200_engine_t *e, uint32_t flags) { if (e) { std::lock_guard<std::mutex> lk(e->mu); e->flags = flags; } }
+
+/* -------------------------------------------------------- resident replay */
+extern "C" void h264b200EngineDropRetained(h264b200_engine_t *e)
+{
+    if (!e) return;
+    h264b200EngineSync(e);
+    std::lock_guard<std::mutex> lk(e->mu);
+    free_retained(e);
+}
+
+extern "C" u32 h264b200EngineReplay(h264b200_engine_t *e, u32 reps, int time_kernels)
+{
+    if (!e) return 0;
+    std::lock_guard<std::mutex> lk(e->mu);
+    set_device(e);
+    size_t need = 0;
+    for (Retained *r : e->retained) if (r->ctrl_words > need) need = r->ctrl_words;
+    u32 pics = 0;
+    for (u32 rep = 0; rep < reps; rep++) for (size_t bi = 0; bi < e->retained.size(); bi++) {
+        Retained *r = e->retained[bi];
+        BatchPlan pl; pl.k1 = r->k1; pl.k2 = r->k2; pl.k3 = r->k3; pl.k4 = r->k4;
+        pl.total_mbs = r->batch.total_mbs; pl.max_hm = r->batch.max_hm; pl.n_jobs = r->batch.n_jobs;
+        cudaEvent_t *tev = nullptr;
+        if (time_kernels) {
+            size_t base = e->tev.size();
+            for (int k = 0; k < 5; k++) { cudaEvent_t ev; cudaEventCreate(&ev); e->tev.push_back(ev); }
+            e->tev_batch.push_back((int)bi);
+            tev = &e->tev[base];
+        }
+        /* the batch's own control area (tickets + wavefront progress) is part of its retained allocation
+         * (r->batch.tickets points at it); batches are serialised on s_comp */
+        cudaMemsetAsync(r->batch.tickets, 0, r->ctrl_words * sizeof(int32_t), e->s_comp);
+        launch_kernels(e, r->batch, pl, tev);
+        pics += r->n_pics;
+    }
+    e->st.pictures += pics; e->st.batches += (uint64_t)reps * e->retained.size();
+    return pics;
+}
+
+/* Fold the event pairs of timed replays into the per-kernel totals (after a sync). */
+extern "C" void h264b200EngineKernelTimes(h264b200_engine_t *e, h264b200_kernel_times_t *out, int reset)
+{
+    if (!e || !out) return;
+    h264b200EngineSync(e);
+    std::lock_guard<std::mutex> lk(e->mu);
+    for (size_t i = 0; i < e->tev_batch.size(); i++) {
+        Retained *r = e->retained[(size_t)e->tev_batch[i]];
+        const bool on[4] = {r->k1, r->k2, r->k3, r->k4};
+        for (int k = 0; k < 4; k++) if (on[k]) {
+            float ms = 0; cudaEventElapsedTime(&ms, e->tev[5 * i + k], e->tev[5 * i + k + 1]);
+            e->k_ms[k] += ms; e->k_bytes[k] += r->bytes[k]; e->k_launches[k]++;
+        }
+    }
+    for (cudaEvent_t ev : e->tev) cudaEventDestroy(ev);
+    e->tev.clear(); e->tev_batch.clear();
+    for (int k = 0; k < 4; k++) { out->ms[k] = e->k_ms[k]; out->bytes[k] = e->k_bytes[k]; out->launches[k] = e->k_launches[k]; }
+    if (reset) { memset(e->k_ms, 0, sizeof e->k_ms); memset(e->k_bytes, 0, sizeof e->k_bytes); memset(e->k_launches, 0, sizeof e->k_launches); }
+}
+
+/* Compare every frame slot on the device with its pinned host mirror (which holds what the
+ * normal decode delivered): returns the number of slots that differ.  Used after a replay. */
+extern "C" u32 h264b200EngineCheckResident(h264b200_engine_t *e)
+{
+    if (!e) return 0xffffffffu;
+    h264b200EngineSync(e);
+    std::lock_guard<std::mutex> lk(e->mu);
+    set_device(e);
+    u32 bad = 0;
+    for (Inst *in : e->insts) {
+        std::vector<uint8_t> tmp(in->frame_bytes);
+        for (uint32_t s = 0; s < in->n_slots; s++) {
+            if (cudaMemcpy(tmp.data(), in->d_frames + (size_t)s * in->frame_bytes, in->frame_bytes, cudaMemcpyDeviceToHost) != cudaSuccess) return 0xffffffffu;
+            if (memcmp(tmp.data(), in->h_frames + (size_t)s * in->frame_bytes, in->frame_bytes)) bad++;
+        }
+    }
+    return bad;
+}
+
+/* ------------------------------------------------------- default backend */
+static h264b200_engine *g_default_engine;
+static std::mutex g_default_mu;
+
+extern "C" h264_backend_t *h264_default_backend(void)
+{
+    std::lock_guard<std::mutex> lk(g_default_mu);
+    if (!g_default_engine) {
+        int dev = -1;
+        const char *s = getenv("H264B200_DEVICE");
+        if (s && *s) dev = atoi(s);
+        g_default_engine = h264b200EngineCreateEx(dev, 0);
+        if (!g_default_engine) {
+            fprintf(stderr, "h264b200: no CUDA engine: this library has no CPU reconstruction path\n");
+            return NULL;
+        }
+    }
+    return &g_default_engine->be;
+}

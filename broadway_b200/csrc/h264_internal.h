@@ -141,6 +141,8 @@ struct h264_backend {
     uint8_t *(*frame_host)(h264_backend_t *be, void *inst, int slot, uint32_t *error_flags);
     void  (*destroy)(h264_backend_t *be);
     void  *ctx;
+    /* optional: address frame_host will return for `slot`, without launching or waiting */
+    uint8_t *(*frame_host_async)(h264_backend_t *be, void *inst, int slot);
 };
 
 /* implemented by whichever backend is linked: the CUDA engine in libh264b200.so */

@@ -1,0 +1,267 @@
+/* h264_runner.c — many independent streams (or IDR-bounded GOP segments) through
+ * one engine: h264b200DecodeStreams and h264b200SplitGops
+ * (include/h264b200_batch.h).
+ *
+ * The reference's closest relative is TestBenchMultipleInstance.c:60-350, which
+ * steps N decoder instances round-robin in one thread.  Here the same
+ * round-robin is the unit of GPU batching: in every ROUND each live stream's
+ * serial CAVLC parse produces one picture (worker threads, one stream at a time
+ * each), the last thread to finish the round launches all of those pictures as
+ * one batch, and the workers go straight on to parse the next round while the
+ * GPU reconstructs — output of round r is waited for only after round r+1 has
+ * been parsed (h264b200NextOutputPictureAsync / h264b200PictureWait).
+ * Streams are independent (no mutable globals in the decoder core), and an IDR
+ * picture empties the DPB (h264bsd_dpb.c:675-708), which is what makes
+ * h264b200SplitGops' segments decodable on their own — on another instance,
+ * thread or GPU.
+ */
+#define _GNU_SOURCE
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+#include <unistd.h>
+#include "h264b200.h"
+#include "h264b200_batch.h"
+
+static double now_s(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return (double)t.tv_sec + 1e-9 * (double)t.tv_nsec; }
+
+#define MAX_PENDING 20
+
+typedef struct { u8 *ptr; u32 ticket, pic_id, err; } pending_t;
+
+typedef struct {
+    storage_t st;
+    uint8_t *buf; size_t len, pos;
+    u32 pic_id, out_index;
+    int inited, finished, failed, flushed;
+    pending_t cur[MAX_PENDING], prev[MAX_PENDING];
+    int n_cur, n_prev;
+    u32 width, height;
+} rstream_t;
+
+typedef struct runner runner_t;
+typedef struct {
+    runner_t *r; uint32_t tid;
+    pthread_t th;
+    uint64_t pictures, bytes_out; uint32_t err_mbs;
+    double parse_s, wait_s;
+} worker_t;
+
+struct runner {
+    h264b200_engine_t *e;
+    rstream_t *s; uint32_t n_streams, n_threads;
+    h264b200_picture_cb cb; void *user;
+    pthread_mutex_t mu; pthread_cond_t cv;
+    uint32_t arrived, generation; uint64_t round_sum, last_sum;
+    uint32_t rounds;
+};
+
+/* Barrier; the last arriver launches the batch.  Returns the number of pictures all threads
+ * produced in this round. */
+static uint64_t round_barrier(runner_t *r, uint64_t produced)
+{
+    uint64_t sum;
+    pthread_mutex_lock(&r->mu);
+    r->round_sum += produced;
+    if (++r->arrived == r->n_threads) {
+        h264b200EngineSubmit(r->e);
+        r->last_sum = r->round_sum; r->round_sum = 0; r->arrived = 0; r->generation++; r->rounds++;
+        pthread_cond_broadcast(&r->cv);
+    } else {
+        uint32_t g = r->generation;
+        while (g == r->generation) pthread_cond_wait(&r->cv, &r->mu);
+    }
+    sum = r->last_sum;
+    pthread_mutex_unlock(&r->mu);
+    return sum;
+}
+
+static void pop_outputs(rstream_t *s)
+{
+    u32 id, idr, err, ticket; u8 *p;
+    while (s->n_cur < MAX_PENDING && (p = h264b200NextOutputPictureAsync(&s->st, &id, &idr, &err, &ticket)) != NULL) {
+        pending_t *q = &s->cur[s->n_cur++];
+        q->ptr = p; q->ticket = ticket; q->pic_id = id; q->err = err;
+    }
+}
+
+/* advance one stream by one picture; 1 if a picture was produced */
+static int step_stream(rstream_t *s)
+{
+    while (s->pos < s->len) {
+        u32 nread = 0, rest = (u32)(s->len - s->pos > 0x7fffffffu ? 0x7fffffffu : s->len - s->pos);
+        u32 rc = h264bsdDecode(&s->st, s->buf + s->pos, rest, s->pic_id, &nread);
+        s->pos += nread;
+        if (rc == H264BSD_PIC_RDY) { s->pic_id++; pop_outputs(s); return 1; }
+        if (rc == H264BSD_HDRS_RDY) { pop_outputs(s); continue; }      /* a flushed DPB may hold pictures (H264SwDecApi.c:417-424) */
+        if (rc == H264BSD_MEMALLOC_ERROR) { s->failed = 1; break; }
+        if (nread == 0 && rc != H264BSD_RDY) { s->failed = 1; break; } /* no progress on an error: give up on this stream */
+    }
+    if (!s->flushed) { s->flushed = 1; h264bsdFlushBuffer(&s->st); pop_outputs(s); }
+    s->finished = 1;
+    return 0;
+}
+
+static void consume_prev(worker_t *w, rstream_t *s, uint32_t stream_index)
+{
+    runner_t *r = w->r;
+    int i;
+    for (i = 0; i < s->n_prev; i++) {
+        pending_t *q = &s->prev[i];
+        double t0 = now_s();
+        u32 rc = h264b200PictureWait(&s->st, q->ticket);
+        w->wait_s += now_s() - t0;
+        if (rc == 0xffffffffu) { s->failed = 1; continue; }
+        if (!s->width) { s->width = 16 * h264bsdPicWidth(&s->st); s->height = 16 * h264bsdPicHeight(&s->st); }
+        if (r->cb) r->cb(r->user, stream_index, s->out_index, q->ptr, s->width, s->height, q->pic_id, q->err);
+        s->out_index++;
+        w->pictures++; w->bytes_out += (uint64_t)s->width * s->height * 3 / 2; w->err_mbs += q->err;
+    }
+    s->n_prev = 0;
+}
+
+static void *worker_main(void *arg)
+{
+    worker_t *w = (worker_t *)arg; runner_t *r = w->r;
+    uint32_t i;
+    for (;;) {
+        uint64_t produced = 0;
+        for (i = w->tid; i < r->n_streams; i += r->n_threads) {
+            rstream_t *s = &r->s[i];
+            if (!s->finished && !s->failed) {
+                double t0 = now_s();
+                produced += (uint64_t)step_stream(s);
+                w->parse_s += now_s() - t0;
+            }
+        }
+        /* pictures popped in the PREVIOUS round were launched one barrier ago: the GPU had this whole
+         * parse to finish them */
+        for (i = w->tid; i < r->n_streams; i += r->n_threads) consume_prev(w, &r->s[i], i);
+        if (round_barrier(r, produced) == 0) break;
+        for (i = w->tid; i < r->n_streams; i += r->n_threads) {
+            rstream_t *s = &r->s[i];
+            memcpy(s->prev, s->cur, (size_t)s->n_cur * sizeof(pending_t)); s->n_prev = s->n_cur; s->n_cur = 0;
+        }
+    }
+    for (i = w->tid; i < r->n_streams; i += r->n_threads) {
+        rstream_t *s = &r->s[i];
+        memcpy(s->prev, s->cur, (size_t)s->n_cur * sizeof(pending_t)); s->n_prev = s->n_cur; s->n_cur = 0;
+        consume_prev(w, s, i);
+    }
+    return NULL;
+}
+
+int h264b200DecodeStreams(h264b200_engine_t *e, const h264b200_stream_t *streams, uint32_t n_streams,
+                          uint32_t n_threads, h264b200_picture_cb cb, void *user, h264b200_run_stats_t *out)
+{
+    runner_t r; worker_t *w; uint32_t i; double t0 = now_s(); int rc = 0;
+    if (!e || !streams || !n_streams) return -1;
+    memset(&r, 0, sizeof r);
+    if (!n_threads) { long n = sysconf(_SC_NPROCESSORS_ONLN); n_threads = n > 0 ? (uint32_t)n : 1; }
+    if (n_threads > n_streams) n_threads = n_streams;
+    r.e = e; r.n_streams = n_streams; r.n_threads = n_threads; r.cb = cb; r.user = user;
+    r.s = (rstream_t *)calloc(n_streams, sizeof(rstream_t));
+    w = (worker_t *)calloc(n_threads, sizeof(worker_t));
+    if (!r.s || !w) { free(r.s); free(w); return -1; }
+    pthread_mutex_init(&r.mu, NULL); pthread_cond_init(&r.cv, NULL);
+    for (i = 0; i < n_streams; i++) {
+        rstream_t *s = &r.s[i];
+        s->len = streams[i].len;
+        s->buf = (uint8_t *)malloc(s->len + 16);            /* private copy: the decoder strips emulation prevention bytes in place */
+        if (!s->buf || h264b200InitOnEngine(&s->st, 0, e) != HANTRO_OK) { s->failed = 1; rc = -1; continue; }
+        memcpy(s->buf, streams[i].data, s->len); memset(s->buf + s->len, 0, 16);
+        s->inited = 1;
+    }
+    for (i = 0; i < n_threads; i++) { w[i].r = &r; w[i].tid = i; }
+    for (i = 1; i < n_threads; i++) pthread_create(&w[i].th, NULL, worker_main, &w[i]);
+    worker_main(&w[0]);
+    for (i = 1; i < n_threads; i++) pthread_join(w[i].th, NULL);
+    h264b200EngineSync(e);
+    if (out) {
+        memset(out, 0, sizeof *out);
+        for (i = 0; i < n_threads; i++) {
+            out->pictures += w[i].pictures; out->bytes_out += w[i].bytes_out; out->err_mbs += w[i].err_mbs;
+            out->parse_seconds += w[i].parse_s; out->wait_seconds += w[i].wait_s;
+        }
+        for (i = 0; i < n_streams; i++) { out->bytes_in += r.s[i].len; if (r.s[i].failed) out->failed_streams++; }
+        out->rounds = r.rounds; out->threads = n_threads;
+    }
+    for (i = 0; i < n_streams; i++) {
+        if (r.s[i].failed) rc = -1;
+        if (r.s[i].inited) h264bsdShutdown(&r.s[i].st);
+        free(r.s[i].buf);
+    }
+    pthread_mutex_destroy(&r.mu); pthread_cond_destroy(&r.cv);
+    free(r.s); free(w);
+    if (out) out->seconds = now_s() - t0;
+    return rc;
+}
+
+/* ------------------------------------------------------------ GOP splitter */
+/* next start code prefix (00 00 01) at or after i; returns len if none.  *sc_len = 3 or 4 (leading zero byte) */
+static size_t next_start_code(const uint8_t *d, size_t len, size_t i, size_t *prefix_start)
+{
+    while (i + 3 <= len) {
+        const uint8_t *z = (const uint8_t *)memchr(d + i, 0, len - i);
+        if (!z) break;
+        i = (size_t)(z - d);
+        if (i + 3 > len) break;
+        if (d[i + 1] == 0) {
+            size_t j = i + 2;
+            while (j < len && d[j] == 0) j++;
+            if (j < len && d[j] == 1) { *prefix_start = i; return j + 1; }
+            i = j;
+        } else i += 2;
+    }
+    *prefix_start = len;
+    return len;
+}
+
+int h264b200SplitGops(const uint8_t *data, size_t len, uint8_t *out, size_t out_cap,
+                      size_t *seg_off, size_t *seg_len, uint32_t max_segs)
+{
+    size_t pre, nal, hdr_cap = 4096, hdr_len = 0, hdr_len_au = 0, au_start = (size_t)-1, cut_prev = (size_t)-1, o = 0;
+    uint8_t *hdr = (uint8_t *)malloc(hdr_cap), *hdr_at_cut = NULL;
+    size_t hdr_at_cut_len = 0;
+    int n = 0;
+    if (!hdr) return -1;
+    nal = next_start_code(data, len, 0, &pre);
+    while (nal < len) {
+        size_t next_pre, next_nal = next_start_code(data, len, nal, &next_pre);
+        int type = data[nal] & 31;
+        if (au_start == (size_t)-1) { au_start = pre; hdr_len_au = hdr_len; }              /* first NAL after a VCL NAL opens a candidate access unit */
+        if (type == 5 && nal + 1 < len && (data[nal + 1] & 0x80)) { /* IDR slice with first_mb_in_slice == 0: cut at its access unit */
+            if (cut_prev != (size_t)-1) {
+                size_t body = au_start - cut_prev;
+                if ((uint32_t)n >= max_segs || o + hdr_at_cut_len + body > out_cap) { free(hdr); free(hdr_at_cut); return -1; }
+                seg_off[n] = o;
+                memcpy(out + o, hdr_at_cut, hdr_at_cut_len); o += hdr_at_cut_len;
+                memcpy(out + o, data + cut_prev, body); o += body;
+                seg_len[n] = o - seg_off[n]; n++;
+            }
+            cut_prev = au_start;
+            free(hdr_at_cut);
+            hdr_at_cut = (uint8_t *)malloc(hdr_len_au + 1); hdr_at_cut_len = hdr_len_au;   /* sets sent BEFORE this access unit */
+            if (!hdr_at_cut) { free(hdr); return -1; }
+            memcpy(hdr_at_cut, hdr, hdr_len_au);
+        }
+        if (type == 7 || type == 8) {                              /* remember parameter sets (sent before the access unit that needs them) */
+            size_t l = next_pre - pre;
+            if (hdr_len + l > hdr_cap) { hdr_cap = (hdr_len + l) * 2; hdr = (uint8_t *)realloc(hdr, hdr_cap); if (!hdr) { free(hdr_at_cut); return -1; } }
+            memcpy(hdr + hdr_len, data + pre, l); hdr_len += l;
+        }
+        if (type == 1 || type == 5) au_start = (size_t)-1;         /* a VCL NAL closes the candidate */
+        pre = next_pre; nal = next_nal;
+    }
+    if (cut_prev != (size_t)-1) {
+        size_t body = len - cut_prev;
+        if ((uint32_t)n >= max_segs || o + hdr_at_cut_len + body > out_cap) { free(hdr); free(hdr_at_cut); return -1; }
+        seg_off[n] = o;
+        memcpy(out + o, hdr_at_cut, hdr_at_cut_len); o += hdr_at_cut_len;
+        memcpy(out + o, data + cut_prev, body); o += body;
+        seg_len[n] = o - seg_off[n]; n++;
+    }
+    free(hdr); free(hdr_at_cut);
+    return n;
+}

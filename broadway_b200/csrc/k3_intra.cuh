@@ -1,0 +1,285 @@
+/* k3_intra.cuh — kernel family 3: intra prediction + residual add as a macroblock
+ * wavefront (also writes I_PCM macroblocks).
+ *
+ * Device replacement of h264bsdIntraPrediction (h264bsd_intra_prediction.c:
+ * 475-532): neighbour fetch h264bsdGetNeighbourPels (:544-613), Intra16x16
+ * (:626-686, modes :999-1148), Intra4x4 (:700-832, Get4x4NeighbourPels
+ * :1387-1480, nine modes :1492-1829), chroma (:844-914, :1159-1376),
+ * h264bsdAddResidual (:926-988) and h264bsdWriteMacroblock (h264bsd_image.c:
+ * 80-143).  Runs AFTER K2: an intra macroblock may predict from inter
+ * neighbours of the same picture (unconstrained intra), and always from
+ * UNFILTERED samples (deblocking is K4).
+ *
+ * Parallelisation: macroblock (x,y) needs (x-1,y), (x-1,y-1), (x,y-1),
+ * (x+1,y-1).  Each warp owns one macroblock ROW of one picture at a time and
+ * walks its intra macroblocks left to right; before touching macroblock x it
+ * spins until the row above has published progress >= min(x+2, width).  Rows
+ * are handed out through an atomic ticket in (row-major, picture-minor) order,
+ * so a warp only ever waits on tickets lower than its own, which are held by
+ * resident warps: forward progress needs no co-residency guarantee beyond
+ * that.  Samples produced by other warps are read with ld.global.cg (L2), never
+ * through the non-coherent L1.
+ * Inside a macroblock: I16x16/chroma -> 8 / 4 samples per lane; I4x4 -> the
+ * sixteen 4x4 blocks in decoding order, 16 lanes each, through a shared-memory
+ * tile that also holds the neighbour row/column.
+ */
+#pragma once
+#include "k_common.cuh"
+
+#define K3_WARPS 4
+#define K3_TP 48                    /* tile pitch (multiple of 16): interior at columns 16..31, up-right 32..35, left column 15 */
+
+struct __align__(16) K3Warp {
+    h264b200_mb_t rec;
+    __align__(16) uint8_t tile[17][K3_TP];       /* row 0 = samples above the macroblock */
+    __align__(16) uint8_t ctile[2][9][24];       /* chroma: interior at columns 8..15, left column 7 */
+};
+
+__device__ __forceinline__ uint8_t ldcg_u8(const uint8_t *p) { return __ldcg(p); }
+
+/* progress protocol ------------------------------------------------------- */
+__device__ __forceinline__ void wf_wait(const int32_t *progress, int row, int need)
+{
+    if (row > 0) {
+        const volatile int32_t *p = progress + (row - 1);
+        while (*p < need) __nanosleep(20);
+    }
+    __threadfence();
+}
+__device__ __forceinline__ void wf_publish(int32_t *progress, int row, int value, int lane)
+{
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) *((volatile int32_t *)(progress + row)) = value;
+}
+
+/* Intra4x4 prediction of sample (x,y) of a block whose top-left is at tile (tx,ty) */
+__device__ __forceinline__ int i4_pred(const uint8_t (*t)[K3_TP], int tx, int ty, int mode, int x, int y, bool has_top, bool has_left, bool has_ur)
+{
+#define T(i) ((int)t[ty - 1][tx + (((i) > 3 && !has_ur) ? 3 : (i))])
+#define L(i) ((int)t[ty + (i)][tx - 1])
+    switch (mode) {
+    case 0: return T(x);
+    case 1: return L(y);
+    case 2:
+        if (has_top && has_left) return (T(0) + T(1) + T(2) + T(3) + L(0) + L(1) + L(2) + L(3) + 4) >> 3;
+        if (has_left) return (L(0) + L(1) + L(2) + L(3) + 2) >> 2;
+        if (has_top) return (T(0) + T(1) + T(2) + T(3) + 2) >> 2;
+        return 128;
+    case 3:
+        if (x == 3 && y == 3) return (T(6) + 3 * T(7) + 2) >> 2;
+        return (T(x + y) + 2 * T(x + y + 1) + T(x + y + 2) + 2) >> 2;
+    case 4:
+        if (x > y) return (T(x - y - 2) + 2 * T(x - y - 1) + T(x - y) + 2) >> 2;
+        if (x < y) return (L(y - x - 2) + 2 * L(y - x - 1) + L(y - x) + 2) >> 2;
+        return (T(0) + 2 * T(-1) + L(0) + 2) >> 2;
+    case 5: {
+        int z = 2 * x - y, k = x - (y >> 1);
+        if (z >= 0 && !(z & 1)) return (T(k - 1) + T(k) + 1) >> 1;
+        if (z >= 0) return (T(k - 2) + 2 * T(k - 1) + T(k) + 2) >> 2;
+        if (z == -1) return (L(0) + 2 * T(-1) + T(0) + 2) >> 2;
+        return (L(y - 1) + 2 * L(y - 2) + L(y - 3) + 2) >> 2; }
+    case 6: {
+        int z = 2 * y - x, k = y - (x >> 1);
+        if (z >= 0 && !(z & 1)) return (L(k - 1) + L(k) + 1) >> 1;
+        if (z >= 0) return (L(k - 2) + 2 * L(k - 1) + L(k) + 2) >> 2;
+        if (z == -1) return (L(0) + 2 * T(-1) + T(0) + 2) >> 2;
+        return (T(x - 1) + 2 * T(x - 2) + T(x - 3) + 2) >> 2; }
+    case 7: {
+        int k = x + (y >> 1);
+        if (!(y & 1)) return (T(k) + T(k + 1) + 1) >> 1;
+        return (T(k) + 2 * T(k + 1) + T(k + 2) + 2) >> 2; }
+    default: {
+        int z = x + 2 * y, k = y + (x >> 1);
+        if (z > 5) return L(3);
+        if (z == 5) return (L(2) + 3 * L(3) + 2) >> 2;
+        if (!(z & 1)) return (L(k) + L(k + 1) + 1) >> 1;
+        return (L(k) + 2 * L(k + 1) + L(k + 2) + 2) >> 2; }
+    }
+#undef T
+#undef L
+}
+
+/* plane prediction parameters from a neighbour row/column held in shared memory.
+ * top(i)/left(i) for i in -1..n-1.  Returns a, b, c of 8.3.3.4 / 8.3.4.4. */
+template <int N, typename FT, typename FL>
+__device__ __forceinline__ void plane_params(FT top, FL left, int &a, int &bb, int &cc)
+{
+    const int half = N / 2;
+    int hh = 0, vv = 0;
+#pragma unroll
+    for (int i = 0; i < half; i++) {
+        hh += (i + 1) * (top(half + i) - top(half - 2 - i));
+        vv += (i + 1) * (left(half + i) - left(half - 2 - i));
+    }
+    a = 16 * (left(N - 1) + top(N - 1));
+    if (N == 16) { bb = (5 * hh + 32) >> 6; cc = (5 * vv + 32) >> 6; }
+    else { bb = (34 * hh + 32) >> 6; cc = (34 * vv + 32) >> 6; }
+}
+
+__device__ void k3_macroblock(const PicJob &job, K3Warp &w, int mbx, int mby, int lane)
+{
+    const int W = job.wm * 16, H = job.hm * 16, CW = W >> 1;
+    const size_t ysize = (size_t)W * H, csize = ysize >> 2;
+    const h264b200_mb_t *mb = job.mbs + (size_t)mby * job.wm + mbx;
+    if (lane < 8) reinterpret_cast<int4 *>(&w.rec)[lane] = __ldg(reinterpret_cast<const int4 *>(mb) + lane);
+    __syncwarp();
+    const int cls = w.rec.mb_class;
+    uint8_t *Y = job.cur + (size_t)mby * 16 * W + mbx * 16;
+    const int16_t *coef = job.coef + (size_t)w.rec.coef_offset * 16;
+
+    if (cls == H264B200_MB_IPCM) {
+        const uint8_t *src = reinterpret_cast<const uint8_t *>(coef);
+        if (lane < 16) *reinterpret_cast<int4 *>(Y + (size_t)lane * W) = __ldg(reinterpret_cast<const int4 *>(src) + lane);
+        else {
+            int pl = (lane - 16) >> 3, r = lane & 7;
+            *reinterpret_cast<int2 *>(job.cur + ysize + (pl ? csize : 0) + (size_t)(mby * 8 + r) * CW + mbx * 8) =
+                __ldg(reinterpret_cast<const int2 *>(src + 256 + 64 * pl) + r);
+        }
+        return;
+    }
+    const uint32_t mask = w.rec.resid_mask;
+    const bool aA = w.rec.avail & H264B200_AVAIL_A, aB = w.rec.avail & H264B200_AVAIL_B;
+    const bool aC = w.rec.avail & H264B200_AVAIL_C, aD = w.rec.avail & H264B200_AVAIL_D;
+
+    /* ---- neighbour samples into the tile: row 0 (corner, 16 above, 4 above-right), column 15 ---- */
+    {
+        int c = lane;                                  /* columns -1..19 relative to the macroblock: 21 samples */
+        if (c < 21) {
+            int rel = c - 1;
+            bool ok = rel < 0 ? aD : rel < 16 ? aB : aC;
+            w.tile[0][16 + rel] = ok ? ldcg_u8(Y - W + rel) : 0;
+        }
+        if (lane < 16) w.tile[1 + lane][15] = aA ? ldcg_u8(Y + (size_t)lane * W - 1) : 0;
+    }
+    __syncwarp();
+
+    if (cls == H264B200_MB_I16x16) {
+        const int mode = w.rec.i16_mode;
+        int dc = 128, pa = 0, pb = 0, pc = 0;
+        if (mode == 2) {
+            int st = lane < 16 ? w.tile[0][16 + lane] : 0, sl = lane < 16 ? w.tile[1 + lane][15] : 0;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) { st += __shfl_xor_sync(0xffffffffu, st, o); sl += __shfl_xor_sync(0xffffffffu, sl, o); }
+            if (aA && aB) dc = (st + sl + 16) >> 5; else if (aA) dc = (sl + 8) >> 4; else if (aB) dc = (st + 8) >> 4;
+        } else if (mode == 3) {
+            plane_params<16>([&](int i) { return (int)w.tile[0][16 + i]; }, [&](int i) { return (int)w.tile[1 + i][15]; }, pa, pb, pc);
+        }
+        /* lane -> row lane>>1, columns (lane&1)*8 .. +7 */
+        const int y = lane >> 1, x0 = (lane & 1) * 8;
+        uint32_t outw[2];
+#pragma unroll
+        for (int hq = 0; hq < 2; hq++) {
+            const int bx4 = (x0 >> 2) + hq, by4 = y >> 2;
+            const int bi = (bx4 & 1) | ((by4 & 1) << 1) | ((bx4 & 2) << 1) | ((by4 & 2) << 2);     /* luma4x4BlkIdx */
+            const bool has_r = (mask >> bi) & 1;
+            const int16_t *rs = coef + slot_index(mask, bi) * 16 + (y & 3) * 4;
+            uint32_t pk = 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int x = x0 + hq * 4 + i;
+                int v;
+                if (mode == 0) v = w.tile[0][16 + x];
+                else if (mode == 1) v = w.tile[1 + y][15];
+                else if (mode == 2) v = dc;
+                else v = clip255((pa + pb * (x - 7) + pc * (y - 7) + 16) >> 5);
+                if (has_r) v = clip255(v + rs[i]);
+                pk |= (uint32_t)v << (8 * i);
+            }
+            outw[hq] = pk;
+        }
+        *reinterpret_cast<uint2 *>(Y + (size_t)y * W + x0) = make_uint2(outw[0], outw[1]);
+    } else {
+        /* ---- Intra4x4: 16 blocks in decoding order through the tile ---- */
+        for (int blk = 0; blk < 16; blk++) {
+            const int x4 = (blk & 1) | ((blk >> 1) & 2), y4 = ((blk >> 1) & 1) | ((blk >> 2) & 2);
+            const bool has_left = x4 > 0 || aA, has_top = y4 > 0 || aB;
+            bool has_ur;
+            if (y4 == 0) has_ur = x4 < 3 ? aB : aC;
+            else has_ur = (0x5744u >> blk) & 1;        /* above-right block already decoded inside this macroblock */
+            const int tx = 16 + 4 * x4, ty = 1 + 4 * y4;
+            int v = 0;
+            if (lane < 16) {
+                const int x = lane & 3, y = lane >> 2;
+                v = i4_pred(w.tile, tx, ty, w.rec.i4_mode[blk], x, y, has_top, has_left, has_ur);
+                if ((mask >> blk) & 1) v = clip255(v + coef[slot_index(mask, blk) * 16 + lane]);
+            }
+            __syncwarp();
+            if (lane < 16) w.tile[ty + (lane >> 2)][tx + (lane & 3)] = (uint8_t)v;
+            __syncwarp();
+        }
+        if (lane < 16) *reinterpret_cast<int4 *>(Y + (size_t)lane * W) = *reinterpret_cast<const int4 *>(&w.tile[1 + lane][16]);
+    }
+
+    /* ---- chroma 8x8 x 2 ---- */
+    {
+        const int pl = lane >> 4, l16 = lane & 15;
+        uint8_t *C = job.cur + ysize + (pl ? csize : 0) + (size_t)mby * 8 * CW + mbx * 8;
+        if (l16 < 9) { int rel = l16 - 1; bool ok = rel < 0 ? aD : aB; w.ctile[pl][0][8 + rel] = ok ? ldcg_u8(C - CW + rel) : 0; }
+        if (l16 < 8) w.ctile[pl][1 + l16][7] = aA ? ldcg_u8(C + (size_t)l16 * CW - 1) : 0;
+        __syncwarp();
+        const int mode = w.rec.chroma_mode;
+        const int y = l16 >> 1, x0 = (l16 & 1) * 4;                 /* lane -> one 4-sample row segment */
+        const uint8_t (*ct)[24] = w.ctile[pl];
+        int dc = 128, pa = 0, pb = 0, pc = 0;
+        if (mode == 0) {
+            const int xo = x0, yo = y & 4;
+            int st = ct[0][8 + xo] + ct[0][9 + xo] + ct[0][10 + xo] + ct[0][11 + xo];
+            int sl = ct[1 + yo][7] + ct[2 + yo][7] + ct[3 + yo][7] + ct[4 + yo][7];
+            const bool diag = (xo == 0) == (yo == 0);              /* blocks 0 and 3 */
+            if (diag) { if (aA && aB) dc = (st + sl + 4) >> 3; else if (aB) dc = (st + 2) >> 2; else if (aA) dc = (sl + 2) >> 2; }
+            else if (yo == 0) { if (aB) dc = (st + 2) >> 2; else if (aA) dc = (sl + 2) >> 2; }   /* block 1 */
+            else { if (aA) dc = (sl + 2) >> 2; else if (aB) dc = (st + 2) >> 2; }                 /* block 2 */
+        } else if (mode == 3) {
+            plane_params<8>([&](int i) { return (int)ct[0][8 + i]; }, [&](int i) { return (int)ct[1 + i][7]; }, pa, pb, pc);
+        }
+        const int cb = 16 + 4 * pl + (y >> 2) * 2 + (x0 >> 2);
+        const bool has_r = (mask >> cb) & 1;
+        const int16_t *rs = coef + slot_index(mask, cb) * 16 + (y & 3) * 4;
+        uint32_t pk = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int x = x0 + i;
+            int v;
+            if (mode == 0) v = dc;
+            else if (mode == 1) v = ct[1 + y][7];
+            else if (mode == 2) v = ct[0][8 + x];
+            else v = clip255((pa + pb * (x - 3) + pc * (y - 3) + 16) >> 5);
+            if (has_r) v = clip255(v + rs[i]);
+            pk |= (uint32_t)v << (8 * i);
+        }
+        *reinterpret_cast<uint32_t *>(C + (size_t)y * CW + x0) = pk;
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(K3_WARPS * 32) k3_intra(Batch b)
+{
+    __shared__ K3Warp sm[K3_WARPS];
+    const int lane = threadIdx.x & 31;
+    K3Warp &w = sm[threadIdx.x >> 5];
+    const uint32_t n_tasks = (uint32_t)b.n_jobs * (uint32_t)b.max_hm;
+    for (;;) {
+        uint32_t t = 0;
+        if (lane == 0) t = atomicAdd(&b.tickets[0], 1u);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= n_tasks) break;
+        const int row = t / b.n_jobs;
+        const PicJob &job = b.jobs[t - (uint32_t)row * b.n_jobs];
+        if (row >= job.hm || job.n_intra == 0) continue;
+        const int wm = job.wm;
+        const h264b200_mb_t *rowrec = job.mbs + (size_t)row * wm;
+        int x = 0;
+        while (x < wm) {
+            int cls = (x + lane < wm) ? __ldg(reinterpret_cast<const uint8_t *>(rowrec + x + lane)) : 0;
+            unsigned m = __ballot_sync(0xffffffffu, cls == H264B200_MB_I4x4 || cls == H264B200_MB_I16x16 || cls == H264B200_MB_IPCM);
+            if (!m) { x += 32; continue; }
+            x += __ffs(m) - 1;
+            wf_publish(job.progress, row, x, lane);              /* everything left of x is final */
+            wf_wait(job.progress, row, min(x + 2, wm));
+            k3_macroblock(job, w, x, row, lane);
+            x++;
+        }
+        wf_publish(job.progress, row, wm, lane);
+    }
+}

@@ -1,0 +1,58 @@
+/* k_common.cuh — device-side view of one batch of pictures and small helpers
+ * shared by the four kernel families (sm_100a). */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "h264b200_records.h"
+#include "h264_consts.h"
+
+#define H264_MAX_SLOTS_DEV 18
+
+/* One picture of a batch.  Frames are planar I420, MB aligned: Y (16*wm x 16*hm),
+ * then Cb, then Cr, pitch = width (the layout the reference hands out,
+ * h264bsd_util.c:265-284), so the device frame is what the D2H copy returns. */
+struct PicJob {
+    const h264b200_mb_t *mbs;      /* wm*hm records, raster order */
+    const int16_t *coef_in;        /* coefficient slots as parsed (levels); == coef unless replaying resident input */
+    int16_t *coef;                 /* residual slots written by K1, read by K2/K3 */
+    uint8_t *cur;                  /* frame being reconstructed */
+    uint8_t *frames;               /* base of the instance's frame pool */
+    uint32_t frame_bytes;          /* wm*hm*384 */
+    int32_t  wm, hm;
+    int32_t *progress;             /* 2*hm wavefront counters: [0,hm) K3, [hm,2hm) K4 */
+    uint32_t n_intra, n_inter, any_deblock;
+    uint32_t mb_base;              /* first macroblock of this picture in the batch-wide numbering */
+};
+
+struct Batch {
+    const PicJob *jobs;
+    int32_t n_jobs;
+    int32_t max_hm;                /* max rows over the batch */
+    uint32_t total_mbs;
+    uint32_t *tickets;             /* [0]: K3 ticket counter, [1]: K4 ticket counter */
+    uint32_t *error_flags;         /* bit 0: residual out of [-512,511] */
+};
+
+__device__ __forceinline__ int clip255(int v) { return min(max(v, 0), 255); }
+__device__ __forceinline__ int clip3i(int lo, int hi, int v) { return min(max(v, lo), hi); }
+
+/* locate (job, local mb index) of batch-wide macroblock g by binary search on mb_base */
+__device__ __forceinline__ int find_job(const Batch &b, uint32_t g)
+{
+    int lo = 0, hi = b.n_jobs - 1;
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (b.jobs[mid].mb_base <= g) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+/* index of the coefficient slot of block blk (0..23) inside the macroblock, given resid_mask with bit blk set */
+__device__ __forceinline__ uint32_t slot_index(uint32_t mask, int blk)
+{
+    uint32_t below = mask & ((1u << blk) - 1u);
+    uint32_t n = __popc(below);
+    if (mask & H264B200_RESID_LUMA_DC) n++;
+    if (blk >= 16 && (mask & H264B200_RESID_CHROMA_DC)) n++;
+    return n;
+}

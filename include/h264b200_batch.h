@@ -1,0 +1,80 @@
+/* h264b200_batch.h — batch-level entry points of libh264b200.so that have no
+ * direct counterpart in the reference: they exist because ONE 1080p picture is
+ * about a microsecond of HBM traffic, so a B200 is only used well when many
+ * independent pictures (one per stream / IDR-bounded GOP segment) go through
+ * each kernel launch.  The nearest reference code is the multi-instance test
+ * bench (Decoder/src/TestBenchMultipleInstance.c:60-350: N decoder instances
+ * stepped round-robin in one thread); h264b200DecodeStreams is that loop with
+ * worker threads for the serial CAVLC parse and one batched GPU launch per
+ * round.
+ */
+#ifndef H264B200_BATCH_H
+#define H264B200_BATCH_H
+#include "h264b200.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* engine flags */
+#define H264B200_ENGINE_BATCHED 1u  /* pictures wait in the engine until h264b200EngineSubmit */
+#define H264B200_ENGINE_RETAIN  2u  /* keep records + coefficient levels of every batch in HBM for h264b200EngineReplay */
+#define H264B200_ENGINE_NO_D2H  4u  /* do not copy finished frames to the host mirrors (kernel-only measurements) */
+
+h264b200_engine_t *h264b200EngineCreateEx(int device, uint32_t flags);
+void h264b200EngineSetFlags(h264b200_engine_t *e, uint32_t flags);
+
+/* Non-blocking variant of h264bsdNextOutputPicture (h264bsd_decoder.c:642): pops
+ * the display queue and returns the host address the picture WILL occupy; the
+ * samples are valid after h264b200PictureWait(ticket) returned 0.  Lets a
+ * caller that drives many instances defer the wait until the batch holding the
+ * picture has been launched. */
+u8  *h264b200NextOutputPictureAsync(storage_t *pStorage, u32 *picId, u32 *isIdrPic, u32 *numErrMbs, u32 *ticket);
+/* 0: picture complete; otherwise the engine error flags / 0xffffffff on a CUDA failure. */
+u32  h264b200PictureWait(storage_t *pStorage, u32 ticket);
+
+/* ---- resident replay (measurement): re-run K1..K4 over every retained batch,
+ * inputs already in HBM, no host<->device copies.  Asynchronous; returns the
+ * number of pictures enqueued.  Requires H264B200_ENGINE_RETAIN while decoding. */
+u32  h264b200EngineReplay(h264b200_engine_t *e, u32 reps, int time_kernels);
+void h264b200EngineDropRetained(h264b200_engine_t *e);
+/* number of frame slots whose device content differs from the host mirror the
+ * normal decode filled (0 = the replay reproduced the same pictures) */
+u32  h264b200EngineCheckResident(h264b200_engine_t *e);
+/* accumulated CUDA-event time, algorithmic bytes and launches per
+ * kernel family [K1 transform, K2 inter, K3 intra, K4 deblock] of timed replays */
+typedef struct { double ms[4]; uint64_t bytes[4]; uint64_t launches[4]; } h264b200_kernel_times_t;
+void h264b200EngineKernelTimes(h264b200_engine_t *e, h264b200_kernel_times_t *out, int reset);
+
+/* ---- many streams through one engine ---- */
+typedef struct { const uint8_t *data; size_t len; } h264b200_stream_t;   /* Annex-B; not modified (copied internally) */
+/* Called from worker threads (concurrently for different streams; in decode order
+ * within a stream).  i420 is valid only during the call. */
+typedef void (*h264b200_picture_cb)(void *user, uint32_t stream, uint32_t index, const uint8_t *i420,
+                                    uint32_t width, uint32_t height, uint32_t pic_id, uint32_t num_err_mbs);
+typedef struct {
+    uint64_t pictures, bytes_in, bytes_out;
+    uint32_t err_mbs, failed_streams, rounds, threads;
+    double   seconds;            /* wall clock of the whole call */
+    double   parse_seconds;      /* summed over threads: time inside h264bsdDecode */
+    double   wait_seconds;       /* summed over threads: time blocked on the GPU */
+} h264b200_run_stats_t;
+/* Decode n_streams independent streams (or GOP segments) with n_threads parser
+ * threads (0: one per online CPU): every round parses one picture of every live
+ * stream, launches them as one batch, and overlaps the next round's parse with
+ * the GPU.  Returns 0 on success. */
+int h264b200DecodeStreams(h264b200_engine_t *e, const h264b200_stream_t *streams, uint32_t n_streams,
+                          uint32_t n_threads, h264b200_picture_cb cb, void *user, h264b200_run_stats_t *out);
+
+/* Cut an Annex-B stream into self-contained segments at IDR access units
+ * (an IDR empties the DPB, h264bsd_dpb.c:675-708, so nothing crosses a cut).
+ * Segment i is written to out + seg_off[i], seg_len[i] bytes: every parameter
+ * set NAL seen before the cut, then the stream bytes up to the next cut.
+ * Returns the number of segments (<= max_segs), or -1 if out_cap is too small
+ * (len * 2 + 4096 is always enough for streams whose parameter sets are sent once). */
+int h264b200SplitGops(const uint8_t *data, size_t len, uint8_t *out, size_t out_cap,
+                      size_t *seg_off, size_t *seg_len, uint32_t max_segs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
