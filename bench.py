@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json's metric: 1080p frames/s of bit-exact H.264 Baseline decode.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: under torchrun, one rank per GPU)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+Workload (config.workload): BASELINE.json configs[2], "synthetic 1080p Baseline IPPP stream
+(random MVs incl. quarter-pel, deblocking on)" — configs[1] (Player/tree.mp4) is absent from the
+reference mount.  Per GPU: S independent 1920x1088 streams of F pictures (1 IDR + F-1 P; all
+partition shapes, quarter-pel vectors, ~30 % coded 4x4 blocks, in-loop deblocking on) from the
+in-repo writer.  One STEP decodes all S*F pictures: F batched launches of S pictures per kernel
+family.  Weak scaling: every rank gets its own S streams.
+
+Own arm prints
+  value       frames/s with records + coefficient levels already resident in HBM (retained batches
+              replayed: K1 transform, K2 inter, K3 intra, K4 deblock only; CUDA events on the
+              engine's compute stream; the replay is checked to rebuild the very same frames)
+  e2e         frames/s through the C ABI (h264b200DecodeStreams -> h264bsdDecode per NAL) from HOST
+              Annex-B bytes to HOST I420 frames: CAVLC parse on the host cores, H2D of records,
+              kernels, D2H of every frame into pinned memory — all inside the timed region
+  roofline    the kernel family with the largest share of device time, algorithmic bytes
+  cpu_baseline the UNMODIFIED reference decoder (oracle/_ref/refdec, gcc -O3), one process per host core
+Reference arm (--impl reference) times that same reference build on the same streams.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WIDTH_MBS, HEIGHT_MBS = 120, 68          # 1920x1088 coded size of 1080p
+DEFAULT_STREAMS, DEFAULT_FRAMES, DISTINCT = 64, 16, 16
+REFDEC = os.path.join(ROOT, "oracle", "_ref", "refdec")
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def make_streams(n_streams, n_frames, rank):
+    """S streams per rank from DISTINCT distinct seeds (the writer produces ~16 1080p pictures per second)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from broadway_b200 import bitstream
+    n_distinct = min(DISTINCT, n_streams)
+
+    def gen(i):
+        return bitstream.synth(WIDTH_MBS, HEIGHT_MBS, n_frames, seed=1234 + 1000 * rank + i)
+    with ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1)) as ex:
+        base = list(ex.map(gen, range(n_distinct)))
+    return [base[i % n_distinct] for i in range(n_streams)]
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe line)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(kernel):
+    """dram bytes per launch of `kernel` from the committed ncu --set full summary, if any."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(kernel)
+        except Exception:
+            return None
+    return None
+
+
+# ----------------------------------------------------------------------------- reference (CPU) timing
+def run_reference(streams, n_procs, reps):
+    """One refdec process per core (taskset-pinned), process i decodes streams[i % len] `reps` times.
+    Returns (frames, wall seconds)."""
+    tmp = tempfile.mkdtemp(prefix="h264ref_")
+    paths = []
+    for i, s in enumerate(streams[:n_procs]):
+        p = os.path.join(tmp, "s%d.264" % i)
+        open(p, "wb").write(s)
+        paths.append(p)
+    have_taskset = subprocess.run(["which", "taskset"], capture_output=True).returncode == 0
+    cpus = sorted(os.sched_getaffinity(0))
+    t0 = time.perf_counter()
+    procs = []
+    for i in range(n_procs):
+        cmd = [REFDEC, "-r", str(reps), paths[i % len(paths)]]
+        if have_taskset:
+            cmd = ["taskset", "-c", str(cpus[i % len(cpus)])] + cmd
+        procs.append(subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True))
+    frames = 0
+    for p in procs:
+        out = p.communicate()[0]
+        frames += json.loads(out.splitlines()[-1])["frames"]
+    dt = time.perf_counter() - t0
+    for p in paths:
+        os.remove(p)
+    os.rmdir(tmp)
+    return frames, dt
+
+
+def reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    if not os.path.exists(REFDEC):
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/refdec not built (reference sources absent at build time)"}))
+        return
+    cores = len(os.sched_getaffinity(0))
+    streams = make_streams(min(cores, DISTINCT), args.frames, 0)
+    for _ in range(args.warmup):
+        run_reference(streams, cores, 1)
+    frames = 0
+    t = 0.0
+    for _ in range(args.steps):
+        f, dt = run_reference(streams, cores, 1)
+        frames += f
+        t += dt
+    fps = frames / t
+    sample = "%d refdec processes (one per host core), each decoding one %d-picture 1080p stream per step" % (cores, args.frames)
+    print(json.dumps({
+        "impl": "reference", "metric": "1080p frames/sec (bit-exact H.264 Baseline decode)", "value": fps, "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * t / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "synthetic 1080p Baseline IPPP (BASELINE.json configs[2])", "width": 1920, "height": 1088,
+                   "frames_per_stream": args.frames, "streams_per_step": cores},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "reference", "sample": sample},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ----------------------------------------------------------------------------- own arm
+def own_arm(args, rank, local_rank, world):
+    import torch
+    from broadway_b200 import capi
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    capi.require_gpu()
+    cores = len(os.sched_getaffinity(0))
+    threads = args.threads or max(1, cores // world)
+    streams = make_streams(args.streams, args.frames, rank)
+    frames_per_step = args.streams * args.frames
+    log("[rank %d] %d streams x %d pictures, %.1f MB of Annex-B, %d parser threads" % (rank, args.streams, args.frames, sum(map(len, streams)) / 1e6, threads))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if not dist:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- parity gate (untimed): every picture of the first streams against the committed per-frame MD5s
+    # of the UNMODIFIED reference (tests/golden/bench_streams.json, made by tools/make_golden.py)
+    check = {}
+    gpath = os.path.join(ROOT, "tests", "golden", "bench_streams.json")
+    if rank == 0 and not args.no_check and os.path.exists(gpath):
+        import hashlib
+        g = json.load(open(gpath))
+        if g["frames"] == args.frames:
+            n_chk = min(len(g["streams"]), len(streams))
+            with capi.Engine(local_rank) as eng:
+                got, _ = eng.decode_streams_md5(streams[:n_chk], threads=n_chk)
+            for i in range(n_chk):
+                if hashlib.md5(streams[i]).hexdigest() != g["streams"][i]["stream_md5"]:
+                    raise SystemExit("bench stream %d is not the stream the golden was made from" % i)
+                if got[i] != g["streams"][i]["frame_md5"]:
+                    raise SystemExit("PARITY FAILURE on bench stream %d against the reference golden" % i)
+            check = {"streams": n_chk, "pictures": n_chk * args.frames, "against": "reference golden MD5 (tests/golden/bench_streams.json)", "md5_exact": True}
+            log("[rank 0] parity gate: %d pictures MD5-exact vs the reference" % check["pictures"])
+
+    # ---- end-to-end leg: host Annex-B -> host I420 frames through the C ABI
+    eng = capi.Engine(local_rank, capi.ENGINE_BATCHED)
+    for _ in range(args.warmup):
+        eng.decode_streams(streams, threads)
+    barrier()
+    s0 = eng.stats()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    t0 = time.perf_counter()
+    parse_s = wait_s = 0.0
+    for _ in range(args.steps):
+        rs = eng.decode_streams(streams, threads)
+        assert rs.pictures == frames_per_step and rs.err_mbs == 0, (rs.pictures, rs.err_mbs)
+        parse_s += rs.parse_seconds
+        wait_s += rs.wait_seconds
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    s1 = eng.stats()
+    eng.close()
+    e2e_fps = world * frames_per_step * args.steps / e2e_s
+    h2d = (s1["h2d_bytes"] - s0["h2d_bytes"]) // args.steps
+    d2h = (s1["d2h_bytes"] - s0["d2h_bytes"]) // args.steps
+    launches_e2e = s1["kernel_launches"] - s0["kernel_launches"]
+
+    # ---- resident leg: retain every batch of one decode in HBM, then replay K1..K4 only
+    eng = capi.Engine(local_rank, capi.ENGINE_BATCHED | capi.ENGINE_RETAIN)
+    eng.decode_streams(streams, threads)
+    eng.sync()
+    assert eng.check_resident() == 0
+    for _ in range(args.warmup):
+        eng.replay(1, False)
+    eng.sync()
+    eng.kernel_times(reset=True)
+    barrier()
+    s0 = eng.stats()
+    n = eng.replay(args.steps, True)
+    dev_ms = eng.replay_ms()
+    barrier()
+    dev_ms = max_over_ranks(dev_ms)
+    s1 = eng.stats()
+    assert n == frames_per_step * args.steps
+    clocks = sampler.stop() if rank == 0 else None
+    kt = eng.kernel_times()
+    bad = eng.check_resident()
+    assert bad == 0, "replay did not reproduce the decoded frames (%d slots differ)" % bad
+    err = eng.error_flags()
+    eng.close()
+    value = world * frames_per_step * args.steps / (dev_ms / 1000.0)
+    launches = s1["kernel_launches"] - s0["kernel_launches"]
+
+    # ---- roofline of the dominant kernel family
+    peak, peak_src = measured_peak()
+    dom = max(kt, key=lambda k: kt[k]["ms"])
+    kinfo = {}
+    total_ms = sum(v["ms"] for v in kt.values()) or 1.0
+    for k, v in kt.items():
+        if v["launches"]:
+            kinfo[k] = {"ms_per_launch": v["ms"] / v["launches"], "GBps": v["bytes"] / v["ms"] / 1e6 if v["ms"] else None,
+                        "frac_of_peak": (v["bytes"] / v["ms"] / 1e6 / peak) if v["ms"] else None, "share_of_step": v["ms"] / total_ms,
+                        "launches": v["launches"], "algorithmic_bytes_per_launch": v["bytes"] // v["launches"]}
+    ach = kinfo[dom]["GBps"]
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": ncu_traffic(dom), "peak_source": peak_src, "kernels": kinfo}
+
+    # ---- CPU baseline: the unmodified reference on this box's host cores (rank 0, N=1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        if os.path.exists(REFDEC):
+            reps = max(1, int(round(200.0 / args.frames)))           # ~200 pictures per core: 10-15 s
+            f, dt = run_reference(streams[:min(cores, DISTINCT)], cores, reps)
+            cpu = {"value": f / dt, "unit": "frames/s", "cores": cores, "kind": "reference",
+                   "sample": "%d refdec processes (unmodified reference, gcc -O3, one per host core) x %d pictures of the same 1080p streams" % (cores, args.frames * reps)}
+        else:
+            cpu = {"value": None, "unit": "frames/s", "cores": cores, "kind": "reference", "sample": "oracle/_ref/refdec missing"}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": "1080p frames/sec (bit-exact H.264 Baseline decode)", "value": value, "unit": "frames/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "synthetic 1080p Baseline IPPP, random MVs incl. quarter-pel, ~30% coded blocks, deblocking on (BASELINE.json configs[2]; configs[1] tree.mp4 absent)",
+                       "width": 1920, "height": 1088, "streams_per_gpu": args.streams, "frames_per_stream": args.frames,
+                       "frames_per_step_per_gpu": frames_per_step, "parser_threads_per_gpu": threads, "host_cores": cores,
+                       "l2": "inputs larger than L2 (per step: %.0f MB of frame pools + records per GPU)" % (args.streams * 2 * 3.13 + h2d / 1e6)},
+            "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": 1000.0 * e2e_s / args.steps, "timing": "wall clock between barrier+synchronize pairs, max over ranks",
+                    "host_parse_core_seconds_per_step": parse_s / args.steps, "host_wait_seconds_per_step": wait_s / args.steps,
+                    "kernel_launches": launches_e2e},
+            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+            "parity": check, "device_error_flags": err,
+        }))
+    if dist:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--streams", type=int, default=DEFAULT_STREAMS, help="independent 1080p streams per GPU")
+    ap.add_argument("--frames", type=int, default=DEFAULT_FRAMES, help="pictures per stream (1 IDR + P)")
+    ap.add_argument("--threads", type=int, default=0, help="parser threads per GPU (0: host cores / ranks)")
+    ap.add_argument("--no-check", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    import __graft_entry__
+    if local_rank == 0:
+        __graft_entry__.build()
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+    else:
+        if args.warmup < 3:
+            log("note: fewer than 3 warm-up steps requested")
+        own_arm(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -95,10 +95,12 @@ struct Scratch {
 struct h264b200_engine {
     int device, sm_count;
     cudaStream_t s_h2d, s_comp, s_d2h;
-    cudaEvent_t ev_h2d, ev_comp;
+    cudaEvent_t ev_h2d, ev_comp, ev_rep0, ev_rep1;
     std::mutex mu;
     std::vector<PicBuf *> queue;
     std::vector<Inst *> insts;
+    std::vector<Inst *> zombies;   /* shut-down instances whose frame pools retained batches still name */
+    std::vector<Inst *> pool;      /* shut-down instances kept for reuse: pinned + device allocation is slow */
     Scratch scr[NSCR];
     int next_scr;
     uint32_t *d_err, *h_err;
@@ -309,6 +311,21 @@ static void *be_inst_create(h264_backend_t *be, uint32_t wm, uint32_t hm, uint32
     h264b200_engine *e = (h264b200_engine *)be->ctx;
     if (n_slots > H264_MAX_SLOTS) return NULL;
     set_device(e);
+    {   /* reuse a pooled instance of the same geometry */
+        std::lock_guard<std::mutex> lk(e->mu);
+        for (size_t i = 0; i < e->pool.size(); i++) {
+            Inst *c = e->pool[i];
+            if (c->wm == wm && c->hm == hm && c->n_slots == n_slots) {
+                e->pool.erase(e->pool.begin() + i);
+                memset(c->slot_flags, 0, sizeof c->slot_flags);
+                c->next_buf = 0; c->queued = 0;
+                c->batched = (e->flags & H264B200_ENGINE_BATCHED) != 0;
+                for (int k = 0; k < NBUF; k++) c->bufs[k].state = 0;
+                e->insts.push_back(c);
+                return c;
+            }
+        }
+    }
     Inst *in = (Inst *)calloc(1, sizeof *in);
     if (!in) return NULL;
     in->e = e; in->wm = wm; in->hm = hm; in->n_mbs = wm * hm; in->n_slots = n_slots;
@@ -325,20 +342,28 @@ static void *be_inst_create(h264_backend_t *be, uint32_t wm, uint32_t hm, uint32
     return in;
 }
 
-static void be_inst_destroy(h264_backend_t *be, void *inst)
+static void inst_free(Inst *in)
 {
-    h264b200_engine *e = (h264b200_engine *)be->ctx; Inst *in = (Inst *)inst;
-    {
-        std::lock_guard<std::mutex> lk(e->mu);
-        if (in->queued) submit_locked(e);
-        for (size_t i = 0; i < e->insts.size(); i++) if (e->insts[i] == in) { e->insts.erase(e->insts.begin() + i); break; }
-    }
-    set_device(e);
-    cudaStreamSynchronize(e->s_comp); cudaStreamSynchronize(e->s_d2h);
     for (int i = 0; i < NBUF; i++) picbuf_free(&in->bufs[i]);
     for (uint32_t i = 0; i < in->n_slots; i++) cudaEventDestroy(in->slot_ready[i]);
     cudaFree(in->d_frames); cudaFreeHost(in->h_frames);
     free(in);
+}
+
+static void be_inst_destroy(h264_backend_t *be, void *inst)
+{
+    h264b200_engine *e = (h264b200_engine *)be->ctx; Inst *in = (Inst *)inst;
+    bool keep;
+    {
+        std::lock_guard<std::mutex> lk(e->mu);
+        if (in->queued) submit_locked(e);
+        keep = !e->retained.empty();           /* retained batches name this instance's frame pool */
+        if (keep) e->zombies.push_back(in);
+        else for (size_t i = 0; i < e->insts.size(); i++) if (e->insts[i] == in) { e->insts.erase(e->insts.begin() + i); break; }
+    }
+    set_device(e);
+    cudaStreamSynchronize(e->s_comp); cudaStreamSynchronize(e->s_d2h);
+    if (!keep) { std::lock_guard<std::mutex> lk(e->mu); e->pool.push_back(in); }
 }
 
 static h264_pic_input_t *be_pic_begin(h264_backend_t *be, void *inst)
@@ -438,6 +463,8 @@ extern "C" h264b200_engine_t *h264b200EngineCreateEx(int device, uint32_t flags)
     CUDA_TRY(cudaStreamCreateWithFlags(&e->s_d2h, cudaStreamNonBlocking), { delete e; return NULL; });
     CUDA_TRY(cudaEventCreateWithFlags(&e->ev_h2d, cudaEventDisableTiming), { delete e; return NULL; });
     CUDA_TRY(cudaEventCreateWithFlags(&e->ev_comp, cudaEventDisableTiming), { delete e; return NULL; });
+    CUDA_TRY(cudaEventCreate(&e->ev_rep0), { delete e; return NULL; });
+    CUDA_TRY(cudaEventCreate(&e->ev_rep1), { delete e; return NULL; });
     for (int i = 0; i < NSCR; i++) CUDA_TRY(cudaEventCreateWithFlags(&e->scr[i].done, cudaEventDisableTiming), { delete e; return NULL; });
     CUDA_TRY(cudaMalloc((void **)&e->d_err, 64), { delete e; return NULL; });
     CUDA_TRY(cudaMemset(e->d_err, 0, 64), { delete e; return NULL; });
@@ -455,6 +482,11 @@ static void free_retained(h264b200_engine *e)
 {
     for (Retained *r : e->retained) { for (void *p : r->owned) cudaFree(p); delete r; }
     e->retained.clear();
+    for (Inst *z : e->zombies) {
+        for (size_t i = 0; i < e->insts.size(); i++) if (e->insts[i] == z) { e->insts.erase(e->insts.begin() + i); break; }
+        inst_free(z);
+    }
+    e->zombies.clear();
 }
 
 extern "C" void h264b200EngineDestroy(h264b200_engine_t *e)
@@ -463,6 +495,8 @@ extern "C" void h264b200EngineDestroy(h264b200_engine_t *e)
     set_device(e);
     cudaStreamSynchronize(e->s_h2d); cudaStreamSynchronize(e->s_comp); cudaStreamSynchronize(e->s_d2h);
     free_retained(e);
+    for (Inst *p : e->pool) inst_free(p);
+    e->pool.clear();
     for (cudaEvent_t ev : e->tev) cudaEventDestroy(ev);
     for (int i = 0; i < NSCR; i++) {
         Scratch &s = e->scr[i];
@@ -473,7 +507,7 @@ extern "C" void h264b200EngineDestroy(h264b200_engine_t *e)
     }
     if (e->d_replay_ctrl) cudaFree(e->d_replay_ctrl);
     cudaFree(e->d_err); cudaFreeHost(e->h_err);
-    cudaEventDestroy(e->ev_h2d); cudaEventDestroy(e->ev_comp);
+    cudaEventDestroy(e->ev_h2d); cudaEventDestroy(e->ev_comp); cudaEventDestroy(e->ev_rep0); cudaEventDestroy(e->ev_rep1);
     cudaStreamDestroy(e->s_h2d); cudaStreamDestroy(e->s_comp); cudaStreamDestroy(e->s_d2h);
     delete e;
 }
@@ -522,6 +556,7 @@ extern "C" u32 h264b200EngineReplay(h264b200_engine_t *e, u32 reps, int time_ker
     size_t need = 0;
     for (Retained *r : e->retained) if (r->ctrl_words > need) need = r->ctrl_words;
     u32 pics = 0;
+    cudaEventRecord(e->ev_rep0, e->s_comp);
     for (u32 rep = 0; rep < reps; rep++) for (size_t bi = 0; bi < e->retained.size(); bi++) {
         Retained *r = e->retained[bi];
         BatchPlan pl; pl.k1 = r->k1; pl.k2 = r->k2; pl.k3 = r->k3; pl.k4 = r->k4;
@@ -539,8 +574,19 @@ extern "C" u32 h264b200EngineReplay(h264b200_engine_t *e, u32 reps, int time_ker
         launch_kernels(e, r->batch, pl, tev);
         pics += r->n_pics;
     }
+    cudaEventRecord(e->ev_rep1, e->s_comp);
     e->st.pictures += pics; e->st.batches += (uint64_t)reps * e->retained.size();
     return pics;
+}
+
+/* Device time of the last h264b200EngineReplay call: CUDA events on the compute stream around all of its launches. */
+extern "C" double h264b200EngineReplayMs(h264b200_engine_t *e)
+{
+    float ms = 0;
+    if (!e) return -1.0;
+    set_device(e);
+    if (cudaEventSynchronize(e->ev_rep1) != cudaSuccess || cudaEventElapsedTime(&ms, e->ev_rep0, e->ev_rep1) != cudaSuccess) return -1.0;
+    return (double)ms;
 }
 
 /* Fold the event pairs of timed replays into the per-kernel totals (after a sync). */

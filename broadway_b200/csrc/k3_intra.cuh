@@ -128,8 +128,8 @@ __device__ void k3_macroblock(const PicJob &job, K3Warp &w, int mbx, int mby, in
     uint8_t *Y = job.cur + (size_t)mby * 16 * W + mbx * 16;
     const int16_t *coef = job.coef + (size_t)w.rec.coef_offset * 16;
 
-    if (cls == H264B200_MB_IPCM) {
-        const uint8_t *src = reinterpret_cast<const uint8_t *>(coef);
+    if (cls == H264B200_MB_IPCM) {                     /* raw samples sit in the INPUT slots (K1 never touches them) */
+        const uint8_t *src = reinterpret_cast<const uint8_t *>(job.coef_in + (size_t)w.rec.coef_offset * 16);
         if (lane < 16) *reinterpret_cast<int4 *>(Y + (size_t)lane * W) = __ldg(reinterpret_cast<const int4 *>(src) + lane);
         else {
             int pl = (lane - 16) >> 3, r = lane & 7;

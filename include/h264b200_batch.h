@@ -36,6 +36,8 @@ u32  h264b200PictureWait(storage_t *pStorage, u32 ticket);
  * inputs already in HBM, no host<->device copies.  Asynchronous; returns the
  * number of pictures enqueued.  Requires H264B200_ENGINE_RETAIN while decoding. */
 u32  h264b200EngineReplay(h264b200_engine_t *e, u32 reps, int time_kernels);
+/* device time (ms, CUDA events on the engine's compute stream) of the last h264b200EngineReplay; blocks until it is done */
+double h264b200EngineReplayMs(h264b200_engine_t *e);
 void h264b200EngineDropRetained(h264b200_engine_t *e);
 /* number of frame slots whose device content differs from the host mirror the
  * normal decode filled (0 = the replay reproduced the same pictures) */

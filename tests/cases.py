@@ -1,0 +1,56 @@
+"""Parity cases shared by tools/make_golden.py (which runs the UNMODIFIED reference
+over them and commits per-frame MD5s to tests/golden/streams.json) and the tests.
+
+Every case is a deterministic synthetic Baseline stream from the in-repo writer
+(include/h264b200_writer.h); `kw` are h264w_params_t overrides.  They cover the
+edge cases the reference's own decode loop distinguishes: intra-only / IPPP /
+I_PCM, every partition shape, P_Skip runs, intra in P pictures with and without
+constrained_intra_pred, several reference frames, several slices per picture
+with per-slice deblocking controls (idc 0/1/2, offsets), QP changes, chroma QP
+offset, far out-of-picture vectors (edge clamp), POC types 0 and 2, cropping,
+and the degenerate one-macroblock picture.
+"""
+
+# name, width_mbs, height_mbs, frames, overrides
+SMALL = [
+    ("ippp_default",      20, 12, 6, dict()),
+    ("intra_only",        20, 12, 3, dict(intra_only=1)),
+    ("intra_nodeblock",   20, 12, 2, dict(intra_only=1, deblock_idc=1)),
+    ("ipcm_then_p16",     20, 12, 4, dict(first_idr_ipcm=1, part_mix=0, coded_blk_permille=0, p_intra_permille=0, p_skip_permille=0)),
+    ("p_noresidual_nodbk", 20, 12, 4, dict(first_idr_ipcm=1, coded_blk_permille=0, p_intra_permille=0, deblock_idc=1)),
+    ("p_dense_residual",  20, 12, 4, dict(coded_blk_permille=900, max_coeffs=16, max_level=3)),
+    ("p_intra_mix",       20, 12, 6, dict(p_intra_permille=250, ipcm_permille=100)),
+    ("constrained_intra", 20, 12, 5, dict(p_intra_permille=300, constrained_intra_pred=1)),
+    ("multi_ref",         20, 12, 8, dict(num_ref_frames=4)),
+    ("multi_slice",       20, 12, 5, dict(slices_per_pic=4, multi_slice_params=1, qp_jitter=6, p_intra_permille=100)),
+    ("deblock_idc2",      20, 12, 4, dict(slices_per_pic=3, deblock_idc=2, p_intra_permille=100)),
+    ("deblock_offsets",   20, 12, 4, dict(alpha_c0_offset_div2=3, beta_offset_div2=-2, qp=34)),
+    ("chroma_qp_offset",  20, 12, 4, dict(chroma_qp_index_offset=-5, qp_jitter=8)),
+    ("low_qp",            20, 12, 3, dict(qp=4, qp_jitter=4, max_level=2)),
+    ("high_qp",           20, 12, 3, dict(qp=46, qp_jitter=5, max_level=1, max_coeffs=2)),
+    ("far_mv",            20, 12, 5, dict(far_mv_permille=200, mv_range_qpel=300)),
+    ("skip_heavy",        20, 12, 5, dict(p_skip_permille=700)),
+    ("poc_type0",         20, 12, 6, dict(poc_type=0)),
+    ("idr_period",        20, 12, 9, dict(idr_period=3)),
+    ("crop",              20, 12, 3, dict(crop=1)),
+    ("one_mb",             1,  1, 4, dict()),
+    ("one_row",            7,  1, 4, dict(p_intra_permille=200)),
+    ("one_col",            1,  6, 4, dict(p_intra_permille=200)),
+    ("odd_size",          11,  9, 5, dict(p_intra_permille=150, slices_per_pic=2)),
+    ("wide",              45,  3, 3, dict(p_intra_permille=150)),
+]
+
+# BASELINE.json's full-size configurations (few frames: the reference runs at ~20 fps per core)
+FULL = [
+    ("1080p_ippp",       120, 68, 4, dict()),
+    ("1080p_intra",      120, 68, 2, dict(intra_only=1)),
+    ("4k_ippp",          240, 135, 3, dict(level_idc=51)),
+]
+
+SEED = 20260718
+
+
+def make_stream(case):
+    from broadway_b200 import bitstream
+    name, w, h, n, kw = case
+    return bitstream.synth(w, h, n, seed=SEED + sum(map(ord, name)), **kw)

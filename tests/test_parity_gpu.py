@@ -1,0 +1,143 @@
+"""GPU parity tests (run on the B200 box with -m gpu).  Everything goes through the C ABI of
+libh264b200.so (include/*.h); the checker is the oracle (CPU restatement run live on the same
+bytes) and the committed golden MD5s of the unmodified reference.  Bar: bit-exact (frame MD5)."""
+import ctypes
+import hashlib
+
+import pytest
+
+import cases
+import util
+from broadway_b200 import bitstream, capi
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _gpu():
+    capi.require_gpu()
+
+
+@pytest.mark.parametrize("case", cases.SMALL, ids=[c[0] for c in cases.SMALL])
+def test_swdec_api_matches_golden_and_oracle(case, golden):
+    data = cases.make_stream(case)
+    got, info = capi.decode_annexb(data, api="swdec")
+    want, _ = util.oracle_md5(data)
+    assert info["err_mbs"] == 0
+    assert got == want
+    assert got == golden[case[0]]["frame_md5"]
+
+
+@pytest.mark.parametrize("case", cases.SMALL[:6], ids=[c[0] for c in cases.SMALL[:6]])
+def test_h264bsd_entry_points_match_golden(case, golden):
+    got, info = capi.decode_annexb(cases.make_stream(case), api="bsd")
+    assert got == golden[case[0]]["frame_md5"]
+    assert info["pic_ids"] == list(range(len(got)))
+
+
+@pytest.mark.parametrize("case", cases.FULL, ids=[c[0] for c in cases.FULL])
+def test_full_size_matches_reference_golden(case, golden):
+    got, info = capi.decode_annexb(cases.make_stream(case))
+    assert (info["width"], info["height"]) == (16 * case[1], 16 * case[2])
+    assert got == golden[case[0]]["frame_md5"]
+
+
+def test_batched_streams_match_golden(golden):
+    """All small cases at once through one engine: pictures of different sizes and types share launches."""
+    streams = [cases.make_stream(c) for c in cases.SMALL]
+    with capi.Engine() as eng:
+        md5s, rs = eng.decode_streams_md5(streams, threads=4)
+        assert rs.failed_streams == 0 and rs.err_mbs == 0
+        for c, m in zip(cases.SMALL, md5s):
+            assert m == golden[c[0]]["frame_md5"], c[0]
+        st = eng.stats()
+        assert st["pictures"] == sum(c[3] for c in cases.SMALL)
+        assert st["batches"] <= max(c[3] for c in cases.SMALL) + 2
+        assert eng.error_flags() == 0
+
+
+def test_thread_count_and_batch_shape_do_not_change_results(golden):
+    streams = [cases.make_stream(c) for c in cases.SMALL[:10]]
+    ref = None
+    for threads in (1, 3, 10):
+        with capi.Engine() as eng:
+            md5s, _ = eng.decode_streams_md5(streams, threads=threads)
+        if ref is None:
+            ref = md5s
+        assert md5s == ref
+
+
+def test_gop_segments_in_parallel_equal_sequential_decode():
+    """Size-independent property at 1080p: IDR-bounded segments decoded as independent instances in
+    one batch give exactly the frames of the sequential decode."""
+    data = bitstream.synth(120, 68, 12, seed=4242, idr_period=3)
+    seq, info = capi.decode_annexb(data)
+    assert len(seq) == 12
+    segs = capi.split_gops(data)
+    assert len(segs) == 4
+    with capi.Engine() as eng:
+        md5s, rs = eng.decode_streams_md5(segs, threads=4)
+    assert [m for s in md5s for m in s] == seq
+    # and against the oracle on the first segment (the CPU restatement needs ~0.1 s per 1080p frame)
+    want, _ = util.oracle_md5(segs[0])
+    assert md5s[0] == want
+
+
+def test_resident_replay_reproduces_the_pictures():
+    """bench.py's kernel-only leg replays retained batches from HBM: it must rebuild the same frames."""
+    streams = [bitstream.synth(20, 12, 5, seed=100 + i, p_intra_permille=100) for i in range(6)]
+    with capi.Engine(flags=capi.ENGINE_BATCHED | capi.ENGINE_RETAIN) as eng:
+        md5s, _ = eng.decode_streams_md5(streams, threads=2)
+        for s, m in zip(streams, md5s):
+            assert m == util.oracle_md5(s)[0]
+        assert eng.check_resident() == 0
+        n = eng.replay(reps=3, time_kernels=True)
+        assert n == 3 * 30
+        assert eng.check_resident() == 0
+        kt = eng.kernel_times()
+        assert kt["k2_inter"]["launches"] == 3 * 4 and kt["k4_deblock"]["ms"] > 0
+
+
+def test_idempotent_redecode_and_instance_reuse():
+    data = cases.make_stream(cases.SMALL[0])
+    a, _ = capi.decode_annexb(data)
+    b, _ = capi.decode_annexb(data)
+    assert a == b
+
+
+def test_output_is_planar_i420_mb_aligned():
+    """Decoder.c:113-147 contract: width*height*3/2 bytes, Y then Cb then Cr; an I_PCM picture makes it checkable."""
+    data = bitstream.synth(4, 3, 1, seed=5, first_idr_ipcm=1, deblock_idc=1)
+    frames, info = capi.decode_annexb(data, keep_frames=True)
+    assert (info["width"], info["height"]) == (64, 48) and len(frames[0]) == 64 * 48 * 3 // 2
+    ref, _ = util.oracle_md5(data)
+    assert hashlib.md5(frames[0]).hexdigest() == ref[0]
+
+
+def test_bare_nal_input_like_the_mp4_player():
+    """Player/mp4.js feeds one bare NAL (no start code) per decode() call (h264bsd_byte_stream.c:101-103)."""
+    data = cases.make_stream(cases.SMALL[0])
+    nals = [n for n in data.split(b"\x00\x00\x00\x01") if n]
+    L = capi.lib()
+    st = capi.Storage()
+    assert L.h264bsdInit(ctypes.byref(st), 0) == 0
+    out, nread = [], ctypes.c_uint32()
+    pid, idr, err = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint32()
+    try:
+        for i, nal in enumerate(nals):
+            buf = ctypes.create_string_buffer(nal, len(nal) + 8)
+            while True:
+                rc = L.h264bsdDecode(ctypes.byref(st), ctypes.addressof(buf), len(nal), i, ctypes.byref(nread))
+                if rc == capi.H264BSD_HDRS_RDY:
+                    w, h = 16 * L.h264bsdPicWidth(ctypes.byref(st)), 16 * L.h264bsdPicHeight(ctypes.byref(st))
+                    continue           # same buffer again (readBytes == 0)
+                break
+            if rc == capi.H264BSD_PIC_RDY:
+                while True:
+                    p = L.h264bsdNextOutputPicture(ctypes.byref(st), ctypes.byref(pid), ctypes.byref(idr), ctypes.byref(err))
+                    if not p:
+                        break
+                    out.append(capi.frame_md5(p, w * h * 3 // 2))
+    finally:
+        L.h264bsdShutdown(ctypes.byref(st))
+    assert out == util.oracle_md5(data)[0]
