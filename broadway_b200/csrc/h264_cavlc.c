@@ -13,14 +13,15 @@
 #include "h264_internal.h"
 #include "cavlc_tables.h"
 
-typedef struct { uint8_t len, tc, t1, pad; } ct_entry_t;
+#include "h264_cavlc_inl.h"
 
 /* coeff_token, nC classes 0..2: index = leading_zeros*8 + (3 bits after the first 1) */
-static ct_entry_t g_ct[3][16 * 8];
-static ct_entry_t g_ct_cdc[256];          /* chroma DC: 8-bit direct */
-static uint8_t g_tz[15][512][2];          /* total_zeros: [tc-1][9 bits] -> {len, value} */
-static uint8_t g_tz_cdc[3][8][2];
-static uint8_t g_rb[6][8][2];             /* run_before, zerosLeft 1..6: [zl-1][3 bits] -> {len, run} */
+ct_entry_t g_ct[3][16 * 8];
+ct_entry_t g_ct_cdc[256];          /* chroma DC: 8-bit direct */
+uint8_t g_tz[15][512][2];          /* total_zeros: [tc-1][9 bits] -> {len, value} */
+uint8_t g_tz_cdc[3][8][2];
+uint8_t g_rb[6][8][2];             /* run_before, zerosLeft 1..6: [zl-1][3 bits] -> {len, run} */
+int8_t  g_lvl[7][256][2];          /* level: [suffixLength][8 bits] -> {level, bits} (bits 0: longer than 8) */
 static int g_init;
 
 static int bitlen(unsigned v) { int n = 0; while (v) { n++; v >>= 1; } return n; }
@@ -75,103 +76,15 @@ void h264_cavlc_init(void)
             g_rb[t - 1][(c.code << (3 - c.len)) | k][1] = (uint8_t)i;
         }
     }
+    for (t = 0; t < 7; t++) for (i = 1; i < 256; i++) {      /* level_prefix + level_suffix codes that fit in 8 bits */
+        int prefix = 7 - (bitlen((unsigned)i) - 1), size = t, code, len;
+        if (t == 0 && prefix >= 14) continue;
+        len = prefix + 1 + size;
+        if (len > 8) continue;
+        code = (prefix << t) + ((i >> (8 - len)) & ((1 << size) - 1));
+        g_lvl[t][i][0] = (int8_t)((code & 1) ? (-code - 1) >> 1 : (code + 2) >> 1);
+        g_lvl[t][i][1] = (int8_t)len;
+    }
     g_init = 1;
 }
 
-int h264_cavlc_block(br_t *b, int nc, int max_coeff, int16_t *out, const uint8_t *scan)
-{
-    int tc, t1, i, sl, zeros_left, pos;
-    int level[16];
-
-    /* ---- coeff_token ---- */
-    if (nc < 0) {
-        ct_entry_t e = g_ct_cdc[br_peek(b, 8)];
-        if (!e.len) return -1;
-        br_skip(b, e.len); tc = e.tc; t1 = e.t1;
-    } else if (nc < 8) {
-        uint32_t v;
-        int lz;
-        ct_entry_t e;
-        if (b->bits < 32) br_refill(b);
-        v = (uint32_t)(b->cache >> 32);
-        if (v < 0x10000u) return -1;              /* more than 15 leading zeros: no such code */
-        lz = __builtin_clz(v);
-        e = g_ct[nc < 2 ? 0 : nc < 4 ? 1 : 2][lz * 8 + ((v >> (28 - lz)) & 7)];
-        if (!e.len) return -1;
-        br_skip(b, e.len); tc = e.tc; t1 = e.t1;
-    } else {
-        uint32_t v = br_get(b, 6);
-        if (v == 3) { tc = 0; t1 = 0; }
-        else { tc = (int)(v >> 2) + 1; t1 = (int)(v & 3); if (t1 > tc) return -1; }
-    }
-    if (tc == 0) return 0;
-    if (tc > max_coeff) return -1;
-
-    /* ---- levels ---- */
-    sl = (tc > 10 && t1 < 3) ? 1 : 0;
-    if (t1) {
-        uint32_t s = br_get(b, t1);
-        for (i = 0; i < t1; i++) level[i] = ((s >> (t1 - 1 - i)) & 1) ? -1 : 1;
-    }
-    for (i = t1; i < tc; i++) {
-        uint32_t v;
-        int prefix, code, lv;
-        if (b->bits < 32) br_refill(b);
-        v = (uint32_t)(b->cache >> 32);
-        if (v < 0x10000u) return -1;              /* level_prefix > 15: not Baseline (h264bsd_cavlc.c:513-514) */
-        prefix = __builtin_clz(v);
-        br_skip(b, prefix + 1);
-        code = (prefix < 15 ? prefix : 15) << sl;
-        if (sl > 0 || prefix >= 14) {
-            int size = (prefix == 14 && sl == 0) ? 4 : prefix >= 15 ? 12 : sl;
-            code += (int)br_get(b, size);
-        }
-        if (prefix >= 15 && sl == 0) code += 15;
-        if (i == t1 && t1 < 3) code += 2;
-        lv = (code & 1) ? (-code - 1) >> 1 : (code + 2) >> 1;
-        level[i] = lv;
-        if (sl == 0) sl = 1;
-        if ((lv < 0 ? -lv : lv) > (3 << (sl - 1)) && sl < 6) sl++;
-    }
-
-    /* ---- total_zeros ---- */
-    if (tc < max_coeff) {
-        if (nc < 0) {
-            const uint8_t *e = g_tz_cdc[tc - 1][br_peek(b, 3)];
-            if (!e[0]) return -1;
-            br_skip(b, e[0]); zeros_left = e[1];
-        } else {
-            const uint8_t *e = g_tz[tc - 1][br_peek(b, 9)];
-            if (!e[0]) return -1;
-            br_skip(b, e[0]); zeros_left = e[1];
-        }
-        if (zeros_left + tc > max_coeff) return -1;
-    } else zeros_left = 0;
-
-    /* ---- run_before + placement (highest frequency first) ---- */
-    pos = zeros_left + tc - 1;
-    for (i = 0; i < tc; i++) {
-        int run = 0;
-        out[scan[pos]] = (int16_t)level[i];
-        if (i == tc - 1) break;
-        if (zeros_left > 0) {
-            if (zeros_left <= 6) {
-                const uint8_t *e = g_rb[zeros_left - 1][br_peek(b, 3)];
-                br_skip(b, e[0]); run = e[1];
-            } else {
-                uint32_t v = br_peek(b, 11);
-                if (v >> 8) { run = 7 - (int)(v >> 8); br_skip(b, 3); }
-                else {
-                    int lz;
-                    if (!v) return -1;
-                    lz = __builtin_clz(v) - 21;      /* leading zeros within the 11 bits */
-                    run = lz + 4; br_skip(b, lz + 1);
-                }
-            }
-            if (run > zeros_left) return -1;
-            zeros_left -= run;
-        }
-        pos -= run + 1;
-    }
-    return tc;
-}

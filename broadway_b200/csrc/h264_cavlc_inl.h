@@ -1,0 +1,118 @@
+/* h264_cavlc_inl.h — the CAVLC residual block decoder as an inline function (it runs
+ * ~100 000 times per 1080p picture; see h264_cavlc.c for the tables and the reference
+ * functions it stands in for: h264bsd_cavlc.c:395-915). */
+#ifndef B200_H264_CAVLC_INL_H
+#define B200_H264_CAVLC_INL_H
+#include "h264_bits.h"
+
+typedef struct { uint8_t len, tc, t1, pad; } ct_entry_t;
+extern ct_entry_t g_ct[3][16 * 8];
+extern ct_entry_t g_ct_cdc[256];
+extern uint8_t g_tz[15][512][2];
+extern uint8_t g_tz_cdc[3][8][2];
+extern uint8_t g_rb[6][8][2];
+extern int8_t  g_lvl[7][256][2];
+
+/* Decode one residual block into out[scan[i]].  `out` (16 x int16) is zeroed here when the block
+ * has coefficients and left untouched when TotalCoeff is 0.  nc < 0: chroma DC.
+ * Returns TotalCoeff, or -1 on a malformed block. */
+static inline int h264_cavlc_block(br_t *b, int nc, int max_coeff, int16_t *out, const uint8_t *scan)
+{
+    int tc, t1, i, sl, zeros_left, pos;
+    int level[16];
+    uint32_t v;
+
+    /* ---- coeff_token ---- */
+    if (b->bits < 32) br_refill(b);
+    v = (uint32_t)(b->cache >> 32);
+    if (nc < 0) {
+        ct_entry_t e = g_ct_cdc[v >> 24];
+        if (!e.len) return -1;
+        br_skip(b, e.len); tc = e.tc; t1 = e.t1;
+    } else if (nc < 8) {
+        int lz;
+        ct_entry_t e;
+        if (nc < 2 && (v >> 31)) { br_skip(b, 1); return 0; }      /* the most frequent token: TotalCoeff 0 */
+        if (v < 0x10000u) return -1;              /* more than 15 leading zeros: no such code */
+        lz = __builtin_clz(v);
+        e = g_ct[nc < 2 ? 0 : nc < 4 ? 1 : 2][lz * 8 + ((v >> (28 - lz)) & 7)];
+        if (!e.len) return -1;
+        br_skip(b, e.len); tc = e.tc; t1 = e.t1;
+    } else {
+        v >>= 26; br_skip(b, 6);
+        if (v == 3) { tc = 0; t1 = 0; }
+        else { tc = (int)(v >> 2) + 1; t1 = (int)(v & 3); if (t1 > tc) return -1; }
+    }
+    if (tc == 0) return 0;
+    if (tc > max_coeff) return -1;
+    memset(out, 0, 32);
+
+    /* ---- levels ---- */
+    sl = (tc > 10 && t1 < 3) ? 1 : 0;
+    if (t1) {
+        uint32_t s = br_get(b, t1);
+        for (i = 0; i < t1; i++) level[i] = ((s >> (t1 - 1 - i)) & 1) ? -1 : 1;
+    }
+    for (i = t1; i < tc; i++) {
+        int lv;
+        const int8_t *q;
+        if (b->bits < 32) br_refill(b);
+        v = (uint32_t)(b->cache >> 32);
+        q = g_lvl[sl][v >> 24];
+        if (q[1]) {                               /* prefix + suffix within 8 bits */
+            lv = q[0];
+            br_skip(b, q[1]);
+            if (i == t1 && t1 < 3) lv += lv > 0 ? 1 : -1;           /* levelCode += 2 */
+        } else {
+            int prefix, code;
+            if (v < 0x10000u) return -1;          /* level_prefix > 15: not Baseline (h264bsd_cavlc.c:513-514) */
+            prefix = __builtin_clz(v);
+            br_skip(b, prefix + 1);
+            code = (prefix < 15 ? prefix : 15) << sl;
+            if (sl > 0 || prefix >= 14) {
+                int size = (prefix == 14 && sl == 0) ? 4 : prefix >= 15 ? 12 : sl;
+                code += (int)br_get(b, size);
+            }
+            if (prefix >= 15 && sl == 0) code += 15;
+            if (i == t1 && t1 < 3) code += 2;
+            lv = (code & 1) ? (-code - 1) >> 1 : (code + 2) >> 1;
+        }
+        level[i] = lv;
+        if (sl == 0) sl = 1;
+        if ((lv < 0 ? -lv : lv) > (3 << (sl - 1)) && sl < 6) sl++;
+    }
+
+    /* ---- total_zeros ---- */
+    if (tc < max_coeff) {
+        const uint8_t *e = nc < 0 ? g_tz_cdc[tc - 1][br_peek(b, 3)] : g_tz[tc - 1][br_peek(b, 9)];
+        if (!e[0]) return -1;
+        br_skip(b, e[0]); zeros_left = e[1];
+        if (zeros_left + tc > max_coeff) return -1;
+    } else zeros_left = 0;
+
+    /* ---- run_before + placement (highest frequency first) ---- */
+    pos = zeros_left + tc - 1;
+    for (i = 0; i < tc - 1 && zeros_left > 0; i++) {
+        int run;
+        out[scan[pos]] = (int16_t)level[i];
+        if (zeros_left <= 6) {
+            const uint8_t *e = g_rb[zeros_left - 1][br_peek(b, 3)];
+            br_skip(b, e[0]); run = e[1];
+        } else {
+            v = br_peek(b, 11);
+            if (v >> 8) { run = 7 - (int)(v >> 8); br_skip(b, 3); }
+            else {
+                int lz;
+                if (!v) return -1;
+                lz = __builtin_clz(v) - 21;      /* leading zeros within the 11 bits */
+                run = lz + 4; br_skip(b, lz + 1);
+            }
+        }
+        if (run > zeros_left) return -1;
+        zeros_left -= run;
+        pos -= run + 1;
+    }
+    for (; i < tc; i++) out[scan[pos--]] = (int16_t)level[i];       /* no zeros left: contiguous */
+    return tc;
+}
+#endif

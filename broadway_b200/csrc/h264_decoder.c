@@ -207,6 +207,10 @@ static void finish_picture(h264_decoder_t *d)
     int is_idr = d->pic_nal_type == NAL_IDR;
     int32_t poc;
     if (d->pic) {
+        if (d->num_decoded_mbs != d->pic_size_mbs) {            /* lost slices: flag what was never parsed */
+            uint32_t i;
+            for (i = 0; i < d->pic_size_mbs; i++) if (!d->mbctx[i].decoded) { memset(&d->pic->mbs[i], 0, sizeof d->pic->mbs[i]); d->pic->mbs[i].mb_class = H264B200_MB_MISSING; }
+        }
         d->pic->cur_slot = h264_dpb_current_slot(&d->dpb);
         d->be->pic_submit(d->be, d->be_inst, d->pic);
         d->pic = NULL;
@@ -220,13 +224,11 @@ static void finish_picture(h264_decoder_t *d)
 
 static int begin_picture(h264_decoder_t *d)
 {
-    uint32_t i;
     d->pic = d->be->pic_begin(d->be, d->be_inst);
     if (!d->pic) return -1;
     d->pic->coef_used = 0; d->pic->n_intra = d->pic->n_inter = 0; d->pic->any_deblock = 0;
     memset(d->pic->ref_slots_used, 0, sizeof d->pic->ref_slots_used);
-    memset(d->mbctx, 0, d->pic_size_mbs * sizeof(h264_mbctx_t));
-    for (i = 0; i < d->pic_size_mbs; i++) d->pic->mbs[i].mb_class = H264B200_MB_MISSING;
+    memset(d->mbctx, 0, d->pic_size_mbs * sizeof(h264_mbctx_t));   /* records of unparsed macroblocks are flagged MISSING in finish_picture */
     d->num_decoded_mbs = 0; d->slice_id = 0;
     return 0;
 }

@@ -202,9 +202,7 @@ int32_t h264_decode_poc(h264_decoder_t *d, const h264_slice_hdr_t *sh, int nal_t
 
 /* CAVLC (h264_cavlc.c) */
 void h264_cavlc_init(void);
-/* Decode one residual block into out[scan[i]] (out pre-zeroed). nc < 0: chroma DC.
- * Returns TotalCoeff, or -1 on a malformed block. */
-int h264_cavlc_block(br_t *b, int nc, int max_coeff, int16_t *out, const uint8_t *scan);
+/* the block decoder itself is inline: h264_cavlc_inl.h */
 
 /* slice data (h264_slice.c): parse all macroblocks of one slice into d->pic */
 int h264_decode_slice_data(h264_decoder_t *d, br_t *b, const h264_slice_hdr_t *sh);

@@ -32,7 +32,7 @@ typedef struct { u8 *ptr; u32 ticket, pic_id, err; } pending_t;
 
 typedef struct {
     storage_t st;
-    uint8_t *buf; size_t len, pos;
+    uint8_t *buf; const uint8_t *src; size_t len, pos;
     u32 pic_id, out_index;
     int inited, finished, failed, flushed;
     pending_t cur[MAX_PENDING], prev[MAX_PENDING];
@@ -125,6 +125,10 @@ static void *worker_main(void *arg)
 {
     worker_t *w = (worker_t *)arg; runner_t *r = w->r;
     uint32_t i;
+    for (i = w->tid; i < r->n_streams; i += r->n_threads) {   /* private copy, made by the thread that will parse it */
+        rstream_t *s = &r->s[i];
+        if (s->buf && s->inited) { memcpy(s->buf, s->src, s->len); memset(s->buf + s->len, 0, 16); }
+    }
     for (;;) {
         uint64_t produced = 0;
         for (i = w->tid; i < r->n_streams; i += r->n_threads) {
@@ -169,8 +173,8 @@ int h264b200DecodeStreams(h264b200_engine_t *e, const h264b200_stream_t *streams
         rstream_t *s = &r.s[i];
         s->len = streams[i].len;
         s->buf = (uint8_t *)malloc(s->len + 16);            /* private copy: the decoder strips emulation prevention bytes in place */
+        s->src = streams[i].data;
         if (!s->buf || h264b200InitOnEngine(&s->st, 0, e) != HANTRO_OK) { s->failed = 1; rc = -1; continue; }
-        memcpy(s->buf, streams[i].data, s->len); memset(s->buf + s->len, 0, 16);
         s->inited = 1;
     }
     for (i = 0; i < n_threads; i++) { w[i].r = &r; w[i].tid = i; }

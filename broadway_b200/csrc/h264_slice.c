@@ -16,6 +16,7 @@
 #include <string.h>
 #include "h264_internal.h"
 #include "h264_consts.h"
+#include "h264_cavlc_inl.h"
 
 typedef struct {
     h264_decoder_t *d;
@@ -45,28 +46,6 @@ static void set_neighbours(sl_t *s)
         if (s->mbx + 1 < (int)W && ctx[a - W + 1].slice_id == s->slice_id) { s->cC = &ctx[a - W + 1]; s->rC = &recs[a - W + 1]; }
         if (s->mbx > 0 && ctx[a - W - 1].slice_id == s->slice_id) { s->cD = &ctx[a - W - 1]; s->rD = &recs[a - W - 1]; }
     }
-}
-
-/* --------------------------------------------------------------- nC (9.2.1) */
-static inline int luma_nc(const sl_t *s, int blk)
-{
-    int r = H264_BLK_TO_RASTER[blk], x4 = r & 3, y4 = r >> 2, na = 0, nb = 0, aa = 0, ab = 0;
-    if (x4 > 0) { aa = 1; na = s->cur->tc[H264_RASTER_TO_BLK[r - 1]]; }
-    else if (s->cA) { aa = 1; na = s->cA->tc[H264_RASTER_TO_BLK[r + 3]]; }
-    if (y4 > 0) { ab = 1; nb = s->cur->tc[H264_RASTER_TO_BLK[r - 4]]; }
-    else if (s->cB) { ab = 1; nb = s->cB->tc[H264_RASTER_TO_BLK[12 + x4]]; }
-    if (aa && ab) return (na + nb + 1) >> 1;
-    return aa ? na : nb;
-}
-static inline int chroma_nc(const sl_t *s, int pl, int c)
-{
-    int x = c & 1, y = c >> 1, base = 16 + 4 * pl, na = 0, nb = 0, aa = 0, ab = 0;
-    if (x > 0) { aa = 1; na = s->cur->tc[base + 2 * y]; }
-    else if (s->cA) { aa = 1; na = s->cA->tc[base + 2 * y + 1]; }
-    if (y > 0) { ab = 1; nb = s->cur->tc[base + x]; }
-    else if (s->cB) { ab = 1; nb = s->cB->tc[base + 2 + x]; }
-    if (aa && ab) return (na + nb + 1) >> 1;
-    return aa ? na : nb;
 }
 
 /* ------------------------------------------------ motion vector prediction */
@@ -149,9 +128,17 @@ static void finish_inter(sl_t *s)
 
 /* --------------------------------------------------------------- residual */
 static inline int16_t *slot_ptr(sl_t *s, uint32_t slot) { return s->pic->coef + (size_t)slot * 16; }
-static inline void slot_zero(int16_t *p) { memset(p, 0, 32); }
 
 static const uint8_t IDENT8[8] = {0, 1, 2, 3, 4, 5, 6, 7};
+
+/* nC (9.2.1) from a TotalCoeff cache laid out with one guard row above and one guard column to the
+ * left; 64 marks "not available", so that a+b >= 64 exactly when a neighbour is missing */
+static inline int nc_of(const uint8_t *cache, int idx, int pitch)
+{
+    int n = cache[idx - 1] + cache[idx - pitch];
+    if (n < 64) n = (n + 1) >> 1;
+    return n & 31;
+}
 
 /* residual( ) of 7.3.5.3 for one macroblock; i16: Intra16x16 structure. Returns 0 / -1. */
 static int parse_residual(sl_t *s, int cbp, int i16)
@@ -159,49 +146,66 @@ static int parse_residual(sl_t *s, int cbp, int i16)
     h264b200_mb_t *r = s->rec; h264_mbctx_t *c = s->cur; br_t *b = s->b;
     uint32_t slot = s->pic->coef_used, mask = 0;
     int blk, pl, k, tc, dc_nz = 0;
+    uint8_t lc[5 * 8], cc[2][3 * 4];
+    /* guard cells from the left / upper macroblocks (luma4x4BlkIdx 5,7,13,15 = right column; 10,11,14,15 = bottom row) */
+    memset(lc, 0, sizeof lc); memset(cc, 0, sizeof cc);
+    if (s->cA) {
+        const uint8_t *t = s->cA->tc;
+        lc[8] = t[5]; lc[16] = t[7]; lc[24] = t[13]; lc[32] = t[15];
+        cc[0][4] = t[17]; cc[0][8] = t[19]; cc[1][4] = t[21]; cc[1][8] = t[23];
+    } else { lc[8] = lc[16] = lc[24] = lc[32] = 64; cc[0][4] = cc[0][8] = cc[1][4] = cc[1][8] = 64; }
+    if (s->cB) {
+        const uint8_t *t = s->cB->tc;
+        lc[1] = t[10]; lc[2] = t[11]; lc[3] = t[14]; lc[4] = t[15];
+        cc[0][1] = t[18]; cc[0][2] = t[19]; cc[1][1] = t[22]; cc[1][2] = t[23];
+    } else { lc[1] = lc[2] = lc[3] = lc[4] = 64; cc[0][1] = cc[0][2] = cc[1][1] = cc[1][2] = 64; }
+
     r->coef_offset = slot;
     if (i16) {
         int16_t *p = slot_ptr(s, slot);
-        slot_zero(p);
-        tc = h264_cavlc_block(b, luma_nc(s, 0), 16, p, H264_ZIGZAG4x4);
+        tc = h264_cavlc_block(b, nc_of(lc, 9, 8), 16, p, H264_ZIGZAG4x4);
         if (tc < 0) return -1;
         if (tc) { dc_nz = 1; mask |= H264B200_RESID_LUMA_DC; slot++; }
     }
     for (blk = 0; blk < 16; blk++) {
-        int16_t *p;
+        /* luma4x4BlkIdx -> cache index of (x4, y4) */
+        const int idx = 9 + (((blk & 1) | ((blk >> 1) & 2))) + 8 * (((blk >> 1) & 1) | ((blk >> 2) & 2));
+        int16_t *p = slot_ptr(s, slot);
         if (!((cbp >> (blk >> 2)) & 1)) {
             c->tc[blk] = 0;
-            if (dc_nz) { slot_zero(slot_ptr(s, slot)); mask |= 1u << blk; slot++; }
+            if (dc_nz) { memset(p, 0, 32); mask |= 1u << blk; slot++; }
             continue;
         }
-        p = slot_ptr(s, slot);
-        slot_zero(p);
-        if (i16) tc = h264_cavlc_block(b, luma_nc(s, blk), 15, p, H264_ZIGZAG4x4 + 1);
-        else     tc = h264_cavlc_block(b, luma_nc(s, blk), 16, p, H264_ZIGZAG4x4);
+        if (i16) tc = h264_cavlc_block(b, nc_of(lc, idx, 8), 15, p, H264_ZIGZAG4x4 + 1);
+        else     tc = h264_cavlc_block(b, nc_of(lc, idx, 8), 16, p, H264_ZIGZAG4x4);
         if (tc < 0) return -1;
-        c->tc[blk] = (uint8_t)tc;
-        if (tc) r->nz_mask |= (uint16_t)(1u << blk);
-        if (tc || dc_nz) { mask |= 1u << blk; slot++; }
+        c->tc[blk] = lc[idx] = (uint8_t)tc;
+        if (tc) { r->nz_mask |= (uint16_t)(1u << blk); mask |= 1u << blk; slot++; }
+        else if (dc_nz) { memset(p, 0, 32); mask |= 1u << blk; slot++; }
     }
     if (cbp & 0x30) {
         int16_t *p = slot_ptr(s, slot);
         int cdc[2];
-        slot_zero(p);
+        memset(p, 0, 32);                           /* both planes share this slot; a plane without coefficients leaves its half zero */
         for (pl = 0; pl < 2; pl++) {
-            cdc[pl] = h264_cavlc_block(b, -1, 4, p, IDENT8 + 4 * pl);
+            int16_t tmp[16];
+            cdc[pl] = h264_cavlc_block(b, -1, 4, tmp, IDENT8);
             if (cdc[pl] < 0) return -1;
+            if (cdc[pl]) memcpy(p + 4 * pl, tmp, 8);
         }
         if (cdc[0] || cdc[1]) { mask |= H264B200_RESID_CHROMA_DC; slot++; }
         for (pl = 0; pl < 2; pl++) for (k = 0; k < 4; k++) {
+            const int idx = 5 + (k & 1) + 4 * (k >> 1);                 /* (y+1)*4 + (x+1) */
             p = slot_ptr(s, slot);
             tc = 0;
             if (cbp & 0x20) {
-                slot_zero(p);
-                tc = h264_cavlc_block(b, chroma_nc(s, pl, k), 15, p, H264_ZIGZAG4x4 + 1);
+                tc = h264_cavlc_block(b, nc_of(cc[pl], idx, 4), 15, p, H264_ZIGZAG4x4 + 1);
                 if (tc < 0) return -1;
-            } else if (cdc[pl]) slot_zero(p);
+                cc[pl][idx] = (uint8_t)tc;
+            }
             c->tc[16 + 4 * pl + k] = (uint8_t)tc;
-            if (tc || cdc[pl]) { mask |= 1u << (16 + 4 * pl + k); slot++; }
+            if (tc) { mask |= 1u << (16 + 4 * pl + k); slot++; }
+            else if (cdc[pl]) { memset(p, 0, 32); mask |= 1u << (16 + 4 * pl + k); slot++; }
         }
     }
     r->resid_mask = mask;
