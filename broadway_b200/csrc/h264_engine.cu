@@ -104,6 +104,7 @@ struct h264b200_engine {
     Scratch scr[NSCR];
     int next_scr;
     uint32_t *d_err, *h_err;
+    unsigned long long *d_trace; int trace_left;
     h264b200_stats_t st;
     uint32_t flags;                /* H264B200_ENGINE_* */
     std::vector<Retained *> retained;
@@ -266,13 +267,23 @@ static uint32_t submit_locked(h264b200_engine *e)
 
     Batch b;
     b.jobs = d_jobs; b.n_jobs = (int32_t)n; b.max_hm = pl.max_hm; b.total_mbs = mb_base;
-    b.tickets = (uint32_t *)d_ctrl; b.error_flags = e->d_err;
+    b.tickets = (uint32_t *)d_ctrl; b.error_flags = e->d_err; b.trace = e->trace_left > 0 ? e->d_trace : nullptr;
 
     cudaEventRecord(e->ev_h2d, e->s_h2d);
     cudaStreamWaitEvent(e->s_comp, e->ev_h2d, 0);
     cudaMemcpyAsync(d_jobs, sc.h_jobs, n * sizeof(PicJob), cudaMemcpyHostToDevice, e->s_comp);
     cudaMemsetAsync(d_ctrl, 0, ctrl_words * sizeof(int32_t), e->s_comp);
     launch_kernels(e, b, pl, nullptr);
+    if (b.trace) {                 /* debug: dump the wavefront timing of job 0 of this batch */
+        std::vector<unsigned long long> h(256 + 4 * 512);
+        cudaStreamSynchronize(e->s_comp);
+        cudaMemcpy(h.data(), e->d_trace, h.size() * 8, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "h264b200 trace: batch of %u, job0 %dx%d MBs; per row: start, first-mb, mid, end (us from row 0 start)\n", n, sc.h_jobs[0].wm, sc.h_jobs[0].hm);
+        for (int r = 0; r < sc.h_jobs[0].hm; r++) { const unsigned long long *q = &h[256 + r * 4], t0 = h[256];
+            fprintf(stderr, "  row %2d: %8.1f %8.1f %8.1f %8.1f\n", r, (q[0] - t0) / 1e3, (q[1] - t0) / 1e3, (q[2] - t0) / 1e3, (q[3] - t0) / 1e3); }
+        cudaMemset(e->d_trace, 0, h.size() * 8);
+        e->trace_left--;
+    }
     cudaEventRecord(sc.done, e->s_comp); sc.used = true;
     cudaEventRecord(e->ev_comp, e->s_comp);
     cudaStreamWaitEvent(e->s_d2h, e->ev_comp, 0);
@@ -293,7 +304,7 @@ static uint32_t submit_locked(h264b200_engine *e)
     e->st.pictures += n; e->st.batches++;
     if (retain) {
         ret->jobs.assign(sc.h_jobs, sc.h_jobs + n);
-        ret->batch = b; ret->ctrl_words = ctrl_words;
+        ret->batch = b; ret->batch.trace = nullptr; ret->ctrl_words = ctrl_words;
         ret->k1 = pl.k1; ret->k2 = pl.k2; ret->k3 = pl.k3; ret->k4 = pl.k4;
         for (int k = 0; k < 4; k++) ret->bytes[k] = bytes[k];
         ret->n_pics = n;
@@ -470,6 +481,12 @@ extern "C" h264b200_engine_t *h264b200EngineCreateEx(int device, uint32_t flags)
     CUDA_TRY(cudaMemset(e->d_err, 0, 64), { delete e; return NULL; });
     CUDA_TRY(cudaHostAlloc((void **)&e->h_err, 64, cudaHostAllocDefault), { delete e; return NULL; });
     *e->h_err = 0;
+    e->d_trace = nullptr; e->trace_left = 0;
+    if (getenv("H264B200_TRACE")) {
+        e->trace_left = atoi(getenv("H264B200_TRACE"));
+        CUDA_TRY(cudaMalloc((void **)&e->d_trace, (256 + 4 * 512) * 8), { delete e; return NULL; });
+        cudaMemset(e->d_trace, 0, (256 + 4 * 512) * 8);
+    }
     e->be.inst_create = be_inst_create; e->be.inst_destroy = be_inst_destroy; e->be.pic_begin = be_pic_begin;
     e->be.coef_grow = be_coef_grow; e->be.pic_submit = be_pic_submit; e->be.frame_host = be_frame_host;
     e->be.frame_host_async = be_frame_host_async;

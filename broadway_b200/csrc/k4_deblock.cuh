@@ -11,70 +11,117 @@
  * The filter is order dependent (macroblock raster order is normative): the
  * top edge of (x,y) reads samples of (x,y-1) that the left edge of (x+1,y-1)
  * has already modified, so (x,y) needs (x-1,y), (x,y-1) and (x+1,y-1) complete:
- * the same 2:1 wavefront as intra prediction, run with the same ticketed
- * row-per-warp scheme (k3_intra.cuh).  Per macroblock the warp
+ * a 2:1 wavefront.  One warp owns one macroblock row of one picture (rows are
+ * handed out by an atomic ticket, row-major / picture-minor, so a warp only
+ * waits on lower tickets = resident warps) and walks it left to right.
+ *
+ * The walk is SOFTWARE PIPELINED, because what bounds a wavefront is the
+ * latency of one macroblock step, not bandwidth: while macroblock x is being
+ * filtered out of shared memory, everything macroblock x+1 needs is already in
+ * flight into registers — its record, the record above, its 16x16 + 2x8x8
+ * unfiltered samples (nobody touches them before this warp does) and, when the
+ * row above is far enough ahead (the usual case), the 4 (2 chroma) sample rows
+ * above it.  The 4-sample column to the left is carried over in shared memory.
+ * Row-to-row hand-over uses st.release.gpu / ld.acquire.gpu on a progress
+ * counter (no __threadfence, no L1 invalidate); samples other warps produced
+ * are read with ld.global.cg.
+ * Per macroblock the warp
  *   1. derives the 32 boundary strengths, one per lane (2 directions x 4 edges
  *      x 4 segments) from the current/left/top records;
- *   2. pulls the 20x20 luma and two 12x12 chroma windows (macroblock + 4
- *      samples left and above) from L2 into shared memory with 32-bit loads;
- *   3. filters vertical edges then horizontal edges in shared memory: lanes
- *      0..15 each own one luma line, lanes 16..31 one chroma line (Cb rows,
- *      Cr rows), all four (two) edges of the line in sequence;
- *   4. writes the window back and publishes progress.
+ *   2. filters vertical edges then horizontal edges in the shared window: lanes
+ *      0..15 own one luma line each (4 edges in sequence), lanes 16..31 one
+ *      chroma line each (Cb rows, Cr rows; 2 edges), in ONE loop so that all 32
+ *      lanes work together;
+ *   3. writes the window back and publishes progress.
  * HBM per macroblock: 384 B read + 384 B written + 128 B record (neighbour
  * records and the 4-sample halos are L2 hits).
  */
 #pragma once
 #include "k_common.cuh"
-#include "k3_intra.cuh"      /* wf_wait / wf_publish */
 
 #define K4_WARPS 4
 #define K4_LP 20             /* luma window pitch: 5 words, conflict-free for one line per lane */
 #define K4_CP 12
+#define K4_PUBLISH 2         /* macroblocks per progress hand-over */
 
 struct __align__(16) K4Warp {
     h264b200_mb_t rec[2];    /* current / left (ping-pong) */
     h264b200_mb_t top;
-    __align__(4) uint8_t y[20][K4_LP];
+    __align__(4) uint8_t y[20][K4_LP];      /* rows/cols 0..3: samples above / left of the macroblock */
     __align__(4) uint8_t c[2][12][K4_CP];
     uint8_t bs[2][4][4];     /* [dir][edge][segment] */
-    uint8_t alpha[2][3], beta[2][3], idxa[2][3];   /* [luma/chroma][left, top, inner] */
+    uint32_t thr[2][3];      /* [luma/chroma][left, top, inner]: alpha | beta << 8 | tc0(bS=1) << 16 */
+    uint32_t tc0[2][3];      /* tc0(bS=1) | tc0(bS=2) << 8 | tc0(bS=3) << 16 */
 };
 
-/* one line of samples across an edge; q0 at pix, neighbours at +-step */
-__device__ __forceinline__ void dbk_line(uint8_t *pix, int step, int bs, int alpha, int beta, int tc0, bool luma)
+/* everything of the NEXT macroblock that can be fetched ahead, one register set per lane */
+struct K4Pre { int4 rec; uint32_t y0, y1, c, top; };
+
+/* progress poll: a relaxed gpu-scope load (no L1 invalidate, unlike ld.acquire).  Ordering of the sample
+ * loads that follow comes from the control dependency on the polled value plus ld.global.cg (L2) reads. */
+__device__ __forceinline__ int ld_acquire(const int32_t *p)
 {
-    const int p0 = pix[-step], p1 = pix[-2 * step], q0 = pix[0], q1 = pix[step];
-    if (abs(p0 - q0) >= alpha || abs(p1 - p0) >= beta || abs(q1 - q0) >= beta) return;
-    if (bs < 4) {
-        int tc;
-        if (luma) {
-            const int p2 = pix[-3 * step], q2 = pix[2 * step];
-            const bool ap = abs(p2 - p0) < beta, aq = abs(q2 - q0) < beta;
-            tc = tc0 + ap + aq;
-            if (ap) pix[-2 * step] = (uint8_t)(p1 + clip3i(-tc0, tc0, (p2 + ((p0 + q0 + 1) >> 1) - (p1 << 1)) >> 1));
-            if (aq) pix[step] = (uint8_t)(q1 + clip3i(-tc0, tc0, (q2 + ((p0 + q0 + 1) >> 1) - (q1 << 1)) >> 1));
-        } else tc = tc0 + 1;
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int32_t *p, int v)
+{
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+
+/* wavefront hand-over: `seen` caches the last progress value read from the row above */
+__device__ __forceinline__ bool wf_try(const int32_t *above, int need, int &seen, int lane)
+{
+    if (seen >= need) return true;
+    int v = 0;
+    if (lane == 0) v = ld_acquire(above);
+    seen = __shfl_sync(0xffffffffu, v, 0);
+    return seen >= need;
+}
+__device__ __forceinline__ void wf_wait2(const int32_t *above, int need, int &seen, int lane)
+{
+    while (!wf_try(above, need, seen, lane)) __nanosleep(40);
+}
+__device__ __forceinline__ void wf_publish2(int32_t *mine, int value, int lane)
+{
+    __syncwarp();
+    if (lane == 0) st_release(mine, value);
+}
+
+/* One edge of one line, entirely in registers (8.7.2.3 / 8.7.2.4; h264bsd_deblocking.c:649-1121).
+ * v[0..3] = p3..p0, v[4..7] = q0..q3.  Branch-free per lane; `any_weak` / `any_strong` are warp-uniform
+ * votes that skip the variant no lane needs.  Chroma lanes (luma == false) only ever change p0 and q0. */
+__device__ __forceinline__ void dbk_edge(int *v, int bs, uint32_t thr, uint32_t tcw, bool luma, bool any_weak, bool any_strong)
+{
+    const int p3 = v[0], p2 = v[1], p1 = v[2], p0 = v[3], q0 = v[4], q1 = v[5], q2 = v[6], q3 = v[7];
+    const int alpha = thr & 0xff, beta = (thr >> 8) & 0xff;
+    const int ad = abs(p0 - q0);
+    const bool on = bs != 0 && ad < alpha && abs(p1 - p0) < beta && abs(q1 - q0) < beta;
+    const bool ap = luma && abs(p2 - p0) < beta, aq = luma && abs(q2 - q0) < beta;
+    int n0 = p0, n1 = p1, n2 = p2, m0 = q0, m1 = q1, m2 = q2;
+    if (any_weak) {
+        const bool wk = on && bs < 4;
+        const int tc0 = (tcw >> (8 * ((bs - 1) & 3))) & 0xff;
+        const int tc = luma ? tc0 + ap + aq : tc0 + 1;
         const int d = clip3i(-tc, tc, (((q0 - p0) << 2) + (p1 - q1) + 4) >> 3);
-        pix[-step] = (uint8_t)clip255(p0 + d);
-        pix[0] = (uint8_t)clip255(q0 - d);
-    } else if (luma) {
-        const int p2 = pix[-3 * step], q2 = pix[2 * step], p3 = pix[-4 * step], q3 = pix[3 * step];
-        const bool small = abs(p0 - q0) < ((alpha >> 2) + 2);
-        if (abs(p2 - p0) < beta && small) {
-            pix[-step] = (uint8_t)((p2 + 2 * p1 + 2 * p0 + 2 * q0 + q1 + 4) >> 3);
-            pix[-2 * step] = (uint8_t)((p2 + p1 + p0 + q0 + 2) >> 2);
-            pix[-3 * step] = (uint8_t)((2 * p3 + 3 * p2 + p1 + p0 + q0 + 4) >> 3);
-        } else pix[-step] = (uint8_t)((2 * p1 + p0 + q1 + 2) >> 2);
-        if (abs(q2 - q0) < beta && small) {
-            pix[0] = (uint8_t)((p1 + 2 * p0 + 2 * q0 + 2 * q1 + q2 + 4) >> 3);
-            pix[step] = (uint8_t)((p0 + q0 + q1 + q2 + 2) >> 2);
-            pix[2 * step] = (uint8_t)((2 * q3 + 3 * q2 + q1 + q0 + p0 + 4) >> 3);
-        } else pix[0] = (uint8_t)((2 * q1 + q0 + p1 + 2) >> 2);
-    } else {
-        pix[-step] = (uint8_t)((2 * p1 + p0 + q1 + 2) >> 2);
-        pix[0] = (uint8_t)((2 * q1 + q0 + p1 + 2) >> 2);
+        const int avg = (p0 + q0 + 1) >> 1;
+        if (wk) {
+            n0 = clip255(p0 + d); m0 = clip255(q0 - d);
+            if (ap) n1 = p1 + clip3i(-tc0, tc0, (p2 + avg - (p1 << 1)) >> 1);
+            if (aq) m1 = q1 + clip3i(-tc0, tc0, (q2 + avg - (q1 << 1)) >> 1);
+        }
     }
+    if (any_strong) {
+        if (on && bs == 4) {
+            const bool small = ad < ((alpha >> 2) + 2);
+            if (ap && small) { n0 = (p2 + 2 * p1 + 2 * p0 + 2 * q0 + q1 + 4) >> 3; n1 = (p2 + p1 + p0 + q0 + 2) >> 2; n2 = (2 * p3 + 3 * p2 + p1 + p0 + q0 + 4) >> 3; }
+            else n0 = (2 * p1 + p0 + q1 + 2) >> 2;
+            if (aq && small) { m0 = (p1 + 2 * p0 + 2 * q0 + 2 * q1 + q2 + 4) >> 3; m1 = (p0 + q0 + q1 + q2 + 2) >> 2; m2 = (2 * q3 + 3 * q2 + q1 + q0 + p0 + 4) >> 3; }
+            else m0 = (2 * q1 + q0 + p1 + 2) >> 2;
+        }
+    }
+    v[1] = n2; v[2] = n1; v[3] = n0; v[4] = m0; v[5] = m1; v[6] = m2;
 }
 
 __device__ __forceinline__ bool rec_intra(const h264b200_mb_t &m) { return m.mb_class != H264B200_MB_INTER; }
@@ -90,17 +137,57 @@ __device__ __forceinline__ int dbk_bs(const h264b200_mb_t &p, int rp, const h264
     return 0;
 }
 
-__device__ void k4_macroblock(const PicJob &job, K4Warp &w, int cur, int mbx, int mby, int lane)
+/* geometry of one row walk */
+struct K4Row {
+    const PicJob *job; const h264b200_mb_t *rowrec;
+    uint8_t *Yrow, *Crow;          /* first luma / Cb sample of the macroblock row */
+    int W, CW, wm, row; size_t csize;
+};
+
+/* loads that depend on no other warp: records and the macroblock's own samples */
+__device__ __forceinline__ void k4_fetch_static(const K4Row &g, int x, int lane, K4Pre &p)
 {
-    const int W = job.wm * 16, H = job.hm * 16, CW = W >> 1;
-    const size_t ysize = (size_t)W * H, csize = ysize >> 2;
+    if (lane < 8) p.rec = __ldg(reinterpret_cast<const int4 *>(g.rowrec + x) + lane);
+    else if (lane < 16 && g.row > 0) p.rec = __ldg(reinterpret_cast<const int4 *>(g.rowrec + x - g.wm) + (lane - 8));
+    const uint8_t *Y = g.Yrow + x * 16 + (size_t)(lane >> 2) * g.W + (lane & 3) * 4;
+    p.y0 = __ldcg(reinterpret_cast<const uint32_t *>(Y));
+    p.y1 = __ldcg(reinterpret_cast<const uint32_t *>(Y + (size_t)8 * g.W));
+    const uint8_t *C = g.Crow + ((lane >> 4) ? g.csize : 0) + (size_t)((lane >> 1) & 7) * g.CW + x * 8 + (lane & 1) * 4;
+    p.c = __ldcg(reinterpret_cast<const uint32_t *>(C));
+}
+/* samples above the macroblock: final once the row above has published >= min(x+2, wm) */
+__device__ __forceinline__ void k4_fetch_top(const K4Row &g, int x, int lane, K4Pre &p)
+{
+    p.top = 0;
+    if (g.row == 0) return;
+    if (lane < 16) p.top = __ldcg(reinterpret_cast<const uint32_t *>(g.Yrow + x * 16 - (ptrdiff_t)(4 - (lane >> 2)) * g.W + (lane & 3) * 4));
+    else if (lane < 24) {
+        const int k = lane - 16, pl = k >> 2, r = (k >> 1) & 1, cw = k & 1;
+        p.top = __ldcg(reinterpret_cast<const uint32_t *>(g.Crow + (pl ? g.csize : 0) + x * 8 - (ptrdiff_t)(2 - r) * g.CW + cw * 4));
+    }
+}
+/* registers -> shared window (interior columns 4.., rows 4..; top rows 0..3) */
+__device__ __forceinline__ void k4_commit(K4Warp &w, int cur, int lane, int row, const K4Pre &p)
+{
+    if (lane < 8) reinterpret_cast<int4 *>(&w.rec[cur])[lane] = p.rec;
+    else if (lane < 16 && row > 0) reinterpret_cast<int4 *>(&w.top)[lane - 8] = p.rec;
+    *reinterpret_cast<uint32_t *>(&w.y[4 + (lane >> 2)][4 + (lane & 3) * 4]) = p.y0;
+    *reinterpret_cast<uint32_t *>(&w.y[12 + (lane >> 2)][4 + (lane & 3) * 4]) = p.y1;
+    *reinterpret_cast<uint32_t *>(&w.c[lane >> 4][4 + ((lane >> 1) & 7)][4 + (lane & 1) * 4]) = p.c;
+    if (lane < 16) *reinterpret_cast<uint32_t *>(&w.y[lane >> 2][4 + (lane & 3) * 4]) = p.top;
+    else if (lane < 24) { const int k = lane - 16; *reinterpret_cast<uint32_t *>(&w.c[k >> 2][2 + ((k >> 1) & 1)][4 + (k & 1) * 4]) = p.top; }
+}
+
+/* filter the macroblock held in the window; returns false when nothing was filtered */
+__device__ __forceinline__ bool k4_filter(K4Warp &w, int cur, int lane)
+{
     const h264b200_mb_t &q = w.rec[cur], &left = w.rec[cur ^ 1], &top = w.top;
     const int fl = q.dbk_flags;
     const bool f_left = (fl & H264B200_DBK_LEFT) && left.mb_class != H264B200_MB_MISSING;
     const bool f_top = (fl & H264B200_DBK_TOP) && top.mb_class != H264B200_MB_MISSING;
     const bool f_inner = fl & H264B200_DBK_INNER;
 
-    /* ---- 1. boundary strengths: lane = dir*16 + edge*4 + segment ---- */
+    /* ---- boundary strengths: lane = dir*16 + edge*4 + segment ---- */
     {
         const int dir = lane >> 4, e = (lane >> 2) & 3, k = lane & 3;
         const int rq = dir ? e * 4 + k : k * 4 + e;
@@ -109,8 +196,7 @@ __device__ void k4_macroblock(const PicJob &job, K4Warp &w, int cur, int mbx, in
             if (dir ? f_top : f_left) bsv = dbk_bs(dir ? top : left, dir ? 12 + k : k * 4 + 3, q, rq, true);
         } else if (f_inner) bsv = dbk_bs(q, dir ? rq - 4 : rq - 1, q, rq, false);
         w.bs[dir][e][k] = (uint8_t)bsv;
-        const unsigned any = __ballot_sync(0xffffffffu, bsv != 0);
-        if (!any) return;                              /* nothing to filter (h264bsd_deblocking.c:611) */
+        if (!__ballot_sync(0xffffffffu, bsv != 0)) return false;      /* h264bsd_deblocking.c:611 */
         if (lane < 6) {                                /* thresholds: [luma/chroma][left, top, inner] */
             const int ch = lane / 3, which = lane - ch * 3;
             int qp_q = q.qp_dbk, qp_p = which == 0 ? left.qp_dbk : which == 1 ? top.qp_dbk : q.qp_dbk;
@@ -120,70 +206,90 @@ __device__ void k4_macroblock(const PicJob &job, K4Warp &w, int cur, int mbx, in
             }
             const int av = (qp_p + qp_q + 1) >> 1;
             const int ia = clip3i(0, 51, av + q.dbk_off_a), ib = clip3i(0, 51, av + q.dbk_off_b);
-            w.alpha[ch][which] = H264_ALPHA[ia]; w.beta[ch][which] = H264_BETA[ib]; w.idxa[ch][which] = (uint8_t)ia;
+            w.thr[ch][which] = (uint32_t)H264_ALPHA[ia] | ((uint32_t)H264_BETA[ib] << 8);
+            w.tc0[ch][which] = (uint32_t)H264_TC0[ia][0] | ((uint32_t)H264_TC0[ia][1] << 8) | ((uint32_t)H264_TC0[ia][2] << 16);
         }
-    }
-
-    /* ---- 2. windows from L2: luma [-4,16) x [-4,16), chroma [-4,8) x [-4,8) ---- */
-    uint8_t *Y = job.cur + (size_t)mby * 16 * W + mbx * 16;
-    for (int i = lane; i < 100; i += 32) {
-        const int r = i / 5, cw = i - r * 5;
-        uint32_t v = 0;
-        if ((r >= 4 || mby > 0) && (cw >= 1 || mbx > 0))
-            v = __ldcg(reinterpret_cast<const uint32_t *>(Y + (ptrdiff_t)(r - 4) * W + (cw - 1) * 4));
-        *reinterpret_cast<uint32_t *>(&w.y[r][cw * 4]) = v;
-    }
-    uint8_t *C0 = job.cur + ysize + (size_t)mby * 8 * CW + mbx * 8;
-    for (int i = lane; i < 72; i += 32) {
-        const int pl = i / 36, j = i - pl * 36, r = j / 3, cw = j - r * 3;
-        uint32_t v = 0;
-        if ((r >= 4 || mby > 0) && (cw >= 1 || mbx > 0))
-            v = __ldcg(reinterpret_cast<const uint32_t *>(C0 + (pl ? csize : 0) + (ptrdiff_t)(r - 4) * CW + (cw - 1) * 4));
-        *reinterpret_cast<uint32_t *>(&w.c[pl][r][cw * 4]) = v;
     }
     __syncwarp();
 
-    /* ---- 3. filter: vertical edges (dir 0), then horizontal edges (dir 1) ---- */
+    /* ---- vertical edges (dir 0), then horizontal edges (dir 1).  Lanes 0..15 hold one luma line of 20
+     * samples in registers, lanes 16..31 one chroma line of 12 (Cb lines, then Cr lines); all four (two)
+     * edges of the line are filtered in registers, one shared-memory round trip per direction. ---- */
+    const bool luma = lane < 16;
+    const int ch = luma ? 0 : 1, pl = (lane >> 3) & 1, i = luma ? lane : (lane & 7);
+    const int n_px = luma ? 20 : 12;
 #pragma unroll
     for (int dir = 0; dir < 2; dir++) {
-        if (lane < 16) {
-            for (int e = 0; e < 4; e++) {
-                const int bsv = w.bs[dir][e][lane >> 2];
-                if (!bsv) continue;
-                const int which = e ? 2 : dir;
-                uint8_t *pix = dir ? &w.y[4 + 4 * e][4 + lane] : &w.y[4 + lane][4 + 4 * e];
-                dbk_line(pix, dir ? K4_LP : 1, bsv, w.alpha[0][which], w.beta[0][which], bsv < 4 ? H264_TC0[w.idxa[0][which]][bsv - 1] : 0, true);
+        int v[20];
+        if (dir == 0) {                                /* a row: word loads */
+            const uint32_t *src = luma ? reinterpret_cast<const uint32_t *>(&w.y[4 + i][0]) : reinterpret_cast<const uint32_t *>(&w.c[pl][4 + i][0]);
+#pragma unroll
+            for (int k = 0; k < 5; k++) {
+                const uint32_t wd = (k < 3 || luma) ? src[k] : 0u;
+                v[4 * k] = wd & 0xff; v[4 * k + 1] = (wd >> 8) & 0xff; v[4 * k + 2] = (wd >> 16) & 0xff; v[4 * k + 3] = wd >> 24;
             }
+        } else {                                       /* a column: byte loads, consecutive lanes hit consecutive bytes */
+            const uint8_t *src = luma ? &w.y[0][4 + i] : &w.c[pl][0][4 + i];
+            const int pitch = luma ? K4_LP : K4_CP;
+#pragma unroll
+            for (int k = 0; k < 20; k++) v[k] = (k < 12 || luma) ? src[k * pitch] : 0;
+        }
+        const uint32_t thr_e0 = w.thr[ch][dir], thr_in = w.thr[ch][2], tc_e0 = w.tc0[ch][dir], tc_in = w.tc0[ch][2];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            /* chroma: luma edges 0 and 2 are its edges at samples 0 and 4, i.e. v[4..] and v[8..] of a 12-sample line */
+            int bsv = w.bs[dir][e][luma ? (i >> 2) : (i >> 1)];
+            if (!luma && (e & 1)) bsv = 0;
+            const unsigned weak = __ballot_sync(0xffffffffu, bsv != 0 && bsv < 4), strong = __ballot_sync(0xffffffffu, bsv == 4);
+            if (!(weak | strong)) continue;            /* warp-uniform */
+            if (e == 0) dbk_edge(v, bsv, thr_e0, tc_e0, luma, weak != 0, strong != 0);
+            else if (e == 2) {
+                /* luma line: samples 8..15; chroma line: samples 4..11 -> same code on a shifted view */
+                int t[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) t[k] = luma ? v[8 + k] : v[4 + k];
+                dbk_edge(t, bsv, thr_in, tc_in, luma, weak != 0, strong != 0);
+#pragma unroll
+                for (int k = 1; k < 7; k++) { if (luma) v[8 + k] = t[k]; else v[4 + k] = t[k]; }
+            } else dbk_edge(v + 4 * e, bsv, thr_in, tc_in, luma, weak != 0, strong != 0);
+        }
+        if (dir == 0) {
+            uint32_t *dst = luma ? reinterpret_cast<uint32_t *>(&w.y[4 + i][0]) : reinterpret_cast<uint32_t *>(&w.c[pl][4 + i][0]);
+#pragma unroll
+            for (int k = 0; k < 5; k++)
+                if (k < 3 || luma) dst[k] = (uint32_t)v[4 * k] | ((uint32_t)v[4 * k + 1] << 8) | ((uint32_t)v[4 * k + 2] << 16) | ((uint32_t)v[4 * k + 3] << 24);
         } else {
-            const int pl = (lane - 16) >> 3, i = lane & 7;
-            for (int e = 0; e < 4; e += 2) {
-                const int bsv = w.bs[dir][e][i >> 1];
-                if (!bsv) continue;
-                const int which = e ? 2 : dir;
-                uint8_t *pix = dir ? &w.c[pl][4 + 2 * e][4 + i] : &w.c[pl][4 + i][4 + 2 * e];
-                dbk_line(pix, dir ? K4_CP : 1, bsv, w.alpha[1][which], w.beta[1][which], bsv < 4 ? H264_TC0[w.idxa[1][which]][bsv - 1] : 0, false);
-            }
+            uint8_t *dst = luma ? &w.y[0][4 + i] : &w.c[pl][0][4 + i];
+            const int pitch = luma ? K4_LP : K4_CP;
+#pragma unroll
+            for (int k = 1; k < 19; k++) if (k < n_px) dst[k * pitch] = (uint8_t)v[k];
         }
         __syncwarp();
     }
+    return true;
+}
 
-    /* ---- 4. write back: rows -3..-1 x cols 0..15, rows 0..15 x cols -4..15 ---- */
+/* window -> frame: rows -3..-1 x cols 0..15, rows 0..15 x cols -4..15 (chroma: row -1; rows 0..7 x cols -4..7) */
+__device__ __forceinline__ void k4_writeback(const K4Row &g, K4Warp &w, int x, int lane)
+{
+    uint8_t *Y = g.Yrow + x * 16;
     for (int i = lane; i < 92; i += 32) {
         int r, cw;
-        if (i < 12) { r = 1 + i / 4; cw = 1 + (i & 3); if (mby == 0) continue; }
-        else { const int j = i - 12; r = 4 + j / 5; cw = j % 5; if (cw == 0 && mbx == 0) continue; }
-        *reinterpret_cast<uint32_t *>(Y + (ptrdiff_t)(r - 4) * W + (cw - 1) * 4) = *reinterpret_cast<const uint32_t *>(&w.y[r][cw * 4]);
+        if (i < 12) { r = 1 + i / 4; cw = 1 + (i & 3); if (g.row == 0) continue; }
+        else { const int j = i - 12; r = 4 + j / 5; cw = j % 5; if (cw == 0 && x == 0) continue; }
+        *reinterpret_cast<uint32_t *>(Y + (ptrdiff_t)(r - 4) * g.W + (cw - 1) * 4) = *reinterpret_cast<const uint32_t *>(&w.y[r][cw * 4]);
     }
-    for (int i = lane; i < 56; i += 32) {
-        const int pl = i / 28, j = i - pl * 28;
+    uint8_t *C0 = g.Crow + x * 8;
+    for (int i = lane; i < 52; i += 32) {
+        const int pl = i / 26, j = i - pl * 26;
         int r, cw;
-        if (j < 4) { r = 2 + (j >> 1); cw = 1 + (j & 1); if (mby == 0) continue; }      /* rows -2,-1 */
-        else { const int k = j - 4; r = 4 + k / 3; cw = k % 3; if (cw == 0 && mbx == 0) continue; }
-        *reinterpret_cast<uint32_t *>(C0 + (pl ? csize : 0) + (ptrdiff_t)(r - 4) * CW + (cw - 1) * 4) = *reinterpret_cast<const uint32_t *>(&w.c[pl][r][cw * 4]);
+        if (j < 2) { r = 3; cw = 1 + j; if (g.row == 0) continue; }                       /* row -1 */
+        else { const int k = j - 2; r = 4 + k / 3; cw = k % 3; if (cw == 0 && x == 0) continue; }
+        *reinterpret_cast<uint32_t *>(C0 + (pl ? g.csize : 0) + (ptrdiff_t)(r - 4) * g.CW + (cw - 1) * 4) = *reinterpret_cast<const uint32_t *>(&w.c[pl][r][cw * 4]);
     }
 }
 
-__global__ void __launch_bounds__(K4_WARPS * 32) k4_deblock(Batch b)
+__global__ void __launch_bounds__(K4_WARPS * 32, 6) k4_deblock(Batch b)
 {
     __shared__ K4Warp sm[K4_WARPS];
     const int lane = threadIdx.x & 31;
@@ -197,19 +303,67 @@ __global__ void __launch_bounds__(K4_WARPS * 32) k4_deblock(Batch b)
         const int row = t / b.n_jobs;
         const PicJob &job = b.jobs[t - (uint32_t)row * b.n_jobs];
         if (row >= job.hm || !job.any_deblock) continue;
-        const int wm = job.wm;
-        const h264b200_mb_t *rowrec = job.mbs + (size_t)row * wm;
+        K4Row g;
+        g.job = &job; g.wm = job.wm; g.row = row; g.W = job.wm * 16; g.CW = g.W >> 1;
+        g.csize = (size_t)g.W * (job.hm * 16) >> 2;
+        g.rowrec = job.mbs + (size_t)row * g.wm;
+        g.Yrow = job.cur + (size_t)row * 16 * g.W;
+        g.Crow = job.cur + (size_t)g.W * (job.hm * 16) + (size_t)row * 8 * g.CW;
         int32_t *prog = job.progress + job.hm;           /* second half: the first hm counters belong to K3 */
+        const int32_t *above = prog + row - 1;
+        int seen = row > 0 ? 0 : 0x7fffffff;
+        const int wm = g.wm;
+
+        const bool tr = b.trace && (t - (uint32_t)row * b.n_jobs) == 0 && lane == 0;
+        if (tr) b.trace[256 + row * 4] = gtime();
+        /* prologue: macroblock 0 straight into the window */
+        K4Pre p;
+        k4_fetch_static(g, 0, lane, p);
+        wf_wait2(above, min(2, wm), seen, lane);
+        k4_fetch_top(g, 0, lane, p);
+        __syncwarp();
+        k4_commit(w, 0, lane, row, p);
         int cur = 0;
+        if (tr) b.trace[256 + row * 4 + 1] = gtime();
         for (int x = 0; x < wm; x++, cur ^= 1) {
-            if (lane < 8) reinterpret_cast<int4 *>(&w.rec[cur])[lane] = __ldg(reinterpret_cast<const int4 *>(rowrec + x) + lane);
-            else if (lane < 16 && row > 0) reinterpret_cast<int4 *>(&w.top)[lane - 8] = __ldg(reinterpret_cast<const int4 *>(rowrec + x - wm) + (lane - 8));
-            __syncwarp();
-            if (w.rec[cur].dbk_flags && w.rec[cur].mb_class != H264B200_MB_MISSING) {
-                wf_wait(prog, row, min(x + 2, wm));
-                k4_macroblock(job, w, cur, x, row, lane);
+            if (tr && x == wm / 2) b.trace[256 + row * 4 + 2] = gtime();
+            /* ---- everything macroblock x+1 needs goes in flight now, while x is filtered ---- */
+            const bool more = x + 1 < wm;
+            bool top_ahead = false;
+            int polled = 0;
+            if (more) {
+                k4_fetch_static(g, x + 1, lane, p);
+                top_ahead = seen >= min(x + 3, wm);
+                if (top_ahead) k4_fetch_top(g, x + 1, lane, p);
             }
-            wf_publish(prog, row, x + 1, lane);
+            const bool poll = seen < wm;                   /* refresh `seen` once per macroblock, without waiting for it here */
+            if (poll && lane == 0) polled = ld_acquire(above);
+            __syncwarp();
+            const bool active = w.rec[cur].dbk_flags && w.rec[cur].mb_class != H264B200_MB_MISSING;
+            if (active) {
+                const int need = min(x + 2, wm);
+                if (seen < need) {
+                    seen = __shfl_sync(0xffffffffu, polled, 0);
+                    wf_wait2(above, need, seen, lane);        /* only a row running right at the wavefront spins here */
+                }
+                if (k4_filter(w, cur, lane)) k4_writeback(g, w, x, lane);
+            }
+            /* the release (a memory barrier over the write-back) is paid once per K4_PUBLISH macroblocks */
+            if (((x + 1) % K4_PUBLISH) == 0 || !more) wf_publish2(prog + row, x + 1, lane);
+            if (more) {
+                /* carry the right 4 columns over as the next left halo, then land the prefetched macroblock */
+                uint32_t carry;
+                if (lane < 16) carry = *reinterpret_cast<const uint32_t *>(&w.y[4 + lane][16]);
+                else carry = *reinterpret_cast<const uint32_t *>(&w.c[(lane >> 3) & 1][4 + (lane & 7)][8]);
+                __syncwarp();
+                if (lane < 16) *reinterpret_cast<uint32_t *>(&w.y[4 + lane][0]) = carry;
+                else *reinterpret_cast<uint32_t *>(&w.c[(lane >> 3) & 1][4 + (lane & 7)][0]) = carry;
+                if (poll) seen = max(seen, __shfl_sync(0xffffffffu, polled, 0));
+                if (!top_ahead) { wf_wait2(above, min(x + 3, wm), seen, lane); k4_fetch_top(g, x + 1, lane, p); }
+                k4_commit(w, cur ^ 1, lane, row, p);
+            }
+            __syncwarp();
         }
+        if (tr) b.trace[256 + row * 4 + 3] = gtime();
     }
 }

@@ -31,6 +31,7 @@ struct Batch {
     uint32_t total_mbs;
     uint32_t *tickets;             /* [0]: K3 ticket counter, [1]: K4 ticket counter */
     uint32_t *error_flags;         /* bit 0: residual out of [-512,511] */
+    unsigned long long *trace;     /* debug (H264B200_TRACE=1): per-row globaltimer stamps of job 0, else NULL */
 };
 
 __device__ __forceinline__ int clip255(int v) { return min(max(v, 0), 255); }
@@ -56,3 +57,5 @@ __device__ __forceinline__ uint32_t slot_index(uint32_t mask, int blk)
     if (blk >= 16 && (mask & H264B200_RESID_CHROMA_DC)) n++;
     return n;
 }
+
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
