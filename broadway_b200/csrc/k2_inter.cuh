@@ -7,18 +7,30 @@
  * (:110-476), the edge-clamped block fetch h264bsdFillBlock (:2222-2314) and
  * h264bsdWriteOutputBlocks (h264bsd_image.c:171-343).
  *
- * One CTA (128 threads) per macroblock.  Prediction is per-sample independent,
- * so every partition shape is handled as sixteen 4x4 blocks with their own
- * vector (the record stores final vectors per 4x4 block):
- *   1. the 16 (9x9 luma) and 32 (3x3 chroma) reference windows, apron included,
- *      are staged into shared memory with coordinate clamping (= the reference's
- *      out-of-frame behaviour);
- *   2. each thread produces two luma samples and one chroma sample from shared
- *      memory: 6-tap (1,-5,20,20,-5,1) half samples with (x+16)>>5, centre sample
- *      from unclipped intermediates with (x+512)>>10, quarter samples as rounded
- *      averages (8.4.2.2.1); chroma bilinear 1/8 pel (8.4.2.2.2);
- *   3. residual (already transformed by K1) is added with clipping and the
- *      macroblock is written from shared memory with 16-byte stores.
+ * ONE THREAD PER 4x4 LUMA BLOCK, everything in registers, no shared memory.
+ * Prediction is per-sample independent, so every partition shape is sixteen
+ * 4x4 blocks with their own vector (the record stores final vectors per 4x4
+ * block).  A half-warp is one macroblock (lane & 15 = raster block index), a
+ * warp two horizontally adjacent macroblocks, so each luma row store of a warp
+ * is one full 32-byte sector.  Per thread:
+ *   - the 9x9 reference window is fetched as 9 rows x 3 aligned 32-bit words
+ *     through the read-only path (windows of neighbouring blocks overlap in L1)
+ *     and byte-aligned with funnel shifts; windows that leave the picture take a
+ *     per-sample clamped path (= the reference's coordinate clamp);
+ *   - horizontal 6-tap sums (1,-5,20,20,-5,1) of a row are eight dp4a on packed
+ *     bytes; vertical 6-tap sums of raw samples run two samples per instruction
+ *     on biased 16-bit lanes; the centre sample j is the vertical filter over the
+ *     unclipped horizontal sums with (x+512)>>10 (8.4.2.2.1);
+ *   - the 16 fractional positions are ONE formula: out = (S*(3-n)+1)>>1 with S
+ *     the sum of the n in {1,2} operands the position uses among {integer
+ *     sample G', horizontal half b', vertical half h', centre j}, where the
+ *     primed operands sit one row lower / one column right when the fraction is
+ *     3/4.  Which operand families a warp needs at all is decided by warp votes,
+ *     so streams with coherent motion skip most of the arithmetic;
+ *   - chroma is the 1/8-pel bilinear blend of a 3x3 window (8.4.2.2.2), two
+ *     2x2 blocks (Cb, Cr) per thread;
+ *   - the residual K1 left in the block's coefficient slot is added with
+ *     clipping and the block is stored: 4 x 32-bit luma, 4 x 16-bit chroma.
  * HBM per inter macroblock: 384 B reference (unique) + 384 B written + 128 B
  * record + 32 B per coded block.
  */
@@ -26,114 +38,212 @@
 #include "k_common.cuh"
 
 #define K2_THREADS 128
-#define K2_LP 12                     /* luma window pitch (9 columns used) */
 
-struct __align__(16) K2Smem {
-    h264b200_mb_t rec;
-    uint8_t luma[16][9][K2_LP];
-    uint8_t chroma[2][16][3][4];
-    __align__(16) uint8_t out_y[16][16];
-    __align__(16) uint8_t out_c[2][8][8];
-};
+__device__ __forceinline__ int tap6(int a, int b, int c, int d, int e, int f) { return (a + f) - 5 * (b + e) + 20 * (c + d); }
 
-__device__ __forceinline__ int tap6(int a, int b, int c, int d, int e, int f) { return a - 5 * b + 20 * c + 20 * d - 5 * e + f; }
-
-/* t: the 9x9 window of one 4x4 block; integer sample G of output (lx,ly) is t[ly+2][lx+2] */
-__device__ __forceinline__ int luma_sample(const uint8_t (*t)[K2_LP], int lx, int ly, int fx, int fy)
+/* four unsigned bytes of a times four signed bytes of b, accumulated (dp4a.u32.s32) */
+__device__ __forceinline__ int dp4a_us(uint32_t a, int b, int c)
 {
-    const int x = lx + 2, y = ly + 2;
-#define PX(dx, dy) ((int)t[y + (dy)][x + (dx)])
-#define HB1(dy) tap6(PX(-2, dy), PX(-1, dy), PX(0, dy), PX(1, dy), PX(2, dy), PX(3, dy))
-#define VH1(dx) tap6(PX(dx, -2), PX(dx, -1), PX(dx, 0), PX(dx, 1), PX(dx, 2), PX(dx, 3))
-    if ((fx | fy) == 0) return PX(0, 0);
-    if (fy == 0) {                                   /* a, b, c */
-        int b = clip255((HB1(0) + 16) >> 5);
-        return fx == 2 ? b : (b + (fx == 1 ? PX(0, 0) : PX(1, 0)) + 1) >> 1;
-    }
-    if (fx == 0) {                                   /* d, h, n */
-        int h = clip255((VH1(0) + 16) >> 5);
-        return fy == 2 ? h : (h + (fy == 1 ? PX(0, 0) : PX(0, 1)) + 1) >> 1;
-    }
-    if (fx == 2 || fy == 2) {                        /* f, i, j, k, q: all need the centre sample j */
-        int j = clip255((tap6(HB1(-2), HB1(-1), HB1(0), HB1(1), HB1(2), HB1(3)) + 512) >> 10);
-        if (fx == 2 && fy == 2) return j;
-        if (fx == 2) return (j + clip255((HB1(fy == 1 ? 0 : 1) + 16) >> 5) + 1) >> 1;      /* f: b above, q: s below */
-        return (j + clip255(((fx == 1 ? VH1(0) : VH1(1)) + 16) >> 5) + 1) >> 1;            /* i: h left, k: m right */
-    }
-    {                                                /* e, g, p, r: diagonal quarter samples */
-        int b = clip255((HB1(fy == 1 ? 0 : 1) + 16) >> 5);
-        int h = clip255(((fx == 1 ? VH1(0) : VH1(1)) + 16) >> 5);
-        return (b + h + 1) >> 1;
-    }
-#undef PX
-#undef HB1
-#undef VH1
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+/* clamped single-sample fetch: the reference's out-of-picture behaviour (h264bsdFillBlock) */
+__device__ __forceinline__ uint32_t ref_px(const uint8_t *pl, int w, int h, int x, int y)
+{
+    x = min(max(x, 0), w - 1); y = min(max(y, 0), h - 1);
+    return __ldg(pl + (size_t)y * w + x);
 }
 
 __global__ void __launch_bounds__(K2_THREADS) k2_inter(Batch b)
 {
-    __shared__ K2Smem s;
-    const int tid = threadIdx.x;
-    const uint32_t g = blockIdx.x;
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, blk = lane & 15, bx = blk & 3, by = blk >> 2;
+    const uint32_t g0 = (blockIdx.x * K2_THREADS + threadIdx.x) >> 4;        /* batch-wide macroblock index */
+    const bool in_range = g0 < b.total_mbs;
+    const uint32_t g = in_range ? g0 : b.total_mbs - 1;
     const PicJob &job = b.jobs[find_job(b, g)];
     const uint32_t mbi = g - job.mb_base;
     const h264b200_mb_t *mb = job.mbs + mbi;
-    if (__ldg(reinterpret_cast<const uint8_t *>(mb)) != H264B200_MB_INTER) return;      /* CTA-uniform */
-    if (tid < 8) reinterpret_cast<int4 *>(&s.rec)[tid] = __ldg(reinterpret_cast<const int4 *>(mb) + tid);
-    __syncthreads();
+    const uint32_t *rec = reinterpret_cast<const uint32_t *>(mb);
+    const bool inter = in_range && (__ldg(rec) & 0xff) == H264B200_MB_INTER;
+    if (!__any_sync(FULL, inter)) return;
 
     const int W = job.wm * 16, H = job.hm * 16, CW = W >> 1, CH = H >> 1;
     const int mbx = mbi % job.wm, mby = mbi / job.wm;
-    const size_t ysize = (size_t)W * H, csize = (size_t)CW * CH;
+    const size_t ysize = (size_t)W * H, csize = ysize >> 2;
+    const uint32_t mvw = __ldg(rec + 16 + blk);                              /* mv[blk] = {hor, ver} */
+    const int mvx = (int)(short)(mvw & 0xffff), mvy = (int)mvw >> 16;
+    const uint32_t slots = __ldg(rec + 6);                                   /* ref_slot[4] */
+    const uint8_t *ref = job.frames + (size_t)((slots >> (8 * ((by >> 1) * 2 + (bx >> 1)))) & 0xff) * job.frame_bytes;
+    const uint32_t mask = __ldg(rec + 4);
+    const int16_t *coef = job.coef + (size_t)__ldg(rec + 3) * 16;
+    const int fx = mvx & 3, fy = mvy & 3;
 
-    /* ---- 1. stage reference windows (coordinate clamp = h264bsdFillBlock) ---- */
-    for (int e = tid; e < 16 * 81; e += K2_THREADS) {
-        int blk = e / 81, r = e - blk * 81, ry = r / 9, rx = r - ry * 9;
-        int bx = blk & 3, by = blk >> 2;
-        const uint8_t *ref = job.frames + (size_t)s.rec.ref_slot[(by >> 1) * 2 + (bx >> 1)] * job.frame_bytes;
-        int x = mbx * 16 + bx * 4 + (s.rec.mv[blk][0] >> 2) - 2 + rx;
-        int y = mby * 16 + by * 4 + (s.rec.mv[blk][1] >> 2) - 2 + ry;
-        x = min(max(x, 0), W - 1); y = min(max(y, 0), H - 1);
-        s.luma[blk][ry][rx] = __ldg(ref + (size_t)y * W + x);
-    }
-    for (int e = tid; e < 2 * 16 * 9; e += K2_THREADS) {
-        int pl = e / 144, r0 = e - pl * 144, blk = r0 / 9, r = r0 - blk * 9, ry = r / 3, rx = r - ry * 3;
-        int bx = blk & 3, by = blk >> 2;
-        const uint8_t *ref = job.frames + (size_t)s.rec.ref_slot[(by >> 1) * 2 + (bx >> 1)] * job.frame_bytes + ysize + (pl ? csize : 0);
-        int x = mbx * 8 + bx * 2 + (s.rec.mv[blk][0] >> 3) + rx;
-        int y = mby * 8 + by * 2 + (s.rec.mv[blk][1] >> 3) + ry;
-        x = min(max(x, 0), CW - 1); y = min(max(y, 0), CH - 1);
-        s.chroma[pl][blk][ry][rx] = __ldg(ref + (size_t)y * CW + x);
-    }
-    __syncthreads();
-
-    /* ---- 2. interpolate + residual ---- */
-    const uint32_t mask = s.rec.resid_mask;
-    const int16_t *coef = job.coef + (size_t)s.rec.coef_offset * 16;
-#pragma unroll
-    for (int pass = 0; pass < 2; pass++) {           /* a warp covers two whole 4x4 blocks: <= 2-way divergence */
-        int blk = pass * 8 + (tid >> 4), p = tid & 15, lx = p & 3, ly = p >> 2;
-        int v = luma_sample(s.luma[blk], lx, ly, s.rec.mv[blk][0] & 3, s.rec.mv[blk][1] & 3);
-        int bi = (blk & 1) | ((blk & 2) << 1) | ((blk & 4) >> 1) | (blk & 8);            /* raster -> luma4x4BlkIdx */
-        if ((mask >> bi) & 1) v = clip255(v + coef[slot_index(mask, bi) * 16 + p]);
-        s.out_y[(blk >> 2) * 4 + ly][(blk & 3) * 4 + lx] = (uint8_t)v;
-    }
+    /* ================================ luma ================================ */
+    uint32_t out_rows[4];
     {
-        int pl = tid >> 6, q = tid & 63, blk = q >> 2, x = q & 1, y = (q >> 1) & 1;
-        int fx = s.rec.mv[blk][0] & 7, fy = s.rec.mv[blk][1] & 7;
-        const uint8_t (*t)[4] = s.chroma[pl][blk];
-        int v = ((8 - fx) * (8 - fy) * t[y][x] + fx * (8 - fy) * t[y][x + 1] + (8 - fx) * fy * t[y + 1][x] + fx * fy * t[y + 1][x + 1] + 32) >> 6;
-        int bx = blk & 3, by = blk >> 2, cb = 16 + 4 * pl + (by >> 1) * 2 + (bx >> 1);
-        if ((mask >> cb) & 1) v = clip255(v + coef[slot_index(mask, cb) * 16 + ((by & 1) * 2 + y) * 4 + (bx & 1) * 2 + x]);
-        s.out_c[pl][by * 2 + y][bx * 2 + x] = (uint8_t)v;
-    }
-    __syncthreads();
+        const int x0 = mbx * 16 + bx * 4 + (mvx >> 2) - 2, y0 = mby * 16 + by * 4 + (mvy >> 2) - 2;   /* window origin */
+        /* which operand families does this position use (see header) */
+        const bool useJ = inter && ((fx == 2 && fy != 0) || (fy == 2 && fx != 0));
+        const bool useB = inter && fx != 0 && fy != 2;
+        const bool useH = inter && fy != 0 && fx != 2;
+        const bool useG = inter && !useJ && !(useB && useH) && !(fx == 2) && !(fy == 2);
+        const int n_ops = (int)useJ + (int)useB + (int)useH + (int)useG;      /* 1 or 2 */
+        const bool anyJ = __any_sync(FULL, useJ), anyB = __any_sync(FULL, useB), anyH = __any_sync(FULL, useH);
+        const int dn = fy == 3, rt = fx == 3;
 
-    /* ---- 3. write the macroblock: 16-byte luma rows, 8-byte chroma rows ---- */
-    if (tid < 16) {
-        *reinterpret_cast<int4 *>(job.cur + (size_t)(mby * 16 + tid) * W + mbx * 16) = *reinterpret_cast<const int4 *>(s.out_y[tid]);
-    } else if (tid < 32) {
-        int pl = (tid - 16) >> 3, r = tid & 7;
-        *reinterpret_cast<int2 *>(job.cur + ysize + (pl ? csize : 0) + (size_t)(mby * 8 + r) * CW + mbx * 8) = *reinterpret_cast<const int2 *>(s.out_c[pl][r]);
+        /* ---- window rows as three byte-aligned words: bytes 0..8 of the row ---- */
+        uint32_t r0[9], r1[9], r2[9];
+        const int sh = x0 & 3, xa = x0 - sh;
+        const bool inside = inter && xa >= 0 && xa + 12 <= W && y0 >= 0 && y0 + 9 <= H;
+        if (inside) {
+            const uint8_t *p = ref + (size_t)y0 * W + xa;
+#pragma unroll
+            for (int r = 0; r < 9; r++) {
+                const uint32_t *q = reinterpret_cast<const uint32_t *>(p + (size_t)r * W);
+                const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2);
+                r0[r] = __funnelshift_r(w0, w1, 8 * sh); r1[r] = __funnelshift_r(w1, w2, 8 * sh); r2[r] = w2 >> (8 * sh);
+            }
+        } else if (inter) {
+#pragma unroll 1
+            for (int r = 0; r < 9; r++) {
+                uint32_t a = 0, c = 0;
+                for (int k = 0; k < 4; k++) { a |= ref_px(ref, W, H, x0 + k, y0 + r) << (8 * k); c |= ref_px(ref, W, H, x0 + 4 + k, y0 + r) << (8 * k); }
+                const uint32_t e = ref_px(ref, W, H, x0 + 8, y0 + r);
+                /* dynamic row index into a register array is not possible: scatter with a switch */
+#pragma unroll
+                for (int k = 0; k < 9; k++) if (k == r) { r0[k] = a; r1[k] = c; r2[k] = e; }
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < 9; r++) { r0[r] = r1[r] = r2[r] = 0; }
+        }
+
+        /* ---- the 4 samples at columns x+rt .. x+rt+3 of every window row (G' and the inputs of h') ---- */
+        uint32_t cw[9];
+#pragma unroll
+        for (int r = 0; r < 9; r++) cw[r] = __funnelshift_r(r0[r], r1[r], 8 * (2 + rt));
+
+        /* ---- horizontal 6-tap sums: hs[r][k] for output column k of window row r ---- */
+        int hs[9][4];
+        if (anyB || anyJ) {
+            const int T0 = 0x1414fb01, T1 = 0x000001fb;      /* (1,-5,20,20) and (-5,1,0,0) as signed bytes, low byte first */
+#pragma unroll
+            for (int r = 0; r < 9; r++) {
+                if (!anyJ && (r < 2 || r > 6)) { hs[r][0] = hs[r][1] = hs[r][2] = hs[r][3] = 0; continue; }
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const uint32_t lo = k ? __funnelshift_r(r0[r], r1[r], 8 * k) : r0[r];
+                    const uint32_t hi = k ? __funnelshift_r(r1[r], r2[r], 8 * k) : r1[r];
+                    hs[r][k] = dp4a_us(lo, T0, dp4a_us(hi, T1, 0));
+                }
+            }
+        }
+
+        /* ---- per output row: operands and the final blend ---- */
+#pragma unroll
+        for (int py = 0; py < 4; py++) {
+            int bq[4] = {0, 0, 0, 0}, hq[4] = {0, 0, 0, 0}, jq[4] = {0, 0, 0, 0};
+            if (anyB) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) bq[k] = clip255(((dn ? hs[py + 3][k] : hs[py + 2][k]) + 16) >> 5);
+            }
+            if (anyH) {
+                /* vertical 6-tap over raw samples, two samples per instruction on biased 16-bit lanes:
+                 * (a+f) + 20(c+d) + 2560 - 5(b+e) stays within [0, 65535] per lane */
+#pragma unroll
+                for (int half = 0; half < 2; half++) {
+                    uint32_t e[6];
+#pragma unroll
+                    for (int t = 0; t < 6; t++) e[t] = (cw[py + t] >> (8 * half)) & 0x00ff00ffu;
+                    const uint32_t s = (e[0] + e[5] + 0x0a000a00u) + 20u * (e[2] + e[3]) - 5u * (e[1] + e[4]);
+                    hq[half] = clip255(((int)(s & 0xffff) - 2560 + 16) >> 5);
+                    hq[half + 2] = clip255(((int)(s >> 16) - 2560 + 16) >> 5);
+                }
+            }
+            if (anyJ) {
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    jq[k] = clip255((tap6(hs[py][k], hs[py + 1][k], hs[py + 2][k], hs[py + 3][k], hs[py + 4][k], hs[py + 5][k]) + 512) >> 10);
+            }
+            const uint32_t gw = dn ? cw[py + 3] : cw[py + 2];
+            uint32_t pk = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                int s = 0;
+                if (useG) s += (gw >> (8 * k)) & 0xff;
+                if (useB) s += bq[k];
+                if (useH) s += hq[k];
+                if (useJ) s += jq[k];
+                const int v = (s * (3 - n_ops) + 1) >> 1;
+                pk |= (uint32_t)v << (8 * k);
+            }
+            out_rows[py] = pk;
+        }
+    }
+
+    /* ---- luma residual + store ---- */
+    if (inter) {
+        const int bi = (blk & 1) | ((blk & 2) << 1) | ((blk & 4) >> 1) | (blk & 8);            /* raster -> luma4x4BlkIdx */
+        uint8_t *dst = job.cur + (size_t)(mby * 16 + by * 4) * W + mbx * 16 + bx * 4;
+        if ((mask >> bi) & 1) {
+            const int4 *rs = reinterpret_cast<const int4 *>(coef + slot_index(mask, bi) * 16);
+            const int4 lo = *rs, hi = *(rs + 1);
+            const int rw[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+            for (int py = 0; py < 4; py++) {
+                const uint32_t p = out_rows[py];
+                const int v0 = clip255((int)(p & 0xff) + (int)(short)(rw[2 * py] & 0xffff)), v1 = clip255((int)((p >> 8) & 0xff) + (rw[2 * py] >> 16));
+                const int v2 = clip255((int)((p >> 16) & 0xff) + (int)(short)(rw[2 * py + 1] & 0xffff)), v3 = clip255((int)(p >> 24) + (rw[2 * py + 1] >> 16));
+                out_rows[py] = (uint32_t)v0 | ((uint32_t)v1 << 8) | ((uint32_t)v2 << 16) | ((uint32_t)v3 << 24);
+            }
+        }
+#pragma unroll
+        for (int py = 0; py < 4; py++) *reinterpret_cast<uint32_t *>(dst + (size_t)py * W) = out_rows[py];
+    }
+
+    /* ================================ chroma ================================ */
+    if (inter) {
+        const int xc = mbx * 8 + bx * 2 + (mvx >> 3), yc = mby * 8 + by * 2 + (mvy >> 3);
+        const int cfx = mvx & 7, cfy = mvy & 7;
+        const int w00 = (8 - cfx) * (8 - cfy), w01 = cfx * (8 - cfy), w10 = (8 - cfx) * cfy, w11 = cfx * cfy;
+        const int sh = xc & 3, xa = xc - sh;
+        const bool inside = xa >= 0 && xa + 8 <= CW && yc >= 0 && yc + 3 <= CH;
+        const int cb0 = 16 + (by >> 1) * 2 + (bx >> 1);                      /* Cb 4x4 block holding this 2x2 */
+        const int roff = (by & 1) * 8 + (bx & 1) * 2;                        /* its position inside that block */
+#pragma unroll
+        for (int pl = 0; pl < 2; pl++) {
+            const uint8_t *rp = ref + ysize + (pl ? csize : 0);
+            uint32_t t[3];                                                   /* bytes 0..2 of each window row */
+            if (inside) {
+#pragma unroll
+                for (int r = 0; r < 3; r++) {
+                    const uint32_t *q = reinterpret_cast<const uint32_t *>(rp + (size_t)(yc + r) * CW + xa);
+                    t[r] = __funnelshift_r(__ldg(q), __ldg(q + 1), 8 * sh);
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < 3; r++)
+                    t[r] = ref_px(rp, CW, CH, xc, yc + r) | (ref_px(rp, CW, CH, xc + 1, yc + r) << 8) | (ref_px(rp, CW, CH, xc + 2, yc + r) << 16);
+            }
+            const int cb = cb0 + 4 * pl;
+            const bool has_r = (mask >> cb) & 1;
+            const int16_t *rs = coef + slot_index(mask, cb) * 16 + roff;
+            uint8_t *dst = job.cur + ysize + (pl ? csize : 0) + (size_t)(mby * 8 + by * 2) * CW + mbx * 8 + bx * 2;
+#pragma unroll
+            for (int y = 0; y < 2; y++) {
+                const int a0 = t[y] & 0xff, a1 = (t[y] >> 8) & 0xff, a2 = (t[y] >> 16) & 0xff;
+                const int c0 = t[y + 1] & 0xff, c1 = (t[y + 1] >> 8) & 0xff, c2 = (t[y + 1] >> 16) & 0xff;
+                int v0 = (w00 * a0 + w01 * a1 + w10 * c0 + w11 * c1 + 32) >> 6;
+                int v1 = (w00 * a1 + w01 * a2 + w10 * c1 + w11 * c2 + 32) >> 6;
+                if (has_r) {
+                    const int rr = *reinterpret_cast<const int *>(rs + 4 * y);
+                    v0 = clip255(v0 + (int)(short)(rr & 0xffff)); v1 = clip255(v1 + (rr >> 16));
+                }
+                *reinterpret_cast<uint16_t *>(dst + (size_t)y * CW) = (uint16_t)(v0 | (v1 << 8));
+            }
+        }
     }
 }
