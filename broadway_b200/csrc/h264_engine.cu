@@ -267,6 +267,8 @@ static uint32_t submit_locked(h264b200_engine *e)
 
     Batch b;
     b.jobs = d_jobs; b.n_jobs = (int32_t)n; b.max_hm = pl.max_hm; b.total_mbs = mb_base;
+    b.uniform_mbs = e->queue[0]->inst->n_mbs;
+    for (PicBuf *p : e->queue) if (p->inst->n_mbs != b.uniform_mbs) b.uniform_mbs = 0;
     b.tickets = (uint32_t *)d_ctrl; b.error_flags = e->d_err; b.trace = e->trace_left > 0 ? e->d_trace : nullptr;
 
     cudaEventRecord(e->ev_h2d, e->s_h2d);

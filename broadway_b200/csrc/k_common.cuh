@@ -29,6 +29,7 @@ struct Batch {
     int32_t n_jobs;
     int32_t max_hm;                /* max rows over the batch */
     uint32_t total_mbs;
+    uint32_t uniform_mbs;          /* macroblocks per picture when every picture of the batch has the same size, else 0 */
     uint32_t *tickets;             /* [0]: K3 ticket counter, [1]: K4 ticket counter */
     uint32_t *error_flags;         /* bit 0: residual out of [-512,511] */
     unsigned long long *trace;     /* debug (H264B200_TRACE=1): per-row globaltimer stamps of job 0, else NULL */
@@ -40,6 +41,7 @@ __device__ __forceinline__ int clip3i(int lo, int hi, int v) { return min(max(v,
 /* locate (job, local mb index) of batch-wide macroblock g by binary search on mb_base */
 __device__ __forceinline__ int find_job(const Batch &b, uint32_t g)
 {
+    if (b.uniform_mbs) return (int)(g / b.uniform_mbs);
     int lo = 0, hi = b.n_jobs - 1;
     while (lo < hi) {
         int mid = (lo + hi + 1) >> 1;

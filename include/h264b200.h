@@ -10,7 +10,7 @@
  *    (h264bsd_storage.h:74-149) and H264SwDecApi.c pokes a few fields
  *    (storage.dpb->flushed/numOut/outIndex :417-424, activeSps :219); this
  *    library therefore also exports the whole H264SwDec* API
- *    (include/h264b200_swdec.h) and the broadway* shim (include/h264b200_shim.h)
+ *    (include/h264b200_swdec.h); Decoder.c (the broadway* shim) links against it unchanged
  *    so that nothing above the boundary needs those fields.
  *  - The macroblock-layer parse stays on the host; reconstruction (dequant +
  *    inverse transforms, inter/intra prediction, deblocking) runs as CUDA
