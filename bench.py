@@ -35,7 +35,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WIDTH_MBS, HEIGHT_MBS = 120, 68          # 1920x1088 coded size of 1080p
-DEFAULT_STREAMS, DEFAULT_FRAMES, DISTINCT = 64, 16, 16
+DEFAULT_STREAMS, DEFAULT_FRAMES, DISTINCT = 256, 16, 16
 REFDEC = os.path.join(ROOT, "oracle", "_ref", "refdec")
 
 

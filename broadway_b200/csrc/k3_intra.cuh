@@ -17,8 +17,9 @@
  * are handed out through an atomic ticket in (row-major, picture-minor) order,
  * so a warp only ever waits on tickets lower than its own, which are held by
  * resident warps: forward progress needs no co-residency guarantee beyond
- * that.  Samples produced by other warps are read with ld.global.cg (L2), never
- * through the non-coherent L1.
+ * that.  Hand-over is st.release.gpu on the row's progress counter and relaxed
+ * polls with back-off on the row above (k_common.cuh); samples produced by other
+ * warps are read with ld.global.cg (L2), never through the non-coherent L1.
  * Inside a macroblock: I16x16/chroma -> 8 / 4 samples per lane; I4x4 -> the
  * sixteen 4x4 blocks in decoding order, 16 lanes each, through a shared-memory
  * tile that also holds the neighbour row/column.
@@ -36,22 +37,6 @@ struct __align__(16) K3Warp {
 };
 
 __device__ __forceinline__ uint8_t ldcg_u8(const uint8_t *p) { return __ldcg(p); }
-
-/* progress protocol ------------------------------------------------------- */
-__device__ __forceinline__ void wf_wait(const int32_t *progress, int row, int need)
-{
-    if (row > 0) {
-        const volatile int32_t *p = progress + (row - 1);
-        while (*p < need) __nanosleep(20);
-    }
-    __threadfence();
-}
-__device__ __forceinline__ void wf_publish(int32_t *progress, int row, int value, int lane)
-{
-    __threadfence();
-    __syncwarp();
-    if (lane == 0) *((volatile int32_t *)(progress + row)) = value;
-}
 
 /* Intra4x4 prediction of sample (x,y) of a block whose top-left is at tile (tx,ty) */
 __device__ __forceinline__ int i4_pred(const uint8_t (*t)[K3_TP], int tx, int ty, int mode, int x, int y, bool has_top, bool has_left, bool has_ur)
@@ -269,17 +254,19 @@ __global__ void __launch_bounds__(K3_WARPS * 32) k3_intra(Batch b)
         if (row >= job.hm || job.n_intra == 0) continue;
         const int wm = job.wm;
         const h264b200_mb_t *rowrec = job.mbs + (size_t)row * wm;
+        const int32_t *above = job.progress + row - 1;
+        int seen = row > 0 ? 0 : 0x7fffffff;
         int x = 0;
         while (x < wm) {
             int cls = (x + lane < wm) ? __ldg(reinterpret_cast<const uint8_t *>(rowrec + x + lane)) : 0;
             unsigned m = __ballot_sync(0xffffffffu, cls == H264B200_MB_I4x4 || cls == H264B200_MB_I16x16 || cls == H264B200_MB_IPCM);
             if (!m) { x += 32; continue; }
             x += __ffs(m) - 1;
-            wf_publish(job.progress, row, x, lane);              /* everything left of x is final */
-            wf_wait(job.progress, row, min(x + 2, wm));
+            wf_publish2(job.progress + row, x, lane);            /* everything left of x is final */
+            wf_wait2(above, min(x + 2, wm), seen, lane);
             k3_macroblock(job, w, x, row, lane);
             x++;
         }
-        wf_publish(job.progress, row, wm, lane);
+        wf_publish2(job.progress + row, wm, lane);
     }
 }

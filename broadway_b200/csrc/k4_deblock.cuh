@@ -57,38 +57,6 @@ struct __align__(16) K4Warp {
 /* everything of the NEXT macroblock that can be fetched ahead, one register set per lane */
 struct K4Pre { int4 rec; uint32_t y0, y1, c, top; };
 
-/* progress poll: a relaxed gpu-scope load (no L1 invalidate, unlike ld.acquire).  Ordering of the sample
- * loads that follow comes from the control dependency on the polled value plus ld.global.cg (L2) reads. */
-__device__ __forceinline__ int ld_acquire(const int32_t *p)
-{
-    int v;
-    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release(int32_t *p, int v)
-{
-    asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
-}
-
-/* wavefront hand-over: `seen` caches the last progress value read from the row above */
-__device__ __forceinline__ bool wf_try(const int32_t *above, int need, int &seen, int lane)
-{
-    if (seen >= need) return true;
-    int v = 0;
-    if (lane == 0) v = ld_acquire(above);
-    seen = __shfl_sync(0xffffffffu, v, 0);
-    return seen >= need;
-}
-__device__ __forceinline__ void wf_wait2(const int32_t *above, int need, int &seen, int lane)
-{
-    while (!wf_try(above, need, seen, lane)) __nanosleep(40);
-}
-__device__ __forceinline__ void wf_publish2(int32_t *mine, int value, int lane)
-{
-    __syncwarp();
-    if (lane == 0) st_release(mine, value);
-}
-
 /* One edge of one line, entirely in registers (8.7.2.3 / 8.7.2.4; h264bsd_deblocking.c:649-1121).
  * v[0..3] = p3..p0, v[4..7] = q0..q3.  Branch-free per lane; `any_weak` / `any_strong` are warp-uniform
  * votes that skip the variant no lane needs.  Chroma lanes (luma == false) only ever change p0 and q0. */
@@ -188,6 +156,7 @@ __device__ __forceinline__ bool k4_filter(K4Warp &w, int cur, int lane)
     const bool f_inner = fl & H264B200_DBK_INNER;
 
     /* ---- boundary strengths: lane = dir*16 + edge*4 + segment ---- */
+    unsigned weak_mask, strong_mask;                   /* one bit per (dir, edge, segment): which edges need which filter variant */
     {
         const int dir = lane >> 4, e = (lane >> 2) & 3, k = lane & 3;
         const int rq = dir ? e * 4 + k : k * 4 + e;
@@ -196,7 +165,8 @@ __device__ __forceinline__ bool k4_filter(K4Warp &w, int cur, int lane)
             if (dir ? f_top : f_left) bsv = dbk_bs(dir ? top : left, dir ? 12 + k : k * 4 + 3, q, rq, true);
         } else if (f_inner) bsv = dbk_bs(q, dir ? rq - 4 : rq - 1, q, rq, false);
         w.bs[dir][e][k] = (uint8_t)bsv;
-        if (!__ballot_sync(0xffffffffu, bsv != 0)) return false;      /* h264bsd_deblocking.c:611 */
+        weak_mask = __ballot_sync(0xffffffffu, bsv != 0 && bsv < 4); strong_mask = __ballot_sync(0xffffffffu, bsv == 4);
+        if (!(weak_mask | strong_mask)) return false;  /* h264bsd_deblocking.c:611 */
         if (lane < 6) {                                /* thresholds: [luma/chroma][left, top, inner] */
             const int ch = lane / 3, which = lane - ch * 3;
             int qp_q = q.qp_dbk, qp_p = which == 0 ? left.qp_dbk : which == 1 ? top.qp_dbk : q.qp_dbk;
@@ -240,7 +210,7 @@ __device__ __forceinline__ bool k4_filter(K4Warp &w, int cur, int lane)
             /* chroma: luma edges 0 and 2 are its edges at samples 0 and 4, i.e. v[4..] and v[8..] of a 12-sample line */
             int bsv = w.bs[dir][e][luma ? (i >> 2) : (i >> 1)];
             if (!luma && (e & 1)) bsv = 0;
-            const unsigned weak = __ballot_sync(0xffffffffu, bsv != 0 && bsv < 4), strong = __ballot_sync(0xffffffffu, bsv == 4);
+            const unsigned weak = weak_mask & (0xfu << (dir * 16 + e * 4)), strong = strong_mask & (0xfu << (dir * 16 + e * 4));
             if (!(weak | strong)) continue;            /* warp-uniform */
             if (e == 0) dbk_edge(v, bsv, thr_e0, tc_e0, luma, weak != 0, strong != 0);
             else if (e == 2) {
@@ -269,24 +239,49 @@ __device__ __forceinline__ bool k4_filter(K4Warp &w, int cur, int lane)
     return true;
 }
 
-/* window -> frame: rows -3..-1 x cols 0..15, rows 0..15 x cols -4..15 (chroma: row -1; rows 0..7 x cols -4..7) */
-__device__ __forceinline__ void k4_writeback(const K4Row &g, K4Warp &w, int x, int lane)
+/* window -> frame: rows -3..-1 x cols 0..15, rows 0..15 x cols -4..15 (chroma: row -1; rows 0..7 x cols -4..7).
+ * Each lane owns up to 3 luma and 2 chroma words; their window / frame offsets are fixed for a row walk. */
+struct K4Wb { int ys[3], cs[2]; int yg[3], cg[2]; unsigned flags; };   /* flags: bit k on, bit 8+k top row, bit 16+k left column (k 0..2 luma, 3..4 chroma) */
+
+__device__ __forceinline__ void k4_wb_init(const K4Row &g, int lane, K4Wb &t)
 {
-    uint8_t *Y = g.Yrow + x * 16;
-    for (int i = lane; i < 92; i += 32) {
-        int r, cw;
-        if (i < 12) { r = 1 + i / 4; cw = 1 + (i & 3); if (g.row == 0) continue; }
-        else { const int j = i - 12; r = 4 + j / 5; cw = j % 5; if (cw == 0 && x == 0) continue; }
-        *reinterpret_cast<uint32_t *>(Y + (ptrdiff_t)(r - 4) * g.W + (cw - 1) * 4) = *reinterpret_cast<const uint32_t *>(&w.y[r][cw * 4]);
+    t.flags = 0;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const int i = lane + 32 * k;
+        int r = 0, cw = 0;
+        if (i < 92) {
+            t.flags |= 1u << k;
+            if (i < 12) { r = 1 + i / 4; cw = 1 + (i & 3); t.flags |= 1u << (8 + k); }
+            else { const int j = i - 12; r = 4 + j / 5; cw = j % 5; if (cw == 0) t.flags |= 1u << (16 + k); }
+        }
+        t.ys[k] = r * K4_LP + cw * 4; t.yg[k] = (r - 4) * g.W + (cw - 1) * 4;
     }
-    uint8_t *C0 = g.Crow + x * 8;
-    for (int i = lane; i < 52; i += 32) {
-        const int pl = i / 26, j = i - pl * 26;
-        int r, cw;
-        if (j < 2) { r = 3; cw = 1 + j; if (g.row == 0) continue; }                       /* row -1 */
-        else { const int k = j - 2; r = 4 + k / 3; cw = k % 3; if (cw == 0 && x == 0) continue; }
-        *reinterpret_cast<uint32_t *>(C0 + (pl ? g.csize : 0) + (ptrdiff_t)(r - 4) * g.CW + (cw - 1) * 4) = *reinterpret_cast<const uint32_t *>(&w.c[pl][r][cw * 4]);
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const int i = lane + 32 * k;
+        int pl = 0, r = 0, cw = 0;
+        if (i < 52) {
+            t.flags |= 1u << (3 + k);
+            pl = i / 26; const int j = i - pl * 26;
+            if (j < 2) { r = 3; cw = 1 + j; t.flags |= 1u << (11 + k); }
+            else { const int q = j - 2; r = 4 + q / 3; cw = q % 3; if (cw == 0) t.flags |= 1u << (19 + k); }
+        }
+        t.cs[k] = (pl * 12 + r) * K4_CP + cw * 4; t.cg[k] = (pl ? (int)g.csize : 0) + (r - 4) * g.CW + (cw - 1) * 4;
     }
+}
+
+__device__ __forceinline__ void k4_writeback(const K4Row &g, K4Warp &w, const K4Wb &t, int x)
+{
+    uint8_t *Y = g.Yrow + x * 16, *C0 = g.Crow + x * 8;
+    const uint8_t *ys = &w.y[0][0], *cs = &w.c[0][0][0];
+    unsigned on = t.flags & 0xff;
+    if (g.row == 0) on &= ~(t.flags >> 8);
+    if (x == 0) on &= ~(t.flags >> 16);
+#pragma unroll
+    for (int k = 0; k < 3; k++) if ((on >> k) & 1) *reinterpret_cast<uint32_t *>(Y + t.yg[k]) = *reinterpret_cast<const uint32_t *>(ys + t.ys[k]);
+#pragma unroll
+    for (int k = 0; k < 2; k++) if ((on >> (3 + k)) & 1) *reinterpret_cast<uint32_t *>(C0 + t.cg[k]) = *reinterpret_cast<const uint32_t *>(cs + t.cs[k]);
 }
 
 __global__ void __launch_bounds__(K4_WARPS * 32, 6) k4_deblock(Batch b)
@@ -313,6 +308,8 @@ __global__ void __launch_bounds__(K4_WARPS * 32, 6) k4_deblock(Batch b)
         const int32_t *above = prog + row - 1;
         int seen = row > 0 ? 0 : 0x7fffffff;
         const int wm = g.wm;
+        K4Wb wb;
+        k4_wb_init(g, lane, wb);
 
         const bool tr = b.trace && (t - (uint32_t)row * b.n_jobs) == 0 && lane == 0;
         if (tr) b.trace[256 + row * 4] = gtime();
@@ -346,8 +343,9 @@ __global__ void __launch_bounds__(K4_WARPS * 32, 6) k4_deblock(Batch b)
                     seen = __shfl_sync(0xffffffffu, polled, 0);
                     wf_wait2(above, need, seen, lane);        /* only a row running right at the wavefront spins here */
                 }
-                if (k4_filter(w, cur, lane)) k4_writeback(g, w, x, lane);
-            }
+                const bool f = k4_filter(w, cur, lane);
+                    if (f) k4_writeback(g, w, wb, x);
+                }
             /* the release (a memory barrier over the write-back) is paid once per K4_PUBLISH macroblocks */
             if (((x + 1) % K4_PUBLISH) == 0 || !more) wf_publish2(prog + row, x + 1, lane);
             if (more) {

@@ -61,3 +61,40 @@ __device__ __forceinline__ uint32_t slot_index(uint32_t mask, int blk)
 }
 
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+
+/* ---- wavefront hand-over between macroblock rows (K3, K4) ---- */
+/* progress poll: a relaxed gpu-scope load (no L1 invalidate, unlike ld.acquire).  Ordering of the sample
+ * loads that follow comes from the control dependency on the polled value plus ld.global.cg (L2) reads. */
+__device__ __forceinline__ int ld_acquire(const int32_t *p)
+{
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int32_t *p, int v)
+{
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+
+/* wavefront hand-over: `seen` caches the last progress value read from the row above */
+__device__ __forceinline__ bool wf_try(const int32_t *above, int need, int &seen, int lane)
+{
+    if (seen >= need) return true;
+    int v = 0;
+    if (lane == 0) v = ld_acquire(above);
+    seen = __shfl_sync(0xffffffffu, v, 0);
+    return seen >= need;
+}
+__device__ __forceinline__ void wf_wait2(const int32_t *above, int need, int &seen, int lane)
+{
+    /* the row above advances one macroblock every few microseconds: back off instead of hammering L2 and
+     * stealing issue slots from the warps that are filtering */
+    unsigned ns = 200;
+    while (!wf_try(above, need, seen, lane)) { __nanosleep(ns); if (ns < 1600) ns *= 2; }
+}
+__device__ __forceinline__ void wf_publish2(int32_t *mine, int value, int lane)
+{
+    __syncwarp();
+    if (lane == 0) st_release(mine, value);
+}
+
