@@ -150,7 +150,7 @@ def reference_arm(args, rank, world):
     if rank != 0:
         return
     if not os.path.exists(REFDEC):
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/refdec not built (reference sources absent at build time)"}))
+        emit(({"impl": "reference", "unavailable": "oracle/_ref/refdec not built (reference sources absent at build time)"}))
         return
     cores = len(os.sched_getaffinity(0))
     streams = make_streams(min(cores, DISTINCT), args.frames, 0)
@@ -164,7 +164,7 @@ def reference_arm(args, rank, world):
         t += dt
     fps = frames / t
     sample = "%d refdec processes (one per host core), each decoding one %d-picture 1080p stream per step" % (cores, args.frames)
-    print(json.dumps({
+    emit(({
         "impl": "reference", "metric": "1080p frames/sec (bit-exact H.264 Baseline decode)", "value": fps, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * t / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
@@ -302,7 +302,7 @@ def own_arm(args, rank, local_rank, world):
             cpu = {"value": None, "unit": "frames/s", "cores": cores, "kind": "reference", "sample": "oracle/_ref/refdec missing"}
 
     if rank == 0:
-        print(json.dumps({
+        emit(({
             "metric": "1080p frames/sec (bit-exact H.264 Baseline decode)", "value": value, "unit": "frames/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
@@ -321,7 +321,19 @@ def own_arm(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
+def emit(obj):
+    """The ONE JSON line goes to the real stdout; everything else printed by libraries (NCCL banner ...)
+    was redirected to stderr in main()."""
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
