@@ -20,7 +20,7 @@ INC = os.path.join(ROOT, "include")
 OBJ = os.path.join(ROOT, "build")
 
 HOST_C = ["h264_decoder.c", "h264_params.c", "h264_dpb.c", "h264_slice.c", "h264_cavlc.c",
-          "h264_swdec.c", "h264_runner.c"]
+          "h264_swdec.c", "h264_runner.c", "h264_mp4.c", "h264_shim.c"]
 CUDA = ["h264_engine.cu"]
 NVCC_ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 

@@ -112,6 +112,8 @@ def lib():
     L.h264b200SplitGops.argtypes = [vp, ctypes.c_size_t, vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t),
                                     ctypes.POINTER(ctypes.c_size_t), u32]
     L.h264b200SplitGops.restype = ctypes.c_int
+    L.h264b200Mp4ToAnnexB.argtypes = [vp, ctypes.c_size_t, vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]
+    L.h264b200Mp4ToAnnexB.restype = ctypes.c_long
     _lib = L
     return L
 
@@ -225,6 +227,19 @@ def split_gops(data, max_segs=4096):
     if n < 0:
         raise RuntimeError("h264b200SplitGops failed")
     return [dst.raw[off[i]:off[i] + ln[i]] for i in range(n)]
+
+
+def mp4_to_annexb(mp4):
+    """h264b200Mp4ToAnnexB: (annexb bytes, number of samples)."""
+    L = lib()
+    src = ctypes.create_string_buffer(bytes(mp4), len(mp4))
+    cap = len(mp4) + 65536
+    dst = ctypes.create_string_buffer(cap)
+    n = ctypes.c_size_t()
+    rc = L.h264b200Mp4ToAnnexB(ctypes.addressof(src), len(mp4), ctypes.addressof(dst), cap, ctypes.byref(n))
+    if rc < 0:
+        raise ValueError("h264b200Mp4ToAnnexB failed (%d)" % rc)
+    return dst.raw[:n.value], rc
 
 
 class Engine:

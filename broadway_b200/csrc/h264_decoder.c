@@ -134,6 +134,8 @@ static int check_au_boundary(h264_decoder_t *d, br_t b /* by value, after the NA
     return br_overrun(&b) ? -1 : 0;
 }
 
+static int apply_output_format(h264_decoder_t *d);
+
 /* --------------------------------------------------------- parameter sets */
 static int sps_equal(const h264_sps_t *a, const h264_sps_t *b) { return memcmp(a, b, sizeof *a) == 0; }
 
@@ -192,6 +194,7 @@ static int activate_param_sets(h264_decoder_t *d, uint32_t pps_id, int is_idr)
         d->be_inst = d->be->inst_create(d->be, d->width_mbs, d->height_mbs, d->n_slots);
         if (!d->be_inst) return -2;
         d->pic = NULL;
+        if (d->out_format && apply_output_format(d)) return -2;
     } else if ((int)pps_id != d->active_pps_id) {
         if (d->pps[pps_id]->sps_id != d->active_sps_id) {
             if (!is_idr) return -1;
@@ -199,6 +202,18 @@ static int activate_param_sets(h264_decoder_t *d, uint32_t pps_id, int is_idr)
         } else { d->active_pps_id = (int)pps_id; d->active_pps = d->pps[pps_id]; }
     }
     return 0;
+}
+
+/* cropped output rectangle of the active SPS (h264bsd_decoder.c:886-917), whole frame without cropping */
+static int apply_output_format(h264_decoder_t *d)
+{
+    const h264_sps_t *p = d->active_sps;
+    int l = 0, t = 0, w, h;
+    if (!d->be || !d->be_inst || !p) return 0;
+    if (!d->be->set_output) return d->out_format ? -1 : 0;
+    w = 16 * (int)p->width_mbs; h = 16 * (int)p->height_mbs;
+    if (p->crop_flag) { l = 2 * (int)p->crop_left; t = 2 * (int)p->crop_top; w -= 2 * (int)(p->crop_left + p->crop_right); h -= 2 * (int)(p->crop_top + p->crop_bottom); }
+    return d->be->set_output(d->be, d->be_inst, d->out_format, l, t, w, h);
 }
 
 /* ------------------------------------------------------------ picture end */
@@ -387,6 +402,14 @@ u8 *h264bsdNextOutputPicture(storage_t *pStorage, u32 *picId, u32 *isIdrPic, u32
     if (isIdrPic) *isIdrPic = o->is_idr;
     if (numErrMbs) *numErrMbs = o->num_err_mbs;
     return p;
+}
+
+u32 h264b200SetOutputFormat(storage_t *pStorage, u32 format)
+{
+    h264_decoder_t *d = DEC(pStorage);
+    if (!d || format > H264B200_OUT_RGBA) return HANTRO_NOK;
+    d->out_format = (int)format;
+    return apply_output_format(d) ? HANTRO_NOK : HANTRO_OK;
 }
 
 /* non-blocking pop + explicit wait (include/h264b200_batch.h) */

@@ -39,6 +39,7 @@
 #include "k2_inter.cuh"
 #include "k3_intra.cuh"
 #include "k4_deblock.cuh"
+#include "k5_rgba.cuh"
 
 #define NBUF 3                 /* input buffers in flight per instance */
 #define NSCR 4                 /* batch scratch sets in flight per engine */
@@ -70,6 +71,9 @@ struct Inst {
     int next_buf;
     int batched;
     int queued;                               /* pictures of this instance waiting in the engine queue */
+    /* optional output formatting (K5): cropped RGBA instead of the I420 frame */
+    int out_format; int cl, ct, cw, ch;
+    uint8_t *d_rgba, *h_rgba; size_t rgba_bytes;
 };
 
 struct Retained {                  /* one batch kept resident for replay */
@@ -293,7 +297,17 @@ static uint32_t submit_locked(h264b200_engine *e)
         PicBuf *p = e->queue[i]; Inst *in = p->inst; int slot = p->in.cur_slot;
         cudaEventRecord(p->done, e->s_comp);
         p->state = 3;
-        if (!(e->flags & H264B200_ENGINE_NO_D2H)) {
+        if (in->out_format == H264B200_OUT_RGBA && in->d_rgba) {
+            /* K5 runs on the copy-out stream: it only reads the finished frame */
+            RgbaJob rj; rj.frame = in->d_frames + (size_t)slot * in->frame_bytes; rj.out = in->d_rgba + (size_t)slot * in->rgba_bytes;
+            rj.W = (int)in->wm * 16; rj.H = (int)in->hm * 16; rj.cl = in->cl; rj.ct = in->ct; rj.cw = in->cw; rj.ch = in->ch;
+            const int items = ((rj.cw + 3) / 4) * ((rj.ch + 1) / 2);
+            k5_rgba<<<(items + 255) / 256, 256, 0, e->s_d2h>>>(rj); e->st.kernel_launches++;
+            if (!(e->flags & H264B200_ENGINE_NO_D2H)) {
+                cudaMemcpyAsync(in->h_rgba + (size_t)slot * in->rgba_bytes, rj.out, in->rgba_bytes, cudaMemcpyDeviceToHost, e->s_d2h);
+                e->st.d2h_bytes += in->rgba_bytes;
+            }
+        } else if (!(e->flags & H264B200_ENGINE_NO_D2H)) {
             cudaMemcpyAsync(in->h_frames + (size_t)slot * in->frame_bytes, in->d_frames + (size_t)slot * in->frame_bytes,
                             in->frame_bytes, cudaMemcpyDeviceToHost, e->s_d2h);
             e->st.d2h_bytes += in->frame_bytes;
@@ -331,7 +345,7 @@ static void *be_inst_create(h264_backend_t *be, uint32_t wm, uint32_t hm, uint32
             if (c->wm == wm && c->hm == hm && c->n_slots == n_slots) {
                 e->pool.erase(e->pool.begin() + i);
                 memset(c->slot_flags, 0, sizeof c->slot_flags);
-                c->next_buf = 0; c->queued = 0;
+                c->next_buf = 0; c->queued = 0; c->out_format = H264B200_OUT_I420;
                 c->batched = (e->flags & H264B200_ENGINE_BATCHED) != 0;
                 for (int k = 0; k < NBUF; k++) c->bufs[k].state = 0;
                 e->insts.push_back(c);
@@ -360,6 +374,7 @@ static void inst_free(Inst *in)
     for (int i = 0; i < NBUF; i++) picbuf_free(&in->bufs[i]);
     for (uint32_t i = 0; i < in->n_slots; i++) cudaEventDestroy(in->slot_ready[i]);
     cudaFree(in->d_frames); cudaFreeHost(in->h_frames);
+    if (in->d_rgba) { cudaFree(in->d_rgba); cudaFreeHost(in->h_rgba); }
     free(in);
 }
 
@@ -429,6 +444,7 @@ static uint8_t *be_frame_host(h264_backend_t *be, void *inst, int slot, uint32_t
         in->slot_flags[slot] &= (uint8_t)~2;
     }
     if (error_flags) *error_flags = *e->h_err;
+    if (in->out_format == H264B200_OUT_RGBA && in->h_rgba) return in->h_rgba + (size_t)slot * in->rgba_bytes;
     return in->h_frames + (size_t)slot * in->frame_bytes;
 }
 
@@ -436,7 +452,30 @@ static uint8_t *be_frame_host_async(h264_backend_t *be, void *inst, int slot)
 {
     Inst *in = (Inst *)inst; (void)be;
     if (slot < 0 || slot >= (int)in->n_slots) return NULL;
+    if (in->out_format == H264B200_OUT_RGBA && in->h_rgba) return in->h_rgba + (size_t)slot * in->rgba_bytes;
     return in->h_frames + (size_t)slot * in->frame_bytes;
+}
+
+/* output format of an instance: 0 ok.  RGBA buffers are allocated on first use. */
+static int be_set_output(h264_backend_t *be, void *inst, int format, int cl, int ct, int cw, int ch)
+{
+    h264b200_engine *e = (h264b200_engine *)be->ctx; Inst *in = (Inst *)inst;
+    if (format != H264B200_OUT_I420 && format != H264B200_OUT_RGBA) return -1;
+    if (format == H264B200_OUT_RGBA) {
+        if (cw <= 0 || ch <= 0 || cl < 0 || ct < 0 || cl + cw > (int)in->wm * 16 || ct + ch > (int)in->hm * 16 || (cl & 1) || (ct & 1)) return -1;
+        const size_t bytes = (size_t)cw * ch * 4;
+        set_device(e);
+        if (in->rgba_bytes != bytes) {
+            if (in->d_rgba) { cudaStreamSynchronize(e->s_d2h); cudaFree(in->d_rgba); cudaFreeHost(in->h_rgba); in->d_rgba = in->h_rgba = NULL; }
+            CUDA_TRY(cudaMalloc((void **)&in->d_rgba, bytes * in->n_slots), return -1);
+            CUDA_TRY(cudaHostAlloc((void **)&in->h_rgba, bytes * in->n_slots, cudaHostAllocDefault), return -1);
+            memset(in->h_rgba, 0, bytes * in->n_slots);
+            in->rgba_bytes = bytes;
+        }
+        in->cl = cl; in->ct = ct; in->cw = cw; in->ch = ch;
+    }
+    in->out_format = format;
+    return 0;
 }
 
 static void be_destroy(h264_backend_t *be) { (void)be; }
@@ -492,6 +531,7 @@ extern "C" h264b200_engine_t *h264b200EngineCreateEx(int device, uint32_t flags)
     e->be.inst_create = be_inst_create; e->be.inst_destroy = be_inst_destroy; e->be.pic_begin = be_pic_begin;
     e->be.coef_grow = be_coef_grow; e->be.pic_submit = be_pic_submit; e->be.frame_host = be_frame_host;
     e->be.frame_host_async = be_frame_host_async;
+    e->be.set_output = be_set_output;
     e->be.destroy = be_destroy; e->be.ctx = e;
     return e;
 }
@@ -638,6 +678,7 @@ extern "C" u32 h264b200EngineCheckResident(h264b200_engine_t *e)
     set_device(e);
     u32 bad = 0;
     for (Inst *in : e->insts) {
+        if (in->out_format != H264B200_OUT_I420) continue;      /* the I420 mirror of an RGBA instance is not filled */
         std::vector<uint8_t> tmp(in->frame_bytes);
         for (uint32_t s = 0; s < in->n_slots; s++) {
             if (cudaMemcpy(tmp.data(), in->d_frames + (size_t)s * in->frame_bytes, in->frame_bytes, cudaMemcpyDeviceToHost) != cudaSuccess) return 0xffffffffu;

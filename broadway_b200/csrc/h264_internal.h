@@ -143,6 +143,8 @@ struct h264_backend {
     void  *ctx;
     /* optional: address frame_host will return for `slot`, without launching or waiting */
     uint8_t *(*frame_host_async)(h264_backend_t *be, void *inst, int slot);
+    /* optional: output format of an instance (H264B200_OUT_*) and the cropping rectangle in luma samples */
+    int (*set_output)(h264_backend_t *be, void *inst, int format, int crop_left, int crop_top, int crop_width, int crop_height);
 };
 
 /* implemented by whichever backend is linked: the CUDA engine in libh264b200.so */
@@ -191,6 +193,7 @@ typedef struct h264_decoder {
     h264_mbctx_t *mbctx;                          /* pic_size_mbs */
     h264_pic_input_t *pic;                        /* input buffer of the picture being parsed */
     int last_output_slot;
+    int out_format;                               /* H264B200_OUT_* requested through h264b200SetOutputFormat */
 } h264_decoder_t;
 
 /* parameter sets / headers (h264_params.c) */

@@ -32,6 +32,16 @@ u8  *h264b200NextOutputPictureAsync(storage_t *pStorage, u32 *picId, u32 *isIdrP
 /* 0: picture complete; otherwise the engine error flags / 0xffffffff on a CUDA failure. */
 u32  h264b200PictureWait(storage_t *pStorage, u32 ticket);
 
+/* ---- output formatting on the device (K5) ----
+ * H264B200_OUT_I420 (default): the reference's output, uncropped MB-aligned planar I420.
+ * H264B200_OUT_RGBA: cropped to the SPS cropping rectangle (the reference only reports it,
+ * h264bsd_decoder.c:886-917) and converted with the wrapper's BT.601 fixed-point formula
+ * (templates/DecoderPost.js:514-560): cropWidth*cropHeight*4 bytes, R,G,B,255 per sample.  The picture
+ * pointers returned afterwards address that buffer.  May be called before or after the headers. */
+#define H264B200_OUT_I420 0u
+#define H264B200_OUT_RGBA 1u
+u32  h264b200SetOutputFormat(storage_t *pStorage, u32 format);
+
 /* ---- resident replay (measurement): re-run K1..K4 over every retained batch,
  * inputs already in HBM, no host<->device copies.  Asynchronous; returns the
  * number of pictures enqueued.  Requires H264B200_ENGINE_RETAIN while decoding. */
@@ -75,6 +85,12 @@ int h264b200DecodeStreams(h264b200_engine_t *e, const h264b200_stream_t *streams
  * (len * 2 + 4096 is always enough for streams whose parameter sets are sent once). */
 int h264b200SplitGops(const uint8_t *data, size_t len, uint8_t *out, size_t out_cap,
                       size_t *seg_off, size_t *seg_len, uint32_t max_segs);
+
+/* MP4 (ISO-BMFF) -> Annex-B, the C counterpart of Player/mp4.js (avcC :414-431, length-prefixed NAL
+ * extraction :711-723): parameter sets of the first avc1 track, then every sample's NAL units, each
+ * behind a 00 00 00 01 start code.  out_cap of len + 64 KiB is always enough.  Returns the number of
+ * samples written, -1 on a malformed / unsupported file, -2 if out_cap is too small. */
+long h264b200Mp4ToAnnexB(const uint8_t *mp4, size_t len, uint8_t *out, size_t out_cap, size_t *out_len);
 
 #ifdef __cplusplus
 }

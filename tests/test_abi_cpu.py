@@ -16,10 +16,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def _declared_symbols():
     names = set()
-    for h in ("h264b200.h", "h264b200_swdec.h", "h264b200_batch.h"):
+    for h in ("h264b200.h", "h264b200_swdec.h", "h264b200_batch.h", "h264b200_shim.h"):
         src = open(os.path.join(ROOT, "include", h)).read()
         src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-        for m in re.finditer(r"\b((?:h264bsd|H264SwDec|h264b200)[A-Za-z0-9_]*)\s*\(", src):
+        for m in re.finditer(r"\b((?:h264bsd|H264SwDec|h264b200|broadway(?=[A-Z]))[A-Za-z0-9_]*)\s*\(", src):
             names.add(m.group(1))
     return names
 

@@ -141,3 +141,96 @@ def test_bare_nal_input_like_the_mp4_player():
     finally:
         L.h264bsdShutdown(ctypes.byref(st))
     assert out == util.oracle_md5(data)[0]
+
+
+def test_broadway_shim_play_stream(golden):
+    """The Decoder.c surface: fill the stream buffer, broadwayPlayStream, pictures arrive by callback."""
+    L = capi.lib()
+    data = cases.make_stream(cases.SMALL[0])
+    got, hdr = [], []
+    HCB = ctypes.CFUNCTYPE(None, ctypes.c_void_p)
+    PCB = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32)
+    on_h = HCB(lambda user: hdr.append(1))
+    on_p = PCB(lambda user, p, w, h: got.append(capi.frame_md5(p, w * h * 3 // 2)))
+    L.broadwaySetCallbacks.argtypes = [HCB, PCB, ctypes.c_void_p]
+    L.broadwayCreateStream.restype = ctypes.c_void_p; L.broadwayCreateStream.argtypes = [ctypes.c_uint32]
+    L.broadwayPlayStream.argtypes = [ctypes.c_uint32]
+    L.broadwaySetCallbacks(on_h, on_p, None)
+    assert L.broadwayInit() == 0
+    buf = L.broadwayCreateStream(len(data))
+    ctypes.memmove(buf, data, len(data))
+    L.broadwayPlayStream(len(data))
+    L.broadwayExit()
+    L.broadwaySetCallbacks(HCB(), PCB(), None)
+    assert hdr == [1]
+    assert got == golden[cases.SMALL[0][0]]["frame_md5"]
+    assert L.broadwayGetMajorVersion() == 2
+
+
+def test_mp4_clip_through_the_decoder(golden):
+    """Config 1/2 shape (Player/*.mp4 are absent from the mount): MP4 -> h264b200Mp4ToAnnexB -> decode."""
+    import mp4mux
+    case = next(c for c in cases.SMALL if c[0] == "p_intra_mix")
+    mp4, n = mp4mux.mux(cases.make_stream(case), 16 * case[1], 16 * case[2])
+    annexb, n2 = capi.mp4_to_annexb(mp4)
+    assert n == n2 == case[3]
+    got, _ = capi.decode_annexb(annexb)
+    assert got == golden["p_intra_mix"]["frame_md5"]
+
+
+def _rgba_reference(frame, W, H, cl, ct, cw, ch):
+    """numpy restatement of templates/DecoderPost.js:514-560 on the cropped rectangle (test oracle)."""
+    import numpy as np
+    f = np.frombuffer(frame, dtype=np.uint8)
+    Y = f[:W * H].reshape(H, W).astype(np.int32)
+    U = f[W * H:W * H + W * H // 4].reshape(H // 2, W // 2).astype(np.int32)
+    V = f[W * H + W * H // 4:].reshape(H // 2, W // 2).astype(np.int32)
+    y = Y[ct:ct + ch, cl:cl + cw]
+    ys, xs = np.mgrid[ct:ct + ch, cl:cl + cw]
+    u, v = U[ys >> 1, xs >> 1], V[ys >> 1, xs >> 1]
+    a0 = 1192 * (y - 16)
+    r = np.clip((a0 + 1634 * (v - 128)) >> 10, 0, 255)
+    g = np.clip((a0 - 832 * (v - 128) - 400 * (u - 128)) >> 10, 0, 255)
+    b = np.clip((a0 + 2066 * (u - 128)) >> 10, 0, 255)
+    out = np.stack([r, g, b, np.full_like(r, 255)], axis=-1).astype(np.uint8)
+    return out.tobytes()
+
+
+@pytest.mark.parametrize("crop", [0, 1], ids=["uncropped", "cropped"])
+def test_rgba_cropped_output_matches_wrapper_formula(crop):
+    """K5: crop + I420->RGBA on the device == the wrapper's converter applied to the I420 frames."""
+    w_mbs, h_mbs, n = 7, 5, 3
+    data = bitstream.synth(w_mbs, h_mbs, n, seed=77, crop=crop, p_intra_permille=100)
+    i420, info = capi.decode_annexb(data, keep_frames=True)
+    L = capi.lib()
+    L.h264b200SetOutputFormat.argtypes = [ctypes.POINTER(capi.Storage), ctypes.c_uint32]; L.h264b200SetOutputFormat.restype = ctypes.c_uint32
+    st = capi.Storage()
+    assert L.h264bsdInit(ctypes.byref(st), 0) == 0
+    assert L.h264b200SetOutputFormat(ctypes.byref(st), 1) == 0
+    buf = ctypes.create_string_buffer(data, len(data) + 16)
+    pos, nread, got = 0, ctypes.c_uint32(), []
+    pid, idr, err = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint32()
+    cf, cl, cw, ct, ch = (ctypes.c_uint32() for _ in range(5))
+    W, H = 16 * w_mbs, 16 * h_mbs
+    try:
+        while pos < len(data):
+            rc = L.h264bsdDecode(ctypes.byref(st), ctypes.addressof(buf) + pos, len(data) - pos, 0, ctypes.byref(nread))
+            pos += nread.value
+            if rc == capi.H264BSD_HDRS_RDY:
+                L.h264bsdCroppingParams(ctypes.byref(st), ctypes.byref(cf), ctypes.byref(cl), ctypes.byref(cw), ctypes.byref(ct), ctypes.byref(ch))
+                rect = (cl.value, ct.value, cw.value, ch.value) if cf.value else (0, 0, W, H)
+            elif rc == capi.H264BSD_PIC_RDY:
+                while True:
+                    p = L.h264bsdNextOutputPicture(ctypes.byref(st), ctypes.byref(pid), ctypes.byref(idr), ctypes.byref(err))
+                    if not p:
+                        break
+                    got.append(ctypes.string_at(p, rect[2] * rect[3] * 4))
+            elif nread.value == 0:
+                break
+    finally:
+        L.h264bsdShutdown(ctypes.byref(st))
+    assert cf.value == crop and len(got) == n
+    if crop:
+        assert rect[3] == H - 8
+    for a, f in zip(got, i420):
+        assert a == _rgba_reference(f, W, H, *rect)
