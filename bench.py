@@ -250,6 +250,13 @@ def own_arm(args, rank, local_rank, world):
     d2h = (s1["d2h_bytes"] - s0["d2h_bytes"]) // args.steps
     launches_e2e = s1["kernel_launches"] - s0["kernel_launches"]
 
+    if args.e2e_only:
+        if rank == 0:
+            sampler.stop()
+            emit({"e2e_only": True, "e2e_fps": e2e_fps, "threads": threads, "streams": args.streams, "ms_per_step": 1000.0 * e2e_s / args.steps,
+                  "parse_core_s": parse_s / args.steps, "wait_s": wait_s / args.steps})
+        return
+
     # ---- resident leg: retain every batch of one decode in HBM, then replay K1..K4 only
     eng = capi.Engine(local_rank, capi.ENGINE_BATCHED | capi.ENGINE_RETAIN)
     eng.decode_streams(streams, threads)
@@ -343,6 +350,7 @@ def main():
     ap.add_argument("--frames", type=int, default=DEFAULT_FRAMES, help="pictures per stream (1 IDR + P)")
     ap.add_argument("--threads", type=int, default=0, help="parser threads per GPU (0: host cores / ranks)")
     ap.add_argument("--no-check", action="store_true")
+    ap.add_argument("--e2e-only", action="store_true", help="host-to-host leg only (experiments)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -270,10 +270,12 @@ class Engine:
         """Decode independent Annex-B streams, one picture of each per batched launch.
         on_picture(stream, index, ptr, width, height, pic_id, err_mbs) is called from worker threads."""
         n = len(streams)
-        keep = [ctypes.create_string_buffer(bytes(s), len(s)) for s in streams]
+        # the C side never writes to the caller's streams (it makes its own copies, in the worker
+        # threads), so the bytes objects are passed by address: no copy here
+        keep = [s if isinstance(s, bytes) else bytes(s) for s in streams]
         descs = (StreamDesc * n)()
         for i, b in enumerate(keep):
-            descs[i].data = ctypes.addressof(b); descs[i].len = len(streams[i])
+            descs[i].data = ctypes.cast(ctypes.c_char_p(b), ctypes.c_void_p); descs[i].len = len(b)
         cb = None
         if on_picture is not None:
             def _cb(user, stream, index, ptr, w, h, pic_id, err):

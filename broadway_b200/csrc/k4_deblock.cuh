@@ -58,36 +58,37 @@ struct __align__(16) K4Warp {
 struct K4Pre { int4 rec; uint32_t y0, y1, c, top; };
 
 /* One edge of one line, entirely in registers (8.7.2.3 / 8.7.2.4; h264bsd_deblocking.c:649-1121).
- * v[0..3] = p3..p0, v[4..7] = q0..q3.  Branch-free per lane; `any_weak` / `any_strong` are warp-uniform
- * votes that skip the variant no lane needs.  Chroma lanes (luma == false) only ever change p0 and q0. */
+ * v[0..3] = p3..p0, v[4..7] = q0..q3.  Straight-line code: every per-lane decision is a select, never a
+ * branch (32 lanes hold 32 different lines); only `any_weak` / `any_strong`, warp-uniform votes, skip
+ * the variant no lane needs.  Chroma lanes (luma == false) only ever change p0 and q0. */
 __device__ __forceinline__ void dbk_edge(int *v, int bs, uint32_t thr, uint32_t tcw, bool luma, bool any_weak, bool any_strong)
 {
     const int p3 = v[0], p2 = v[1], p1 = v[2], p0 = v[3], q0 = v[4], q1 = v[5], q2 = v[6], q3 = v[7];
     const int alpha = thr & 0xff, beta = (thr >> 8) & 0xff;
     const int ad = abs(p0 - q0);
-    const bool on = bs != 0 && ad < alpha && abs(p1 - p0) < beta && abs(q1 - q0) < beta;
-    const bool ap = luma && abs(p2 - p0) < beta, aq = luma && abs(q2 - q0) < beta;
+    const bool on = (bs != 0) & (ad < alpha) & (abs(p1 - p0) < beta) & (abs(q1 - q0) < beta);
+    const bool ap = luma & (abs(p2 - p0) < beta), aq = luma & (abs(q2 - q0) < beta);
     int n0 = p0, n1 = p1, n2 = p2, m0 = q0, m1 = q1, m2 = q2;
     if (any_weak) {
-        const bool wk = on && bs < 4;
-        const int tc0 = (tcw >> (8 * ((bs - 1) & 3))) & 0xff;
-        const int tc = luma ? tc0 + ap + aq : tc0 + 1;
+        const bool wk = on & (bs < 4);
+        const int tc0 = (tcw >> ((8 * (bs - 1)) & 31)) & 0xff;
+        const int tc = tc0 + (luma ? (int)ap + (int)aq : 1);
         const int d = clip3i(-tc, tc, (((q0 - p0) << 2) + (p1 - q1) + 4) >> 3);
         const int avg = (p0 + q0 + 1) >> 1;
-        if (wk) {
-            n0 = clip255(p0 + d); m0 = clip255(q0 - d);
-            if (ap) n1 = p1 + clip3i(-tc0, tc0, (p2 + avg - (p1 << 1)) >> 1);
-            if (aq) m1 = q1 + clip3i(-tc0, tc0, (q2 + avg - (q1 << 1)) >> 1);
-        }
+        const int e1 = clip3i(-tc0, tc0, (p2 + avg - (p1 << 1)) >> 1), f1 = clip3i(-tc0, tc0, (q2 + avg - (q1 << 1)) >> 1);
+        n0 = wk ? clip255(p0 + d) : p0; m0 = wk ? clip255(q0 - d) : q0;
+        n1 = (wk & ap) ? p1 + e1 : p1;  m1 = (wk & aq) ? q1 + f1 : q1;
     }
     if (any_strong) {
-        if (on && bs == 4) {
-            const bool small = ad < ((alpha >> 2) + 2);
-            if (ap && small) { n0 = (p2 + 2 * p1 + 2 * p0 + 2 * q0 + q1 + 4) >> 3; n1 = (p2 + p1 + p0 + q0 + 2) >> 2; n2 = (2 * p3 + 3 * p2 + p1 + p0 + q0 + 4) >> 3; }
-            else n0 = (2 * p1 + p0 + q1 + 2) >> 2;
-            if (aq && small) { m0 = (p1 + 2 * p0 + 2 * q0 + 2 * q1 + q2 + 4) >> 3; m1 = (p0 + q0 + q1 + q2 + 2) >> 2; m2 = (2 * q3 + 3 * q2 + q1 + q0 + p0 + 4) >> 3; }
-            else m0 = (2 * q1 + q0 + p1 + 2) >> 2;
-        }
+        const bool st = on & (bs == 4);
+        const bool small = ad < ((alpha >> 2) + 2);
+        const bool sp = st & ap & small, sq = st & aq & small;
+        const int s = p0 + q0;
+        const int sp0 = (p2 + 2 * (p1 + s) + q1 + 4) >> 3, sp1 = (p2 + p1 + s + 2) >> 2, sp2 = (2 * p3 + 3 * p2 + p1 + s + 4) >> 3;
+        const int sq0 = (q2 + 2 * (q1 + s) + p1 + 4) >> 3, sq1 = (q2 + q1 + s + 2) >> 2, sq2 = (2 * q3 + 3 * q2 + q1 + s + 4) >> 3;
+        const int wp0 = (2 * p1 + p0 + q1 + 2) >> 2, wq0 = (2 * q1 + q0 + p1 + 2) >> 2;
+        n0 = sp ? sp0 : (st ? wp0 : n0); n1 = sp ? sp1 : n1; n2 = sp ? sp2 : n2;
+        m0 = sq ? sq0 : (st ? wq0 : m0); m1 = sq ? sq1 : m1; m2 = sq ? sq2 : m2;
     }
     v[1] = n2; v[2] = n1; v[3] = n0; v[4] = m0; v[5] = m1; v[6] = m2;
 }
@@ -183,11 +184,12 @@ __device__ __forceinline__ bool k4_filter(K4Warp &w, int cur, int lane)
     __syncwarp();
 
     /* ---- vertical edges (dir 0), then horizontal edges (dir 1).  Lanes 0..15 hold one luma line of 20
-     * samples in registers, lanes 16..31 one chroma line of 12 (Cb lines, then Cr lines); all four (two)
-     * edges of the line are filtered in registers, one shared-memory round trip per direction. ---- */
+     * samples in registers, lanes 16..31 one chroma line of 12 (Cb lines, then Cr lines); all edges of the
+     * line are filtered in registers, one shared-memory round trip per direction.  Loop step e filters luma
+     * edge e (samples v[4e..4e+7]) and, for e < 2, chroma edge e (same registers), whose strength is that of
+     * luma edge 2e (h264bsd_deblocking.c:1650-1735). ---- */
     const bool luma = lane < 16;
     const int ch = luma ? 0 : 1, pl = (lane >> 3) & 1, i = luma ? lane : (lane & 7);
-    const int n_px = luma ? 20 : 12;
 #pragma unroll
     for (int dir = 0; dir < 2; dir++) {
         int v[20];
@@ -207,21 +209,12 @@ __device__ __forceinline__ bool k4_filter(K4Warp &w, int cur, int lane)
         const uint32_t thr_e0 = w.thr[ch][dir], thr_in = w.thr[ch][2], tc_e0 = w.tc0[ch][dir], tc_in = w.tc0[ch][2];
 #pragma unroll
         for (int e = 0; e < 4; e++) {
-            /* chroma: luma edges 0 and 2 are its edges at samples 0 and 4, i.e. v[4..] and v[8..] of a 12-sample line */
-            int bsv = w.bs[dir][e][luma ? (i >> 2) : (i >> 1)];
-            if (!luma && (e & 1)) bsv = 0;
-            const unsigned weak = weak_mask & (0xfu << (dir * 16 + e * 4)), strong = strong_mask & (0xfu << (dir * 16 + e * 4));
+            const unsigned wl = 0xfu << (dir * 16 + e * 4), wc = e < 2 ? 0xfu << (dir * 16 + e * 8) : 0u;
+            const unsigned weak = weak_mask & (wl | wc), strong = strong_mask & (wl | wc);
             if (!(weak | strong)) continue;            /* warp-uniform */
-            if (e == 0) dbk_edge(v, bsv, thr_e0, tc_e0, luma, weak != 0, strong != 0);
-            else if (e == 2) {
-                /* luma line: samples 8..15; chroma line: samples 4..11 -> same code on a shifted view */
-                int t[8];
-#pragma unroll
-                for (int k = 0; k < 8; k++) t[k] = luma ? v[8 + k] : v[4 + k];
-                dbk_edge(t, bsv, thr_in, tc_in, luma, weak != 0, strong != 0);
-#pragma unroll
-                for (int k = 1; k < 7; k++) { if (luma) v[8 + k] = t[k]; else v[4 + k] = t[k]; }
-            } else dbk_edge(v + 4 * e, bsv, thr_in, tc_in, luma, weak != 0, strong != 0);
+            int bsv = luma ? w.bs[dir][e][i >> 2] : w.bs[dir][(2 * e) & 3][i >> 1];
+            if (!luma && e >= 2) bsv = 0;
+            dbk_edge(v + 4 * e, bsv, e ? thr_in : thr_e0, e ? tc_in : tc_e0, luma, weak != 0, strong != 0);
         }
         if (dir == 0) {
             uint32_t *dst = luma ? reinterpret_cast<uint32_t *>(&w.y[4 + i][0]) : reinterpret_cast<uint32_t *>(&w.c[pl][4 + i][0]);
@@ -232,7 +225,7 @@ __device__ __forceinline__ bool k4_filter(K4Warp &w, int cur, int lane)
             uint8_t *dst = luma ? &w.y[0][4 + i] : &w.c[pl][0][4 + i];
             const int pitch = luma ? K4_LP : K4_CP;
 #pragma unroll
-            for (int k = 1; k < 19; k++) if (k < n_px) dst[k * pitch] = (uint8_t)v[k];
+            for (int k = 1; k < 19; k++) if (k < 12 || luma) dst[k * pitch] = (uint8_t)v[k];
         }
         __syncwarp();
     }
