@@ -34,7 +34,14 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WIDTH_MBS, HEIGHT_MBS = 120, 68          # 1920x1088 coded size of 1080p
+WIDTH_MBS, HEIGHT_MBS = 120, 68          # 1920x1088 coded size of 1080p (default workload)
+WORKLOADS = {
+    # name: (width_mbs, height_mbs, writer overrides, description)
+    "1080p_ippp": (120, 68, {}, "synthetic 1080p Baseline IPPP, random MVs incl. quarter-pel, ~30% coded blocks, deblocking on (BASELINE.json configs[2]; configs[1] tree.mp4 absent)"),
+    "1080p_intra": (120, 68, {"intra_only": 1}, "synthetic 1080p intra-only (I16x16/I4x4 mix) stressing the intra and deblock wavefronts (BASELINE.json configs[3])"),
+    "4k_ippp": (240, 135, {"level_idc": 51}, "synthetic 4K (3840x2160) Baseline IPPP multi-stream (BASELINE.json configs[4])"),
+}
+_WL = {"name": "1080p_ippp"}
 DEFAULT_STREAMS, DEFAULT_FRAMES, DISTINCT = 256, 16, 16
 REFDEC = os.path.join(ROOT, "oracle", "_ref", "refdec")
 
@@ -49,8 +56,10 @@ def make_streams(n_streams, n_frames, rank):
     from broadway_b200 import bitstream
     n_distinct = min(DISTINCT, n_streams)
 
+    w, h, kw, _ = WORKLOADS[_WL["name"]]
+
     def gen(i):
-        return bitstream.synth(WIDTH_MBS, HEIGHT_MBS, n_frames, seed=1234 + 1000 * rank + i)
+        return bitstream.synth(w, h, n_frames, seed=1234 + 1000 * rank + i, **kw)
     with ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1)) as ex:
         base = list(ex.map(gen, range(n_distinct)))
     return [base[i % n_distinct] for i in range(n_streams)]
@@ -168,7 +177,7 @@ def reference_arm(args, rank, world):
         "impl": "reference", "metric": "1080p frames/sec (bit-exact H.264 Baseline decode)", "value": fps, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * t / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "synthetic 1080p Baseline IPPP (BASELINE.json configs[2])", "width": 1920, "height": 1088,
+        "config": {"workload": WORKLOADS[args.workload][3], "width": 16 * WORKLOADS[args.workload][0], "height": 16 * WORKLOADS[args.workload][1],
                    "frames_per_stream": args.frames, "streams_per_step": cores},
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "reference", "sample": sample},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -210,7 +219,7 @@ def own_arm(args, rank, local_rank, world):
     # of the UNMODIFIED reference (tests/golden/bench_streams.json, made by tools/make_golden.py)
     check = {}
     gpath = os.path.join(ROOT, "tests", "golden", "bench_streams.json")
-    if rank == 0 and not args.no_check and os.path.exists(gpath):
+    if rank == 0 and not args.no_check and os.path.exists(gpath) and args.workload == "1080p_ippp":
         import hashlib
         g = json.load(open(gpath))
         if g["frames"] == args.frames:
@@ -310,13 +319,13 @@ def own_arm(args, rank, local_rank, world):
 
     if rank == 0:
         emit(({
-            "metric": "1080p frames/sec (bit-exact H.264 Baseline decode)", "value": value, "unit": "frames/s",
+            "metric": "%s frames/sec (bit-exact H.264 Baseline decode)" % ("4K" if args.workload.startswith("4k") else "1080p"), "value": value, "unit": "frames/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "synthetic 1080p Baseline IPPP, random MVs incl. quarter-pel, ~30% coded blocks, deblocking on (BASELINE.json configs[2]; configs[1] tree.mp4 absent)",
-                       "width": 1920, "height": 1088, "streams_per_gpu": args.streams, "frames_per_stream": args.frames,
+            "config": {"workload": WORKLOADS[args.workload][3],
+                       "width": 16 * WORKLOADS[args.workload][0], "height": 16 * WORKLOADS[args.workload][1], "streams_per_gpu": args.streams, "frames_per_stream": args.frames,
                        "frames_per_step_per_gpu": frames_per_step, "parser_threads_per_gpu": threads, "host_cores": cores,
-                       "l2": "inputs larger than L2 (per step: %.0f MB of frame pools + records per GPU)" % (args.streams * 2 * 3.13 + h2d / 1e6)},
+                       "l2": "inputs larger than L2 (per step: %.0f MB of frame pools + records per GPU)" % (args.streams * 2 * WORKLOADS[args.workload][0] * WORKLOADS[args.workload][1] * 384 / 1e6 + h2d / 1e6)},
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1000.0 * e2e_s / args.steps, "timing": "wall clock between barrier+synchronize pairs, max over ranks",
                     "host_parse_core_seconds_per_step": parse_s / args.steps, "host_wait_seconds_per_step": wait_s / args.steps,
@@ -349,10 +358,12 @@ def main():
     ap.add_argument("--streams", type=int, default=DEFAULT_STREAMS, help="independent 1080p streams per GPU")
     ap.add_argument("--frames", type=int, default=DEFAULT_FRAMES, help="pictures per stream (1 IDR + P)")
     ap.add_argument("--threads", type=int, default=0, help="parser threads per GPU (0: host cores / ranks)")
+    ap.add_argument("--workload", default="1080p_ippp", choices=sorted(WORKLOADS), help="default: the configuration BASELINE.json's metric is quoted on")
     ap.add_argument("--no-check", action="store_true")
     ap.add_argument("--e2e-only", action="store_true", help="host-to-host leg only (experiments)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    _WL["name"] = args.workload
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

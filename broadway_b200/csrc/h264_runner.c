@@ -55,38 +55,18 @@ struct runner {
     pthread_mutex_t mu; pthread_cond_t cv;
     uint32_t arrived, generation; uint64_t round_sum, last_sum;
     uint32_t rounds;
-    /* batch launches run on their own thread so that no parser thread stalls in the CUDA calls */
-    pthread_t submitter; pthread_cond_t sub_cv; uint32_t rounds_ready, rounds_submitted; int stop;
 };
 
-static void *submitter_main(void *arg)
-{
-    runner_t *r = (runner_t *)arg;
-    pthread_mutex_lock(&r->mu);
-    for (;;) {
-        while (r->rounds_submitted == r->rounds_ready && !r->stop) pthread_cond_wait(&r->sub_cv, &r->mu);
-        if (r->rounds_submitted == r->rounds_ready && r->stop) break;
-        r->rounds_submitted = r->rounds_ready;
-        pthread_mutex_unlock(&r->mu);
-        h264b200EngineSubmit(r->e);
-        pthread_mutex_lock(&r->mu);
-    }
-    pthread_mutex_unlock(&r->mu);
-    return NULL;
-}
-
-/* Barrier; the last arriver hands the round to the submitter thread (if a parser thread reaches its
- * next picture before the submitter ran, the engine's dependency rule makes that thread launch the
- * batch itself: a picture is never queued behind an unlaunched picture of the same instance).
- * Returns the number of pictures all threads produced in this round. */
+/* Barrier; the last arriver launches the batch (every picture of the round is queued by then, and no
+ * thread is past the barrier, so a batch is always exactly one round).  Returns the number of pictures
+ * all threads produced in this round. */
 static uint64_t round_barrier(runner_t *r, uint64_t produced)
 {
     uint64_t sum;
     pthread_mutex_lock(&r->mu);
     r->round_sum += produced;
     if (++r->arrived == r->n_threads) {
-        r->rounds_ready++;
-        pthread_cond_signal(&r->sub_cv);
+        h264b200EngineSubmit(r->e);
         r->last_sum = r->round_sum; r->round_sum = 0; r->arrived = 0; r->generation++; r->rounds++;
         pthread_cond_broadcast(&r->cv);
     } else {
@@ -198,15 +178,10 @@ int h264b200DecodeStreams(h264b200_engine_t *e, const h264b200_stream_t *streams
         if (!s->buf || h264b200InitOnEngine(&s->st, 0, e) != HANTRO_OK) { s->failed = 1; rc = -1; continue; }
         s->inited = 1;
     }
-    pthread_cond_init(&r.sub_cv, NULL);
-    pthread_create(&r.submitter, NULL, submitter_main, &r);
     for (i = 0; i < n_threads; i++) { w[i].r = &r; w[i].tid = i; }
     for (i = 1; i < n_threads; i++) pthread_create(&w[i].th, NULL, worker_main, &w[i]);
     worker_main(&w[0]);
     for (i = 1; i < n_threads; i++) pthread_join(w[i].th, NULL);
-    pthread_mutex_lock(&r.mu); r.stop = 1; pthread_cond_signal(&r.sub_cv); pthread_mutex_unlock(&r.mu);
-    pthread_join(r.submitter, NULL);
-    pthread_cond_destroy(&r.sub_cv);
     h264b200EngineSync(e);
     if (out) {
         memset(out, 0, sizeof *out);

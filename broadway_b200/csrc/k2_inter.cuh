@@ -81,6 +81,15 @@ __global__ void __launch_bounds__(K2_THREADS) k2_inter(Batch b)
     const int16_t *coef = job.coef + (size_t)__ldg(rec + 3) * 16;
     const int fx = mvx & 3, fy = mvy & 3;
 
+    /* residual of this block: requested now, consumed after the interpolation */
+    const int bi = (blk & 1) | ((blk & 2) << 1) | ((blk & 4) >> 1) | (blk & 8);                /* raster -> luma4x4BlkIdx */
+    const bool has_res = inter && ((mask >> bi) & 1);
+    int4 res_lo = make_int4(0, 0, 0, 0), res_hi = make_int4(0, 0, 0, 0);
+    if (has_res) {
+        const int4 *rs = reinterpret_cast<const int4 *>(coef + slot_index(mask, bi) * 16);
+        res_lo = __ldg(rs); res_hi = __ldg(rs + 1);
+    }
+
     /* ================================ luma ================================ */
     uint32_t out_rows[4];
     {
@@ -186,12 +195,9 @@ __global__ void __launch_bounds__(K2_THREADS) k2_inter(Batch b)
 
     /* ---- luma residual + store ---- */
     if (inter) {
-        const int bi = (blk & 1) | ((blk & 2) << 1) | ((blk & 4) >> 1) | (blk & 8);            /* raster -> luma4x4BlkIdx */
         uint8_t *dst = job.cur + (size_t)(mby * 16 + by * 4) * W + mbx * 16 + bx * 4;
-        if ((mask >> bi) & 1) {
-            const int4 *rs = reinterpret_cast<const int4 *>(coef + slot_index(mask, bi) * 16);
-            const int4 lo = *rs, hi = *(rs + 1);
-            const int rw[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+        if (has_res) {
+            const int rw[8] = {res_lo.x, res_lo.y, res_lo.z, res_lo.w, res_hi.x, res_hi.y, res_hi.z, res_hi.w};
 #pragma unroll
             for (int py = 0; py < 4; py++) {
                 const uint32_t p = out_rows[py];

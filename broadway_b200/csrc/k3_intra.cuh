@@ -34,6 +34,7 @@ struct __align__(16) K3Warp {
     h264b200_mb_t rec;
     __align__(16) uint8_t tile[17][K3_TP];       /* row 0 = samples above the macroblock */
     __align__(16) uint8_t ctile[2][9][24];       /* chroma: interior at columns 8..15, left column 7 */
+    __align__(16) int16_t res[26][16];           /* the macroblock's residual slots, staged once (the I4x4 chain must not wait on HBM 16 times) */
 };
 
 __device__ __forceinline__ uint8_t ldcg_u8(const uint8_t *p) { return __ldcg(p); }
@@ -124,6 +125,11 @@ __device__ void k3_macroblock(const PicJob &job, K3Warp &w, int mbx, int mby, in
         return;
     }
     const uint32_t mask = w.rec.resid_mask;
+    /* residual slots of this macroblock (K1 output) -> registers now, shared memory below: one exposed latency */
+    const int n_vec = 2 * __popc(mask & 0x3ffffffu);                /* 16-byte vectors: two per slot, DC slots included */
+    int4 rv0 = make_int4(0, 0, 0, 0), rv1 = rv0;
+    if (lane < n_vec) rv0 = __ldg(reinterpret_cast<const int4 *>(coef) + lane);
+    if (lane + 32 < n_vec) rv1 = __ldg(reinterpret_cast<const int4 *>(coef) + lane + 32);
     const bool aA = w.rec.avail & H264B200_AVAIL_A, aB = w.rec.avail & H264B200_AVAIL_B;
     const bool aC = w.rec.avail & H264B200_AVAIL_C, aD = w.rec.avail & H264B200_AVAIL_D;
 
@@ -137,6 +143,8 @@ __device__ void k3_macroblock(const PicJob &job, K3Warp &w, int mbx, int mby, in
         }
         if (lane < 16) w.tile[1 + lane][15] = aA ? ldcg_u8(Y + (size_t)lane * W - 1) : 0;
     }
+    if (lane < n_vec) reinterpret_cast<int4 *>(&w.res[0][0])[lane] = rv0;
+    if (lane + 32 < n_vec) reinterpret_cast<int4 *>(&w.res[0][0])[lane + 32] = rv1;
     __syncwarp();
 
     if (cls == H264B200_MB_I16x16) {
@@ -158,7 +166,7 @@ __device__ void k3_macroblock(const PicJob &job, K3Warp &w, int mbx, int mby, in
             const int bx4 = (x0 >> 2) + hq, by4 = y >> 2;
             const int bi = (bx4 & 1) | ((by4 & 1) << 1) | ((bx4 & 2) << 1) | ((by4 & 2) << 2);     /* luma4x4BlkIdx */
             const bool has_r = (mask >> bi) & 1;
-            const int16_t *rs = coef + slot_index(mask, bi) * 16 + (y & 3) * 4;
+            const int16_t *rs = &w.res[slot_index(mask, bi)][(y & 3) * 4];
             uint32_t pk = 0;
 #pragma unroll
             for (int i = 0; i < 4; i++) {
@@ -187,7 +195,7 @@ __device__ void k3_macroblock(const PicJob &job, K3Warp &w, int mbx, int mby, in
             if (lane < 16) {
                 const int x = lane & 3, y = lane >> 2;
                 v = i4_pred(w.tile, tx, ty, w.rec.i4_mode[blk], x, y, has_top, has_left, has_ur);
-                if ((mask >> blk) & 1) v = clip255(v + coef[slot_index(mask, blk) * 16 + lane]);
+                if ((mask >> blk) & 1) v = clip255(v + w.res[slot_index(mask, blk)][lane]);
             }
             __syncwarp();
             if (lane < 16) w.tile[ty + (lane >> 2)][tx + (lane & 3)] = (uint8_t)v;
@@ -220,7 +228,7 @@ __device__ void k3_macroblock(const PicJob &job, K3Warp &w, int mbx, int mby, in
         }
         const int cb = 16 + 4 * pl + (y >> 2) * 2 + (x0 >> 2);
         const bool has_r = (mask >> cb) & 1;
-        const int16_t *rs = coef + slot_index(mask, cb) * 16 + (y & 3) * 4;
+        const int16_t *rs = &w.res[slot_index(mask, cb)][(y & 3) * 4];
         uint32_t pk = 0;
 #pragma unroll
         for (int i = 0; i < 4; i++) {
