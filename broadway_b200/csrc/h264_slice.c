@@ -356,7 +356,7 @@ static int parse_inter_mb(sl_t *s, uint32_t mb_type /* 0..4 */)
         for (i = 0; i < 4; i++) if (set_ref(s, i, ref)) return -1;
         dx = br_se(b); dy = br_se(b);
         predict_mv(s, 0, 0, 4, ref, 0, 0, &px, &py);
-        mx = (int16_t)(px + dx); my = (int16_t)(py + dy);
+        mx = (int16_t)((unsigned)px + (unsigned)dx); my = (int16_t)((unsigned)py + (unsigned)dy);
         if (!mv_in_range(mx, my)) return -1;
         fill_mv(r, 0, 0, 4, 4, mx, my, &done);
     } else if (mb_type == 1 || mb_type == 2) {
@@ -368,7 +368,7 @@ static int parse_inter_mb(sl_t *s, uint32_t mb_type /* 0..4 */)
         for (i = 0; i < 2; i++) {
             if (mb_type == 1) predict_mv(s, 0, 2 * i, 4, ref[i], done, i == 0 ? 2 : 1, &px, &py);
             else              predict_mv(s, 2 * i, 0, 2, ref[i], done, i == 0 ? 1 : 3, &px, &py);
-            mx = (int16_t)(px + dx[i]); my = (int16_t)(py + dy[i]);
+            mx = (int16_t)((unsigned)px + (unsigned)dx[i]); my = (int16_t)((unsigned)py + (unsigned)dy[i]);
             if (!mv_in_range(mx, my)) return -1;
             if (mb_type == 1) fill_mv(r, 0, 2 * i, 4, 2, mx, my, &done);
             else              fill_mv(r, 2 * i, 0, 2, 4, mx, my, &done);
@@ -392,7 +392,7 @@ static int parse_inter_mb(sl_t *s, uint32_t mb_type /* 0..4 */)
                 default: x4 = ox + (k & 1); y4 = oy + (k >> 1); w4 = 1; h4 = 1; break;
                 }
                 predict_mv(s, x4, y4, w4, ref[q], done, 0, &px, &py);
-                mx = (int16_t)(px + mvd[m][0]); my = (int16_t)(py + mvd[m][1]);
+                mx = (int16_t)((unsigned)px + (unsigned)mvd[m][0]); my = (int16_t)((unsigned)py + (unsigned)mvd[m][1]);
                 if (!mv_in_range(mx, my)) return -1;
                 fill_mv(r, x4, y4, w4, h4, mx, my, &done);
             }
