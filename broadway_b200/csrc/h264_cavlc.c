@@ -20,8 +20,8 @@ ct_entry_t g_ct[3][16 * 8];
 ct_entry_t g_ct_cdc[256];          /* chroma DC: 8-bit direct */
 uint8_t g_tz[15][512][2];          /* total_zeros: [tc-1][9 bits] -> {len, value} */
 uint8_t g_tz_cdc[3][8][2];
-uint8_t g_rb[6][8][2];             /* run_before, zerosLeft 1..6: [zl-1][3 bits] -> {len, run} */
-int8_t  g_lvl[7][256][2];          /* level: [suffixLength][8 bits] -> {level, bits} (bits 0: longer than 8) */
+uint8_t g_rb[7][8][2];             /* run_before, zerosLeft 1..6 and >6: [min(zl,7)-1][3 bits] -> {len, run} (len 0: code longer than 3 bits) */
+int8_t  g_lvl[7][256][4];          /* level: [suffixLength][8 bits] -> {level, bits, next suffixLength} (bits 0: longer than 8) */
 static int g_init;
 
 static int bitlen(unsigned v) { int n = 0; while (v) { n++; v >>= 1; } return n; }
@@ -84,7 +84,13 @@ void h264_cavlc_init(void)
         code = (prefix << t) + ((i >> (8 - len)) & ((1 << size) - 1));
         g_lvl[t][i][0] = (int8_t)((code & 1) ? (-code - 1) >> 1 : (code + 2) >> 1);
         g_lvl[t][i][1] = (int8_t)len;
+        {   /* suffixLength after this level (9.2.2.1), valid when no levelCode adjustment applies */
+            int a = g_lvl[t][i][0] < 0 ? -g_lvl[t][i][0] : g_lvl[t][i][0], ns = t ? t : 1;
+            if (a > (3 << (ns - 1)) && ns < 6) ns++;
+            g_lvl[t][i][2] = (int8_t)ns;
+        }
     }
+    for (i = 1; i < 8; i++) { g_rb[6][i][0] = 3; g_rb[6][i][1] = (uint8_t)(7 - i); }   /* zerosLeft > 6: 111 -> 0 ... 001 -> 6 */
     g_init = 1;
 }
 

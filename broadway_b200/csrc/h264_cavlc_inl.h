@@ -10,8 +10,8 @@ extern ct_entry_t g_ct[3][16 * 8];
 extern ct_entry_t g_ct_cdc[256];
 extern uint8_t g_tz[15][512][2];
 extern uint8_t g_tz_cdc[3][8][2];
-extern uint8_t g_rb[6][8][2];
-extern int8_t  g_lvl[7][256][2];
+extern uint8_t g_rb[7][8][2];          /* row 6: zerosLeft > 6, 3-bit codes only (len 0: longer code) */
+extern int8_t  g_lvl[7][256][4];      /* {level, bits, next suffixLength, -} */
 
 /* Decode one residual block into out[scan[i]].  `out` (16 x int16) is zeroed here when the block
  * has coefficients and left untouched when TotalCoeff is 0.  nc < 0: chroma DC.
@@ -35,7 +35,7 @@ static inline int h264_cavlc_block(br_t *b, int nc, int max_coeff, int16_t *out,
         if (nc < 2 && (v >> 31)) { br_skip(b, 1); return 0; }      /* the most frequent token: TotalCoeff 0 */
         if (v < 0x10000u) return -1;              /* more than 15 leading zeros: no such code */
         lz = __builtin_clz(v);
-        e = g_ct[nc < 2 ? 0 : nc < 4 ? 1 : 2][lz * 8 + ((v >> (28 - lz)) & 7)];
+        e = g_ct[(0xaa50 >> (2 * nc)) & 3][lz * 8 + ((v >> (28 - lz)) & 7)];     /* nC 0,1 -> 0; 2,3 -> 1; 4..7 -> 2 */
         if (!e.len) return -1;
         br_skip(b, e.len); tc = e.tc; t1 = e.t1;
     } else {
@@ -49,9 +49,10 @@ static inline int h264_cavlc_block(br_t *b, int nc, int max_coeff, int16_t *out,
 
     /* ---- levels ---- */
     sl = (tc > 10 && t1 < 3) ? 1 : 0;
-    if (t1) {
-        uint32_t s = br_get(b, t1);
-        for (i = 0; i < t1; i++) level[i] = ((s >> (t1 - 1 - i)) & 1) ? -1 : 1;
+    {   /* trailing ones: up to three sign bits, decoded without a loop (entries beyond t1 are overwritten below) */
+        const uint32_t s = (uint32_t)(b->cache >> 61);          /* next 3 bits; b->bits >= 32 - 16 here */
+        level[0] = 1 - (int)((s >> 1) & 2); level[1] = 1 - (int)(s & 2); level[2] = 1 - (int)((s << 1) & 2);
+        br_skip(b, t1);
     }
     for (i = t1; i < tc; i++) {
         int lv;
@@ -59,10 +60,14 @@ static inline int h264_cavlc_block(br_t *b, int nc, int max_coeff, int16_t *out,
         if (b->bits < 32) br_refill(b);
         v = (uint32_t)(b->cache >> 32);
         q = g_lvl[sl][v >> 24];
-        if (q[1]) {                               /* prefix + suffix within 8 bits */
+        if (q[1] && i != t1) {                    /* prefix + suffix within 8 bits: level and next suffixLength from the table */
+            level[i] = q[0]; br_skip(b, q[1]); sl = q[2];
+            continue;
+        }
+        if (q[1]) {                               /* first level after the trailing ones: levelCode += 2 when t1 < 3 */
             lv = q[0];
             br_skip(b, q[1]);
-            if (i == t1 && t1 < 3) lv += lv > 0 ? 1 : -1;           /* levelCode += 2 */
+            if (t1 < 3) lv += lv > 0 ? 1 : -1;
         } else {
             int prefix, code;
             if (v < 0x10000u) return -1;          /* level_prefix > 15: not Baseline (h264bsd_cavlc.c:513-514) */
@@ -95,14 +100,12 @@ static inline int h264_cavlc_block(br_t *b, int nc, int max_coeff, int16_t *out,
     for (i = 0; i < tc - 1 && zeros_left > 0; i++) {
         int run;
         out[scan[pos]] = (int16_t)level[i];
-        if (zeros_left <= 6) {
-            const uint8_t *e = g_rb[zeros_left - 1][br_peek(b, 3)];
-            br_skip(b, e[0]); run = e[1];
-        } else {
-            v = br_peek(b, 11);
-            if (v >> 8) { run = 7 - (int)(v >> 8); br_skip(b, 3); }
-            else {
+        {
+            const uint8_t *e = g_rb[(zeros_left < 7 ? zeros_left : 7) - 1][br_peek(b, 3)];
+            if (e[0]) { br_skip(b, e[0]); run = e[1]; }
+            else {                               /* zerosLeft > 6 and 000 prefix: unary tail, up to 11 bits */
                 int lz;
+                v = br_peek(b, 11);
                 if (!v) return -1;
                 lz = __builtin_clz(v) - 21;      /* leading zeros within the 11 bits */
                 run = lz + 4; br_skip(b, lz + 1);

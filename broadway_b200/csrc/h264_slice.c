@@ -170,12 +170,13 @@ static int parse_residual(sl_t *s, int cbp, int i16)
     for (blk = 0; blk < 16; blk++) {
         /* luma4x4BlkIdx -> cache index of (x4, y4) */
         const int idx = 9 + (((blk & 1) | ((blk >> 1) & 2))) + 8 * (((blk >> 1) & 1) | ((blk >> 2) & 2));
-        int16_t *p = slot_ptr(s, slot);
-        if (!((cbp >> (blk >> 2)) & 1)) {
-            c->tc[blk] = 0;
-            if (dc_nz) { memset(p, 0, 32); mask |= 1u << blk; slot++; }
+        int16_t *p;
+        if (!((cbp >> (blk >> 2)) & 1)) {              /* 8x8 quadrant without AC: TotalCoeff stays 0 (context was cleared) */
+            if (dc_nz) { int k4; for (k4 = 0; k4 < 4; k4++) { memset(slot_ptr(s, slot), 0, 32); mask |= 1u << (blk + k4); slot++; } }
+            blk += 3;
             continue;
         }
+        p = slot_ptr(s, slot);
         if (i16) tc = h264_cavlc_block(b, nc_of(lc, idx, 8), 15, p, H264_ZIGZAG4x4 + 1);
         else     tc = h264_cavlc_block(b, nc_of(lc, idx, 8), 16, p, H264_ZIGZAG4x4);
         if (tc < 0) return -1;

@@ -38,6 +38,9 @@ SMALL = [
     ("one_col",            1,  6, 4, dict(p_intra_permille=200)),
     ("odd_size",          11,  9, 5, dict(p_intra_permille=150, slices_per_pic=2)),
     ("wide",              45,  3, 3, dict(p_intra_permille=150)),
+    ("big_levels",        20, 12, 4, dict(max_level=200, qp=2, qp_jitter=0, max_coeffs=3, coded_blk_permille=500)),
+    ("escape_levels",     20, 12, 4, dict(max_level=2000, qp=0, qp_jitter=0, max_coeffs=1, coded_blk_permille=400)),
+    ("many_coeffs",       20, 12, 3, dict(max_level=6, max_coeffs=16, coded_blk_permille=700, qp=20)),
 ]
 
 # BASELINE.json's full-size configurations (few frames: the reference runs at ~20 fps per core)
@@ -54,3 +57,21 @@ def make_stream(case):
     from broadway_b200 import bitstream
     name, w, h, n, kw = case
     return bitstream.synth(w, h, n, seed=SEED + sum(map(ord, name)), **kw)
+
+
+def reverse_slice_order(data):
+    """Arbitrary slice order (ASO, Baseline): the slices of every picture in reverse order.  Slice membership,
+    not arrival order, decides neighbour availability, so the decoded pictures do not change."""
+    sc = b"\x00\x00\x00\x01"
+    nals = [n for n in data.split(sc) if n]
+    out, cur = [], []
+    for n in nals:
+        if n[0] & 31 in (1, 5):
+            if (n[1] & 0x80) and cur:
+                out.extend(reversed(cur)); cur = []
+            cur.append(n)
+        else:
+            out.extend(reversed(cur)); cur = []
+            out.append(n)
+    out.extend(reversed(cur))
+    return b"".join(sc + n for n in out)

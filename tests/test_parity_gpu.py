@@ -234,3 +234,11 @@ def test_rgba_cropped_output_matches_wrapper_formula(crop):
         assert rect[3] == H - 8
     for a, f in zip(got, i420):
         assert a == _rgba_reference(f, W, H, *rect)
+
+
+def test_arbitrary_slice_order_on_gpu(golden):
+    """ASO: the wavefront kernels take availability from the records, not from arrival order."""
+    for name in ("multi_slice", "deblock_idc2"):
+        case = next(c for c in cases.SMALL if c[0] == name)
+        got, info = capi.decode_annexb(cases.reverse_slice_order(cases.make_stream(case)))
+        assert info["err_mbs"] == 0 and got == golden[name]["frame_md5"]
