@@ -46,7 +46,7 @@ WORKER = textwrap.dedent('''
     golden = json.load(open(os.path.join(%(root)r, "tests", "golden", "streams.json")))["idr_period"]["frame_md5"]
     ok = [m for r in res for m in r] == golden
     mine = shard.assign([len(s) for s in segs], world)[rank]
-    print("RANK", rank, "OK" if ok else "BAD", "units", mine, flush=True)
+    open(os.path.join(%(out)r, "rank%%d.json" %% rank), "w").write(json.dumps({"ok": ok, "units": mine}))
     dist.barrier(); dist.destroy_process_group()
     sys.exit(0 if ok else 1)
 ''')
@@ -54,11 +54,13 @@ WORKER = textwrap.dedent('''
 
 def test_two_ranks_gloo(tmp_path):
     script = tmp_path / "worker.py"
-    script.write_text(WORKER % {"root": ROOT})
+    script.write_text(WORKER % {"root": ROOT, "out": str(tmp_path)})
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                         "--master-port", "29533", str(script)], capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    assert r.stdout.count("OK") == 2
-    # the three segments were split 2 + 1 across the ranks
-    assert "units [0]" in r.stdout or "units [0, " in r.stdout
+    import json
+    res = [json.load(open(tmp_path / ("rank%d.json" % k))) for k in range(2)]
+    assert all(x["ok"] for x in res)
+    # the three segments were split 2 + 1 across the ranks, every segment exactly once
+    assert sorted(res[0]["units"] + res[1]["units"]) == [0, 1, 2] and {len(res[0]["units"]), len(res[1]["units"])} == {1, 2}
