@@ -172,7 +172,7 @@ static void launch_kernels(h264b200_engine *e, const Batch &b, const BatchPlan &
 {
     cudaStream_t s = e->s_comp;
     if (tev) cudaEventRecord(tev[0], s);
-    if (pl.k1) { uint32_t blocks = (pl.total_mbs * 32 + 255) / 256; k1_transform<<<blocks, 256, 0, s>>>(b); e->st.kernel_launches++; }
+    if (pl.k1) { uint32_t blocks = (pl.total_mbs * 8 + 255) / 256; k1_transform<<<blocks, 256, 0, s>>>(b); e->st.kernel_launches++; }   /* 8 lanes per macroblock */
     if (tev) cudaEventRecord(tev[1], s);
     if (pl.k2) { k2_inter<<<(pl.total_mbs * 16 + K2_THREADS - 1) / K2_THREADS, K2_THREADS, 0, s>>>(b); e->st.kernel_launches++; }   /* 16 threads per macroblock */
     if (tev) cudaEventRecord(tev[2], s);
