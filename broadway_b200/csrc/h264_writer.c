@@ -631,10 +631,12 @@ static void write_inter_mb(wr_t *w, bitw_t *b, wmb_t *cur, int mbx, int mby)
 
 /* ------------------------------------------------------- stream assembly */
 typedef struct { int idc, a, bq, qp; } slice_par_t;
+/* per-picture reference handling (dpb_stress): nal_ref_idc, list reordering, adaptive marking */
+typedef struct { int ref_idc; int reorder; int mmco1_diff_minus1; } pic_par_t;
 
 static size_t write_slice(wr_t *w, uint8_t *out, size_t cap, uint8_t *scratch, size_t scratch_cap,
                           uint32_t first_mb, uint32_t n_mbs, int idr, int is_p, uint32_t frame_num,
-                          uint32_t idr_pic_id, uint32_t poc_lsb, const slice_par_t *sp)
+                          uint32_t idr_pic_id, uint32_t poc_lsb, const slice_par_t *sp, const pic_par_t *pp)
 {
     const h264w_params_t *p = w->p;
     bitw_t b; uint32_t i, skip_run = 0;
@@ -649,10 +651,21 @@ static size_t write_slice(wr_t *w, uint8_t *out, size_t cap, uint8_t *scratch, s
         int def = (int)p->num_ref_frames;            /* PPS default = num_ref_frames */
         if (w->num_ref_active != def) { bw_put(&b, 1, 1); bw_ue(&b, (uint32_t)(w->num_ref_active - 1)); }
         else bw_put(&b, 1, 0);
-        bw_put(&b, 1, 0);                            /* ref_pic_list_reordering_flag_l0 */
+        if (pp->reorder) {                           /* move the second most recent short-term picture to index 0 (8.2.4.3.1) */
+            bw_put(&b, 1, 1);                        /* ref_pic_list_reordering_flag_l0 */
+            bw_ue(&b, 0); bw_ue(&b, 1);              /* reordering_of_pic_nums_idc 0, abs_diff_pic_num_minus1 = 1 */
+            bw_ue(&b, 3);                            /* end */
+        } else bw_put(&b, 1, 0);
     }
-    /* dec_ref_pic_marking (every picture is a reference picture) */
-    if (idr) { bw_put(&b, 1, 0); bw_put(&b, 1, 0); } else bw_put(&b, 1, 0);
+    /* dec_ref_pic_marking: only in reference pictures (7.3.3) */
+    if (pp->ref_idc) {
+        if (idr) { bw_put(&b, 1, 0); bw_put(&b, 1, 0); }
+        else if (pp->mmco1_diff_minus1 >= 0) {       /* adaptive marking: drop one short-term picture (MMCO 1) */
+            bw_put(&b, 1, 1);
+            bw_ue(&b, 1); bw_ue(&b, (uint32_t)pp->mmco1_diff_minus1);
+            bw_ue(&b, 0);
+        } else bw_put(&b, 1, 0);
+    }
     bw_se(&b, sp->qp - p->qp);                       /* slice_qp_delta vs pic_init_qp */
     /* deblocking_filter_control_present_flag = 1 */
     bw_ue(&b, (uint32_t)sp->idc);
@@ -684,7 +697,7 @@ static size_t write_slice(wr_t *w, uint8_t *out, size_t cap, uint8_t *scratch, s
     if (is_p && skip_run) bw_ue(&b, skip_run);
     bw_trailing(&b);
     if (b.ovf) return 0;
-    return emit_nal(out, cap, 1, idr ? 5 : 1, scratch, b.pos);
+    return emit_nal(out, cap, pp->ref_idc, idr ? 5 : 1, scratch, b.pos);
 }
 
 void h264w_default_params(h264w_params_t *p, uint32_t width_mbs, uint32_t height_mbs, uint32_t n_frames)
@@ -708,7 +721,7 @@ size_t h264w_bound(const h264w_params_t *p)
 size_t h264w_generate(const h264w_params_t *p, uint8_t *out, size_t cap)
 {
     wr_t w; bitw_t b; uint8_t hdr[64]; uint8_t *scratch; size_t scratch_cap, o = 0, n;
-    uint32_t f, since_idr = 0, idr_id = 0, s;
+    uint32_t f, since_idr = 0, idr_id = 0, s, n_short = 0, prev_ref_fn = 0;
     if (!p || !out || !p->width_mbs || !p->height_mbs || !p->n_frames) return 0;
     if (p->num_ref_frames < 1 || p->num_ref_frames > 16 || (p->poc_type != 0 && p->poc_type != 2)) return 0;
     if (p->qp < 0 || p->qp > 51 || p->deblock_idc > 2) return 0;
@@ -763,9 +776,21 @@ size_t h264w_generate(const h264w_params_t *p, uint8_t *out, size_t cap)
         int idr = f == 0 || (p->idr_period && f % p->idr_period == 0);
         int is_p = !idr && !p->intra_only;
         uint32_t nsl = p->slices_per_pic ? p->slices_per_pic : 1, first = 0;
-        if (idr) { since_idr = 0; idr_id++; }
+        pic_par_t pp;
+        uint32_t frame_num;
+        if (idr) { since_idr = 0; idr_id++; n_short = 0; }
         if (nsl > w.nmb) nsl = w.nmb;
-        w.num_ref_active = (int)(since_idr < p->num_ref_frames ? since_idr : p->num_ref_frames);
+        /* frame_num: 0 at an IDR, else one more than the last REFERENCE picture's (7.4.3) */
+        frame_num = idr ? 0 : prev_ref_fn + 1;
+        pp.ref_idc = 1; pp.reorder = 0; pp.mmco1_diff_minus1 = -1;
+        if (p->dpb_stress && !idr) {
+            /* every third picture is a non-reference picture (never two in a row: POC type 2 forbids it) */
+            if (since_idr % 3 == 2) pp.ref_idc = 0;
+            if (is_p && n_short >= 2 && since_idr % 2 == 0) pp.reorder = 1;
+            /* a reference picture sometimes removes the oldest short-term picture itself instead of the sliding window */
+            if (pp.ref_idc && n_short >= 2 && since_idr % 4 == 1) pp.mmco1_diff_minus1 = (int)n_short - 1;
+        }
+        w.num_ref_active = (int)(n_short < p->num_ref_frames ? n_short : p->num_ref_frames);
         if (w.num_ref_active < 1) w.num_ref_active = 1;
         for (s = 0; s < nsl; s++) {
             uint32_t cnt = (w.nmb * (s + 1)) / nsl - (w.nmb * s) / nsl;
@@ -779,9 +804,15 @@ size_t h264w_generate(const h264w_params_t *p, uint8_t *out, size_t cap)
             }
             w.cur_slice = s + 1;
             n = write_slice(&w, out + o, cap - o, scratch, scratch_cap, first, cnt, idr, is_p,
-                            since_idr, idr_id & 0xffff, since_idr * 2, &sp);
+                            frame_num, idr_id & 0xffff, since_idr * 2, &sp, &pp);
             if (!n) goto fail;
             o += n; first += cnt;
+        }
+        if (pp.ref_idc) {                            /* decoded reference picture marking as the decoder will do it */
+            if (idr) n_short = 1;
+            else if (pp.mmco1_diff_minus1 >= 0) n_short = n_short - 1 + 1;
+            else n_short = n_short < p->num_ref_frames ? n_short + 1 : p->num_ref_frames;
+            prev_ref_fn = frame_num;
         }
         since_idr++;
     }

@@ -8,7 +8,8 @@ I_PCM, every partition shape, P_Skip runs, intra in P pictures with and without
 constrained_intra_pred, several reference frames, several slices per picture
 with per-slice deblocking controls (idc 0/1/2, offsets), QP changes, chroma QP
 offset, far out-of-picture vectors (edge clamp), POC types 0 and 2, cropping,
-and the degenerate one-macroblock picture.
+the degenerate one-macroblock picture, escape-coded levels, and decoded-picture-buffer
+handling (non-reference pictures, frame_num wrap, list reordering, MMCO 1).
 """
 
 # name, width_mbs, height_mbs, frames, overrides
@@ -41,6 +42,9 @@ SMALL = [
     ("big_levels",        20, 12, 4, dict(max_level=200, qp=2, qp_jitter=0, max_coeffs=3, coded_blk_permille=500)),
     ("escape_levels",     20, 12, 4, dict(max_level=2000, qp=0, qp_jitter=0, max_coeffs=1, coded_blk_permille=400)),
     ("many_coeffs",       20, 12, 3, dict(max_level=6, max_coeffs=16, coded_blk_permille=700, qp=20)),
+    # decoded picture buffer: non-reference pictures, frame_num wrap (24 > 16), list reordering, MMCO 1
+    ("dpb_stress",        20, 12, 24, dict(num_ref_frames=3, dpb_stress=1)),
+    ("dpb_stress_poc0",   11,  9, 24, dict(num_ref_frames=4, dpb_stress=1, poc_type=0, slices_per_pic=2, p_intra_permille=100)),
 ]
 
 # BASELINE.json's full-size configurations (few frames: the reference runs at ~20 fps per core)
