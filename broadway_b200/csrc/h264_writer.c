@@ -632,7 +632,7 @@ static void write_inter_mb(wr_t *w, bitw_t *b, wmb_t *cur, int mbx, int mby)
 /* ------------------------------------------------------- stream assembly */
 typedef struct { int idc, a, bq, qp; } slice_par_t;
 /* per-picture reference handling (dpb_stress): nal_ref_idc, list reordering, adaptive marking */
-typedef struct { int ref_idc; int reorder; int mmco1_diff_minus1; } pic_par_t;
+typedef struct { int ref_idc; int reorder_diff_minus1; int mmco1_diff_minus1; int make_long; int drop_long; } pic_par_t;
 
 static size_t write_slice(wr_t *w, uint8_t *out, size_t cap, uint8_t *scratch, size_t scratch_cap,
                           uint32_t first_mb, uint32_t n_mbs, int idr, int is_p, uint32_t frame_num,
@@ -651,18 +651,20 @@ static size_t write_slice(wr_t *w, uint8_t *out, size_t cap, uint8_t *scratch, s
         int def = (int)p->num_ref_frames;            /* PPS default = num_ref_frames */
         if (w->num_ref_active != def) { bw_put(&b, 1, 1); bw_ue(&b, (uint32_t)(w->num_ref_active - 1)); }
         else bw_put(&b, 1, 0);
-        if (pp->reorder) {                           /* move the second most recent short-term picture to index 0 (8.2.4.3.1) */
+        if (pp->reorder_diff_minus1 >= 0) {          /* move an older short-term picture to index 0 (8.2.4.3.1) */
             bw_put(&b, 1, 1);                        /* ref_pic_list_reordering_flag_l0 */
-            bw_ue(&b, 0); bw_ue(&b, 1);              /* reordering_of_pic_nums_idc 0, abs_diff_pic_num_minus1 = 1 */
+            bw_ue(&b, 0); bw_ue(&b, (uint32_t)pp->reorder_diff_minus1);   /* reordering_of_pic_nums_idc 0, abs_diff_pic_num_minus1 */
             bw_ue(&b, 3);                            /* end */
         } else bw_put(&b, 1, 0);
     }
     /* dec_ref_pic_marking: only in reference pictures (7.3.3) */
     if (pp->ref_idc) {
         if (idr) { bw_put(&b, 1, 0); bw_put(&b, 1, 0); }
-        else if (pp->mmco1_diff_minus1 >= 0) {       /* adaptive marking: drop one short-term picture (MMCO 1) */
+        else if (pp->mmco1_diff_minus1 >= 0 || pp->make_long || pp->drop_long) {   /* adaptive marking (8.2.5.4) */
             bw_put(&b, 1, 1);
-            bw_ue(&b, 1); bw_ue(&b, (uint32_t)pp->mmco1_diff_minus1);
+            if (pp->mmco1_diff_minus1 >= 0) { bw_ue(&b, 1); bw_ue(&b, (uint32_t)pp->mmco1_diff_minus1); }   /* short-term -> unused */
+            if (pp->drop_long) { bw_ue(&b, 2); bw_ue(&b, 0); }                                               /* LongTermPicNum 0 -> unused */
+            if (pp->make_long) { bw_ue(&b, 4); bw_ue(&b, 1); bw_ue(&b, 6); bw_ue(&b, 0); }                   /* max idx + 1 = 1; current -> long-term idx 0 */
             bw_ue(&b, 0);
         } else bw_put(&b, 1, 0);
     }
@@ -721,7 +723,8 @@ size_t h264w_bound(const h264w_params_t *p)
 size_t h264w_generate(const h264w_params_t *p, uint8_t *out, size_t cap)
 {
     wr_t w; bitw_t b; uint8_t hdr[64]; uint8_t *scratch; size_t scratch_cap, o = 0, n;
-    uint32_t f, since_idr = 0, idr_id = 0, s, n_short = 0, prev_ref_fn = 0;
+    uint32_t f, since_idr = 0, idr_id = 0, s, n_short = 0, n_long = 0, prev_ref_fn = 0, ref_ord = 0;
+    uint32_t short_ord[17];                          /* ordinal (count of reference pictures since the IDR) of each short-term picture, most recent first */
     if (!p || !out || !p->width_mbs || !p->height_mbs || !p->n_frames) return 0;
     if (p->num_ref_frames < 1 || p->num_ref_frames > 16 || (p->poc_type != 0 && p->poc_type != 2)) return 0;
     if (p->qp < 0 || p->qp > 51 || p->deblock_idc > 2) return 0;
@@ -778,19 +781,28 @@ size_t h264w_generate(const h264w_params_t *p, uint8_t *out, size_t cap)
         uint32_t nsl = p->slices_per_pic ? p->slices_per_pic : 1, first = 0;
         pic_par_t pp;
         uint32_t frame_num;
-        if (idr) { since_idr = 0; idr_id++; n_short = 0; }
+        if (idr) { since_idr = 0; idr_id++; n_short = 0; n_long = 0; ref_ord = 0; }
         if (nsl > w.nmb) nsl = w.nmb;
         /* frame_num: 0 at an IDR, else one more than the last REFERENCE picture's (7.4.3) */
         frame_num = idr ? 0 : prev_ref_fn + 1;
-        pp.ref_idc = 1; pp.reorder = 0; pp.mmco1_diff_minus1 = -1;
+        pp.ref_idc = 1; pp.reorder_diff_minus1 = -1; pp.mmco1_diff_minus1 = -1; pp.make_long = 0; pp.drop_long = 0;
         if (p->dpb_stress && !idr) {
+            /* PicNum of a short-term picture = CurrPicNum - (ref_ord - its ordinal) as long as fewer than 16 reference
+             * pictures lie between (frame_num has 4 bits) */
             /* every third picture is a non-reference picture (never two in a row: POC type 2 forbids it) */
             if (since_idr % 3 == 2) pp.ref_idc = 0;
-            if (is_p && n_short >= 2 && since_idr % 2 == 0) pp.reorder = 1;
-            /* a reference picture sometimes removes the oldest short-term picture itself instead of the sliding window */
-            if (pp.ref_idc && n_short >= 2 && since_idr % 4 == 1) pp.mmco1_diff_minus1 = (int)n_short - 1;
+            if (is_p && n_short >= 2 && since_idr % 2 == 0) pp.reorder_diff_minus1 = (int)(ref_ord - short_ord[1]) - 1;
+            if (pp.ref_idc) {
+                if (p->dpb_stress > 1 && since_idr % 8 == 3 && !n_long) pp.make_long = 1;
+                else if (p->dpb_stress > 1 && since_idr % 8 == 7 && n_long) pp.drop_long = 1;
+                /* a reference picture sometimes removes the oldest short-term picture itself instead of the sliding window;
+                 * it must when adaptive marking is on and the buffer is full */
+                if (n_short >= 2 && (since_idr % 4 == 1 || ((pp.make_long || pp.drop_long) && n_short + n_long - (uint32_t)pp.drop_long >= p->num_ref_frames)))
+                    pp.mmco1_diff_minus1 = (int)(ref_ord - short_ord[n_short - 1]) - 1;
+                if ((pp.make_long || pp.drop_long) && pp.mmco1_diff_minus1 < 0 && n_short + n_long - (uint32_t)pp.drop_long >= p->num_ref_frames) { pp.make_long = 0; pp.drop_long = 0; }
+            }
         }
-        w.num_ref_active = (int)(n_short < p->num_ref_frames ? n_short : p->num_ref_frames);
+        w.num_ref_active = (int)(n_short + n_long < p->num_ref_frames ? n_short + n_long : p->num_ref_frames);
         if (w.num_ref_active < 1) w.num_ref_active = 1;
         for (s = 0; s < nsl; s++) {
             uint32_t cnt = (w.nmb * (s + 1)) / nsl - (w.nmb * s) / nsl;
@@ -809,9 +821,15 @@ size_t h264w_generate(const h264w_params_t *p, uint8_t *out, size_t cap)
             o += n; first += cnt;
         }
         if (pp.ref_idc) {                            /* decoded reference picture marking as the decoder will do it */
-            if (idr) n_short = 1;
-            else if (pp.mmco1_diff_minus1 >= 0) n_short = n_short - 1 + 1;
-            else n_short = n_short < p->num_ref_frames ? n_short + 1 : p->num_ref_frames;
+            uint32_t k;
+            if (idr) { n_short = 0; n_long = 0; }
+            else if (pp.mmco1_diff_minus1 >= 0 || pp.make_long || pp.drop_long) {
+                if (pp.mmco1_diff_minus1 >= 0) n_short--;                    /* the oldest one */
+                if (pp.drop_long) n_long = 0;
+            } else if (n_short + n_long >= p->num_ref_frames && n_short) n_short--;   /* sliding window */
+            if (pp.make_long) n_long = 1;
+            else { for (k = n_short; k > 0; k--) short_ord[k] = short_ord[k - 1]; short_ord[0] = ref_ord; n_short++; }
+            ref_ord++;
             prev_ref_fn = frame_num;
         }
         since_idr++;

@@ -52,7 +52,8 @@ typedef struct {
     uint32_t part_mix;             /* 0: 16x16 only; 1: all partition shapes */
     uint32_t crop;                 /* 1: signal frame cropping of 8 luma rows (1088 -> 1080) */
     uint32_t multi_slice_params;   /* 1: vary deblock idc/offsets and QP per slice */
-    uint32_t dpb_stress;           /* 1: non-reference pictures, ref list reordering and MMCO 1 marking (needs num_ref_frames >= 2) */
+    uint32_t dpb_stress;           /* 1: non-reference pictures, ref list reordering and MMCO 1 marking (needs num_ref_frames >= 2);
+                                      2: also long-term pictures (MMCO 4+6, released by MMCO 2) */
 } h264w_params_t;
 
 /* Fill *p with the defaults used by BASELINE.json config 3 at the given size. */

@@ -45,6 +45,9 @@ SMALL = [
     # decoded picture buffer: non-reference pictures, frame_num wrap (24 > 16), list reordering, MMCO 1
     ("dpb_stress",        20, 12, 24, dict(num_ref_frames=3, dpb_stress=1)),
     ("dpb_stress_poc0",   11,  9, 24, dict(num_ref_frames=4, dpb_stress=1, poc_type=0, slices_per_pic=2, p_intra_permille=100)),
+    # ... plus long-term reference pictures (MMCO 4 + 6, released by MMCO 2)
+    ("dpb_long_term",     11,  9, 40, dict(num_ref_frames=3, dpb_stress=2)),
+    ("dpb_long_term_5",   11,  9, 40, dict(num_ref_frames=5, dpb_stress=2, poc_type=0, p_intra_permille=60)),
 ]
 
 # BASELINE.json's full-size configurations (few frames: the reference runs at ~20 fps per core)
