@@ -425,7 +425,12 @@ u8 *h264b200NextOutputPictureAsync(storage_t *pStorage, u32 *picId, u32 *isIdrPi
     if (picId) *picId = o->pic_id;
     if (isIdrPic) *isIdrPic = o->is_idr;
     if (numErrMbs) *numErrMbs = o->num_err_mbs;
-    if (d->be->frame_host_async) return d->be->frame_host_async(d->be, d->be_inst, o->slot);
+    if (d->be->frame_host_async && d->be->frame_wait) {
+        uint32_t gen = 0;
+        u8 *p = d->be->frame_host_async(d->be, d->be_inst, o->slot, &gen);
+        *ticket = (u32)o->slot | (gen << 8);          /* which picture of the slot: slots are re-used */
+        return p;
+    }
     return d->be->frame_host(d->be, d->be_inst, o->slot, &err);
 }
 u32 h264b200PictureWait(storage_t *pStorage, u32 ticket)
@@ -433,7 +438,13 @@ u32 h264b200PictureWait(storage_t *pStorage, u32 ticket)
     h264_decoder_t *d = DEC(pStorage);
     uint32_t err = 0;
     if (!d || !d->be_inst) return 0xffffffffu;
-    if (!d->be->frame_host(d->be, d->be_inst, (int)ticket, &err)) return 0xffffffffu;
+    if (d->be->frame_host_async && d->be->frame_wait) {
+        int rc = d->be->frame_wait(d->be, d->be_inst, (int)(ticket & 0xff), ticket >> 8, &err);
+        if (rc < 0) return 0xffffffffu;
+        if (rc > 0) return 0xfffffffeu;               /* waited too long: a later picture already occupies the slot */
+        return err;
+    }
+    if (!d->be->frame_host(d->be, d->be_inst, (int)(ticket & 0xff), &err)) return 0xffffffffu;
     return err;
 }
 

@@ -66,7 +66,9 @@ struct Inst {
     size_t frame_bytes;
     uint8_t *d_frames, *h_frames;
     cudaEvent_t slot_ready[H264_MAX_SLOTS];   /* the host mirror of the slot is complete */
-    uint8_t slot_flags[H264_MAX_SLOTS];       /* bit 0: picture queued, not launched; bit 1: launched, host has not waited yet */
+    uint8_t slot_flags[H264_MAX_SLOTS];       /* bit 1: a copy-out into the slot's mirror has been issued (slot_ready is valid) */
+    uint32_t slot_qgen[H264_MAX_SLOTS];       /* pictures handed over (queued) into the slot so far */
+    uint32_t slot_lgen[H264_MAX_SLOTS];       /* generation of the last LAUNCHED picture of the slot */
     PicBuf bufs[NBUF];
     int next_buf;
     int batched;
@@ -313,7 +315,7 @@ static uint32_t submit_locked(h264b200_engine *e)
             e->st.d2h_bytes += in->frame_bytes;
         }
         cudaEventRecord(in->slot_ready[slot], e->s_d2h);
-        in->slot_flags[slot] = 2;
+        in->slot_flags[slot] = 2; in->slot_lgen[slot] = in->slot_qgen[slot];
         in->queued--;
     }
     cudaMemcpyAsync(e->h_err, e->d_err, sizeof(uint32_t), cudaMemcpyDeviceToHost, e->s_d2h);
@@ -344,7 +346,7 @@ static void *be_inst_create(h264_backend_t *be, uint32_t wm, uint32_t hm, uint32
             Inst *c = e->pool[i];
             if (c->wm == wm && c->hm == hm && c->n_slots == n_slots) {
                 e->pool.erase(e->pool.begin() + i);
-                memset(c->slot_flags, 0, sizeof c->slot_flags);
+                memset(c->slot_flags, 0, sizeof c->slot_flags); memset(c->slot_qgen, 0, sizeof c->slot_qgen); memset(c->slot_lgen, 0, sizeof c->slot_lgen);
                 c->next_buf = 0; c->queued = 0; c->out_format = H264B200_OUT_I420;
                 c->batched = (e->flags & H264B200_ENGINE_BATCHED) != 0;
                 for (int k = 0; k < NBUF; k++) c->bufs[k].state = 0;
@@ -425,35 +427,61 @@ static int be_pic_submit(h264_backend_t *be, void *inst, h264_pic_input_t *pic)
     std::lock_guard<std::mutex> lk(e->mu);
     if (in->queued) submit_locked(e);          /* consecutive pictures of one stream depend on each other */
     p->state = 2;
-    in->slot_flags[pic->cur_slot] |= 1;
+    in->slot_qgen[pic->cur_slot]++;
     in->queued++;
     e->queue.push_back(p);
     if (!in->batched) submit_locked(e);
     return 0;
 }
 
-static uint8_t *be_frame_host(h264_backend_t *be, void *inst, int slot, uint32_t *error_flags)
+/* Wait until generation `gen` of `slot` is in its host mirror.  Returns 0, or 1 when a LATER picture has already been
+ * launched into the slot (its mirror may be overwritten: the caller waited too long), or -1 on a CUDA error. */
+static int wait_slot(h264b200_engine *e, Inst *in, int slot, uint32_t gen)
 {
-    h264b200_engine *e = (h264b200_engine *)be->ctx; Inst *in = (Inst *)inst;
-    if (slot < 0 || slot >= (int)in->n_slots) return NULL;
-    if (in->slot_flags[slot] & 1) { std::lock_guard<std::mutex> lk(e->mu); submit_locked(e); }
+    if ((int32_t)(in->slot_lgen[slot] - gen) < 0) { std::lock_guard<std::mutex> lk(e->mu); submit_locked(e); }
+    if (in->slot_lgen[slot] != gen) return 1;
     if (in->slot_flags[slot] & 2) {
         set_device(e);
         cudaError_t er = cudaEventSynchronize(in->slot_ready[slot]);
-        if (er != cudaSuccess) { fprintf(stderr, "h264b200: reconstruction failed: %s\n", cudaGetErrorString(er)); return NULL; }
-        in->slot_flags[slot] &= (uint8_t)~2;
+        if (er != cudaSuccess) { fprintf(stderr, "h264b200: reconstruction failed: %s\n", cudaGetErrorString(er)); return -1; }
     }
-    if (error_flags) *error_flags = *e->h_err;
+    return 0;
+}
+
+static uint8_t *slot_mirror(Inst *in, int slot)
+{
     if (in->out_format == H264B200_OUT_RGBA && in->h_rgba) return in->h_rgba + (size_t)slot * in->rgba_bytes;
     return in->h_frames + (size_t)slot * in->frame_bytes;
 }
 
-static uint8_t *be_frame_host_async(h264_backend_t *be, void *inst, int slot)
+static uint8_t *be_frame_host(h264_backend_t *be, void *inst, int slot, uint32_t *error_flags)
+{
+    h264b200_engine *e = (h264b200_engine *)be->ctx; Inst *in = (Inst *)inst;
+    if (slot < 0 || slot >= (int)in->n_slots) return NULL;
+    if (wait_slot(e, in, slot, in->slot_qgen[slot]) < 0) return NULL;
+    if (error_flags) *error_flags = *e->h_err;
+    return slot_mirror(in, slot);
+}
+
+/* non-blocking: where the newest picture of `slot` will be, and its generation (for frame_wait) */
+static uint8_t *be_frame_host_async(h264_backend_t *be, void *inst, int slot, uint32_t *gen)
 {
     Inst *in = (Inst *)inst; (void)be;
     if (slot < 0 || slot >= (int)in->n_slots) return NULL;
-    if (in->out_format == H264B200_OUT_RGBA && in->h_rgba) return in->h_rgba + (size_t)slot * in->rgba_bytes;
-    return in->h_frames + (size_t)slot * in->frame_bytes;
+    if (gen) *gen = in->slot_qgen[slot];
+    return slot_mirror(in, slot);
+}
+
+static int be_frame_wait(h264_backend_t *be, void *inst, int slot, uint32_t gen, uint32_t *error_flags)
+{
+    h264b200_engine *e = (h264b200_engine *)be->ctx; Inst *in = (Inst *)inst;
+    if (slot < 0 || slot >= (int)in->n_slots) return -1;
+    /* the ticket carries 24 bits of the generation: take the value nearest below the current one */
+    uint32_t full = (in->slot_qgen[slot] & 0xff000000u) | (gen & 0xffffffu);
+    if (full > in->slot_qgen[slot]) full -= 1u << 24;
+    int rc = wait_slot(e, in, slot, full);
+    if (error_flags) *error_flags = *e->h_err;
+    return rc;
 }
 
 /* output format of an instance: 0 ok.  RGBA buffers are allocated on first use. */
@@ -531,6 +559,7 @@ extern "C" h264b200_engine_t *h264b200EngineCreateEx(int device, uint32_t flags)
     e->be.inst_create = be_inst_create; e->be.inst_destroy = be_inst_destroy; e->be.pic_begin = be_pic_begin;
     e->be.coef_grow = be_coef_grow; e->be.pic_submit = be_pic_submit; e->be.frame_host = be_frame_host;
     e->be.frame_host_async = be_frame_host_async;
+    e->be.frame_wait = be_frame_wait;
     e->be.set_output = be_set_output;
     e->be.destroy = be_destroy; e->be.ctx = e;
     return e;

@@ -142,7 +142,9 @@ struct h264_backend {
     void  (*destroy)(h264_backend_t *be);
     void  *ctx;
     /* optional: address frame_host will return for `slot`, without launching or waiting */
-    uint8_t *(*frame_host_async)(h264_backend_t *be, void *inst, int slot);
+    uint8_t *(*frame_host_async)(h264_backend_t *be, void *inst, int slot, uint32_t *gen);
+    /* optional: wait for generation `gen` (from frame_host_async) of `slot`; 0 ok, 1 overwritten by a later picture, -1 error */
+    int (*frame_wait)(h264_backend_t *be, void *inst, int slot, uint32_t gen, uint32_t *error_flags);
     /* optional: output format of an instance (H264B200_OUT_*) and the cropping rectangle in luma samples */
     int (*set_output)(h264_backend_t *be, void *inst, int format, int crop_left, int crop_top, int crop_width, int crop_height);
 };

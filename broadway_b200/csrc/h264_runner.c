@@ -113,7 +113,7 @@ static void consume_prev(worker_t *w, rstream_t *s, uint32_t stream_index)
         double t0 = now_s();
         u32 rc = h264b200PictureWait(&s->st, q->ticket);
         w->wait_s += now_s() - t0;
-        if (rc == 0xffffffffu) { s->failed = 1; continue; }
+        if (rc == 0xffffffffu || rc == 0xfffffffeu) { s->failed = 1; continue; }
         if (!s->width) { s->width = 16 * h264bsdPicWidth(&s->st); s->height = 16 * h264bsdPicHeight(&s->st); }
         if (r->cb) r->cb(r->user, stream_index, s->out_index, q->ptr, s->width, s->height, q->pic_id, q->err);
         s->out_index++;

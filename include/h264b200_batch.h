@@ -29,7 +29,8 @@ void h264b200EngineSetFlags(h264b200_engine_t *e, uint32_t flags);
  * caller that drives many instances defer the wait until the batch holding the
  * picture has been launched. */
 u8  *h264b200NextOutputPictureAsync(storage_t *pStorage, u32 *picId, u32 *isIdrPic, u32 *numErrMbs, u32 *ticket);
-/* 0: picture complete; otherwise the engine error flags / 0xffffffff on a CUDA failure. */
+/* 0: picture complete; otherwise the engine error flags, 0xffffffff on a CUDA failure, or 0xfffffffe when the
+ * caller waited so long that a later picture was already reconstructed into the same frame buffer. */
 u32  h264b200PictureWait(storage_t *pStorage, u32 ticket);
 
 /* ---- output formatting on the device (K5) ----
