@@ -23,7 +23,7 @@ class WriterParams(ctypes.Structure):
         ("i16_permille", ctypes.c_uint32), ("mv_range_qpel", ctypes.c_int32),
         ("far_mv_permille", ctypes.c_uint32), ("level_idc", ctypes.c_uint32),
         ("first_idr_ipcm", ctypes.c_uint32), ("part_mix", ctypes.c_uint32),
-        ("crop", ctypes.c_uint32), ("multi_slice_params", ctypes.c_uint32), ("dpb_stress", ctypes.c_uint32),
+        ("crop", ctypes.c_uint32), ("multi_slice_params", ctypes.c_uint32), ("dpb_stress", ctypes.c_uint32), ("fmo_type", ctypes.c_uint32), ("fmo_groups", ctypes.c_uint32),
     ]
 
 

@@ -155,8 +155,9 @@ static int store_pps(h264_decoder_t *d, const h264_pps_t *p)
 {
     int id = p->pps_id;
     if (!d->pps[id]) { d->pps[id] = (h264_pps_t *)malloc(sizeof *p); if (!d->pps[id]) return -1; }
-    else if (id == d->active_pps_id) {
-        if (p->sps_id != d->active_sps_id) d->active_pps_id = H264_MAX_PPS + 1;
+    else {
+        free((void *)d->pps[id]->fmo.group_id);     /* the stored copy owns the explicit slice group map */
+        if (id == d->active_pps_id && p->sps_id != d->active_sps_id) d->active_pps_id = H264_MAX_PPS + 1;
     }
     *d->pps[id] = *p;
     if (id == d->active_pps_id) d->active_pps = d->pps[id];
@@ -172,10 +173,27 @@ static void select_sets(h264_decoder_t *d, uint32_t pps_id)
     d->pending_activation = 1;
 }
 
+/* slice group parameters against the picture size (h264bsd_storage.c:801-850 CheckPps) */
+static int check_fmo(const h264_pps_t *pps, const h264_sps_t *sps)
+{
+    const uint32_t size = sps->width_mbs * sps->height_mbs, W = sps->width_mbs;
+    const h264_fmo_t *f = &pps->fmo;
+    uint32_t i;
+    if (pps->num_slice_groups <= 1) return 0;
+    if (f->type == 0) { for (i = 0; i < f->n_groups; i++) if (f->run_length[i] > size) return -1; }
+    else if (f->type == 2) {
+        for (i = 0; i + 1 < f->n_groups; i++)
+            if (f->top_left[i] > f->bottom_right[i] || f->bottom_right[i] >= size || f->top_left[i] % W > f->bottom_right[i] % W) return -1;
+    } else if (f->type >= 3 && f->type <= 5) { if (f->change_rate > size) return -1; }
+    else if (f->type == 6 && pps->fmo_map_units != size) return -1;
+    return 0;
+}
+
 /* 0 ok, -1 bad combination, -2 allocation failure (h264bsd_storage.c:298-420) */
 static int activate_param_sets(h264_decoder_t *d, uint32_t pps_id, int is_idr)
 {
     if (!d->pps[pps_id] || !d->sps[d->pps[pps_id]->sps_id]) return -1;
+    if (check_fmo(d->pps[pps_id], d->sps[d->pps[pps_id]->sps_id])) return -1;
     if (d->active_pps_id == H264_MAX_PPS) select_sets(d, pps_id);
     else if (d->pending_activation) {
         const h264_sps_t *sps = d->active_sps;
@@ -184,6 +202,9 @@ static int activate_param_sets(h264_decoder_t *d, uint32_t pps_id, int is_idr)
         free(d->mbctx);
         d->mbctx = (h264_mbctx_t *)calloc(d->pic_size_mbs, sizeof(h264_mbctx_t));
         if (!d->mbctx) return -2;
+        free(d->slice_group_map);
+        d->slice_group_map = (uint8_t *)malloc(d->pic_size_mbs);
+        if (!d->slice_group_map) return -2;
         no_reorder = d->no_reordering_app || sps->poc_type == 2 ||
                      (sps->vui_present && sps->bitstream_restriction && !sps->num_reorder_frames);
         h264_dpb_init(&d->dpb, sps->max_dpb_size, sps->num_ref_frames, sps->max_frame_num, no_reorder);
@@ -326,8 +347,8 @@ u32 h264bsdDecode(storage_t *pStorage, u8 *byteStrm, u32 len, u32 picId, u32 *re
         break; }
     case NAL_PPS: {
         h264_pps_t pps;
-        if (h264_parse_pps(&b, &pps)) return H264BSD_ERROR;
-        if (store_pps(d, &pps)) return H264BSD_MEMALLOC_ERROR;
+        if (h264_parse_pps(&b, &pps)) { free((void *)pps.fmo.group_id); return H264BSD_ERROR; }
+        if (store_pps(d, &pps)) { free((void *)pps.fmo.group_id); return H264BSD_MEMALLOC_ERROR; }
         break; }
     case NAL_IDR:
     case NAL_SLICE: {
@@ -368,6 +389,12 @@ u32 h264bsdDecode(storage_t *pStorage, u8 *byteStrm, u32 len, u32 picId, u32 *re
         if (start_of_pic) {
             if (type != NAL_IDR && h264_dpb_check_gaps(&d->dpb, sh.frame_num, ref_idc != 0, d->active_sps->gaps_allowed)) return H264BSD_ERROR;
             if (begin_picture(d)) return H264BSD_MEMALLOC_ERROR;
+        }
+        if (d->active_pps->num_slice_groups > 1) {
+            const h264_fmo_t *f = &d->active_pps->fmo;
+            uint32_t units0 = sh.slice_group_change_cycle * f->change_rate;
+            if (units0 > d->pic_size_mbs) units0 = d->pic_size_mbs;
+            h264_fmo_build_map(d->slice_group_map, d->width_mbs, d->height_mbs, f, units0);
         }
         d->sh = sh; d->valid_slice_in_au = 1;
         d->pic_nal_type = (uint8_t)type; d->pic_nal_ref_idc = (uint8_t)ref_idc;
@@ -455,8 +482,8 @@ void h264bsdShutdown(storage_t *pStorage)
     if (!d) return;
     if (d->be_inst) d->be->inst_destroy(d->be, d->be_inst);
     for (i = 0; i < H264_MAX_SPS; i++) free(d->sps[i]);
-    for (i = 0; i < H264_MAX_PPS; i++) free(d->pps[i]);
-    free(d->mbctx);
+    for (i = 0; i < H264_MAX_PPS; i++) { if (d->pps[i]) free((void *)d->pps[i]->fmo.group_id); free(d->pps[i]); }
+    free(d->mbctx); free(d->slice_group_map);
     free(d);
     pStorage->impl = NULL;
 }

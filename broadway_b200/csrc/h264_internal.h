@@ -10,6 +10,7 @@
 #include <stddef.h>
 #include "h264b200_records.h"
 #include "h264_bits.h"
+#include "h264_fmo.h"
 
 #ifdef __cplusplus
 extern "C" {
@@ -53,6 +54,8 @@ typedef struct {
     uint8_t  pps_id, sps_id;
     uint8_t  pic_order_present;
     uint32_t num_slice_groups;
+    h264_fmo_t fmo;                    /* valid when num_slice_groups > 1; fmo.group_id is owned by the stored copy */
+    uint32_t fmo_map_units;            /* type 6: pic_size_in_map_units */
     uint32_t num_ref_idx_l0_default;
     int32_t  pic_init_qp;
     int32_t  chroma_qp_index_offset;
@@ -73,6 +76,7 @@ typedef struct {
     uint8_t  no_output_of_prior_pics, long_term_reference_flag, adaptive_marking;
     uint32_t n_mmco; h264_mmco_t mmco[36];
     int32_t  slice_qp;
+    uint32_t slice_group_change_cycle;
     uint8_t  disable_deblocking_idc; int8_t alpha_off, beta_off;   /* offsets already *2 */
 } h264_slice_hdr_t;
 
@@ -193,6 +197,7 @@ typedef struct h264_decoder {
 
     h264_dpb_t dpb;
     h264_mbctx_t *mbctx;                          /* pic_size_mbs */
+    uint8_t *slice_group_map;                     /* pic_size_mbs, NULL without FMO (one slice group) */
     h264_pic_input_t *pic;                        /* input buffer of the picture being parsed */
     int last_output_slot;
     int out_format;                               /* H264B200_OUT_* requested through h264b200SetOutputFormat */

@@ -5,6 +5,7 @@
  * 125-131), no weighted prediction (:264-270), I and P slices only
  * (h264bsd_slice_header.c:135-144).  Return 0 on success, <0 on error. */
 #include <string.h>
+#include <stdlib.h>
 #include "h264_internal.h"
 
 #define CHECK_UE(v) do { if ((v) == 0xffffffffu) return -1; } while (0)
@@ -143,8 +144,31 @@ int h264_parse_pps(br_t *b, h264_pps_t *p)
     v = br_ue(b); CHECK_UE(v); if (v >= H264_MAX_SPS) return -1; p->sps_id = (uint8_t)v;
     if (br_get1(b)) return -1;                 /* entropy_coding_mode_flag: CABAC is not Baseline */
     p->pic_order_present = (uint8_t)br_get1(b);
-    v = br_ue(b); CHECK_UE(v); p->num_slice_groups = v + 1;
-    if (p->num_slice_groups > 1) return -2;    /* FMO: not supported yet */
+    v = br_ue(b); CHECK_UE(v); if (v > 7) return -1; p->num_slice_groups = v + 1;
+    if (p->num_slice_groups > 1) {             /* flexible macroblock ordering (h264bsd_pic_param_set.c:150-262) */
+        h264_fmo_t *f = &p->fmo;
+        uint32_t i;
+        f->n_groups = p->num_slice_groups;
+        v = br_ue(b); CHECK_UE(v); if (v > 6) return -1; f->type = v;
+        if (f->type == 0) {
+            for (i = 0; i < f->n_groups; i++) { v = br_ue(b); CHECK_UE(v); f->run_length[i] = v + 1; }
+        } else if (f->type == 2) {
+            for (i = 0; i + 1 < f->n_groups; i++) { v = br_ue(b); CHECK_UE(v); f->top_left[i] = v; v = br_ue(b); CHECK_UE(v); f->bottom_right[i] = v; }
+        } else if (f->type >= 3 && f->type <= 5) {
+            f->change_direction = br_get1(b);
+            v = br_ue(b); CHECK_UE(v); f->change_rate = v + 1;
+        } else if (f->type == 6) {
+            uint32_t bits = 0, n;
+            uint8_t *ids;
+            v = br_ue(b); CHECK_UE(v); if (v >= 36864u) return -1;
+            n = v + 1; p->fmo_map_units = n;
+            while ((1u << bits) < f->n_groups) bits++;
+            ids = (uint8_t *)malloc(n);
+            if (!ids) return -1;
+            for (i = 0; i < n; i++) { ids[i] = (uint8_t)br_get(b, (int)bits); if (ids[i] >= f->n_groups) { free(ids); return -1; } }
+            f->group_id = ids;
+        }
+    }
     v = br_ue(b); CHECK_UE(v); if (v > 31) return -1; p->num_ref_idx_l0_default = v + 1;
     v = br_ue(b); CHECK_UE(v); if (v > 31) return -1;
     if (br_get1(b)) return -1;                 /* weighted_pred_flag */
@@ -259,6 +283,11 @@ int h264_parse_slice_header(br_t *b, h264_slice_hdr_t *sh, const h264_sps_t *sps
             sv = br_se(b); if (sv < -6 || sv > 6) return -1; sh->alpha_off = (int8_t)(sv * 2);
             sv = br_se(b); if (sv < -6 || sv > 6) return -1; sh->beta_off = (int8_t)(sv * 2);
         }
+    }
+    if (pps->num_slice_groups > 1 && pps->fmo.type >= 3 && pps->fmo.type <= 5) {
+        const uint32_t size = sps->width_mbs * sps->height_mbs, rate = pps->fmo.change_rate;
+        sh->slice_group_change_cycle = br_get(b, (int)h264_fmo_cycle_bits(size, rate));
+        if (sh->slice_group_change_cycle > (size + rate - 1) / rate) return -1;      /* h264bsd_slice_header.c:371-380 */
     }
     return br_overrun(b) ? -1 : 0;
 }

@@ -489,7 +489,10 @@ int h264_decode_slice_data(h264_decoder_t *d, br_t *b, const h264_slice_hdr_t *s
         c->decoded = 1;
         mb_count++;
         more = br_more_data(b) || skip_run;
-        addr++;                                  /* single slice group: next MB address is addr+1 */
+        if (d->active_pps->num_slice_groups > 1) {   /* next macroblock of the same slice group (h264bsd_util.c:219-245) */
+            const uint8_t *map = d->slice_group_map, grp = map[addr];
+            do addr++; while (addr < d->pic_size_mbs && map[addr] != grp);
+        } else addr++;
         if (more && addr >= d->pic_size_mbs) return -1;
     } while (more);
     if (d->num_decoded_mbs + mb_count > d->pic_size_mbs) return -1;

@@ -10,6 +10,7 @@
 #include "h264b200_writer.h"
 #include "h264_consts.h"
 #include "cavlc_tables.h"
+#include "h264_fmo.h"
 
 /* ------------------------------------------------------------------ PRNG */
 typedef struct { uint64_t s; } rng_t;
@@ -634,14 +635,16 @@ typedef struct { int idc, a, bq, qp; } slice_par_t;
 /* per-picture reference handling (dpb_stress): nal_ref_idc, list reordering, adaptive marking */
 typedef struct { int ref_idc; int reorder_diff_minus1; int mmco1_diff_minus1; int make_long; int drop_long; } pic_par_t;
 
+/* mbs[0..n_mbs): macroblock addresses of the slice in decoding order (ascending; contiguous without FMO) */
 static size_t write_slice(wr_t *w, uint8_t *out, size_t cap, uint8_t *scratch, size_t scratch_cap,
-                          uint32_t first_mb, uint32_t n_mbs, int idr, int is_p, uint32_t frame_num,
-                          uint32_t idr_pic_id, uint32_t poc_lsb, const slice_par_t *sp, const pic_par_t *pp)
+                          const uint32_t *mbs, uint32_t n_mbs, int idr, int is_p, uint32_t frame_num,
+                          uint32_t idr_pic_id, uint32_t poc_lsb, const slice_par_t *sp, const pic_par_t *pp,
+                          int cycle_bits, uint32_t change_cycle)
 {
     const h264w_params_t *p = w->p;
     bitw_t b; uint32_t i, skip_run = 0;
     bw_init(&b, scratch, scratch_cap);
-    bw_ue(&b, first_mb);
+    bw_ue(&b, mbs[0]);
     bw_ue(&b, is_p ? 0u : 2u);
     bw_ue(&b, 0);                                    /* pic_parameter_set_id */
     bw_put(&b, 4, frame_num & 15);                   /* log2_max_frame_num = 4 */
@@ -672,11 +675,12 @@ static size_t write_slice(wr_t *w, uint8_t *out, size_t cap, uint8_t *scratch, s
     /* deblocking_filter_control_present_flag = 1 */
     bw_ue(&b, (uint32_t)sp->idc);
     if (sp->idc != 1) { bw_se(&b, sp->a); bw_se(&b, sp->bq); }
+    if (cycle_bits >= 0) bw_put(&b, cycle_bits, change_cycle);   /* slice_group_change_cycle (map types 3..5) */
 
     w->qp = sp->qp;
     w->is_p = is_p;
     for (i = 0; i < n_mbs; i++) {
-        uint32_t addr = first_mb + i;
+        uint32_t addr = mbs[i];
         int mbx = (int)(addr % w->W), mby = (int)(addr / w->W);
         wmb_t *cur = &w->mb[addr];
         memset(cur, 0, sizeof *cur);
@@ -725,6 +729,7 @@ size_t h264w_generate(const h264w_params_t *p, uint8_t *out, size_t cap)
     wr_t w; bitw_t b; uint8_t hdr[64]; uint8_t *scratch; size_t scratch_cap, o = 0, n;
     uint32_t f, since_idr = 0, idr_id = 0, s, n_short = 0, n_long = 0, prev_ref_fn = 0, ref_ord = 0;
     uint32_t short_ord[17];                          /* ordinal (count of reference pictures since the IDR) of each short-term picture, most recent first */
+    h264_fmo_t fmo; uint8_t *group_ids = NULL, *map = NULL; uint32_t *order = NULL;
     if (!p || !out || !p->width_mbs || !p->height_mbs || !p->n_frames) return 0;
     if (p->num_ref_frames < 1 || p->num_ref_frames > 16 || (p->poc_type != 0 && p->poc_type != 2)) return 0;
     if (p->qp < 0 || p->qp > 51 || p->deblock_idc > 2) return 0;
@@ -758,11 +763,39 @@ size_t h264w_generate(const h264w_params_t *p, uint8_t *out, size_t cap)
     bw_trailing(&b);
     n = emit_nal(out + o, cap - o, 1, 7, hdr, b.pos); if (!n) goto fail; o += n;
     /* PPS (7.3.2.2) */
-    bw_init(&b, hdr, sizeof hdr);
+    bw_init(&b, scratch, scratch_cap);
     bw_ue(&b, 0); bw_ue(&b, 0);
     bw_put(&b, 1, 0);                  /* entropy_coding_mode_flag: CAVLC */
     bw_put(&b, 1, 0);                  /* pic_order_present_flag */
-    bw_ue(&b, 0);                      /* num_slice_groups_minus1 */
+    if (p->fmo_type) {                 /* flexible macroblock ordering: slice_group_map_type = fmo_type - 1 */
+        uint32_t i, bits = 0;
+        memset(&fmo, 0, sizeof fmo);
+        fmo.n_groups = p->fmo_groups < 2 ? 2 : p->fmo_groups > 8 ? 8 : p->fmo_groups;
+        fmo.type = p->fmo_type - 1;
+        if (fmo.type >= 3 && fmo.type <= 5) fmo.n_groups = 2;
+        bw_ue(&b, fmo.n_groups - 1);
+        bw_ue(&b, fmo.type);
+        if (fmo.type == 0) {
+            for (i = 0; i < fmo.n_groups; i++) { fmo.run_length[i] = 1 + rng_u(&w.rng, 2 * w.W); bw_ue(&b, fmo.run_length[i] - 1); }
+        } else if (fmo.type == 2) {
+            for (i = 0; i + 1 < fmo.n_groups; i++) {
+                uint32_t x0 = rng_u(&w.rng, w.W), x1 = x0 + rng_u(&w.rng, w.W - x0), y0 = rng_u(&w.rng, w.H), y1 = y0 + rng_u(&w.rng, w.H - y0);
+                fmo.top_left[i] = y0 * w.W + x0; fmo.bottom_right[i] = y1 * w.W + x1;
+                bw_ue(&b, fmo.top_left[i]); bw_ue(&b, fmo.bottom_right[i]);
+            }
+        } else if (fmo.type >= 3 && fmo.type <= 5) {
+            fmo.change_direction = rng_u(&w.rng, 2);
+            fmo.change_rate = 1 + rng_u(&w.rng, w.W);
+            bw_put(&b, 1, fmo.change_direction); bw_ue(&b, fmo.change_rate - 1);
+        } else if (fmo.type == 6) {
+            group_ids = (uint8_t *)malloc(w.nmb);
+            if (!group_ids) goto fail;
+            while ((1u << bits) < fmo.n_groups) bits++;
+            bw_ue(&b, w.nmb - 1);
+            for (i = 0; i < w.nmb; i++) { group_ids[i] = (uint8_t)rng_u(&w.rng, fmo.n_groups); bw_put(&b, (int)bits, group_ids[i]); }
+            fmo.group_id = group_ids;
+        }
+    } else bw_ue(&b, 0);               /* num_slice_groups_minus1 */
     bw_ue(&b, p->num_ref_frames - 1);  /* num_ref_idx_l0_default_active_minus1 */
     bw_ue(&b, 0);
     bw_put(&b, 1, 0); bw_put(&b, 2, 0);/* weighted_pred_flag, weighted_bipred_idc */
@@ -773,7 +806,19 @@ size_t h264w_generate(const h264w_params_t *p, uint8_t *out, size_t cap)
     bw_put(&b, 1, p->constrained_intra_pred ? 1 : 0);
     bw_put(&b, 1, 0);                  /* redundant_pic_cnt_present_flag */
     bw_trailing(&b);
-    n = emit_nal(out + o, cap - o, 1, 8, hdr, b.pos); if (!n) goto fail; o += n;
+    if (b.ovf) goto fail;
+    {   /* the RBSP sits in `scratch`, which emit_nal only reads */
+        uint8_t *tmp = (uint8_t *)malloc(b.pos + 1);
+        if (!tmp) goto fail;
+        memcpy(tmp, scratch, b.pos);
+        n = emit_nal(out + o, cap - o, 1, 8, tmp, b.pos);
+        free(tmp);
+        if (!n) goto fail;
+        o += n;
+    }
+    order = (uint32_t *)malloc(w.nmb * sizeof(uint32_t));
+    map = (uint8_t *)malloc(w.nmb);
+    if (!order || !map) goto fail;
 
     for (f = 0; f < p->n_frames; f++) {
         int idr = f == 0 || (p->idr_period && f % p->idr_period == 0);
@@ -804,8 +849,47 @@ size_t h264w_generate(const h264w_params_t *p, uint8_t *out, size_t cap)
         }
         w.num_ref_active = (int)(n_short + n_long < p->num_ref_frames ? n_short + n_long : p->num_ref_frames);
         if (w.num_ref_active < 1) w.num_ref_active = 1;
+        {   /* macroblocks of a slice are stamped with its id as they are written: forget the previous picture's */
+            uint32_t a;
+            for (a = 0; a < w.nmb; a++) w.mb[a].slice = 0;
+        }
+        if (p->fmo_type) {
+            /* one or more slices per slice group, each listing the group's macroblocks in ascending order */
+            uint32_t cycle = 0, units0 = 0, g, a;
+            int cycle_bits = -1;
+            if (fmo.type >= 3 && fmo.type <= 5) {
+                const uint32_t max_cycle = (w.nmb + fmo.change_rate - 1) / fmo.change_rate;
+                cycle_bits = (int)h264_fmo_cycle_bits(w.nmb, fmo.change_rate);
+                cycle = rng_u(&w.rng, max_cycle + 1);
+                units0 = cycle * fmo.change_rate; if (units0 > w.nmb) units0 = w.nmb;
+            }
+            h264_fmo_build_map(map, w.W, w.H, &fmo, units0);
+            s = 0;
+            for (g = 0; g < fmo.n_groups; g++) {
+                uint32_t cnt = 0, parts, part;
+                for (a = 0; a < w.nmb; a++) if (map[a] == g) order[cnt++] = a;
+                if (!cnt) continue;
+                parts = nsl < cnt ? nsl : cnt;
+                for (part = 0; part < parts; part++) {
+                    const uint32_t lo = (cnt * part) / parts, hi = (cnt * (part + 1)) / parts;
+                    slice_par_t sp;
+                    sp.idc = (int)p->deblock_idc; sp.a = p->alpha_c0_offset_div2; sp.bq = p->beta_offset_div2; sp.qp = p->qp;
+                    if (p->multi_slice_params) {
+                        sp.idc = (int)rng_u(&w.rng, 3); sp.a = rng_range(&w.rng, -3, 3); sp.bq = rng_range(&w.rng, -3, 3);
+                        sp.qp = p->qp + rng_range(&w.rng, -2, 2);
+                        if (sp.qp < 0) sp.qp = 0;
+                        if (sp.qp > 51) sp.qp = 51;
+                    }
+                    w.cur_slice = ++s;
+                    n = write_slice(&w, out + o, cap - o, scratch, scratch_cap, order + lo, hi - lo, idr, is_p,
+                                    frame_num, idr_id & 0xffff, since_idr * 2, &sp, &pp, cycle_bits, cycle);
+                    if (!n) goto fail;
+                    o += n;
+                }
+            }
+        } else
         for (s = 0; s < nsl; s++) {
-            uint32_t cnt = (w.nmb * (s + 1)) / nsl - (w.nmb * s) / nsl;
+            uint32_t cnt = (w.nmb * (s + 1)) / nsl - (w.nmb * s) / nsl, a;
             slice_par_t sp;
             sp.idc = (int)p->deblock_idc; sp.a = p->alpha_c0_offset_div2; sp.bq = p->beta_offset_div2; sp.qp = p->qp;
             if (p->multi_slice_params) {
@@ -814,9 +898,10 @@ size_t h264w_generate(const h264w_params_t *p, uint8_t *out, size_t cap)
                 if (sp.qp < 0) sp.qp = 0;
                 if (sp.qp > 51) sp.qp = 51;
             }
+            for (a = 0; a < cnt; a++) order[a] = first + a;
             w.cur_slice = s + 1;
-            n = write_slice(&w, out + o, cap - o, scratch, scratch_cap, first, cnt, idr, is_p,
-                            frame_num, idr_id & 0xffff, since_idr * 2, &sp, &pp);
+            n = write_slice(&w, out + o, cap - o, scratch, scratch_cap, order, cnt, idr, is_p,
+                            frame_num, idr_id & 0xffff, since_idr * 2, &sp, &pp, -1, 0);
             if (!n) goto fail;
             o += n; first += cnt;
         }
@@ -834,9 +919,9 @@ size_t h264w_generate(const h264w_params_t *p, uint8_t *out, size_t cap)
         }
         since_idr++;
     }
-    free(w.mb); free(scratch);
+    free(w.mb); free(scratch); free(group_ids); free(map); free(order);
     return o;
 fail:
-    free(w.mb); free(scratch);
+    free(w.mb); free(scratch); free(group_ids); free(map); free(order);
     return 0;
 }

@@ -54,6 +54,8 @@ typedef struct {
     uint32_t multi_slice_params;   /* 1: vary deblock idc/offsets and QP per slice */
     uint32_t dpb_stress;           /* 1: non-reference pictures, ref list reordering and MMCO 1 marking (needs num_ref_frames >= 2);
                                       2: also long-term pictures (MMCO 4+6, released by MMCO 2) */
+    uint32_t fmo_type;             /* 0: one slice group; t+1: flexible macroblock ordering with slice_group_map_type t (0..6) */
+    uint32_t fmo_groups;           /* slice groups 2..8 (map types 3..5 always use 2) */
 } h264w_params_t;
 
 /* Fill *p with the defaults used by BASELINE.json config 3 at the given size. */

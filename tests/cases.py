@@ -9,7 +9,8 @@ constrained_intra_pred, several reference frames, several slices per picture
 with per-slice deblocking controls (idc 0/1/2, offsets), QP changes, chroma QP
 offset, far out-of-picture vectors (edge clamp), POC types 0 and 2, cropping,
 the degenerate one-macroblock picture, escape-coded levels, and decoded-picture-buffer
-handling (non-reference pictures, frame_num wrap, list reordering, MMCO 1).
+handling (non-reference pictures, frame_num wrap, list reordering, MMCO 1/2/4/6,
+long-term pictures), and flexible macroblock ordering (all seven map types).
 """
 
 # name, width_mbs, height_mbs, frames, overrides
@@ -48,6 +49,14 @@ SMALL = [
     # ... plus long-term reference pictures (MMCO 4 + 6, released by MMCO 2)
     ("dpb_long_term",     11,  9, 40, dict(num_ref_frames=3, dpb_stress=2)),
     ("dpb_long_term_5",   11,  9, 40, dict(num_ref_frames=5, dpb_stress=2, poc_type=0, p_intra_permille=60)),
+    # flexible macroblock ordering: the seven slice group map types
+    ("fmo_interleaved",   11,  9, 4, dict(fmo_type=1, fmo_groups=3, p_intra_permille=150)),
+    ("fmo_dispersed",     11,  9, 4, dict(fmo_type=2, fmo_groups=4, slices_per_pic=2, multi_slice_params=1)),
+    ("fmo_foreground",    11,  9, 4, dict(fmo_type=3, fmo_groups=3, p_intra_permille=150)),
+    ("fmo_box_out",       11,  9, 5, dict(fmo_type=4, p_intra_permille=100)),
+    ("fmo_raster",        11,  9, 5, dict(fmo_type=5, deblock_idc=2)),
+    ("fmo_wipe",          11,  9, 5, dict(fmo_type=6, p_intra_permille=100, constrained_intra_pred=1)),
+    ("fmo_explicit",      11,  9, 4, dict(fmo_type=7, fmo_groups=8, p_intra_permille=150, num_ref_frames=2)),
 ]
 
 # BASELINE.json's full-size configurations (few frames: the reference runs at ~20 fps per core)
