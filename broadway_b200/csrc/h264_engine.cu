@@ -51,11 +51,11 @@
 struct Inst;
 
 struct PicBuf {
-    h264_pic_input_t in;           /* in.mbs / in.coef: pinned host memory */
-    h264b200_mb_t *d_mbs;
+    h264_pic_input_t in;           /* in.mbs / in.coef: ONE pinned block, records first, coefficient slots behind them */
+    h264b200_mb_t *d_mbs;          /* device twin of the block: one cudaMemcpyAsync per picture */
     int16_t *d_coef;
     uint32_t d_coef_cap;           /* slots */
-    cudaEvent_t done;              /* kernels that read this buffer have finished */
+    cudaEvent_t done;              /* (not owned) event of the batch whose kernels read this buffer */
     int state;                     /* 0 free, 1 being filled by the parser, 2 queued, 3 launched */
     Inst *inst;
 };
@@ -65,7 +65,7 @@ struct Inst {
     uint32_t wm, hm, n_mbs, n_slots;
     size_t frame_bytes;
     uint8_t *d_frames, *h_frames;
-    cudaEvent_t slot_ready[H264_MAX_SLOTS];   /* the host mirror of the slot is complete */
+    cudaEvent_t slot_ready[H264_MAX_SLOTS];   /* (not owned) copy-out event of the batch that last wrote the slot's mirror */
     uint8_t slot_flags[H264_MAX_SLOTS];       /* bit 1: a copy-out into the slot's mirror has been issued (slot_ready is valid) */
     uint32_t slot_qgen[H264_MAX_SLOTS];       /* pictures handed over (queued) into the slot so far */
     uint32_t slot_lgen[H264_MAX_SLOTS];       /* generation of the last LAUNCHED picture of the slot */
@@ -94,7 +94,8 @@ struct Scratch {
     uint32_t cap_jobs;
     int32_t *d_ctrl;
     size_t cap_ctrl;               /* words */
-    cudaEvent_t done;
+    cudaEvent_t done;              /* kernels of the batch finished */
+    cudaEvent_t d2h_done;          /* copy-out of the batch finished */
     bool used;
 };
 
@@ -129,11 +130,11 @@ static int picbuf_alloc(PicBuf *p, Inst *in, uint32_t coef_cap)
 {
     memset(p, 0, sizeof *p);
     p->inst = in;
-    CUDA_TRY(cudaHostAlloc((void **)&p->in.mbs, (size_t)in->n_mbs * sizeof(h264b200_mb_t), cudaHostAllocDefault), return -1);
-    CUDA_TRY(cudaHostAlloc((void **)&p->in.coef, (size_t)coef_cap * 32, cudaHostAllocDefault), return -1);
-    CUDA_TRY(cudaMalloc((void **)&p->d_mbs, (size_t)in->n_mbs * sizeof(h264b200_mb_t)), return -1);
-    CUDA_TRY(cudaMalloc((void **)&p->d_coef, (size_t)coef_cap * 32), return -1);
-    CUDA_TRY(cudaEventCreateWithFlags(&p->done, cudaEventDisableTiming), return -1);
+    const size_t rec_bytes = (size_t)in->n_mbs * sizeof(h264b200_mb_t);
+    CUDA_TRY(cudaHostAlloc((void **)&p->in.mbs, rec_bytes + (size_t)coef_cap * 32, cudaHostAllocDefault), return -1);
+    p->in.coef = (int16_t *)((uint8_t *)p->in.mbs + rec_bytes);
+    CUDA_TRY(cudaMalloc((void **)&p->d_mbs, rec_bytes + (size_t)coef_cap * 32), return -1);
+    p->d_coef = (int16_t *)((uint8_t *)p->d_mbs + rec_bytes);
     p->in.coef_cap = coef_cap; p->d_coef_cap = coef_cap;
     p->in.priv = p;
     return 0;
@@ -141,10 +142,7 @@ static int picbuf_alloc(PicBuf *p, Inst *in, uint32_t coef_cap)
 static void picbuf_free(PicBuf *p)
 {
     if (p->in.mbs) cudaFreeHost(p->in.mbs);
-    if (p->in.coef) cudaFreeHost(p->in.coef);
     if (p->d_mbs) cudaFree(p->d_mbs);
-    if (p->d_coef) cudaFree(p->d_coef);
-    if (p->done) cudaEventDestroy(p->done);
     memset(p, 0, sizeof *p);
 }
 
@@ -233,24 +231,24 @@ static uint32_t submit_locked(h264b200_engine *e)
         PicBuf *p = e->queue[i]; Inst *in = p->inst; h264_pic_input_t *pic = &p->in;
         h264b200_mb_t *d_mbs = p->d_mbs; int16_t *d_coef_in = p->d_coef, *d_coef = p->d_coef;
         size_t coef_bytes = (size_t)pic->coef_used * 32;
-        if (retain) {
-            void *a = nullptr, *b = nullptr, *c = nullptr;
-            CUDA_TRY(cudaMalloc(&a, (size_t)in->n_mbs * sizeof(h264b200_mb_t)), return 0);
-            CUDA_TRY(cudaMalloc(&b, coef_bytes + 32), return 0);
+        const size_t rec_bytes = (size_t)in->n_mbs * sizeof(h264b200_mb_t);
+        if (retain) {                                          /* [records | levels] and a separate residual buffer, kept */
+            void *a = nullptr, *c = nullptr;
+            CUDA_TRY(cudaMalloc(&a, rec_bytes + coef_bytes + 32), return 0);
             CUDA_TRY(cudaMalloc(&c, coef_bytes + 32), return 0);
-            ret->owned.push_back(a); ret->owned.push_back(b); ret->owned.push_back(c);
-            d_mbs = (h264b200_mb_t *)a; d_coef_in = (int16_t *)b; d_coef = (int16_t *)c;
+            ret->owned.push_back(a); ret->owned.push_back(c);
+            d_mbs = (h264b200_mb_t *)a; d_coef_in = (int16_t *)((uint8_t *)a + rec_bytes); d_coef = (int16_t *)c;
         } else if (p->d_coef_cap < pic->coef_used) {          /* the host side grew: follow */
-            /* the previous device buffer may still be read by an earlier batch of this ring slot: it is not
-             * (pic_begin waited for `done`), so it can be replaced */
-            cudaFree(p->d_coef);
+            /* no earlier batch reads this ring slot any more (pic_begin waited for `done`), so it can be replaced */
+            cudaFree(p->d_mbs);
             p->d_coef_cap = pic->coef_cap;
-            CUDA_TRY(cudaMalloc((void **)&p->d_coef, (size_t)p->d_coef_cap * 32), return 0);
-            d_coef_in = d_coef = p->d_coef;
+            CUDA_TRY(cudaMalloc((void **)&p->d_mbs, rec_bytes + (size_t)p->d_coef_cap * 32), return 0);
+            p->d_coef = (int16_t *)((uint8_t *)p->d_mbs + rec_bytes);
+            d_mbs = p->d_mbs; d_coef_in = d_coef = p->d_coef;
         }
-        CUDA_TRY(cudaMemcpyAsync(d_mbs, pic->mbs, (size_t)in->n_mbs * sizeof(h264b200_mb_t), cudaMemcpyHostToDevice, e->s_h2d), return 0);
-        if (coef_bytes) CUDA_TRY(cudaMemcpyAsync(d_coef_in, pic->coef, coef_bytes, cudaMemcpyHostToDevice, e->s_h2d), return 0);
-        e->st.h2d_bytes += (size_t)in->n_mbs * sizeof(h264b200_mb_t) + coef_bytes;
+        /* records and coefficient slots are adjacent on both sides: one copy */
+        CUDA_TRY(cudaMemcpyAsync(d_mbs, pic->mbs, rec_bytes + coef_bytes, cudaMemcpyHostToDevice, e->s_h2d), return 0);
+        e->st.h2d_bytes += rec_bytes + coef_bytes;
 
         PicJob &j = sc.h_jobs[i];
         j.mbs = d_mbs; j.coef_in = d_coef_in; j.coef = d_coef;
@@ -297,7 +295,7 @@ static uint32_t submit_locked(h264b200_engine *e)
     cudaStreamWaitEvent(e->s_d2h, e->ev_comp, 0);
     for (uint32_t i = 0; i < n; i++) {
         PicBuf *p = e->queue[i]; Inst *in = p->inst; int slot = p->in.cur_slot;
-        cudaEventRecord(p->done, e->s_comp);
+        p->done = sc.done;
         p->state = 3;
         if (in->out_format == H264B200_OUT_RGBA && in->d_rgba) {
             /* K5 runs on the copy-out stream: it only reads the finished frame */
@@ -314,11 +312,12 @@ static uint32_t submit_locked(h264b200_engine *e)
                             in->frame_bytes, cudaMemcpyDeviceToHost, e->s_d2h);
             e->st.d2h_bytes += in->frame_bytes;
         }
-        cudaEventRecord(in->slot_ready[slot], e->s_d2h);
+        in->slot_ready[slot] = sc.d2h_done;
         in->slot_flags[slot] = 2; in->slot_lgen[slot] = in->slot_qgen[slot];
         in->queued--;
     }
     cudaMemcpyAsync(e->h_err, e->d_err, sizeof(uint32_t), cudaMemcpyDeviceToHost, e->s_d2h);
+    cudaEventRecord(sc.d2h_done, e->s_d2h);
     e->st.pictures += n; e->st.batches++;
     if (retain) {
         ret->jobs.assign(sc.h_jobs, sc.h_jobs + n);
@@ -364,7 +363,6 @@ static void *be_inst_create(h264_backend_t *be, uint32_t wm, uint32_t hm, uint32
     CUDA_TRY(cudaMemset(in->d_frames, 0, in->frame_bytes * n_slots), { free(in); return NULL; });
     CUDA_TRY(cudaHostAlloc((void **)&in->h_frames, in->frame_bytes * n_slots, cudaHostAllocDefault), { free(in); return NULL; });
     memset(in->h_frames, 0, in->frame_bytes * n_slots);
-    for (uint32_t i = 0; i < n_slots; i++) CUDA_TRY(cudaEventCreateWithFlags(&in->slot_ready[i], cudaEventDisableTiming), { free(in); return NULL; });
     for (int i = 0; i < NBUF; i++) if (picbuf_alloc(&in->bufs[i], in, in->n_mbs * 10 + 64)) return NULL;
     std::lock_guard<std::mutex> lk(e->mu);
     e->insts.push_back(in);
@@ -374,7 +372,6 @@ static void *be_inst_create(h264_backend_t *be, uint32_t wm, uint32_t hm, uint32
 static void inst_free(Inst *in)
 {
     for (int i = 0; i < NBUF; i++) picbuf_free(&in->bufs[i]);
-    for (uint32_t i = 0; i < in->n_slots; i++) cudaEventDestroy(in->slot_ready[i]);
     cudaFree(in->d_frames); cudaFreeHost(in->h_frames);
     if (in->d_rgba) { cudaFree(in->d_rgba); cudaFreeHost(in->h_rgba); }
     free(in);
@@ -409,14 +406,15 @@ static h264_pic_input_t *be_pic_begin(h264_backend_t *be, void *inst)
 
 static int be_coef_grow(h264_backend_t *be, void *inst, h264_pic_input_t *pic, uint32_t min_slots)
 {
-    h264b200_engine *e = (h264b200_engine *)be->ctx; (void)inst;
+    h264b200_engine *e = (h264b200_engine *)be->ctx; Inst *in = (Inst *)inst;
+    const size_t rec_bytes = (size_t)in->n_mbs * sizeof(h264b200_mb_t);
     uint32_t cap = pic->coef_cap * 2 > min_slots ? pic->coef_cap * 2 : min_slots;
-    int16_t *n = NULL;
+    uint8_t *n = NULL;
     set_device(e);
-    CUDA_TRY(cudaHostAlloc((void **)&n, (size_t)cap * 32, cudaHostAllocDefault), return -1);
-    memcpy(n, pic->coef, (size_t)pic->coef_used * 32);
-    cudaFreeHost(pic->coef);
-    pic->coef = n; pic->coef_cap = cap;
+    CUDA_TRY(cudaHostAlloc((void **)&n, rec_bytes + (size_t)cap * 32, cudaHostAllocDefault), return -1);
+    memcpy(n, pic->mbs, rec_bytes + (size_t)pic->coef_used * 32);           /* records written so far and their slots */
+    cudaFreeHost(pic->mbs);
+    pic->mbs = (h264b200_mb_t *)n; pic->coef = (int16_t *)(n + rec_bytes); pic->coef_cap = cap;
     return 0;
 }
 
@@ -545,7 +543,10 @@ extern "C" h264b200_engine_t *h264b200EngineCreateEx(int device, uint32_t flags)
     CUDA_TRY(cudaEventCreateWithFlags(&e->ev_comp, cudaEventDisableTiming), { delete e; return NULL; });
     CUDA_TRY(cudaEventCreate(&e->ev_rep0), { delete e; return NULL; });
     CUDA_TRY(cudaEventCreate(&e->ev_rep1), { delete e; return NULL; });
-    for (int i = 0; i < NSCR; i++) CUDA_TRY(cudaEventCreateWithFlags(&e->scr[i].done, cudaEventDisableTiming), { delete e; return NULL; });
+    for (int i = 0; i < NSCR; i++) {
+        CUDA_TRY(cudaEventCreateWithFlags(&e->scr[i].done, cudaEventDisableTiming), { delete e; return NULL; });
+        CUDA_TRY(cudaEventCreateWithFlags(&e->scr[i].d2h_done, cudaEventDisableTiming), { delete e; return NULL; });
+    }
     CUDA_TRY(cudaMalloc((void **)&e->d_err, 64), { delete e; return NULL; });
     CUDA_TRY(cudaMemset(e->d_err, 0, 64), { delete e; return NULL; });
     CUDA_TRY(cudaHostAlloc((void **)&e->h_err, 64, cudaHostAllocDefault), { delete e; return NULL; });
@@ -591,7 +592,7 @@ extern "C" void h264b200EngineDestroy(h264b200_engine_t *e)
         if (s.h_jobs) cudaFreeHost(s.h_jobs);
         if (s.d_jobs) cudaFree(s.d_jobs);
         if (s.d_ctrl) cudaFree(s.d_ctrl);
-        cudaEventDestroy(s.done);
+        cudaEventDestroy(s.done); cudaEventDestroy(s.d2h_done);
     }
     if (e->d_replay_ctrl) cudaFree(e->d_replay_ctrl);
     cudaFree(e->d_err); cudaFreeHost(e->h_err);

@@ -447,10 +447,12 @@ int h264_decode_slice_data(h264_decoder_t *d, br_t *b, const h264_slice_hdr_t *s
 
     do {
         h264_mbctx_t *c = &d->mbctx[addr];
-        h264b200_mb_t *r = &s.pic->mbs[addr];
+        h264b200_mb_t *r;
         int rc = 0;
         if (c->decoded) return -1;              /* redundant pictures are not decoded; a primary MB twice is an error */
+        /* growing moves the picture's records AND slots (one block): take pointers only afterwards */
         if (s.pic->coef_used + 32 > s.pic->coef_cap && d->be->coef_grow(d->be, d->be_inst, s.pic, s.pic->coef_used + 4096)) return -1;
+        r = &s.pic->mbs[addr];
         s.addr = addr; s.mbx = (int)(addr % s.W); s.mby = (int)(addr / s.W);
         s.cur = c; s.rec = r;
         memset(r, 0, 64);                       /* mv[] is always written for inter MBs and never read for intra */
