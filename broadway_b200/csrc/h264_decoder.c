@@ -20,6 +20,7 @@
 #include "h264b200.h"
 #include "h264b200_batch.h"
 #include "h264_internal.h"
+#include "h264_consts.h"
 
 static h264_decoder_t *DEC(storage_t *s) { return s ? (h264_decoder_t *)s->impl : NULL; }
 
@@ -237,16 +238,96 @@ static int apply_output_format(h264_decoder_t *d)
     return d->be->set_output(d->be, d->be_inst, d->out_format, l, t, w, h);
 }
 
+/* ------------------------------------------------------------ concealment */
+/* Macroblocks of lost slices (h264bsd_conceal.c:125-255 h264bsdConceal, :262-330 ConcealMb), expressed as ordinary
+ * records so the kernels need nothing new:
+ *   - P picture with a reference available: the co-located macroblock of the reference picture with the smallest
+ *     list index (zero vector, no residual), QP 40, all edges filtered, treated as intra by the deblocking filter;
+ *   - nothing of the picture decoded: a copy of that reference picture, or mid-grey (128) for an I picture /
+ *     no reference, with deblocking off everywhere;
+ *   - a PARTLY lost I picture (spatial interpolation, h264bsd_conceal.c:330-631) is NOT implemented: those
+ *     macroblocks are flagged MISSING and keep whatever the frame buffer held.
+ * Returns the number of macroblocks concealed or missing. */
+static uint32_t conceal_picture(h264_decoder_t *d)
+{
+    h264_pic_input_t *pic = d->pic;
+    const int is_p = !d->valid_slice_in_au || d->sh.slice_type == 0;
+    const int whole = d->num_decoded_mbs == 0;
+    const uint32_t W = d->width_mbs, H = d->height_mbs, N = d->pic_size_mbs;
+    uint32_t i, n = 0;
+    int ref = -1;
+    if (is_p) for (i = 0; i < H264_MAX_REFS && ref < 0; i++) ref = h264_dpb_ref_slot(&d->dpb, i);
+    pic->n_conceal = 0;
+    if (ref >= 0 || whole) {
+        for (i = 0; i < N; i++) {
+            h264b200_mb_t *r = &pic->mbs[i];
+            if (d->mbctx[i].decoded) continue;
+            memset(r, 0, sizeof *r);
+            n++;
+            if (ref >= 0) {
+                int q;
+                r->mb_class = H264B200_MB_INTER; r->part_flags = 31;
+                for (q = 0; q < 4; q++) r->ref_slot[q] = (uint8_t)ref;
+                r->qp_y = r->qp_dbk = 40; r->qp_c = H264_QPC[40];
+                r->flags = H264B200_MBF_DBK_AS_INTRA;
+                if (!whole) {
+                    r->dbk_flags = (uint8_t)(H264B200_DBK_INNER | (i % W ? H264B200_DBK_LEFT : 0) | (i >= W ? H264B200_DBK_TOP : 0));
+                    pic->any_deblock = 1;
+                }
+                pic->n_inter++; pic->ref_slots_used[ref] = 1;
+            } else {                                      /* grey picture: raw samples, like I_PCM */
+                if (pic->coef_used + 12 > pic->coef_cap && d->be->coef_grow(d->be, d->be_inst, pic, pic->coef_used + 12 * (N - i))) { pic->mbs[i].mb_class = H264B200_MB_MISSING; continue; }
+                r = &pic->mbs[i];                         /* growing may move the records */
+                r->mb_class = H264B200_MB_IPCM; r->coef_offset = pic->coef_used; r->nz_mask = 0xffff;
+                memset(pic->coef + (size_t)pic->coef_used * 16, 128, 384);
+                pic->coef_used += 12; pic->n_intra++;
+            }
+        }
+        if (whole) for (i = 0; i < N; i++) pic->mbs[i].dbk_flags = 0;   /* no filtering of a fully concealed picture */
+        return n;
+    }
+    /* spatial interpolation, in the reference's order (h264bsd_conceal.c:186-252): the row of the first decoded
+     * macroblock (leftwards from it, then rightwards), the rows above it column by column going up, the rows below in
+     * raster order; every concealed macroblock counts as available for the ones after it */
+    {
+        uint32_t lost = N - d->num_decoded_mbs, need = (lost * 4 + 31) / 32, *list, row, col, j;
+        if (pic->coef_used + need > pic->coef_cap && d->be->coef_grow(d->be, d->be_inst, pic, pic->coef_used + need)) {
+            for (i = 0; i < N; i++) if (!d->mbctx[i].decoded) { memset(&pic->mbs[i], 0, sizeof pic->mbs[i]); pic->mbs[i].mb_class = H264B200_MB_MISSING; }
+            return lost;
+        }
+        list = (uint32_t *)(pic->coef + (size_t)pic->coef_used * 16);
+        pic->conceal_offset = pic->coef_used;
+        for (i = 0; i < N && !d->mbctx[i].decoded; i++) ;
+        row = i / W; col = i % W;
+#define CONCEAL_ONE(addr) do { \
+            const uint32_t a_ = (addr), y_ = a_ / W, x_ = a_ % W; \
+            h264b200_mb_t *r_ = &pic->mbs[a_]; \
+            memset(r_, 0, sizeof *r_); \
+            r_->mb_class = H264B200_MB_CONCEAL; \
+            r_->avail = (uint8_t)((y_ > 0 && d->mbctx[a_ - W].decoded ? H264B200_CN_ABOVE : 0) | (y_ + 1 < H && d->mbctx[a_ + W].decoded ? H264B200_CN_BELOW : 0) | \
+                                  (x_ > 0 && d->mbctx[a_ - 1].decoded ? H264B200_CN_LEFT : 0) | (x_ + 1 < W && d->mbctx[a_ + 1].decoded ? H264B200_CN_RIGHT : 0)); \
+            r_->qp_y = r_->qp_dbk = 40; r_->qp_c = H264_QPC[40]; \
+            r_->dbk_flags = (uint8_t)(H264B200_DBK_INNER | (x_ ? H264B200_DBK_LEFT : 0) | (y_ ? H264B200_DBK_TOP : 0)); \
+            d->mbctx[a_].decoded = 1; list[n++] = a_; } while (0)
+        for (j = col; j-- > 0;) CONCEAL_ONE(row * W + j);
+        for (j = col + 1; j < W; j++) if (!d->mbctx[row * W + j].decoded) CONCEAL_ONE(row * W + j);
+        if (row) for (j = 0; j < W; j++) for (i = row; i-- > 0;) CONCEAL_ONE(i * W + j);
+        for (i = row + 1; i < H; i++) for (j = 0; j < W; j++) if (!d->mbctx[i * W + j].decoded) CONCEAL_ONE(i * W + j);
+#undef CONCEAL_ONE
+        pic->n_conceal = n;
+        pic->coef_used += (n * 4 + 31) / 32;
+        pic->any_deblock = 1;
+    }
+    return n;
+}
+
 /* ------------------------------------------------------------ picture end */
 static void finish_picture(h264_decoder_t *d)
 {
     int is_idr = d->pic_nal_type == NAL_IDR;
     int32_t poc;
     if (d->pic) {
-        if (d->num_decoded_mbs != d->pic_size_mbs) {            /* lost slices: flag what was never parsed */
-            uint32_t i;
-            for (i = 0; i < d->pic_size_mbs; i++) if (!d->mbctx[i].decoded) { memset(&d->pic->mbs[i], 0, sizeof d->pic->mbs[i]); d->pic->mbs[i].mb_class = H264B200_MB_MISSING; }
-        }
+        if (d->num_decoded_mbs != d->pic_size_mbs) d->num_err_mbs = conceal_picture(d);    /* lost slices */
         d->pic->cur_slot = h264_dpb_current_slot(&d->dpb);
         d->be->pic_submit(d->be, d->be_inst, d->pic);
         d->pic = NULL;
@@ -262,7 +343,7 @@ static int begin_picture(h264_decoder_t *d)
 {
     d->pic = d->be->pic_begin(d->be, d->be_inst);
     if (!d->pic) return -1;
-    d->pic->coef_used = 0; d->pic->n_intra = d->pic->n_inter = 0; d->pic->any_deblock = 0;
+    d->pic->coef_used = 0; d->pic->n_intra = d->pic->n_inter = 0; d->pic->any_deblock = 0; d->pic->n_conceal = 0; d->pic->conceal_offset = 0;
     memset(d->pic->ref_slots_used, 0, sizeof d->pic->ref_slots_used);
     memset(d->mbctx, 0, d->pic_size_mbs * sizeof(h264_mbctx_t));   /* records of unparsed macroblocks are flagged MISSING in finish_picture */
     d->num_decoded_mbs = 0; d->slice_id = 0;

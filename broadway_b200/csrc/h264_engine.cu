@@ -38,6 +38,7 @@
 #include "k1_transform.cuh"
 #include "k2_inter.cuh"
 #include "k3_intra.cuh"
+#include "k3c_conceal.cuh"
 #include "k4_deblock.cuh"
 #include "k5_rgba.cuh"
 
@@ -166,7 +167,7 @@ static void count_bytes(const h264_pic_input_t *pic, uint32_t n_mbs, uint64_t ou
 }
 
 /* ------------------------------------------------------------ kernel launch */
-struct BatchPlan { bool k1, k2, k3, k4; uint32_t total_mbs; int max_hm; int n_jobs; };
+struct BatchPlan { bool k1, k2, k3, k3c, k4; uint32_t total_mbs; int max_hm; int n_jobs; };
 
 static void launch_kernels(h264b200_engine *e, const Batch &b, const BatchPlan &pl, cudaEvent_t *tev)
 {
@@ -181,6 +182,7 @@ static void launch_kernels(h264b200_engine *e, const Batch &b, const BatchPlan &
         uint32_t blocks = (n_tasks + K3_WARPS - 1) / K3_WARPS, cap = (uint32_t)e->sm_count * 16;
         k3_intra<<<blocks < cap ? blocks : cap, K3_WARPS * 32, 0, s>>>(b); e->st.kernel_launches++;
     }
+    if (pl.k3c) { k3c_conceal<<<pl.n_jobs, 32, 0, s>>>(b); e->st.kernel_launches++; }   /* lost slices only: one warp per picture */
     if (tev) cudaEventRecord(tev[3], s);
     if (pl.k4) {
         uint32_t blocks = (n_tasks + K4_WARPS - 1) / K4_WARPS, cap = (uint32_t)e->sm_count * 16;
@@ -258,6 +260,9 @@ static uint32_t submit_locked(h264b200_engine *e)
         j.progress = d_ctrl + prog_off; prog_off += 2 * (size_t)in->hm;
         j.n_intra = pic->n_intra; j.n_inter = pic->n_inter; j.any_deblock = pic->any_deblock;
         j.mb_base = mb_base; mb_base += in->n_mbs;
+        j.n_conceal = pic->n_conceal;
+        j.conceal_list = reinterpret_cast<const uint32_t *>(d_coef_in + (size_t)pic->conceal_offset * 16);
+        if (pic->n_conceal) pl.k3c = true;
         if (pic->coef_used) pl.k1 = true;
         if (pic->n_inter) pl.k2 = true;
         if (pic->n_intra) pl.k3 = true;
@@ -649,6 +654,7 @@ extern "C" u32 h264b200EngineReplay(h264b200_engine_t *e, u32 reps, int time_ker
     for (u32 rep = 0; rep < reps; rep++) for (size_t bi = 0; bi < e->retained.size(); bi++) {
         Retained *r = e->retained[bi];
         BatchPlan pl; pl.k1 = r->k1; pl.k2 = r->k2; pl.k3 = r->k3; pl.k4 = r->k4;
+        pl.k3c = false; for (const PicJob &pj : r->jobs) if (pj.n_conceal) pl.k3c = true;
         pl.total_mbs = r->batch.total_mbs; pl.max_hm = r->batch.max_hm; pl.n_jobs = r->batch.n_jobs;
         cudaEvent_t *tev = nullptr;
         if (time_kernels) {

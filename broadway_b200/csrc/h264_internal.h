@@ -125,6 +125,8 @@ typedef struct {
     uint32_t  coef_used;       /* slots written */
     uint32_t  n_intra, n_inter;/* macroblock class counts (lets the engine skip kernels) */
     uint32_t  any_deblock;     /* some macroblock has filtering enabled */
+    uint32_t  n_conceal;       /* H264B200_MB_CONCEAL macroblocks; their addresses, in concealment order, are uint32 values ... */
+    uint32_t  conceal_offset;  /* ... starting at this coefficient slot */
     int       cur_slot;
     uint8_t   ref_slots_used[H264_MAX_SLOTS];
     void     *priv;

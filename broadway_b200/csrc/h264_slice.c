@@ -460,7 +460,7 @@ int h264_decode_slice_data(h264_decoder_t *d, br_t *b, const h264_slice_hdr_t *s
         c->slice_id = s.slice_id; r->slice_id = s.slice_id;
         r->chroma_qp_off = (int8_t)s.chroma_qp_off;
         r->dbk_off_a = sh->alpha_off; r->dbk_off_b = sh->beta_off;
-        r->reserved[0] = sh->disable_deblocking_idc;
+        r->dbk_idc = sh->disable_deblocking_idc;
         set_neighbours(&s);
         if (s.is_p && !prev_skipped) {
             skip_run = br_ue(b);

@@ -93,7 +93,7 @@ __device__ __forceinline__ void dbk_edge(int *v, int bs, uint32_t thr, uint32_t 
     v[1] = n2; v[2] = n1; v[3] = n0; v[4] = m0; v[5] = m1; v[6] = m2;
 }
 
-__device__ __forceinline__ bool rec_intra(const h264b200_mb_t &m) { return m.mb_class != H264B200_MB_INTER; }
+__device__ __forceinline__ bool rec_intra(const h264b200_mb_t &m) { return m.mb_class != H264B200_MB_INTER || (m.flags & H264B200_MBF_DBK_AS_INTRA); }
 
 /* bS between 4x4 block rp of macroblock p and block rq of macroblock q (raster indices) */
 __device__ __forceinline__ int dbk_bs(const h264b200_mb_t &p, int rp, const h264b200_mb_t &q, int rq, bool mb_edge)

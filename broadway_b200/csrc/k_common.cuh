@@ -22,6 +22,8 @@ struct PicJob {
     int32_t *progress;             /* 2*hm wavefront counters: [0,hm) K3, [hm,2hm) K4 */
     uint32_t n_intra, n_inter, any_deblock;
     uint32_t mb_base;              /* first macroblock of this picture in the batch-wide numbering */
+    uint32_t n_conceal;            /* H264B200_MB_CONCEAL macroblocks (k3c_conceal.cuh) ... */
+    const uint32_t *conceal_list;  /* ... their addresses in concealment order */
 };
 
 struct Batch {

@@ -31,6 +31,8 @@
 #define H264B200_MB_I4x4    1
 #define H264B200_MB_I16x16  2
 #define H264B200_MB_IPCM    3
+#define H264B200_MB_CONCEAL 4   /* lost macroblock filled by spatial interpolation from its neighbours (h264bsd_conceal.c:330-631);
+                                  `avail` then holds H264B200_CN_*: the neighbours usable at its turn of the concealment order */
 #define H264B200_MB_MISSING 255 /* never decoded (lost slice); concealment is out of scope */
 
 /* avail bits: neighbour usable for intra sample prediction (position, slice,
@@ -41,10 +43,19 @@
 #define H264B200_AVAIL_C 4   /* up-right */
 #define H264B200_AVAIL_D 8   /* up-left */
 
+/* neighbours of a H264B200_MB_CONCEAL macroblock (decoded or already concealed) */
+#define H264B200_CN_ABOVE 1
+#define H264B200_CN_BELOW 2
+#define H264B200_CN_LEFT  4
+#define H264B200_CN_RIGHT 8
+
 /* dbk_flags (h264bsd_deblocking.c:288-319 GetMbFilteringFlags, resolved on the host) */
 #define H264B200_DBK_INNER 1 /* filter internal edges  (disable_deblocking_filter_idc != 1) */
 #define H264B200_DBK_LEFT  2 /* filter left macroblock edge */
 #define H264B200_DBK_TOP   4 /* filter top macroblock edge */
+
+/* flags */
+#define H264B200_MBF_DBK_AS_INTRA 1  /* concealed macroblock: the deblocking filter treats it as intra (h264bsd_conceal.c:300-306) */
 
 /* resid_mask: bit b (0..15) luma4x4BlkIdx b has a slot; bits 16..19 Cb, 20..23 Cr;
  * bit 24: an Intra16x16 luma DC slot precedes the luma slots; bit 25: a chroma DC
@@ -73,7 +84,9 @@ typedef struct {
     uint16_t slice_id;        /* diagnostic only */
     uint8_t  ref_slot[4];     /* frame-pool slot of the reference picture per 8x8 quadrant (buffer identity for bS) */
     uint8_t  i4_mode[16];     /* Intra4x4PredMode by luma4x4BlkIdx */
-    uint8_t  reserved[20];
+    uint8_t  dbk_idc;         /* disable_deblocking_filter_idc of the macroblock's slice (diagnostic) */
+    uint8_t  flags;           /* H264B200_MBF_* */
+    uint8_t  reserved[18];
     int16_t  mv[16][2];       /* final motion vectors, quarter pel, by RASTER 4x4 position (by*4+bx): {hor, ver} */
 } h264b200_mb_t;
 

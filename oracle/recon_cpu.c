@@ -67,7 +67,7 @@ int recon_cpu_residual_mb(const h264b200_mb_t *mb, int16_t *coef)
     int16_t *slot = coef + (size_t)mb->coef_offset * 16;
     int dcy[16], dcc[8], blk, k, bad = 0, qp = mb->qp_y, qpc = mb->qp_c;
     int has_ldc = (mb->resid_mask & H264B200_RESID_LUMA_DC) != 0, has_cdc = (mb->resid_mask & H264B200_RESID_CHROMA_DC) != 0;
-    if (mb->mb_class == H264B200_MB_IPCM || mb->mb_class == H264B200_MB_MISSING) return 0;
+    if (mb->mb_class == H264B200_MB_IPCM || mb->mb_class == H264B200_MB_MISSING || mb->mb_class == H264B200_MB_CONCEAL) return 0;
     if (has_ldc) {
         int f[16], i, ls = H264_LEVEL_SCALE[qp % 6][0];
         for (i = 0; i < 4; i++) {
@@ -373,14 +373,67 @@ void recon_cpu_predict_picture(const h264b200_mb_t *mbs, const int16_t *coef, in
     /* raster order satisfies every intra dependency (left, up-left, up, up-right) */
     for (mby = 0; mby < hm; mby++) for (mbx = 0; mbx < wm; mbx++) {
         const h264b200_mb_t *mb = &mbs[mby * wm + mbx];
-        if (mb->mb_class == H264B200_MB_MISSING) continue;
+        if (mb->mb_class == H264B200_MB_MISSING || mb->mb_class == H264B200_MB_CONCEAL) continue;
         if (mb->mb_class == H264B200_MB_INTER) inter_mb(mb, coef, mbx, mby, cur, frames, wm, hm);
         else intra_mb(mb, coef, mbx, mby, cur);
     }
 }
 
+/* ==================================================== K3c: spatial concealment */
+/* ConcealMb's interpolation path + Transform (h264bsd_conceal.c:330-631), driven by the order list the host parser
+ * prepared (H264B200_MB_CONCEAL records; avail = usable neighbours at the macroblock's turn) */
+static void conceal_plane(uint8_t *P, int st, int x0, int y0, int S, int fl, int luma)
+{
+    const int g = S / 4, A = fl & H264B200_CN_ABOVE, B = fl & H264B200_CN_BELOW, L = fl & H264B200_CN_LEFT, R = fl & H264B200_CN_RIGHT;
+    int a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0}, l[4] = {0, 0, 0, 0}, r[4] = {0, 0, 0, 0}, fp[16], k, t, j = 0, hor = 0, ver = 0, x, y;
+    memset(fp, 0, sizeof fp);
+    for (k = 0; k < 4; k++) for (t = 0; t < g; t++) {
+        if (A) a[k] += P[(size_t)(y0 - 1) * st + x0 + k * g + t];
+        if (B) b[k] += P[(size_t)(y0 + S) * st + x0 + k * g + t];
+        if (L) l[k] += P[(size_t)(y0 + k * g + t) * st + x0 - 1];
+        if (R) r[k] += P[(size_t)(y0 + k * g + t) * st + x0 + S];
+    }
+    if (A) { j++; hor++; fp[0] += a[0] + a[1] + a[2] + a[3]; fp[1] += a[0] + a[1] - a[2] - a[3]; }
+    if (B) { j++; hor++; fp[0] += b[0] + b[1] + b[2] + b[3]; fp[1] += b[0] + b[1] - b[2] - b[3]; }
+    if (L) { j++; ver++; fp[0] += l[0] + l[1] + l[2] + l[3]; fp[4] += l[0] + l[1] - l[2] - l[3]; }
+    if (R) { j++; ver++; fp[0] += r[0] + r[1] + r[2] + r[3]; fp[4] += r[0] + r[1] - r[2] - r[3]; }
+    if (!hor && L && R) fp[1] = (l[0] + l[1] + l[2] + l[3] - r[0] - r[1] - r[2] - r[3]) >> (luma ? 5 : 4);
+    else if (hor) fp[1] >>= ((luma ? 3 : 2) + hor);
+    if (!ver && A && B) fp[4] = (a[0] + a[1] + a[2] + a[3] - b[0] - b[1] - b[2] - b[3]) >> (luma ? 5 : 4);
+    else if (ver) fp[4] >>= ((luma ? 3 : 2) + ver);
+    switch (j) {
+    case 1: fp[0] >>= luma ? 4 : 3; break;
+    case 2: fp[0] >>= luma ? 5 : 4; break;
+    case 3: fp[0] = (21 * fp[0]) >> (luma ? 10 : 9); break;
+    default: fp[0] >>= luma ? 6 : 5; break;
+    }
+    if (!fp[1] && !fp[4]) { for (k = 1; k < 16; k++) fp[k] = fp[0]; }
+    else {
+        int t0 = fp[0], t1 = fp[1], v = fp[4], c;
+        fp[0] = t0 + t1; fp[1] = t0 + (t1 >> 1); fp[2] = t0 - (t1 >> 1); fp[3] = t0 - t1;
+        fp[5] = fp[6] = fp[7] = v;
+        for (c = 0; c < 4; c++) {
+            int u0 = fp[c], u1 = fp[4 + c];
+            fp[c] = u0 + u1; fp[4 + c] = u0 + (u1 >> 1); fp[8 + c] = u0 - (u1 >> 1); fp[12 + c] = u0 - u1;
+        }
+    }
+    for (y = 0; y < S; y++) for (x = 0; x < S; x++) P[(size_t)(y0 + y) * st + x0 + x] = (uint8_t)clip255(fp[4 * (y / g) + x / g]);
+}
+
+void recon_cpu_conceal_picture(const h264b200_mb_t *mbs, const uint32_t *list, uint32_t n, int wm, int hm, uint8_t *frame)
+{
+    planes_t f = planes_of(frame, wm, hm);
+    uint32_t e;
+    for (e = 0; e < n; e++) {
+        const int mbx = (int)(list[e] % (uint32_t)wm), mby = (int)(list[e] / (uint32_t)wm), fl = mbs[list[e]].avail;
+        conceal_plane(f.y, f.w, mbx * 16, mby * 16, 16, fl, 1);
+        conceal_plane(f.cb, f.w / 2, mbx * 8, mby * 8, 8, fl, 0);
+        conceal_plane(f.cr, f.w / 2, mbx * 8, mby * 8, 8, fl, 0);
+    }
+}
+
 /* ==================================================== K4: deblocking */
-static inline int mb_intra(const h264b200_mb_t *m) { return m->mb_class != H264B200_MB_INTER; }
+static inline int mb_intra(const h264b200_mb_t *m) { return m->mb_class != H264B200_MB_INTER || (m->flags & H264B200_MBF_DBK_AS_INTRA); }
 
 /* bS between 4x4 blocks p (in mbp, raster index rp) and q (in mbq, raster rq); mb_edge: edge lies on a MB boundary */
 static int boundary_strength(const h264b200_mb_t *mbp, int rp, const h264b200_mb_t *mbq, int rq, int mb_edge)
@@ -538,6 +591,7 @@ static int cpu_pic_submit(h264_backend_t *be, void *inst, h264_pic_input_t *pic)
     for (i = 0; i < n; i++) if (recon_cpu_residual_mb(&pic->mbs[i], pic->coef)) in->errors |= 1;
     if (g_tap.residual) g_tap.residual(g_tap.user, pic->coef, pic->coef_used);
     recon_cpu_predict_picture(pic->mbs, pic->coef, (int)in->wm, (int)in->hm, in->frames[pic->cur_slot], in->frames);
+    if (pic->n_conceal) recon_cpu_conceal_picture(pic->mbs, (const uint32_t *)(pic->coef + (size_t)pic->conceal_offset * 16), pic->n_conceal, (int)in->wm, (int)in->hm, in->frames[pic->cur_slot]);
     memcpy(in->predeblock, in->frames[pic->cur_slot], (size_t)n * 384);
     if (g_tap.predeblock) g_tap.predeblock(g_tap.user, in->predeblock, (size_t)n * 384);
     recon_cpu_deblock_picture(pic->mbs, (int)in->wm, (int)in->hm, in->frames[pic->cur_slot]);

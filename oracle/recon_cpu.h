@@ -10,6 +10,8 @@
 int  recon_cpu_residual_mb(const h264b200_mb_t *mb, int16_t *coef);
 /* K2+K3: inter and intra prediction + residual add of a whole picture (slots already transformed). */
 void recon_cpu_predict_picture(const h264b200_mb_t *mbs, const int16_t *coef, int wm, int hm, uint8_t *cur_frame, uint8_t *const *frames);
+/* K3c: spatial concealment of the H264B200_MB_CONCEAL macroblocks, in the order of `list`. */
+void recon_cpu_conceal_picture(const h264b200_mb_t *mbs, const uint32_t *list, uint32_t n, int wm, int hm, uint8_t *frame);
 /* K4: in-loop deblocking of a whole picture, in place. */
 void recon_cpu_deblock_picture(const h264b200_mb_t *mbs, int wm, int hm, uint8_t *frame);
 /* single fractional samples (unit tests of the interpolators) */

@@ -91,3 +91,44 @@ def reverse_slice_order(data):
             out.append(n)
     out.extend(reversed(cur))
     return b"".join(sc + n for n in out)
+
+
+def drop_slices(data, drops):
+    """Remove whole slice NAL units: `drops` is a set of (picture index, slice index within the picture).
+    Models packet loss; the decoder must conceal the macroblocks of the missing slices."""
+    sc = b"\x00\x00\x00\x01"
+    nals = [n for n in data.split(sc) if n]
+    out, pic, sl = [], -1, 0
+    for n in nals:
+        if n[0] & 31 in (1, 5):
+            if n[1] & 0x80:            # first_mb_in_slice == 0: a new picture starts
+                pic += 1; sl = 0
+            keep = (pic, sl) not in drops
+            sl += 1
+            if not keep:
+                continue
+        out.append(n)
+    return b"".join(sc + n for n in out)
+
+
+# Packet-loss cases: (name, writer case, set of dropped (picture, slice) NAL units).  The reference conceals the
+# macroblocks of the missing slices (h264bsd_conceal.c); goldens also pin the number of concealed macroblocks.
+_LOSS_P = ("loss_base_p", 11, 9, 7, dict(slices_per_pic=3, num_ref_frames=2))
+_LOSS_I = ("loss_base_i", 11, 9, 5, dict(slices_per_pic=4, intra_only=1))
+_LOSS_M = ("loss_base_mixed", 20, 12, 6, dict(slices_per_pic=5, idr_period=3, p_intra_permille=100))
+LOSS = [
+    ("loss_p_mid_slices",    _LOSS_P, {(2, 1), (4, 1)}),
+    ("loss_p_first_slice",   _LOSS_P, {(3, 0)}),
+    ("loss_p_two_slices",    _LOSS_P, {(2, 1), (2, 2)}),
+    ("loss_whole_picture",   _LOSS_P, {(3, 0), (3, 1), (3, 2)}),
+    ("loss_idr_mid_slice",   _LOSS_P, {(0, 1)}),
+    ("loss_idr_first_slice", _LOSS_P, {(0, 0)}),
+    ("loss_idr_two_slices",  _LOSS_P, {(0, 0), (0, 2)}),
+    ("loss_intra_only",      _LOSS_I, {(0, 1), (1, 0), (2, 3), (3, 1), (3, 2)}),
+    ("loss_mixed",           _LOSS_M, {(0, 2), (1, 1), (3, 0), (3, 4), (4, 2)}),
+]
+
+
+def make_loss_stream(loss_case):
+    name, base, drops = loss_case
+    return drop_slices(make_stream(base), drops)

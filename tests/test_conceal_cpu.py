@@ -1,0 +1,39 @@
+"""CPU tests of error concealment for lost slices: the host decoder turns the macroblocks of
+missing slices into ordinary records (copy from the reference picture / grey picture) or into H264B200_MB_CONCEAL
+records with the reference's concealment order, and the oracle restatement reproduces the reference's frames and
+its count of concealed macroblocks (tests/golden/loss.json, made by running the unmodified reference)."""
+import hashlib
+import json
+import os
+
+import pytest
+
+import cases
+import util
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LOSS_GOLDEN = json.load(open(os.path.join(ROOT, "tests", "golden", "loss.json")))
+
+
+@pytest.mark.parametrize("lc", cases.LOSS, ids=[c[0] for c in cases.LOSS])
+def test_concealment_matches_reference_golden(lc):
+    data = cases.make_loss_stream(lc)
+    g = LOSS_GOLDEN[lc[0]]
+    assert hashlib.md5(data).hexdigest() == g["stream_md5"]
+    md5s, summary = util.oracle_md5(data)
+    assert md5s == g["frame_md5"]
+    assert summary["err_mbs"] == g["err_mbs"]
+
+
+def test_concealment_live_against_reference():
+    if util.reference_md5(b"\\x00\\x00\\x00\\x01\\x09\\x10") is None:
+        pytest.skip("oracle/_ref not built here")
+    import random
+    rng = random.Random(4)
+    for base in (cases._LOSS_P, cases._LOSS_M, cases._LOSS_I):
+        for _ in range(4):
+            drops = {(rng.randrange(base[3]), rng.randrange(base[4]["slices_per_pic"])) for _ in range(rng.randrange(1, 5))}
+            data = cases.drop_slices(cases.make_stream(base), drops)
+            a, sa = util.oracle_md5(data)
+            b, sb = util.reference_md5(data)
+            assert a == b and sa["err_mbs"] == sb["err_mbs"], (base[0], sorted(drops))

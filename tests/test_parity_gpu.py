@@ -242,3 +242,30 @@ def test_arbitrary_slice_order_on_gpu(golden):
         case = next(c for c in cases.SMALL if c[0] == name)
         got, info = capi.decode_annexb(cases.reverse_slice_order(cases.make_stream(case)))
         assert info["err_mbs"] == 0 and got == golden[name]["frame_md5"]
+
+
+@pytest.mark.parametrize("lc", cases.LOSS, ids=[c[0] for c in cases.LOSS])
+def test_concealment_of_lost_slices_on_gpu(lc):
+    """Lost slice NAL units: P macroblocks are copied from the reference picture by K2, I macroblocks are
+    interpolated by k3c_conceal in the reference's order, both deblocked as intra with QP 40 — frames and the
+    concealed-macroblock count equal the reference's (tests/golden/loss.json)."""
+    import json, os
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "loss.json")))[lc[0]]
+    got, info = capi.decode_annexb(cases.make_loss_stream(lc))
+    assert got == g["frame_md5"]
+    assert info["err_mbs"] == g["err_mbs"]
+
+
+def test_concealment_in_a_batch():
+    """Lossy and clean streams share launches; the conceal kernel only touches the pictures that need it."""
+    import json, os
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "loss.json")))
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "streams.json")))
+    streams = [cases.make_loss_stream(lc) for lc in cases.LOSS] + [cases.make_stream(c) for c in cases.SMALL[:4]]
+    with capi.Engine() as eng:
+        md5s, rs = eng.decode_streams_md5(streams, threads=4)
+    for lc, m in zip(cases.LOSS, md5s):
+        assert m == g[lc[0]]["frame_md5"], lc[0]
+    for c, m in zip(cases.SMALL[:4], md5s[len(cases.LOSS):]):
+        assert m == gold[c[0]]["frame_md5"], c[0]
+    assert rs.err_mbs == sum(g[lc[0]]["err_mbs"] for lc in cases.LOSS)

@@ -21,8 +21,9 @@ def _run_cli(exe, data, extra=()):
         r = subprocess.run([exe, "-m", *extra, path], capture_output=True, text=True, timeout=600)
     finally:
         os.remove(path)
-    assert r.returncode == 0, (exe, r.returncode, r.stderr[-400:])
     lines = r.stdout.splitlines()
+    # exit code 1 with a summary line = "decoded, but macroblocks were concealed" (like DecTestBench.c:424-428)
+    assert r.returncode == 0 or (r.returncode == 1 and lines and lines[-1].startswith("{")), (exe, r.returncode, r.stderr[-400:])
     return [l.split()[2] for l in lines if l.startswith("frame ")], json.loads(lines[-1])
 
 

@@ -29,6 +29,24 @@ for case in cases.SMALL + cases.FULL:
     os.remove(path)
 json.dump(out, open(os.path.join(ROOT, "tests", "golden", "streams.json"), "w"), indent=1, sort_keys=True)
 
+# packet-loss cases: the reference conceals; pin frames AND the concealed-macroblock count
+def ref_md5_lossy(path):
+    exe = os.path.join(ROOT, "oracle", "_ref", "refdec")
+    r = subprocess.run([exe, "-m", path], capture_output=True, text=True)
+    lines = r.stdout.splitlines()
+    return [l.split()[2] for l in lines if l.startswith("frame ")], json.loads(lines[-1])
+
+loss = {}
+for lc in cases.LOSS:
+    data = cases.make_loss_stream(lc)
+    path = "/tmp/golden_%s.264" % lc[0]
+    open(path, "wb").write(data)
+    md5s, summary = ref_md5_lossy(path)
+    loss[lc[0]] = {"stream_md5": hashlib.md5(data).hexdigest(), "frame_md5": md5s, "err_mbs": summary["err_mbs"]}
+    print(lc[0], len(md5s), "frames,", summary["err_mbs"], "concealed macroblocks")
+    os.remove(path)
+json.dump(loss, open(os.path.join(ROOT, "tests", "golden", "loss.json"), "w"), indent=1, sort_keys=True)
+
 # bench.py's parity gate: the first streams of its workload (rank 0), decoded by the reference
 from broadway_b200 import bitstream
 bench = {"width_mbs": 120, "height_mbs": 68, "frames": 16, "streams": []}
