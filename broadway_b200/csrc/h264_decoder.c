@@ -238,6 +238,32 @@ static int apply_output_format(h264_decoder_t *d)
     return d->be->set_output(d->be, d->be_inst, d->out_format, l, t, w, h);
 }
 
+/* Give the macroblocks of the slice that just failed back to "not decoded" (h264bsd_slice_data.c:302-358
+ * h264bsdMarkSliceCorrupted): a P slice loses all of them; an I slice keeps what lies more than
+ * max(picture width, 10) of its macroblocks before the last good one. */
+static void mark_slice_corrupted(h264_decoder_t *d, uint32_t first_mb)
+{
+    const uint32_t sid = d->slice_id, N = d->pic_size_mbs;
+    uint32_t cur = first_mb;
+    if (d->slice_last_mb) {
+        uint32_t i = d->slice_last_mb - 1, cnt = 0, lim = d->width_mbs > 10 ? d->width_mbs : 10;
+        while (i > cur) {
+            if (d->mbctx[i].slice_id == sid && ++cnt >= lim) break;
+            i--;
+        }
+        cur = i;
+    }
+    do {
+        if (d->mbctx[cur].slice_id != sid || !d->mbctx[cur].decoded) break;
+        d->mbctx[cur].decoded = 0;
+        if (d->active_pps->num_slice_groups > 1) {
+            const uint8_t *map = d->slice_group_map, grp = map[cur];
+            do cur++; while (cur < N && map[cur] != grp);
+            if (cur >= N) cur = 0;
+        } else cur = cur + 1 < N ? cur + 1 : 0;
+    } while (cur);
+}
+
 /* ------------------------------------------------------------ concealment */
 /* Macroblocks of lost slices (h264bsd_conceal.c:125-255 h264bsdConceal, :262-330 ConcealMb), expressed as ordinary
  * records so the kernels need nothing new:
@@ -483,8 +509,8 @@ u32 h264bsdDecode(storage_t *pStorage, u8 *byteStrm, u32 len, u32 picId, u32 *re
         h264_dpb_init_ref_list(&d->dpb);
         if (h264_dpb_reorder(&d->dpb, &d->sh)) return H264BSD_ERROR;
         if (h264_decode_slice_data(d, &b, &d->sh)) {
-            /* the reference marks the slice corrupt and conceals at the next access unit
-             * (h264bsd_slice_data.c:302-358); here its macroblocks stay MISSING */
+            /* the macroblocks of a slice that failed are given back (they are concealed when the access unit ends) */
+            mark_slice_corrupted(d, d->sh.first_mb);
             return H264BSD_ERROR;
         }
         if (d->num_decoded_mbs == d->pic_size_mbs) { pic_ready = 1; d->skip_redundant = 1; }

@@ -191,6 +191,7 @@ typedef struct h264_decoder {
 
     h264_slice_hdr_t sh;                          /* last valid slice header */
     uint32_t slice_id;                            /* restarts at 1 each picture */
+    uint32_t slice_last_mb;                       /* I slices: address of the last macroblock parsed without error (0: none) */
     uint32_t num_decoded_mbs, num_err_mbs;
     uint32_t current_pic_id;
 

@@ -442,6 +442,7 @@ int h264_decode_slice_data(h264_decoder_t *d, br_t *b, const h264_slice_hdr_t *s
     s.chroma_qp_off = d->active_pps->chroma_qp_index_offset;
     s.qp = sh->slice_qp;
     s.slice_id = (uint16_t)(++d->slice_id);
+    d->slice_last_mb = 0;
     for (i = 0; i <= H264_MAX_REFS; i++) s.ref_slot[i] = -1;
     if (s.is_p) for (i = 0; i < sh->num_ref_idx_active && i <= H264_MAX_REFS; i++) s.ref_slot[i] = h264_dpb_ref_slot(&d->dpb, i);
 
@@ -490,6 +491,7 @@ int h264_decode_slice_data(h264_decoder_t *d, br_t *b, const h264_slice_hdr_t *s
         }
         c->decoded = 1;
         mb_count++;
+        if (!s.is_p) d->slice_last_mb = addr;       /* h264bsd_slice_data.c:208-211 */
         more = br_more_data(b) || skip_run;
         if (d->active_pps->num_slice_groups > 1) {   /* next macroblock of the same slice group (h264bsd_util.c:219-245) */
             const uint8_t *map = d->slice_group_map, grp = map[addr];

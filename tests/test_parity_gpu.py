@@ -269,3 +269,18 @@ def test_concealment_in_a_batch():
     for c, m in zip(cases.SMALL[:4], md5s[len(cases.LOSS):]):
         assert m == gold[c[0]]["frame_md5"], c[0]
     assert rs.err_mbs == sum(g[lc[0]]["err_mbs"] for lc in cases.LOSS)
+
+
+def test_corrupted_streams_never_fault_and_equal_the_oracle():
+    """Bit errors inside slices: the CUDA path must not fault or hang on whatever records survive, and (same host
+    parser, same records) must produce the oracle's pictures and concealed-macroblock counts."""
+    import random
+    rng = random.Random(55)
+    bases = [cases.make_stream(c) for c in cases.SMALL[:14]]
+    for _ in range(24):
+        data = bytearray(rng.choice(bases))
+        for _ in range(rng.randrange(1, 4)):
+            data[rng.randrange(60, len(data))] ^= 1 << rng.randrange(8)
+        got, info = capi.decode_annexb(bytes(data))
+        want, s = util.oracle_md5(bytes(data))
+        assert got == want and info["err_mbs"] == s["err_mbs"]
