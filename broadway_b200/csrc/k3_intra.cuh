@@ -28,63 +28,18 @@
 #include "k_common.cuh"
 
 #define K3_WARPS 4
+#define K3_PUBLISH 2                /* macroblocks per progress hand-over (the release is a memory barrier) */
 #define K3_TP 48                    /* tile pitch (multiple of 16): interior at columns 16..31, up-right 32..35, left column 15 */
 
 struct __align__(16) K3Warp {
     h264b200_mb_t rec;
     __align__(16) uint8_t tile[17][K3_TP];       /* row 0 = samples above the macroblock */
     __align__(16) uint8_t ctile[2][9][24];       /* chroma: interior at columns 8..15, left column 7 */
+    uint8_t i4taps[9][16];                       /* H264_I4_TAPS copied to shared memory: indexed by lane, constant memory would serialise */
     __align__(16) int16_t res[26][16];           /* the macroblock's residual slots, staged once (the I4x4 chain must not wait on HBM 16 times) */
 };
 
 __device__ __forceinline__ uint8_t ldcg_u8(const uint8_t *p) { return __ldcg(p); }
-
-/* Intra4x4 prediction of sample (x,y) of a block whose top-left is at tile (tx,ty) */
-__device__ __forceinline__ int i4_pred(const uint8_t (*t)[K3_TP], int tx, int ty, int mode, int x, int y, bool has_top, bool has_left, bool has_ur)
-{
-#define T(i) ((int)t[ty - 1][tx + (((i) > 3 && !has_ur) ? 3 : (i))])
-#define L(i) ((int)t[ty + (i)][tx - 1])
-    switch (mode) {
-    case 0: return T(x);
-    case 1: return L(y);
-    case 2:
-        if (has_top && has_left) return (T(0) + T(1) + T(2) + T(3) + L(0) + L(1) + L(2) + L(3) + 4) >> 3;
-        if (has_left) return (L(0) + L(1) + L(2) + L(3) + 2) >> 2;
-        if (has_top) return (T(0) + T(1) + T(2) + T(3) + 2) >> 2;
-        return 128;
-    case 3:
-        if (x == 3 && y == 3) return (T(6) + 3 * T(7) + 2) >> 2;
-        return (T(x + y) + 2 * T(x + y + 1) + T(x + y + 2) + 2) >> 2;
-    case 4:
-        if (x > y) return (T(x - y - 2) + 2 * T(x - y - 1) + T(x - y) + 2) >> 2;
-        if (x < y) return (L(y - x - 2) + 2 * L(y - x - 1) + L(y - x) + 2) >> 2;
-        return (T(0) + 2 * T(-1) + L(0) + 2) >> 2;
-    case 5: {
-        int z = 2 * x - y, k = x - (y >> 1);
-        if (z >= 0 && !(z & 1)) return (T(k - 1) + T(k) + 1) >> 1;
-        if (z >= 0) return (T(k - 2) + 2 * T(k - 1) + T(k) + 2) >> 2;
-        if (z == -1) return (L(0) + 2 * T(-1) + T(0) + 2) >> 2;
-        return (L(y - 1) + 2 * L(y - 2) + L(y - 3) + 2) >> 2; }
-    case 6: {
-        int z = 2 * y - x, k = y - (x >> 1);
-        if (z >= 0 && !(z & 1)) return (L(k - 1) + L(k) + 1) >> 1;
-        if (z >= 0) return (L(k - 2) + 2 * L(k - 1) + L(k) + 2) >> 2;
-        if (z == -1) return (L(0) + 2 * T(-1) + T(0) + 2) >> 2;
-        return (T(x - 1) + 2 * T(x - 2) + T(x - 3) + 2) >> 2; }
-    case 7: {
-        int k = x + (y >> 1);
-        if (!(y & 1)) return (T(k) + T(k + 1) + 1) >> 1;
-        return (T(k) + 2 * T(k + 1) + T(k + 2) + 2) >> 2; }
-    default: {
-        int z = x + 2 * y, k = y + (x >> 1);
-        if (z > 5) return L(3);
-        if (z == 5) return (L(2) + 3 * L(3) + 2) >> 2;
-        if (!(z & 1)) return (L(k) + L(k + 1) + 1) >> 1;
-        return (L(k) + 2 * L(k + 1) + L(k + 2) + 2) >> 2; }
-    }
-#undef T
-#undef L
-}
 
 /* plane prediction parameters from a neighbour row/column held in shared memory.
  * top(i)/left(i) for i in -1..n-1.  Returns a, b, c of 8.3.3.4 / 8.3.4.4. */
@@ -103,12 +58,12 @@ __device__ __forceinline__ void plane_params(FT top, FL left, int &a, int &bb, i
     else { bb = (34 * hh + 32) >> 6; cc = (34 * vv + 32) >> 6; }
 }
 
-__device__ void k3_macroblock(const PicJob &job, K3Warp &w, int mbx, int mby, int lane)
+/* recv: the macroblock's record, one 16-byte piece in each of lanes 0..7 (fetched by the caller before it waited) */
+__device__ void k3_macroblock(const PicJob &job, K3Warp &w, int mbx, int mby, int lane, int4 recv)
 {
     const int W = job.wm * 16, H = job.hm * 16, CW = W >> 1;
     const size_t ysize = (size_t)W * H, csize = ysize >> 2;
-    const h264b200_mb_t *mb = job.mbs + (size_t)mby * job.wm + mbx;
-    if (lane < 8) reinterpret_cast<int4 *>(&w.rec)[lane] = __ldg(reinterpret_cast<const int4 *>(mb) + lane);
+    if (lane < 8) reinterpret_cast<int4 *>(&w.rec)[lane] = recv;
     __syncwarp();
     const int cls = w.rec.mb_class;
     uint8_t *Y = job.cur + (size_t)mby * 16 * W + mbx * 16;
@@ -183,7 +138,21 @@ __device__ void k3_macroblock(const PicJob &job, K3Warp &w, int mbx, int mby, in
         }
         *reinterpret_cast<uint2 *>(Y + (size_t)y * W + x0) = make_uint2(outw[0], outw[1]);
     } else {
-        /* ---- Intra4x4: 16 blocks in decoding order through the tile ---- */
+        /* ---- Intra4x4: 16 blocks in decoding order through the tile.  Every sample of the eight directional modes
+         * is a 1/2/3-tap filter over consecutive entries of one edge array E = [L3 L3 L2 L1 L0 TL T0..T7 T7]
+         * (H264_I4_TAPS, generated by tools/gen_i4_tables.py): no per-mode code, no divergence inside a block.
+         * A block only reads samples outside itself, so one warp barrier per block is enough. ---- */
+        /* everything that does not depend on reconstructed samples is fetched before the serial chain: per block this
+         * lane's tap descriptor and residual value (the chain then is: 3 tile loads -> filter -> store -> barrier) */
+        const int l16 = lane & 15;
+        int tp_all[16], rs_all[16];
+#pragma unroll
+        for (int blk = 0; blk < 16; blk++) {
+            const int mode = w.rec.i4_mode[blk];
+            tp_all[blk] = mode == 2 ? 0 : w.i4taps[mode][l16];
+            rs_all[blk] = ((mask >> blk) & 1) ? (int)w.res[slot_index(mask, blk)][l16] : 0;
+        }
+#pragma unroll
         for (int blk = 0; blk < 16; blk++) {
             const int x4 = (blk & 1) | ((blk >> 1) & 2), y4 = ((blk >> 1) & 1) | ((blk >> 2) & 2);
             const bool has_left = x4 > 0 || aA, has_top = y4 > 0 || aB;
@@ -191,14 +160,31 @@ __device__ void k3_macroblock(const PicJob &job, K3Warp &w, int mbx, int mby, in
             if (y4 == 0) has_ur = x4 < 3 ? aB : aC;
             else has_ur = (0x5744u >> blk) & 1;        /* above-right block already decoded inside this macroblock */
             const int tx = 16 + 4 * x4, ty = 1 + 4 * y4;
-            int v = 0;
             if (lane < 16) {
-                const int x = lane & 3, y = lane >> 2;
-                v = i4_pred(w.tile, tx, ty, w.rec.i4_mode[blk], x, y, has_top, has_left, has_ur);
-                if ((mask >> blk) & 1) v = clip255(v + w.res[slot_index(mask, blk)][lane]);
+                const int tp = tp_all[blk];
+                int v;
+                if (tp == 0) {                         /* DC (8.3.1.2.3) */
+                    const uint8_t *top = &w.tile[ty - 1][tx];
+                    const int st = top[0] + top[1] + top[2] + top[3];
+                    const int sl = w.tile[ty][tx - 1] + w.tile[ty + 1][tx - 1] + w.tile[ty + 2][tx - 1] + w.tile[ty + 3][tx - 1];
+                    v = has_top && has_left ? (st + sl + 4) >> 3 : has_left ? (sl + 2) >> 2 : has_top ? (st + 2) >> 2 : 128;
+                } else {
+                    const int i0 = tp & 15, n = tp >> 4;
+                    int e[3];
+#pragma unroll
+                    for (int k = 0; k < 3; k++) {
+                        const int i = min(i0 + k, 14);
+                        if (i >= 5) {                  /* TL, T0..T7 (T4..T7 repeat T3 when the block above-right is not available) */
+                            int c = min(i - 6, 7);
+                            if (c > 3 && !has_ur) c = 3;
+                            e[k] = w.tile[ty - 1][tx + c];
+                        } else e[k] = w.tile[ty + min(3, 4 - i)][tx - 1];
+                    }
+                    v = n == 1 ? e[0] : n == 2 ? (e[0] + e[1] + 1) >> 1 : (e[0] + 2 * e[1] + e[2] + 2) >> 2;
+                }
+                if ((mask >> blk) & 1) v = clip255(v + rs_all[blk]);
+                w.tile[ty + (lane >> 2)][tx + (lane & 3)] = (uint8_t)v;
             }
-            __syncwarp();
-            if (lane < 16) w.tile[ty + (lane >> 2)][tx + (lane & 3)] = (uint8_t)v;
             __syncwarp();
         }
         if (lane < 16) *reinterpret_cast<int4 *>(Y + (size_t)lane * W) = *reinterpret_cast<const int4 *>(&w.tile[1 + lane][16]);
@@ -246,11 +232,13 @@ __device__ void k3_macroblock(const PicJob &job, K3Warp &w, int mbx, int mby, in
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(K3_WARPS * 32) k3_intra(Batch b)
+__global__ void __launch_bounds__(K3_WARPS * 32, 6) k3_intra(Batch b)
 {
     __shared__ K3Warp sm[K3_WARPS];
     const int lane = threadIdx.x & 31;
     K3Warp &w = sm[threadIdx.x >> 5];
+    for (int i = lane; i < 9 * 16; i += 32) (&w.i4taps[0][0])[i] = H264_I4_TAPS[i >> 4][i & 15];
+    __syncwarp();
     const uint32_t n_tasks = (uint32_t)b.n_jobs * (uint32_t)b.max_hm;
     for (;;) {
         uint32_t t = 0;
@@ -263,17 +251,20 @@ __global__ void __launch_bounds__(K3_WARPS * 32) k3_intra(Batch b)
         const int wm = job.wm;
         const h264b200_mb_t *rowrec = job.mbs + (size_t)row * wm;
         const int32_t *above = job.progress + row - 1;
-        int seen = row > 0 ? 0 : 0x7fffffff;
-        int x = 0;
-        while (x < wm) {
-            int cls = (x + lane < wm) ? __ldg(reinterpret_cast<const uint8_t *>(rowrec + x + lane)) : 0;
+        int seen = row > 0 ? 0 : 0x7fffffff, published = 0;
+        for (int x0 = 0; x0 < wm; x0 += 32) {
+            const int cls = (x0 + lane < wm) ? __ldg(reinterpret_cast<const uint8_t *>(rowrec + x0 + lane)) : 0;
             unsigned m = __ballot_sync(0xffffffffu, cls == H264B200_MB_I4x4 || cls == H264B200_MB_I16x16 || cls == H264B200_MB_IPCM);
-            if (!m) { x += 32; continue; }
-            x += __ffs(m) - 1;
-            wf_publish2(job.progress + row, x, lane);            /* everything left of x is final */
-            wf_wait2(above, min(x + 2, wm), seen, lane);
-            k3_macroblock(job, w, x, row, lane);
-            x++;
+            while (m) {
+                const int x = x0 + __ffs(m) - 1;
+                m &= m - 1;
+                /* the record is requested before the hand-over so that its latency overlaps the release and the wait */
+                int4 recv = make_int4(0, 0, 0, 0);
+                if (lane < 8) recv = __ldg(reinterpret_cast<const int4 *>(rowrec + x) + lane);
+                if (x - published >= K3_PUBLISH) { wf_publish2(job.progress + row, x, lane); published = x; }   /* everything left of x is final */
+                wf_wait2(above, min(x + 2, wm), seen, lane);
+                k3_macroblock(job, w, x, row, lane, recv);
+            }
         }
         wf_publish2(job.progress + row, wm, lane);
     }
