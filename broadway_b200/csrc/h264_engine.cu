@@ -11,9 +11,11 @@
  *     K1 k1_transform   dequant + inverse transforms          (k1_transform.cuh)
  *     K2 k2_inter       motion compensation + residual add    (k2_inter.cuh)
  *     K3 k3_intra       intra prediction wavefront            (k3_intra.cuh)
+ *        k3c_conceal    spatial concealment of lost MBs       (k3c_conceal.cuh; only pictures that lost slices)
  *     K4 k4_deblock     deblocking wavefront                  (k4_deblock.cuh)
- * then copies each finished frame into a pinned host mirror, which is the
- * pointer h264bsdNextOutputPicture returns (Decoder.c:113-147 layout).
+ * then copies each finished frame — or, on request, its cropped RGBA version (K5,
+ * k5_rgba.cuh) — into a pinned host mirror, which is the pointer
+ * h264bsdNextOutputPicture returns (Decoder.c:113-147 layout).
  *
  * HBM layout per decoder instance: n_slots frames back to back, each planar
  * I420, MB aligned (Y 16wm x 16hm, Cb, Cr; pitch = width) — exactly the
@@ -116,7 +118,6 @@ struct h264b200_engine {
     h264b200_stats_t st;
     uint32_t flags;                /* H264B200_ENGINE_* */
     std::vector<Retained *> retained;
-    int32_t *d_replay_ctrl; size_t replay_ctrl_cap;
     /* per-kernel timing of replays */
     std::vector<cudaEvent_t> tev;  /* 5 events per replayed batch */
     std::vector<int> tev_batch;
@@ -148,7 +149,7 @@ static void picbuf_free(PicBuf *p)
 }
 
 /* algorithmic bytes of one picture per kernel family, as SURVEY.md 8(d) defines them */
-static void count_bytes(const h264_pic_input_t *pic, uint32_t n_mbs, uint64_t out[4], uint32_t *coded_blocks)
+static void count_bytes(const h264_pic_input_t *pic, uint32_t n_mbs, uint64_t out[4])
 {
     uint64_t inter = 0, intra = 0, blocks = 0, dc = 0, blk_inter = 0, blk_intra = 0, dbk = 0;
     for (uint32_t i = 0; i < n_mbs; i++) {
@@ -163,7 +164,6 @@ static void count_bytes(const h264_pic_input_t *pic, uint32_t n_mbs, uint64_t ou
     out[1] = inter * (384 + 384 + 128) + blk_inter * 32;    /* K2 */
     out[2] = intra * (384 + 64 + 128) + blk_intra * 32;     /* K3 */
     out[3] = dbk * (384 + 384 + 128);                       /* K4 */
-    if (coded_blocks) *coded_blocks = (uint32_t)blocks;
 }
 
 /* ------------------------------------------------------------ kernel launch */
@@ -270,7 +270,7 @@ static uint32_t submit_locked(h264b200_engine *e)
         if ((int)in->hm > pl.max_hm) pl.max_hm = (int)in->hm;
         /* the frame being written may still be on its way to the host from an earlier batch */
         if (in->slot_flags[pic->cur_slot] & 2) cudaStreamWaitEvent(e->s_comp, in->slot_ready[pic->cur_slot], 0);
-        if (retain) { uint64_t bb[4]; count_bytes(pic, in->n_mbs, bb, nullptr); for (int k = 0; k < 4; k++) bytes[k] += bb[k]; }
+        if (retain) { uint64_t bb[4]; count_bytes(pic, in->n_mbs, bb); for (int k = 0; k < 4; k++) bytes[k] += bb[k]; }
     }
     pl.total_mbs = mb_base; pl.n_jobs = (int)n;
 
@@ -536,7 +536,6 @@ extern "C" h264b200_engine_t *h264b200EngineCreateEx(int device, uint32_t flags)
     e->device = device; e->flags = flags; e->next_scr = 0;
     memset(&e->st, 0, sizeof e->st); memset(e->scr, 0, sizeof e->scr);
     memset(e->k_ms, 0, sizeof e->k_ms); memset(e->k_bytes, 0, sizeof e->k_bytes); memset(e->k_launches, 0, sizeof e->k_launches);
-    e->d_replay_ctrl = NULL; e->replay_ctrl_cap = 0;
     CUDA_TRY(cudaSetDevice(device), { delete e; return NULL; });
     cudaDeviceProp p;
     CUDA_TRY(cudaGetDeviceProperties(&p, device), { delete e; return NULL; });
@@ -599,7 +598,6 @@ extern "C" void h264b200EngineDestroy(h264b200_engine_t *e)
         if (s.d_ctrl) cudaFree(s.d_ctrl);
         cudaEventDestroy(s.done); cudaEventDestroy(s.d2h_done);
     }
-    if (e->d_replay_ctrl) cudaFree(e->d_replay_ctrl);
     cudaFree(e->d_err); cudaFreeHost(e->h_err);
     cudaEventDestroy(e->ev_h2d); cudaEventDestroy(e->ev_comp); cudaEventDestroy(e->ev_rep0); cudaEventDestroy(e->ev_rep1);
     cudaStreamDestroy(e->s_h2d); cudaStreamDestroy(e->s_comp); cudaStreamDestroy(e->s_d2h);
