@@ -184,8 +184,9 @@ static void launch_kernels(h264b200_engine *e, const Batch &b, const BatchPlan &
     }
     if (pl.k3c) { k3c_conceal<<<pl.n_jobs, 32, 0, s>>>(b); e->st.kernel_launches++; }   /* lost slices only: one warp per picture */
     if (tev) cudaEventRecord(tev[3], s);
-    if (pl.k4) {
-        uint32_t blocks = (n_tasks + K4_WARPS - 1) / K4_WARPS, cap = (uint32_t)e->sm_count * 16;
+    if (pl.k4) {                   /* one warp per PAIR of macroblock rows */
+        uint32_t n_pairs = (uint32_t)pl.n_jobs * (((uint32_t)pl.max_hm + 1) / 2);
+        uint32_t blocks = (n_pairs + K4_WARPS - 1) / K4_WARPS, cap = (uint32_t)e->sm_count * 16;
         k4_deblock<<<blocks < cap ? blocks : cap, K4_WARPS * 32, 0, s>>>(b); e->st.kernel_launches++;
     }
     if (tev) cudaEventRecord(tev[4], s);

@@ -17,6 +17,7 @@
  */
 #define _GNU_SOURCE
 #include <pthread.h>
+#include <sched.h>
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
@@ -35,6 +36,7 @@ typedef struct {
     uint8_t *buf; const uint8_t *src; size_t len, pos;
     u32 pic_id, out_index;
     int inited, finished, failed, flushed;
+    uint32_t stepped;                 /* rounds this stream has been advanced through (hand-over between the parse and the output phase) */
     pending_t cur[MAX_PENDING], prev[MAX_PENDING];
     int n_cur, n_prev;
     u32 width, height;
@@ -55,6 +57,7 @@ struct runner {
     pthread_mutex_t mu; pthread_cond_t cv;
     uint32_t arrived, generation; uint64_t round_sum, last_sum;
     uint32_t rounds;
+    uint32_t next_parse, next_out;    /* per-round work counters: streams are claimed one at a time, so a slow stream never idles a thread */
 };
 
 /* Barrier; the last arriver launches the batch (every picture of the round is queued by then, and no
@@ -67,6 +70,7 @@ static uint64_t round_barrier(runner_t *r, uint64_t produced)
     r->round_sum += produced;
     if (++r->arrived == r->n_threads) {
         h264b200EngineSubmit(r->e);
+        __atomic_store_n(&r->next_parse, 0, __ATOMIC_RELAXED); __atomic_store_n(&r->next_out, 0, __ATOMIC_RELAXED);
         r->last_sum = r->round_sum; r->round_sum = 0; r->arrived = 0; r->generation++; r->rounds++;
         pthread_cond_broadcast(&r->cv);
     } else {
@@ -125,35 +129,33 @@ static void consume_prev(worker_t *w, rstream_t *s, uint32_t stream_index)
 static void *worker_main(void *arg)
 {
     worker_t *w = (worker_t *)arg; runner_t *r = w->r;
-    uint32_t i;
-    for (i = w->tid; i < r->n_streams; i += r->n_threads) {   /* private copy, made by the thread that will parse it */
-        rstream_t *s = &r->s[i];
-        if (s->buf && s->inited) { memcpy(s->buf, s->src, s->len); memset(s->buf + s->len, 0, 16); }
-    }
-    for (;;) {
+    uint32_t i, round;
+    for (round = 1;; round++) {
         uint64_t produced = 0;
-        for (i = w->tid; i < r->n_streams; i += r->n_threads) {
+        /* parse phase: every thread claims the next unparsed stream of the round */
+        while ((i = __atomic_fetch_add(&r->next_parse, 1, __ATOMIC_RELAXED)) < r->n_streams) {
             rstream_t *s = &r->s[i];
+            /* private copy (the decoder strips emulation prevention bytes in place), made by the first thread to touch the stream */
+            if (round == 1 && s->buf && s->inited) { memcpy(s->buf, s->src, s->len); memset(s->buf + s->len, 0, 16); }
             if (!s->finished && !s->failed) {
                 double t0 = now_s();
                 produced += (uint64_t)step_stream(s);
                 w->parse_s += now_s() - t0;
             }
+            __atomic_store_n(&s->stepped, round, __ATOMIC_RELEASE);
         }
-        /* pictures popped in the PREVIOUS round were launched one barrier ago: the GPU had this whole
-         * parse to finish them */
-        for (i = w->tid; i < r->n_streams; i += r->n_threads) consume_prev(w, &r->s[i], i);
-        if (round_barrier(r, produced) == 0) break;
-        for (i = w->tid; i < r->n_streams; i += r->n_threads) {
+        /* output phase: pictures popped in the PREVIOUS round were launched one barrier ago, so the GPU had
+         * this whole parse phase to finish them.  Streams are taken in the order they were parsed; the few
+         * still being parsed by another thread are waited for (the decoder state is single-threaded). */
+        while ((i = __atomic_fetch_add(&r->next_out, 1, __ATOMIC_RELAXED)) < r->n_streams) {
             rstream_t *s = &r->s[i];
+            while (__atomic_load_n(&s->stepped, __ATOMIC_ACQUIRE) != round) sched_yield();
+            consume_prev(w, s, i);
             memcpy(s->prev, s->cur, (size_t)s->n_cur * sizeof(pending_t)); s->n_prev = s->n_cur; s->n_cur = 0;
         }
+        if (round_barrier(r, produced) == 0) break;
     }
-    for (i = w->tid; i < r->n_streams; i += r->n_threads) {
-        rstream_t *s = &r->s[i];
-        memcpy(s->prev, s->cur, (size_t)s->n_cur * sizeof(pending_t)); s->n_prev = s->n_cur; s->n_cur = 0;
-        consume_prev(w, s, i);
-    }
+    for (i = w->tid; i < r->n_streams; i += r->n_threads) consume_prev(w, &r->s[i], i);   /* what the last round popped */
     return NULL;
 }
 
