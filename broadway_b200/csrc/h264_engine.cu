@@ -187,7 +187,8 @@ static void launch_kernels(h264b200_engine *e, const Batch &b, const BatchPlan &
     if (pl.k4) {                   /* one warp per PAIR of macroblock rows */
         uint32_t n_pairs = (uint32_t)pl.n_jobs * (((uint32_t)pl.max_hm + 1) / 2);
         uint32_t blocks = (n_pairs + K4_WARPS - 1) / K4_WARPS, cap = (uint32_t)e->sm_count * 16;
-        k4_deblock<<<blocks < cap ? blocks : cap, K4_WARPS * 32, 0, s>>>(b); e->st.kernel_launches++;
+        k4_deblock<<<blocks < cap ? blocks : cap, K4_WARPS * 32, 0, s>>>(b);
+        e->st.kernel_launches++;
     }
     if (tev) cudaEventRecord(tev[4], s);
 }

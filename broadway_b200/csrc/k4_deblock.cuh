@@ -52,15 +52,23 @@
 #define K4_PUBLISH 2         /* macroblocks per progress hand-over */
 
 /* the window of one row half: the macroblock plus 4 samples to the left and 4 (2 chroma) rows above */
+/* Bank layout (found by enumerating paddings against the access patterns of the two passes, the commit and the
+ * write-back, all 32 lanes = both halves at once): luma at bank 0, chroma one word later with its planes 40 words
+ * apart, the two halves 16 banks apart.  47 shared-memory wavefronts for the 38 access instructions of a step
+ * where the unpadded layout needed 96. */
+struct K4Chroma { __align__(4) uint8_t r[12][K4_CP]; uint8_t pad[16]; };
 struct __align__(16) K4Half {
     h264b200_mb_t rec[2];    /* by macroblock column parity: rec[x & 1] current, the other one left */
     h264b200_mb_t top;
     __align__(4) uint8_t y[20][K4_LP];      /* rows/cols 0..3: samples above / left of the macroblock */
-    __align__(4) uint8_t c[2][12][K4_CP];
+    uint32_t pad0;
+    K4Chroma c[2];
     uint8_t bs[2][4][4];     /* [dir][edge][segment] */
     uint32_t thr[2][3];      /* [luma/chroma][left, top, inner]: alpha | beta << 8 */
     uint32_t tc0[2][3];      /* tc0(bS=1) | tc0(bS=2) << 8 | tc0(bS=3) << 16 */
+    uint32_t pad1[7];
 };
+static_assert(sizeof(K4Half) % 128 == 64, "the two row halves must sit 16 banks apart");
 struct __align__(16) K4Pair {
     K4Half h[2];
     uint32_t ring[2][32];    /* [macroblock parity]: window rows 16..19 (20 words), chroma rows 10..11 (12 words) of the upper row */
@@ -69,17 +77,21 @@ struct __align__(16) K4Pair {
 /* everything of the NEXT macroblock that can be fetched ahead, one register set per lane */
 struct K4Pre { int4 rec; int4 y; int2 c; uint32_t top0, top1; };
 
-__device__ __forceinline__ bool rec_intra(const h264b200_mb_t &m) { return m.mb_class != H264B200_MB_INTER || (m.flags & H264B200_MBF_DBK_AS_INTRA); }
+/* Records are read as 32-bit words (h264b200_records.h): word 0 = mb_class | qp_y << 8 | qp_c << 16 | qp_dbk << 24,
+ * word 1 = chroma_qp_off | dbk_flags << 8 | off_a << 16 | off_b << 24, word 5 = nz_mask | slice_id << 16,
+ * word 6 = ref_slot[4], word 11 = dbk_idc | flags << 8, words 16..31 = mv[16]. */
+__device__ __forceinline__ bool rec_intra(const uint32_t *m) { return (m[0] & 0xff) != H264B200_MB_INTER || ((m[11] >> 8) & H264B200_MBF_DBK_AS_INTRA); }
 
-/* bS between 4x4 block rp of macroblock p and block rq of macroblock q (raster indices) */
-__device__ __forceinline__ int dbk_bs(const h264b200_mb_t &p, int rp, const h264b200_mb_t &q, int rq, bool mb_edge)
+/* bS between 4x4 block rp of macroblock p and block rq of macroblock q (raster indices); straight-line code */
+__device__ __forceinline__ int dbk_bs(const uint32_t *p, int rp, const uint32_t *q, int rq, bool any_intra, bool mb_edge)
 {
-    if (rec_intra(p) || rec_intra(q)) return mb_edge ? 4 : 3;
     const int bp = (rp & 1) | ((rp & 2) << 1) | ((rp & 4) >> 1) | (rp & 8), bq = (rq & 1) | ((rq & 2) << 1) | ((rq & 4) >> 1) | (rq & 8);
-    if (((p.nz_mask >> bp) | (q.nz_mask >> bq)) & 1) return 2;
-    if (p.ref_slot[(rp >> 3) * 2 + ((rp & 3) >> 1)] != q.ref_slot[(rq >> 3) * 2 + ((rq & 3) >> 1)]) return 1;
-    if (abs(p.mv[rp][0] - q.mv[rq][0]) >= 4 || abs(p.mv[rp][1] - q.mv[rq][1]) >= 4) return 1;
-    return 0;
+    const bool nz = ((p[5] >> bp) | (q[5] >> bq)) & 1;
+    const uint32_t refp = (p[6] >> (8 * ((rp >> 3) * 2 + ((rp & 3) >> 1)))) & 0xff, refq = (q[6] >> (8 * ((rq >> 3) * 2 + ((rq & 3) >> 1)))) & 0xff;
+    const uint32_t mp = p[16 + rp], mq = q[16 + rq];
+    const int dx = (int)(int16_t)mp - (int)(int16_t)mq, dy = ((int)mp >> 16) - ((int)mq >> 16);
+    const bool far = (unsigned)(dx + 3) > 6u || (unsigned)(dy + 3) > 6u || refp != refq;     /* abs(d) >= 4, quarter samples */
+    return any_intra ? (mb_edge ? 4 : 3) : nz ? 2 : far ? 1 : 0;
 }
 
 /* geometry of one row walk (per row half) */
@@ -126,11 +138,11 @@ __device__ __forceinline__ void k4_commit(K4Half &w, int x, int hl, int row, con
     else if (row > 0) reinterpret_cast<int4 *>(&w.top)[hl - 8] = p.rec;
     uint32_t *dy = reinterpret_cast<uint32_t *>(&w.y[4 + hl][4]);
     dy[0] = (uint32_t)p.y.x; dy[1] = (uint32_t)p.y.y; dy[2] = (uint32_t)p.y.z; dy[3] = (uint32_t)p.y.w;
-    uint32_t *dc = reinterpret_cast<uint32_t *>(&w.c[hl >> 3][4 + (hl & 7)][4]);
+    uint32_t *dc = reinterpret_cast<uint32_t *>(&w.c[hl >> 3].r[4 + (hl & 7)][4]);
     dc[0] = (uint32_t)p.c.x; dc[1] = (uint32_t)p.c.y;
     if (row > 0) {
         *reinterpret_cast<uint32_t *>(&w.y[hl >> 2][4 + (hl & 3) * 4]) = p.top0;
-        if (hl < 8) *reinterpret_cast<uint32_t *>(&w.c[hl >> 2][2 + ((hl >> 1) & 1)][4 + (hl & 1) * 4]) = p.top1;
+        if (hl < 8) *reinterpret_cast<uint32_t *>(&w.c[hl >> 2].r[2 + ((hl >> 1) & 1)][4 + (hl & 1) * 4]) = p.top1;
     }
 }
 
@@ -140,10 +152,12 @@ __device__ __forceinline__ void k4_commit(K4Half &w, int x, int hl, int row, con
 __device__ __forceinline__ bool k4_filter(K4Half &w, int x, int hl, int half, bool act)
 {
     const h264b200_mb_t &q = w.rec[x & 1], &left = w.rec[(x & 1) ^ 1], &top = w.top;
-    const int fl = act ? q.dbk_flags : 0;
-    const bool f_left = (fl & H264B200_DBK_LEFT) && left.mb_class != H264B200_MB_MISSING;
-    const bool f_top = (fl & H264B200_DBK_TOP) && top.mb_class != H264B200_MB_MISSING;
+    const uint32_t *qw = reinterpret_cast<const uint32_t *>(&q), *lw = reinterpret_cast<const uint32_t *>(&left), *tw = reinterpret_cast<const uint32_t *>(&top);
+    const int fl = act ? (int)((qw[1] >> 8) & 0xff) : 0;
+    const bool f_left = (fl & H264B200_DBK_LEFT) && (lw[0] & 0xff) != H264B200_MB_MISSING;
+    const bool f_top = (fl & H264B200_DBK_TOP) && (tw[0] & 0xff) != H264B200_MB_MISSING;
     const bool f_inner = fl & H264B200_DBK_INNER;
+    const bool q_in = rec_intra(qw), l_in = rec_intra(lw), t_in = rec_intra(tw);
 
     /* ---- boundary strengths: lane hl = edge*4 + segment, both directions ---- */
     unsigned weak[2], strong[2];                       /* one bit per (half, edge, segment) and direction */
@@ -152,10 +166,12 @@ __device__ __forceinline__ bool k4_filter(K4Half &w, int x, int hl, int half, bo
 #pragma unroll
         for (int dir = 0; dir < 2; dir++) {
             const int rq = dir ? e * 4 + k : k * 4 + e;
-            int bsv = 0;
-            if (e == 0) {
-                if (dir ? f_top : f_left) bsv = dbk_bs(dir ? top : left, dir ? 12 + k : k * 4 + 3, q, rq, true);
-            } else if (f_inner) bsv = dbk_bs(q, dir ? rq - 4 : rq - 1, q, rq, false);
+            /* the block on the other side of the edge: in the left / upper macroblock for edge 0 */
+            const uint32_t *pw_ = e ? qw : dir ? tw : lw;
+            const int rp = e ? (dir ? rq - 4 : rq - 1) : dir ? 12 + k : k * 4 + 3;
+            const bool on = e ? f_inner : dir ? f_top : f_left;
+            const bool any_intra = q_in | (e ? q_in : dir ? t_in : l_in);
+            const int bsv = on ? dbk_bs(pw_, rp, qw, rq, any_intra, e == 0) : 0;
             w.bs[dir][e][k] = (uint8_t)bsv;
             weak[dir] = __ballot_sync(0xffffffffu, bsv != 0 && bsv < 4); strong[dir] = __ballot_sync(0xffffffffu, bsv == 4);
         }
@@ -183,11 +199,13 @@ __device__ __forceinline__ bool k4_filter(K4Half &w, int x, int hl, int half, bo
      * 4-sample (2-sample) segment, so they share bS. ---- */
     const bool luma = hl < 8;
     const int ch = luma ? 0 : 1, pl = (hl >> 2) & 1, i = luma ? hl : (hl & 3);   /* i: line pair index */
-#pragma unroll
+    /* the direction loop stays rolled: one copy of the four edge filters in the instruction stream instead of two
+     * (the unrolled kernel was 45 KB of SASS and stalled on instruction fetch, more so with more resident warps) */
+#pragma unroll 1
     for (int dir = 0; dir < 2; dir++) {
         uint32_t v[20];
         if (dir == 0) {                                /* two rows: word loads */
-            const uint32_t *ra = luma ? reinterpret_cast<const uint32_t *>(&w.y[4 + 2 * i][0]) : reinterpret_cast<const uint32_t *>(&w.c[pl][4 + 2 * i][0]);
+            const uint32_t *ra = luma ? reinterpret_cast<const uint32_t *>(&w.y[4 + 2 * i][0]) : reinterpret_cast<const uint32_t *>(&w.c[pl].r[4 + 2 * i][0]);
             const int pw = luma ? K4_LP / 4 : K4_CP / 4;
 #pragma unroll
             for (int k = 0; k < 5; k++) {
@@ -195,7 +213,7 @@ __device__ __forceinline__ bool k4_filter(K4Half &w, int x, int hl, int half, bo
                 else { v[4 * k] = v[4 * k + 1] = v[4 * k + 2] = v[4 * k + 3] = 0; }
             }
         } else {                                       /* two columns: 16-bit loads, consecutive lanes hit consecutive halfwords */
-            const uint8_t *src = luma ? &w.y[0][4 + 2 * i] : &w.c[pl][0][4 + 2 * i];
+            const uint8_t *src = luma ? &w.y[0][4 + 2 * i] : &w.c[pl].r[0][4 + 2 * i];
             const int pitch = luma ? K4_LP : K4_CP;
 #pragma unroll
             for (int k = 0; k < 20; k++) v[k] = (k < 12 || luma) ? k4s_unpack_pair(*reinterpret_cast<const uint16_t *>(src + k * pitch)) : 0u;
@@ -204,7 +222,7 @@ __device__ __forceinline__ bool k4_filter(K4Half &w, int x, int hl, int half, bo
 #pragma unroll
         for (int e = 0; e < 4; e++) {
             const unsigned wl = 0x000f000fu << (e * 4), wc = e < 2 ? 0x000f000fu << (e * 8) : 0u;
-            const unsigned wk = weak[dir] & (wl | wc), st = strong[dir] & (wl | wc);
+            const unsigned wk = (dir ? weak[1] : weak[0]) & (wl | wc), st = (dir ? strong[1] : strong[0]) & (wl | wc);
             if (!(wk | st)) continue;                  /* warp-uniform */
             int bsv = luma ? w.bs[dir][e][i >> 1] : w.bs[dir][(2 * e) & 3][i];
             if (!luma && e >= 2) bsv = 0;
@@ -212,12 +230,12 @@ __device__ __forceinline__ bool k4_filter(K4Half &w, int x, int hl, int half, bo
         }
         if (mine) {
             if (dir == 0) {
-                uint32_t *ra = luma ? reinterpret_cast<uint32_t *>(&w.y[4 + 2 * i][0]) : reinterpret_cast<uint32_t *>(&w.c[pl][4 + 2 * i][0]);
+                uint32_t *ra = luma ? reinterpret_cast<uint32_t *>(&w.y[4 + 2 * i][0]) : reinterpret_cast<uint32_t *>(&w.c[pl].r[4 + 2 * i][0]);
                 const int pw = luma ? K4_LP / 4 : K4_CP / 4;
 #pragma unroll
                 for (int k = 0; k < 5; k++) if (k < 3 || luma) k4s_pack_rows(v + 4 * k, &ra[k], &ra[pw + k]);
             } else {
-                uint8_t *dst = luma ? &w.y[0][4 + 2 * i] : &w.c[pl][0][4 + 2 * i];
+                uint8_t *dst = luma ? &w.y[0][4 + 2 * i] : &w.c[pl].r[0][4 + 2 * i];
                 const int pitch = luma ? K4_LP : K4_CP;
 #pragma unroll
                 for (int k = 1; k < 19; k++) if (k < 12 || luma) *reinterpret_cast<uint16_t *>(dst + k * pitch) = (uint16_t)k4s_pack_pair(v[k]);
@@ -241,7 +259,7 @@ __device__ __forceinline__ void k4_writeback(const K4Row &g, const K4Half &w, in
     }
     {
         const int pl = hl >> 3, r = hl & 7;
-        const uint32_t *s = reinterpret_cast<const uint32_t *>(&w.c[pl][4 + r][0]);
+        const uint32_t *s = reinterpret_cast<const uint32_t *>(&w.c[pl].r[4 + r][0]);
         uint8_t *d = g.Crow + (pl ? g.csize : 0) + (size_t)r * g.CW + x * 8;
         if (x > 0) *reinterpret_cast<uint32_t *>(d - 4) = s[0];
         *reinterpret_cast<int2 *>(d) = make_int2((int)s[1], (int)s[2]);
@@ -252,12 +270,12 @@ __device__ __forceinline__ void k4_writeback(const K4Row &g, const K4Half &w, in
             *reinterpret_cast<uint32_t *>(g.Yrow + x * 16 - (ptrdiff_t)(3 - r) * g.W + k * 4) = *reinterpret_cast<const uint32_t *>(&w.y[1 + r][4 + 4 * k]);
         } else {
             const int pl = (hl >> 1) & 1, k = hl & 1;
-            *reinterpret_cast<uint32_t *>(g.Crow + (pl ? g.csize : 0) + x * 8 - (ptrdiff_t)g.CW + k * 4) = *reinterpret_cast<const uint32_t *>(&w.c[pl][3][4 + 4 * k]);
+            *reinterpret_cast<uint32_t *>(g.Crow + (pl ? g.csize : 0) + x * 8 - (ptrdiff_t)g.CW + k * 4) = *reinterpret_cast<const uint32_t *>(&w.c[pl].r[3][4 + 4 * k]);
         }
     }
 }
 
-__global__ void __launch_bounds__(K4_WARPS * 32, 4) k4_deblock(Batch b)
+__device__ __forceinline__ void k4_body(const Batch &b)
 {
     __shared__ K4Pair sm[K4_WARPS];
     const int lane = threadIdx.x & 31, hl = lane & 15, half = lane >> 4;
@@ -267,7 +285,7 @@ __global__ void __launch_bounds__(K4_WARPS * 32, 4) k4_deblock(Batch b)
     /* ring source of this lane: word `lane` of the strip = upper window rows 16..19 (5 words each), chroma rows 10..11 (3 words each) */
     const uint32_t *ring_src;
     if (lane < 20) ring_src = reinterpret_cast<const uint32_t *>(&pw.h[0].y[16 + lane / 5][0]) + lane % 5;
-    else { const int j = lane - 20, plr = j / 3; ring_src = reinterpret_cast<const uint32_t *>(&pw.h[0].c[plr >> 1][10 + (plr & 1)][0]) + j % 3; }
+    else { const int j = lane - 20, plr = j / 3; ring_src = reinterpret_cast<const uint32_t *>(&pw.h[0].c[plr >> 1].r[10 + (plr & 1)][0]) + j % 3; }
 
     for (;;) {
         uint32_t t = 0;
@@ -325,12 +343,11 @@ __global__ void __launch_bounds__(K4_WARPS * 32, 4) k4_deblock(Batch b)
 
             const bool act = have && w.rec[x & 1].dbk_flags && w.rec[x & 1].mb_class != H264B200_MB_MISSING;
             const bool f = k4_filter(w, x, hl, half, act);
+            /* lower row: publish what the PREVIOUS steps completed (i - 2 macroblocks), once per K4_PUBLISH macroblocks and
+             * before this step's write-back: the stores the release has to cover were issued a whole filter ago, so
+             * its memory barrier returns at once instead of stalling the warp on stores still in flight */
+            if (lower && i > 2 && ((i - 2) % K4_PUBLISH) == 0 && lane == 16) st_release(prog + row0 + 1, i - 2);
             if (f) k4_writeback(g, w, x, hl);
-            /* lower row: the release (a memory barrier over the write-back) is paid once per K4_PUBLISH macroblocks */
-            if (lower && i >= 2 && (((i - 1) % K4_PUBLISH) == 0 || i - 1 == wm)) {
-                __syncwarp();
-                if (lane == 16) st_release(prog + row0 + 1, i - 1);
-            }
             __syncwarp();
             /* upper row -> ring: the strip of this step (left halo final, macroblock columns 0..12 final) */
             if (lower && i <= wm) pw.ring[i & 1][lane] = *ring_src;
@@ -338,12 +355,12 @@ __global__ void __launch_bounds__(K4_WARPS * 32, 4) k4_deblock(Batch b)
             uint32_t cy = 0, cc = 0;
             if (have) {
                 cy = *reinterpret_cast<const uint32_t *>(&w.y[4 + hl][16]);
-                cc = *reinterpret_cast<const uint32_t *>(&w.c[hl >> 3][4 + (hl & 7)][8]);
+                cc = *reinterpret_cast<const uint32_t *>(&w.c[hl >> 3].r[4 + (hl & 7)][8]);
             }
             __syncwarp();
             if (have) {
                 *reinterpret_cast<uint32_t *>(&w.y[4 + hl][0]) = cy;
-                *reinterpret_cast<uint32_t *>(&w.c[hl >> 3][4 + (hl & 7)][0]) = cc;
+                *reinterpret_cast<uint32_t *>(&w.c[hl >> 3].r[4 + (hl & 7)][0]) = cc;
             }
             if (poll) seen = max(seen, __shfl_sync(0xffffffffu, polled, 0));
             /* land the prefetched macroblock */
@@ -357,6 +374,13 @@ __global__ void __launch_bounds__(K4_WARPS * 32, 4) k4_deblock(Batch b)
             }
             __syncwarp();
         }
+        if (lower && lane == 16) st_release(prog + row0 + 1, wm);      /* the loop ended on a __syncwarp: every lane's stores are ordered before */
         if (tr) b.trace[256 + g.row * 4 + 3] = gtime();
     }
 }
+
+/* Occupancy: 4 CTAs (16 warps) per SM at 127 registers.  Capping registers for 5 or 6 CTAs per SM (96 / 80
+ * registers, a few spills) measured SLOWER on B200 (2.67 / 2.86 / 3.18 ms per 256 pictures): the walk is one long
+ * dependent chain per warp, and more co-resident warps at different points of a 33 KB instruction stream cost more
+ * in instruction fetch than they hide in latency. */
+__global__ void __launch_bounds__(K4_WARPS * 32, 4) k4_deblock(Batch b) { k4_body(b); }
