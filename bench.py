@@ -236,7 +236,7 @@ def own_arm(args, rank, local_rank, world):
 
     # ---- end-to-end leg: host Annex-B -> host I420 frames through the C ABI
     eng = capi.Engine(local_rank, capi.ENGINE_BATCHED)
-    for _ in range(args.warmup):
+    for _ in range(0 if args.skip_e2e else args.warmup):
         eng.decode_streams(streams, threads)
     barrier()
     s0 = eng.stats()
@@ -245,7 +245,7 @@ def own_arm(args, rank, local_rank, world):
         sampler.start()
     t0 = time.perf_counter()
     parse_s = wait_s = 0.0
-    for _ in range(args.steps):
+    for _ in range(0 if args.skip_e2e else args.steps):
         rs = eng.decode_streams(streams, threads)
         assert rs.pictures == frames_per_step and rs.err_mbs == 0, (rs.pictures, rs.err_mbs)
         parse_s += rs.parse_seconds
@@ -361,6 +361,7 @@ def main():
     ap.add_argument("--workload", default="1080p_ippp", choices=sorted(WORKLOADS), help="default: the configuration BASELINE.json's metric is quoted on")
     ap.add_argument("--no-check", action="store_true")
     ap.add_argument("--e2e-only", action="store_true", help="host-to-host leg only (experiments)")
+    ap.add_argument("--skip-e2e", action="store_true", help="kernel-tuning aid: skip the host-to-host leg (the line then carries no valid e2e and is not a bench result)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     _WL["name"] = args.workload
