@@ -4,12 +4,18 @@
  *
  * The reference's closest relative is TestBenchMultipleInstance.c:60-350, which
  * steps N decoder instances round-robin in one thread.  Here the same
- * round-robin is the unit of GPU batching: in every ROUND each live stream's
- * serial CAVLC parse produces one picture (worker threads, one stream at a time
- * each), the last thread to finish the round launches all of those pictures as
- * one batch, and the workers go straight on to parse the next round while the
- * GPU reconstructs — output of round r is waited for only after round r+1 has
- * been parsed (h264b200NextOutputPictureAsync / h264b200PictureWait).
+ * round-robin is the unit of GPU batching, without ever idling a parser thread:
+ * work items (round r, stream s) are claimed from one atomic counter, a
+ * picture's serial CAVLC parse runs on whichever thread claimed it, and the
+ * streams are split into two groups that are launched separately — the last
+ * thread to finish a group's pictures of a round launches them as one batch
+ * while everybody else is already parsing the other group.  The only thing a
+ * claim ever waits for is that the same stream's previous picture has been
+ * launched (consecutive pictures of a stream depend on each other), which in
+ * steady state happened half a round earlier.  Output of round r is collected
+ * right after the stream's round r+1 picture has been parsed
+ * (h264b200NextOutputPictureAsync / h264b200PictureWait): the GPU had a whole
+ * round to finish it.
  * Streams are independent (no mutable globals in the decoder core), and an IDR
  * picture empties the DPB (h264bsd_dpb.c:675-708), which is what makes
  * h264b200SplitGops' segments decodable on their own — on another instance,
@@ -36,7 +42,6 @@ typedef struct {
     uint8_t *buf; const uint8_t *src; size_t len, pos;
     u32 pic_id, out_index;
     int inited, finished, failed, flushed;
-    uint32_t stepped;                 /* rounds this stream has been advanced through (hand-over between the parse and the output phase) */
     pending_t cur[MAX_PENDING], prev[MAX_PENDING];
     int n_cur, n_prev;
     u32 width, height;
@@ -50,37 +55,19 @@ typedef struct {
     double parse_s, wait_s;
 } worker_t;
 
+#define MAX_GROUPS 2
 struct runner {
     h264b200_engine_t *e;
     rstream_t *s; uint32_t n_streams, n_threads;
     h264b200_picture_cb cb; void *user;
-    pthread_mutex_t mu; pthread_cond_t cv;
-    uint32_t arrived, generation; uint64_t round_sum, last_sum;
-    uint32_t rounds;
-    uint32_t next_parse, next_out;    /* per-round work counters: streams are claimed one at a time, so a slow stream never idles a thread */
+    pthread_mutex_t mu;
+    uint64_t next_item;                       /* next (round, stream) work item: round = item / n_streams */
+    uint32_t n_groups, gstart[MAX_GROUPS + 1];/* group g = streams [gstart[g], gstart[g+1]) */
+    uint32_t arrived[MAX_GROUPS], produced[MAX_GROUPS], dead[MAX_GROUPS];   /* under mu: the group's current round */
+    uint32_t launched[MAX_GROUPS];            /* rounds of the group that have been handed to the GPU (release / acquire) */
+    int stop;                                 /* every group went through a round without producing a picture */
+    uint32_t rounds;                          /* batches launched */
 };
-
-/* Barrier; the last arriver launches the batch (every picture of the round is queued by then, and no
- * thread is past the barrier, so a batch is always exactly one round).  Returns the number of pictures
- * all threads produced in this round. */
-static uint64_t round_barrier(runner_t *r, uint64_t produced)
-{
-    uint64_t sum;
-    pthread_mutex_lock(&r->mu);
-    r->round_sum += produced;
-    if (++r->arrived == r->n_threads) {
-        h264b200EngineSubmit(r->e);
-        __atomic_store_n(&r->next_parse, 0, __ATOMIC_RELAXED); __atomic_store_n(&r->next_out, 0, __ATOMIC_RELAXED);
-        r->last_sum = r->round_sum; r->round_sum = 0; r->arrived = 0; r->generation++; r->rounds++;
-        pthread_cond_broadcast(&r->cv);
-    } else {
-        uint32_t g = r->generation;
-        while (g == r->generation) pthread_cond_wait(&r->cv, &r->mu);
-    }
-    sum = r->last_sum;
-    pthread_mutex_unlock(&r->mu);
-    return sum;
-}
 
 static void pop_outputs(rstream_t *s)
 {
@@ -126,36 +113,52 @@ static void consume_prev(worker_t *w, rstream_t *s, uint32_t stream_index)
     s->n_prev = 0;
 }
 
+/* one more picture of group g's round is parsed; the last one launches the group (and whatever of the other
+ * group is already queued) */
+static void group_arrive(runner_t *r, uint32_t g, uint32_t round, uint32_t produced)
+{
+    uint32_t k, all_dead = 1;
+    pthread_mutex_lock(&r->mu);
+    r->produced[g] += produced;
+    if (++r->arrived[g] == r->gstart[g + 1] - r->gstart[g]) {
+        h264b200EngineSubmit(r->e);
+        r->rounds++;
+        if (!r->produced[g]) r->dead[g] = 1;
+        r->produced[g] = 0; r->arrived[g] = 0;
+        for (k = 0; k < r->n_groups; k++) all_dead &= r->dead[k];
+        if (all_dead) __atomic_store_n(&r->stop, 1, __ATOMIC_RELEASE);
+        __atomic_store_n(&r->launched[g], round + 1, __ATOMIC_RELEASE);
+    }
+    pthread_mutex_unlock(&r->mu);
+}
+
 static void *worker_main(void *arg)
 {
     worker_t *w = (worker_t *)arg; runner_t *r = w->r;
-    uint32_t i, round;
-    for (round = 1;; round++) {
-        uint64_t produced = 0;
-        /* parse phase: every thread claims the next unparsed stream of the round */
-        while ((i = __atomic_fetch_add(&r->next_parse, 1, __ATOMIC_RELAXED)) < r->n_streams) {
-            rstream_t *s = &r->s[i];
-            /* private copy (the decoder strips emulation prevention bytes in place), made by the first thread to touch the stream */
-            if (round == 1 && s->buf && s->inited) { memcpy(s->buf, s->src, s->len); memset(s->buf + s->len, 0, 16); }
-            if (!s->finished && !s->failed) {
-                double t0 = now_s();
-                produced += (uint64_t)step_stream(s);
-                w->parse_s += now_s() - t0;
-            }
-            __atomic_store_n(&s->stepped, round, __ATOMIC_RELEASE);
+    while (!__atomic_load_n(&r->stop, __ATOMIC_ACQUIRE)) {
+        const uint64_t item = __atomic_fetch_add(&r->next_item, 1, __ATOMIC_RELAXED);
+        const uint32_t round = (uint32_t)(item / r->n_streams), idx = (uint32_t)(item % r->n_streams);
+        const uint32_t g = (r->n_groups > 1 && idx >= r->gstart[1]) ? 1 : 0;
+        rstream_t *s = &r->s[idx];
+        uint32_t produced = 0;
+        /* the stream's previous picture must have been launched (this also hands the decoder state, which is
+         * single-threaded, from the thread that parsed that picture to this one) */
+        while (__atomic_load_n(&r->launched[g], __ATOMIC_ACQUIRE) < round) {
+            if (__atomic_load_n(&r->stop, __ATOMIC_ACQUIRE)) return NULL;
+            sched_yield();
         }
-        /* output phase: pictures popped in the PREVIOUS round were launched one barrier ago, so the GPU had
-         * this whole parse phase to finish them.  Streams are taken in the order they were parsed; the few
-         * still being parsed by another thread are waited for (the decoder state is single-threaded). */
-        while ((i = __atomic_fetch_add(&r->next_out, 1, __ATOMIC_RELAXED)) < r->n_streams) {
-            rstream_t *s = &r->s[i];
-            while (__atomic_load_n(&s->stepped, __ATOMIC_ACQUIRE) != round) sched_yield();
-            consume_prev(w, s, i);
-            memcpy(s->prev, s->cur, (size_t)s->n_cur * sizeof(pending_t)); s->n_prev = s->n_cur; s->n_cur = 0;
+        /* private copy (the decoder strips emulation prevention bytes in place), made by the first thread to touch the stream */
+        if (round == 0 && s->buf && s->inited) { memcpy(s->buf, s->src, s->len); memset(s->buf + s->len, 0, 16); }
+        if (!s->finished && !s->failed) {
+            double t0 = now_s();
+            produced = (uint32_t)step_stream(s);
+            w->parse_s += now_s() - t0;
         }
-        if (round_barrier(r, produced) == 0) break;
+        /* what the previous round popped was launched a whole round ago */
+        consume_prev(w, s, idx);
+        memcpy(s->prev, s->cur, (size_t)s->n_cur * sizeof(pending_t)); s->n_prev = s->n_cur; s->n_cur = 0;
+        group_arrive(r, g, round, produced);
     }
-    for (i = w->tid; i < r->n_streams; i += r->n_threads) consume_prev(w, &r->s[i], i);   /* what the last round popped */
     return NULL;
 }
 
@@ -171,7 +174,10 @@ int h264b200DecodeStreams(h264b200_engine_t *e, const h264b200_stream_t *streams
     r.s = (rstream_t *)calloc(n_streams, sizeof(rstream_t));
     w = (worker_t *)calloc(n_threads, sizeof(worker_t));
     if (!r.s || !w) { free(r.s); free(w); return -1; }
-    pthread_mutex_init(&r.mu, NULL); pthread_cond_init(&r.cv, NULL);
+    pthread_mutex_init(&r.mu, NULL);
+    /* two groups once every thread has a few streams per group; otherwise one (a round is then one batch) */
+    r.n_groups = n_streams >= 4 * n_threads ? 2 : 1;
+    r.gstart[0] = 0; r.gstart[1] = r.n_groups > 1 ? n_streams / 2 : n_streams; r.gstart[2] = n_streams;
     for (i = 0; i < n_streams; i++) {
         rstream_t *s = &r.s[i];
         s->len = streams[i].len;
@@ -184,6 +190,7 @@ int h264b200DecodeStreams(h264b200_engine_t *e, const h264b200_stream_t *streams
     for (i = 1; i < n_threads; i++) pthread_create(&w[i].th, NULL, worker_main, &w[i]);
     worker_main(&w[0]);
     for (i = 1; i < n_threads; i++) pthread_join(w[i].th, NULL);
+    for (i = 0; i < n_streams; i++) consume_prev(&w[0], &r.s[i], i);           /* what the last round popped */
     h264b200EngineSync(e);
     if (out) {
         memset(out, 0, sizeof *out);
@@ -199,7 +206,7 @@ int h264b200DecodeStreams(h264b200_engine_t *e, const h264b200_stream_t *streams
         if (r.s[i].inited) h264bsdShutdown(&r.s[i].st);
         free(r.s[i].buf);
     }
-    pthread_mutex_destroy(&r.mu); pthread_cond_destroy(&r.cv);
+    pthread_mutex_destroy(&r.mu);
     free(r.s); free(w);
     if (out) out->seconds = now_s() - t0;
     return rc;

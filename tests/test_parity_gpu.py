@@ -52,7 +52,8 @@ def test_batched_streams_match_golden(golden):
             assert m == golden[c[0]]["frame_md5"], c[0]
         st = eng.stats()
         assert st["pictures"] == sum(c[3] for c in cases.SMALL)
-        assert st["batches"] <= max(c[3] for c in cases.SMALL) + 2
+        # the runner launches the streams as two groups per round: at most two batches per picture index
+        assert st["batches"] <= 2 * (max(c[3] for c in cases.SMALL) + 2)
         assert eng.error_flags() == 0
 
 
