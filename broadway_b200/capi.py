@@ -11,7 +11,7 @@ import hashlib
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libh264b200.so")
+LIB_PATH = os.environ.get("H264B200_LIB") or os.path.join(_HERE, "libh264b200.so")   # the override is for A/B builds of the host parser
 
 H264BSD_RDY, H264BSD_PIC_RDY, H264BSD_HDRS_RDY, H264BSD_ERROR, H264BSD_PARAM_SET_ERROR, H264BSD_MEMALLOC_ERROR = range(6)
 H264SWDEC_OK, H264SWDEC_STRM_PROCESSED, H264SWDEC_PIC_RDY, H264SWDEC_PIC_RDY_BUFF_NOT_EMPTY, H264SWDEC_HDRS_RDY_BUFF_NOT_EMPTY = range(5)

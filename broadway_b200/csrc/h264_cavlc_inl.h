@@ -16,7 +16,7 @@ extern int8_t  g_lvl[7][256][4];      /* {level, bits, next suffixLength, -} */
 /* Decode one residual block into out[scan[i]].  `out` (16 x int16) is zeroed here when the block
  * has coefficients and left untouched when TotalCoeff is 0.  nc < 0: chroma DC.
  * Returns TotalCoeff, or -1 on a malformed block. */
-static inline int h264_cavlc_block(br_t *b, int nc, int max_coeff, int16_t *out, const uint8_t *scan)
+static __attribute__((noinline)) int h264_cavlc_block_full(br_t *b, int nc, int max_coeff, int16_t *out, const uint8_t *scan)
 {
     int tc, t1, i, sl, zeros_left, pos;
     int level[16];
@@ -117,5 +117,15 @@ static inline int h264_cavlc_block(br_t *b, int nc, int max_coeff, int16_t *out,
     }
     for (; i < tc; i++) out[scan[pos--]] = (int16_t)level[i];       /* no zeros left: contiguous */
     return tc;
+}
+/* Two blocks out of three are empty in typical streams, and with sparse neighbours (nC < 2) that is the single
+ * bit '1': answered at the call site, without the call into the full decoder. */
+static inline int h264_cavlc_block(br_t *b, int nc, int max_coeff, int16_t *out, const uint8_t *scan)
+{
+    if ((unsigned)nc < 2u) {
+        if (b->bits < 1) br_refill(b);
+        if (b->cache >> 63) { br_skip(b, 1); return 0; }
+    }
+    return h264_cavlc_block_full(b, nc, max_coeff, out, scan);
 }
 #endif
