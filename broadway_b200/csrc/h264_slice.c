@@ -99,31 +99,20 @@ static void predict_mv(const sl_t *s, int x4, int y4, int w4, int ref, unsigned 
     } else { *px = a.x; *py = a.y; }
 }
 static inline int mv_in_range(int x, int y) { return x >= -8192 && x <= 8191 && y >= -2048 && y <= 2047; }
+/* the vector of a w4 x h4 partition goes to every 4x4 block it covers (raster order): whole 32-bit {hor, ver} pairs,
+ * two at a time where the partition is at least 8 samples wide */
 static inline void fill_mv(h264b200_mb_t *r, int x4, int y4, int w4, int h4, int mx, int my, unsigned *done)
 {
-    int i, j;
-    for (j = y4; j < y4 + h4; j++) for (i = x4; i < x4 + w4; i++) {
-        r->mv[j * 4 + i][0] = (int16_t)mx; r->mv[j * 4 + i][1] = (int16_t)my; *done |= 1u << (j * 4 + i);
+    const uint32_t v = (uint32_t)(uint16_t)mx | ((uint32_t)(uint16_t)my << 16);
+    const uint64_t vv = (uint64_t)v | ((uint64_t)v << 32);
+    int j;
+    for (j = y4; j < y4 + h4; j++) {
+        int16_t *row = r->mv[j * 4 + x4];
+        if (w4 == 4) { memcpy(row, &vv, 8); memcpy(row + 4, &vv, 8); }
+        else if (w4 == 2) memcpy(row, &vv, 8);
+        else memcpy(row, &v, 4);
+        *done |= ((1u << w4) - 1u) << (j * 4 + x4);
     }
-}
-static void finish_inter(sl_t *s)
-{
-    h264b200_mb_t *r = s->rec;
-    int q, flags = 0;
-    static const uint8_t qbase[4] = {0, 2, 8, 10};
-    for (q = 0; q < 4; q++) {
-        const int16_t (*m)[2] = r->mv + qbase[q];
-        int32_t v0, v1, v4, v5;
-        memcpy(&v0, m[0], 4); memcpy(&v1, m[1], 4); memcpy(&v4, m[4], 4); memcpy(&v5, m[5], 4);
-        if (v0 == v1 && v0 == v4 && v0 == v5) flags |= 1 << q;
-    }
-    if (flags == 15) {
-        int32_t v0, v2, v8, v10;
-        memcpy(&v0, r->mv[0], 4); memcpy(&v2, r->mv[2], 4); memcpy(&v8, r->mv[8], 4); memcpy(&v10, r->mv[10], 4);
-        if (v0 == v2 && v0 == v8 && v0 == v10 && r->ref_slot[0] == r->ref_slot[1] && r->ref_slot[0] == r->ref_slot[2] && r->ref_slot[0] == r->ref_slot[3])
-            flags |= 16;
-    }
-    r->part_flags = (uint8_t)flags;
 }
 
 /* --------------------------------------------------------------- residual */
@@ -360,6 +349,7 @@ static int parse_inter_mb(sl_t *s, uint32_t mb_type /* 0..4 */)
         mx = (int16_t)((unsigned)px + (unsigned)dx); my = (int16_t)((unsigned)py + (unsigned)dy);
         if (!mv_in_range(mx, my)) return -1;
         fill_mv(r, 0, 0, 4, 4, mx, my, &done);
+        r->part_flags = 31;
     } else if (mb_type == 1 || mb_type == 2) {
         int ref[2], dx[2], dy[2];
         for (i = 0; i < 2; i++) { ref[i] = read_ref_idx(s, n_active); if (ref[i] < 0) return -1; }
@@ -374,9 +364,10 @@ static int parse_inter_mb(sl_t *s, uint32_t mb_type /* 0..4 */)
             if (mb_type == 1) fill_mv(r, 0, 2 * i, 4, 2, mx, my, &done);
             else              fill_mv(r, 2 * i, 0, 2, 4, mx, my, &done);
         }
+        r->part_flags = 15;
     } else {
         int sub[4], ref[4], q, k, mvd[16][2], n = 0, m = 0;
-        for (q = 0; q < 4; q++) { v = br_ue(b); if (v > 3) return -1; sub[q] = (int)v; }
+        for (q = 0; q < 4; q++) { v = br_ue(b); if (v > 3) return -1; sub[q] = (int)v; if (!v) r->part_flags |= (uint8_t)(1 << q); }
         for (q = 0; q < 4; q++) {
             ref[q] = mb_type == 4 ? 0 : read_ref_idx(s, n_active);
             if (ref[q] < 0 || set_ref(s, q, ref[q])) return -1;
@@ -399,7 +390,6 @@ static int parse_inter_mb(sl_t *s, uint32_t mb_type /* 0..4 */)
             }
         }
     }
-    finish_inter(s);
     v = br_ue(b); if (v > 47) return -1;
     cbp = H264_CBP_MAP[v][1];
     if (cbp) {
@@ -433,7 +423,7 @@ static int do_skip_mb(sl_t *s)
 int h264_decode_slice_data(h264_decoder_t *d, br_t *b, const h264_slice_hdr_t *sh)
 {
     sl_t s;
-    uint32_t skip_run = 0, mb_count = 0, addr = sh->first_mb, i;
+    uint32_t skip_run = 0, mb_count = 0, addr = sh->first_mb, next_linear = 0xffffffffu, i;
     int prev_skipped = 0, more;
     memset(&s, 0, sizeof s);
     s.d = d; s.b = b; s.sh = sh; s.pic = d->pic; s.W = d->width_mbs; s.H = d->height_mbs;
@@ -454,7 +444,10 @@ int h264_decode_slice_data(h264_decoder_t *d, br_t *b, const h264_slice_hdr_t *s
         /* growing moves the picture's records AND slots (one block): take pointers only afterwards */
         if (s.pic->coef_used + 32 > s.pic->coef_cap && d->be->coef_grow(d->be, d->be_inst, s.pic, s.pic->coef_used + 4096)) return -1;
         r = &s.pic->mbs[addr];
-        s.addr = addr; s.mbx = (int)(addr % s.W); s.mby = (int)(addr / s.W);
+        s.addr = addr;
+        if (addr != next_linear) { s.mbx = (int)(addr % s.W); s.mby = (int)(addr / s.W); }    /* first macroblock, or a jump in the slice group map */
+        else if (++s.mbx == (int)s.W) { s.mbx = 0; s.mby++; }
+        next_linear = addr + 1;
         s.cur = c; s.rec = r;
         memset(r, 0, 64);                       /* mv[] is always written for inter MBs and never read for intra */
         memset(c, 0, sizeof *c);

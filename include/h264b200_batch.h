@@ -72,9 +72,11 @@ typedef struct {
     double   wait_seconds;       /* summed over threads: time blocked on the GPU */
 } h264b200_run_stats_t;
 /* Decode n_streams independent streams (or GOP segments) with n_threads parser
- * threads (0: one per online CPU): every round parses one picture of every live
- * stream, launches them as one batch, and overlaps the next round's parse with
- * the GPU.  Returns 0 on success. */
+ * threads (0: one per online CPU).  Every round parses one picture of every live
+ * stream; the pictures of a round are launched as one batch (two, one per half of
+ * the streams, when there are at least four streams per thread, so that no
+ * thread ever waits for a round to end) while the next pictures are being parsed.
+ * `rounds` in the statistics counts the batches.  Returns 0 on success. */
 int h264b200DecodeStreams(h264b200_engine_t *e, const h264b200_stream_t *streams, uint32_t n_streams,
                           uint32_t n_threads, h264b200_picture_cb cb, void *user, h264b200_run_stats_t *out);
 

@@ -77,8 +77,8 @@ typedef struct {
     uint8_t  avail;           /* H264B200_AVAIL_* */
     uint8_t  i16_mode;        /* Intra16x16PredMode 0..3 */
     uint8_t  chroma_mode;     /* intra_chroma_pred_mode 0..3 */
-    uint8_t  part_flags;      /* bit q (0..3): 8x8 quadrant q has one vector; bit 4: whole MB one vector+ref (informational: the
-                                 kernels take the per-4x4 vectors) */
+    uint8_t  part_flags;      /* by partition syntax: bit q (0..3): 8x8 quadrant q is one partition; bit 4: the macroblock is one
+                                 16x16 partition (informational: the kernels take the per-4x4 vectors) */
     uint32_t coef_offset;     /* first slot of this macroblock in the picture's slot array */
     uint32_t resid_mask;      /* see above */
     uint16_t nz_mask;         /* bit b: luma4x4BlkIdx b has TotalCoeff != 0 (bS=2 test; I_PCM: 0xffff) */
