@@ -40,6 +40,10 @@ WORKLOADS = {
     "1080p_ippp": (120, 68, {}, "synthetic 1080p Baseline IPPP, random MVs incl. quarter-pel, ~30% coded blocks, deblocking on (BASELINE.json configs[2]; configs[1] tree.mp4 absent)"),
     "1080p_intra": (120, 68, {"intra_only": 1}, "synthetic 1080p intra-only (I16x16/I4x4 mix) stressing the intra and deblock wavefronts (BASELINE.json configs[3])"),
     "4k_ippp": (240, 135, {"level_idc": 51}, "synthetic 4K (3840x2160) Baseline IPPP multi-stream (BASELINE.json configs[4])"),
+    # not BASELINE.json configurations: the same 1080p IPPP structure at streaming bitrates, to show how the host-parse
+    # bound of e2e moves with the bitrate; ~54 Mbit/s at 30 frames/s for the default workload
+    "1080p_ippp_17mbps": (120, 68, {"coded_blk_permille": 40, "p_skip_permille": 400}, "synthetic 1080p Baseline IPPP at ~17 Mbit/s (4% coded blocks, 40% P_Skip); illustration, not a BASELINE.json config"),
+    "1080p_ippp_6mbps": (120, 68, {"coded_blk_permille": 20, "p_skip_permille": 600, "part_mix": 0}, "synthetic 1080p Baseline IPPP at ~6 Mbit/s (2% coded blocks, 60% P_Skip, 16x16 partitions); illustration, not a BASELINE.json config"),
 }
 _WL = {"name": "1080p_ippp"}
 DEFAULT_STREAMS, DEFAULT_FRAMES, DISTINCT = 256, 16, 16

@@ -632,6 +632,7 @@ extern "C" void h264b200EngineSync(h264b200_engine_t *e)
 extern "C" void h264b200EngineStats(h264b200_engine_t *e, h264b200_stats_t *out) { if (e && out) { std::lock_guard<std::mutex> lk(e->mu); *out = e->st; } }
 extern "C" u32 h264b200EngineErrorFlags(h264b200_engine_t *e) { return e ? *e->h_err : 0; }
 extern "C" void h264b200EngineSetFlags(h264b200_engine_t *e, uint32_t flags) { if (e) { std::lock_guard<std::mutex> lk(e->mu); e->flags = flags; } }
+extern "C" uint32_t h264b200EngineFlags(h264b200_engine_t *e) { if (!e) return 0; std::lock_guard<std::mutex> lk(e->mu); return e->flags; }
 
 /* -------------------------------------------------------- resident replay */
 extern "C" void h264b200EngineDropRetained(h264b200_engine_t *e)

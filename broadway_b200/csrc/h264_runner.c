@@ -175,8 +175,9 @@ int h264b200DecodeStreams(h264b200_engine_t *e, const h264b200_stream_t *streams
     w = (worker_t *)calloc(n_threads, sizeof(worker_t));
     if (!r.s || !w) { free(r.s); free(w); return -1; }
     pthread_mutex_init(&r.mu, NULL);
-    /* two groups once every thread has a few streams per group; otherwise one (a round is then one batch) */
-    r.n_groups = n_streams >= 4 * n_threads ? 2 : 1;
+    /* two groups once every thread has a few streams per group; otherwise one (a round is then one batch).  Batches
+     * retained for h264b200EngineReplay are always whole rounds. */
+    r.n_groups = (n_streams >= 4 * n_threads && !(h264b200EngineFlags(e) & H264B200_ENGINE_RETAIN)) ? 2 : 1;
     r.gstart[0] = 0; r.gstart[1] = r.n_groups > 1 ? n_streams / 2 : n_streams; r.gstart[2] = n_streams;
     for (i = 0; i < n_streams; i++) {
         rstream_t *s = &r.s[i];

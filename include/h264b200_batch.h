@@ -22,6 +22,7 @@ extern "C" {
 
 h264b200_engine_t *h264b200EngineCreateEx(int device, uint32_t flags);
 void h264b200EngineSetFlags(h264b200_engine_t *e, uint32_t flags);
+uint32_t h264b200EngineFlags(h264b200_engine_t *e);
 
 /* Non-blocking variant of h264bsdNextOutputPicture (h264bsd_decoder.c:642): pops
  * the display queue and returns the host address the picture WILL occupy; the
@@ -75,7 +76,8 @@ typedef struct {
  * threads (0: one per online CPU).  Every round parses one picture of every live
  * stream; the pictures of a round are launched as one batch (two, one per half of
  * the streams, when there are at least four streams per thread, so that no
- * thread ever waits for a round to end) while the next pictures are being parsed.
+ * thread ever waits for a round to end; always one while H264B200_ENGINE_RETAIN is
+ * set, so that a retained batch is a whole round) while the next pictures are being parsed.
  * `rounds` in the statistics counts the batches.  Returns 0 on success. */
 int h264b200DecodeStreams(h264b200_engine_t *e, const h264b200_stream_t *streams, uint32_t n_streams,
                           uint32_t n_threads, h264b200_picture_cb cb, void *user, h264b200_run_stats_t *out);
