@@ -379,8 +379,9 @@ __device__ __forceinline__ void k4_body(const Batch &b)
     }
 }
 
-/* Occupancy: 4 CTAs (16 warps) per SM at 127 registers.  Capping registers for 5 or 6 CTAs per SM (96 / 80
- * registers, a few spills) measured SLOWER on B200 (2.67 / 2.86 / 3.18 ms per 256 pictures): the walk is one long
- * dependent chain per warp, and more co-resident warps at different points of a 33 KB instruction stream cost more
- * in instruction fetch than they hide in latency. */
+/* Occupancy: 4 CTAs (16 warps) per SM at 127 registers, the whole register file.  Measured on B200 per 256 pictures:
+ * 2 / 3 / 4 CTAs per SM at 127 registers (limited with dynamic shared memory) 3.81 / 3.24 / 2.68 ms — more warps
+ * help — but capping registers for 5 / 6 CTAs (96 / 80 registers) gives 2.86 / 3.18 ms: what the compiler gives up
+ * below 127 registers costs more than the extra warps hide.  Getting the prefetch registers (K4Pre) out of the way
+ * with cp.async into a double-buffered window is the next step for this kernel. */
 __global__ void __launch_bounds__(K4_WARPS * 32, 4) k4_deblock(Batch b) { k4_body(b); }
