@@ -381,7 +381,7 @@ __device__ __forceinline__ void k4_body(const Batch &b)
 
 /* Occupancy: 4 CTAs (16 warps) per SM at 127 registers, the whole register file.  Measured on B200 per 256 pictures:
  * 2 / 3 / 4 CTAs per SM at 127 registers (limited with dynamic shared memory) 3.81 / 3.24 / 2.68 ms — more warps
- * help — but capping registers for 5 / 6 CTAs (96 / 80 registers) gives 2.86 / 3.18 ms: what the compiler gives up
- * below 127 registers costs more than the extra warps hide.  Getting the prefetch registers (K4Pre) out of the way
- * with cp.async into a double-buffered window is the next step for this kernel. */
+ * help — but capping registers for 5 / 6 CTAs (96 / 80 registers) gives 2.86 / 3.18 ms: the 96-register code is 14 % slower
+ * at equal occupancy (3.04 ms at 4 CTAs, no spills: less room for ptxas to overlap the dependent chains), which the
+ * fifth CTA (+5 %) does not win back. */
 __global__ void __launch_bounds__(K4_WARPS * 32, 4) k4_deblock(Batch b) { k4_body(b); }
