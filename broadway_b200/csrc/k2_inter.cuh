@@ -105,7 +105,7 @@ __device__ __forceinline__ void k2_block(const Batch &b, uint32_t g0, int blk, i
         const int n_ops = (int)useJ + (int)useB + (int)useH + (int)useG;      /* 1 or 2 */
         const bool anyJ = __any_sync(FULL, useJ), anyB = __any_sync(FULL, useB), anyH = __any_sync(FULL, useH);
         const int dn = fy == 3, rt = fx == 3;
-        const bool outer = anyH || anyJ;           /* window rows 0, 1, 7, 8 are only inputs of the vertical filters */
+        const bool outer = !STAGED || anyH || anyJ;   /* window rows 0, 1, 7, 8 are only inputs of the vertical filters (skipping them did not pay in the unsorted kernel) */
 
         /* ---- window rows as three byte-aligned words: bytes 0..8 of the row ---- */
         uint32_t r0[9], r1[9], r2[9];
