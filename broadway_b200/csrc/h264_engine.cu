@@ -175,12 +175,7 @@ static void launch_kernels(h264b200_engine *e, const Batch &b, const BatchPlan &
     if (tev) cudaEventRecord(tev[0], s);
     if (pl.k1) { uint32_t blocks = (pl.total_mbs * 8 + 255) / 256; k1_transform<<<blocks, 256, 0, s>>>(b); e->st.kernel_launches++; }   /* 8 lanes per macroblock */
     if (tev) cudaEventRecord(tev[1], s);
-    if (pl.k2) {                   /* 16 threads per macroblock */
-        static const int k2_sorted = getenv("H264B200_K2") && !strcmp(getenv("H264B200_K2"), "sorted");     /* A/B: see k2_inter_sorted */
-        if (k2_sorted) k2_inter_sorted<<<(pl.total_mbs * 16 + K2S_THREADS - 1) / K2S_THREADS, K2S_THREADS, 0, s>>>(b);
-        else k2_inter<<<(pl.total_mbs * 16 + K2_THREADS - 1) / K2_THREADS, K2_THREADS, 0, s>>>(b);
-        e->st.kernel_launches++;
-    }
+    if (pl.k2) { k2_inter<<<(pl.total_mbs * 16 + K2_THREADS - 1) / K2_THREADS, K2_THREADS, 0, s>>>(b); e->st.kernel_launches++; }   /* 16 threads per macroblock */
     if (tev) cudaEventRecord(tev[2], s);
     uint32_t n_tasks = (uint32_t)pl.n_jobs * (uint32_t)pl.max_hm;
     if (pl.k3) {

@@ -56,14 +56,24 @@ __device__ __forceinline__ uint32_t ref_px(const uint8_t *pl, int w, int h, int 
     return __ldg(pl + (size_t)y * w + x);
 }
 
-/* The work of one thread: the 4x4 luma block `blk` (raster) of batch-wide macroblock g0 and the two 2x2 chroma
- * blocks under it.  STAGED == false: results go straight to the frame.  STAGED == true (k2_inter, below): they go
- * to the CTA's staging arrays sy / sc at index `slot`, to be stored by the thread that owns the block's position. */
-template <bool STAGED>
-__device__ __forceinline__ void k2_block(const Batch &b, uint32_t g0, int blk, int4 *sy, uint2 *sc, int slot)
+/* 8 CTAs per SM at 64 registers (a few spilled words): measured 2.19 ms per 256 pictures against 2.24 ms at 80 and
+ * 2.33 ms at 96 registers without spills — the loads of the reference window are what the extra warps hide.
+ * (An L2 prefetch of the records of later CTAs made no difference.)
+ *
+ * Tried and dropped (round 1, all bit-exact, default bench, ms per 256 pictures against 2.19 for this kernel; ncu of
+ * this kernel: 1 540 warp instructions per thread, issue slots 64 % busy, DRAM traffic = algorithmic bytes):
+ *   - sorting the 4x4 blocks of a CTA by fractional-position class (G | b | b+h | h | h+j | j | j+b) so that the
+ *     warp votes above switch most of the arithmetic off: 2.69 (256-block tiles, one run per warp) and 3.15
+ *     (512-block tiles, chunks of 32 claimed dynamically so the warps finish together).  A sorted warp gathers
+ *     blocks from up to 32 macroblocks, so its window loads no longer share sectors; the two neighbouring
+ *     macroblocks of an unsorted warp overlap heavily and that locality is worth more than the instructions;
+ *   - the three window words as two 8-byte loads plus selects: 2.31;
+ *   - prefetch.global.L1 of the residual slots at the top (ptxas sinks the loads to their use): 2.21, no change. */
+__global__ void __launch_bounds__(K2_THREADS, 8) k2_inter(Batch b)
 {
     const unsigned FULL = 0xffffffffu;
-    const int bx = blk & 3, by = blk >> 2;
+    const int lane = threadIdx.x & 31, blk = lane & 15, bx = blk & 3, by = blk >> 2;
+    const uint32_t g0 = (blockIdx.x * K2_THREADS + threadIdx.x) >> 4;        /* batch-wide macroblock index */
     const bool in_range = g0 < b.total_mbs;
     const uint32_t g = in_range ? g0 : b.total_mbs - 1;
     const PicJob &job = b.jobs[find_job(b, g)];
@@ -105,7 +115,6 @@ __device__ __forceinline__ void k2_block(const Batch &b, uint32_t g0, int blk, i
         const int n_ops = (int)useJ + (int)useB + (int)useH + (int)useG;      /* 1 or 2 */
         const bool anyJ = __any_sync(FULL, useJ), anyB = __any_sync(FULL, useB), anyH = __any_sync(FULL, useH);
         const int dn = fy == 3, rt = fx == 3;
-        const bool outer = !STAGED || anyH || anyJ;   /* window rows 0, 1, 7, 8 are only inputs of the vertical filters (skipping them did not pay in the unsorted kernel) */
 
         /* ---- window rows as three byte-aligned words: bytes 0..8 of the row ---- */
         uint32_t r0[9], r1[9], r2[9];
@@ -115,7 +124,6 @@ __device__ __forceinline__ void k2_block(const Batch &b, uint32_t g0, int blk, i
             const uint8_t *p = ref + (size_t)y0 * W + xa;
 #pragma unroll
             for (int r = 0; r < 9; r++) {
-                if (!outer && (r < 2 || r > 6)) { r0[r] = r1[r] = r2[r] = 0; continue; }      /* warp uniform */
                 const uint32_t *q = reinterpret_cast<const uint32_t *>(p + (size_t)r * W);
                 const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2);
                 r0[r] = __funnelshift_r(w0, w1, 8 * sh); r1[r] = __funnelshift_r(w1, w2, 8 * sh); r2[r] = w2 >> (8 * sh);
@@ -211,11 +219,8 @@ __device__ __forceinline__ void k2_block(const Batch &b, uint32_t g0, int blk, i
                 out_rows[py] = (uint32_t)v0 | ((uint32_t)v1 << 8) | ((uint32_t)v2 << 16) | ((uint32_t)v3 << 24);
             }
         }
-        if (STAGED) sy[slot] = make_int4((int)out_rows[0], (int)out_rows[1], (int)out_rows[2], (int)out_rows[3]);
-        else {
 #pragma unroll
-            for (int py = 0; py < 4; py++) *reinterpret_cast<uint32_t *>(dst + (size_t)py * W) = out_rows[py];
-        }
+        for (int py = 0; py < 4; py++) *reinterpret_cast<uint32_t *>(dst + (size_t)py * W) = out_rows[py];
     }
 
     /* ================================ chroma ================================ */
@@ -227,7 +232,6 @@ __device__ __forceinline__ void k2_block(const Batch &b, uint32_t g0, int blk, i
         const bool inside = xa >= 0 && xa + 8 <= CW && yc >= 0 && yc + 3 <= CH;
         const int cb0 = 16 + (by >> 1) * 2 + (bx >> 1);                      /* Cb 4x4 block holding this 2x2 */
         const int roff = (by & 1) * 8 + (bx & 1) * 2;                        /* its position inside that block */
-        uint32_t cpk[2];                                                     /* per plane: row 0 | row 1 << 16 */
 #pragma unroll
         for (int pl = 0; pl < 2; pl++) {
             const uint8_t *rp = ref + ysize + (pl ? csize : 0);
@@ -247,7 +251,6 @@ __device__ __forceinline__ void k2_block(const Batch &b, uint32_t g0, int blk, i
             const bool has_r = (mask >> cb) & 1;
             const int16_t *rs = coef + slot_index(mask, cb) * 16 + roff;
             uint8_t *dst = job.cur + ysize + (pl ? csize : 0) + (size_t)(mby * 8 + by * 2) * CW + mbx * 8 + bx * 2;
-            cpk[pl] = 0;
 #pragma unroll
             for (int y = 0; y < 2; y++) {
                 const int a0 = t[y] & 0xff, a1 = (t[y] >> 8) & 0xff, a2 = (t[y] >> 16) & 0xff;
@@ -258,105 +261,8 @@ __device__ __forceinline__ void k2_block(const Batch &b, uint32_t g0, int blk, i
                     const int rr = *reinterpret_cast<const int *>(rs + 4 * y);
                     v0 = clip255(v0 + (int)(short)(rr & 0xffff)); v1 = clip255(v1 + (rr >> 16));
                 }
-                if (STAGED) cpk[pl] |= (uint32_t)(v0 | (v1 << 8)) << (16 * y);
-                else *reinterpret_cast<uint16_t *>(dst + (size_t)y * CW) = (uint16_t)(v0 | (v1 << 8));
+                *reinterpret_cast<uint16_t *>(dst + (size_t)y * CW) = (uint16_t)(v0 | (v1 << 8));
             }
         }
-        if (STAGED) sc[slot] = make_uint2(cpk[0], cpk[1]);
-    }
-}
-
-/* A half-warp is one macroblock, a warp two horizontally adjacent macroblocks; every thread keeps the block its
- * index names and stores it itself.  8 CTAs per SM at 64 registers (a few spilled words): measured 2.19 ms per 256
- * pictures against 2.24 ms at 80 and 2.33 ms at 96 registers without spills — the loads of the reference window are
- * what the extra warps hide.  (An L2 prefetch of the records of later CTAs made no difference.) */
-__global__ void __launch_bounds__(K2_THREADS, 8) k2_inter(Batch b)
-{
-    k2_block<false>(b, (blockIdx.x * K2_THREADS + threadIdx.x) >> 4, threadIdx.x & 15, nullptr, nullptr, 0);
-}
-
-/* EXPERIMENT, not the default (H264B200_K2=sorted selects it; bit-exact, the GPU parity suite passes with it):
- * the blocks of a CTA (16 macroblocks = 256 blocks) are SORTED BY FRACTIONAL-POSITION CLASS before they are
- * interpolated.  Which operand families (horizontal half b, vertical half h, centre j) a warp computes is a warp
- * vote; with one macroblock pair per warp and vectors that differ per partition, nearly every warp needs all
- * three and every thread pays for the worst position.  After a counting sort over the seven classes
- *     G | b | b+h | h | h+j | j | j+b      (neighbours differ by one family; class 7: not an inter block)
- * a warp holds one or two classes and the votes switch most of the arithmetic off; results return through
- * shared memory to the thread that owns the block's position, so the frame is still written as full 32-byte
- * sectors per warp row store.
- * Measured on B200, default bench, per 256 pictures: 2.69 ms against 2.22 ms for k2_inter.  The kernel is bound by
- * the latency of its dependent loads (record -> window -> residual; ncu: 40 % of the samples on the long
- * scoreboard), not by the arithmetic the sort removes, and the warps of a CTA now finish at very different times
- * (a G warp does a sixth of a j+h warp's work) while their registers stay allocated until the slowest one ends,
- * so fewer warps are left to hide that latency.  A version that balances the classes across warps (several tiles
- * per CTA, chunks of sorted blocks claimed dynamically) is the open follow-up. */
-#define K2S_THREADS 256
-__global__ void __launch_bounds__(K2S_THREADS, 4) k2_inter_sorted(Batch b)
-{
-    __shared__ int4 sy[K2S_THREADS];
-    __shared__ uint2 sc[K2S_THREADS];
-    __shared__ uint16_t perm[K2S_THREADS];
-    __shared__ uint32_t hist[64];                /* [class][warp] counts, then exclusive offsets */
-    const unsigned FULL = 0xffffffffu;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t mb0 = blockIdx.x * (K2S_THREADS / 16);
-    const uint32_t gA = mb0 + (tid >> 4);
-    const bool inA = gA < b.total_mbs;
-    const uint32_t gc = inA ? gA : b.total_mbs - 1;
-    bool interA;
-    int cls = 7;
-    {
-        const PicJob &job = b.jobs[find_job(b, gc)];
-        const uint32_t *rec = reinterpret_cast<const uint32_t *>(job.mbs + (gc - job.mb_base));
-        interA = inA && (__ldg(rec) & 0xff) == H264B200_MB_INTER;
-        if (interA) {
-            const uint32_t mvw = __ldg(rec + 16 + (tid & 15));
-            const int fx = mvw & 3, fy = (mvw >> 16) & 3;
-            const int useJ = (fx == 2 && fy != 0) || (fy == 2 && fx != 0), useB = fx != 0 && fy != 2, useH = fy != 0 && fx != 2;
-            cls = (0x04652310u >> (4 * (useB | (useH << 1) | (useJ << 2)))) & 7;
-        }
-    }
-    if (!__syncthreads_or(interA)) return;
-    /* counting sort, stable in thread order: rank inside the warp from ballots, class/warp offsets from one warp scan */
-    int rank = 0; uint32_t cnt = 0;
-#pragma unroll
-    for (int c = 0; c < 8; c++) {
-        const unsigned m = __ballot_sync(FULL, cls == c);
-        if (cls == c) rank = __popc(m & ((1u << lane) - 1u));
-        if (lane == c) cnt = __popc(m);
-    }
-    if (lane < 8) hist[lane * 8 + warp] = cnt;
-    __syncthreads();
-    if (warp == 0) {
-        const uint32_t a = hist[2 * lane], c2 = hist[2 * lane + 1];
-        uint32_t incl = a + c2;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += v; }
-        hist[2 * lane] = incl - a - c2; hist[2 * lane + 1] = incl - c2;
-    }
-    __syncthreads();
-    perm[hist[cls * 8 + warp] + rank] = (uint16_t)tid;
-    __syncthreads();
-    const int t2 = perm[tid];
-    k2_block<true>(b, mb0 + (t2 >> 4), t2 & 15, sy, sc, t2);
-    __syncthreads();
-    if (interA) {
-        const PicJob &job = b.jobs[find_job(b, gc)];
-        const uint32_t mbi = gc - job.mb_base;
-        const int W = job.wm * 16, H = job.hm * 16, CW = W >> 1;
-        const int mbx = mbi % job.wm, mby = mbi / job.wm, blk = tid & 15, bx = blk & 3, by = blk >> 2;
-        const size_t ysize = (size_t)W * H, csize = ysize >> 2;
-        const int4 y = sy[tid];
-        const uint2 c = sc[tid];
-        uint8_t *dst = job.cur + (size_t)(mby * 16 + by * 4) * W + mbx * 16 + bx * 4;
-        *reinterpret_cast<uint32_t *>(dst) = (uint32_t)y.x;
-        *reinterpret_cast<uint32_t *>(dst + (size_t)W) = (uint32_t)y.y;
-        *reinterpret_cast<uint32_t *>(dst + (size_t)2 * W) = (uint32_t)y.z;
-        *reinterpret_cast<uint32_t *>(dst + (size_t)3 * W) = (uint32_t)y.w;
-        uint8_t *dc = job.cur + ysize + (size_t)(mby * 8 + by * 2) * CW + mbx * 8 + bx * 2;
-        *reinterpret_cast<uint16_t *>(dc) = (uint16_t)c.x;
-        *reinterpret_cast<uint16_t *>(dc + CW) = (uint16_t)(c.x >> 16);
-        *reinterpret_cast<uint16_t *>(dc + csize) = (uint16_t)c.y;
-        *reinterpret_cast<uint16_t *>(dc + csize + CW) = (uint16_t)(c.y >> 16);
     }
 }
