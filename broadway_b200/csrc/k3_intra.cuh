@@ -232,7 +232,13 @@ __device__ void k3_macroblock(const PicJob &job, K3Warp &w, int mbx, int mby, in
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(K3_WARPS * 32, 6) k3_intra(Batch b)
+/* Occupancy: the kernel is latency bound (ncu: issue slots 21 % busy), so resident warps are throughput up to the point
+ * where spills lengthen the serial Intra4x4 chain.  Measured on B200, 256 all-intra 1080p pictures per launch:
+ * 6 / 8 / 10 / 12 / 16 CTAs per SM (80 / 64 / 48 / 40 / 32 registers) = 3.88 / 3.51 / 3.72 / 4.22 / 4.65 ms. */
+#ifndef K3_MINB
+#define K3_MINB 8
+#endif
+__global__ void __launch_bounds__(K3_WARPS * 32, K3_MINB) k3_intra(Batch b)
 {
     __shared__ K3Warp sm[K3_WARPS];
     const int lane = threadIdx.x & 31;
