@@ -341,6 +341,7 @@ static uint32_t submit_locked(h264b200_engine *e)
 }
 
 /* ------------------------------------------------------- backend callbacks */
+static void inst_free(Inst *in);
 static void *be_inst_create(h264_backend_t *be, uint32_t wm, uint32_t hm, uint32_t n_slots)
 {
     h264b200_engine *e = (h264b200_engine *)be->ctx;
@@ -367,10 +368,10 @@ static void *be_inst_create(h264_backend_t *be, uint32_t wm, uint32_t hm, uint32
     in->frame_bytes = (size_t)in->n_mbs * 384;
     in->batched = (e->flags & H264B200_ENGINE_BATCHED) != 0;
     CUDA_TRY(cudaMalloc((void **)&in->d_frames, in->frame_bytes * n_slots), { free(in); return NULL; });
-    CUDA_TRY(cudaMemset(in->d_frames, 0, in->frame_bytes * n_slots), { free(in); return NULL; });
-    CUDA_TRY(cudaHostAlloc((void **)&in->h_frames, in->frame_bytes * n_slots, cudaHostAllocDefault), { free(in); return NULL; });
+    CUDA_TRY(cudaMemset(in->d_frames, 0, in->frame_bytes * n_slots), { cudaFree(in->d_frames); free(in); return NULL; });
+    CUDA_TRY(cudaHostAlloc((void **)&in->h_frames, in->frame_bytes * n_slots, cudaHostAllocDefault), { cudaFree(in->d_frames); free(in); return NULL; });
     memset(in->h_frames, 0, in->frame_bytes * n_slots);
-    for (int i = 0; i < NBUF; i++) if (picbuf_alloc(&in->bufs[i], in, in->n_mbs * 10 + 64)) return NULL;
+    for (int i = 0; i < NBUF; i++) if (picbuf_alloc(&in->bufs[i], in, in->n_mbs * 10 + 64)) { inst_free(in); return NULL; }   /* frees what was allocated so far */
     std::lock_guard<std::mutex> lk(e->mu);
     e->insts.push_back(in);
     return in;
