@@ -36,18 +36,9 @@
  */
 #pragma once
 #include "k_common.cuh"
+#include "k2_math.cuh"
 
 #define K2_THREADS 128
-
-__device__ __forceinline__ int tap6(int a, int b, int c, int d, int e, int f) { return (a + f) - 5 * (b + e) + 20 * (c + d); }
-
-/* four unsigned bytes of a times four signed bytes of b, accumulated (dp4a.u32.s32) */
-__device__ __forceinline__ int dp4a_us(uint32_t a, int b, int c)
-{
-    int d;
-    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-    return d;
-}
 
 /* clamped single-sample fetch: the reference's out-of-picture behaviour (h264bsdFillBlock) */
 __device__ __forceinline__ uint32_t ref_px(const uint8_t *pl, int w, int h, int x, int y)
@@ -114,7 +105,6 @@ __global__ void __launch_bounds__(K2_THREADS, 8) k2_inter(Batch b)
         const bool useG = inter && !useJ && !(useB && useH) && !(fx == 2) && !(fy == 2);
         const int n_ops = (int)useJ + (int)useB + (int)useH + (int)useG;      /* 1 or 2 */
         const bool anyJ = __any_sync(FULL, useJ), anyB = __any_sync(FULL, useB), anyH = __any_sync(FULL, useH);
-        const int dn = fy == 3, rt = fx == 3;
 
         /* ---- window rows as three byte-aligned words: bytes 0..8 of the row ---- */
         uint32_t r0[9], r1[9], r2[9];
@@ -143,67 +133,8 @@ __global__ void __launch_bounds__(K2_THREADS, 8) k2_inter(Batch b)
             for (int r = 0; r < 9; r++) { r0[r] = r1[r] = r2[r] = 0; }
         }
 
-        /* ---- the 4 samples at columns x+rt .. x+rt+3 of every window row (G' and the inputs of h') ---- */
-        uint32_t cw[9];
-#pragma unroll
-        for (int r = 0; r < 9; r++) cw[r] = __funnelshift_r(r0[r], r1[r], 8 * (2 + rt));
-
-        /* ---- horizontal 6-tap sums: hs[r][k] for output column k of window row r ---- */
-        int hs[9][4];
-        if (anyB || anyJ) {
-            const int T0 = 0x1414fb01, T1 = 0x000001fb;      /* (1,-5,20,20) and (-5,1,0,0) as signed bytes, low byte first */
-#pragma unroll
-            for (int r = 0; r < 9; r++) {
-                if (!anyJ && (r < 2 || r > 6)) { hs[r][0] = hs[r][1] = hs[r][2] = hs[r][3] = 0; continue; }
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const uint32_t lo = k ? __funnelshift_r(r0[r], r1[r], 8 * k) : r0[r];
-                    const uint32_t hi = k ? __funnelshift_r(r1[r], r2[r], 8 * k) : r1[r];
-                    hs[r][k] = dp4a_us(lo, T0, dp4a_us(hi, T1, 0));
-                }
-            }
-        }
-
-        /* ---- per output row: operands and the final blend ---- */
-#pragma unroll
-        for (int py = 0; py < 4; py++) {
-            int bq[4] = {0, 0, 0, 0}, hq[4] = {0, 0, 0, 0}, jq[4] = {0, 0, 0, 0};
-            if (anyB) {
-#pragma unroll
-                for (int k = 0; k < 4; k++) bq[k] = clip255(((dn ? hs[py + 3][k] : hs[py + 2][k]) + 16) >> 5);
-            }
-            if (anyH) {
-                /* vertical 6-tap over raw samples, two samples per instruction on biased 16-bit lanes:
-                 * (a+f) + 20(c+d) + 2560 - 5(b+e) stays within [0, 65535] per lane */
-#pragma unroll
-                for (int half = 0; half < 2; half++) {
-                    uint32_t e[6];
-#pragma unroll
-                    for (int t = 0; t < 6; t++) e[t] = (cw[py + t] >> (8 * half)) & 0x00ff00ffu;
-                    const uint32_t s = (e[0] + e[5] + 0x0a000a00u) + 20u * (e[2] + e[3]) - 5u * (e[1] + e[4]);
-                    hq[half] = clip255(((int)(s & 0xffff) - 2560 + 16) >> 5);
-                    hq[half + 2] = clip255(((int)(s >> 16) - 2560 + 16) >> 5);
-                }
-            }
-            if (anyJ) {
-#pragma unroll
-                for (int k = 0; k < 4; k++)
-                    jq[k] = clip255((tap6(hs[py][k], hs[py + 1][k], hs[py + 2][k], hs[py + 3][k], hs[py + 4][k], hs[py + 5][k]) + 512) >> 10);
-            }
-            const uint32_t gw = dn ? cw[py + 3] : cw[py + 2];
-            uint32_t pk = 0;
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                int s = 0;
-                if (useG) s += (gw >> (8 * k)) & 0xff;
-                if (useB) s += bq[k];
-                if (useH) s += hq[k];
-                if (useJ) s += jq[k];
-                const int v = (s * (3 - n_ops) + 1) >> 1;
-                pk |= (uint32_t)v << (8 * k);
-            }
-            out_rows[py] = pk;
-        }
+        /* ---- interpolation on registers (k2_math.cuh; CPU-checked by tests/test_k2_math_cpu.py) ---- */
+        k2m_luma4x4(r0, r1, r2, fx, fy, useG, useB, useH, useJ, n_ops, anyB, anyH, anyJ, out_rows);
     }
 
     /* ---- luma residual + store ---- */
