@@ -13,6 +13,10 @@ u32  broadwayInit(void);                       /* Decoder.c:74-93: 0 on success 
 void broadwayExit(void);                       /* Decoder.c:164-168 */
 u8  *broadwayCreateStream(u32 length);         /* Decoder.c:58-61: buffer the caller fills with NAL units / Annex-B */
 void broadwayPlayStream(u32 length);           /* Decoder.c:67-70: decode `length` bytes of that buffer */
+/* One deliberate difference: after a picture the reference's loop zeroes the remaining length even when the decoder
+ * reported "buffer not empty" (Decoder.c:129-134, the test on PIC_RDY is commented out), i.e. it plays at most one
+ * picture per call and drops the rest of the buffer.  The Player feeds one NAL unit per call, where both behave the
+ * same; this library decodes everything the caller put in the buffer. */
 u32  broadwayGetMajorVersion(void);            /* Decoder.c:178-184 */
 u32  broadwayGetMinorVersion(void);
 
