@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("H264B200_LIB") or os.path.join(_HERE, "libh264b200.so
 
 H264BSD_RDY, H264BSD_PIC_RDY, H264BSD_HDRS_RDY, H264BSD_ERROR, H264BSD_PARAM_SET_ERROR, H264BSD_MEMALLOC_ERROR = range(6)
 H264SWDEC_OK, H264SWDEC_STRM_PROCESSED, H264SWDEC_PIC_RDY, H264SWDEC_PIC_RDY_BUFF_NOT_EMPTY, H264SWDEC_HDRS_RDY_BUFF_NOT_EMPTY = range(5)
-ENGINE_BATCHED, ENGINE_RETAIN, ENGINE_NO_D2H = 1, 2, 4
+ENGINE_BATCHED, ENGINE_RETAIN, ENGINE_NO_D2H, ENGINE_DEVICE_PARSE = 1, 2, 4, 8
 
 
 class Storage(ctypes.Structure):
@@ -43,11 +43,11 @@ class SwDecInfo(ctypes.Structure):
 
 
 class Stats(ctypes.Structure):
-    _fields_ = [(n, ctypes.c_uint64) for n in ("kernel_launches", "pictures", "h2d_bytes", "d2h_bytes", "batches")]
+    _fields_ = [(n, ctypes.c_uint64) for n in ("kernel_launches", "pictures", "h2d_bytes", "d2h_bytes", "batches", "kp_launches", "kp_pictures")]
 
 
 class KernelTimes(ctypes.Structure):
-    _fields_ = [("ms", ctypes.c_double * 4), ("bytes", ctypes.c_uint64 * 4), ("launches", ctypes.c_uint64 * 4)]
+    _fields_ = [("ms", ctypes.c_double * 5), ("bytes", ctypes.c_uint64 * 5), ("launches", ctypes.c_uint64 * 5)]
 
 
 class StreamDesc(ctypes.Structure):
@@ -107,6 +107,11 @@ def lib():
     L.h264b200EngineKernelTimes.argtypes = [vp, ctypes.POINTER(KernelTimes), ctypes.c_int]; L.h264b200EngineKernelTimes.restype = None
     L.h264b200NextOutputPictureAsync.argtypes = [sp, u32p, u32p, u32p, u32p]; L.h264b200NextOutputPictureAsync.restype = vp
     L.h264b200PictureWait.argtypes = [sp, u32]; L.h264b200PictureWait.restype = u32
+    L.h264b200EngineAdvance.argtypes = [vp]; L.h264b200EngineAdvance.restype = u32
+    L.h264b200EngineSetWindow.argtypes = [vp, u32, u32]; L.h264b200EngineSetWindow.restype = None
+    L.h264b200DeviceParse.argtypes = [sp]; L.h264b200DeviceParse.restype = u32
+    if hasattr(L, "h264b200DebugFetchParse"):
+        L.h264b200DebugFetchParse.argtypes = [sp, ctypes.c_int, vp, vp, u32, vp]; L.h264b200DebugFetchParse.restype = ctypes.c_int
     L.h264b200DecodeStreams.argtypes = [vp, ctypes.POINTER(StreamDesc), u32, u32, vp, vp, ctypes.POINTER(RunStats)]
     L.h264b200DecodeStreams.restype = ctypes.c_int
     L.h264b200SplitGops.argtypes = [vp, ctypes.c_size_t, vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t),
@@ -308,8 +313,8 @@ class Engine:
     def kernel_times(self, reset=False):
         kt = KernelTimes()
         self.L.h264b200EngineKernelTimes(self.h, ctypes.byref(kt), 1 if reset else 0)
-        names = ("k1_transform", "k2_inter", "k3_intra", "k4_deblock")
-        return {names[k]: {"ms": kt.ms[k], "bytes": kt.bytes[k], "launches": kt.launches[k]} for k in range(4)}
+        names = ("k1_transform", "k2_inter", "k3_intra", "k4_deblock", "kp_parse")
+        return {names[k]: {"ms": kt.ms[k], "bytes": kt.bytes[k], "launches": kt.launches[k]} for k in range(5)}
 
     def check_resident(self):
         return self.L.h264b200EngineCheckResident(self.h)

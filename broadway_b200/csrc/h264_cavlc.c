@@ -10,10 +10,13 @@
  */
 #include <stdlib.h>
 #include <stdio.h>
+#include <string.h>
 #include "h264_internal.h"
 #include "cavlc_tables.h"
 
 #include "h264_cavlc_inl.h"
+#include "h264_consts.h"
+#include "kp_types.h"
 
 /* coeff_token, nC classes 0..2: index = leading_zeros*8 + (3 bits after the first 1) */
 ct_entry_t g_ct[3][16 * 8];
@@ -94,3 +97,21 @@ void h264_cavlc_init(void)
     g_init = 1;
 }
 
+
+/* The same look-up tables, as one block for the device-side parser (kernel Kp, kp_core.h): the CUDA engine copies it to
+ * HBM once; the CPU test build of kp_core.h reads it in place. */
+void h264_kp_fill_tables(KpTables *t)
+{
+    h264_cavlc_init();
+    memset(t, 0, sizeof *t);
+    memcpy(t->ct, g_ct, sizeof t->ct);
+    memcpy(t->ct_cdc, g_ct_cdc, sizeof t->ct_cdc);
+    memcpy(t->tz, g_tz, sizeof t->tz);
+    memcpy(t->tz_cdc, g_tz_cdc, sizeof t->tz_cdc);
+    memcpy(t->rb, g_rb, sizeof t->rb);
+    memcpy(t->lvl, g_lvl, sizeof t->lvl);
+    memcpy(t->cbp_map, H264_CBP_MAP, sizeof t->cbp_map);
+    memcpy(t->zigzag, H264_ZIGZAG4x4, sizeof t->zigzag);
+    memcpy(t->raster_to_blk, H264_RASTER_TO_BLK, sizeof t->raster_to_blk);
+    memcpy(t->qpc, H264_QPC, sizeof t->qpc);
+}

@@ -215,6 +215,7 @@ static int activate_param_sets(h264_decoder_t *d, uint32_t pps_id, int is_idr)
         if (d->be_inst) { d->be->inst_destroy(d->be, d->be_inst); d->be_inst = NULL; }
         d->be_inst = d->be->inst_create(d->be, d->width_mbs, d->height_mbs, d->n_slots);
         if (!d->be_inst) return -2;
+        d->device_parse = d->be->block_grow && d->be->parse_mode;
         d->pic = NULL;
         if (d->out_format && apply_output_format(d)) return -2;
     } else if ((int)pps_id != d->active_pps_id) {
@@ -347,12 +348,65 @@ static uint32_t conceal_picture(h264_decoder_t *d)
     return n;
 }
 
+/* ------------------------------------------------ device-parse path: queue a slice */
+/* Append the slice NAL (RBSP, emulation prevention already removed) and what the kernel needs from its header to the
+ * picture's block (include/h264b200_slices.h).  `b` stands at the first bit of slice_data(). */
+static int enqueue_slice(h264_decoder_t *d, const br_t *b, const h264_slice_hdr_t *sh)
+{
+    h264_pic_input_t *pic = d->pic;
+    const uint32_t rbsp_len = (uint32_t)b->len, N = d->pic_size_mbs;
+    const int fmo = d->active_pps->num_slice_groups > 1;
+    const uint32_t rb_pad = (rbsp_len + 15u) & ~15u, map_pad = fmo ? (N + 15u) & ~15u : 0;
+    const uint32_t need = (uint32_t)sizeof(h264b200_slice_t) + rb_pad + map_pad;
+    h264b200_slice_t *sl; uint8_t *p; uint32_t i;
+    if (pic->block_used + need > pic->block_cap && d->be->block_grow(d->be, d->be_inst, pic, pic->block_used + need)) return -1;
+    p = pic->block + pic->block_used;
+    sl = (h264b200_slice_t *)p;
+    memset(sl, 0, sizeof *sl);
+    sl->size = need; sl->rbsp_len = rbsp_len;
+    sl->bit_off = (uint32_t)br_pos(b); sl->payload_bits = (uint32_t)b->payload_bits;
+    sl->first_mb = sh->first_mb;
+    sl->slice_id = (uint16_t)(++d->slice_id);
+    sl->is_p = sh->slice_type == 0;
+    sl->num_ref_idx_active = (uint8_t)sh->num_ref_idx_active;
+    sl->slice_qp = (int8_t)sh->slice_qp;
+    sl->chroma_qp_off = (int8_t)d->active_pps->chroma_qp_index_offset;
+    sl->alpha_off = sh->alpha_off; sl->beta_off = sh->beta_off;
+    sl->disable_deblocking_idc = sh->disable_deblocking_idc;
+    sl->constrained_intra = d->active_pps->constrained_intra_pred;
+    for (i = 0; i <= H264_MAX_REFS; i++) sl->ref_slot[i] = -1;
+    if (sl->is_p) for (i = 0; i < sh->num_ref_idx_active && i <= H264_MAX_REFS; i++) sl->ref_slot[i] = (int8_t)h264_dpb_ref_slot(&d->dpb, i);
+    memcpy(p + sizeof *sl, b->data, rbsp_len);
+    memset(p + sizeof *sl + rbsp_len, 0, rb_pad - rbsp_len);
+    if (fmo) {
+        sl->map_off = (uint32_t)sizeof *sl + rb_pad;
+        memcpy(p + sl->map_off, d->slice_group_map, N);
+        memset(p + sl->map_off + N, 0, map_pad - N);
+    }
+    ((h264b200_pichdr_t *)pic->block)->n_slices++;
+    pic->block_used += need;
+    if (sl->is_p) pic->has_p_slice = 1;
+    return 0;
+}
+
 /* ------------------------------------------------------------ picture end */
 static void finish_picture(h264_decoder_t *d)
 {
     int is_idr = d->pic_nal_type == NAL_IDR;
     int32_t poc;
     if (d->pic) {
+        if (d->device_parse) {
+            /* kernel Kp finds out which macroblocks the slices delivered and conceals the rest (kp_core.h
+             * kp_conceal_picture); what it needs from the DPB goes into the picture header.  The number of
+             * concealed macroblocks comes back with the frame (h264b200_picstat_t). */
+            h264b200_pichdr_t *hdr = (h264b200_pichdr_t *)d->pic->block;
+            const int is_p = !d->valid_slice_in_au || d->sh.slice_type == 0;
+            int ref = -1; uint32_t i;
+            if (is_p) for (i = 0; i < H264_MAX_REFS && ref < 0; i++) ref = h264_dpb_ref_slot(&d->dpb, i);
+            hdr->conceal_as_p = (uint8_t)is_p; hdr->conceal_ref_slot = (int8_t)ref;
+            hdr->total_bytes = d->pic->block_used;
+            d->num_err_mbs = 0;
+        } else
         if (d->num_decoded_mbs != d->pic_size_mbs) d->num_err_mbs = conceal_picture(d);    /* lost slices */
         d->pic->cur_slot = h264_dpb_current_slot(&d->dpb);
         d->be->pic_submit(d->be, d->be_inst, d->pic);
@@ -371,8 +425,22 @@ static int begin_picture(h264_decoder_t *d)
     if (!d->pic) return -1;
     d->pic->coef_used = 0; d->pic->n_intra = d->pic->n_inter = 0; d->pic->any_deblock = 0; d->pic->n_conceal = 0; d->pic->conceal_offset = 0;
     memset(d->pic->ref_slots_used, 0, sizeof d->pic->ref_slots_used);
-    memset(d->mbctx, 0, d->pic_size_mbs * sizeof(h264_mbctx_t));   /* records of unparsed macroblocks are flagged MISSING in finish_picture */
+    d->pic->block_used = 0; d->pic->has_p_slice = 0;
     d->num_decoded_mbs = 0; d->slice_id = 0;
+    if (d->device_parse) {                      /* the block starts with the picture header; slices follow (enqueue_slice) */
+        h264b200_pichdr_t *hdr;
+        if (!d->pic->block || d->pic->block_cap < sizeof *hdr) {
+            if (d->be->block_grow(d->be, d->be_inst, d->pic, 4096) || !d->pic->block) return -1;
+        }
+        hdr = (h264b200_pichdr_t *)d->pic->block;
+        memset(hdr, 0, sizeof *hdr);
+        hdr->magic = H264B200_PICHDR_MAGIC;
+        hdr->width_mbs = (uint16_t)d->width_mbs; hdr->height_mbs = (uint16_t)d->height_mbs;
+        hdr->conceal_ref_slot = -1;
+        d->pic->block_used = sizeof *hdr;
+        return 0;
+    }
+    memset(d->mbctx, 0, d->pic_size_mbs * sizeof(h264_mbctx_t));   /* records of unparsed macroblocks are flagged MISSING in finish_picture */
     return 0;
 }
 
@@ -508,6 +576,12 @@ u32 h264bsdDecode(storage_t *pStorage, u8 *byteStrm, u32 len, u32 picId, u32 *re
         if (sh.redundant_pic_cnt) break;          /* redundant coded pictures are not decoded */
         h264_dpb_init_ref_list(&d->dpb);
         if (h264_dpb_reorder(&d->dpb, &d->sh)) return H264BSD_ERROR;
+        if (d->device_parse) {
+            /* the picture ends when the next access unit begins (or at h264bsdFlushBuffer): how many macroblocks
+             * the slice holds is only known once kernel Kp has parsed it */
+            if (enqueue_slice(d, &b, &d->sh)) return H264BSD_MEMALLOC_ERROR;
+            break;
+        }
         if (h264_decode_slice_data(d, &b, &d->sh)) {
             /* the macroblocks of a slice that failed are given back (they are concealed when the access unit ends) */
             mark_slice_corrupted(d, d->sh.first_mb);
@@ -529,13 +603,20 @@ u8 *h264bsdNextOutputPicture(storage_t *pStorage, u32 *picId, u32 *isIdrPic, u32
     uint32_t err = 0;
     uint8_t *p;
     if (!d || !d->dpb.allocated || !d->be_inst) return NULL;
-    o = h264_dpb_next_output(&d->dpb);
-    if (!o) return NULL;
-    p = d->be->frame_host(d->be, d->be_inst, o->slot, &err);
-    if (picId) *picId = o->pic_id;
-    if (isIdrPic) *isIdrPic = o->is_idr;
-    if (numErrMbs) *numErrMbs = o->num_err_mbs;
-    return p;
+    for (;;) {
+        h264b200_picstat_t ps;
+        o = h264_dpb_next_output(&d->dpb);
+        if (!o) return NULL;
+        p = d->be->frame_host(d->be, d->be_inst, o->slot, &err);
+        if (picId) *picId = o->pic_id;
+        if (isIdrPic) *isIdrPic = o->is_idr;
+        if (numErrMbs) *numErrMbs = o->num_err_mbs;
+        if (d->device_parse && p && d->be->frame_status && !d->be->frame_status(d->be, d->be_inst, o->slot, &ps)) {
+            if (ps.flags & H264B200_PS_DROPPED) continue;     /* incomplete last picture of the stream: never became a picture */
+            if (numErrMbs) *numErrMbs = ps.err_mbs;
+        }
+        return p;
+    }
 }
 
 u32 h264b200SetOutputFormat(storage_t *pStorage, u32 format)
@@ -581,6 +662,25 @@ u32 h264b200PictureWait(storage_t *pStorage, u32 ticket)
     if (!d->be->frame_host(d->be, d->be_inst, (int)(ticket & 0xff), &err)) return 0xffffffffu;
     return err;
 }
+
+/* 0 and the status words of the picture behind `ticket` (after h264b200PictureWait returned 0); 1 if the backend keeps none */
+u32 h264b200PictureStatus(storage_t *pStorage, u32 ticket, h264b200_picstat_t *out)
+{
+    h264_decoder_t *d = DEC(pStorage);
+    if (!d || !d->be_inst || !out || !d->device_parse || !d->be->frame_status) return 1;
+    return d->be->frame_status(d->be, d->be_inst, (int)(ticket & 0xff), out) ? 1 : 0;
+}
+void h264b200PictureRelease(storage_t *pStorage, u32 ticket)
+{
+    h264_decoder_t *d = DEC(pStorage);
+    if (d && d->be_inst && d->be->frame_release) d->be->frame_release(d->be, d->be_inst, (int)(ticket & 0xff), ticket >> 8);
+}
+u32 h264b200PicturesPending(storage_t *pStorage)
+{
+    h264_decoder_t *d = DEC(pStorage);
+    return d && d->be_inst && d->be->inst_pending ? d->be->inst_pending(d->be, d->be_inst) : 0;
+}
+u32 h264b200DeviceParse(storage_t *pStorage) { h264_decoder_t *d = DEC(pStorage); return d ? (u32)d->device_parse : 0; }
 
 void h264bsdShutdown(storage_t *pStorage)
 {
@@ -640,7 +740,17 @@ u32 h264bsdCheckValidParamSets(storage_t *s)
     for (i = 0; i < H264_MAX_PPS; i++) if (d->pps[i] && d->sps[d->pps[i]->sps_id]) return 1;
     return 0;
 }
-void h264bsdFlushBuffer(storage_t *s) { h264_decoder_t *d = DEC(s); if (d) h264_dpb_flush(&d->dpb); }
+void h264bsdFlushBuffer(storage_t *s)
+{
+    h264_decoder_t *d = DEC(s);
+    if (!d) return;
+    /* device-parse: the last picture of the stream has no following access unit to end it */
+    if (d->device_parse && d->pic_started && d->valid_slice_in_au && d->pic && !d->pending_activation) {
+        ((h264b200_pichdr_t *)d->pic->block)->tentative = 1;
+        finish_picture(d);
+    }
+    h264_dpb_flush(&d->dpb);
+}
 u32 h264bsdProfile(storage_t *s) { h264_decoder_t *d = DEC(s); return d && d->active_sps ? d->active_sps->profile_idc : 0; }
 
 /* used by the H264SwDec layer (h264_swdec.c): DPB flags the reference's API pokes directly */

@@ -22,6 +22,13 @@
  * reference's output layout, so D2H needs no repacking.  Records and slots of a
  * picture live in a ring of NBUF input buffers (pinned host + device twin).
  *
+ * DEVICE-PARSE instances (H264B200_ENGINE_DEVICE_PARSE) hand over slice NAL units instead of records
+ * (include/h264b200_slices.h); kernel Kp (kp_core.h, kp_parse.cuh) parses the slice data of every queued
+ * picture of every instance in one launch on its own stream — pictures of one stream are independent at
+ * that level, so the look-ahead window of all streams is the parallelism — and writes the same records
+ * and slots into HBM.  Pictures wait in a FIFO per instance; every h264b200EngineAdvance launches Kp
+ * when enough of them are queued and then ONE reconstruction round (the oldest picture of each instance).
+ *
  * Streams: s_h2d (records/slots in) -> s_comp (K1..K4) -> s_d2h (frames out),
  * chained with events, so the copy-in of batch n+1 and the copy-out of batch
  * n-1 overlap the kernels of batch n.  There is no CPU reconstruction path in
@@ -32,6 +39,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <atomic>
+#include <deque>
 #include <mutex>
 #include <vector>
 #include "h264b200.h"
@@ -43,9 +52,12 @@
 #include "k3c_conceal.cuh"
 #include "k4_deblock.cuh"
 #include "k5_rgba.cuh"
+#include "kp_parse.cuh"
 
-#define NBUF 3                 /* input buffers in flight per instance */
+#define NBUF 3                 /* input buffers in flight per instance (host-parse; device-parse: look-ahead depth + 2) */
 #define NSCR 4                 /* batch scratch sets in flight per engine */
+#define NPAR 4                 /* Kp launch scratch sets in flight per engine */
+#define STAT_TAIL 128          /* bytes behind every frame: h264b200_picstat_t of the picture (device-parse), copied out with it */
 #define CTRL_HEAD 16           /* int32 words before the progress counters: [0] K3 ticket, [1] K4 ticket */
 
 #define CUDA_TRY(call, fail) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { \
@@ -54,42 +66,72 @@
 struct Inst;
 
 struct PicBuf {
-    h264_pic_input_t in;           /* in.mbs / in.coef: ONE pinned block, records first, coefficient slots behind them */
-    h264b200_mb_t *d_mbs;          /* device twin of the block: one cudaMemcpyAsync per picture */
-    int16_t *d_coef;
+    h264_pic_input_t in;           /* host-parse: in.mbs / in.coef = ONE pinned block, records first, coefficient slots behind them;
+                                      device-parse: in.block = pinned {picture header, slices} (include/h264b200_slices.h) */
+    h264b200_mb_t *d_mbs;          /* host-parse: device twin of the pinned block (one cudaMemcpyAsync per picture);
+                                      device-parse: where kernel Kp writes the records ... */
+    int16_t *d_coef;               /* ... and the coefficient slots (worst-case capacity, KP_COEF_CAP) */
     uint32_t d_coef_cap;           /* slots */
-    cudaEvent_t done;              /* (not owned) event of the batch whose kernels read this buffer */
+    cudaEvent_t done;              /* (not owned) event of the round whose kernels read this buffer */
     int state;                     /* 0 free, 1 being filled by the parser, 2 queued, 3 launched */
+    int own_host, own_dev;         /* the pinned / device memory of this buffer is its own allocation (not a slice of the instance's) */
     Inst *inst;
+    /* device-parse */
+    uint8_t *d_block; uint32_t d_block_cap; int own_dblock;
+    KpMbCtx *d_ctx; KpResult *d_res;
+    cudaEvent_t parsed;            /* (not owned) event of the Kp launch that parses this picture */
+    uint32_t parse_seq;            /* which Kp launch; 0: not launched yet */
+    uint32_t gate_gen;             /* generation of the frame slot's host mirror that must have been released before this picture is launched */
+    int tape_parse, tape_last_round;   /* retained runs: tape index of the Kp launch that fills / of the last round that read this buffer */
 };
 
 struct Inst {
     h264b200_engine *e;
     uint32_t wm, hm, n_mbs, n_slots;
     size_t frame_bytes;
+    size_t frame_stride;                      /* frame_bytes + STAT_TAIL */
     uint8_t *d_frames, *h_frames;
     cudaEvent_t slot_ready[H264_MAX_SLOTS];   /* (not owned) copy-out event of the batch that last wrote the slot's mirror */
     uint8_t slot_flags[H264_MAX_SLOTS];       /* bit 1: a copy-out into the slot's mirror has been issued (slot_ready is valid) */
     uint32_t slot_qgen[H264_MAX_SLOTS];       /* pictures handed over (queued) into the slot so far */
     uint32_t slot_lgen[H264_MAX_SLOTS];       /* generation of the last LAUNCHED picture of the slot */
-    PicBuf bufs[NBUF];
+    uint32_t slot_popped[H264_MAX_SLOTS];     /* newest generation of the slot handed out through frame_host_async */
+    std::atomic<uint32_t> slot_released[H264_MAX_SLOTS];   /* newest generation the caller is done with (h264b200PictureRelease) */
+    PicBuf *bufs; int n_bufs;
     int next_buf;
     int batched;
-    int queued;                               /* pictures of this instance waiting in the engine queue */
+    int dev_parse;                            /* slice data parsed by kernel Kp */
+    std::deque<PicBuf *> *fifo;               /* pictures handed over, oldest first; one per round is launched (engine mutex) */
+    std::atomic<uint32_t> n_pending;          /* == fifo->size(), readable without the mutex */
+    uint8_t *h_blocks, *d_blocks, *d_parse;   /* device-parse: the instance-wide allocations the buffers are slices of */
     /* optional output formatting (K5): cropped RGBA instead of the I420 frame */
     int out_format; int cl, ct, cw, ch;
     uint8_t *d_rgba, *h_rgba; size_t rgba_bytes;
 };
 
-struct Retained {                  /* one batch kept resident for replay */
+struct BatchPlan { bool k1, k2, k3, k3c, k4, k0; uint32_t total_mbs; int max_hm; int n_jobs; };
+
+/* Retained runs (H264B200_ENGINE_RETAIN) keep a TAPE of what was launched — Kp launches and reconstruction rounds, in
+ * host order, with their inputs resident in HBM — so that h264b200EngineReplay can re-run the device work alone. */
+struct Retained {
+    int kind;                      /* 0: reconstruction round, 1: Kp launch */
+    std::vector<void *> owned;     /* device allocations of this entry */
+    cudaEvent_t ev;                /* recorded after the entry's work, every time it runs */
+    uint32_t n_pics;
+    /* round */
     std::vector<PicJob> jobs;      /* host copy */
     PicJob *d_jobs;
-    std::vector<void *> owned;     /* device allocations of this batch */
     Batch batch;
     size_t ctrl_words;
-    bool k1, k2, k3, k4;
-    uint64_t bytes[4];             /* algorithmic bytes per kernel family */
-    uint32_t n_pics;
+    BatchPlan pl;
+    std::vector<int> wait_parse;   /* tape indices of the Kp launches that produce this round's records */
+    unsigned long long *d_bytes;   /* algorithmic bytes per kernel family, counted on the device after the live run */
+    uint64_t bytes[4]; bool bytes_read;
+    /* Kp launch */
+    KpBatch kp; int stream;
+    int wait_round;                /* tape index of the last round that read a parse buffer this launch overwrites, -1: none */
+    uint64_t kp_in_bytes, kp_rec_bytes;
+    std::vector<int> rounds;       /* tape indices of the rounds that consume this launch (for its slot bytes) */
 };
 
 struct Scratch {
@@ -102,76 +144,101 @@ struct Scratch {
     bool used;
 };
 
+struct ParseScratch {              /* one Kp launch */
+    KpPic *h_pics, *d_pics;
+    uint32_t cap;
+    uint32_t *d_ticket;
+    cudaEvent_t done;              /* the launch has finished */
+    bool used;
+};
+
 struct h264b200_engine {
     int device, sm_count;
-    cudaStream_t s_h2d, s_comp, s_d2h;
-    cudaEvent_t ev_h2d, ev_comp, ev_rep0, ev_rep1;
+    cudaStream_t s_h2d, s_comp, s_d2h, s_parse[2];
+    cudaEvent_t ev_h2d, ev_comp, ev_rep0, ev_rep1, ev_gate;
     std::mutex mu;
-    std::vector<PicBuf *> queue;
     std::vector<Inst *> insts;
     std::vector<Inst *> zombies;   /* shut-down instances whose frame pools retained batches still name */
     std::vector<Inst *> pool;      /* shut-down instances kept for reuse: pinned + device allocation is slow */
+    std::vector<PicBuf *> tmp_parse, tmp_round;
     Scratch scr[NSCR];
     int next_scr;
+    ParseScratch pscr[NPAR];
+    int next_pscr;
+    uint32_t parse_seq;
+    KpTables *d_tables;
+    uint32_t window, parse_threshold;
     uint32_t *d_err, *h_err;
     unsigned long long *d_trace; int trace_left;
     h264b200_stats_t st;
     uint32_t flags;                /* H264B200_ENGINE_* */
     std::vector<Retained *> retained;
     /* per-kernel timing of replays */
-    std::vector<cudaEvent_t> tev;  /* 5 events per replayed batch */
-    std::vector<int> tev_batch;
-    double k_ms[4]; uint64_t k_bytes[4]; uint64_t k_launches[4];
+    std::vector<cudaEvent_t> tev;  /* rounds: 5 events, Kp launches: 2 events per timed tape entry */
+    std::vector<int> tev_entry;
+    double k_ms[5]; uint64_t k_bytes[5]; uint64_t k_launches[5];
     h264_backend_t be;
 };
 
 /* ----------------------------------------------------------------- helpers */
 static void set_device(h264b200_engine *e) { cudaSetDevice(e->device); }
 
-static int picbuf_alloc(PicBuf *p, Inst *in, uint32_t coef_cap)
+static size_t parse_bytes_per_buf(uint32_t n_mbs)
+{
+    /* records | contexts | result | coefficient slots (worst case) */
+    return (size_t)n_mbs * (sizeof(h264b200_mb_t) + sizeof(KpMbCtx)) + 256 + (size_t)KP_COEF_CAP(n_mbs) * 32;
+}
+static uint32_t block_cap0(uint32_t n_mbs) { return (n_mbs * 48u + 4096u + 255u) & ~255u; }
+
+static int picbuf_alloc_host(PicBuf *p, Inst *in, uint32_t coef_cap)
 {
     memset(p, 0, sizeof *p);
-    p->inst = in;
+    p->inst = in; p->tape_parse = p->tape_last_round = -1;
     const size_t rec_bytes = (size_t)in->n_mbs * sizeof(h264b200_mb_t);
     CUDA_TRY(cudaHostAlloc((void **)&p->in.mbs, rec_bytes + (size_t)coef_cap * 32, cudaHostAllocDefault), return -1);
     p->in.coef = (int16_t *)((uint8_t *)p->in.mbs + rec_bytes);
     CUDA_TRY(cudaMalloc((void **)&p->d_mbs, rec_bytes + (size_t)coef_cap * 32), return -1);
     p->d_coef = (int16_t *)((uint8_t *)p->d_mbs + rec_bytes);
     p->in.coef_cap = coef_cap; p->d_coef_cap = coef_cap;
+    p->own_host = p->own_dev = 1;
     p->in.priv = p;
     return 0;
 }
 static void picbuf_free(PicBuf *p)
 {
-    if (p->in.mbs) cudaFreeHost(p->in.mbs);
-    if (p->d_mbs) cudaFree(p->d_mbs);
+    if (p->own_host && p->in.mbs) cudaFreeHost(p->in.mbs);
+    if (p->own_host && p->in.block) cudaFreeHost(p->in.block);
+    if (p->own_dev && p->d_mbs) cudaFree(p->d_mbs);
+    if (p->own_dblock && p->d_block) cudaFree(p->d_block);
     memset(p, 0, sizeof *p);
 }
 
-/* algorithmic bytes of one picture per kernel family, as SURVEY.md 8(d) defines them */
-static void count_bytes(const h264_pic_input_t *pic, uint32_t n_mbs, uint64_t out[4])
-{
-    uint64_t inter = 0, intra = 0, blocks = 0, dc = 0, blk_inter = 0, blk_intra = 0, dbk = 0;
-    for (uint32_t i = 0; i < n_mbs; i++) {
-        const h264b200_mb_t *m = &pic->mbs[i];
-        uint32_t nb = (uint32_t)__builtin_popcount(m->resid_mask & 0xffffffu), nd = (uint32_t)__builtin_popcount(m->resid_mask >> 24);
-        if (m->mb_class == H264B200_MB_MISSING) continue;
-        if (m->mb_class == H264B200_MB_INTER) { inter++; blk_inter += nb; } else { intra++; blk_intra += nb; if (m->mb_class == H264B200_MB_IPCM) blk_intra += 12; }
-        blocks += nb; dc += nd;
-        if (m->dbk_flags) dbk++;
-    }
-    out[0] = blocks * 64 + dc * 64;                         /* K1: 32 B in + 32 B out per coded block / DC block */
-    out[1] = inter * (384 + 384 + 128) + blk_inter * 32;    /* K2 */
-    out[2] = intra * (384 + 64 + 128) + blk_intra * 32;     /* K3 */
-    out[3] = dbk * (384 + 384 + 128);                       /* K4 */
-}
-
 /* ------------------------------------------------------------ kernel launch */
-struct BatchPlan { bool k1, k2, k3, k3c, k4; uint32_t total_mbs; int max_hm; int n_jobs; };
+/* algorithmic bytes of a batch per kernel family, as SURVEY.md 8(d) defines them; runs once per retained round, outside
+ * any timed region (the records of a device-parsed picture only exist on the device) */
+__global__ void k_count_bytes(Batch b, unsigned long long *out)
+{
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= b.total_mbs) return;
+    const PicJob &job = b.jobs[find_job(b, g)];
+    const h264b200_mb_t *m = job.mbs + (g - job.mb_base);
+    const uint32_t nb = __popc(m->resid_mask & 0xffffffu), nd = __popc(m->resid_mask >> 24);
+    if (m->mb_class == H264B200_MB_MISSING) return;
+    unsigned long long k1 = (unsigned long long)(nb + nd) * 64, k2 = 0, k3 = 0, k4 = 0;
+    if (m->mb_class == H264B200_MB_INTER) k2 = 896 + nb * 32;
+    else k3 = 576 + (nb + (m->mb_class == H264B200_MB_IPCM ? 12 : 0)) * 32;
+    if (m->dbk_flags) k4 = 896;
+    for (int o = 16; o; o >>= 1) {
+        k1 += __shfl_down_sync(0xffffffffu, k1, o); k2 += __shfl_down_sync(0xffffffffu, k2, o);
+        k3 += __shfl_down_sync(0xffffffffu, k3, o); k4 += __shfl_down_sync(0xffffffffu, k4, o);
+    }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(out, k1); atomicAdd(out + 1, k2); atomicAdd(out + 2, k3); atomicAdd(out + 3, k4); }
+}
 
 static void launch_kernels(h264b200_engine *e, const Batch &b, const BatchPlan &pl, cudaEvent_t *tev)
 {
     cudaStream_t s = e->s_comp;
+    if (pl.k0) { k0_jobs<<<(pl.n_jobs + 127) / 128, 128, 0, s>>>(const_cast<PicJob *>(b.jobs), pl.n_jobs); e->st.kernel_launches++; }
     if (tev) cudaEventRecord(tev[0], s);
     if (pl.k1) { uint32_t blocks = (pl.total_mbs * 8 + 255) / 256; k1_transform<<<blocks, 256, 0, s>>>(b); e->st.kernel_launches++; }   /* 8 lanes per macroblock */
     if (tev) cudaEventRecord(tev[1], s);
@@ -193,93 +260,200 @@ static void launch_kernels(h264b200_engine *e, const Batch &b, const BatchPlan &
     if (tev) cudaEventRecord(tev[4], s);
 }
 
-/* ------------------------------------------------------------------ submit */
-/* engine mutex held.  Launch every queued picture as one batch. */
-static uint32_t submit_locked(h264b200_engine *e)
+static uint32_t kp_grid(h264b200_engine *e, uint32_t n_pics)
 {
-    uint32_t n = (uint32_t)e->queue.size();
-    if (!n) return 0;
-    set_device(e);
+    uint32_t blocks = (n_pics + KP_WARPS - 1) / KP_WARPS, cap = (uint32_t)e->sm_count * KP_MINB;
+    return blocks < cap ? blocks : cap;
+}
+
+/* ------------------------------------------------------------------ Kp launch */
+/* engine mutex held.  Copy the blocks of the given queued pictures to the device and parse them all in one launch. */
+static int launch_parse(h264b200_engine *e, std::vector<PicBuf *> &list)
+{
+    const uint32_t n = (uint32_t)list.size();
     const bool retain = (e->flags & H264B200_ENGINE_RETAIN) != 0;
-    Retained *ret = retain ? new Retained() : nullptr;
+    ParseScratch &ps = e->pscr[e->next_pscr];
+    const int stream = e->next_pscr & 1;
+    e->next_pscr = (e->next_pscr + 1) % NPAR;
+    if (ps.used) cudaEventSynchronize(ps.done);
+    if (ps.cap < n) {
+        if (ps.h_pics) cudaFreeHost(ps.h_pics);
+        if (ps.d_pics) cudaFree(ps.d_pics);
+        ps.cap = n + 64;
+        CUDA_TRY(cudaHostAlloc((void **)&ps.h_pics, ps.cap * sizeof(KpPic), cudaHostAllocDefault), return -1);
+        CUDA_TRY(cudaMalloc((void **)&ps.d_pics, ps.cap * sizeof(KpPic)), return -1);
+    }
+    Retained *ret = nullptr;
+    KpPic *d_pics = ps.d_pics; uint32_t *d_ticket = ps.d_ticket;
+    if (retain) {
+        ret = new Retained();
+        ret->kind = 1; ret->stream = stream; ret->wait_round = -1; ret->n_pics = n; ret->d_jobs = nullptr; ret->d_bytes = nullptr;
+        ret->kp_in_bytes = ret->kp_rec_bytes = 0; ret->bytes_read = false;
+        CUDA_TRY(cudaEventCreateWithFlags(&ret->ev, cudaEventDisableTiming), return -1);
+        CUDA_TRY(cudaMalloc((void **)&d_pics, n * sizeof(KpPic)), return -1);
+        ret->owned.push_back(d_pics);
+        CUDA_TRY(cudaMalloc((void **)&d_ticket, 64), return -1);
+        ret->owned.push_back(d_ticket);
+    }
+    e->parse_seq++;
+    if (!e->parse_seq) e->parse_seq = 1;
+    uint64_t in_bytes = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        PicBuf *p = list[i]; Inst *in = p->inst; h264_pic_input_t *pic = &p->in;
+        uint8_t *d_block = p->d_block;
+        if (retain) {              /* the block stays resident for the replay */
+            void *a = nullptr;
+            CUDA_TRY(cudaMalloc(&a, pic->block_used), return -1);
+            ret->owned.push_back(a);
+            d_block = (uint8_t *)a;
+            if (p->tape_last_round > ret->wait_round) ret->wait_round = p->tape_last_round;
+            p->tape_parse = (int)e->retained.size();
+            ret->kp_in_bytes += pic->block_used; ret->kp_rec_bytes += (uint64_t)in->n_mbs * sizeof(h264b200_mb_t);
+        } else if (p->d_block_cap < pic->block_used) {
+            /* no earlier launch reads this buffer's block any more (pic_begin waited for `done`) */
+            if (p->own_dblock) cudaFree(p->d_block);
+            p->d_block_cap = pic->block_cap; p->own_dblock = 1;
+            CUDA_TRY(cudaMalloc((void **)&p->d_block, p->d_block_cap), return -1);
+            d_block = p->d_block;
+        }
+        CUDA_TRY(cudaMemcpyAsync(d_block, pic->block, pic->block_used, cudaMemcpyHostToDevice, e->s_h2d), return -1);
+        in_bytes += pic->block_used;
+        KpPic &kp = ps.h_pics[i];
+        kp.block = d_block; kp.mbs = p->d_mbs; kp.coef = p->d_coef; kp.ctx = p->d_ctx; kp.coef_cap = p->d_coef_cap; kp.pad = 0; kp.res = p->d_res;
+        p->parsed = retain ? ret->ev : ps.done;
+        p->parse_seq = e->parse_seq;
+    }
+    e->st.h2d_bytes += in_bytes;
+    cudaStream_t s = e->s_parse[stream];
+    cudaEventRecord(e->ev_h2d, e->s_h2d);
+    cudaStreamWaitEvent(s, e->ev_h2d, 0);
+    cudaMemcpyAsync(d_pics, ps.h_pics, n * sizeof(KpPic), cudaMemcpyHostToDevice, s);
+    cudaMemsetAsync(d_ticket, 0, 64, s);
+    KpBatch kb; kb.pics = d_pics; kb.n_pics = n; kb.ticket = d_ticket; kb.tables = e->d_tables;
+    kp_parse<<<kp_grid(e, n), KP_WARPS * 32, 0, s>>>(kb);
+    e->st.kernel_launches++; e->st.kp_launches++; e->st.kp_pictures += n;
+    cudaEventRecord(ps.done, s); ps.used = true;
+    if (retain) {
+        cudaEventRecord(ret->ev, s);
+        ret->kp = kb;
+        e->retained.push_back(ret);
+    }
+    cudaError_t le = cudaGetLastError();
+    if (le != cudaSuccess) { fprintf(stderr, "h264b200: Kp launch failed: %s\n", cudaGetErrorString(le)); return -1; }
+    return 0;
+}
+
+/* ------------------------------------------------------------------ round launch */
+/* engine mutex held.  Reconstruct the given pictures (at most one per instance) as one batch. */
+static uint32_t launch_round(h264b200_engine *e, std::vector<PicBuf *> &list)
+{
+    uint32_t n = (uint32_t)list.size();
+    if (!n) return 0;
+    const bool retain = (e->flags & H264B200_ENGINE_RETAIN) != 0;
+    Retained *ret = nullptr;
     Scratch &sc = e->scr[e->next_scr];
     e->next_scr = (e->next_scr + 1) % NSCR;
     if (sc.used) cudaEventSynchronize(sc.done);
     size_t ctrl_words = CTRL_HEAD;
-    for (PicBuf *p : e->queue) ctrl_words += 2 * (size_t)p->inst->hm;
+    for (PicBuf *p : list) ctrl_words += 2 * (size_t)p->inst->hm;
     if (sc.cap_jobs < n) {
         if (sc.h_jobs) cudaFreeHost(sc.h_jobs);
         if (sc.d_jobs) cudaFree(sc.d_jobs);
+        sc.h_jobs = nullptr; sc.d_jobs = nullptr;
         sc.cap_jobs = n + 16;
-        CUDA_TRY(cudaHostAlloc((void **)&sc.h_jobs, sc.cap_jobs * sizeof(PicJob), cudaHostAllocDefault), return 0);
-        CUDA_TRY(cudaMalloc((void **)&sc.d_jobs, sc.cap_jobs * sizeof(PicJob)), return 0);
+        CUDA_TRY(cudaHostAlloc((void **)&sc.h_jobs, sc.cap_jobs * sizeof(PicJob), cudaHostAllocDefault), { sc.cap_jobs = 0; goto fail; });
+        CUDA_TRY(cudaMalloc((void **)&sc.d_jobs, sc.cap_jobs * sizeof(PicJob)), { sc.cap_jobs = 0; goto fail; });
     }
     if (sc.cap_ctrl < ctrl_words) {
         if (sc.d_ctrl) cudaFree(sc.d_ctrl);
+        sc.d_ctrl = nullptr;
         sc.cap_ctrl = ctrl_words + 1024;
-        CUDA_TRY(cudaMalloc((void **)&sc.d_ctrl, sc.cap_ctrl * sizeof(int32_t)), return 0);
+        CUDA_TRY(cudaMalloc((void **)&sc.d_ctrl, sc.cap_ctrl * sizeof(int32_t)), { sc.cap_ctrl = 0; goto fail; });
     }
+    {
     PicJob *d_jobs = sc.d_jobs; int32_t *d_ctrl = sc.d_ctrl;
-    if (retain) {                  /* a retained batch owns its job table and control area */
-        CUDA_TRY(cudaMalloc((void **)&ret->d_jobs, n * sizeof(PicJob)), return 0);
+    if (retain) {                  /* a retained round owns its job table and control area */
+        ret = new Retained();
+        ret->kind = 0; ret->n_pics = n; ret->bytes_read = false; ret->wait_round = -1; ret->d_bytes = nullptr;
+        memset(ret->bytes, 0, sizeof ret->bytes);
+        CUDA_TRY(cudaEventCreateWithFlags(&ret->ev, cudaEventDisableTiming), goto fail);
+        CUDA_TRY(cudaMalloc((void **)&ret->d_jobs, n * sizeof(PicJob)), goto fail);
         ret->owned.push_back(ret->d_jobs);
         d_jobs = ret->d_jobs;
-        CUDA_TRY(cudaMalloc((void **)&d_ctrl, ctrl_words * sizeof(int32_t)), return 0);
+        CUDA_TRY(cudaMalloc((void **)&d_ctrl, ctrl_words * sizeof(int32_t)), goto fail);
         ret->owned.push_back(d_ctrl);
+        CUDA_TRY(cudaMalloc((void **)&ret->d_bytes, 4 * sizeof(unsigned long long)), goto fail);
+        ret->owned.push_back(ret->d_bytes);
     }
 
     BatchPlan pl; memset(&pl, 0, sizeof pl);
     uint32_t mb_base = 0; size_t prog_off = CTRL_HEAD;
-    uint64_t bytes[4] = {0, 0, 0, 0};
+    uint32_t last_parse_seq = 0;
     for (uint32_t i = 0; i < n; i++) {
-        PicBuf *p = e->queue[i]; Inst *in = p->inst; h264_pic_input_t *pic = &p->in;
+        PicBuf *p = list[i]; Inst *in = p->inst; h264_pic_input_t *pic = &p->in;
         h264b200_mb_t *d_mbs = p->d_mbs; int16_t *d_coef_in = p->d_coef, *d_coef = p->d_coef;
-        size_t coef_bytes = (size_t)pic->coef_used * 32;
-        const size_t rec_bytes = (size_t)in->n_mbs * sizeof(h264b200_mb_t);
-        if (retain) {                                          /* [records | levels] and a separate residual buffer, kept */
-            void *a = nullptr, *c = nullptr;
-            CUDA_TRY(cudaMalloc(&a, rec_bytes + coef_bytes + 32), return 0);
-            CUDA_TRY(cudaMalloc(&c, coef_bytes + 32), return 0);
-            ret->owned.push_back(a); ret->owned.push_back(c);
-            d_mbs = (h264b200_mb_t *)a; d_coef_in = (int16_t *)((uint8_t *)a + rec_bytes); d_coef = (int16_t *)c;
-        } else if (p->d_coef_cap < pic->coef_used) {          /* the host side grew: follow */
-            /* no earlier batch reads this ring slot any more (pic_begin waited for `done`), so it can be replaced */
-            cudaFree(p->d_mbs);
-            p->d_coef_cap = pic->coef_cap;
-            CUDA_TRY(cudaMalloc((void **)&p->d_mbs, rec_bytes + (size_t)p->d_coef_cap * 32), return 0);
-            p->d_coef = (int16_t *)((uint8_t *)p->d_mbs + rec_bytes);
-            d_mbs = p->d_mbs; d_coef_in = d_coef = p->d_coef;
-        }
-        /* records and coefficient slots are adjacent on both sides: one copy */
-        CUDA_TRY(cudaMemcpyAsync(d_mbs, pic->mbs, rec_bytes + coef_bytes, cudaMemcpyHostToDevice, e->s_h2d), return 0);
-        e->st.h2d_bytes += rec_bytes + coef_bytes;
-
         PicJob &j = sc.h_jobs[i];
+        memset(&j, 0, sizeof j);
+        if (in->dev_parse) {
+            /* records and slots are where kernel Kp left them; its launch must have finished */
+            if (p->parse_seq != last_parse_seq) { cudaStreamWaitEvent(e->s_comp, p->parsed, 0); last_parse_seq = p->parse_seq; }
+            j.kp_res = p->d_res;
+            pl.k0 = pl.k1 = pl.k3 = pl.k3c = pl.k4 = true;
+            if (pic->has_p_slice) pl.k2 = true;
+            if (retain) {
+                bool seen = false;
+                for (int w : ret->wait_parse) if (w == p->tape_parse) seen = true;
+                if (!seen && p->tape_parse >= 0) { ret->wait_parse.push_back(p->tape_parse); e->retained[(size_t)p->tape_parse]->rounds.push_back((int)e->retained.size()); }
+                p->tape_last_round = (int)e->retained.size();
+            }
+        } else {
+            size_t coef_bytes = (size_t)pic->coef_used * 32;
+            const size_t rec_bytes = (size_t)in->n_mbs * sizeof(h264b200_mb_t);
+            if (retain) {                                          /* [records | levels] and a separate residual buffer, kept */
+                void *a = nullptr, *c = nullptr;
+                CUDA_TRY(cudaMalloc(&a, rec_bytes + coef_bytes + 32), goto fail);
+                ret->owned.push_back(a);
+                CUDA_TRY(cudaMalloc(&c, coef_bytes + 32), goto fail);
+                ret->owned.push_back(c);
+                d_mbs = (h264b200_mb_t *)a; d_coef_in = (int16_t *)((uint8_t *)a + rec_bytes); d_coef = (int16_t *)c;
+            } else if (p->d_coef_cap < pic->coef_used) {          /* the host side grew: follow */
+                /* no earlier batch reads this ring slot any more (pic_begin waited for `done`), so it can be replaced */
+                cudaFree(p->d_mbs);
+                p->d_mbs = nullptr;
+                p->d_coef_cap = pic->coef_cap;
+                CUDA_TRY(cudaMalloc((void **)&p->d_mbs, rec_bytes + (size_t)p->d_coef_cap * 32), goto fail);
+                p->d_coef = (int16_t *)((uint8_t *)p->d_mbs + rec_bytes);
+                d_mbs = p->d_mbs; d_coef_in = d_coef = p->d_coef;
+            }
+            /* records and coefficient slots are adjacent on both sides: one copy */
+            CUDA_TRY(cudaMemcpyAsync(d_mbs, pic->mbs, rec_bytes + coef_bytes, cudaMemcpyHostToDevice, e->s_h2d), goto fail);
+            e->st.h2d_bytes += rec_bytes + coef_bytes;
+            j.n_intra = pic->n_intra; j.n_inter = pic->n_inter; j.any_deblock = pic->any_deblock;
+            j.n_conceal = pic->n_conceal;
+            j.conceal_list = reinterpret_cast<const uint32_t *>(d_coef_in + (size_t)pic->conceal_offset * 16);
+            if (pic->n_conceal) pl.k3c = true;
+            if (pic->coef_used) pl.k1 = true;
+            if (pic->n_inter) pl.k2 = true;
+            if (pic->n_intra) pl.k3 = true;
+            if (pic->any_deblock) pl.k4 = true;
+        }
         j.mbs = d_mbs; j.coef_in = d_coef_in; j.coef = d_coef;
-        j.cur = in->d_frames + (size_t)pic->cur_slot * in->frame_bytes;
-        j.frames = in->d_frames; j.frame_bytes = (uint32_t)in->frame_bytes;
+        j.cur = in->d_frames + (size_t)pic->cur_slot * in->frame_stride;
+        j.frames = in->d_frames; j.frame_bytes = (uint32_t)in->frame_stride;
+        j.stat_off = (uint32_t)in->frame_bytes;
         j.wm = (int32_t)in->wm; j.hm = (int32_t)in->hm;
         j.progress = d_ctrl + prog_off; prog_off += 2 * (size_t)in->hm;
-        j.n_intra = pic->n_intra; j.n_inter = pic->n_inter; j.any_deblock = pic->any_deblock;
         j.mb_base = mb_base; mb_base += in->n_mbs;
-        j.n_conceal = pic->n_conceal;
-        j.conceal_list = reinterpret_cast<const uint32_t *>(d_coef_in + (size_t)pic->conceal_offset * 16);
-        if (pic->n_conceal) pl.k3c = true;
-        if (pic->coef_used) pl.k1 = true;
-        if (pic->n_inter) pl.k2 = true;
-        if (pic->n_intra) pl.k3 = true;
-        if (pic->any_deblock) pl.k4 = true;
         if ((int)in->hm > pl.max_hm) pl.max_hm = (int)in->hm;
         /* the frame being written may still be on its way to the host from an earlier batch */
         if (in->slot_flags[pic->cur_slot] & 2) cudaStreamWaitEvent(e->s_comp, in->slot_ready[pic->cur_slot], 0);
-        if (retain) { uint64_t bb[4]; count_bytes(pic, in->n_mbs, bb); for (int k = 0; k < 4; k++) bytes[k] += bb[k]; }
     }
     pl.total_mbs = mb_base; pl.n_jobs = (int)n;
 
     Batch b;
     b.jobs = d_jobs; b.n_jobs = (int32_t)n; b.max_hm = pl.max_hm; b.total_mbs = mb_base;
-    b.uniform_mbs = e->queue[0]->inst->n_mbs;
-    for (PicBuf *p : e->queue) if (p->inst->n_mbs != b.uniform_mbs) b.uniform_mbs = 0;
+    b.uniform_mbs = list[0]->inst->n_mbs;
+    for (PicBuf *p : list) if (p->inst->n_mbs != b.uniform_mbs) b.uniform_mbs = 0;
     b.tickets = (uint32_t *)d_ctrl; b.error_flags = e->d_err; b.trace = e->trace_left > 0 ? e->d_trace : nullptr;
 
     cudaEventRecord(e->ev_h2d, e->s_h2d);
@@ -287,12 +461,17 @@ static uint32_t submit_locked(h264b200_engine *e)
     cudaMemcpyAsync(d_jobs, sc.h_jobs, n * sizeof(PicJob), cudaMemcpyHostToDevice, e->s_comp);
     cudaMemsetAsync(d_ctrl, 0, ctrl_words * sizeof(int32_t), e->s_comp);
     launch_kernels(e, b, pl, nullptr);
+    if (retain) {
+        cudaMemsetAsync(ret->d_bytes, 0, 4 * sizeof(unsigned long long), e->s_comp);
+        k_count_bytes<<<(mb_base + 255) / 256, 256, 0, e->s_comp>>>(b, ret->d_bytes);
+    }
     if (b.trace) {                 /* debug: dump the wavefront timing of job 0 of this batch */
+        const int rows = sc.h_jobs[0].hm < 512 ? sc.h_jobs[0].hm : 512;
         std::vector<unsigned long long> h(256 + 4 * 512);
         cudaStreamSynchronize(e->s_comp);
         cudaMemcpy(h.data(), e->d_trace, h.size() * 8, cudaMemcpyDeviceToHost);
         fprintf(stderr, "h264b200 trace: batch of %u, job0 %dx%d MBs; per row: start, first-mb, mid, end (us from row 0 start)\n", n, sc.h_jobs[0].wm, sc.h_jobs[0].hm);
-        for (int r = 0; r < sc.h_jobs[0].hm; r++) { const unsigned long long *q = &h[256 + r * 4], t0 = h[256];
+        for (int r = 0; r < rows; r++) { const unsigned long long *q = &h[256 + r * 4], t0 = h[256];
             fprintf(stderr, "  row %2d: %8.1f %8.1f %8.1f %8.1f\n", r, (q[0] - t0) / 1e3, (q[1] - t0) / 1e3, (q[2] - t0) / 1e3, (q[3] - t0) / 1e3); }
         cudaMemset(e->d_trace, 0, h.size() * 8);
         e->trace_left--;
@@ -301,43 +480,97 @@ static uint32_t submit_locked(h264b200_engine *e)
     cudaEventRecord(e->ev_comp, e->s_comp);
     cudaStreamWaitEvent(e->s_d2h, e->ev_comp, 0);
     for (uint32_t i = 0; i < n; i++) {
-        PicBuf *p = e->queue[i]; Inst *in = p->inst; int slot = p->in.cur_slot;
+        PicBuf *p = list[i]; Inst *in = p->inst; int slot = p->in.cur_slot;
+        uint8_t *d_frame = in->d_frames + (size_t)slot * in->frame_stride, *h_frame = in->h_frames + (size_t)slot * in->frame_stride;
         p->done = sc.done;
         p->state = 3;
         if (in->out_format == H264B200_OUT_RGBA && in->d_rgba) {
             /* K5 runs on the copy-out stream: it only reads the finished frame */
-            RgbaJob rj; rj.frame = in->d_frames + (size_t)slot * in->frame_bytes; rj.out = in->d_rgba + (size_t)slot * in->rgba_bytes;
+            RgbaJob rj; rj.frame = d_frame; rj.out = in->d_rgba + (size_t)slot * in->rgba_bytes;
             rj.W = (int)in->wm * 16; rj.H = (int)in->hm * 16; rj.cl = in->cl; rj.ct = in->ct; rj.cw = in->cw; rj.ch = in->ch;
             const int items = ((rj.cw + 3) / 4) * ((rj.ch + 1) / 2);
             k5_rgba<<<(items + 255) / 256, 256, 0, e->s_d2h>>>(rj); e->st.kernel_launches++;
             if (!(e->flags & H264B200_ENGINE_NO_D2H)) {
                 cudaMemcpyAsync(in->h_rgba + (size_t)slot * in->rgba_bytes, rj.out, in->rgba_bytes, cudaMemcpyDeviceToHost, e->s_d2h);
+                cudaMemcpyAsync(h_frame + in->frame_bytes, d_frame + in->frame_bytes, sizeof(h264b200_picstat_t), cudaMemcpyDeviceToHost, e->s_d2h);
                 e->st.d2h_bytes += in->rgba_bytes;
             }
         } else if (!(e->flags & H264B200_ENGINE_NO_D2H)) {
-            cudaMemcpyAsync(in->h_frames + (size_t)slot * in->frame_bytes, in->d_frames + (size_t)slot * in->frame_bytes,
-                            in->frame_bytes, cudaMemcpyDeviceToHost, e->s_d2h);
+            /* the frame and the status words behind it: one copy */
+            cudaMemcpyAsync(h_frame, d_frame, in->frame_bytes + sizeof(h264b200_picstat_t), cudaMemcpyDeviceToHost, e->s_d2h);
             e->st.d2h_bytes += in->frame_bytes;
         }
         in->slot_ready[slot] = sc.d2h_done;
-        in->slot_flags[slot] = 2; in->slot_lgen[slot] = in->slot_qgen[slot];
-        in->queued--;
+        in->slot_flags[slot] = 2; in->slot_lgen[slot]++;
     }
     cudaMemcpyAsync(e->h_err, e->d_err, sizeof(uint32_t), cudaMemcpyDeviceToHost, e->s_d2h);
     cudaEventRecord(sc.d2h_done, e->s_d2h);
     e->st.pictures += n; e->st.batches++;
     if (retain) {
+        cudaEventRecord(ret->ev, e->s_comp);
         ret->jobs.assign(sc.h_jobs, sc.h_jobs + n);
         ret->batch = b; ret->batch.trace = nullptr; ret->ctrl_words = ctrl_words;
-        ret->k1 = pl.k1; ret->k2 = pl.k2; ret->k3 = pl.k3; ret->k4 = pl.k4;
-        for (int k = 0; k < 4; k++) ret->bytes[k] = bytes[k];
-        ret->n_pics = n;
+        ret->pl = pl;
         e->retained.push_back(ret);
+        ret = nullptr;
     }
-    e->queue.clear();
     cudaError_t le = cudaGetLastError();
     if (le != cudaSuccess) fprintf(stderr, "h264b200: kernel launch failed: %s\n", cudaGetErrorString(le));
     return n;
+    }
+fail:
+    /* an allocation or copy failed before anything of this round was launched: give the buffers back and remember the
+     * failure per instance (frame_host then returns NULL for it) instead of leaving them queued */
+    if (ret) { for (void *q : ret->owned) cudaFree(q); delete ret; }
+    for (PicBuf *p : list) { p->state = 0; p->inst->slot_lgen[p->in.cur_slot]++; p->inst->slot_flags[p->in.cur_slot] |= 4; }
+    return 0;
+}
+
+/* ------------------------------------------------------------------ scheduling */
+static bool gated(const PicBuf *p)
+{
+    const Inst *in = p->inst;
+    return (int32_t)(in->slot_released[p->in.cur_slot].load(std::memory_order_acquire) - p->gate_gen) < 0;
+}
+
+/* engine mutex held.  One scheduling step: Kp over the queued device-parse pictures when it pays (or must happen), then
+ * one reconstruction round over the oldest queued picture of every instance. */
+static uint32_t advance_locked(h264b200_engine *e, bool force)
+{
+    set_device(e);
+    std::vector<PicBuf *> &pl = e->tmp_parse; pl.clear();
+    bool head_unparsed = false;
+    for (Inst *in : e->insts) {
+        if (!in->dev_parse || in->fifo->empty()) continue;
+        bool first = true;
+        for (PicBuf *p : *in->fifo) {
+            if (!p->parse_seq) { pl.push_back(p); if (first && !gated(p)) head_unparsed = true; }
+            first = false;
+        }
+    }
+    if (!pl.empty() && (force || head_unparsed || pl.size() >= e->parse_threshold)) {
+        if (launch_parse(e, pl)) {
+            for (PicBuf *p : pl) p->inst->slot_flags[p->in.cur_slot] |= 4;
+        }
+    }
+    std::vector<PicBuf *> &rl = e->tmp_round; rl.clear();
+    for (Inst *in : e->insts) {
+        if (in->fifo->empty()) continue;
+        PicBuf *p = in->fifo->front();
+        if (in->dev_parse && !p->parse_seq) continue;
+        if (gated(p)) continue;
+        rl.push_back(p);
+    }
+    if (rl.empty()) return 0;
+    for (PicBuf *p : rl) { p->inst->fifo->pop_front(); p->inst->n_pending.fetch_sub(1, std::memory_order_release); }
+    launch_round(e, rl);
+    return (uint32_t)rl.size();
+}
+static uint32_t advance_all_locked(h264b200_engine *e)
+{
+    uint32_t total = 0, n;
+    while ((n = advance_locked(e, true)) != 0) total += n;
+    return total;
 }
 
 /* ------------------------------------------------------- backend callbacks */
@@ -347,31 +580,66 @@ static void *be_inst_create(h264_backend_t *be, uint32_t wm, uint32_t hm, uint32
     h264b200_engine *e = (h264b200_engine *)be->ctx;
     if (n_slots > H264_MAX_SLOTS) return NULL;
     set_device(e);
+    const int dev_parse = (e->flags & H264B200_ENGINE_DEVICE_PARSE) != 0;
+    const int n_bufs = dev_parse ? (int)e->window + 2 : NBUF;
     {   /* reuse a pooled instance of the same geometry */
         std::lock_guard<std::mutex> lk(e->mu);
         for (size_t i = 0; i < e->pool.size(); i++) {
             Inst *c = e->pool[i];
-            if (c->wm == wm && c->hm == hm && c->n_slots == n_slots) {
+            if (c->wm == wm && c->hm == hm && c->n_slots == n_slots && c->dev_parse == dev_parse && c->n_bufs == n_bufs) {
                 e->pool.erase(e->pool.begin() + i);
                 memset(c->slot_flags, 0, sizeof c->slot_flags); memset(c->slot_qgen, 0, sizeof c->slot_qgen); memset(c->slot_lgen, 0, sizeof c->slot_lgen);
-                c->next_buf = 0; c->queued = 0; c->out_format = H264B200_OUT_I420;
+                memset(c->slot_popped, 0, sizeof c->slot_popped);
+                for (int k = 0; k < H264_MAX_SLOTS; k++) c->slot_released[k].store(0);
+                c->next_buf = 0; c->out_format = H264B200_OUT_I420;
                 c->batched = (e->flags & H264B200_ENGINE_BATCHED) != 0;
-                for (int k = 0; k < NBUF; k++) c->bufs[k].state = 0;
+                for (int k = 0; k < c->n_bufs; k++) { c->bufs[k].state = 0; c->bufs[k].parse_seq = 0; c->bufs[k].tape_parse = c->bufs[k].tape_last_round = -1; }
+                /* a new stream must not start on the previous stream's samples (they would show through MISSING
+                 * macroblocks and through frame_host of a slot nothing was decoded into) */
+                cudaMemsetAsync(c->d_frames, 0, c->frame_stride * c->n_slots, e->s_comp);
+                memset(c->h_frames, 0, c->frame_stride * c->n_slots);
+                if (c->d_rgba) { cudaMemsetAsync(c->d_rgba, 0, c->rgba_bytes * c->n_slots, e->s_comp); memset(c->h_rgba, 0, c->rgba_bytes * c->n_slots); }
                 e->insts.push_back(c);
                 return c;
             }
         }
     }
-    Inst *in = (Inst *)calloc(1, sizeof *in);
-    if (!in) return NULL;
+    Inst *in = new Inst();
     in->e = e; in->wm = wm; in->hm = hm; in->n_mbs = wm * hm; in->n_slots = n_slots;
     in->frame_bytes = (size_t)in->n_mbs * 384;
+    in->frame_stride = in->frame_bytes + STAT_TAIL;
     in->batched = (e->flags & H264B200_ENGINE_BATCHED) != 0;
-    CUDA_TRY(cudaMalloc((void **)&in->d_frames, in->frame_bytes * n_slots), { free(in); return NULL; });
-    CUDA_TRY(cudaMemset(in->d_frames, 0, in->frame_bytes * n_slots), { cudaFree(in->d_frames); free(in); return NULL; });
-    CUDA_TRY(cudaHostAlloc((void **)&in->h_frames, in->frame_bytes * n_slots, cudaHostAllocDefault), { cudaFree(in->d_frames); free(in); return NULL; });
-    memset(in->h_frames, 0, in->frame_bytes * n_slots);
-    for (int i = 0; i < NBUF; i++) if (picbuf_alloc(&in->bufs[i], in, in->n_mbs * 10 + 64)) { inst_free(in); return NULL; }   /* frees what was allocated so far */
+    in->dev_parse = dev_parse; in->n_bufs = n_bufs;
+    in->fifo = new std::deque<PicBuf *>();
+    in->bufs = (PicBuf *)calloc((size_t)n_bufs, sizeof(PicBuf));
+    if (!in->bufs) { inst_free(in); return NULL; }
+    CUDA_TRY(cudaMalloc((void **)&in->d_frames, in->frame_stride * n_slots), { inst_free(in); return NULL; });
+    CUDA_TRY(cudaMemset(in->d_frames, 0, in->frame_stride * n_slots), { inst_free(in); return NULL; });
+    CUDA_TRY(cudaHostAlloc((void **)&in->h_frames, in->frame_stride * n_slots, cudaHostAllocDefault), { inst_free(in); return NULL; });
+    memset(in->h_frames, 0, in->frame_stride * n_slots);
+    if (!dev_parse) {
+        for (int i = 0; i < n_bufs; i++) if (picbuf_alloc_host(&in->bufs[i], in, in->n_mbs * 10 + 64)) { inst_free(in); return NULL; }   /* frees what was allocated so far */
+    } else {
+        /* three allocations per instance: pinned blocks, their device twins, and what kernel Kp writes */
+        const size_t pb = parse_bytes_per_buf(in->n_mbs), cap0 = block_cap0(in->n_mbs);
+        const size_t rec_bytes = (size_t)in->n_mbs * sizeof(h264b200_mb_t), ctx_bytes = (size_t)in->n_mbs * sizeof(KpMbCtx);
+        CUDA_TRY(cudaHostAlloc((void **)&in->h_blocks, cap0 * n_bufs, cudaHostAllocDefault), { inst_free(in); return NULL; });
+        CUDA_TRY(cudaMalloc((void **)&in->d_blocks, cap0 * n_bufs), { inst_free(in); return NULL; });
+        CUDA_TRY(cudaMalloc((void **)&in->d_parse, pb * n_bufs), { inst_free(in); return NULL; });
+        for (int i = 0; i < n_bufs; i++) {
+            PicBuf *p = &in->bufs[i];
+            uint8_t *base = in->d_parse + pb * i;
+            p->inst = in; p->tape_parse = p->tape_last_round = -1;
+            p->in.block = in->h_blocks + cap0 * i; p->in.block_cap = (uint32_t)cap0;
+            p->d_block = in->d_blocks + cap0 * i; p->d_block_cap = (uint32_t)cap0;
+            p->d_mbs = (h264b200_mb_t *)base;
+            p->d_ctx = (KpMbCtx *)(base + rec_bytes);
+            p->d_res = (KpResult *)(base + rec_bytes + ctx_bytes);
+            p->d_coef = (int16_t *)(base + rec_bytes + ctx_bytes + 256);
+            p->d_coef_cap = KP_COEF_CAP(in->n_mbs);
+            p->in.priv = p;
+        }
+    }
     std::lock_guard<std::mutex> lk(e->mu);
     e->insts.push_back(in);
     return in;
@@ -379,10 +647,15 @@ static void *be_inst_create(h264_backend_t *be, uint32_t wm, uint32_t hm, uint32
 
 static void inst_free(Inst *in)
 {
-    for (int i = 0; i < NBUF; i++) picbuf_free(&in->bufs[i]);
-    cudaFree(in->d_frames); cudaFreeHost(in->h_frames);
+    if (in->bufs) { for (int i = 0; i < in->n_bufs; i++) picbuf_free(&in->bufs[i]); free(in->bufs); }
+    if (in->h_blocks) cudaFreeHost(in->h_blocks);
+    if (in->d_blocks) cudaFree(in->d_blocks);
+    if (in->d_parse) cudaFree(in->d_parse);
+    if (in->d_frames) cudaFree(in->d_frames);
+    if (in->h_frames) cudaFreeHost(in->h_frames);
     if (in->d_rgba) { cudaFree(in->d_rgba); cudaFreeHost(in->h_rgba); }
-    free(in);
+    delete in->fifo;
+    delete in;
 }
 
 static void be_inst_destroy(h264_backend_t *be, void *inst)
@@ -391,12 +664,21 @@ static void be_inst_destroy(h264_backend_t *be, void *inst)
     bool keep;
     {
         std::lock_guard<std::mutex> lk(e->mu);
-        if (in->queued) submit_locked(e);
-        keep = !e->retained.empty();           /* retained batches name this instance's frame pool */
+        while (!in->fifo->empty()) {
+            if (!advance_all_locked(e) && !in->fifo->empty()) {
+                /* held back by an output nobody will release any more */
+                for (int k = 0; k < H264_MAX_SLOTS; k++) in->slot_released[k].store(in->slot_popped[k]);
+                if (!advance_all_locked(e)) break;
+            }
+        }
+        while (!in->fifo->empty()) { in->fifo->front()->state = 0; in->fifo->pop_front(); }
+        in->n_pending.store(0);
+        keep = !e->retained.empty();           /* retained batches name this instance's frame pool and parse buffers */
         if (keep) e->zombies.push_back(in);
-        else for (size_t i = 0; i < e->insts.size(); i++) if (e->insts[i] == in) { e->insts.erase(e->insts.begin() + i); break; }
+        for (size_t i = 0; i < e->insts.size(); i++) if (e->insts[i] == in) { e->insts.erase(e->insts.begin() + i); break; }
     }
     set_device(e);
+    cudaStreamSynchronize(e->s_parse[0]); cudaStreamSynchronize(e->s_parse[1]);
     cudaStreamSynchronize(e->s_comp); cudaStreamSynchronize(e->s_d2h);
     if (!keep) { std::lock_guard<std::mutex> lk(e->mu); e->pool.push_back(in); }
 }
@@ -405,10 +687,18 @@ static h264_pic_input_t *be_pic_begin(h264_backend_t *be, void *inst)
 {
     h264b200_engine *e = (h264b200_engine *)be->ctx; Inst *in = (Inst *)inst;
     PicBuf *p = &in->bufs[in->next_buf];
-    in->next_buf = (in->next_buf + 1) % NBUF;
-    if (p->state == 2) { std::lock_guard<std::mutex> lk(e->mu); submit_locked(e); }
+    in->next_buf = (in->next_buf + 1) % in->n_bufs;
+    if (p->state == 2) {           /* the look-ahead ran a whole ring ahead of the launches */
+        std::lock_guard<std::mutex> lk(e->mu);
+        while (p->state == 2) {
+            if (!advance_all_locked(e) && p->state == 2) {
+                for (int k = 0; k < H264_MAX_SLOTS; k++) in->slot_released[k].store(in->slot_popped[k]);
+                if (!advance_all_locked(e)) return NULL;
+            }
+        }
+    }
     if (p->state == 3) { set_device(e); cudaEventSynchronize(p->done); }
-    p->state = 1;
+    p->state = 1; p->parse_seq = 0;
     return &p->in;
 }
 
@@ -418,6 +708,7 @@ static int be_coef_grow(h264_backend_t *be, void *inst, h264_pic_input_t *pic, u
     const size_t rec_bytes = (size_t)in->n_mbs * sizeof(h264b200_mb_t);
     uint32_t cap = pic->coef_cap * 2 > min_slots ? pic->coef_cap * 2 : min_slots;
     uint8_t *n = NULL;
+    if (in->dev_parse) return -1;
     set_device(e);
     CUDA_TRY(cudaHostAlloc((void **)&n, rec_bytes + (size_t)cap * 32, cudaHostAllocDefault), return -1);
     memcpy(n, pic->mbs, rec_bytes + (size_t)pic->coef_used * 32);           /* records written so far and their slots */
@@ -426,26 +717,57 @@ static int be_coef_grow(h264_backend_t *be, void *inst, h264_pic_input_t *pic, u
     return 0;
 }
 
+/* device-parse: room for a longer block (the pinned side; the device twin follows at the Kp launch) */
+static int be_block_grow(h264_backend_t *be, void *inst, h264_pic_input_t *pic, uint32_t min_bytes)
+{
+    h264b200_engine *e = (h264b200_engine *)be->ctx; Inst *in = (Inst *)inst;
+    PicBuf *p = (PicBuf *)pic->priv;
+    if (!in->dev_parse) return -1;
+    uint32_t cap = pic->block_cap * 2 > min_bytes ? pic->block_cap * 2 : min_bytes;
+    cap = (cap + 4095u) & ~4095u;
+    uint8_t *n = NULL;
+    set_device(e);
+    CUDA_TRY(cudaHostAlloc((void **)&n, cap, cudaHostAllocDefault), return -1);
+    if (pic->block && pic->block_used) memcpy(n, pic->block, pic->block_used);
+    if (p->own_host && pic->block) cudaFreeHost(pic->block);
+    pic->block = n; pic->block_cap = cap; p->own_host = 1;
+    return 0;
+}
+
 static int be_pic_submit(h264_backend_t *be, void *inst, h264_pic_input_t *pic)
 {
     h264b200_engine *e = (h264b200_engine *)be->ctx; Inst *in = (Inst *)inst;
     PicBuf *p = (PicBuf *)pic->priv;
     std::lock_guard<std::mutex> lk(e->mu);
-    if (in->queued) submit_locked(e);          /* consecutive pictures of one stream depend on each other */
     p->state = 2;
     in->slot_qgen[pic->cur_slot]++;
-    in->queued++;
-    e->queue.push_back(p);
-    if (!in->batched) submit_locked(e);
+    /* whatever the caller still holds of this frame slot (h264b200NextOutputPictureAsync) must be released before the
+     * picture may overwrite the slot's host mirror; pops of a slot always precede its re-use in host order */
+    p->gate_gen = in->slot_popped[pic->cur_slot];
+    in->fifo->push_back(p);
+    in->n_pending.fetch_add(1, std::memory_order_release);
+    if (!in->batched) advance_all_locked(e);
     return 0;
 }
 
-/* Wait until generation `gen` of `slot` is in its host mirror.  Returns 0, or 1 when a LATER picture has already been
- * launched into the slot (its mirror may be overwritten: the caller waited too long), or -1 on a CUDA error. */
-static int wait_slot(h264b200_engine *e, Inst *in, int slot, uint32_t gen)
+/* Wait until generation `gen` of `slot` is in its host mirror.  Returns 0; 1 when a LATER picture has already been
+ * launched into the slot (its mirror may be overwritten: the caller waited too long); 2 when the picture is still queued
+ * (only without may_advance); -1 on a CUDA error. */
+static int wait_slot(h264b200_engine *e, Inst *in, int slot, uint32_t gen, bool may_advance)
 {
-    if ((int32_t)(in->slot_lgen[slot] - gen) < 0) { std::lock_guard<std::mutex> lk(e->mu); submit_locked(e); }
-    if (in->slot_lgen[slot] != gen) return 1;
+    if ((int32_t)(in->slot_lgen[slot] - gen) < 0) {
+        if (!may_advance) return 2;
+        std::lock_guard<std::mutex> lk(e->mu);
+        while ((int32_t)(in->slot_lgen[slot] - gen) < 0) {
+            if (!advance_locked(e, true)) {
+                /* nothing can be launched: the picture is held back by an unreleased output of this very caller */
+                for (int k = 0; k < H264_MAX_SLOTS; k++) in->slot_released[k].store(in->slot_popped[k]);
+                if (!advance_locked(e, true)) break;
+            }
+        }
+    }
+    if (in->slot_lgen[slot] != gen) return (int32_t)(in->slot_lgen[slot] - gen) < 0 ? 2 : 1;
+    if (in->slot_flags[slot] & 4) return -1;
     if (in->slot_flags[slot] & 2) {
         set_device(e);
         cudaError_t er = cudaEventSynchronize(in->slot_ready[slot]);
@@ -457,14 +779,14 @@ static int wait_slot(h264b200_engine *e, Inst *in, int slot, uint32_t gen)
 static uint8_t *slot_mirror(Inst *in, int slot)
 {
     if (in->out_format == H264B200_OUT_RGBA && in->h_rgba) return in->h_rgba + (size_t)slot * in->rgba_bytes;
-    return in->h_frames + (size_t)slot * in->frame_bytes;
+    return in->h_frames + (size_t)slot * in->frame_stride;
 }
 
 static uint8_t *be_frame_host(h264_backend_t *be, void *inst, int slot, uint32_t *error_flags)
 {
     h264b200_engine *e = (h264b200_engine *)be->ctx; Inst *in = (Inst *)inst;
     if (slot < 0 || slot >= (int)in->n_slots) return NULL;
-    if (wait_slot(e, in, slot, in->slot_qgen[slot]) < 0) return NULL;
+    if (wait_slot(e, in, slot, in->slot_qgen[slot], true) < 0) return NULL;
     if (error_flags) *error_flags = *e->h_err;
     return slot_mirror(in, slot);
 }
@@ -475,20 +797,45 @@ static uint8_t *be_frame_host_async(h264_backend_t *be, void *inst, int slot, ui
     Inst *in = (Inst *)inst; (void)be;
     if (slot < 0 || slot >= (int)in->n_slots) return NULL;
     if (gen) *gen = in->slot_qgen[slot];
+    in->slot_popped[slot] = in->slot_qgen[slot];
     return slot_mirror(in, slot);
+}
+
+/* the ticket carries 24 bits of the generation: take the value nearest below the current one */
+static uint32_t full_gen(const Inst *in, int slot, uint32_t gen)
+{
+    uint32_t full = (in->slot_qgen[slot] & 0xff000000u) | (gen & 0xffffffu);
+    if (full > in->slot_qgen[slot]) full -= 1u << 24;
+    return full;
 }
 
 static int be_frame_wait(h264_backend_t *be, void *inst, int slot, uint32_t gen, uint32_t *error_flags)
 {
     h264b200_engine *e = (h264b200_engine *)be->ctx; Inst *in = (Inst *)inst;
     if (slot < 0 || slot >= (int)in->n_slots) return -1;
-    /* the ticket carries 24 bits of the generation: take the value nearest below the current one */
-    uint32_t full = (in->slot_qgen[slot] & 0xff000000u) | (gen & 0xffffffu);
-    if (full > in->slot_qgen[slot]) full -= 1u << 24;
-    int rc = wait_slot(e, in, slot, full);
+    /* a batched device-parse instance is driven by h264b200EngineAdvance: never launch from here */
+    int rc = wait_slot(e, in, slot, full_gen(in, slot, gen), !(in->dev_parse && in->batched));
     if (error_flags) *error_flags = *e->h_err;
     return rc;
 }
+
+static void be_frame_release(h264_backend_t *be, void *inst, int slot, uint32_t gen)
+{
+    Inst *in = (Inst *)inst; (void)be;
+    if (slot < 0 || slot >= (int)in->n_slots) return;
+    const uint32_t g = full_gen(in, slot, gen);
+    if ((int32_t)(g - in->slot_released[slot].load(std::memory_order_relaxed)) > 0) in->slot_released[slot].store(g, std::memory_order_release);
+}
+
+static int be_frame_status(h264_backend_t *be, void *inst, int slot, h264b200_picstat_t *out)
+{
+    Inst *in = (Inst *)inst; (void)be;
+    if (slot < 0 || slot >= (int)in->n_slots || !out) return -1;
+    memcpy(out, in->h_frames + (size_t)slot * in->frame_stride + in->frame_bytes, sizeof *out);
+    return 0;
+}
+
+static uint32_t be_inst_pending(h264_backend_t *be, void *inst) { (void)be; return ((Inst *)inst)->n_pending.load(std::memory_order_acquire); }
 
 /* output format of an instance: 0 ok.  RGBA buffers are allocated on first use. */
 static int be_set_output(h264_backend_t *be, void *inst, int format, int cl, int ct, int cw, int ch)
@@ -536,8 +883,9 @@ extern "C" h264b200_engine_t *h264b200EngineCreateEx(int device, uint32_t flags)
     if (h264b200Probe(msg, sizeof msg)) { fprintf(stderr, "h264b200: %s\n", msg); return NULL; }
     if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
     h264b200_engine *e = new h264b200_engine();
-    e->device = device; e->flags = flags; e->next_scr = 0;
-    memset(&e->st, 0, sizeof e->st); memset(e->scr, 0, sizeof e->scr);
+    e->device = device; e->flags = flags; e->next_scr = 0; e->next_pscr = 0; e->parse_seq = 0;
+    e->window = 1; e->parse_threshold = 1;
+    memset(&e->st, 0, sizeof e->st); memset(e->scr, 0, sizeof e->scr); memset(e->pscr, 0, sizeof e->pscr);
     memset(e->k_ms, 0, sizeof e->k_ms); memset(e->k_bytes, 0, sizeof e->k_bytes); memset(e->k_launches, 0, sizeof e->k_launches);
     CUDA_TRY(cudaSetDevice(device), { delete e; return NULL; });
     cudaDeviceProp p;
@@ -546,13 +894,28 @@ extern "C" h264b200_engine_t *h264b200EngineCreateEx(int device, uint32_t flags)
     CUDA_TRY(cudaStreamCreateWithFlags(&e->s_h2d, cudaStreamNonBlocking), { delete e; return NULL; });
     CUDA_TRY(cudaStreamCreateWithFlags(&e->s_comp, cudaStreamNonBlocking), { delete e; return NULL; });
     CUDA_TRY(cudaStreamCreateWithFlags(&e->s_d2h, cudaStreamNonBlocking), { delete e; return NULL; });
+    CUDA_TRY(cudaStreamCreateWithFlags(&e->s_parse[0], cudaStreamNonBlocking), { delete e; return NULL; });
+    CUDA_TRY(cudaStreamCreateWithFlags(&e->s_parse[1], cudaStreamNonBlocking), { delete e; return NULL; });
     CUDA_TRY(cudaEventCreateWithFlags(&e->ev_h2d, cudaEventDisableTiming), { delete e; return NULL; });
     CUDA_TRY(cudaEventCreateWithFlags(&e->ev_comp, cudaEventDisableTiming), { delete e; return NULL; });
+    CUDA_TRY(cudaEventCreateWithFlags(&e->ev_gate, cudaEventDisableTiming), { delete e; return NULL; });
     CUDA_TRY(cudaEventCreate(&e->ev_rep0), { delete e; return NULL; });
     CUDA_TRY(cudaEventCreate(&e->ev_rep1), { delete e; return NULL; });
     for (int i = 0; i < NSCR; i++) {
         CUDA_TRY(cudaEventCreateWithFlags(&e->scr[i].done, cudaEventDisableTiming), { delete e; return NULL; });
         CUDA_TRY(cudaEventCreateWithFlags(&e->scr[i].d2h_done, cudaEventDisableTiming), { delete e; return NULL; });
+    }
+    for (int i = 0; i < NPAR; i++) {
+        CUDA_TRY(cudaEventCreateWithFlags(&e->pscr[i].done, cudaEventDisableTiming), { delete e; return NULL; });
+        CUDA_TRY(cudaMalloc((void **)&e->pscr[i].d_ticket, 64), { delete e; return NULL; });
+    }
+    {   /* the host parser's code tables, for kernel Kp */
+        KpTables *t = (KpTables *)malloc(sizeof(KpTables));
+        if (!t) { delete e; return NULL; }
+        h264_kp_fill_tables(t);
+        CUDA_TRY(cudaMalloc((void **)&e->d_tables, sizeof(KpTables)), { free(t); delete e; return NULL; });
+        CUDA_TRY(cudaMemcpy(e->d_tables, t, sizeof(KpTables), cudaMemcpyHostToDevice), { free(t); delete e; return NULL; });
+        free(t);
     }
     CUDA_TRY(cudaMalloc((void **)&e->d_err, 64), { delete e; return NULL; });
     CUDA_TRY(cudaMemset(e->d_err, 0, 64), { delete e; return NULL; });
@@ -564,11 +927,15 @@ extern "C" h264b200_engine_t *h264b200EngineCreateEx(int device, uint32_t flags)
         CUDA_TRY(cudaMalloc((void **)&e->d_trace, (256 + 4 * 512) * 8), { delete e; return NULL; });
         cudaMemset(e->d_trace, 0, (256 + 4 * 512) * 8);
     }
+    memset(&e->be, 0, sizeof e->be);
     e->be.inst_create = be_inst_create; e->be.inst_destroy = be_inst_destroy; e->be.pic_begin = be_pic_begin;
     e->be.coef_grow = be_coef_grow; e->be.pic_submit = be_pic_submit; e->be.frame_host = be_frame_host;
     e->be.frame_host_async = be_frame_host_async;
     e->be.frame_wait = be_frame_wait;
     e->be.set_output = be_set_output;
+    e->be.block_grow = be_block_grow; e->be.frame_status = be_frame_status; e->be.frame_release = be_frame_release;
+    e->be.inst_pending = be_inst_pending;
+    e->be.parse_mode = (flags & H264B200_ENGINE_DEVICE_PARSE) != 0;
     e->be.destroy = be_destroy; e->be.ctx = e;
     return e;
 }
@@ -576,24 +943,24 @@ extern "C" h264b200_engine_t *h264b200EngineCreate(int device) { return h264b200
 
 static void free_retained(h264b200_engine *e)
 {
-    for (Retained *r : e->retained) { for (void *p : r->owned) cudaFree(p); delete r; }
+    for (Retained *r : e->retained) { for (void *p : r->owned) cudaFree(p); cudaEventDestroy(r->ev); delete r; }
     e->retained.clear();
-    for (Inst *z : e->zombies) {
-        for (size_t i = 0; i < e->insts.size(); i++) if (e->insts[i] == z) { e->insts.erase(e->insts.begin() + i); break; }
-        inst_free(z);
-    }
+    for (Inst *z : e->zombies) inst_free(z);
     e->zombies.clear();
+    for (Inst *in : e->insts) for (int k = 0; k < in->n_bufs; k++) in->bufs[k].tape_parse = in->bufs[k].tape_last_round = -1;
+    for (cudaEvent_t ev : e->tev) cudaEventDestroy(ev);
+    e->tev.clear(); e->tev_entry.clear();
 }
 
 extern "C" void h264b200EngineDestroy(h264b200_engine_t *e)
 {
     if (!e) return;
     set_device(e);
-    cudaStreamSynchronize(e->s_h2d); cudaStreamSynchronize(e->s_comp); cudaStreamSynchronize(e->s_d2h);
+    cudaStreamSynchronize(e->s_h2d); cudaStreamSynchronize(e->s_parse[0]); cudaStreamSynchronize(e->s_parse[1]);
+    cudaStreamSynchronize(e->s_comp); cudaStreamSynchronize(e->s_d2h);
     free_retained(e);
     for (Inst *p : e->pool) inst_free(p);
     e->pool.clear();
-    for (cudaEvent_t ev : e->tev) cudaEventDestroy(ev);
     for (int i = 0; i < NSCR; i++) {
         Scratch &s = e->scr[i];
         if (s.h_jobs) cudaFreeHost(s.h_jobs);
@@ -601,9 +968,19 @@ extern "C" void h264b200EngineDestroy(h264b200_engine_t *e)
         if (s.d_ctrl) cudaFree(s.d_ctrl);
         cudaEventDestroy(s.done); cudaEventDestroy(s.d2h_done);
     }
+    for (int i = 0; i < NPAR; i++) {
+        ParseScratch &s = e->pscr[i];
+        if (s.h_pics) cudaFreeHost(s.h_pics);
+        if (s.d_pics) cudaFree(s.d_pics);
+        if (s.d_ticket) cudaFree(s.d_ticket);
+        cudaEventDestroy(s.done);
+    }
+    cudaFree(e->d_tables);
     cudaFree(e->d_err); cudaFreeHost(e->h_err);
-    cudaEventDestroy(e->ev_h2d); cudaEventDestroy(e->ev_comp); cudaEventDestroy(e->ev_rep0); cudaEventDestroy(e->ev_rep1);
+    if (e->d_trace) cudaFree(e->d_trace);
+    cudaEventDestroy(e->ev_h2d); cudaEventDestroy(e->ev_comp); cudaEventDestroy(e->ev_rep0); cudaEventDestroy(e->ev_rep1); cudaEventDestroy(e->ev_gate);
     cudaStreamDestroy(e->s_h2d); cudaStreamDestroy(e->s_comp); cudaStreamDestroy(e->s_d2h);
+    cudaStreamDestroy(e->s_parse[0]); cudaStreamDestroy(e->s_parse[1]);
     delete e;
 }
 
@@ -618,21 +995,41 @@ extern "C" u32 h264b200EngineSubmit(h264b200_engine_t *e)
 {
     if (!e) return 0;
     std::lock_guard<std::mutex> lk(e->mu);
-    return submit_locked(e);
+    return advance_all_locked(e);
 }
+extern "C" u32 h264b200EngineAdvance(h264b200_engine_t *e)
+{
+    if (!e) return 0;
+    std::lock_guard<std::mutex> lk(e->mu);
+    return advance_locked(e, false);
+}
+extern "C" void h264b200EngineSetWindow(h264b200_engine_t *e, uint32_t depth, uint32_t parse_threshold)
+{
+    if (!e) return;
+    std::lock_guard<std::mutex> lk(e->mu);
+    e->window = depth ? (depth > 64 ? 64 : depth) : 1;
+    e->parse_threshold = parse_threshold ? parse_threshold : 1;
+}
+extern "C" uint32_t h264b200EngineWindow(h264b200_engine_t *e) { return e ? e->window : 0; }
 
 extern "C" void h264b200EngineSync(h264b200_engine_t *e)
 {
     if (!e) return;
     set_device(e);
-    cudaError_t a = cudaStreamSynchronize(e->s_h2d), b = cudaStreamSynchronize(e->s_comp), c = cudaStreamSynchronize(e->s_d2h);
-    if (a != cudaSuccess || b != cudaSuccess || c != cudaSuccess)
-        fprintf(stderr, "h264b200: engine sync failed: %s\n", cudaGetErrorString(a != cudaSuccess ? a : b != cudaSuccess ? b : c));
+    cudaError_t a = cudaStreamSynchronize(e->s_h2d), p0 = cudaStreamSynchronize(e->s_parse[0]), p1 = cudaStreamSynchronize(e->s_parse[1]);
+    cudaError_t b = cudaStreamSynchronize(e->s_comp), c = cudaStreamSynchronize(e->s_d2h);
+    if (a != cudaSuccess || b != cudaSuccess || c != cudaSuccess || p0 != cudaSuccess || p1 != cudaSuccess)
+        fprintf(stderr, "h264b200: engine sync failed: %s\n", cudaGetErrorString(a != cudaSuccess ? a : p0 != cudaSuccess ? p0 : p1 != cudaSuccess ? p1 : b != cudaSuccess ? b : c));
 }
 
 extern "C" void h264b200EngineStats(h264b200_engine_t *e, h264b200_stats_t *out) { if (e && out) { std::lock_guard<std::mutex> lk(e->mu); *out = e->st; } }
 extern "C" u32 h264b200EngineErrorFlags(h264b200_engine_t *e) { return e ? *e->h_err : 0; }
-extern "C" void h264b200EngineSetFlags(h264b200_engine_t *e, uint32_t flags) { if (e) { std::lock_guard<std::mutex> lk(e->mu); e->flags = flags; } }
+extern "C" void h264b200EngineSetFlags(h264b200_engine_t *e, uint32_t flags)
+{
+    if (!e) return;
+    std::lock_guard<std::mutex> lk(e->mu);
+    e->flags = flags; e->be.parse_mode = (flags & H264B200_ENGINE_DEVICE_PARSE) != 0;
+}
 extern "C" uint32_t h264b200EngineFlags(h264b200_engine_t *e) { if (!e) return 0; std::lock_guard<std::mutex> lk(e->mu); return e->flags; }
 
 /* -------------------------------------------------------- resident replay */
@@ -644,35 +1041,52 @@ extern "C" void h264b200EngineDropRetained(h264b200_engine_t *e)
     free_retained(e);
 }
 
+/* Re-run the tape: every Kp launch and every reconstruction round of the retained run, in the order and with the
+ * dependencies of the live run (a round waits for the Kp launches that produce its records; a Kp launch waits for the
+ * last round that read a parse buffer it overwrites), inputs resident in HBM, no host<->device copies. */
 extern "C" u32 h264b200EngineReplay(h264b200_engine_t *e, u32 reps, int time_kernels)
 {
     if (!e) return 0;
     std::lock_guard<std::mutex> lk(e->mu);
     set_device(e);
-    size_t need = 0;
-    for (Retained *r : e->retained) if (r->ctrl_words > need) need = r->ctrl_words;
     u32 pics = 0;
     cudaEventRecord(e->ev_rep0, e->s_comp);
-    for (u32 rep = 0; rep < reps; rep++) for (size_t bi = 0; bi < e->retained.size(); bi++) {
-        Retained *r = e->retained[bi];
-        BatchPlan pl; pl.k1 = r->k1; pl.k2 = r->k2; pl.k3 = r->k3; pl.k4 = r->k4;
-        pl.k3c = false; for (const PicJob &pj : r->jobs) if (pj.n_conceal) pl.k3c = true;
-        pl.total_mbs = r->batch.total_mbs; pl.max_hm = r->batch.max_hm; pl.n_jobs = r->batch.n_jobs;
-        cudaEvent_t *tev = nullptr;
-        if (time_kernels) {
-            size_t base = e->tev.size();
-            for (int k = 0; k < 5; k++) { cudaEvent_t ev; cudaEventCreate(&ev); e->tev.push_back(ev); }
-            e->tev_batch.push_back((int)bi);
-            tev = &e->tev[base];
+    for (u32 rep = 0; rep < reps; rep++) {
+        /* nothing of this repetition starts before the previous one (or the caller's earlier work) has finished */
+        cudaEventRecord(e->ev_gate, e->s_comp);
+        cudaStreamWaitEvent(e->s_parse[0], e->ev_gate, 0); cudaStreamWaitEvent(e->s_parse[1], e->ev_gate, 0);
+        for (size_t bi = 0; bi < e->retained.size(); bi++) {
+            Retained *r = e->retained[bi];
+            cudaEvent_t *tev = nullptr;
+            if (time_kernels) {
+                const int nev = r->kind == 0 ? 5 : 2;
+                size_t base = e->tev.size();
+                for (int k = 0; k < nev; k++) { cudaEvent_t ev; cudaEventCreate(&ev); e->tev.push_back(ev); }
+                e->tev_entry.push_back((int)bi);
+                tev = &e->tev[base];
+            }
+            if (r->kind == 1) {
+                cudaStream_t s = e->s_parse[r->stream];
+                if (r->wait_round >= 0) cudaStreamWaitEvent(s, e->retained[(size_t)r->wait_round]->ev, 0);
+                cudaMemsetAsync(r->kp.ticket, 0, 64, s);
+                if (tev) cudaEventRecord(tev[0], s);
+                kp_parse<<<kp_grid(e, r->kp.n_pics), KP_WARPS * 32, 0, s>>>(r->kp);
+                if (tev) cudaEventRecord(tev[1], s);
+                cudaEventRecord(r->ev, s);
+                e->st.kernel_launches++; e->st.kp_launches++; e->st.kp_pictures += r->kp.n_pics;
+            } else {
+                for (int w : r->wait_parse) cudaStreamWaitEvent(e->s_comp, e->retained[(size_t)w]->ev, 0);
+                /* the round's own control area (tickets + wavefront progress) and job table are part of its retained allocation */
+                cudaMemsetAsync(r->batch.tickets, 0, r->ctrl_words * sizeof(int32_t), e->s_comp);
+                launch_kernels(e, r->batch, r->pl, tev);
+                cudaEventRecord(r->ev, e->s_comp);
+                pics += r->n_pics;
+                e->st.batches++;
+            }
         }
-        /* the batch's own control area (tickets + wavefront progress) is part of its retained allocation
-         * (r->batch.tickets points at it); batches are serialised on s_comp */
-        cudaMemsetAsync(r->batch.tickets, 0, r->ctrl_words * sizeof(int32_t), e->s_comp);
-        launch_kernels(e, r->batch, pl, tev);
-        pics += r->n_pics;
     }
     cudaEventRecord(e->ev_rep1, e->s_comp);
-    e->st.pictures += pics; e->st.batches += (uint64_t)reps * e->retained.size();
+    e->st.pictures += pics;
     return pics;
 }
 
@@ -686,23 +1100,41 @@ extern "C" double h264b200EngineReplayMs(h264b200_engine_t *e)
     return (double)ms;
 }
 
-/* Fold the event pairs of timed replays into the per-kernel totals (after a sync). */
+/* Fold the event pairs of timed replays into the per-kernel totals (after a sync).  Families: K1, K2, K3, K4, Kp. */
 extern "C" void h264b200EngineKernelTimes(h264b200_engine_t *e, h264b200_kernel_times_t *out, int reset)
 {
     if (!e || !out) return;
     h264b200EngineSync(e);
     std::lock_guard<std::mutex> lk(e->mu);
-    for (size_t i = 0; i < e->tev_batch.size(); i++) {
-        Retained *r = e->retained[(size_t)e->tev_batch[i]];
-        const bool on[4] = {r->k1, r->k2, r->k3, r->k4};
-        for (int k = 0; k < 4; k++) if (on[k]) {
-            float ms = 0; cudaEventElapsedTime(&ms, e->tev[5 * i + k], e->tev[5 * i + k + 1]);
-            e->k_ms[k] += ms; e->k_bytes[k] += r->bytes[k]; e->k_launches[k]++;
+    set_device(e);
+    for (Retained *r : e->retained) if (r->kind == 0 && !r->bytes_read) {
+        unsigned long long h[4] = {0, 0, 0, 0};
+        cudaMemcpy(h, r->d_bytes, sizeof h, cudaMemcpyDeviceToHost);
+        for (int k = 0; k < 4; k++) r->bytes[k] = h[k];
+        r->bytes_read = true;
+    }
+    size_t pos = 0;
+    for (size_t i = 0; i < e->tev_entry.size(); i++) {
+        Retained *r = e->retained[(size_t)e->tev_entry[i]];
+        if (r->kind == 0) {
+            const bool on[4] = {r->pl.k1, r->pl.k2, r->pl.k3 || r->pl.k3c, r->pl.k4};
+            for (int k = 0; k < 4; k++) if (on[k]) {
+                float ms = 0; cudaEventElapsedTime(&ms, e->tev[pos + k], e->tev[pos + k + 1]);
+                e->k_ms[k] += ms; e->k_bytes[k] += r->bytes[k]; e->k_launches[k]++;
+            }
+            pos += 5;
+        } else {
+            /* Kp: the blocks read + the records and coefficient slots written (= half of K1's bytes of the rounds it feeds) */
+            float ms = 0; cudaEventElapsedTime(&ms, e->tev[pos], e->tev[pos + 1]);
+            uint64_t slots = 0;
+            for (int w : r->rounds) slots += e->retained[(size_t)w]->bytes[0] / 2;
+            e->k_ms[4] += ms; e->k_bytes[4] += r->kp_in_bytes + r->kp_rec_bytes + slots; e->k_launches[4]++;
+            pos += 2;
         }
     }
     for (cudaEvent_t ev : e->tev) cudaEventDestroy(ev);
-    e->tev.clear(); e->tev_batch.clear();
-    for (int k = 0; k < 4; k++) { out->ms[k] = e->k_ms[k]; out->bytes[k] = e->k_bytes[k]; out->launches[k] = e->k_launches[k]; }
+    e->tev.clear(); e->tev_entry.clear();
+    for (int k = 0; k < 5; k++) { out->ms[k] = e->k_ms[k]; out->bytes[k] = e->k_bytes[k]; out->launches[k] = e->k_launches[k]; }
     if (reset) { memset(e->k_ms, 0, sizeof e->k_ms); memset(e->k_bytes, 0, sizeof e->k_bytes); memset(e->k_launches, 0, sizeof e->k_launches); }
 }
 
@@ -715,15 +1147,45 @@ extern "C" u32 h264b200EngineCheckResident(h264b200_engine_t *e)
     std::lock_guard<std::mutex> lk(e->mu);
     set_device(e);
     u32 bad = 0;
-    for (Inst *in : e->insts) {
+    std::vector<Inst *> all(e->insts);
+    all.insert(all.end(), e->zombies.begin(), e->zombies.end());
+    for (Inst *in : all) {
         if (in->out_format != H264B200_OUT_I420) continue;      /* the I420 mirror of an RGBA instance is not filled */
         std::vector<uint8_t> tmp(in->frame_bytes);
         for (uint32_t s = 0; s < in->n_slots; s++) {
-            if (cudaMemcpy(tmp.data(), in->d_frames + (size_t)s * in->frame_bytes, in->frame_bytes, cudaMemcpyDeviceToHost) != cudaSuccess) return 0xffffffffu;
-            if (memcmp(tmp.data(), in->h_frames + (size_t)s * in->frame_bytes, in->frame_bytes)) bad++;
+            if (cudaMemcpy(tmp.data(), in->d_frames + (size_t)s * in->frame_stride, in->frame_bytes, cudaMemcpyDeviceToHost) != cudaSuccess) return 0xffffffffu;
+            if (memcmp(tmp.data(), in->h_frames + (size_t)s * in->frame_stride, in->frame_bytes)) bad++;
         }
     }
     return bad;
+}
+
+/* Debug / parity: records, coefficient slots and results of the device-parse picture most recently LAUNCHED for the
+ * instance behind `inst`... (see h264b200DebugFetchParse in h264_decoder.c) */
+extern "C" int h264b200_engine_fetch_parse(h264_backend_t *be, void *inst, int back, h264b200_mb_t *mbs, int16_t *coef, uint32_t coef_cap, KpResult *res)
+{
+    h264b200_engine *e = (h264b200_engine *)be->ctx; Inst *in = (Inst *)inst;
+    if (!in->dev_parse || back < 0 || back >= in->n_bufs) return -1;
+    h264b200EngineSync(e);
+    set_device(e);
+    const PicBuf *p = &in->bufs[(in->next_buf + in->n_bufs - 1 - back) % in->n_bufs];
+    if (p->state != 3) return -2;
+    KpResult r;
+    if (cudaMemcpy(&r, p->d_res, sizeof r, cudaMemcpyDeviceToHost) != cudaSuccess) return -3;
+    if (res) *res = r;
+    if (mbs && cudaMemcpy(mbs, p->d_mbs, (size_t)in->n_mbs * sizeof(h264b200_mb_t), cudaMemcpyDeviceToHost) != cudaSuccess) return -3;
+    if (coef) {
+        const uint32_t n = r.coef_used < coef_cap ? r.coef_used : coef_cap;
+        if (n && cudaMemcpy(coef, p->d_coef, (size_t)n * 32, cudaMemcpyDeviceToHost) != cudaSuccess) return -3;
+    }
+    return 0;
+}
+
+extern "C" int h264b200DebugFetchParse(storage_t *pStorage, int back, void *mbs, int16_t *coef, uint32_t coef_cap, uint32_t *res)
+{
+    h264_decoder_t *d = pStorage ? (h264_decoder_t *)pStorage->impl : NULL;
+    if (!d || !d->be || !d->be_inst || !d->device_parse || d->be->inst_create != be_inst_create) return -1;
+    return h264b200_engine_fetch_parse(d->be, d->be_inst, back, (h264b200_mb_t *)mbs, coef, coef_cap, (KpResult *)res);
 }
 
 /* ------------------------------------------------------- default backend */
@@ -735,9 +1197,11 @@ extern "C" h264_backend_t *h264_default_backend(void)
     std::lock_guard<std::mutex> lk(g_default_mu);
     if (!g_default_engine) {
         int dev = -1;
-        const char *s = getenv("H264B200_DEVICE");
+        const char *s = getenv("H264B200_DEVICE"), *pm = getenv("H264B200_PARSE");
         if (s && *s) dev = atoi(s);
-        g_default_engine = h264b200EngineCreateEx(dev, 0);
+        /* the synchronous single-instance API parses on the host by default (one picture at a time gives kernel Kp
+         * nothing to run in parallel); H264B200_PARSE=device selects the device parser anyway */
+        g_default_engine = h264b200EngineCreateEx(dev, (pm && !strcmp(pm, "device")) ? H264B200_ENGINE_DEVICE_PARSE : 0);
         if (!g_default_engine) {
             fprintf(stderr, "h264b200: no CUDA engine: this library has no CPU reconstruction path\n");
             return NULL;

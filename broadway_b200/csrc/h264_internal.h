@@ -9,6 +9,7 @@
 #include <stdint.h>
 #include <stddef.h>
 #include "h264b200_records.h"
+#include "h264b200_slices.h"
 #include "h264_bits.h"
 #include "h264_fmo.h"
 
@@ -130,6 +131,11 @@ typedef struct {
     int       cur_slot;
     uint8_t   ref_slots_used[H264_MAX_SLOTS];
     void     *priv;
+    /* device-parse path (kernel Kp): instead of records and slots the host assembles ONE block per picture,
+     * h264b200_pichdr_t + per slice {h264b200_slice_t, RBSP, slice group map} (include/h264b200_slices.h) */
+    uint8_t  *block;           /* NULL: this picture is parsed on the host */
+    uint32_t  block_cap, block_used;
+    uint32_t  has_p_slice;     /* a P slice was queued (inter prediction may be needed) */
 } h264_pic_input_t;
 
 typedef struct h264_backend h264_backend_t;
@@ -153,6 +159,18 @@ struct h264_backend {
     int (*frame_wait)(h264_backend_t *be, void *inst, int slot, uint32_t gen, uint32_t *error_flags);
     /* optional: output format of an instance (H264B200_OUT_*) and the cropping rectangle in luma samples */
     int (*set_output)(h264_backend_t *be, void *inst, int format, int crop_left, int crop_top, int crop_width, int crop_height);
+    /* optional, device-parse backends: make room for at least min_bytes in pic->block (contents preserved); 0 on success.
+     * A backend that provides it hands out pictures with pic->block != NULL when the instance was created in
+     * device-parse mode (see parse_mode below). */
+    int (*block_grow)(h264_backend_t *be, void *inst, h264_pic_input_t *pic, uint32_t min_bytes);
+    /* optional: status words of the picture last reconstructed into `slot` (valid after frame_host / frame_wait) */
+    int (*frame_status)(h264_backend_t *be, void *inst, int slot, h264b200_picstat_t *out);
+    /* optional: the caller is done with generation `gen` of `slot` (frame_host_async): its host mirror may be overwritten */
+    void (*frame_release)(h264_backend_t *be, void *inst, int slot, uint32_t gen);
+    /* optional: pictures of the instance submitted but not yet launched */
+    uint32_t (*inst_pending)(h264_backend_t *be, void *inst);
+    /* 1: instances are to be created in device-parse mode (h264b200_slices.h); read by the decoder at activation */
+    int parse_mode;
 };
 
 /* implemented by whichever backend is linked: the CUDA engine in libh264b200.so */
@@ -204,6 +222,8 @@ typedef struct h264_decoder {
     h264_pic_input_t *pic;                        /* input buffer of the picture being parsed */
     int last_output_slot;
     int out_format;                               /* H264B200_OUT_* requested through h264b200SetOutputFormat */
+    int device_parse;                             /* slice data is parsed by kernel Kp: slices are queued, pictures end at the
+                                                     next access unit boundary (or h264bsdFlushBuffer) */
 } h264_decoder_t;
 
 /* parameter sets / headers (h264_params.c) */
@@ -215,6 +235,8 @@ int32_t h264_decode_poc(h264_decoder_t *d, const h264_slice_hdr_t *sh, int nal_t
 
 /* CAVLC (h264_cavlc.c) */
 void h264_cavlc_init(void);
+#include "kp_types.h"
+void h264_kp_fill_tables(KpTables *t);
 /* the block decoder itself is inline: h264_cavlc_inl.h */
 
 /* slice data (h264_slice.c): parse all macroblocks of one slice into d->pic */

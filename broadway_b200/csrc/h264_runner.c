@@ -45,6 +45,9 @@ typedef struct {
     pending_t cur[MAX_PENDING], prev[MAX_PENDING];
     int n_cur, n_prev;
     u32 width, height;
+    /* device-parse pipeline: outputs popped while scanning ahead, oldest first */
+    pending_t *outq; u32 outq_cap, outq_head, outq_n;
+    u32 depth;                  /* look-ahead this stream may use */
 } rstream_t;
 
 typedef struct runner runner_t;
@@ -107,6 +110,7 @@ static void consume_prev(worker_t *w, rstream_t *s, uint32_t stream_index)
         if (rc == 0xffffffffu || rc == 0xfffffffeu) { s->failed = 1; continue; }
         if (!s->width) { s->width = 16 * h264bsdPicWidth(&s->st); s->height = 16 * h264bsdPicHeight(&s->st); }
         if (r->cb) r->cb(r->user, stream_index, s->out_index, q->ptr, s->width, s->height, q->pic_id, q->err);
+        h264b200PictureRelease(&s->st, q->ticket);      /* the frame slot's host mirror may be overwritten from now on */
         s->out_index++;
         w->pictures++; w->bytes_out += (uint64_t)s->width * s->height * 3 / 2; w->err_mbs += q->err;
     }
@@ -149,15 +153,128 @@ static void *worker_main(void *arg)
         }
         /* private copy (the decoder strips emulation prevention bytes in place), made by the first thread to touch the stream */
         if (round == 0 && s->buf && s->inited) { memcpy(s->buf, s->src, s->len); memset(s->buf + s->len, 0, 16); }
+        /* What the previous round popped was launched a whole round ago.  It is consumed BEFORE the next picture is
+         * parsed: the DPB may hand that picture the very frame slot whose host mirror the callback is about to read,
+         * and the engine holds a picture back while an output of its slot is unreleased. */
+        consume_prev(w, s, idx);
         if (!s->finished && !s->failed) {
             double t0 = now_s();
             produced = (uint32_t)step_stream(s);
             w->parse_s += now_s() - t0;
         }
-        /* what the previous round popped was launched a whole round ago */
-        consume_prev(w, s, idx);
         memcpy(s->prev, s->cur, (size_t)s->n_cur * sizeof(pending_t)); s->n_prev = s->n_cur; s->n_cur = 0;
         group_arrive(r, g, round, produced);
+    }
+    return NULL;
+}
+
+/* ------------------------------------------------ device-parse pipeline */
+/* With kernel Kp the host does no slice-data parsing: a picture costs it a NAL scan, a slice header and the DPB
+ * bookkeeping.  So every stream SCANS AHEAD of the GPU by up to `depth` pictures (they wait in the engine), which is what
+ * gives Kp thousands of independent pictures per launch; every round of the loop below then (1) hands finished
+ * pictures to the callback and releases their buffers, (2) tops the look-ahead up, and the last thread of the round
+ * calls h264b200EngineAdvance once: a Kp launch when enough pictures are queued, and one reconstruction round. */
+static void outq_push(rstream_t *s, const pending_t *q)
+{
+    if (s->outq_n == s->outq_cap) {
+        u32 ncap = s->outq_cap ? s->outq_cap * 2 : 64, i;
+        pending_t *n = (pending_t *)malloc(ncap * sizeof *n);
+        if (!n) { s->failed = 1; return; }
+        for (i = 0; i < s->outq_n; i++) n[i] = s->outq[(s->outq_head + i) % s->outq_cap];
+        free(s->outq); s->outq = n; s->outq_cap = ncap; s->outq_head = 0;
+    }
+    s->outq[(s->outq_head + s->outq_n++) % s->outq_cap] = *q;
+}
+static void dev_pop_outputs(rstream_t *s)
+{
+    pending_t q; u32 idr;
+    while ((q.ptr = h264b200NextOutputPictureAsync(&s->st, &q.pic_id, &idr, &q.err, &q.ticket)) != NULL) outq_push(s, &q);
+}
+/* scan one picture ahead (NAL units up to the next H264BSD_PIC_RDY); 1 if a picture was queued */
+static int dev_scan_one(rstream_t *s)
+{
+    while (s->pos < s->len) {
+        u32 nread = 0, rest = (u32)(s->len - s->pos > 0x7fffffffu ? 0x7fffffffu : s->len - s->pos);
+        u32 rc = h264bsdDecode(&s->st, s->buf + s->pos, rest, s->pic_id, &nread);
+        s->pos += nread;
+        if (rc == H264BSD_PIC_RDY) { s->pic_id++; dev_pop_outputs(s); return 1; }
+        if (rc == H264BSD_HDRS_RDY) { dev_pop_outputs(s); continue; }
+        if (rc == H264BSD_MEMALLOC_ERROR) { s->failed = 1; break; }
+        if (nread == 0 && rc != H264BSD_RDY) { s->failed = 1; break; }
+    }
+    if (!s->flushed) {          /* the last picture has no following access unit to end it */
+        const u32 before = h264b200PicturesPending(&s->st);
+        s->flushed = 1; h264bsdFlushBuffer(&s->st); dev_pop_outputs(s);
+        s->finished = 1;
+        return h264b200PicturesPending(&s->st) > before;
+    }
+    s->finished = 1;
+    return 0;
+}
+/* hand over every output whose picture has been launched; returns how many */
+static u32 dev_consume(worker_t *w, rstream_t *s, uint32_t stream_index)
+{
+    runner_t *r = w->r;
+    u32 n = 0;
+    while (s->outq_n) {
+        pending_t *q = &s->outq[s->outq_head];
+        h264b200_picstat_t ps;
+        double t0 = now_s();
+        u32 rc = h264b200PictureWait(&s->st, q->ticket);
+        w->wait_s += now_s() - t0;
+        if (rc == H264B200_WAIT_NOT_LAUNCHED) break;
+        if (rc == 0xffffffffu || rc == 0xfffffffeu) s->failed = 1;
+        else if (!h264b200PictureStatus(&s->st, q->ticket, &ps) && (ps.flags & H264B200_PS_DROPPED)) ;   /* incomplete last picture: not output */
+        else {
+            if (!h264b200PictureStatus(&s->st, q->ticket, &ps)) q->err = ps.err_mbs;
+            if (!s->width) { s->width = 16 * h264bsdPicWidth(&s->st); s->height = 16 * h264bsdPicHeight(&s->st); }
+            if (r->cb) r->cb(r->user, stream_index, s->out_index, q->ptr, s->width, s->height, q->pic_id, q->err);
+            s->out_index++;
+            w->pictures++; w->bytes_out += (uint64_t)s->width * s->height * 3 / 2; w->err_mbs += q->err;
+        }
+        h264b200PictureRelease(&s->st, q->ticket);
+        s->outq_head = (s->outq_head + 1) % s->outq_cap; s->outq_n--;
+        n++;
+    }
+    return n;
+}
+
+static void *dev_worker_main(void *arg)
+{
+    worker_t *w = (worker_t *)arg; runner_t *r = w->r;
+    while (!__atomic_load_n(&r->stop, __ATOMIC_ACQUIRE)) {
+        const uint64_t item = __atomic_fetch_add(&r->next_item, 1, __ATOMIC_RELAXED);
+        const uint32_t round = (uint32_t)(item / r->n_streams), idx = (uint32_t)(item % r->n_streams);
+        rstream_t *s = &r->s[idx];
+        uint32_t activity = 0, burst;
+        while (__atomic_load_n(&r->launched[0], __ATOMIC_ACQUIRE) < round) {
+            if (__atomic_load_n(&r->stop, __ATOMIC_ACQUIRE)) return NULL;
+            sched_yield();
+        }
+        if (round == 0 && s->buf && s->inited) { memcpy(s->buf, s->src, s->len); memset(s->buf + s->len, 0, 16); }
+        if (s->inited) {
+            activity += dev_consume(w, s, idx);
+            /* fill the look-ahead at once when the stream starts, then keep it topped up */
+            burst = s->pic_id == 0 ? s->depth : 2;
+            while (burst-- && !s->finished && !s->failed && h264b200PicturesPending(&s->st) < s->depth) {
+                double t0 = now_s();
+                activity += (uint32_t)dev_scan_one(s);
+                w->parse_s += now_s() - t0;
+            }
+            if (!s->finished && !s->failed) activity++;
+            activity += s->outq_n + h264b200PicturesPending(&s->st);
+        }
+        /* the last stream of the round drives the engine */
+        pthread_mutex_lock(&r->mu);
+        r->produced[0] += activity;
+        if (++r->arrived[0] == r->n_streams) {
+            const uint32_t launched = h264b200EngineAdvance(r->e);
+            if (launched) r->rounds++;
+            if (!r->produced[0] && !launched) __atomic_store_n(&r->stop, 1, __ATOMIC_RELEASE);
+            r->produced[0] = 0; r->arrived[0] = 0;
+            __atomic_store_n(&r->launched[0], round + 1, __ATOMIC_RELEASE);
+        }
+        pthread_mutex_unlock(&r->mu);
     }
     return NULL;
 }
@@ -165,7 +282,7 @@ static void *worker_main(void *arg)
 int h264b200DecodeStreams(h264b200_engine_t *e, const h264b200_stream_t *streams, uint32_t n_streams,
                           uint32_t n_threads, h264b200_picture_cb cb, void *user, h264b200_run_stats_t *out)
 {
-    runner_t r; worker_t *w; uint32_t i; double t0 = now_s(); int rc = 0;
+    runner_t r; worker_t *w; uint32_t i, depth = 1; double t0 = now_s(); int rc = 0, dev;
     if (!e || !streams || !n_streams) return -1;
     memset(&r, 0, sizeof r);
     if (!n_threads) { long n = sysconf(_SC_NPROCESSORS_ONLN); n_threads = n > 0 ? (uint32_t)n : 1; }
@@ -175,9 +292,17 @@ int h264b200DecodeStreams(h264b200_engine_t *e, const h264b200_stream_t *streams
     w = (worker_t *)calloc(n_threads, sizeof(worker_t));
     if (!r.s || !w) { free(r.s); free(w); return -1; }
     pthread_mutex_init(&r.mu, NULL);
+    dev = (h264b200EngineFlags(e) & H264B200_ENGINE_DEVICE_PARSE) != 0;
+    if (dev) {
+        /* look-ahead per stream: enough pictures in flight for kernel Kp (thousands), within what the engine can hold */
+        const char *wenv = getenv("H264B200_WINDOW");
+        depth = wenv && atoi(wenv) > 0 ? (uint32_t)atoi(wenv) : 16;
+        h264b200EngineSetWindow(e, depth, n_streams * ((depth + 1) / 2));
+        depth = h264b200EngineWindow(e);
+    }
     /* two groups once every thread has a few streams per group; otherwise one (a round is then one batch).  Batches
      * retained for h264b200EngineReplay are always whole rounds. */
-    r.n_groups = (n_streams >= 4 * n_threads && !(h264b200EngineFlags(e) & H264B200_ENGINE_RETAIN)) ? 2 : 1;
+    r.n_groups = (!dev && n_streams >= 4 * n_threads && !(h264b200EngineFlags(e) & H264B200_ENGINE_RETAIN)) ? 2 : 1;
     r.gstart[0] = 0; r.gstart[1] = r.n_groups > 1 ? n_streams / 2 : n_streams; r.gstart[2] = n_streams;
     for (i = 0; i < n_streams; i++) {
         rstream_t *s = &r.s[i];
@@ -185,12 +310,17 @@ int h264b200DecodeStreams(h264b200_engine_t *e, const h264b200_stream_t *streams
         s->buf = (uint8_t *)malloc(s->len + 16);            /* private copy: the decoder strips emulation prevention bytes in place */
         s->src = streams[i].data;
         if (!s->buf || h264b200InitOnEngine(&s->st, 0, e) != HANTRO_OK) { s->failed = 1; rc = -1; continue; }
-        s->inited = 1;
+        s->inited = 1; s->depth = depth;
     }
     for (i = 0; i < n_threads; i++) { w[i].r = &r; w[i].tid = i; }
-    for (i = 1; i < n_threads; i++) pthread_create(&w[i].th, NULL, worker_main, &w[i]);
-    worker_main(&w[0]);
+    for (i = 1; i < n_threads; i++) pthread_create(&w[i].th, NULL, dev ? dev_worker_main : worker_main, &w[i]);
+    if (dev) dev_worker_main(&w[0]); else worker_main(&w[0]);
     for (i = 1; i < n_threads; i++) pthread_join(w[i].th, NULL);
+    if (dev) {                                                                   /* nothing should be left; be safe */
+        for (i = 0; i < n_streams; i++) while (r.s[i].inited && r.s[i].outq_n) {
+            if (!dev_consume(&w[0], &r.s[i], i) && !h264b200EngineSubmit(e)) { r.s[i].failed = 1; break; }
+        }
+    } else
     for (i = 0; i < n_streams; i++) consume_prev(&w[0], &r.s[i], i);           /* what the last round popped */
     h264b200EngineSync(e);
     if (out) {
@@ -205,7 +335,7 @@ int h264b200DecodeStreams(h264b200_engine_t *e, const h264b200_stream_t *streams
     for (i = 0; i < n_streams; i++) {
         if (r.s[i].failed) rc = -1;
         if (r.s[i].inited) h264bsdShutdown(&r.s[i].st);
-        free(r.s[i].buf);
+        free(r.s[i].buf); free(r.s[i].outq);
     }
     pthread_mutex_destroy(&r.mu);
     free(r.s); free(w);

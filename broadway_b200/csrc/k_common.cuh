@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include "h264b200_records.h"
 #include "h264_consts.h"
+#include "kp_types.h"
 
 #define H264_MAX_SLOTS_DEV 18
 
@@ -17,13 +18,16 @@ struct PicJob {
     int16_t *coef;                 /* residual slots written by K1, read by K2/K3 */
     uint8_t *cur;                  /* frame being reconstructed */
     uint8_t *frames;               /* base of the instance's frame pool */
-    uint32_t frame_bytes;          /* wm*hm*384 */
+    uint32_t frame_bytes;          /* distance between the frames of the pool: wm*hm*384 samples + the status words behind them */
     int32_t  wm, hm;
     int32_t *progress;             /* 2*hm wavefront counters: [0,hm) K3, [hm,2hm) K4 */
     uint32_t n_intra, n_inter, any_deblock;
     uint32_t mb_base;              /* first macroblock of this picture in the batch-wide numbering */
     uint32_t n_conceal;            /* H264B200_MB_CONCEAL macroblocks (k3c_conceal.cuh) ... */
     const uint32_t *conceal_list;  /* ... their addresses in concealment order */
+    const KpResult *kp_res;        /* device-parsed picture: where kernel Kp left its findings (k0_jobs copies them into this job); else NULL */
+    uint32_t stat_off;             /* offset from `cur` of the h264b200_picstat_t that travels to the host behind the frame */
+    uint32_t pad0;
 };
 
 struct Batch {

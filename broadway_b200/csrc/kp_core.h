@@ -1,0 +1,881 @@
+/* kp_core.h — slice_data() parsing for kernel Kp: bitstream -> macroblock records + coefficient slots, ON THE DEVICE.
+ *
+ * Same job, same output bytes as the host parser (h264_slice.c, h264_cavlc_inl.h), i.e. the reference's
+ * h264bsdDecodeSliceData (h264bsd_slice_data.c:85-235), h264bsdDecodeMacroblockLayer with mb_pred / sub_mb_pred /
+ * residual / nC (h264bsd_macroblock_layer.c:133-242, :353-496, :699-869), h264bsdDecodeResidualBlockCavlc
+ * (h264bsd_cavlc.c:395-915), motion vector prediction (h264bsd_inter_prediction.c:499-1031), Intra4x4PredMode
+ * derivation (h264bsd_intra_prediction.c:1885-1936), the QP update (h264bsd_macroblock_layer.c:1043-1049),
+ * h264bsdMarkSliceCorrupted (h264bsd_slice_data.c:302-358) and the bookkeeping half of h264bsdConceal
+ * (h264bsd_conceal.c:125-255) — but organised for a GPU:
+ *
+ *   - one WARP per picture (slices of a picture in order, like the host); the bit-serial syntax walk runs on lane 0,
+ *     all 32 lanes move data: the four neighbour records + contexts are staged into shared memory with one
+ *     coalesced load per macroblock, the finished 128-byte record, the 32-byte context and the coefficient slots
+ *     go out as 16-byte stores, I_PCM samples are copied by the whole warp;
+ *   - the slot staging area is kept all-zero between macroblocks, so lane 0 only ever writes non-zero levels;
+ *   - the bit reader refills a 64-bit window with ALIGNED 32-bit words (the host pads every RBSP to 16 bytes);
+ *   - code tables (the host parser's own LUTs, built once on the host) live in shared memory.
+ *
+ * The file compiles twice: under nvcc for kp_parse.cuh (KP_LANES 32), and as plain C++ (KP_LANES 1) for the CPU
+ * test-suite, where tests/ drive it through oracle/engine_shim to check "device records == host records" and the
+ * golden MD5s without a GPU.  The product never runs the CPU build.
+ */
+#ifndef B200_KP_CORE_H
+#define B200_KP_CORE_H
+#include <stdint.h>
+#include <string.h>
+#include "h264b200_records.h"
+#include "h264b200_slices.h"
+
+#ifdef __CUDACC__
+#define KP_FN __device__ __forceinline__
+#define KP_NOINL __device__ __noinline__
+#define KP_HOT __device__ __forceinline__   /* hot: inlined so that the bit reader state stays in registers */
+#define KP_LANES 32
+#define KP_SYNC() __syncwarp()
+#define KP_BCAST(x) __shfl_sync(0xffffffffu, (x), 0)
+#define KP_CLZ(x) __clz((int)(x))
+#define KP_CTZ(x) (__ffs((int)(x)) - 1)
+#define KP_BSWAP(x) __byte_perm((x), 0, 0x0123)
+#else
+#define KP_FN static inline
+#define KP_NOINL static
+#define KP_HOT static inline
+#define KP_LANES 1
+#define KP_SYNC() ((void)0)
+#define KP_BCAST(x) (x)
+#define KP_CLZ(x) __builtin_clz(x)
+#define KP_CTZ(x) __builtin_ctz(x)
+#define KP_BSWAP(x) __builtin_bswap32(x)
+#endif
+
+#include "kp_types.h"
+
+/* lane-0 state of the slice being parsed */
+typedef struct {
+    const uint32_t *words; uint32_t n_words, wpos; uint64_t cache; int bits;
+    uint32_t rbsp_bits, payload_bits;
+    const KpTables *T; KpStage *st;
+    const h264b200_slice_t *sl;
+    uint32_t W, N, addr; int mbx, mby;
+    int is_p, qp;
+    const KpMbCtx *cA, *cB, *cC, *cD;
+    const h264b200_mb_t *rA, *rB, *rC, *rD;
+    uint32_t n_slots;            /* slots of the current macroblock */
+    uint32_t coef_used, n_intra, n_inter, any_deblock;
+    int32_t ipcm_byte;           /* >= 0: the macroblock is I_PCM, its 384 samples start at this RBSP byte */
+    uint32_t skip_run; int prev_skipped;
+} KpS;
+
+/* ------------------------------------------------------------------ bits */
+KP_FN void kp_refill(KpS &s)     /* requires bits <= 32 */
+{
+    uint32_t w = 0;
+    if (s.wpos < s.n_words) w = KP_BSWAP(s.words[s.wpos]);
+    s.wpos++;
+    s.cache |= (uint64_t)w << (32 - s.bits);
+    s.bits += 32;
+}
+KP_FN void kp_bits_init(KpS &s, const uint8_t *rbsp, uint32_t len, uint32_t bit_off, uint32_t payload_bits)
+{
+    s.words = (const uint32_t *)rbsp; s.n_words = (len + 3) >> 2;     /* the block pads every RBSP with zeros to 16 bytes */
+    s.wpos = bit_off >> 5; s.cache = 0; s.bits = 0;
+    s.rbsp_bits = len * 8; s.payload_bits = payload_bits;
+    kp_refill(s);
+    s.cache <<= (bit_off & 31); s.bits -= (int)(bit_off & 31);
+}
+KP_FN uint32_t kp_pos(const KpS &s) { return s.wpos * 32u - (uint32_t)s.bits; }
+KP_FN void kp_need32(KpS &s) { if (s.bits < 32) kp_refill(s); }
+KP_FN uint32_t kp_peek(KpS &s, int n) { if (s.bits < n) kp_refill(s); return (uint32_t)(s.cache >> (64 - n)); }   /* 1 <= n <= 32 */
+KP_FN void kp_skip(KpS &s, int n) { s.cache <<= n; s.bits -= n; }
+KP_FN uint32_t kp_get(KpS &s, int n) { uint32_t v; if (n == 0) return 0; v = kp_peek(s, n); kp_skip(s, n); return v; }
+KP_FN uint32_t kp_get1(KpS &s) { uint32_t v; if (s.bits < 1) kp_refill(s); v = (uint32_t)(s.cache >> 63); s.cache <<= 1; s.bits--; return v; }
+KP_FN uint32_t kp_ue(KpS &s)     /* 0xffffffff: malformed (h264_bits.h br_ue) */
+{
+    uint32_t v; int lz;
+    kp_need32(s);
+    v = (uint32_t)(s.cache >> 32);
+    if (v & 0x80000000u) { kp_skip(s, 1); return 0; }
+    if (v == 0) { kp_skip(s, 32); return 0xffffffffu; }
+    lz = KP_CLZ(v);
+    if (lz <= 15) { v >>= (31 - 2 * lz); kp_skip(s, 2 * lz + 1); return v - 1; }
+    kp_skip(s, lz);
+    v = kp_get(s, lz + 1);
+    return v - 1;
+}
+KP_FN int32_t kp_se(KpS &s)
+{
+    uint32_t k = kp_ue(s);
+    if (k == 0xffffffffu) return INT32_MIN;
+    return (k & 1) ? (int32_t)((k + 1) >> 1) : -(int32_t)(k >> 1);
+}
+KP_FN int kp_more_data(const KpS &s) { return kp_pos(s) < s.payload_bits; }
+KP_FN int kp_overrun(const KpS &s) { return kp_pos(s) > s.rbsp_bits; }
+
+/* ------------------------------------------------------------------ CAVLC block (h264_cavlc_inl.h) */
+/* Levels go to out[scan[i]] (scan == NULL: identity, chroma DC); `out` is all zero on entry.  Returns TotalCoeff or -1. */
+KP_HOT int kp_cavlc_block_full(KpS &s, int nc, int max_coeff, int16_t *out, const uint8_t *scan)
+{
+    const KpTables *T = s.T;
+    int16_t *level = s.st->lvl;
+    int tc, t1, i, sl, zeros_left, pos;
+    uint32_t v;
+
+    kp_need32(s);
+    v = (uint32_t)(s.cache >> 32);
+    if (nc < 0) {
+        const uint8_t *e = T->ct_cdc[v >> 24];
+        if (!e[0]) return -1;
+        kp_skip(s, e[0]); tc = e[1]; t1 = e[2];
+    } else if (nc < 8) {
+        int lz; const uint8_t *e;
+        if (nc < 2 && (v >> 31)) { kp_skip(s, 1); return 0; }
+        if (v < 0x10000u) return -1;
+        lz = KP_CLZ(v);
+        e = T->ct[(0xaa50 >> (2 * nc)) & 3][lz * 8 + ((v >> (28 - lz)) & 7)];
+        if (!e[0]) return -1;
+        kp_skip(s, e[0]); tc = e[1]; t1 = e[2];
+    } else {
+        v >>= 26; kp_skip(s, 6);
+        if (v == 3) { tc = 0; t1 = 0; }
+        else { tc = (int)(v >> 2) + 1; t1 = (int)(v & 3); if (t1 > tc) return -1; }
+    }
+    if (tc == 0) return 0;
+    if (tc > max_coeff) return -1;
+
+    sl = (tc > 10 && t1 < 3) ? 1 : 0;
+    {
+        const uint32_t sg = (uint32_t)(s.cache >> 61);           /* at least 16 valid bits are left here */
+        level[0] = (int16_t)(1 - (int)((sg >> 1) & 2)); level[1] = (int16_t)(1 - (int)(sg & 2)); level[2] = (int16_t)(1 - (int)((sg << 1) & 2));
+        kp_skip(s, t1);
+    }
+    for (i = t1; i < tc; i++) {
+        int lv;
+        const int8_t *q;
+        kp_need32(s);
+        v = (uint32_t)(s.cache >> 32);
+        q = T->lvl[sl][v >> 24];
+        if (q[1] && i != t1) { level[i] = q[0]; kp_skip(s, q[1]); sl = q[2]; continue; }
+        if (q[1]) {
+            lv = q[0];
+            kp_skip(s, q[1]);
+            if (t1 < 3) lv += lv > 0 ? 1 : -1;
+        } else {
+            int prefix, code;
+            if (v < 0x10000u) return -1;
+            prefix = KP_CLZ(v);
+            kp_skip(s, prefix + 1);
+            code = (prefix < 15 ? prefix : 15) << sl;
+            if (sl > 0 || prefix >= 14) {
+                int size = (prefix == 14 && sl == 0) ? 4 : prefix >= 15 ? 12 : sl;
+                code += (int)kp_get(s, size);
+            }
+            if (prefix >= 15 && sl == 0) code += 15;
+            if (i == t1 && t1 < 3) code += 2;
+            lv = (code & 1) ? (-code - 1) >> 1 : (code + 2) >> 1;
+        }
+        level[i] = (int16_t)lv;
+        if (sl == 0) sl = 1;
+        if ((lv < 0 ? -lv : lv) > (3 << (sl - 1)) && sl < 6) sl++;
+    }
+
+    if (tc < max_coeff) {
+        const uint8_t *e = nc < 0 ? T->tz_cdc[tc - 1][kp_peek(s, 3)] : T->tz[tc - 1][kp_peek(s, 9)];
+        if (!e[0]) return -1;
+        kp_skip(s, e[0]); zeros_left = e[1];
+        if (zeros_left + tc > max_coeff) return -1;
+    } else zeros_left = 0;
+
+    pos = zeros_left + tc - 1;
+    for (i = 0; i < tc - 1 && zeros_left > 0; i++) {
+        int run;
+        out[scan ? scan[pos] : pos] = level[i];
+        {
+            const uint8_t *e = T->rb[(zeros_left < 7 ? zeros_left : 7) - 1][kp_peek(s, 3)];
+            if (e[0]) { kp_skip(s, e[0]); run = e[1]; }
+            else {
+                int lz;
+                v = kp_peek(s, 11);
+                if (!v) return -1;
+                lz = KP_CLZ(v) - 21;
+                run = lz + 4; kp_skip(s, lz + 1);
+            }
+        }
+        if (run > zeros_left) return -1;
+        zeros_left -= run;
+        pos -= run + 1;
+    }
+    for (; i < tc; i++, pos--) out[scan ? scan[pos] : pos] = level[i];
+    return tc;
+}
+KP_FN int kp_cavlc_block(KpS &s, int nc, int max_coeff, int16_t *out, const uint8_t *scan)
+{
+    if ((unsigned)nc < 2u) {
+        if (s.bits < 1) kp_refill(s);
+        if (s.cache >> 63) { kp_skip(s, 1); return 0; }
+    }
+    return kp_cavlc_block_full(s, nc, max_coeff, out, scan);
+}
+
+/* ------------------------------------------------------------------ motion vector prediction (h264_slice.c) */
+typedef struct { int avail, ref, x, y; } KpMvn;
+
+KP_FN KpMvn kp_mvn_from(const KpMbCtx *c, const h264b200_mb_t *r, int x4, int y4)
+{
+    KpMvn n; n.avail = 0; n.ref = -1; n.x = n.y = 0;
+    if (!c) return n;
+    n.avail = 1;
+    if (c->kind == H264B200_MB_INTER) {
+        n.ref = c->ref_idx[(y4 >> 1) * 2 + (x4 >> 1)];
+        n.x = r->mv[y4 * 4 + x4][0]; n.y = r->mv[y4 * 4 + x4][1];
+    }
+    return n;
+}
+KP_FN KpMvn kp_mvn_at(const KpS &s, int x4, int y4, unsigned done)
+{
+    KpMvn n; n.avail = 0; n.ref = -1; n.x = n.y = 0;
+    if (y4 < 0) {
+        if (x4 < 0) return kp_mvn_from(s.cD, s.rD, 3, 3);
+        if (x4 > 3) return kp_mvn_from(s.cC, s.rC, x4 - 4, 3);
+        return kp_mvn_from(s.cB, s.rB, x4, 3);
+    }
+    if (x4 < 0) return kp_mvn_from(s.cA, s.rA, 3, y4);
+    if (x4 > 3) return n;
+    if (!((done >> (y4 * 4 + x4)) & 1)) return n;
+    n.avail = 1;
+    n.ref = s.st->ctx.ref_idx[(y4 >> 1) * 2 + (x4 >> 1)];
+    n.x = s.st->rec.mv[y4 * 4 + x4][0]; n.y = s.st->rec.mv[y4 * 4 + x4][1];
+    return n;
+}
+KP_FN int kp_median3(int a, int b, int c) { int mx = a > b ? a : b, mn = a < b ? a : b; return c > mx ? mx : c < mn ? mn : c; }
+
+/* dir: 0 median, 1 A first, 2 B first, 3 C first */
+KP_HOT void kp_predict_mv(const KpS &s, int x4, int y4, int w4, int ref, unsigned done, int dir, int *px, int *py)
+{
+    KpMvn a = kp_mvn_at(s, x4 - 1, y4, done), b = kp_mvn_at(s, x4, y4 - 1, done), c = kp_mvn_at(s, x4 + w4, y4 - 1, done);
+    if (!c.avail) c = kp_mvn_at(s, x4 - 1, y4 - 1, done);
+    if (dir == 1 && a.ref == ref) { *px = a.x; *py = a.y; return; }
+    if (dir == 2 && b.ref == ref) { *px = b.x; *py = b.y; return; }
+    if (dir == 3 && c.ref == ref) { *px = c.x; *py = c.y; return; }
+    if (b.avail || c.avail || !a.avail) {
+        int ia = a.ref == ref, ib = b.ref == ref, ic = c.ref == ref;
+        if (ia + ib + ic != 1) { *px = kp_median3(a.x, b.x, c.x); *py = kp_median3(a.y, b.y, c.y); }
+        else if (ia) { *px = a.x; *py = a.y; }
+        else if (ib) { *px = b.x; *py = b.y; }
+        else { *px = c.x; *py = c.y; }
+    } else { *px = a.x; *py = a.y; }
+}
+KP_FN int kp_mv_in_range(int x, int y) { return x >= -8192 && x <= 8191 && y >= -2048 && y <= 2047; }
+KP_FN void kp_fill_mv(h264b200_mb_t *r, int x4, int y4, int w4, int h4, int mx, int my, unsigned *done)
+{
+    const uint32_t v = (uint32_t)(uint16_t)mx | ((uint32_t)(uint16_t)my << 16);
+    for (int j = y4; j < y4 + h4; j++) {
+        uint32_t *row = (uint32_t *)r->mv[j * 4 + x4];
+        for (int i = 0; i < w4; i++) row[i] = v;
+        *done |= ((1u << w4) - 1u) << (j * 4 + x4);
+    }
+}
+
+/* ------------------------------------------------------------------ residual */
+/* nC (9.2.1): the blocks to the left of / above luma4x4BlkIdx b, one nibble each; blocks 0,2,8,10 take the left one
+ * from macroblock A, blocks 0,1,4,5 the upper one from macroblock B */
+#define KP_LEFT_BLK 0xEBC9AF8D63412705ull
+#define KP_UP_BLK   0xDC76983254FE10BAull
+KP_FN int kp_nc_avg(int a, int b)            /* 64 = not available */
+{
+    int n = a + b;
+    if (n < 64) n = (n + 1) >> 1;
+    return n & 31;
+}
+KP_FN int kp_nc_luma(const KpS &s, int blk)
+{
+    const int lb = (int)((KP_LEFT_BLK >> (4 * blk)) & 15), ub = (int)((KP_UP_BLK >> (4 * blk)) & 15);
+    const int a = ((0x0505 >> blk) & 1) ? (s.cA ? s.cA->tc[lb] : 64) : s.st->ctx.tc[lb];
+    const int b = ((0x0033 >> blk) & 1) ? (s.cB ? s.cB->tc[ub] : 64) : s.st->ctx.tc[ub];
+    return kp_nc_avg(a, b);
+}
+KP_FN int kp_nc_chroma(const KpS &s, int pl, int k)
+{
+    const int base = 16 + 4 * pl;
+    const int a = (k & 1) ? s.st->ctx.tc[base + k - 1] : (s.cA ? s.cA->tc[base + k + 1] : 64);
+    const int b = (k & 2) ? s.st->ctx.tc[base + k - 2] : (s.cB ? s.cB->tc[base + k + 2] : 64);
+    return kp_nc_avg(a, b);
+}
+
+KP_HOT int kp_parse_residual(KpS &s, int cbp, int i16)
+{
+    h264b200_mb_t *r = &s.st->rec; KpMbCtx *c = &s.st->ctx;
+    const uint8_t *zz = s.T->zigzag;
+    uint32_t slot = 0, mask = 0;
+    int blk, pl, k, tc, dc_nz = 0;
+
+    r->coef_offset = s.coef_used;
+    if (i16) {
+        /* nC of the DC block = nC of block 0 */
+        tc = kp_cavlc_block(s, kp_nc_luma(s, 0), 16, s.st->slots, zz);
+        if (tc < 0) return -1;
+        if (tc) { dc_nz = 1; mask |= H264B200_RESID_LUMA_DC; slot++; }
+    }
+    for (blk = 0; blk < 16; blk++) {
+        int16_t *p;
+        if (!((cbp >> (blk >> 2)) & 1)) {
+            if (dc_nz) { mask |= 15u << blk; slot += 4; }        /* four all-zero slots (staging is zero) */
+            blk += 3;
+            continue;
+        }
+        p = s.st->slots + slot * 16;
+        if (i16) tc = kp_cavlc_block(s, kp_nc_luma(s, blk), 15, p, zz + 1);
+        else     tc = kp_cavlc_block(s, kp_nc_luma(s, blk), 16, p, zz);
+        if (tc < 0) return -1;
+        c->tc[blk] = (uint8_t)tc;
+        if (tc) { r->nz_mask |= (uint16_t)(1u << blk); mask |= 1u << blk; slot++; }
+        else if (dc_nz) { mask |= 1u << blk; slot++; }
+    }
+    if (cbp & 0x30) {
+        int16_t *p = s.st->slots + slot * 16;
+        int cdc[2];
+        for (pl = 0; pl < 2; pl++) {
+            cdc[pl] = kp_cavlc_block(s, -1, 4, p + 4 * pl, NULL);
+            if (cdc[pl] < 0) return -1;
+        }
+        if (cdc[0] || cdc[1]) { mask |= H264B200_RESID_CHROMA_DC; slot++; }
+        for (pl = 0; pl < 2; pl++) for (k = 0; k < 4; k++) {
+            p = s.st->slots + slot * 16;
+            tc = 0;
+            if (cbp & 0x20) {
+                tc = kp_cavlc_block(s, kp_nc_chroma(s, pl, k), 15, p, zz + 1);
+                if (tc < 0) return -1;
+            }
+            c->tc[16 + 4 * pl + k] = (uint8_t)tc;
+            if (tc) { mask |= 1u << (16 + 4 * pl + k); slot++; }
+            else if (cdc[pl]) { mask |= 1u << (16 + 4 * pl + k); slot++; }
+        }
+    }
+    r->resid_mask = mask;
+    s.n_slots = slot;
+    return 0;
+}
+
+/* ------------------------------------------------------------------ intra */
+KP_FN int kp_intra_usable(const KpS &s, const KpMbCtx *c)
+{
+    return c && !(s.sl->constrained_intra && c->kind == H264B200_MB_INTER);
+}
+KP_FN int kp_pred_i4_mode(const KpS &s, int blk)
+{
+    const uint8_t *r2b = s.T->raster_to_blk;
+    int r = r2b[blk], x4 = r & 3, y4 = r >> 2, ma, mb;
+    if (x4 > 0) ma = s.st->rec.i4_mode[r2b[r - 1]];
+    else {
+        if (!kp_intra_usable(s, s.cA)) return 2;
+        ma = s.cA->kind == H264B200_MB_I4x4 ? s.rA->i4_mode[r2b[r + 3]] : 2;
+    }
+    if (y4 > 0) mb = s.st->rec.i4_mode[r2b[r - 4]];
+    else {
+        if (!kp_intra_usable(s, s.cB)) return 2;
+        mb = s.cB->kind == H264B200_MB_I4x4 ? s.rB->i4_mode[r2b[12 + x4]] : 2;
+    }
+    return ma < mb ? ma : mb;
+}
+KP_FN int kp_update_qp(KpS &s, int delta)
+{
+    if (delta < -26 || delta > 25) return -1;
+    if (delta) { s.qp += delta; if (s.qp < 0) s.qp += 52; else if (s.qp >= 52) s.qp -= 52; }
+    return 0;
+}
+KP_FN void kp_set_qp_fields(const KpS &s, h264b200_mb_t *r)
+{
+    int qc = s.qp + s.sl->chroma_qp_off;
+    qc = qc < 0 ? 0 : qc > 51 ? 51 : qc;
+    r->qp_y = (uint8_t)s.qp; r->qp_dbk = (uint8_t)s.qp; r->qp_c = s.T->qpc[qc];
+}
+
+KP_HOT int kp_parse_intra_mb(KpS &s, uint32_t mb_type /* 0 I4x4, 1..24 I16x16, 25 I_PCM */)
+{
+    h264b200_mb_t *r = &s.st->rec; KpMbCtx *c = &s.st->ctx;
+    const int aA = kp_intra_usable(s, s.cA), aB = kp_intra_usable(s, s.cB), aC = kp_intra_usable(s, s.cC), aD = kp_intra_usable(s, s.cD);
+    uint32_t v; int blk, cbp;
+    r->avail = (uint8_t)((aA ? H264B200_AVAIL_A : 0) | (aB ? H264B200_AVAIL_B : 0) | (aC ? H264B200_AVAIL_C : 0) | (aD ? H264B200_AVAIL_D : 0));
+    c->ref_idx[0] = c->ref_idx[1] = c->ref_idx[2] = c->ref_idx[3] = -1;
+    s.n_intra++;
+    if (mb_type == 25) {
+        uint32_t byte_pos;
+        c->kind = r->mb_class = H264B200_MB_IPCM;
+        while (kp_pos(s) & 7) if (kp_get1(s)) return -1;            /* pcm_alignment_zero_bit */
+        byte_pos = kp_pos(s) >> 3;
+        if (byte_pos + 384 > (s.rbsp_bits >> 3)) return -1;
+        r->coef_offset = s.coef_used;
+        s.ipcm_byte = (int32_t)byte_pos;                           /* the warp copies the samples when the macroblock is stored */
+        s.n_slots = 12;
+        {   /* reposition behind the samples */
+            const uint32_t np = byte_pos + 384;
+            s.wpos = np >> 2; s.cache = 0; s.bits = 0;
+            kp_refill(s);
+            s.cache <<= 8 * (np & 3); s.bits -= (int)(8 * (np & 3));
+        }
+        for (blk = 0; blk < 24; blk++) c->tc[blk] = 16;
+        r->nz_mask = 0xffff;
+        kp_set_qp_fields(s, r);
+        r->qp_dbk = 0;
+        return 0;
+    }
+    if (mb_type == 0) {
+        const uint8_t *r2b = s.T->raster_to_blk;
+        c->kind = r->mb_class = H264B200_MB_I4x4;
+        for (blk = 0; blk < 16; blk++) {
+            int pred = kp_pred_i4_mode(s, blk), mode;
+            if (kp_get1(s)) mode = pred;
+            else { int rem = (int)kp_get(s, 3); mode = rem < pred ? rem : rem + 1; }
+            r->i4_mode[blk] = (uint8_t)mode;
+            {
+                int rr = r2b[blk], x4 = rr & 3, y4 = rr >> 2;
+                int left = x4 > 0 ? 1 : aA, up = y4 > 0 ? 1 : aB;
+                int ul = (x4 > 0 && y4 > 0) ? 1 : x4 > 0 ? aB : y4 > 0 ? aA : aD;
+                switch (mode) {
+                case 0: case 3: case 7: if (!up) return -1; break;
+                case 1: case 8: if (!left) return -1; break;
+                case 4: case 5: case 6: if (!up || !left || !ul) return -1; break;
+                default: break;
+                }
+            }
+        }
+    } else {
+        c->kind = r->mb_class = H264B200_MB_I16x16;
+        r->i16_mode = (uint8_t)((mb_type - 1) & 3);
+        switch (r->i16_mode) {
+        case 0: if (!aB) return -1; break;
+        case 1: if (!aA) return -1; break;
+        case 3: if (!aA || !aB || !aD) return -1; break;
+        default: break;
+        }
+    }
+    v = kp_ue(s); if (v > 3) return -1;
+    r->chroma_mode = (uint8_t)v;
+    switch (v) {
+    case 1: if (!aA) return -1; break;
+    case 2: if (!aB) return -1; break;
+    case 3: if (!aA || !aB || !aD) return -1; break;
+    default: break;
+    }
+    if (mb_type == 0) {
+        v = kp_ue(s); if (v > 47) return -1;
+        cbp = s.T->cbp_map[v][0];
+    } else cbp = (((mb_type - 1) >> 2) % 3) << 4 | (mb_type >= 13 ? 15 : 0);
+    if (cbp || mb_type != 0) {
+        if (kp_update_qp(s, kp_se(s))) return -1;
+        kp_set_qp_fields(s, r);
+        if (kp_parse_residual(s, cbp, mb_type != 0)) return -1;
+    } else kp_set_qp_fields(s, r);
+    return 0;
+}
+
+/* ------------------------------------------------------------------ inter */
+KP_FN int kp_read_ref_idx(KpS &s, uint32_t n_active)
+{
+    uint32_t v;
+    if (n_active <= 1) return 0;
+    v = n_active - 1 > 1 ? kp_ue(s) : !kp_get1(s);               /* te(v) */
+    if (v >= n_active) return -1;
+    return (int)v;
+}
+KP_FN int kp_set_ref(KpS &s, int q, int ref)
+{
+    int slot = ref <= 16 ? s.sl->ref_slot[ref] : -1;
+    if (slot < 0) return -1;
+    s.st->ctx.ref_idx[q] = (int8_t)ref; s.st->rec.ref_slot[q] = (uint8_t)slot;
+    return 0;
+}
+
+KP_HOT int kp_parse_inter_mb(KpS &s, uint32_t mb_type /* 0..4 */)
+{
+    h264b200_mb_t *r = &s.st->rec; KpMbCtx *c = &s.st->ctx;
+    const uint32_t n_active = s.sl->num_ref_idx_active;
+    uint32_t v;
+    unsigned done = 0;
+    int px, py, mx, my, i, cbp;
+    c->kind = r->mb_class = H264B200_MB_INTER;
+    s.n_inter++;
+    if (mb_type == 0) {
+        int ref = kp_read_ref_idx(s, n_active), dx, dy;
+        if (ref < 0) return -1;
+        for (i = 0; i < 4; i++) if (kp_set_ref(s, i, ref)) return -1;
+        dx = kp_se(s); dy = kp_se(s);
+        kp_predict_mv(s, 0, 0, 4, ref, 0, 0, &px, &py);
+        mx = (int16_t)((unsigned)px + (unsigned)dx); my = (int16_t)((unsigned)py + (unsigned)dy);
+        if (!kp_mv_in_range(mx, my)) return -1;
+        kp_fill_mv(r, 0, 0, 4, 4, mx, my, &done);
+        r->part_flags = 31;
+    } else if (mb_type == 1 || mb_type == 2) {
+        int ref[2], dx[2], dy[2];
+        for (i = 0; i < 2; i++) { ref[i] = kp_read_ref_idx(s, n_active); if (ref[i] < 0) return -1; }
+        for (i = 0; i < 2; i++) { dx[i] = kp_se(s); dy[i] = kp_se(s); }
+        if (mb_type == 1) { if (kp_set_ref(s, 0, ref[0]) || kp_set_ref(s, 1, ref[0]) || kp_set_ref(s, 2, ref[1]) || kp_set_ref(s, 3, ref[1])) return -1; }
+        else              { if (kp_set_ref(s, 0, ref[0]) || kp_set_ref(s, 2, ref[0]) || kp_set_ref(s, 1, ref[1]) || kp_set_ref(s, 3, ref[1])) return -1; }
+        for (i = 0; i < 2; i++) {
+            if (mb_type == 1) kp_predict_mv(s, 0, 2 * i, 4, ref[i], done, i == 0 ? 2 : 1, &px, &py);
+            else              kp_predict_mv(s, 2 * i, 0, 2, ref[i], done, i == 0 ? 1 : 3, &px, &py);
+            mx = (int16_t)((unsigned)px + (unsigned)dx[i]); my = (int16_t)((unsigned)py + (unsigned)dy[i]);
+            if (!kp_mv_in_range(mx, my)) return -1;
+            if (mb_type == 1) kp_fill_mv(r, 0, 2 * i, 4, 2, mx, my, &done);
+            else              kp_fill_mv(r, 2 * i, 0, 2, 4, mx, my, &done);
+        }
+        r->part_flags = 15;
+    } else {
+        int sub[4], ref[4], q, k;
+        uint32_t *mvd = s.st->mvd;                                /* read before any vector is derived (sub_mb_pred order) */
+        int n = 0, m = 0;
+        for (q = 0; q < 4; q++) { v = kp_ue(s); if (v > 3) return -1; sub[q] = (int)v; if (!v) r->part_flags |= (uint8_t)(1 << q); }
+        for (q = 0; q < 4; q++) {
+            ref[q] = mb_type == 4 ? 0 : kp_read_ref_idx(s, n_active);
+            if (ref[q] < 0 || kp_set_ref(s, q, ref[q])) return -1;
+        }
+        for (q = 0; q < 4; q++) {
+            int cnt = sub[q] == 0 ? 1 : sub[q] == 3 ? 4 : 2;
+            for (k = 0; k < cnt; k++) {
+                const uint32_t dx = (uint32_t)kp_se(s), dy = (uint32_t)kp_se(s);
+                mvd[n++] = (dx & 0xffffu) | (dy << 16);
+            }
+        }
+        for (q = 0; q < 4; q++) {
+            int ox = (q & 1) * 2, oy = (q >> 1) * 2, cnt = sub[q] == 0 ? 1 : sub[q] == 3 ? 4 : 2;
+            for (k = 0; k < cnt; k++, m++) {
+                int x4, y4, w4, h4;
+                switch (sub[q]) {
+                case 0: x4 = ox; y4 = oy; w4 = 2; h4 = 2; break;
+                case 1: x4 = ox; y4 = oy + k; w4 = 2; h4 = 1; break;
+                case 2: x4 = ox + k; y4 = oy; w4 = 1; h4 = 2; break;
+                default: x4 = ox + (k & 1); y4 = oy + (k >> 1); w4 = 1; h4 = 1; break;
+                }
+                kp_predict_mv(s, x4, y4, w4, ref[q], done, 0, &px, &py);
+                mx = (int16_t)((unsigned)px + (mvd[m] & 0xffffu)); my = (int16_t)((unsigned)py + (mvd[m] >> 16));
+                if (!kp_mv_in_range(mx, my)) return -1;
+                kp_fill_mv(r, x4, y4, w4, h4, mx, my, &done);
+            }
+        }
+    }
+    v = kp_ue(s); if (v > 47) return -1;
+    cbp = s.T->cbp_map[v][1];
+    if (cbp) {
+        if (kp_update_qp(s, kp_se(s))) return -1;
+        kp_set_qp_fields(s, r);
+        if (kp_parse_residual(s, cbp, 0)) return -1;
+    } else kp_set_qp_fields(s, r);
+    return 0;
+}
+
+KP_HOT int kp_do_skip_mb(KpS &s)
+{
+    h264b200_mb_t *r = &s.st->rec; KpMbCtx *c = &s.st->ctx;
+    KpMvn a = kp_mvn_at(s, -1, 0, 0), bq = kp_mvn_at(s, 0, -1, 0);
+    int mx = 0, my = 0, i;
+    unsigned done = 0;
+    c->kind = r->mb_class = H264B200_MB_INTER;
+    s.n_inter++;
+    for (i = 0; i < 4; i++) if (kp_set_ref(s, i, 0)) return -1;
+    if (a.avail && bq.avail && !(a.ref == 0 && a.x == 0 && a.y == 0) && !(bq.ref == 0 && bq.x == 0 && bq.y == 0)) {
+        kp_predict_mv(s, 0, 0, 4, 0, 0, 0, &mx, &my);
+        if (!kp_mv_in_range(mx, my)) return -1;
+    }
+    kp_fill_mv(r, 0, 0, 4, 4, mx, my, &done);
+    r->part_flags = 31;
+    kp_set_qp_fields(s, r);
+    return 0;
+}
+
+/* ------------------------------------------------------------------ one macroblock (lane 0) */
+#define KP_MB_OK        0
+#define KP_MB_FAIL      1    /* syntax error: the context of the macroblock is cleared, nothing else is stored */
+#define KP_MB_FAIL_KEEP 2    /* the macroblock had been decoded before (h264_slice.c: `if (c->decoded) return -1`): nothing is touched */
+
+/* neighbours are staged in s.st->nrec / nctx; returns KP_MB_* and leaves record / context / slots in the staging area */
+KP_FN int kp_parse_mb(KpS &s)
+{
+    KpStage *st = s.st;
+    h264b200_mb_t *r = &st->rec; KpMbCtx *c = &st->ctx;
+    const h264b200_slice_t *sl = s.sl;
+    const uint16_t sid = sl->slice_id;
+    int rc;
+    if (st->old.decoded) return KP_MB_FAIL_KEEP;
+    c->slice_id = sid; r->slice_id = sid;
+    r->chroma_qp_off = sl->chroma_qp_off;
+    r->dbk_off_a = sl->alpha_off; r->dbk_off_b = sl->beta_off;
+    r->dbk_idc = sl->disable_deblocking_idc;
+    s.cA = s.cB = s.cC = s.cD = NULL; s.rA = s.rB = s.rC = s.rD = NULL;
+    if (s.mbx > 0 && st->nctx[0].slice_id == sid) { s.cA = &st->nctx[0]; s.rA = &st->nrec[0]; }
+    if (s.mby > 0) {
+        if (st->nctx[1].slice_id == sid) { s.cB = &st->nctx[1]; s.rB = &st->nrec[1]; }
+        if (s.mbx + 1 < (int)s.W && st->nctx[2].slice_id == sid) { s.cC = &st->nctx[2]; s.rC = &st->nrec[2]; }
+        if (s.mbx > 0 && st->nctx[3].slice_id == sid) { s.cD = &st->nctx[3]; s.rD = &st->nrec[3]; }
+    }
+    s.n_slots = 0; s.ipcm_byte = -1;
+    if (s.is_p && !s.prev_skipped) {
+        s.skip_run = kp_ue(s);
+        if (s.skip_run == 0xffffffffu || s.skip_run > s.N - s.addr) return KP_MB_FAIL;
+        if (s.skip_run) s.prev_skipped = 1;
+    }
+    if (s.skip_run) { s.skip_run--; rc = kp_do_skip_mb(s); }
+    else {
+        uint32_t mb_type = kp_ue(s);
+        s.prev_skipped = 0;
+        if (s.is_p) {
+            if (mb_type > 30) return KP_MB_FAIL;
+            rc = mb_type < 5 ? kp_parse_inter_mb(s, mb_type) : kp_parse_intra_mb(s, mb_type - 5);
+        } else {
+            if (mb_type > 25) return KP_MB_FAIL;
+            rc = kp_parse_intra_mb(s, mb_type);
+        }
+    }
+    if (rc || kp_overrun(s)) return KP_MB_FAIL;
+    if (sl->disable_deblocking_idc != 1) {
+        int fl = H264B200_DBK_INNER;
+        if (s.mbx > 0 && (sl->disable_deblocking_idc != 2 || st->nctx[0].slice_id == sid)) fl |= H264B200_DBK_LEFT;
+        if (s.mby > 0 && (sl->disable_deblocking_idc != 2 || st->nctx[1].slice_id == sid)) fl |= H264B200_DBK_TOP;
+        r->dbk_flags = (uint8_t)fl;
+        s.any_deblock = 1;
+    }
+    c->decoded = 1;
+    return KP_MB_OK;
+}
+
+/* ------------------------------------------------------------------ warp-cooperative data movement */
+#ifdef __CUDACC__
+typedef uint4 KpU4;
+#else
+typedef struct { uint32_t x, y, z, w; } KpU4;
+#endif
+
+/* stage the neighbours A, B, C, D of macroblock `addr` (records + contexts) and the old context of `addr` itself;
+ * clear the record / context being built */
+KP_FN void kp_stage_in(int lane, const KpPic &p, KpStage *st, uint32_t addr, int mbx, int mby, uint32_t W)
+{
+    for (int v = lane; v < 32; v += KP_LANES) {
+        const int nb = v >> 3, part = v & 7;
+        const int ok = nb == 0 ? mbx > 0 : nb == 1 ? mby > 0 : nb == 2 ? (mby > 0 && mbx + 1 < (int)W) : (mby > 0 && mbx > 0);
+        const uint32_t na = nb == 0 ? addr - 1 : nb == 1 ? addr - W : nb == 2 ? addr - W + 1 : addr - W - 1;
+        if (ok) ((KpU4 *)&st->nrec[nb])[part] = ((const KpU4 *)&p.mbs[na])[part];
+        if (part < 2) {
+            KpU4 z = {0, 0, 0, 0};
+            if (ok) z = ((const KpU4 *)&p.ctx[na])[part];
+            ((KpU4 *)&st->nctx[nb])[part] = z;
+        }
+        if (nb == 0 && part >= 2 && part < 4) ((KpU4 *)&st->old)[part - 2] = ((const KpU4 *)&p.ctx[addr])[part - 2];
+        if (nb == 1 && part >= 2 && part < 4) { KpU4 z = {0, 0, 0, 0}; ((KpU4 *)&st->ctx)[part - 2] = z; }
+        if (nb == 2) { KpU4 z = {0, 0, 0, 0}; ((KpU4 *)&st->rec)[part] = z; }
+    }
+}
+
+/* store the finished macroblock: record, context, coefficient slots (re-zeroing the staging area) or I_PCM samples */
+KP_FN void kp_stage_out(int lane, const KpPic &p, KpStage *st, uint32_t addr, uint32_t coef_off, uint32_t n_slots,
+                        int32_t ipcm_byte, const uint8_t *rbsp)
+{
+    for (int v = lane; v < 32; v += KP_LANES) {
+        if (v < 8) ((KpU4 *)&p.mbs[addr])[v] = ((const KpU4 *)&st->rec)[v];
+        else if (v < 10) ((KpU4 *)&p.ctx[addr])[v - 8] = ((const KpU4 *)&st->ctx)[v - 8];
+    }
+    if (ipcm_byte >= 0) {
+        uint32_t *dst = (uint32_t *)(p.coef + (size_t)coef_off * 16);
+        const uint8_t *src = rbsp + ipcm_byte;
+        for (int i = lane; i < 96; i += KP_LANES)
+            dst[i] = (uint32_t)src[4 * i] | ((uint32_t)src[4 * i + 1] << 8) | ((uint32_t)src[4 * i + 2] << 16) | ((uint32_t)src[4 * i + 3] << 24);
+    } else {
+        KpU4 *dst = (KpU4 *)(p.coef + (size_t)coef_off * 16);
+        KpU4 *src = (KpU4 *)st->slots;
+        const KpU4 z = {0, 0, 0, 0};
+        for (uint32_t i = (uint32_t)lane; i < 2 * n_slots; i += KP_LANES) { dst[i] = src[i]; src[i] = z; }
+    }
+}
+KP_FN void kp_stage_clear(int lane, KpStage *st)
+{
+    const KpU4 z = {0, 0, 0, 0};
+    for (int i = lane; i < (int)(sizeof st->slots / 16); i += KP_LANES) ((KpU4 *)st->slots)[i] = z;
+}
+
+/* ------------------------------------------------------------------ failed slices and lost macroblocks (lane 0) */
+/* h264_decoder.c mark_slice_corrupted (h264bsdMarkSliceCorrupted, h264bsd_slice_data.c:302-358) */
+KP_NOINL void kp_mark_slice_corrupted(const KpPic &p, const h264b200_slice_t *sl, const uint8_t *map, uint32_t W, uint32_t N, uint32_t slice_last_mb)
+{
+    const uint16_t sid = sl->slice_id;
+    uint32_t cur = sl->first_mb;
+    if (cur >= N) return;
+    if (slice_last_mb) {
+        uint32_t i = slice_last_mb - 1, cnt = 0, lim = W > 10 ? W : 10;
+        while (i > cur) {
+            if (p.ctx[i].slice_id == sid && ++cnt >= lim) break;
+            i--;
+        }
+        cur = i;
+    }
+    do {
+        if (p.ctx[cur].slice_id != sid || !p.ctx[cur].decoded) break;
+        p.ctx[cur].decoded = 0;
+        if (map) {
+            const uint8_t grp = map[cur];
+            do cur++; while (cur < N && map[cur] != grp);
+            if (cur >= N) cur = 0;
+        } else cur = cur + 1 < N ? cur + 1 : 0;
+    } while (cur);
+}
+
+KP_FN void kp_zero_rec(h264b200_mb_t *r) { KpU4 z = {0, 0, 0, 0}; for (int i = 0; i < 8; i++) ((KpU4 *)r)[i] = z; }
+
+/* h264_decoder.c conceal_picture: records for the macroblocks no slice delivered.  Returns their number. */
+KP_NOINL uint32_t kp_conceal_picture(const KpPic &p, const KpTables *T, const h264b200_pichdr_t *hdr, uint32_t num_decoded, KpResult &res)
+{
+    const uint32_t W = hdr->width_mbs, H = hdr->height_mbs, N = W * H;
+    const int whole = num_decoded == 0;
+    const int ref = hdr->conceal_as_p ? hdr->conceal_ref_slot : -1;
+    uint32_t i, n = 0;
+    res.n_conceal = 0;
+    if (ref >= 0 || whole) {
+        for (i = 0; i < N; i++) {
+            h264b200_mb_t *r = &p.mbs[i];
+            if (p.ctx[i].decoded) continue;
+            kp_zero_rec(r);
+            n++;
+            if (ref >= 0) {
+                r->mb_class = H264B200_MB_INTER; r->part_flags = 31;
+                for (int q = 0; q < 4; q++) r->ref_slot[q] = (uint8_t)ref;
+                r->qp_y = r->qp_dbk = 40; r->qp_c = T->qpc[40];
+                r->flags = H264B200_MBF_DBK_AS_INTRA;
+                if (!whole) {
+                    r->dbk_flags = (uint8_t)(H264B200_DBK_INNER | (i % W ? H264B200_DBK_LEFT : 0) | (i >= W ? H264B200_DBK_TOP : 0));
+                    res.any_deblock = 1;
+                }
+                res.n_inter++;
+            } else {
+                uint32_t *dst;
+                if (res.coef_used + 12 > p.coef_cap) { r->mb_class = H264B200_MB_MISSING; continue; }
+                r->mb_class = H264B200_MB_IPCM; r->coef_offset = res.coef_used; r->nz_mask = 0xffff;
+                dst = (uint32_t *)(p.coef + (size_t)res.coef_used * 16);
+                for (int k = 0; k < 96; k++) dst[k] = 0x80808080u;
+                res.coef_used += 12; res.n_intra++;
+            }
+        }
+        if (whole) for (i = 0; i < N; i++) p.mbs[i].dbk_flags = 0;
+        return n;
+    }
+    {
+        uint32_t lost = N - num_decoded, need = (lost * 4 + 31) / 32, *list, row, col, j;
+        if (res.coef_used + need > p.coef_cap) {
+            for (i = 0; i < N; i++) if (!p.ctx[i].decoded) { kp_zero_rec(&p.mbs[i]); p.mbs[i].mb_class = H264B200_MB_MISSING; }
+            return lost;
+        }
+        list = (uint32_t *)(p.coef + (size_t)res.coef_used * 16);
+        res.conceal_offset = res.coef_used;
+        for (i = 0; i < N && !p.ctx[i].decoded; i++) ;
+        row = i / W; col = i % W;
+#define KP_CONCEAL_ONE(addr_) do { \
+            const uint32_t a_ = (addr_), y_ = a_ / W, x_ = a_ % W; \
+            h264b200_mb_t *r_ = &p.mbs[a_]; \
+            kp_zero_rec(r_); \
+            r_->mb_class = H264B200_MB_CONCEAL; \
+            r_->avail = (uint8_t)((y_ > 0 && p.ctx[a_ - W].decoded ? H264B200_CN_ABOVE : 0) | (y_ + 1 < H && p.ctx[a_ + W].decoded ? H264B200_CN_BELOW : 0) | \
+                                  (x_ > 0 && p.ctx[a_ - 1].decoded ? H264B200_CN_LEFT : 0) | (x_ + 1 < W && p.ctx[a_ + 1].decoded ? H264B200_CN_RIGHT : 0)); \
+            r_->qp_y = r_->qp_dbk = 40; r_->qp_c = T->qpc[40]; \
+            r_->dbk_flags = (uint8_t)(H264B200_DBK_INNER | (x_ ? H264B200_DBK_LEFT : 0) | (y_ ? H264B200_DBK_TOP : 0)); \
+            p.ctx[a_].decoded = 1; list[n++] = a_; } while (0)
+        for (j = col; j-- > 0;) KP_CONCEAL_ONE(row * W + j);
+        for (j = col + 1; j < W; j++) if (!p.ctx[row * W + j].decoded) KP_CONCEAL_ONE(row * W + j);
+        if (row) for (j = 0; j < W; j++) for (i = row; i-- > 0;) KP_CONCEAL_ONE(i * W + j);
+        for (i = row + 1; i < H; i++) for (j = 0; j < W; j++) if (!p.ctx[i * W + j].decoded) KP_CONCEAL_ONE(i * W + j);
+#undef KP_CONCEAL_ONE
+        res.n_conceal = n;
+        res.coef_used += (n * 4 + 31) / 32;
+        res.any_deblock = 1;
+    }
+    return n;
+}
+
+/* ------------------------------------------------------------------ one picture (the whole warp) */
+KP_FN void kp_parse_picture(int lane, const KpPic &p, KpStage *st, const KpTables *T)
+{
+    const h264b200_pichdr_t *hdr = (const h264b200_pichdr_t *)p.block;
+    const uint32_t W = hdr->width_mbs, H = hdr->height_mbs, N = W * H, n_slices = hdr->n_slices;
+    uint32_t num_decoded = 0, off = sizeof(h264b200_pichdr_t), flags = 0;
+    KpS s;
+    {   /* contexts: nothing decoded yet */
+        const KpU4 z = {0, 0, 0, 0};
+        for (uint32_t i = (uint32_t)lane; i < 2 * N; i += KP_LANES) ((KpU4 *)p.ctx)[i] = z;
+    }
+    kp_stage_clear(lane, st);
+    s.T = T; s.st = st; s.W = W; s.N = N;
+    s.coef_used = 0; s.n_intra = s.n_inter = s.any_deblock = 0;
+    KP_SYNC();
+
+    for (uint32_t k = 0; k < n_slices; k++) {
+        const h264b200_slice_t *sl = (const h264b200_slice_t *)(p.block + off);
+        const uint8_t *rbsp = (const uint8_t *)(sl + 1);
+        const uint8_t *map = sl->map_off ? (const uint8_t *)sl + sl->map_off : NULL;
+        uint32_t addr = sl->first_mb, next_linear = 0xffffffffu, mb_count = 0, slice_last_mb = 0;
+        int more = 1, failed = 0;
+        off += sl->size;
+        if (num_decoded == N) continue;                           /* the picture is complete: later slices of the access unit are ignored */
+        s.sl = sl; s.is_p = sl->is_p; s.qp = sl->slice_qp;
+        s.skip_run = 0; s.prev_skipped = 0;
+        s.mbx = s.mby = 0;
+        if (lane == 0) kp_bits_init(s, rbsp, sl->rbsp_len, sl->bit_off, sl->payload_bits);
+        if (addr >= N) { failed = 1; more = 0; }
+        while (more) {
+            int rc = 0; uint32_t n_slots = 0, coef_off = 0; int32_t ipcm = -1;
+            if (addr != next_linear) { s.mbx = (int)(addr % W); s.mby = (int)(addr / W); }
+            else if (++s.mbx == (int)W) { s.mbx = 0; s.mby++; }
+            next_linear = addr + 1;
+            s.addr = addr;
+            kp_stage_in(lane, p, st, addr, s.mbx, s.mby, W);
+            KP_SYNC();
+            if (lane == 0) {
+                rc = kp_parse_mb(s);
+                n_slots = s.n_slots; coef_off = s.coef_used; ipcm = s.ipcm_byte;
+                if (rc == KP_MB_OK) {
+                    s.coef_used += n_slots;
+                    more = kp_more_data(s) || s.skip_run;
+                } else if (rc == KP_MB_FAIL) {
+                    /* h264_slice.c: memset(c, 0) ... c->slice_id = 0 */
+                    KpU4 z = {0, 0, 0, 0};
+                    ((KpU4 *)&st->ctx)[0] = z; ((KpU4 *)&st->ctx)[1] = z;
+                }
+            }
+            KP_SYNC();
+            rc = KP_BCAST(rc); more = KP_BCAST(more);
+            n_slots = KP_BCAST(n_slots); coef_off = KP_BCAST(coef_off); ipcm = KP_BCAST(ipcm);
+            if (rc == KP_MB_OK) kp_stage_out(lane, p, st, addr, coef_off, n_slots, ipcm, rbsp);
+            else {
+                if (rc == KP_MB_FAIL) for (int v = lane; v < 2; v += KP_LANES) ((KpU4 *)&p.ctx[addr])[v] = ((const KpU4 *)&st->ctx)[v];
+                kp_stage_clear(lane, st);
+                failed = 1; more = 0;
+                KP_SYNC();
+                break;
+            }
+            KP_SYNC();
+            mb_count++;
+            if (!s.is_p) slice_last_mb = addr;
+            if (map) { const uint8_t grp = map[addr]; do addr++; while (addr < N && map[addr] != grp); }
+            else addr++;
+            if (more && addr >= N) { failed = 1; more = 0; }
+        }
+        if (!failed && num_decoded + mb_count > N) failed = 1;
+        if (!failed) num_decoded += mb_count;
+        else {
+            flags |= H264B200_PS_SLICE_ERROR;
+            if (lane == 0) kp_mark_slice_corrupted(p, sl, map, W, N, slice_last_mb);
+            KP_SYNC();
+        }
+    }
+
+    if (lane == 0) {
+        KpResult res;
+        res.coef_used = s.coef_used; res.n_intra = s.n_intra; res.n_inter = s.n_inter; res.any_deblock = s.any_deblock;
+        res.n_conceal = 0; res.conceal_offset = 0; res.pad[0] = res.pad[1] = 0;
+        res.stat.err_mbs = 0; res.stat.flags = flags; res.stat.decoded_mbs = num_decoded;
+        if (num_decoded != N) {
+            res.stat.flags |= H264B200_PS_INCOMPLETE;
+            if (hdr->tentative) res.stat.flags |= H264B200_PS_DROPPED;
+            res.stat.err_mbs = kp_conceal_picture(p, T, hdr, num_decoded, res);
+        }
+        res.stat.coef_slots = res.coef_used;
+        *p.res = res;
+    }
+    KP_SYNC();
+}
+
+#endif

@@ -1,0 +1,65 @@
+/* kp_parse.cuh — kernel Kp: slice data of MANY pictures parsed on the device, one warp per picture (kp_core.h), and
+ * k0_jobs, which hands Kp's per-picture results (class counts, concealment list, status words) to the job table the
+ * reconstruction kernels K1..K4 read.
+ *
+ * Launch shape: persistent CTAs of KP_WARPS warps; a warp takes pictures from an atomic ticket until none is left, so a
+ * launch over more pictures than resident warps stays balanced.  Per CTA the host parser's look-up tables (25 KB,
+ * KpTables) are copied into shared memory once; per warp 1.8 KB of staging (KpStage).  Only lane 0 walks the syntax —
+ * the bitstream is serial — so the kernel is bound by dependent-instruction latency, not by HBM: what makes it pay is
+ * that thousands of pictures (every picture of the look-ahead window of every stream) are in flight at once, which is
+ * parallelism the host cores do not have.
+ */
+#pragma once
+#include "k_common.cuh"
+#include "kp_core.h"
+
+#ifndef KP_WARPS
+#define KP_WARPS 8
+#endif
+#ifndef KP_MINB
+#define KP_MINB 4
+#endif
+
+struct KpBatch {
+    const KpPic *pics;
+    uint32_t n_pics;
+    uint32_t *ticket;              /* zeroed before the launch */
+    const KpTables *tables;        /* device copy of the host-built tables */
+};
+
+__global__ void __launch_bounds__(KP_WARPS * 32, KP_MINB) kp_parse(KpBatch b)
+{
+    __shared__ __align__(16) KpTables T;
+    __shared__ __align__(16) KpStage stage[KP_WARPS];
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(b.tables);
+        uint4 *dst = reinterpret_cast<uint4 *>(&T);
+        for (uint32_t i = threadIdx.x; i < sizeof(KpTables) / 16; i += blockDim.x) dst[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    KpStage *st = &stage[threadIdx.x >> 5];
+    for (;;) {
+        uint32_t t = 0;
+        if (lane == 0) t = atomicAdd(b.ticket, 1u);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= b.n_pics) break;
+        const KpPic p = b.pics[t];
+        kp_parse_picture(lane, p, st, &T);
+    }
+}
+
+/* After Kp, before K1: copy what the parse found out about each picture into its job, and put the status words behind
+ * the frame so that they travel to the host with it. */
+__global__ void k0_jobs(PicJob *jobs, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    PicJob &j = jobs[i];
+    const KpResult *r = j.kp_res;
+    if (!r) return;
+    j.n_intra = r->n_intra; j.n_inter = r->n_inter; j.any_deblock = r->any_deblock;
+    j.n_conceal = r->n_conceal;
+    j.conceal_list = reinterpret_cast<const uint32_t *>(j.coef_in + (size_t)r->conceal_offset * 16);
+    *reinterpret_cast<h264b200_picstat_t *>(j.cur + j.stat_off) = r->stat;
+}

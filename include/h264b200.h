@@ -83,8 +83,9 @@ u32  h264b200InitOnEngine(storage_t *pStorage, u32 noOutputReordering, h264b200_
 u32  h264b200EngineSubmit(h264b200_engine_t *e);
 /* Block until everything submitted so far has completed. */
 void h264b200EngineSync(h264b200_engine_t *e);
-/* Counters since creation: kernels launched, pictures reconstructed, H2D and D2H bytes. */
-typedef struct { uint64_t kernel_launches, pictures, h2d_bytes, d2h_bytes, batches; } h264b200_stats_t;
+/* Counters since creation: kernels launched, pictures reconstructed, H2D and D2H bytes, reconstruction rounds, launches of
+ * the device-side slice parser (kernel Kp) and pictures it parsed. */
+typedef struct { uint64_t kernel_launches, pictures, h2d_bytes, d2h_bytes, batches, kp_launches, kp_pictures; } h264b200_stats_t;
 void h264b200EngineStats(h264b200_engine_t *e, h264b200_stats_t *out);
 /* Device-side error word of the last completed batch: bit 0 = a residual left
  * [-512,511] (the reference's mid-parse check, h264bsd_transform.c:181-185). */

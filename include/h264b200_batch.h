@@ -19,6 +19,10 @@ extern "C" {
 #define H264B200_ENGINE_BATCHED 1u  /* pictures wait in the engine until h264b200EngineSubmit */
 #define H264B200_ENGINE_RETAIN  2u  /* keep records + coefficient levels of every batch in HBM for h264b200EngineReplay */
 #define H264B200_ENGINE_NO_D2H  4u  /* do not copy finished frames to the host mirrors (kernel-only measurements) */
+#define H264B200_ENGINE_DEVICE_PARSE 8u /* instances parse slice data on the device (kernel Kp, include/h264b200_slices.h): the host
+                                       keeps NAL extraction, parameter sets, slice headers and the DPB; a picture ends when the next
+                                       access unit begins or at h264bsdFlushBuffer, so H264BSD_PIC_RDY comes one NAL unit later
+                                       (with *readBytes == 0, the reference's own re-feed protocol, h264bsd_decoder.c:267-268) */
 
 h264b200_engine_t *h264b200EngineCreateEx(int device, uint32_t flags);
 void h264b200EngineSetFlags(h264b200_engine_t *e, uint32_t flags);
@@ -33,6 +37,27 @@ u8  *h264b200NextOutputPictureAsync(storage_t *pStorage, u32 *picId, u32 *isIdrP
 /* 0: picture complete; otherwise the engine error flags, 0xffffffff on a CUDA failure, or 0xfffffffe when the
  * caller waited so long that a later picture was already reconstructed into the same frame buffer. */
 u32  h264b200PictureWait(storage_t *pStorage, u32 ticket);
+#define H264B200_WAIT_NOT_LAUNCHED 0xfffffffdu   /* the picture is still queued in the engine (device-parse look-ahead): call h264b200EngineAdvance */
+/* The caller is done with the picture behind `ticket`: its host buffer may be overwritten by a later picture of the
+ * same frame slot.  Until then the engine holds that later picture back (it is launched by a later
+ * h264b200EngineAdvance).  Only needed after h264b200NextOutputPictureAsync. */
+void h264b200PictureRelease(storage_t *pStorage, u32 ticket);
+/* status words of a device-parsed picture (concealed macroblocks ...), valid after h264b200PictureWait returned 0; returns 0 on success */
+#include "h264b200_slices.h"
+u32  h264b200PictureStatus(storage_t *pStorage, u32 ticket, h264b200_picstat_t *out);
+/* pictures of this instance handed to the engine but not yet launched */
+u32  h264b200PicturesPending(storage_t *pStorage);
+/* 1 if the instance parses slice data on the device */
+u32  h264b200DeviceParse(storage_t *pStorage);
+/* One scheduling step of the engine: (1) if enough queued device-parse pictures have accumulated (or a stream would
+ * otherwise stall) launch kernel Kp over all of them; (2) launch ONE round of reconstruction: the oldest queued picture
+ * of every instance whose output buffer is free.  Returns the number of pictures reconstructed by this call.
+ * h264b200EngineSubmit repeats this until nothing is left that can be launched. */
+u32  h264b200EngineAdvance(h264b200_engine_t *e);
+/* look-ahead of the device-parse path: how many pictures per instance may be queued (parse buffers are allocated for
+ * depth + 2), and how many queued pictures make kernel Kp worth launching.  Call before the instances are created. */
+void h264b200EngineSetWindow(h264b200_engine_t *e, uint32_t depth, uint32_t parse_threshold);
+uint32_t h264b200EngineWindow(h264b200_engine_t *e);
 
 /* ---- output formatting on the device (K5) ----
  * H264B200_OUT_I420 (default): the reference's output, uncropped MB-aligned planar I420.
@@ -55,9 +80,18 @@ void h264b200EngineDropRetained(h264b200_engine_t *e);
  * normal decode filled (0 = the replay reproduced the same pictures) */
 u32  h264b200EngineCheckResident(h264b200_engine_t *e);
 /* accumulated CUDA-event time, algorithmic bytes and launches per
- * kernel family [K1 transform, K2 inter, K3 intra, K4 deblock] of timed replays */
-typedef struct { double ms[4]; uint64_t bytes[4]; uint64_t launches[4]; } h264b200_kernel_times_t;
+ * kernel family [K1 transform, K2 inter, K3 intra, K4 deblock, Kp slice-data parse] of timed replays.  Kp runs on its
+ * own stream concurrently with the reconstruction rounds of earlier pictures: its time is that of its launches, not a
+ * share of the step. */
+typedef struct { double ms[5]; uint64_t bytes[5]; uint64_t launches[5]; } h264b200_kernel_times_t;
 void h264b200EngineKernelTimes(h264b200_engine_t *e, h264b200_kernel_times_t *out, int reset);
+
+/* Parity / debugging aid: records, coefficient slots and findings of kernel Kp for the picture this device-parse instance
+ * submitted most recently (back = 0) or `back` pictures earlier (while its parse buffer has not been re-used).  mbs:
+ * PicWidth*PicHeight records; coef: up to coef_cap slots of 16 int16; res: 12 uint32 {coef_used, n_intra, n_inter,
+ * any_deblock, n_conceal, conceal_offset, -, -, err_mbs, flags, decoded_mbs, coef_slots}.  Blocks until the engine is idle.
+ * Returns 0, or a negative value when the picture is not available. */
+int  h264b200DebugFetchParse(storage_t *pStorage, int back, void *mbs, int16_t *coef, uint32_t coef_cap, uint32_t *res);
 
 /* ---- many streams through one engine ---- */
 typedef struct { const uint8_t *data; size_t len; } h264b200_stream_t;   /* Annex-B; not modified (copied internally) */

@@ -10,7 +10,8 @@
 #include "h264b200_batch.h"
 #include "../broadway_b200/csrc/h264_internal.h"
 
-struct h264b200_engine { uint32_t flags; uint32_t submits; };
+struct h264b200_engine { uint32_t flags; uint32_t submits; uint32_t window; h264_backend_t be; };
+h264_backend_t recon_cpu_backend(int device_parse);      /* recon_cpu.c */
 
 u32 h264_decoder_create(storage_t *pStorage, u32 noOutputReordering, h264_backend_t *be);
 
@@ -18,17 +19,20 @@ h264b200_engine_t *h264b200EngineCreateEx(int device, uint32_t flags)
 {
     h264b200_engine_t *e = (h264b200_engine_t *)calloc(1, sizeof *e);
     (void)device;
-    if (e) e->flags = flags;
+    if (e) { e->flags = flags; e->window = 1; e->be = recon_cpu_backend((flags & H264B200_ENGINE_DEVICE_PARSE) != 0); }
     return e;
 }
 h264b200_engine_t *h264b200EngineCreate(int device) { return h264b200EngineCreateEx(device, H264B200_ENGINE_BATCHED); }
 void h264b200EngineDestroy(h264b200_engine_t *e) { free(e); }
-void h264b200EngineSetFlags(h264b200_engine_t *e, uint32_t flags) { if (e) e->flags = flags; }
+void h264b200EngineSetFlags(h264b200_engine_t *e, uint32_t flags) { if (e) { e->flags = flags; e->be.parse_mode = (flags & H264B200_ENGINE_DEVICE_PARSE) != 0; } }
 uint32_t h264b200EngineFlags(h264b200_engine_t *e) { return e ? e->flags : 0; }
 u32 h264b200InitOnEngine(storage_t *pStorage, u32 noOutputReordering, h264b200_engine_t *e)
 {
     if (!e) return HANTRO_NOK;
-    return h264_decoder_create(pStorage, noOutputReordering, NULL);      /* NULL: the linked default backend = recon_cpu.c */
+    return h264_decoder_create(pStorage, noOutputReordering, &e->be);    /* recon_cpu.c, host- or device-parse (kp_cpu.cpp) as the engine flags say */
 }
 u32 h264b200EngineSubmit(h264b200_engine_t *e) { if (e) e->submits++; return 0; }
 void h264b200EngineSync(h264b200_engine_t *e) { (void)e; }
+u32 h264b200EngineAdvance(h264b200_engine_t *e) { if (e) e->submits++; return 0; }
+void h264b200EngineSetWindow(h264b200_engine_t *e, uint32_t depth, uint32_t parse_threshold) { (void)parse_threshold; if (e) e->window = depth ? depth : 1; }
+uint32_t h264b200EngineWindow(h264b200_engine_t *e) { return e ? e->window : 0; }

@@ -546,7 +546,14 @@ typedef struct {
     uint8_t *predeblock;         /* copy of the last picture before deblocking (tests) */
     h264_pic_input_t pic;
     uint32_t errors;
+    /* device-parse emulation (kp_cpu.cpp): contexts for kp_core, status words per frame slot */
+    int dev_parse;
+    KpMbCtx *kctx;
+    h264b200_picstat_t stat[H264_MAX_SLOTS];
 } cpu_inst_t;
+
+void kp_cpu_parse_picture(const KpPic *pic, const KpTables *tables);   /* kp_cpu.cpp */
+static KpTables *g_kp_tables;
 
 static recon_cpu_tap_t g_tap;
 void recon_cpu_set_tap(const recon_cpu_tap_t *t) { if (t) g_tap = *t; else memset(&g_tap, 0, sizeof g_tap); }
@@ -555,14 +562,19 @@ static void *cpu_inst_create(h264_backend_t *be, uint32_t wm, uint32_t hm, uint3
 {
     cpu_inst_t *in = (cpu_inst_t *)calloc(1, sizeof *in);
     uint32_t i;
-    (void)be;
     if (!in || n_slots > H264_MAX_SLOTS) return NULL;
     in->wm = wm; in->hm = hm; in->n_slots = n_slots;
     for (i = 0; i < n_slots; i++) in->frames[i] = (uint8_t *)calloc((size_t)wm * hm, 384);
     in->predeblock = (uint8_t *)calloc((size_t)wm * hm, 384);
     in->pic.mbs = (h264b200_mb_t *)calloc((size_t)wm * hm, sizeof(h264b200_mb_t));
-    in->pic.coef_cap = wm * hm * 8 + 64;
+    in->dev_parse = be->parse_mode;
+    in->pic.coef_cap = in->dev_parse ? KP_COEF_CAP(wm * hm) : wm * hm * 8 + 64;
     in->pic.coef = (int16_t *)malloc((size_t)in->pic.coef_cap * 32);
+    if (in->dev_parse) {
+        in->kctx = (KpMbCtx *)calloc((size_t)wm * hm, sizeof(KpMbCtx));
+        in->pic.block_cap = 1 << 16; in->pic.block = (uint8_t *)malloc(in->pic.block_cap);
+        if (!g_kp_tables) { g_kp_tables = (KpTables *)malloc(sizeof(KpTables)); h264_kp_fill_tables(g_kp_tables); }
+    }
     return in;
 }
 static void cpu_inst_destroy(h264_backend_t *be, void *inst)
@@ -570,7 +582,7 @@ static void cpu_inst_destroy(h264_backend_t *be, void *inst)
     cpu_inst_t *in = (cpu_inst_t *)inst; uint32_t i;
     (void)be;
     for (i = 0; i < in->n_slots; i++) free(in->frames[i]);
-    free(in->predeblock); free(in->pic.mbs); free(in->pic.coef); free(in);
+    free(in->predeblock); free(in->pic.mbs); free(in->pic.coef); free(in->pic.block); free(in->kctx); free(in);
 }
 static h264_pic_input_t *cpu_pic_begin(h264_backend_t *be, void *inst) { (void)be; return &((cpu_inst_t *)inst)->pic; }
 static int cpu_coef_grow(h264_backend_t *be, void *inst, h264_pic_input_t *pic, uint32_t min_slots)
@@ -587,6 +599,15 @@ static int cpu_pic_submit(h264_backend_t *be, void *inst, h264_pic_input_t *pic)
     cpu_inst_t *in = (cpu_inst_t *)inst;
     uint32_t i, n = in->wm * in->hm;
     (void)be;
+    if (in->dev_parse) {            /* what kernel Kp does on the GPU: slices -> records, slots, concealment, status */
+        KpPic kp; KpResult res;
+        memset(&res, 0, sizeof res);
+        kp.block = pic->block; kp.mbs = pic->mbs; kp.coef = pic->coef; kp.ctx = in->kctx; kp.coef_cap = pic->coef_cap; kp.pad = 0; kp.res = &res;
+        kp_cpu_parse_picture(&kp, g_kp_tables);
+        pic->coef_used = res.coef_used; pic->n_intra = res.n_intra; pic->n_inter = res.n_inter; pic->any_deblock = res.any_deblock;
+        pic->n_conceal = res.n_conceal; pic->conceal_offset = res.conceal_offset;
+        in->stat[pic->cur_slot] = res.stat;
+    }
     if (g_tap.records) g_tap.records(g_tap.user, pic->mbs, n, pic->coef, pic->coef_used);
     for (i = 0; i < n; i++) if (recon_cpu_residual_mb(&pic->mbs[i], pic->coef)) in->errors |= 1;
     if (g_tap.residual) g_tap.residual(g_tap.user, pic->coef, pic->coef_used);
@@ -605,6 +626,40 @@ static uint8_t *cpu_frame_host(h264_backend_t *be, void *inst, int slot, uint32_
     return in->frames[slot];
 }
 static void cpu_destroy(h264_backend_t *be) { (void)be; }
+static int cpu_block_grow(h264_backend_t *be, void *inst, h264_pic_input_t *pic, uint32_t min_bytes)
+{
+    uint32_t cap = pic->block_cap * 2 > min_bytes ? pic->block_cap * 2 : min_bytes;
+    uint8_t *n = (uint8_t *)realloc(pic->block, cap);
+    (void)be; (void)inst;
+    if (!n) return -1;
+    pic->block = n; pic->block_cap = cap;
+    return 0;
+}
+static int cpu_frame_status(h264_backend_t *be, void *inst, int slot, h264b200_picstat_t *out)
+{
+    (void)be; *out = ((cpu_inst_t *)inst)->stat[slot]; return 0;
+}
+static uint8_t *cpu_frame_host_async(h264_backend_t *be, void *inst, int slot, uint32_t *gen) { if (gen) *gen = 0; return cpu_frame_host(be, inst, slot, NULL); }
+static int cpu_frame_wait(h264_backend_t *be, void *inst, int slot, uint32_t gen, uint32_t *err) { (void)be; (void)slot; (void)gen; if (err) *err = ((cpu_inst_t *)inst)->errors; return 0; }
 
-static h264_backend_t g_cpu_backend = { cpu_inst_create, cpu_inst_destroy, cpu_pic_begin, cpu_coef_grow, cpu_pic_submit, cpu_frame_host, cpu_destroy, NULL };
-h264_backend_t *h264_default_backend(void) { return &g_cpu_backend; }
+/* every picture is reconstructed synchronously in pic_submit, so the asynchronous half of the interface is trivial */
+h264_backend_t recon_cpu_backend(int device_parse)
+{
+    h264_backend_t b;
+    memset(&b, 0, sizeof b);
+    b.inst_create = cpu_inst_create; b.inst_destroy = cpu_inst_destroy; b.pic_begin = cpu_pic_begin; b.coef_grow = cpu_coef_grow;
+    b.pic_submit = cpu_pic_submit; b.frame_host = cpu_frame_host; b.destroy = cpu_destroy;
+    b.frame_host_async = cpu_frame_host_async; b.frame_wait = cpu_frame_wait;
+    b.block_grow = cpu_block_grow; b.frame_status = cpu_frame_status;
+    b.parse_mode = device_parse;
+    return b;
+}
+static h264_backend_t g_cpu_backend;
+h264_backend_t *h264_default_backend(void)
+{
+    if (!g_cpu_backend.inst_create) {
+        const char *pm = getenv("H264B200_PARSE");
+        g_cpu_backend = recon_cpu_backend(pm && !strcmp(pm, "device"));
+    }
+    return &g_cpu_backend;
+}
