@@ -204,6 +204,7 @@ def own_arm(args, rank, local_rank, world):
     threads = args.threads or max(1, cores // world)
     streams = make_streams(args.streams, args.frames, rank)
     frames_per_step = args.streams * args.frames
+    pflag = capi.ENGINE_DEVICE_PARSE if args.parse == "device" else 0
     log("[rank %d] %d streams x %d pictures, %.1f MB of Annex-B, %d parser threads" % (rank, args.streams, args.frames, sum(map(len, streams)) / 1e6, threads))
 
     def barrier():
@@ -228,7 +229,7 @@ def own_arm(args, rank, local_rank, world):
         g = json.load(open(gpath))
         if g["frames"] == args.frames:
             n_chk = min(len(g["streams"]), len(streams))
-            with capi.Engine(local_rank) as eng:
+            with capi.Engine(local_rank, capi.ENGINE_BATCHED | pflag) as eng:
                 got, _ = eng.decode_streams_md5(streams[:n_chk], threads=n_chk)
             for i in range(n_chk):
                 if hashlib.md5(streams[i]).hexdigest() != g["streams"][i]["stream_md5"]:
@@ -239,7 +240,7 @@ def own_arm(args, rank, local_rank, world):
             log("[rank 0] parity gate: %d pictures MD5-exact vs the reference" % check["pictures"])
 
     # ---- end-to-end leg: host Annex-B -> host I420 frames through the C ABI
-    eng = capi.Engine(local_rank, capi.ENGINE_BATCHED)
+    eng = capi.Engine(local_rank, capi.ENGINE_BATCHED | pflag)
     for _ in range(0 if args.skip_e2e else args.warmup):
         eng.decode_streams(streams, threads)
     barrier()
@@ -271,7 +272,7 @@ def own_arm(args, rank, local_rank, world):
         return
 
     # ---- resident leg: retain every batch of one decode in HBM, then replay K1..K4 only
-    eng = capi.Engine(local_rank, capi.ENGINE_BATCHED | capi.ENGINE_RETAIN)
+    eng = capi.Engine(local_rank, capi.ENGINE_BATCHED | capi.ENGINE_RETAIN | pflag)
     eng.decode_streams(streams, threads)
     eng.sync()
     assert eng.check_resident() == 0
@@ -328,7 +329,7 @@ def own_arm(args, rank, local_rank, world):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": WORKLOADS[args.workload][3],
                        "width": 16 * WORKLOADS[args.workload][0], "height": 16 * WORKLOADS[args.workload][1], "streams_per_gpu": args.streams, "frames_per_stream": args.frames,
-                       "frames_per_step_per_gpu": frames_per_step, "parser_threads_per_gpu": threads, "host_cores": cores,
+                       "frames_per_step_per_gpu": frames_per_step, "parser_threads_per_gpu": threads, "host_cores": cores, "slice_data_parse": args.parse,
                        "l2": "inputs larger than L2 (per step: %.0f MB of frame pools + records per GPU)" % (args.streams * 2 * WORKLOADS[args.workload][0] * WORKLOADS[args.workload][1] * 384 / 1e6 + h2d / 1e6)},
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1000.0 * e2e_s / args.steps, "timing": "wall clock between barrier+synchronize pairs, max over ranks",
@@ -363,6 +364,7 @@ def main():
     ap.add_argument("--frames", type=int, default=DEFAULT_FRAMES, help="pictures per stream (1 IDR + P)")
     ap.add_argument("--threads", type=int, default=0, help="parser threads per GPU (0: host cores / ranks)")
     ap.add_argument("--workload", default="1080p_ippp", choices=sorted(WORKLOADS), help="default: the configuration BASELINE.json's metric is quoted on")
+    ap.add_argument("--parse", default="device", choices=["device", "host"], help="where slice data is parsed: kernel Kp (default) or the host cores")
     ap.add_argument("--no-check", action="store_true")
     ap.add_argument("--e2e-only", action="store_true", help="host-to-host leg only (experiments)")
     ap.add_argument("--skip-e2e", action="store_true", help="kernel-tuning aid: skip the host-to-host leg (the line then carries no valid e2e and is not a bench result)")

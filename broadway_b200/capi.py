@@ -220,6 +220,74 @@ def decode_annexb(data, keep_frames=False, no_reordering=0, api="swdec"):
     return out, info
 
 
+def decode_on_engine(eng, data, keep_frames=False, fetch_parse=False, no_reordering=0):
+    """Decode one Annex-B stream with the h264bsd* loop on an instance attached to `eng` (h264b200InitOnEngine).  On an
+    engine that is not batched every finished picture is launched at once, so this is the synchronous API on an engine
+    of the caller's choice — in particular a device-parse one (ENGINE_DEVICE_PARSE): slice data parsed by kernel Kp.
+    fetch_parse: also return, per picture in decoding order, what Kp produced (h264b200DebugFetchParse):
+    (records bytes, coefficient slot bytes, 12 result words).  Returns (md5s or frames, info[, parses])."""
+    L = lib()
+    buf = ctypes.create_string_buffer(bytes(data), len(data) + 16)
+    base = ctypes.addressof(buf)
+    out, parses = [], []
+    info = {"err_mbs": 0, "width": 0, "height": 0, "pic_ids": [], "device_parse": 0}
+    st = Storage()
+    if L.h264b200InitOnEngine(ctypes.byref(st), no_reordering, eng.h) != 0:
+        raise RuntimeError("h264b200InitOnEngine failed")
+    try:
+        pos, n, pic_id = 0, len(data), 0
+        nread, pid, idr, err = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint32()
+
+        def drain():
+            while True:
+                p = L.h264bsdNextOutputPicture(ctypes.byref(st), ctypes.byref(pid), ctypes.byref(idr), ctypes.byref(err))
+                if not p:
+                    break
+                nb = info["width"] * info["height"] * 3 // 2
+                out.append(ctypes.string_at(p, nb) if keep_frames else frame_md5(p, nb))
+                info["err_mbs"] += err.value
+                info["pic_ids"].append(pid.value)
+
+        def fetch():
+            n_mbs = info["width"] * info["height"] // 256
+            mbs = ctypes.create_string_buffer(n_mbs * 128)
+            cap = n_mbs * 28 + 16
+            coef = ctypes.create_string_buffer(cap * 32)
+            res = (ctypes.c_uint32 * 12)()
+            rc = L.h264b200DebugFetchParse(ctypes.byref(st), 0, mbs, coef, cap, res)
+            if rc != 0:
+                raise RuntimeError("h264b200DebugFetchParse failed (%d)" % rc)
+            parses.append((mbs.raw, coef.raw[:res[0] * 32], list(res)))
+        while pos < n:
+            rc = L.h264bsdDecode(ctypes.byref(st), base + pos, n - pos, pic_id, ctypes.byref(nread))
+            pos += nread.value
+            if rc == H264BSD_MEMALLOC_ERROR:
+                raise RuntimeError("h264bsdDecode: H264BSD_MEMALLOC_ERROR (CUDA engine unavailable?)")
+            if rc == H264BSD_HDRS_RDY:
+                info["width"] = 16 * L.h264bsdPicWidth(ctypes.byref(st)); info["height"] = 16 * L.h264bsdPicHeight(ctypes.byref(st))
+                drain()
+            elif rc == H264BSD_PIC_RDY:
+                pic_id += 1
+                info["device_parse"] = L.h264b200DeviceParse(ctypes.byref(st))
+                if fetch_parse:
+                    fetch()
+                drain()
+            elif nread.value == 0:
+                break
+        before = len(info["pic_ids"])
+        L.h264bsdFlushBuffer(ctypes.byref(st))
+        if fetch_parse and L.h264b200DeviceParse(ctypes.byref(st)) and len(parses) < pic_id + 1:
+            try:
+                fetch()                 # the picture the flush ended (device-parse: the last one of the stream)
+            except RuntimeError:
+                pass
+        drain()
+        del before
+    finally:
+        L.h264bsdShutdown(ctypes.byref(st))
+    return (out, info, parses) if fetch_parse else (out, info)
+
+
 def split_gops(data, max_segs=4096):
     """h264b200SplitGops: list of self-contained IDR-bounded segments (bytes)."""
     L = lib()

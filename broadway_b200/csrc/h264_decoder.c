@@ -656,6 +656,7 @@ u32 h264b200PictureWait(storage_t *pStorage, u32 ticket)
     if (d->be->frame_host_async && d->be->frame_wait) {
         int rc = d->be->frame_wait(d->be, d->be_inst, (int)(ticket & 0xff), ticket >> 8, &err);
         if (rc < 0) return 0xffffffffu;
+        if (rc == 2) return H264B200_WAIT_NOT_LAUNCHED; /* still queued in the engine (device-parse look-ahead) */
         if (rc > 0) return 0xfffffffeu;               /* waited too long: a later picture already occupies the slot */
         return err;
     }

@@ -12,6 +12,7 @@
 
 struct h264b200_engine { uint32_t flags; uint32_t submits; uint32_t window; h264_backend_t be; };
 h264_backend_t recon_cpu_backend(int device_parse);      /* recon_cpu.c */
+uint32_t recon_cpu_advance(void *ctx);
 
 u32 h264_decoder_create(storage_t *pStorage, u32 noOutputReordering, h264_backend_t *be);
 
@@ -19,7 +20,8 @@ h264b200_engine_t *h264b200EngineCreateEx(int device, uint32_t flags)
 {
     h264b200_engine_t *e = (h264b200_engine_t *)calloc(1, sizeof *e);
     (void)device;
-    if (e) { e->flags = flags; e->window = 1; e->be = recon_cpu_backend((flags & H264B200_ENGINE_DEVICE_PARSE) != 0); }
+    if (e) { e->flags = flags; e->window = 1; e->be = recon_cpu_backend((flags & H264B200_ENGINE_DEVICE_PARSE) != 0);
+             if (flags & H264B200_ENGINE_BATCHED) e->be.ctx = e; }   /* batched device-parse instances defer their launches to h264b200EngineAdvance */
     return e;
 }
 h264b200_engine_t *h264b200EngineCreate(int device) { return h264b200EngineCreateEx(device, H264B200_ENGINE_BATCHED); }
@@ -31,8 +33,15 @@ u32 h264b200InitOnEngine(storage_t *pStorage, u32 noOutputReordering, h264b200_e
     if (!e) return HANTRO_NOK;
     return h264_decoder_create(pStorage, noOutputReordering, &e->be);    /* recon_cpu.c, host- or device-parse (kp_cpu.cpp) as the engine flags say */
 }
-u32 h264b200EngineSubmit(h264b200_engine_t *e) { if (e) e->submits++; return 0; }
+u32 h264b200EngineSubmit(h264b200_engine_t *e)
+{
+    u32 total = 0, n;
+    if (!e) return 0;
+    e->submits++;
+    while ((n = recon_cpu_advance(e)) != 0) total += n;
+    return total;
+}
 void h264b200EngineSync(h264b200_engine_t *e) { (void)e; }
-u32 h264b200EngineAdvance(h264b200_engine_t *e) { if (e) e->submits++; return 0; }
+u32 h264b200EngineAdvance(h264b200_engine_t *e) { if (!e) return 0; e->submits++; return recon_cpu_advance(e); }
 void h264b200EngineSetWindow(h264b200_engine_t *e, uint32_t depth, uint32_t parse_threshold) { (void)parse_threshold; if (e) e->window = depth ? depth : 1; }
 uint32_t h264b200EngineWindow(h264b200_engine_t *e) { return e ? e->window : 0; }

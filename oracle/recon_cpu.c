@@ -550,7 +550,19 @@ typedef struct {
     int dev_parse;
     KpMbCtx *kctx;
     h264b200_picstat_t stat[H264_MAX_SLOTS];
+    /* deferred launches, like the CUDA engine's per-instance FIFO (device-parse + batched): pictures wait as blocks until
+     * recon_cpu_advance launches the oldest one, held back while an output of its frame slot is unreleased */
+    int deferred;
+    void *ctx;
+    struct cpu_qpic { uint8_t *block; uint32_t used; int cur_slot; uint32_t gate_gen; } *q;
+    uint32_t q_cap, q_head, q_n;
+    uint32_t qgen[H264_MAX_SLOTS], lgen[H264_MAX_SLOTS], popped[H264_MAX_SLOTS], released[H264_MAX_SLOTS];
 } cpu_inst_t;
+
+#include <pthread.h>
+static pthread_mutex_t g_reg_mu = PTHREAD_MUTEX_INITIALIZER;
+static cpu_inst_t *g_reg[4096];
+static uint32_t g_reg_n;
 
 void kp_cpu_parse_picture(const KpPic *pic, const KpTables *tables);   /* kp_cpu.cpp */
 static KpTables *g_kp_tables;
@@ -568,6 +580,13 @@ static void *cpu_inst_create(h264_backend_t *be, uint32_t wm, uint32_t hm, uint3
     in->predeblock = (uint8_t *)calloc((size_t)wm * hm, 384);
     in->pic.mbs = (h264b200_mb_t *)calloc((size_t)wm * hm, sizeof(h264b200_mb_t));
     in->dev_parse = be->parse_mode;
+    in->deferred = in->dev_parse && be->ctx != NULL;      /* engine_shim.c sets ctx on batched engines */
+    in->ctx = be->ctx;
+    if (in->deferred) {
+        pthread_mutex_lock(&g_reg_mu);
+        if (g_reg_n < 4096) g_reg[g_reg_n++] = in;
+        pthread_mutex_unlock(&g_reg_mu);
+    }
     in->pic.coef_cap = in->dev_parse ? KP_COEF_CAP(wm * hm) : wm * hm * 8 + 64;
     in->pic.coef = (int16_t *)malloc((size_t)in->pic.coef_cap * 32);
     if (in->dev_parse) {
@@ -581,6 +600,13 @@ static void cpu_inst_destroy(h264_backend_t *be, void *inst)
 {
     cpu_inst_t *in = (cpu_inst_t *)inst; uint32_t i;
     (void)be;
+    if (in->deferred) {
+        pthread_mutex_lock(&g_reg_mu);
+        for (i = 0; i < g_reg_n; i++) if (g_reg[i] == in) { g_reg[i] = g_reg[--g_reg_n]; break; }
+        pthread_mutex_unlock(&g_reg_mu);
+        for (i = 0; i < in->q_n; i++) free(in->q[(in->q_head + i) % in->q_cap].block);
+        free(in->q);
+    }
     for (i = 0; i < in->n_slots; i++) free(in->frames[i]);
     free(in->predeblock); free(in->pic.mbs); free(in->pic.coef); free(in->pic.block); free(in->kctx); free(in);
 }
@@ -594,11 +620,60 @@ static int cpu_coef_grow(h264_backend_t *be, void *inst, h264_pic_input_t *pic, 
     pic->coef = n; pic->coef_cap = cap;
     return 0;
 }
+static int cpu_reconstruct(cpu_inst_t *in, h264_pic_input_t *pic);
 static int cpu_pic_submit(h264_backend_t *be, void *inst, h264_pic_input_t *pic)
 {
     cpu_inst_t *in = (cpu_inst_t *)inst;
-    uint32_t i, n = in->wm * in->hm;
     (void)be;
+    in->qgen[pic->cur_slot]++;
+    if (in->deferred) {             /* keep the block; recon_cpu_advance launches it */
+        struct cpu_qpic *e;
+        if (in->q_n == in->q_cap) {
+            uint32_t ncap = in->q_cap ? in->q_cap * 2 : 32, k;
+            struct cpu_qpic *nq = (struct cpu_qpic *)calloc(ncap, sizeof *nq);
+            for (k = 0; k < in->q_n; k++) nq[k] = in->q[(in->q_head + k) % in->q_cap];
+            free(in->q); in->q = nq; in->q_cap = ncap; in->q_head = 0;
+        }
+        e = &in->q[(in->q_head + in->q_n) % in->q_cap];
+        e->block = (uint8_t *)malloc(pic->block_used); memcpy(e->block, pic->block, pic->block_used);
+        e->used = pic->block_used; e->cur_slot = pic->cur_slot; e->gate_gen = in->popped[pic->cur_slot];
+        __atomic_fetch_add(&in->q_n, 1, __ATOMIC_RELEASE);
+        return 0;
+    }
+    in->lgen[pic->cur_slot]++;
+    return cpu_reconstruct(in, pic);
+}
+/* one scheduling step for every deferred instance of engine `ctx`: launch its oldest queued picture unless an output of
+ * that picture's frame slot is still unreleased.  Returns the number of pictures reconstructed. */
+uint32_t recon_cpu_advance(void *ctx)
+{
+    uint32_t i, launched = 0, n;
+    cpu_inst_t *list[4096];
+    pthread_mutex_lock(&g_reg_mu);
+    n = g_reg_n; memcpy(list, g_reg, n * sizeof list[0]);
+    pthread_mutex_unlock(&g_reg_mu);
+    for (i = 0; i < n; i++) {
+        cpu_inst_t *in = list[i];
+        struct cpu_qpic *e;
+        uint8_t *saved; uint32_t saved_used;
+        if (in->ctx != ctx || !in->q_n) continue;
+        e = &in->q[in->q_head];
+        if ((int32_t)(__atomic_load_n(&in->released[e->cur_slot], __ATOMIC_ACQUIRE) - e->gate_gen) < 0) continue;
+        saved = in->pic.block; saved_used = in->pic.block_used;
+        in->pic.block = e->block; in->pic.block_used = e->used; in->pic.cur_slot = e->cur_slot;
+        cpu_reconstruct(in, &in->pic);
+        in->pic.block = saved; in->pic.block_used = saved_used;
+        free(e->block);
+        in->q_head = (in->q_head + 1) % in->q_cap;
+        __atomic_fetch_add(&in->lgen[e->cur_slot], 1, __ATOMIC_RELEASE);
+        __atomic_fetch_sub(&in->q_n, 1, __ATOMIC_RELEASE);
+        launched++;
+    }
+    return launched;
+}
+static int cpu_reconstruct(cpu_inst_t *in, h264_pic_input_t *pic)
+{
+    uint32_t i, n = in->wm * in->hm;
     if (in->dev_parse) {            /* what kernel Kp does on the GPU: slices -> records, slots, concealment, status */
         KpPic kp; KpResult res;
         memset(&res, 0, sizeof res);
@@ -639,8 +714,30 @@ static int cpu_frame_status(h264_backend_t *be, void *inst, int slot, h264b200_p
 {
     (void)be; *out = ((cpu_inst_t *)inst)->stat[slot]; return 0;
 }
-static uint8_t *cpu_frame_host_async(h264_backend_t *be, void *inst, int slot, uint32_t *gen) { if (gen) *gen = 0; return cpu_frame_host(be, inst, slot, NULL); }
-static int cpu_frame_wait(h264_backend_t *be, void *inst, int slot, uint32_t gen, uint32_t *err) { (void)be; (void)slot; (void)gen; if (err) *err = ((cpu_inst_t *)inst)->errors; return 0; }
+static uint8_t *cpu_frame_host_async(h264_backend_t *be, void *inst, int slot, uint32_t *gen)
+{
+    cpu_inst_t *in = (cpu_inst_t *)inst;
+    (void)be;
+    if (gen) *gen = in->qgen[slot];
+    in->popped[slot] = in->qgen[slot];
+    return in->frames[slot];
+}
+static int cpu_frame_wait(h264_backend_t *be, void *inst, int slot, uint32_t gen, uint32_t *err)
+{
+    cpu_inst_t *in = (cpu_inst_t *)inst;
+    const uint32_t l = __atomic_load_n(&in->lgen[slot], __ATOMIC_ACQUIRE) & 0xffffffu;
+    (void)be;
+    if (err) *err = in->errors;
+    if (l == (gen & 0xffffffu)) return 0;
+    return (int32_t)((l - gen) << 8) < 0 ? 2 : 1;      /* 2: still queued; 1: a later picture already took the slot */
+}
+static void cpu_frame_release(h264_backend_t *be, void *inst, int slot, uint32_t gen)
+{
+    cpu_inst_t *in = (cpu_inst_t *)inst;
+    (void)be;
+    if ((int32_t)(gen - in->released[slot]) > 0) __atomic_store_n(&in->released[slot], gen, __ATOMIC_RELEASE);
+}
+static uint32_t cpu_inst_pending(h264_backend_t *be, void *inst) { (void)be; return __atomic_load_n(&((cpu_inst_t *)inst)->q_n, __ATOMIC_ACQUIRE); }
 
 /* every picture is reconstructed synchronously in pic_submit, so the asynchronous half of the interface is trivial */
 h264_backend_t recon_cpu_backend(int device_parse)
@@ -651,6 +748,7 @@ h264_backend_t recon_cpu_backend(int device_parse)
     b.pic_submit = cpu_pic_submit; b.frame_host = cpu_frame_host; b.destroy = cpu_destroy;
     b.frame_host_async = cpu_frame_host_async; b.frame_wait = cpu_frame_wait;
     b.block_grow = cpu_block_grow; b.frame_status = cpu_frame_status;
+    b.frame_release = cpu_frame_release; b.inst_pending = cpu_inst_pending;
     b.parse_mode = device_parse;
     return b;
 }
