@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("H264B200_LIB") or os.path.join(_HERE, "libh264b200.so
 
 H264BSD_RDY, H264BSD_PIC_RDY, H264BSD_HDRS_RDY, H264BSD_ERROR, H264BSD_PARAM_SET_ERROR, H264BSD_MEMALLOC_ERROR = range(6)
 H264SWDEC_OK, H264SWDEC_STRM_PROCESSED, H264SWDEC_PIC_RDY, H264SWDEC_PIC_RDY_BUFF_NOT_EMPTY, H264SWDEC_HDRS_RDY_BUFF_NOT_EMPTY = range(5)
-ENGINE_BATCHED, ENGINE_RETAIN, ENGINE_NO_D2H, ENGINE_DEVICE_PARSE = 1, 2, 4, 8
+ENGINE_BATCHED, ENGINE_RETAIN, ENGINE_NO_D2H, ENGINE_DEVICE_PARSE, ENGINE_NO_RECON = 1, 2, 4, 8, 16
 
 
 class Storage(ctypes.Structure):

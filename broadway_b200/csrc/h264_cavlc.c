@@ -114,4 +114,9 @@ void h264_kp_fill_tables(KpTables *t)
     memcpy(t->zigzag, H264_ZIGZAG4x4, sizeof t->zigzag);
     memcpy(t->raster_to_blk, H264_RASTER_TO_BLK, sizeof t->raster_to_blk);
     memcpy(t->qpc, H264_QPC, sizeof t->qpc);
+    {
+        int blk;
+        for (blk = 0; blk < 16; blk++) t->lc_idx[blk] = (uint8_t)(9 + ((blk & 1) | ((blk >> 1) & 2)) + 8 * (((blk >> 1) & 1) | ((blk >> 2) & 2)));
+        for (blk = 0; blk < 4; blk++) t->ident4[blk] = (uint8_t)blk;
+    }
 }

@@ -449,6 +449,7 @@ static uint32_t launch_round(h264b200_engine *e, std::vector<PicBuf *> &list)
         if (in->slot_flags[pic->cur_slot] & 2) cudaStreamWaitEvent(e->s_comp, in->slot_ready[pic->cur_slot], 0);
     }
     pl.total_mbs = mb_base; pl.n_jobs = (int)n;
+    if (e->flags & H264B200_ENGINE_NO_RECON) pl.k1 = pl.k2 = pl.k3 = pl.k3c = pl.k4 = false;
 
     Batch b;
     b.jobs = d_jobs; b.n_jobs = (int32_t)n; b.max_hm = pl.max_hm; b.total_mbs = mb_base;

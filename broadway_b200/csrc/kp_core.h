@@ -32,6 +32,7 @@
 #define KP_NOINL __device__ __noinline__
 #define KP_HOT __device__ __forceinline__   /* hot: inlined so that the bit reader state stays in registers */
 #define KP_LANES 32
+#define KP_NOUNROLL _Pragma("unroll 1")   /* code size: the hot path has to live in the instruction cache */
 #define KP_SYNC() __syncwarp()
 #define KP_BCAST(x) __shfl_sync(0xffffffffu, (x), 0)
 #define KP_CLZ(x) __clz((int)(x))
@@ -42,6 +43,7 @@
 #define KP_NOINL static
 #define KP_HOT static inline
 #define KP_LANES 1
+#define KP_NOUNROLL
 #define KP_SYNC() ((void)0)
 #define KP_BCAST(x) (x)
 #define KP_CLZ(x) __builtin_clz(x)
@@ -51,6 +53,12 @@
 
 #include "kp_types.h"
 
+#ifdef __CUDACC__
+typedef uint4 KpU4;
+#else
+typedef struct { uint32_t x, y, z, w; } KpU4;
+#endif
+
 /* lane-0 state of the slice being parsed */
 typedef struct {
     const uint32_t *words; uint32_t n_words, wpos; uint64_t cache; int bits;
@@ -59,8 +67,7 @@ typedef struct {
     const h264b200_slice_t *sl;
     uint32_t W, N, addr; int mbx, mby;
     int is_p, qp;
-    const KpMbCtx *cA, *cB, *cC, *cD;
-    const h264b200_mb_t *rA, *rB, *rC, *rD;
+    uint32_t avail;              /* bit 0..3: macroblock A, B, C, D belongs to this slice (staged in st->nctx / nrec [0..3]) */
     uint32_t n_slots;            /* slots of the current macroblock */
     uint32_t coef_used, n_intra, n_inter, any_deblock;
     int32_t ipcm_byte;           /* >= 0: the macroblock is I_PCM, its 384 samples start at this RBSP byte */
@@ -113,7 +120,7 @@ KP_FN int kp_more_data(const KpS &s) { return kp_pos(s) < s.payload_bits; }
 KP_FN int kp_overrun(const KpS &s) { return kp_pos(s) > s.rbsp_bits; }
 
 /* ------------------------------------------------------------------ CAVLC block (h264_cavlc_inl.h) */
-/* Levels go to out[scan[i]] (scan == NULL: identity, chroma DC); `out` is all zero on entry.  Returns TotalCoeff or -1. */
+/* Levels go to out[scan[i]]; `out` is all zero on entry.  Returns TotalCoeff or -1. */
 KP_HOT int kp_cavlc_block_full(KpS &s, int nc, int max_coeff, int16_t *out, const uint8_t *scan)
 {
     const KpTables *T = s.T;
@@ -121,8 +128,7 @@ KP_HOT int kp_cavlc_block_full(KpS &s, int nc, int max_coeff, int16_t *out, cons
     int tc, t1, i, sl, zeros_left, pos;
     uint32_t v;
 
-    kp_need32(s);
-    v = (uint32_t)(s.cache >> 32);
+    v = (uint32_t)(s.cache >> 32);                               /* the caller made sure of 32 valid bits */
     if (nc < 0) {
         const uint8_t *e = T->ct_cdc[v >> 24];
         if (!e[0]) return -1;
@@ -149,6 +155,7 @@ KP_HOT int kp_cavlc_block_full(KpS &s, int nc, int max_coeff, int16_t *out, cons
         level[0] = (int16_t)(1 - (int)((sg >> 1) & 2)); level[1] = (int16_t)(1 - (int)(sg & 2)); level[2] = (int16_t)(1 - (int)((sg << 1) & 2));
         kp_skip(s, t1);
     }
+KP_NOUNROLL
     for (i = t1; i < tc; i++) {
         int lv;
         const int8_t *q;
@@ -187,9 +194,10 @@ KP_HOT int kp_cavlc_block_full(KpS &s, int nc, int max_coeff, int16_t *out, cons
     } else zeros_left = 0;
 
     pos = zeros_left + tc - 1;
+KP_NOUNROLL
     for (i = 0; i < tc - 1 && zeros_left > 0; i++) {
         int run;
-        out[scan ? scan[pos] : pos] = level[i];
+        out[scan[pos]] = level[i];
         {
             const uint8_t *e = T->rb[(zeros_left < 7 ? zeros_left : 7) - 1][kp_peek(s, 3)];
             if (e[0]) { kp_skip(s, e[0]); run = e[1]; }
@@ -205,175 +213,135 @@ KP_HOT int kp_cavlc_block_full(KpS &s, int nc, int max_coeff, int16_t *out, cons
         zeros_left -= run;
         pos -= run + 1;
     }
-    for (; i < tc; i++, pos--) out[scan ? scan[pos] : pos] = level[i];
+KP_NOUNROLL
+    for (; i < tc; i++, pos--) out[scan[pos]] = level[i];
     return tc;
 }
-KP_FN int kp_cavlc_block(KpS &s, int nc, int max_coeff, int16_t *out, const uint8_t *scan)
-{
-    if ((unsigned)nc < 2u) {
-        if (s.bits < 1) kp_refill(s);
-        if (s.cache >> 63) { kp_skip(s, 1); return 0; }
-    }
-    return kp_cavlc_block_full(s, nc, max_coeff, out, scan);
-}
-
-/* ------------------------------------------------------------------ motion vector prediction (h264_slice.c) */
-typedef struct { int avail, ref, x, y; } KpMvn;
-
-KP_FN KpMvn kp_mvn_from(const KpMbCtx *c, const h264b200_mb_t *r, int x4, int y4)
-{
-    KpMvn n; n.avail = 0; n.ref = -1; n.x = n.y = 0;
-    if (!c) return n;
-    n.avail = 1;
-    if (c->kind == H264B200_MB_INTER) {
-        n.ref = c->ref_idx[(y4 >> 1) * 2 + (x4 >> 1)];
-        n.x = r->mv[y4 * 4 + x4][0]; n.y = r->mv[y4 * 4 + x4][1];
-    }
-    return n;
-}
-KP_FN KpMvn kp_mvn_at(const KpS &s, int x4, int y4, unsigned done)
-{
-    KpMvn n; n.avail = 0; n.ref = -1; n.x = n.y = 0;
-    if (y4 < 0) {
-        if (x4 < 0) return kp_mvn_from(s.cD, s.rD, 3, 3);
-        if (x4 > 3) return kp_mvn_from(s.cC, s.rC, x4 - 4, 3);
-        return kp_mvn_from(s.cB, s.rB, x4, 3);
-    }
-    if (x4 < 0) return kp_mvn_from(s.cA, s.rA, 3, y4);
-    if (x4 > 3) return n;
-    if (!((done >> (y4 * 4 + x4)) & 1)) return n;
-    n.avail = 1;
-    n.ref = s.st->ctx.ref_idx[(y4 >> 1) * 2 + (x4 >> 1)];
-    n.x = s.st->rec.mv[y4 * 4 + x4][0]; n.y = s.st->rec.mv[y4 * 4 + x4][1];
-    return n;
-}
+/* ------------------------------------------------------------------ motion vector prediction (h264_slice.c predict_mv) */
+/* The vectors and reference indices a prediction can look at form a 5 x 6 grid (KpStage.mvg / refg): row 0 = the row
+ * of 4x4 blocks above the macroblock (D, B0..B3, C), column 0 = the column to its left (A0..A3), the rest = the
+ * macroblock itself.  The border is filled by the whole warp when the neighbours are staged (kp_stage_derive); the
+ * interior starts "not available" and is filled as the partitions are derived, which is exactly the availability rule
+ * inside a macroblock.  refg: -2 not available, -1 available but not inter, else refIdxL0. */
+#define KP_G(r, c) ((r) * 12 + 3 + (c))      /* row stride 12: the four interior entries of a row start 16-byte aligned */
 KP_FN int kp_median3(int a, int b, int c) { int mx = a > b ? a : b, mn = a < b ? a : b; return c > mx ? mx : c < mn ? mn : c; }
 
-/* dir: 0 median, 1 A first, 2 B first, 3 C first */
-KP_HOT void kp_predict_mv(const KpS &s, int x4, int y4, int w4, int ref, unsigned done, int dir, int *px, int *py)
+/* dir: 0 median, 1 A first (8x16 left / 16x8 bottom), 2 B first (16x8 top), 3 C first (8x16 right).  Returns {hor, ver} packed. */
+KP_FN uint32_t kp_predict_mv(const KpStage *st, int x4, int y4, int w4, int ref, int dir)
 {
-    KpMvn a = kp_mvn_at(s, x4 - 1, y4, done), b = kp_mvn_at(s, x4, y4 - 1, done), c = kp_mvn_at(s, x4 + w4, y4 - 1, done);
-    if (!c.avail) c = kp_mvn_at(s, x4 - 1, y4 - 1, done);
-    if (dir == 1 && a.ref == ref) { *px = a.x; *py = a.y; return; }
-    if (dir == 2 && b.ref == ref) { *px = b.x; *py = b.y; return; }
-    if (dir == 3 && c.ref == ref) { *px = c.x; *py = c.y; return; }
-    if (b.avail || c.avail || !a.avail) {
-        int ia = a.ref == ref, ib = b.ref == ref, ic = c.ref == ref;
-        if (ia + ib + ic != 1) { *px = kp_median3(a.x, b.x, c.x); *py = kp_median3(a.y, b.y, c.y); }
-        else if (ia) { *px = a.x; *py = a.y; }
-        else if (ib) { *px = b.x; *py = b.y; }
-        else { *px = c.x; *py = c.y; }
-    } else { *px = a.x; *py = a.y; }
+    const int ia = KP_G(y4 + 1, x4), ib = KP_G(y4, x4 + 1);
+    int ic = KP_G(y4, x4 + 1 + w4);
+    const int ra = st->refg[ia], rb = st->refg[ib];
+    int rc = st->refg[ic];
+    if (rc == -2) { ic = KP_G(y4, x4); rc = st->refg[ic]; }      /* C not available: D */
+    const uint32_t ma = st->mvg[ia], mb = st->mvg[ib], mc = st->mvg[ic];
+    if (dir == 1 && ra == ref) return ma;
+    if (dir == 2 && rb == ref) return mb;
+    if (dir == 3 && rc == ref) return mc;
+    if (rb != -2 || rc != -2 || ra == -2) {
+        const int ea = ra == ref, eb = rb == ref, ec = rc == ref;
+        if (ea + eb + ec != 1) {
+            const int mx = kp_median3((int16_t)(ma & 0xffff), (int16_t)(mb & 0xffff), (int16_t)(mc & 0xffff));
+            const int my = kp_median3((int32_t)ma >> 16, (int32_t)mb >> 16, (int32_t)mc >> 16);
+            return (uint32_t)(uint16_t)mx | ((uint32_t)(uint16_t)my << 16);
+        }
+        return ea ? ma : eb ? mb : mc;
+    }
+    return ma;
 }
 KP_FN int kp_mv_in_range(int x, int y) { return x >= -8192 && x <= 8191 && y >= -2048 && y <= 2047; }
-KP_FN void kp_fill_mv(h264b200_mb_t *r, int x4, int y4, int w4, int h4, int mx, int my, unsigned *done)
-{
-    const uint32_t v = (uint32_t)(uint16_t)mx | ((uint32_t)(uint16_t)my << 16);
-    for (int j = y4; j < y4 + h4; j++) {
-        uint32_t *row = (uint32_t *)r->mv[j * 4 + x4];
-        for (int i = 0; i < w4; i++) row[i] = v;
-        *done |= ((1u << w4) - 1u) << (j * 4 + x4);
-    }
-}
 
 /* ------------------------------------------------------------------ residual */
-/* nC (9.2.1): the blocks to the left of / above luma4x4BlkIdx b, one nibble each; blocks 0,2,8,10 take the left one
- * from macroblock A, blocks 0,1,4,5 the upper one from macroblock B */
-#define KP_LEFT_BLK 0xEBC9AF8D63412705ull
-#define KP_UP_BLK   0xDC76983254FE10BAull
-KP_FN int kp_nc_avg(int a, int b)            /* 64 = not available */
+/* nC (9.2.1) from TotalCoeff grids with one guard row above and one guard column to the left (KpStage.lc: luma, 5 rows
+ * of 8; KpStage.cc: one 3 x 4 grid per chroma plane), the host parser's own layout (h264_slice.c parse_residual): the
+ * guards come from macroblocks A and B (64 = not available, so that a + b >= 64 exactly when a neighbour is missing) and
+ * are written by the whole warp when the neighbours are staged; the interior starts at zero. */
+KP_FN int kp_nc_avg(int a, int b)
 {
     int n = a + b;
     if (n < 64) n = (n + 1) >> 1;
     return n & 31;
 }
-KP_FN int kp_nc_luma(const KpS &s, int blk)
-{
-    const int lb = (int)((KP_LEFT_BLK >> (4 * blk)) & 15), ub = (int)((KP_UP_BLK >> (4 * blk)) & 15);
-    const int a = ((0x0505 >> blk) & 1) ? (s.cA ? s.cA->tc[lb] : 64) : s.st->ctx.tc[lb];
-    const int b = ((0x0033 >> blk) & 1) ? (s.cB ? s.cB->tc[ub] : 64) : s.st->ctx.tc[ub];
-    return kp_nc_avg(a, b);
-}
-KP_FN int kp_nc_chroma(const KpS &s, int pl, int k)
-{
-    const int base = 16 + 4 * pl;
-    const int a = (k & 1) ? s.st->ctx.tc[base + k - 1] : (s.cA ? s.cA->tc[base + k + 1] : 64);
-    const int b = (k & 2) ? s.st->ctx.tc[base + k - 2] : (s.cB ? s.cB->tc[base + k + 2] : 64);
-    return kp_nc_avg(a, b);
-}
 
+/* residual( ) of 7.3.5.3 as ONE loop with ONE call of the block decoder (code size: the kernel has to live in the
+ * instruction cache): step 0 = Intra16x16 DC, 1..16 = luma4x4BlkIdx 0..15, 17/18 = chroma DC Cb/Cr, 19..26 = chroma AC.
+ * Slot order and masks as include/h264b200_records.h says.  Returns 0 / -1. */
 KP_HOT int kp_parse_residual(KpS &s, int cbp, int i16)
 {
-    h264b200_mb_t *r = &s.st->rec; KpMbCtx *c = &s.st->ctx;
+    KpStage *st = s.st;
+    h264b200_mb_t *r = &st->rec;
     const uint8_t *zz = s.T->zigzag;
-    uint32_t slot = 0, mask = 0;
-    int blk, pl, k, tc, dc_nz = 0;
-
+    uint32_t slot = 0, mask = 0, nz = 0;
+    int dc_nz = 0, cdc = 0;                                       /* cdc: bit 0 / 1: the Cb / Cr DC block has coefficients */
+    const int last = (cbp & 0x30) ? 27 : 17;
     r->coef_offset = s.coef_used;
-    if (i16) {
-        /* nC of the DC block = nC of block 0 */
-        tc = kp_cavlc_block(s, kp_nc_luma(s, 0), 16, s.st->slots, zz);
-        if (tc < 0) return -1;
-        if (tc) { dc_nz = 1; mask |= H264B200_RESID_LUMA_DC; slot++; }
-    }
-    for (blk = 0; blk < 16; blk++) {
-        int16_t *p;
-        if (!((cbp >> (blk >> 2)) & 1)) {
-            if (dc_nz) { mask |= 15u << blk; slot += 4; }        /* four all-zero slots (staging is zero) */
-            blk += 3;
-            continue;
-        }
-        p = s.st->slots + slot * 16;
-        if (i16) tc = kp_cavlc_block(s, kp_nc_luma(s, blk), 15, p, zz + 1);
-        else     tc = kp_cavlc_block(s, kp_nc_luma(s, blk), 16, p, zz);
-        if (tc < 0) return -1;
-        c->tc[blk] = (uint8_t)tc;
-        if (tc) { r->nz_mask |= (uint16_t)(1u << blk); mask |= 1u << blk; slot++; }
-        else if (dc_nz) { mask |= 1u << blk; slot++; }
-    }
-    if (cbp & 0x30) {
-        int16_t *p = s.st->slots + slot * 16;
-        int cdc[2];
-        for (pl = 0; pl < 2; pl++) {
-            cdc[pl] = kp_cavlc_block(s, -1, 4, p + 4 * pl, NULL);
-            if (cdc[pl] < 0) return -1;
-        }
-        if (cdc[0] || cdc[1]) { mask |= H264B200_RESID_CHROMA_DC; slot++; }
-        for (pl = 0; pl < 2; pl++) for (k = 0; k < 4; k++) {
-            p = s.st->slots + slot * 16;
-            tc = 0;
-            if (cbp & 0x20) {
-                tc = kp_cavlc_block(s, kp_nc_chroma(s, pl, k), 15, p, zz + 1);
-                if (tc < 0) return -1;
+KP_NOUNROLL
+    for (int step = i16 ? 0 : 1; step < last; step++) {
+        int nc, maxc, tc;
+        uint8_t *g;                                               /* where TotalCoeff of this block goes */
+        int16_t *out = st->slots + slot * 16;
+        const uint8_t *scan = zz + i16;
+        maxc = 16 - i16;
+        if (step < 17) {
+            const int blk = step ? step - 1 : 0;
+            if (step && !((cbp >> (blk >> 2)) & 1)) {             /* 8x8 quadrant without coefficients */
+                if (dc_nz) { mask |= 15u << blk; slot += 4; }     /* four all-zero slots (staging is zero) */
+                step += 3;
+                continue;
             }
-            c->tc[16 + 4 * pl + k] = (uint8_t)tc;
-            if (tc) { mask |= 1u << (16 + 4 * pl + k); slot++; }
-            else if (cdc[pl]) { mask |= 1u << (16 + 4 * pl + k); slot++; }
+            g = st->lc + s.T->lc_idx[blk];
+            nc = kp_nc_avg(g[-1], g[-8]);
+            if (!step) { maxc = 16; scan = zz; g = &st->lvl_dummy; }
+        } else if (step < 19) { nc = -1; maxc = 4; out += 4 * (step - 17); scan = s.T->ident4; g = &st->lvl_dummy; }
+        else {
+            const int pl = (step - 19) >> 2, k = (step - 19) & 3;
+            if (!(cbp & 0x20)) {                                  /* DC only: a slot per block of a plane whose DC is coded */
+                if ((cdc >> pl) & 1) { mask |= 1u << (step - 3); slot++; }
+                continue;
+            }
+            g = st->cc[pl] + 5 + (k & 1) + 4 * (k >> 1);
+            nc = kp_nc_avg(g[-1], g[-4]); maxc = 15; scan = zz + 1;
         }
+        /* two blocks out of three are empty, and with sparse neighbours that is the single bit '1' */
+        kp_need32(s);
+        if ((unsigned)nc < 2u && (int64_t)s.cache < 0) { kp_skip(s, 1); tc = 0; }
+        else {
+            tc = kp_cavlc_block_full(s, nc, maxc, out, scan);
+            if (tc < 0) return -1;
+            *g = (uint8_t)tc;
+        }
+        if (step == 0) { if (tc) { dc_nz = 1; mask |= H264B200_RESID_LUMA_DC; slot++; } }
+        else if (step < 17) {
+            if (tc) { nz |= 1u << (step - 1); mask |= 1u << (step - 1); slot++; }
+            else if (dc_nz) { mask |= 1u << (step - 1); slot++; }
+        } else if (step < 19) {
+            if (tc) cdc |= 1 << (step - 17);
+            if (step == 18 && cdc) { mask |= H264B200_RESID_CHROMA_DC; slot++; }
+        } else if (tc || ((cdc >> ((step - 19) >> 2)) & 1)) { mask |= 1u << (step - 3); slot++; }
     }
-    r->resid_mask = mask;
+    r->resid_mask = mask; r->nz_mask = (uint16_t)nz;
     s.n_slots = slot;
     return 0;
 }
 
 /* ------------------------------------------------------------------ intra */
-KP_FN int kp_intra_usable(const KpS &s, const KpMbCtx *c)
+KP_FN int kp_intra_usable(const KpS &s, int nb)
 {
-    return c && !(s.sl->constrained_intra && c->kind == H264B200_MB_INTER);
+    return ((s.avail >> nb) & 1) && !(s.sl->constrained_intra && s.st->nctx[nb].kind == H264B200_MB_INTER);
 }
-KP_FN int kp_pred_i4_mode(const KpS &s, int blk)
+KP_FN int kp_pred_i4_mode(const KpS &s, int blk, int aA, int aB)
 {
     const uint8_t *r2b = s.T->raster_to_blk;
     int r = r2b[blk], x4 = r & 3, y4 = r >> 2, ma, mb;
     if (x4 > 0) ma = s.st->rec.i4_mode[r2b[r - 1]];
     else {
-        if (!kp_intra_usable(s, s.cA)) return 2;
-        ma = s.cA->kind == H264B200_MB_I4x4 ? s.rA->i4_mode[r2b[r + 3]] : 2;
+        if (!aA) return 2;
+        ma = s.st->nctx[0].kind == H264B200_MB_I4x4 ? s.st->nrec[0].i4_mode[r2b[r + 3]] : 2;
     }
     if (y4 > 0) mb = s.st->rec.i4_mode[r2b[r - 4]];
     else {
-        if (!kp_intra_usable(s, s.cB)) return 2;
-        mb = s.cB->kind == H264B200_MB_I4x4 ? s.rB->i4_mode[r2b[12 + x4]] : 2;
+        if (!aB) return 2;
+        mb = s.st->nctx[1].kind == H264B200_MB_I4x4 ? s.st->nrec[1].i4_mode[r2b[12 + x4]] : 2;
     }
     return ma < mb ? ma : mb;
 }
@@ -390,83 +358,42 @@ KP_FN void kp_set_qp_fields(const KpS &s, h264b200_mb_t *r)
     r->qp_y = (uint8_t)s.qp; r->qp_dbk = (uint8_t)s.qp; r->qp_c = s.T->qpc[qc];
 }
 
-KP_HOT int kp_parse_intra_mb(KpS &s, uint32_t mb_type /* 0 I4x4, 1..24 I16x16, 25 I_PCM */)
+/* mb_pred of an intra macroblock (mb_type 0 I4x4, 1..24 I16x16; I_PCM is handled by the caller): modes + legality.
+ * Returns coded_block_pattern (>= 0), -1 on an error, -2 when coded_block_pattern is still to be read (I4x4). */
+KP_HOT int kp_intra_pred(KpS &s, uint32_t mb_type)
 {
     h264b200_mb_t *r = &s.st->rec; KpMbCtx *c = &s.st->ctx;
-    const int aA = kp_intra_usable(s, s.cA), aB = kp_intra_usable(s, s.cB), aC = kp_intra_usable(s, s.cC), aD = kp_intra_usable(s, s.cD);
-    uint32_t v; int blk, cbp;
+    const int aA = kp_intra_usable(s, 0), aB = kp_intra_usable(s, 1), aC = kp_intra_usable(s, 2), aD = kp_intra_usable(s, 3);
+    uint32_t v;
     r->avail = (uint8_t)((aA ? H264B200_AVAIL_A : 0) | (aB ? H264B200_AVAIL_B : 0) | (aC ? H264B200_AVAIL_C : 0) | (aD ? H264B200_AVAIL_D : 0));
-    c->ref_idx[0] = c->ref_idx[1] = c->ref_idx[2] = c->ref_idx[3] = -1;
-    s.n_intra++;
-    if (mb_type == 25) {
-        uint32_t byte_pos;
-        c->kind = r->mb_class = H264B200_MB_IPCM;
-        while (kp_pos(s) & 7) if (kp_get1(s)) return -1;            /* pcm_alignment_zero_bit */
-        byte_pos = kp_pos(s) >> 3;
-        if (byte_pos + 384 > (s.rbsp_bits >> 3)) return -1;
-        r->coef_offset = s.coef_used;
-        s.ipcm_byte = (int32_t)byte_pos;                           /* the warp copies the samples when the macroblock is stored */
-        s.n_slots = 12;
-        {   /* reposition behind the samples */
-            const uint32_t np = byte_pos + 384;
-            s.wpos = np >> 2; s.cache = 0; s.bits = 0;
-            kp_refill(s);
-            s.cache <<= 8 * (np & 3); s.bits -= (int)(8 * (np & 3));
-        }
-        for (blk = 0; blk < 24; blk++) c->tc[blk] = 16;
-        r->nz_mask = 0xffff;
-        kp_set_qp_fields(s, r);
-        r->qp_dbk = 0;
-        return 0;
-    }
     if (mb_type == 0) {
         const uint8_t *r2b = s.T->raster_to_blk;
         c->kind = r->mb_class = H264B200_MB_I4x4;
-        for (blk = 0; blk < 16; blk++) {
-            int pred = kp_pred_i4_mode(s, blk), mode;
+KP_NOUNROLL
+        for (int blk = 0; blk < 16; blk++) {
+            int pred = kp_pred_i4_mode(s, blk, aA, aB), mode;
             if (kp_get1(s)) mode = pred;
             else { int rem = (int)kp_get(s, 3); mode = rem < pred ? rem : rem + 1; }
             r->i4_mode[blk] = (uint8_t)mode;
             {
-                int rr = r2b[blk], x4 = rr & 3, y4 = rr >> 2;
-                int left = x4 > 0 ? 1 : aA, up = y4 > 0 ? 1 : aB;
-                int ul = (x4 > 0 && y4 > 0) ? 1 : x4 > 0 ? aB : y4 > 0 ? aA : aD;
-                switch (mode) {
-                case 0: case 3: case 7: if (!up) return -1; break;
-                case 1: case 8: if (!left) return -1; break;
-                case 4: case 5: case 6: if (!up || !left || !ul) return -1; break;
-                default: break;
-                }
+                const int rr = r2b[blk], x4 = rr & 3, y4 = rr >> 2;
+                const int left = x4 > 0 ? 1 : aA, up = y4 > 0 ? 1 : aB;
+                const int ul = (x4 > 0 && y4 > 0) ? 1 : x4 > 0 ? aB : y4 > 0 ? aA : aD;
+                /* modes 0,3,7 need up; 1,8 left; 4,5,6 all three (h264bsd_intra_prediction.c:773-823) */
+                const int need_up = (0x0f9 >> mode) & 1, need_left = (0x172 >> mode) & 1, need_ul = (0x070 >> mode) & 1;
+                if ((need_up && !up) || (need_left && !left) || (need_ul && !ul)) return -1;
             }
         }
     } else {
         c->kind = r->mb_class = H264B200_MB_I16x16;
         r->i16_mode = (uint8_t)((mb_type - 1) & 3);
-        switch (r->i16_mode) {
-        case 0: if (!aB) return -1; break;
-        case 1: if (!aA) return -1; break;
-        case 3: if (!aA || !aB || !aD) return -1; break;
-        default: break;
-        }
+        if ((r->i16_mode == 0 && !aB) || (r->i16_mode == 1 && !aA) || (r->i16_mode == 3 && (!aA || !aB || !aD))) return -1;
     }
     v = kp_ue(s); if (v > 3) return -1;
     r->chroma_mode = (uint8_t)v;
-    switch (v) {
-    case 1: if (!aA) return -1; break;
-    case 2: if (!aB) return -1; break;
-    case 3: if (!aA || !aB || !aD) return -1; break;
-    default: break;
-    }
-    if (mb_type == 0) {
-        v = kp_ue(s); if (v > 47) return -1;
-        cbp = s.T->cbp_map[v][0];
-    } else cbp = (((mb_type - 1) >> 2) % 3) << 4 | (mb_type >= 13 ? 15 : 0);
-    if (cbp || mb_type != 0) {
-        if (kp_update_qp(s, kp_se(s))) return -1;
-        kp_set_qp_fields(s, r);
-        if (kp_parse_residual(s, cbp, mb_type != 0)) return -1;
-    } else kp_set_qp_fields(s, r);
-    return 0;
+    if ((v == 1 && !aA) || (v == 2 && !aB) || (v == 3 && (!aA || !aB || !aD))) return -1;
+    if (mb_type == 0) return -2;
+    return (int)((((mb_type - 1) >> 2) % 3) << 4 | (mb_type >= 13 ? 15 : 0));
 }
 
 /* ------------------------------------------------------------------ inter */
@@ -478,107 +405,85 @@ KP_FN int kp_read_ref_idx(KpS &s, uint32_t n_active)
     if (v >= n_active) return -1;
     return (int)v;
 }
-KP_FN int kp_set_ref(KpS &s, int q, int ref)
-{
-    int slot = ref <= 16 ? s.sl->ref_slot[ref] : -1;
-    if (slot < 0) return -1;
-    s.st->ctx.ref_idx[q] = (int8_t)ref; s.st->rec.ref_slot[q] = (uint8_t)slot;
-    return 0;
-}
 
-KP_HOT int kp_parse_inter_mb(KpS &s, uint32_t mb_type /* 0..4 */)
+/* partitions of a P macroblock as a list (KpStage.part): x4 | y4 << 2 | (w4-1) << 4 | (h4-1) << 6 | quadrant << 8 | dir << 10 */
+#define KP_PART(x, y, w, h, q, d) ((uint16_t)((x) | ((y) << 2) | (((w) - 1) << 4) | (((h) - 1) << 6) | ((q) << 8) | ((d) << 10)))
+
+/* mb_pred / sub_mb_pred + vector derivation of a P macroblock; mb_type 0..4, or 5 = P_Skip (nothing is read).  0 / -1. */
+KP_HOT int kp_inter_pred(KpS &s, uint32_t mb_type)
 {
-    h264b200_mb_t *r = &s.st->rec; KpMbCtx *c = &s.st->ctx;
+    KpStage *st = s.st;
+    h264b200_mb_t *r = &st->rec; KpMbCtx *c = &st->ctx;
     const uint32_t n_active = s.sl->num_ref_idx_active;
-    uint32_t v;
-    unsigned done = 0;
-    int px, py, mx, my, i, cbp;
+    uint16_t *part = st->part;
+    int n_part, n_ref, skip_zero = 0;
     c->kind = r->mb_class = H264B200_MB_INTER;
-    s.n_inter++;
-    if (mb_type == 0) {
-        int ref = kp_read_ref_idx(s, n_active), dx, dy;
-        if (ref < 0) return -1;
-        for (i = 0; i < 4; i++) if (kp_set_ref(s, i, ref)) return -1;
-        dx = kp_se(s); dy = kp_se(s);
-        kp_predict_mv(s, 0, 0, 4, ref, 0, 0, &px, &py);
-        mx = (int16_t)((unsigned)px + (unsigned)dx); my = (int16_t)((unsigned)py + (unsigned)dy);
-        if (!kp_mv_in_range(mx, my)) return -1;
-        kp_fill_mv(r, 0, 0, 4, 4, mx, my, &done);
-        r->part_flags = 31;
-    } else if (mb_type == 1 || mb_type == 2) {
-        int ref[2], dx[2], dy[2];
-        for (i = 0; i < 2; i++) { ref[i] = kp_read_ref_idx(s, n_active); if (ref[i] < 0) return -1; }
-        for (i = 0; i < 2; i++) { dx[i] = kp_se(s); dy[i] = kp_se(s); }
-        if (mb_type == 1) { if (kp_set_ref(s, 0, ref[0]) || kp_set_ref(s, 1, ref[0]) || kp_set_ref(s, 2, ref[1]) || kp_set_ref(s, 3, ref[1])) return -1; }
-        else              { if (kp_set_ref(s, 0, ref[0]) || kp_set_ref(s, 2, ref[0]) || kp_set_ref(s, 1, ref[1]) || kp_set_ref(s, 3, ref[1])) return -1; }
-        for (i = 0; i < 2; i++) {
-            if (mb_type == 1) kp_predict_mv(s, 0, 2 * i, 4, ref[i], done, i == 0 ? 2 : 1, &px, &py);
-            else              kp_predict_mv(s, 2 * i, 0, 2, ref[i], done, i == 0 ? 1 : 3, &px, &py);
-            mx = (int16_t)((unsigned)px + (unsigned)dx[i]); my = (int16_t)((unsigned)py + (unsigned)dy[i]);
-            if (!kp_mv_in_range(mx, my)) return -1;
-            if (mb_type == 1) kp_fill_mv(r, 0, 2 * i, 4, 2, mx, my, &done);
-            else              kp_fill_mv(r, 2 * i, 0, 2, 4, mx, my, &done);
+    /* the partition list, and how many ref_idx are read (one per 16x16 / 16x8 / 8x16 partition or 8x8 quadrant) */
+    if (mb_type == 0 || mb_type == 5) { part[0] = KP_PART(0, 0, 4, 4, 0, 0); n_part = 1; n_ref = 1; r->part_flags = 31; }
+    else if (mb_type == 1) { part[0] = KP_PART(0, 0, 4, 2, 0, 2); part[1] = KP_PART(0, 2, 4, 2, 2, 1); n_part = 2; n_ref = 2; r->part_flags = 15; }
+    else if (mb_type == 2) { part[0] = KP_PART(0, 0, 2, 4, 0, 1); part[1] = KP_PART(2, 0, 2, 4, 1, 3); n_part = 2; n_ref = 2; r->part_flags = 15; }
+    else {
+        n_part = 0; n_ref = 4;
+KP_NOUNROLL
+        for (int q = 0; q < 4; q++) {
+            const uint32_t v = kp_ue(s);
+            const int ox = (q & 1) * 2, oy = (q >> 1) * 2;
+            if (v > 3) return -1;
+            if (v == 0) { part[n_part++] = KP_PART(ox, oy, 2, 2, q, 0); r->part_flags |= (uint8_t)(1 << q); }
+            else if (v == 1) { part[n_part++] = KP_PART(ox, oy, 2, 1, q, 0); part[n_part++] = KP_PART(ox, oy + 1, 2, 1, q, 0); }
+            else if (v == 2) { part[n_part++] = KP_PART(ox, oy, 1, 2, q, 0); part[n_part++] = KP_PART(ox + 1, oy, 1, 2, q, 0); }
+            else {
+                part[n_part++] = KP_PART(ox, oy, 1, 1, q, 0); part[n_part++] = KP_PART(ox + 1, oy, 1, 1, q, 0);
+                part[n_part++] = KP_PART(ox, oy + 1, 1, 1, q, 0); part[n_part++] = KP_PART(ox + 1, oy + 1, 1, 1, q, 0);
+            }
         }
-        r->part_flags = 15;
+    }
+    /* ref_idx_l0: quadrants covered by reference k are  16x16: all;  16x8: 2k, 2k+1;  8x16: k, k+2;  8x8: k */
+KP_NOUNROLL
+    for (int k = 0; k < n_ref; k++) {
+        const int ref = (mb_type >= 4) ? 0 : kp_read_ref_idx(s, n_active);
+        const int slot = (ref >= 0 && ref <= 16) ? s.sl->ref_slot[ref] : -1;
+        const uint32_t qm = n_ref == 1 ? 15u : n_ref == 4 ? 1u << k : mb_type == 1 ? 3u << (2 * k) : 5u << k;
+        if (ref < 0 || slot < 0) return -1;                       /* bad index, or a missing / non-existing picture (h264bsd_dpb.c:846-860) */
+        for (int q = 0; q < 4; q++) if ((qm >> q) & 1) { c->ref_idx[q] = (int8_t)ref; r->ref_slot[q] = (uint8_t)slot; }
+    }
+    /* mvd_l0, in partition order, before any vector is derived */
+    if (mb_type == 5) {
+        /* P_Skip: zero vector when A or B is missing or is a zero vector to reference 0 (h264bsd_inter_prediction.c:521-527) */
+        const int ra = st->refg[KP_G(1, 0)], rb = st->refg[KP_G(0, 1)];
+        st->mvd[0] = 0;
+        skip_zero = ra == -2 || rb == -2 || (ra == 0 && st->mvg[KP_G(1, 0)] == 0) || (rb == 0 && st->mvg[KP_G(0, 1)] == 0);
     } else {
-        int sub[4], ref[4], q, k;
-        uint32_t *mvd = s.st->mvd;                                /* read before any vector is derived (sub_mb_pred order) */
-        int n = 0, m = 0;
-        for (q = 0; q < 4; q++) { v = kp_ue(s); if (v > 3) return -1; sub[q] = (int)v; if (!v) r->part_flags |= (uint8_t)(1 << q); }
-        for (q = 0; q < 4; q++) {
-            ref[q] = mb_type == 4 ? 0 : kp_read_ref_idx(s, n_active);
-            if (ref[q] < 0 || kp_set_ref(s, q, ref[q])) return -1;
-        }
-        for (q = 0; q < 4; q++) {
-            int cnt = sub[q] == 0 ? 1 : sub[q] == 3 ? 4 : 2;
-            for (k = 0; k < cnt; k++) {
-                const uint32_t dx = (uint32_t)kp_se(s), dy = (uint32_t)kp_se(s);
-                mvd[n++] = (dx & 0xffffu) | (dy << 16);
-            }
-        }
-        for (q = 0; q < 4; q++) {
-            int ox = (q & 1) * 2, oy = (q >> 1) * 2, cnt = sub[q] == 0 ? 1 : sub[q] == 3 ? 4 : 2;
-            for (k = 0; k < cnt; k++, m++) {
-                int x4, y4, w4, h4;
-                switch (sub[q]) {
-                case 0: x4 = ox; y4 = oy; w4 = 2; h4 = 2; break;
-                case 1: x4 = ox; y4 = oy + k; w4 = 2; h4 = 1; break;
-                case 2: x4 = ox + k; y4 = oy; w4 = 1; h4 = 2; break;
-                default: x4 = ox + (k & 1); y4 = oy + (k >> 1); w4 = 1; h4 = 1; break;
-                }
-                kp_predict_mv(s, x4, y4, w4, ref[q], done, 0, &px, &py);
-                mx = (int16_t)((unsigned)px + (mvd[m] & 0xffffu)); my = (int16_t)((unsigned)py + (mvd[m] >> 16));
-                if (!kp_mv_in_range(mx, my)) return -1;
-                kp_fill_mv(r, x4, y4, w4, h4, mx, my, &done);
-            }
+KP_NOUNROLL
+        for (int k = 0; k < n_part; k++) {
+            const uint32_t dx = (uint32_t)kp_se(s), dy = (uint32_t)kp_se(s);
+            st->mvd[k] = (dx & 0xffffu) | (dy << 16);             /* only the low 16 bits reach the int16 vector */
         }
     }
-    v = kp_ue(s); if (v > 47) return -1;
-    cbp = s.T->cbp_map[v][1];
-    if (cbp) {
-        if (kp_update_qp(s, kp_se(s))) return -1;
-        kp_set_qp_fields(s, r);
-        if (kp_parse_residual(s, cbp, 0)) return -1;
-    } else kp_set_qp_fields(s, r);
-    return 0;
-}
-
-KP_HOT int kp_do_skip_mb(KpS &s)
-{
-    h264b200_mb_t *r = &s.st->rec; KpMbCtx *c = &s.st->ctx;
-    KpMvn a = kp_mvn_at(s, -1, 0, 0), bq = kp_mvn_at(s, 0, -1, 0);
-    int mx = 0, my = 0, i;
-    unsigned done = 0;
-    c->kind = r->mb_class = H264B200_MB_INTER;
-    s.n_inter++;
-    for (i = 0; i < 4; i++) if (kp_set_ref(s, i, 0)) return -1;
-    if (a.avail && bq.avail && !(a.ref == 0 && a.x == 0 && a.y == 0) && !(bq.ref == 0 && bq.x == 0 && bq.y == 0)) {
-        kp_predict_mv(s, 0, 0, 4, 0, 0, 0, &mx, &my);
+KP_NOUNROLL
+    for (int k = 0; k < n_part; k++) {
+        const uint32_t pt = part[k];
+        const int x4 = pt & 3, y4 = (pt >> 2) & 3, w4 = ((pt >> 4) & 3) + 1, h4 = ((pt >> 6) & 3) + 1;
+        const int ref = c->ref_idx[(pt >> 8) & 3];
+        const uint32_t pred = skip_zero ? 0u : kp_predict_mv(st, x4, y4, w4, ref, (pt >> 10) & 3);
+        const int mx = (int16_t)((pred & 0xffffu) + (st->mvd[k] & 0xffffu)), my = (int16_t)((pred >> 16) + (st->mvd[k] >> 16));
+        const uint32_t mv = (uint32_t)(uint16_t)mx | ((uint32_t)(uint16_t)my << 16);
         if (!kp_mv_in_range(mx, my)) return -1;
+        /* the interior of the grid is also the record's vector array (kp_stage_out copies its rows) */
+KP_NOUNROLL
+        for (int j = y4; j < y4 + h4; j++) {
+            uint32_t *row = &st->mvg[KP_G(j + 1, x4 + 1)];
+            int8_t *rrow = &st->refg[KP_G(j + 1, x4 + 1)];
+            if (w4 == 4) {
+                KpU4 v4; v4.x = v4.y = v4.z = v4.w = mv;
+                *(KpU4 *)row = v4;
+                *(uint32_t *)rrow = 0x01010101u * (uint32_t)(uint8_t)ref;
+            } else if (w4 == 2) {
+                row[0] = mv; row[1] = mv;
+                *(uint16_t *)rrow = (uint16_t)(0x0101u * (uint32_t)(uint8_t)ref);
+            } else { row[0] = mv; rrow[0] = (int8_t)ref; }
+        }
     }
-    kp_fill_mv(r, 0, 0, 4, 4, mx, my, &done);
-    r->part_flags = 31;
-    kp_set_qp_fields(s, r);
     return 0;
 }
 
@@ -587,45 +492,84 @@ KP_HOT int kp_do_skip_mb(KpS &s)
 #define KP_MB_FAIL      1    /* syntax error: the context of the macroblock is cleared, nothing else is stored */
 #define KP_MB_FAIL_KEEP 2    /* the macroblock had been decoded before (h264_slice.c: `if (c->decoded) return -1`): nothing is touched */
 
-/* neighbours are staged in s.st->nrec / nctx; returns KP_MB_* and leaves record / context / slots in the staging area */
+/* neighbours are staged (kp_stage_in, kp_stage_derive); returns KP_MB_* and leaves record / context / slots in the staging area */
 KP_FN int kp_parse_mb(KpS &s)
 {
     KpStage *st = s.st;
     h264b200_mb_t *r = &st->rec; KpMbCtx *c = &st->ctx;
     const h264b200_slice_t *sl = s.sl;
     const uint16_t sid = sl->slice_id;
-    int rc;
+    uint32_t mb_type;
+    int cbp = 0, i16 = 0;
     if (st->old.decoded) return KP_MB_FAIL_KEEP;
     c->slice_id = sid; r->slice_id = sid;
     r->chroma_qp_off = sl->chroma_qp_off;
     r->dbk_off_a = sl->alpha_off; r->dbk_off_b = sl->beta_off;
     r->dbk_idc = sl->disable_deblocking_idc;
-    s.cA = s.cB = s.cC = s.cD = NULL; s.rA = s.rB = s.rC = s.rD = NULL;
-    if (s.mbx > 0 && st->nctx[0].slice_id == sid) { s.cA = &st->nctx[0]; s.rA = &st->nrec[0]; }
-    if (s.mby > 0) {
-        if (st->nctx[1].slice_id == sid) { s.cB = &st->nctx[1]; s.rB = &st->nrec[1]; }
-        if (s.mbx + 1 < (int)s.W && st->nctx[2].slice_id == sid) { s.cC = &st->nctx[2]; s.rC = &st->nrec[2]; }
-        if (s.mbx > 0 && st->nctx[3].slice_id == sid) { s.cD = &st->nctx[3]; s.rD = &st->nrec[3]; }
-    }
     s.n_slots = 0; s.ipcm_byte = -1;
     if (s.is_p && !s.prev_skipped) {
         s.skip_run = kp_ue(s);
         if (s.skip_run == 0xffffffffu || s.skip_run > s.N - s.addr) return KP_MB_FAIL;
         if (s.skip_run) s.prev_skipped = 1;
     }
-    if (s.skip_run) { s.skip_run--; rc = kp_do_skip_mb(s); }
+    if (s.skip_run) { s.skip_run--; mb_type = 5; }
     else {
-        uint32_t mb_type = kp_ue(s);
+        mb_type = kp_ue(s);
         s.prev_skipped = 0;
-        if (s.is_p) {
-            if (mb_type > 30) return KP_MB_FAIL;
-            rc = mb_type < 5 ? kp_parse_inter_mb(s, mb_type) : kp_parse_intra_mb(s, mb_type - 5);
-        } else {
-            if (mb_type > 25) return KP_MB_FAIL;
-            rc = kp_parse_intra_mb(s, mb_type);
-        }
+        if (mb_type > (s.is_p ? 30u : 25u)) return KP_MB_FAIL;
+        /* one numbering for both slice types: 0..4 P partitions, 5 = P_Skip, 6.. = intra (I4x4, 24 x I16x16, I_PCM) */
+        if (!s.is_p) mb_type += 6;
+        else if (mb_type >= 5) mb_type += 1;
     }
-    if (rc || kp_overrun(s)) return KP_MB_FAIL;
+    if (mb_type <= 5) {
+        s.n_inter++;
+        if (kp_inter_pred(s, mb_type)) return KP_MB_FAIL;
+        if (mb_type < 5) {
+            const uint32_t v = kp_ue(s);
+            if (v > 47) return KP_MB_FAIL;
+            cbp = s.T->cbp_map[v][1];
+        }
+    } else {
+        const uint32_t it = mb_type - 6;                          /* 0 I4x4, 1..24 I16x16, 25 I_PCM */
+        c->ref_idx[0] = c->ref_idx[1] = c->ref_idx[2] = c->ref_idx[3] = -1;
+        s.n_intra++;
+        if (it == 25) {
+            uint32_t byte_pos;
+            r->avail = (uint8_t)((kp_intra_usable(s, 0) ? H264B200_AVAIL_A : 0) | (kp_intra_usable(s, 1) ? H264B200_AVAIL_B : 0) |
+                                 (kp_intra_usable(s, 2) ? H264B200_AVAIL_C : 0) | (kp_intra_usable(s, 3) ? H264B200_AVAIL_D : 0));
+            c->kind = r->mb_class = H264B200_MB_IPCM;
+            while (kp_pos(s) & 7) if (kp_get1(s)) return KP_MB_FAIL;      /* pcm_alignment_zero_bit */
+            byte_pos = kp_pos(s) >> 3;
+            if (byte_pos + 384 > (s.rbsp_bits >> 3)) return KP_MB_FAIL;
+            r->coef_offset = s.coef_used;
+            s.ipcm_byte = (int32_t)byte_pos;                       /* the warp copies the samples when the macroblock is stored */
+            s.n_slots = 12;
+            {   /* reposition behind the samples */
+                const uint32_t np = byte_pos + 384;
+                s.wpos = np >> 2; s.cache = 0; s.bits = 0;
+                kp_refill(s);
+                s.cache <<= 8 * (np & 3); s.bits -= (int)(8 * (np & 3));
+            }
+            r->nz_mask = 0xffff;                                   /* TotalCoeff 16 everywhere: kp_stage_out */
+            kp_set_qp_fields(s, r);
+            r->qp_dbk = 0;                                         /* h264bsd_macroblock_layer.c:1003 */
+            goto mb_done;
+        }
+        cbp = kp_intra_pred(s, it);
+        if (cbp == -1) return KP_MB_FAIL;
+        if (cbp == -2) {
+            const uint32_t v = kp_ue(s);
+            if (v > 47) return KP_MB_FAIL;
+            cbp = s.T->cbp_map[v][0];
+        } else i16 = 1;
+    }
+    if (cbp || i16) {
+        if (kp_update_qp(s, kp_se(s))) return KP_MB_FAIL;
+        kp_set_qp_fields(s, r);
+        if (kp_parse_residual(s, cbp, i16)) return KP_MB_FAIL;
+    } else kp_set_qp_fields(s, r);
+mb_done:
+    if (kp_overrun(s)) return KP_MB_FAIL;
     if (sl->disable_deblocking_idc != 1) {
         int fl = H264B200_DBK_INNER;
         if (s.mbx > 0 && (sl->disable_deblocking_idc != 2 || st->nctx[0].slice_id == sid)) fl |= H264B200_DBK_LEFT;
@@ -638,11 +582,6 @@ KP_FN int kp_parse_mb(KpS &s)
 }
 
 /* ------------------------------------------------------------------ warp-cooperative data movement */
-#ifdef __CUDACC__
-typedef uint4 KpU4;
-#else
-typedef struct { uint32_t x, y, z, w; } KpU4;
-#endif
 
 /* stage the neighbours A, B, C, D of macroblock `addr` (records + contexts) and the old context of `addr` itself;
  * clear the record / context being built */
@@ -664,13 +603,78 @@ KP_FN void kp_stage_in(int lane, const KpPic &p, KpStage *st, uint32_t addr, int
     }
 }
 
-/* store the finished macroblock: record, context, coefficient slots (re-zeroing the staging area) or I_PCM samples */
-KP_FN void kp_stage_out(int lane, const KpPic &p, KpStage *st, uint32_t addr, uint32_t coef_off, uint32_t n_slots,
+/* after kp_stage_in (and a warp sync): which neighbours belong to the slice; the guard cells of the TotalCoeff grids
+ * (nC) from macroblocks A and B and zeros inside; in P slices the border of the motion vector grid (KP_G) from the
+ * neighbour records, "not available" inside.  Every lane computes the same availability word. */
+KP_FN uint32_t kp_stage_derive(int lane, KpStage *st, uint16_t sid, int is_p, int mbx, int mby, uint32_t W)
+{
+    uint32_t av = 0;
+    if (mbx > 0 && st->nctx[0].slice_id == sid) av |= 1;
+    if (mby > 0) {
+        if (st->nctx[1].slice_id == sid) av |= 2;
+        if (mbx + 1 < (int)W && st->nctx[2].slice_id == sid) av |= 4;
+        if (mbx > 0 && st->nctx[3].slice_id == sid) av |= 8;
+    }
+    for (int v = lane; v < 64; v += KP_LANES) {
+        int val = 0;
+        if (v < 40) {                                             /* luma: 5 rows of 8, block (x, y) at 9 + x + 8 y */
+            const int rr = v >> 3, c = v & 7;
+            if (rr == 0 && c >= 1 && c <= 4) { const int i = c - 1; val = (av & 2) ? st->nctx[1].tc[10 + i + 2 * (i >> 1)] : 64; }       /* B: blocks 10 11 14 15 */
+            else if (rr >= 1 && c == 0) { const int i = rr - 1; val = (av & 1) ? st->nctx[0].tc[5 + 2 * i + 4 * (i >> 1)] : 64; }      /* A: blocks 5 7 13 15 */
+            st->lc[v] = (uint8_t)val;
+        } else {                                                  /* chroma: per plane 3 rows of 4, block (x, y) at 5 + x + 4 y */
+            const int w = v - 40, pl = w >= 12, i = w - 12 * pl, rr = i >> 2, c = i & 3;
+            if (rr == 0 && (c == 1 || c == 2)) val = (av & 2) ? st->nctx[1].tc[16 + 4 * pl + 1 + c] : 64;
+            else if (rr >= 1 && c == 0) val = (av & 1) ? st->nctx[0].tc[16 + 4 * pl + 2 * rr - 1] : 64;
+            st->cc[pl][i] = (uint8_t)val;
+        }
+    }
+    if (is_p) {
+        for (int v = lane; v < 60; v += KP_LANES) {
+            const int rr = v / 12, c = v - 12 * rr - 3;
+            int nb = -1, ri = 0, mi = 0, ref = -2;
+            uint32_t mv = 0;
+            if (rr == 0) {
+                if (c == 0) { nb = 3; ri = 3; mi = 15; }                                   /* D: its bottom right block */
+                else if (c >= 1 && c <= 4) { nb = 1; ri = 2 + ((c - 1) >> 1); mi = 11 + c; } /* B: bottom row */
+                else if (c == 5) { nb = 2; ri = 2; mi = 12; }                              /* C: bottom left block */
+            } else if (c == 0) { nb = 0; ri = ((rr - 1) >> 1) * 2 + 1; mi = (rr - 1) * 4 + 3; }   /* A: right column */
+            if (nb >= 0 && ((av >> nb) & 1)) {
+                ref = -1;
+                if (st->nctx[nb].kind == H264B200_MB_INTER) { ref = st->nctx[nb].ref_idx[ri]; mv = ((const uint32_t *)st->nrec[nb].mv)[mi]; }
+            }
+            st->refg[v] = (int8_t)ref; st->mvg[v] = mv;
+        }
+    }
+    return av;
+}
+
+/* store the finished macroblock: the record (its vector half = the interior rows of the motion vector grid), the
+ * context (TotalCoeff gathered from the nC grids), the coefficient slots (re-zeroing the staging area) or I_PCM samples */
+KP_FN void kp_stage_out(int lane, const KpPic &p, KpStage *st, const KpTables *T, uint32_t addr, uint32_t coef_off, uint32_t n_slots,
                         int32_t ipcm_byte, const uint8_t *rbsp)
 {
-    for (int v = lane; v < 32; v += KP_LANES) {
-        if (v < 8) ((KpU4 *)&p.mbs[addr])[v] = ((const KpU4 *)&st->rec)[v];
-        else if (v < 10) ((KpU4 *)&p.ctx[addr])[v - 8] = ((const KpU4 *)&st->ctx)[v - 8];
+    const int inter = st->rec.mb_class == H264B200_MB_INTER;
+    for (int v = lane; v < 16; v += KP_LANES) {
+        if (v < 4) ((KpU4 *)&p.mbs[addr])[v] = ((const KpU4 *)&st->rec)[v];
+        else if (v < 8) {
+            KpU4 row = {0, 0, 0, 0};
+            if (inter) row = *(const KpU4 *)&st->mvg[KP_G(v - 3, 1)];
+            ((KpU4 *)&p.mbs[addr])[v] = row;
+        } else {
+            const int w = v - 8;
+            uint32_t val;
+            if (w >= 6) val = ((const uint32_t *)&st->ctx)[w];
+            else if (ipcm_byte >= 0) val = 0x10101010u;
+            else if (w < 4) {
+                const uint8_t *ix = T->lc_idx + 4 * w;
+                val = (uint32_t)st->lc[ix[0]] | ((uint32_t)st->lc[ix[1]] << 8) | ((uint32_t)st->lc[ix[2]] << 16) | ((uint32_t)st->lc[ix[3]] << 24);
+            } else {
+                const uint8_t *g = st->cc[w - 4];
+                val = (uint32_t)g[5] | ((uint32_t)g[6] << 8) | ((uint32_t)g[9] << 16) | ((uint32_t)g[10] << 24);
+            }
+            ((uint32_t *)&p.ctx[addr])[w] = val;
+        }
     }
     if (ipcm_byte >= 0) {
         uint32_t *dst = (uint32_t *)(p.coef + (size_t)coef_off * 16);
@@ -823,6 +827,8 @@ KP_FN void kp_parse_picture(int lane, const KpPic &p, KpStage *st, const KpTable
             s.addr = addr;
             kp_stage_in(lane, p, st, addr, s.mbx, s.mby, W);
             KP_SYNC();
+            s.avail = kp_stage_derive(lane, st, sl->slice_id, s.is_p, s.mbx, s.mby, W);
+            KP_SYNC();
             if (lane == 0) {
                 rc = kp_parse_mb(s);
                 n_slots = s.n_slots; coef_off = s.coef_used; ipcm = s.ipcm_byte;
@@ -838,7 +844,7 @@ KP_FN void kp_parse_picture(int lane, const KpPic &p, KpStage *st, const KpTable
             KP_SYNC();
             rc = KP_BCAST(rc); more = KP_BCAST(more);
             n_slots = KP_BCAST(n_slots); coef_off = KP_BCAST(coef_off); ipcm = KP_BCAST(ipcm);
-            if (rc == KP_MB_OK) kp_stage_out(lane, p, st, addr, coef_off, n_slots, ipcm, rbsp);
+            if (rc == KP_MB_OK) kp_stage_out(lane, p, st, T, addr, coef_off, n_slots, ipcm, rbsp);
             else {
                 if (rc == KP_MB_FAIL) for (int v = lane; v < 2; v += KP_LANES) ((KpU4 *)&p.ctx[addr])[v] = ((const KpU4 *)&st->ctx)[v];
                 kp_stage_clear(lane, st);

@@ -19,7 +19,9 @@ typedef struct {
     uint8_t zigzag[16];
     uint8_t raster_to_blk[16];
     uint8_t qpc[52];
-    uint8_t pad[12];
+    uint8_t lc_idx[16];          /* luma4x4BlkIdx -> index of the block in the luma TotalCoeff grid (KpStage.lc): 9 + x4 + 8 y4 */
+    uint8_t ident4[4];           /* "scan" of a chroma DC block */
+    uint8_t pad[8];
 } KpTables;
 
 typedef struct {                 /* == h264_mbctx_t (h264_internal.h) */
@@ -38,7 +40,14 @@ typedef struct {
     KpMbCtx old;                 /* what ctx[addr] held before (a macroblock decoded twice is an error) */
     int16_t slots[27 * 16];      /* coefficient slots of this macroblock; ALL ZERO between macroblocks */
     int16_t lvl[16];             /* levels of the block being decoded, in decoding order */
-    uint32_t mvd[16];            /* P_8x8: the vector differences {hor, ver} (low 16 bits each: only those reach the int16 vector) */
+    uint32_t mvd[16];            /* the vector differences {hor, ver} of the partitions (low 16 bits each: only those reach the int16 vector) */
+    uint32_t mvg[60];            /* neighbour grid of motion vector prediction, 5 rows of 12 (kp_core.h KP_G); 16-byte aligned */
+    int8_t   refg[64];           /* ... and its reference indices: -2 not available, -1 not inter */
+    uint16_t part[16];           /* partition list of the macroblock (KP_PART) */
+    uint8_t  lc[40];             /* TotalCoeff grid of the luma blocks with guard row / column (nC), 5 rows of 8 */
+    uint8_t  cc[2][12];          /* ... of the chroma blocks, per plane 3 rows of 4 */
+    uint8_t  lvl_dummy;          /* where TotalCoeff of a DC block goes (it takes part in no nC) */
+    uint8_t  pad[15];
 } KpStage;
 
 typedef struct {                 /* outputs of one picture besides records / slots / contexts */

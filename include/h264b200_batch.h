@@ -24,6 +24,9 @@ extern "C" {
                                        access unit begins or at h264bsdFlushBuffer, so H264BSD_PIC_RDY comes one NAL unit later
                                        (with *readBytes == 0, the reference's own re-feed protocol, h264bsd_decoder.c:267-268) */
 
+#define H264B200_ENGINE_NO_RECON 16u /* parity aid: reconstruction rounds launch no K1..K4, so that what kernel Kp wrote (levels, not yet
+                                       transformed in place by K1) can be read back with h264b200DebugFetchParse; frames are garbage */
+
 h264b200_engine_t *h264b200EngineCreateEx(int device, uint32_t flags);
 void h264b200EngineSetFlags(h264b200_engine_t *e, uint32_t flags);
 uint32_t h264b200EngineFlags(h264b200_engine_t *e);

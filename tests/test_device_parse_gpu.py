@@ -31,14 +31,22 @@ def sync_engine():
         yield eng
 
 
+@pytest.fixture(scope="module")
+def parse_only_engine():
+    """Kp only (no K1..K4): the coefficient slots still hold the levels Kp wrote (K1 transforms them in place)"""
+    with capi.Engine(flags=DEV | capi.ENGINE_NO_RECON) as eng:
+        yield eng
+
+
 @pytest.mark.parametrize("case", cases.SMALL, ids=[c[0] for c in cases.SMALL])
-def test_device_parse_matches_golden_and_host_records(case, golden, sync_engine):
+def test_device_parse_matches_golden_and_host_records(case, golden, sync_engine, parse_only_engine):
     data = cases.make_stream(case)
-    got, info, parses = capi.decode_on_engine(sync_engine, data, fetch_parse=True)
+    got, info = capi.decode_on_engine(sync_engine, data)
     assert info["device_parse"] == 1
     assert info["err_mbs"] == 0
     assert got == golden[case[0]]["frame_md5"]
     # what Kp left in HBM against the host parser's records and coefficient slots
+    _, _, parses = capi.decode_on_engine(parse_only_engine, data, fetch_parse=True)
     host = util.capture_records(util.cpuchk_lib(), data, False)
     assert len(parses) == len(host) == case[3]
     n_mbs = case[1] * case[2]
