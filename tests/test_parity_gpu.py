@@ -285,3 +285,22 @@ def test_corrupted_streams_never_fault_and_equal_the_oracle():
         got, info = capi.decode_annexb(bytes(data))
         want, s = util.oracle_md5(bytes(data))
         assert got == want and info["err_mbs"] == s["err_mbs"]
+
+
+def test_cuda_luma_equals_ffmpeg_golden():
+    """Third-decoder check on the GPU path: the luma plane the CUDA engine reconstructs equals FFmpeg's for every
+    case FFmpeg can decode (tests/golden/ffmpeg_luma.json, tools/make_ffmpeg_golden.py; both parse modes)."""
+    import json
+    import os
+    import test_ffmpeg_crosscheck_cpu as ff
+    fx = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ffmpeg_luma.json")))
+    with capi.Engine(flags=capi.ENGINE_DEVICE_PARSE) as dev, capi.Engine(flags=0) as host:
+        for case in ff.CASES:
+            if case[1] * case[2] > 8160:
+                continue                                   # 4K: covered by the MD5 goldens
+            g = fx[case[0]]
+            data = cases.make_stream(case)
+            for eng in (dev, host):
+                frames, info = capi.decode_on_engine(eng, data, keep_frames=True)
+                got = ff.luma_md5s(b"".join(frames), info["width"], info["height"], g["rows"], g["cols"])
+                assert got == g["luma_md5"], case[0]
