@@ -154,6 +154,7 @@ struct ParseScratch {              /* one Kp launch */
 
 struct h264b200_engine {
     int device, sm_count;
+    uint32_t wf_cap;               /* CTAs per SM the wavefront kernels K3 / K4 are launched with at most (tickets hand out the rows); H264B200_WF_CAP, default 16 */
     cudaStream_t s_h2d, s_comp, s_d2h, s_parse[2];
     cudaEvent_t ev_h2d, ev_comp, ev_rep0, ev_rep1, ev_gate;
     std::mutex mu;
@@ -246,14 +247,14 @@ static void launch_kernels(h264b200_engine *e, const Batch &b, const BatchPlan &
     if (tev) cudaEventRecord(tev[2], s);
     uint32_t n_tasks = (uint32_t)pl.n_jobs * (uint32_t)pl.max_hm;
     if (pl.k3) {
-        uint32_t blocks = (n_tasks + K3_WARPS - 1) / K3_WARPS, cap = (uint32_t)e->sm_count * 16;
+        uint32_t blocks = (n_tasks + K3_WARPS - 1) / K3_WARPS, cap = (uint32_t)e->sm_count * e->wf_cap;
         k3_intra<<<blocks < cap ? blocks : cap, K3_WARPS * 32, 0, s>>>(b); e->st.kernel_launches++;
     }
     if (pl.k3c) { k3c_conceal<<<pl.n_jobs, 32, 0, s>>>(b); e->st.kernel_launches++; }   /* lost slices only: one warp per picture */
     if (tev) cudaEventRecord(tev[3], s);
     if (pl.k4) {                   /* one warp per PAIR of macroblock rows */
         uint32_t n_pairs = (uint32_t)pl.n_jobs * (((uint32_t)pl.max_hm + 1) / 2);
-        uint32_t blocks = (n_pairs + K4_WARPS - 1) / K4_WARPS, cap = (uint32_t)e->sm_count * 16;
+        uint32_t blocks = (n_pairs + K4_WARPS - 1) / K4_WARPS, cap = (uint32_t)e->sm_count * e->wf_cap;
         k4_deblock<<<blocks < cap ? blocks : cap, K4_WARPS * 32, 0, s>>>(b);
         e->st.kernel_launches++;
     }
@@ -892,6 +893,8 @@ extern "C" h264b200_engine_t *h264b200EngineCreateEx(int device, uint32_t flags)
     cudaDeviceProp p;
     CUDA_TRY(cudaGetDeviceProperties(&p, device), { delete e; return NULL; });
     e->sm_count = p.multiProcessorCount;
+    e->wf_cap = 16;
+    { const char *c = getenv("H264B200_WF_CAP"); if (c && atoi(c) > 0 && atoi(c) <= 64) e->wf_cap = (uint32_t)atoi(c); }
     CUDA_TRY(cudaStreamCreateWithFlags(&e->s_h2d, cudaStreamNonBlocking), { delete e; return NULL; });
     CUDA_TRY(cudaStreamCreateWithFlags(&e->s_comp, cudaStreamNonBlocking), { delete e; return NULL; });
     CUDA_TRY(cudaStreamCreateWithFlags(&e->s_d2h, cudaStreamNonBlocking), { delete e; return NULL; });

@@ -17,7 +17,7 @@
  * are handed out through an atomic ticket in (row-major, picture-minor) order,
  * so a warp only ever waits on tickets lower than its own, which are held by
  * resident warps: forward progress needs no co-residency guarantee beyond
- * that.  Hand-over is st.release.gpu on the row's progress counter and relaxed
+ * that.  Hand-over is st.release.gpu on the row's progress counter and acquire
  * polls with back-off on the row above (k_common.cuh); samples produced by other
  * warps are read with ld.global.cg (L2), never through the non-coherent L1.
  * Inside a macroblock: I16x16/chroma -> 8 / 4 samples per lane; I4x4 -> the

@@ -23,7 +23,7 @@
  *     2p+1 takes the samples above it from a two-slot ring in shared memory that
  *     row 2p fills, not from global memory, and never polls.  Only row 2p waits
  *     on another warp (the pair above), through the progress counter of row
- *     2p-1 (st.release / relaxed poll with back-off, ld.global.cg samples);
+ *     2p-1 (st.release / acquire poll with back-off, ld.global.cg samples);
  *   - the edge filter runs on TWO lines per lane, one per 16-bit half of a
  *     register (k4_simd.cuh: VABSDIFF4, VIMNMX.S16x2, PRMT sign masks, biased
  *     32-bit arithmetic): of the 16 lanes of a row, 8 hold two luma lines each
@@ -341,7 +341,7 @@ __device__ __forceinline__ void k4_body(const Batch &b)
                 if (top_ahead && half == 0) k4_fetch_top(g, i + 1, hl, p);
             }
             const bool poll = seen < wm;                 /* refresh `seen` once per step, without waiting for it here */
-            if (poll && lane == 0) polled = ld_acquire(above);
+            if (poll && lane == 0) { polled = ld_poll(above); wf_acquired(polled > seen); }   /* an acquire: k_common.cuh; the __syncwarp()s of the step order it before the other lanes' loads */
 
             const bool act = have && w.rec[x & 1].dbk_flags && w.rec[x & 1].mb_class != H264B200_MB_MISSING;
             const bool f = k4_filter(w, x, hl, half, act);

@@ -304,3 +304,22 @@ def test_cuda_luma_equals_ffmpeg_golden():
                 frames, info = capi.decode_on_engine(eng, data, keep_frames=True)
                 got = ff.luma_md5s(b"".join(frames), info["width"], info["height"], g["rows"], g["cols"])
                 assert got == g["luma_md5"], case[0]
+
+
+@pytest.mark.parametrize("cap", [1, 4, 16])
+def test_wavefront_handover_stress(cap, monkeypatch):
+    """the K3 / K4 row hand-over (st.release -> acquire poll, k_common.cuh) under stress: 200
+    replays of a retained batch of pictures of mixed sizes and types, at 1, 4 and 16 wavefront CTAs per SM (few CTAs:
+    long ticket queues, rows of one picture on the same warps; many: every row pair of every picture in flight at
+    once).  Every replay must rebuild exactly the frames of the live decode, which were checked against the goldens."""
+    monkeypatch.setenv("H264B200_WF_CAP", str(cap))
+    sel = [c for c in cases.SMALL if c[0] in ("ippp_default", "intra_only", "p_intra_mix", "multi_slice", "one_row", "one_col",
+                                               "odd_size", "wide", "deblock_idc2", "constrained_intra")]
+    streams = [cases.make_stream(c) for c in sel] + [bitstream.synth(120, 68, 3, seed=77 + i, p_intra_permille=200) for i in range(3)]
+    with capi.Engine(flags=capi.ENGINE_BATCHED | capi.ENGINE_RETAIN | capi.ENGINE_DEVICE_PARSE) as eng:
+        eng.decode_streams_md5(streams, threads=4)
+        assert eng.check_resident() == 0
+        for _ in range(20):
+            eng.replay(reps=10, time_kernels=False)
+            assert eng.check_resident() == 0
+        assert eng.error_flags() == 0
