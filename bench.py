@@ -374,15 +374,20 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        # the reference arm loads nothing of the product: only the stream writer (input generator) and oracle/_ref/refdec
+        if rank == 0:
+            from broadway_b200 import build as b
+            b.build_writer()
+            b.build_oracle()
+        reference_arm(args, rank, world)
+        return
     import __graft_entry__
     if local_rank == 0:
         __graft_entry__.build()
-    if args.impl == "reference":
-        reference_arm(args, rank, world)
-    else:
-        if args.warmup < 3:
-            log("note: fewer than 3 warm-up steps requested")
-        own_arm(args, rank, local_rank, world)
+    if args.warmup < 3:
+        log("note: fewer than 3 warm-up steps requested")
+    own_arm(args, rank, local_rank, world)
 
 
 if __name__ == "__main__":

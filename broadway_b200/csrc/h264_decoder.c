@@ -143,7 +143,7 @@ static int sps_equal(const h264_sps_t *a, const h264_sps_t *b) { return memcmp(a
 static int store_sps(h264_decoder_t *d, const h264_sps_t *s)
 {
     int id = s->sps_id;
-    if (!d->sps[id]) { d->sps[id] = (h264_sps_t *)malloc(sizeof *s); if (!d->sps[id]) return -1; }
+    if (!d->sps[id]) { d->sps[id] = (h264_sps_t *)h264_malloc(sizeof *s); if (!d->sps[id]) return -1; }
     else if (id == d->active_sps_id) {
         if (sps_equal(s, d->active_sps)) return 0;
         d->active_sps_id = H264_MAX_SPS + 1; d->active_pps_id = H264_MAX_PPS + 1;
@@ -155,9 +155,9 @@ static int store_sps(h264_decoder_t *d, const h264_sps_t *s)
 static int store_pps(h264_decoder_t *d, const h264_pps_t *p)
 {
     int id = p->pps_id;
-    if (!d->pps[id]) { d->pps[id] = (h264_pps_t *)malloc(sizeof *p); if (!d->pps[id]) return -1; }
+    if (!d->pps[id]) { d->pps[id] = (h264_pps_t *)h264_malloc(sizeof *p); if (!d->pps[id]) return -1; }
     else {
-        free((void *)d->pps[id]->fmo.group_id);     /* the stored copy owns the explicit slice group map */
+        h264_free((void *)d->pps[id]->fmo.group_id);     /* the stored copy owns the explicit slice group map */
         if (id == d->active_pps_id && p->sps_id != d->active_sps_id) d->active_pps_id = H264_MAX_PPS + 1;
     }
     *d->pps[id] = *p;
@@ -200,11 +200,11 @@ static int activate_param_sets(h264_decoder_t *d, uint32_t pps_id, int is_idr)
         const h264_sps_t *sps = d->active_sps;
         int no_reorder;
         d->pending_activation = 0;
-        free(d->mbctx);
-        d->mbctx = (h264_mbctx_t *)calloc(d->pic_size_mbs, sizeof(h264_mbctx_t));
+        h264_free(d->mbctx);
+        d->mbctx = (h264_mbctx_t *)h264_calloc(d->pic_size_mbs, sizeof(h264_mbctx_t));
         if (!d->mbctx) return -2;
-        free(d->slice_group_map);
-        d->slice_group_map = (uint8_t *)malloc(d->pic_size_mbs);
+        h264_free(d->slice_group_map);
+        d->slice_group_map = (uint8_t *)h264_malloc(d->pic_size_mbs);
         if (!d->slice_group_map) return -2;
         no_reorder = d->no_reordering_app || sps->poc_type == 2 ||
                      (sps->vui_present && sps->bitstream_restriction && !sps->num_reorder_frames);
@@ -450,7 +450,7 @@ u32 h264_decoder_create(storage_t *pStorage, u32 noOutputReordering, h264_backen
     h264_decoder_t *d;
     if (!pStorage) return HANTRO_NOK;
     memset(pStorage, 0, sizeof *pStorage);
-    d = (h264_decoder_t *)calloc(1, sizeof *d);
+    d = (h264_decoder_t *)h264_calloc(1, sizeof *d);
     if (!d) return HANTRO_NOK;
     h264_cavlc_init();
     d->be = be;
@@ -513,17 +513,17 @@ u32 h264bsdDecode(storage_t *pStorage, u8 *byteStrm, u32 len, u32 picId, u32 *re
 
     if (!pic_ready) switch (type) {
     case NAL_SPS: {
-        h264_sps_t *sps = (h264_sps_t *)malloc(sizeof *sps);
+        h264_sps_t *sps = (h264_sps_t *)h264_malloc(sizeof *sps);
         if (!sps) return H264BSD_MEMALLOC_ERROR;
         rc = h264_parse_sps(&b, sps);
         if (!rc) rc = store_sps(d, sps);
-        free(sps);
+        h264_free(sps);
         if (rc) return H264BSD_ERROR;
         break; }
     case NAL_PPS: {
         h264_pps_t pps;
-        if (h264_parse_pps(&b, &pps)) { free((void *)pps.fmo.group_id); return H264BSD_ERROR; }
-        if (store_pps(d, &pps)) { free((void *)pps.fmo.group_id); return H264BSD_MEMALLOC_ERROR; }
+        if (h264_parse_pps(&b, &pps)) { h264_free((void *)pps.fmo.group_id); return H264BSD_ERROR; }
+        if (store_pps(d, &pps)) { h264_free((void *)pps.fmo.group_id); return H264BSD_MEMALLOC_ERROR; }
         break; }
     case NAL_IDR:
     case NAL_SLICE: {
@@ -689,10 +689,10 @@ void h264bsdShutdown(storage_t *pStorage)
     int i;
     if (!d) return;
     if (d->be_inst) d->be->inst_destroy(d->be, d->be_inst);
-    for (i = 0; i < H264_MAX_SPS; i++) free(d->sps[i]);
-    for (i = 0; i < H264_MAX_PPS; i++) { if (d->pps[i]) free((void *)d->pps[i]->fmo.group_id); free(d->pps[i]); }
-    free(d->mbctx); free(d->slice_group_map);
-    free(d);
+    for (i = 0; i < H264_MAX_SPS; i++) h264_free(d->sps[i]);
+    for (i = 0; i < H264_MAX_PPS; i++) { if (d->pps[i]) h264_free((void *)d->pps[i]->fmo.group_id); h264_free(d->pps[i]); }
+    h264_free(d->mbctx); h264_free(d->slice_group_map);
+    h264_free(d);
     pStorage->impl = NULL;
 }
 

@@ -13,6 +13,14 @@
 #include "h264_bits.h"
 #include "h264_fmo.h"
 
+/* host-side allocations go through the embedder hooks of the API layer (H264SwDecApi.h:163-173; weak defaults in h264_swdec.c) */
+void *H264SwDecMalloc(unsigned int size);
+void H264SwDecFree(void *ptr);
+void H264SwDecMemset(void *ptr, int value, unsigned int count);
+static inline void *h264_malloc(size_t n) { return n > 0xffffffffu ? NULL : H264SwDecMalloc((unsigned int)n); }
+static inline void *h264_calloc(size_t k, size_t n) { void *p = (k && n > 0xffffffffu / k) ? NULL : H264SwDecMalloc((unsigned int)(k * n)); if (p) H264SwDecMemset(p, 0, (unsigned int)(k * n)); return p; }
+static inline void h264_free(void *p) { if (p) H264SwDecFree(p); }
+
 #ifdef __cplusplus
 extern "C" {
 #endif

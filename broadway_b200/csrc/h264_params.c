@@ -163,9 +163,9 @@ int h264_parse_pps(br_t *b, h264_pps_t *p)
             v = br_ue(b); CHECK_UE(v); if (v >= 36864u) return -1;
             n = v + 1; p->fmo_map_units = n;
             while ((1u << bits) < f->n_groups) bits++;
-            ids = (uint8_t *)malloc(n);
+            ids = (uint8_t *)h264_malloc(n);
             if (!ids) return -1;
-            for (i = 0; i < n; i++) { ids[i] = (uint8_t)br_get(b, (int)bits); if (ids[i] >= f->n_groups) { free(ids); return -1; } }
+            for (i = 0; i < n; i++) { ids[i] = (uint8_t)br_get(b, (int)bits); if (ids[i] >= f->n_groups) { h264_free(ids); return -1; } }
             f->group_id = ids;
         }
     }

@@ -9,6 +9,13 @@
 
 int h264_decoder_flushed_pending(storage_t *s);
 
+/* H264SwDecApi.c:78-96: the embedder hooks, here as weak defaults over the C library */
+__attribute__((weak)) void H264SwDecTrace(char *string) { (void)string; }
+__attribute__((weak)) void *H264SwDecMalloc(u32 size) { return malloc(size); }
+__attribute__((weak)) void H264SwDecFree(void *ptr) { free(ptr); }
+__attribute__((weak)) void H264SwDecMemcpy(void *dest, void *src, u32 count) { memcpy(dest, src, count); }
+__attribute__((weak)) void H264SwDecMemset(void *ptr, i32 value, u32 count) { memset(ptr, value, count); }
+
 enum { ST_UNINITIALIZED = 0, ST_INITIALIZED, ST_NEW_HEADERS };
 typedef struct { int stat; u32 pic_number; storage_t storage; } container_t;
 
@@ -18,9 +25,10 @@ H264SwDecRet H264SwDecInit(H264SwDecInst *decInst, u32 noOutputReordering)
     if (!decInst) return H264SWDEC_PARAM_ERR;
     *decInst = NULL;
     if (((-1) >> 1) != (-1)) return H264SWDEC_INITFAIL;       /* arithmetic right shift required (H264SwDecApi.c:134) */
-    c = (container_t *)calloc(1, sizeof *c);
+    c = (container_t *)H264SwDecMalloc((u32)sizeof *c);
     if (!c) return H264SWDEC_MEMFAIL;
-    if (h264bsdInit(&c->storage, noOutputReordering) != HANTRO_OK) { free(c); return H264SWDEC_INITFAIL; }
+    H264SwDecMemset(c, 0, (u32)sizeof *c);
+    if (h264bsdInit(&c->storage, noOutputReordering) != HANTRO_OK) { H264SwDecFree(c); return H264SWDEC_INITFAIL; }
     c->stat = ST_INITIALIZED;
     *decInst = c;
     return H264SWDEC_OK;
@@ -49,7 +57,7 @@ void H264SwDecRelease(H264SwDecInst decInst)
     container_t *c = (container_t *)decInst;
     if (!c) return;
     h264bsdShutdown(&c->storage);
-    free(c);
+    H264SwDecFree(c);
 }
 
 H264SwDecRet H264SwDecDecode(H264SwDecInst decInst, H264SwDecInput *in, H264SwDecOutput *out)

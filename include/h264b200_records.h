@@ -33,7 +33,7 @@
 #define H264B200_MB_IPCM    3
 #define H264B200_MB_CONCEAL 4   /* lost macroblock filled by spatial interpolation from its neighbours (h264bsd_conceal.c:330-631);
                                   `avail` then holds H264B200_CN_*: the neighbours usable at its turn of the concealment order */
-#define H264B200_MB_MISSING 255 /* never decoded (lost slice); concealment is out of scope */
+#define H264B200_MB_MISSING 255 /* never decoded and not concealable (no room for the concealment list): the samples of the frame slot stay as they are */
 
 /* avail bits: neighbour usable for intra sample prediction (position, slice,
  * constrained_intra_pred all resolved on the host; h264bsd_neighbour.c:369-381,

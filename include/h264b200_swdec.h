@@ -33,7 +33,7 @@ typedef struct {                                 /* H264SwDecApi.h:77-85 */
     u8 *pStream;                 /* stream to decode; the decoder edits it in place */
     u32 dataLen;
     u32 picId;                   /* caller's tag, returned with the picture */
-    u32 intraConcealmentMethod;  /* accepted, unused: concealment is out of scope */
+    u32 intraConcealmentMethod;  /* accepted; lost macroblocks of I pictures are always concealed the way the reference's default (0) does, csrc/k3c_conceal.cuh */
 } H264SwDecInput;
 
 typedef struct { u8 *pStrmCurrPos; } H264SwDecOutput;
@@ -60,6 +60,18 @@ H264SwDecRet H264SwDecNextPicture(H264SwDecInst decInst, H264SwDecPicture *pOutp
 H264SwDecRet H264SwDecGetInfo(H264SwDecInst decInst, H264SwDecInfo *pDecInfo);
 void H264SwDecRelease(H264SwDecInst decInst);
 H264SwDecApiVersion H264SwDecGetAPIVersion(void);
+
+/* Embedder hooks (H264SwDecApi.h:158-173).  The reference's API layer defines them itself with the C library
+ * (H264SwDecApi.c:78-96); so does this library, as WEAK symbols: an embedder that defines its own (every test bench of
+ * the reference does) overrides them at link / load time.  Every allocation of the host-side decoder state (parameter
+ * sets, macroblock contexts, slice group maps, instance containers) goes through H264SwDecMalloc / H264SwDecFree.
+ * Frame storage is NOT host heap memory here — it is CUDA device memory with pinned host mirrors — and is not routed
+ * through the hooks. */
+void H264SwDecTrace(char *string);
+void *H264SwDecMalloc(u32 size);
+void H264SwDecFree(void *ptr);
+void H264SwDecMemcpy(void *dest, void *src, u32 count);
+void H264SwDecMemset(void *ptr, i32 value, u32 count);
 
 #ifdef __cplusplus
 }

@@ -9,9 +9,11 @@
  *   (2) give the GPU parity tests a stage-by-stage checker (residual slots after
  *       K1, the picture before deblocking, the picture after deblocking).
  * PARITY PINNING: the reference ships no golden vectors; this
- * restatement is pinned by tests/test_oracle_vs_reference.py, which decodes the
- * synthetic streams with both and compares per-frame MD5, and by the MD5
- * fixtures under tests/golden/ generated from oracle/_ref.
+ * restatement is pinned by tests/test_oracle_cpu.py: against the per-frame MD5
+ * fixtures under tests/golden/ that tools/make_golden.py generated with oracle/_ref
+ * (the unmodified reference), against the live reference on a seeded parameter
+ * sweep where oracle/_ref is built, and by tests/test_ffmpeg_crosscheck_cpu.py
+ * against FFmpeg's luma.
  *
  * What each part restates (reference file:line):
  *   residual_mb      h264bsd_macroblock_layer.c:1343-1424 ProcessResidual,

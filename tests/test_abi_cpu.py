@@ -82,3 +82,48 @@ def test_split_gops_single_idr_and_empty():
     segs = capi.split_gops(data)
     assert len(segs) == 1 and segs[0] == data
     assert capi.split_gops(b"\x00\x00\x00\x01\x09\x10") == []
+
+
+HOOK_PROBE = r"""
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "h264b200_swdec.h"
+/* an embedder's own hooks, like every test bench of the reference defines them (DecTestBench.c:678-760) */
+static unsigned n_malloc, n_free, n_memset; static long live;
+void *H264SwDecMalloc(u32 size) { n_malloc++; live++; return malloc(size); }
+void H264SwDecFree(void *p) { n_free++; live--; free(p); }
+void H264SwDecMemset(void *p, i32 v, u32 n) { n_memset++; memset(p, v, n); }
+void H264SwDecMemcpy(void *d, void *s, u32 n) { memcpy(d, s, n); }
+void H264SwDecTrace(char *s) { (void)s; }
+int main(int argc, char **argv)
+{
+    H264SwDecInst inst; H264SwDecInput in; H264SwDecOutput out;
+    FILE *f = fopen(argv[1], "rb"); static unsigned char buf[1 << 20]; size_t n = fread(buf, 1, sizeof buf - 64, f); fclose(f);
+    if (H264SwDecInit(&inst, 0) != H264SWDEC_OK) return 2;
+    in.pStream = buf; in.dataLen = (u32)n; in.picId = 0; in.intraConcealmentMethod = 0;
+    H264SwDecDecode(inst, &in, &out);            /* parameter sets are stored (host heap) whether or not a GPU is present */
+    H264SwDecRelease(inst);
+    printf("%u %u %u %ld\n", n_malloc, n_free, n_memset, live);
+    return 0;
+}
+"""
+
+
+def test_swdec_memory_hooks_are_honoured(tmp_path):
+    """H264SwDecApi.h:158-173: the embedder's H264SwDecMalloc / Free / Memset replace the library's weak defaults, and
+    every host-side allocation of the decoder goes through them (none leaks)."""
+    import subprocess
+    src = tmp_path / "hooks.c"
+    src.write_text(HOOK_PROBE)
+    exe = tmp_path / "hooks"
+    pkg = os.path.join(ROOT, "broadway_b200")
+    subprocess.run(["gcc", "-O1", "-I" + os.path.join(ROOT, "include"), str(src), "-o", str(exe), "-L" + pkg, "-lh264b200",
+                    "-Wl,-rpath," + pkg], check=True)
+    stream = tmp_path / "s.264"
+    data = cases.make_stream(cases.SMALL[0])
+    stream.write_bytes(data[:data.index(b"\x00\x00\x00\x01", data.index(b"\x00\x00\x00\x01", 8) + 4)])    # SPS + PPS only
+    r = subprocess.run([str(exe), str(stream)], capture_output=True, text=True, check=True)
+    n_malloc, n_free, n_memset, live = map(int, r.stdout.split())
+    assert n_malloc >= 3 and n_memset >= 1            # container, decoder state, parameter sets
+    assert n_malloc == n_free and live == 0
