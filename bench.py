@@ -46,7 +46,7 @@ WORKLOADS = {
     "1080p_ippp_6mbps": (120, 68, {"coded_blk_permille": 20, "p_skip_permille": 600, "part_mix": 0}, "synthetic 1080p Baseline IPPP at ~6 Mbit/s (2% coded blocks, 60% P_Skip, 16x16 partitions); illustration, not a BASELINE.json config"),
 }
 _WL = {"name": "1080p_ippp"}
-DEFAULT_STREAMS, DEFAULT_FRAMES, DISTINCT = 256, 16, 16
+DEFAULT_STREAMS, DEFAULT_FRAMES, DISTINCT = 256, 64, 16
 REFDEC = os.path.join(ROOT, "oracle", "_ref", "refdec")
 
 

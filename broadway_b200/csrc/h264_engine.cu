@@ -56,7 +56,8 @@
 
 #define NBUF 3                 /* input buffers in flight per instance (host-parse; device-parse: look-ahead depth + 2) */
 #define NSCR 4                 /* batch scratch sets in flight per engine */
-#define NPAR 4                 /* Kp launch scratch sets in flight per engine */
+#define NPAR 4                 /* Kp launches in flight per engine: one scratch set and one CUDA stream each, so that they overlap —
+                                  a launch over a quarter of the look-ahead window does not fill the SMs on its own */
 #define STAT_TAIL 128          /* bytes behind every frame: h264b200_picstat_t of the picture (device-parse), copied out with it */
 #define CTRL_HEAD 16           /* int32 words before the progress counters: [0] K3 ticket, [1] K4 ticket */
 
@@ -155,7 +156,7 @@ struct ParseScratch {              /* one Kp launch */
 struct h264b200_engine {
     int device, sm_count;
     uint32_t wf_cap;               /* CTAs per SM the wavefront kernels K3 / K4 are launched with at most (tickets hand out the rows); H264B200_WF_CAP, default 16 */
-    cudaStream_t s_h2d, s_comp, s_d2h, s_parse[2];
+    cudaStream_t s_h2d, s_comp, s_d2h, s_parse[NPAR];
     cudaEvent_t ev_h2d, ev_comp, ev_rep0, ev_rep1, ev_gate;
     std::mutex mu;
     std::vector<Inst *> insts;
@@ -274,7 +275,7 @@ static int launch_parse(h264b200_engine *e, std::vector<PicBuf *> &list)
     const uint32_t n = (uint32_t)list.size();
     const bool retain = (e->flags & H264B200_ENGINE_RETAIN) != 0;
     ParseScratch &ps = e->pscr[e->next_pscr];
-    const int stream = e->next_pscr & 1;
+    const int stream = e->next_pscr;
     e->next_pscr = (e->next_pscr + 1) % NPAR;
     if (ps.used) cudaEventSynchronize(ps.done);
     if (ps.cap < n) {
@@ -550,7 +551,12 @@ static uint32_t advance_locked(h264b200_engine *e, bool force)
             first = false;
         }
     }
-    if (!pl.empty() && (force || head_unparsed || pl.size() >= e->parse_threshold)) {
+    /* a launch over `parse_threshold` pictures (a quarter of the look-ahead of every stream) as soon as that many wait
+     * and one of the NPAR launch slots is free: up to NPAR launches overlap on the device, and the reconstruction
+     * rounds of pictures parsed earlier run beside them */
+    const ParseScratch &nps = e->pscr[e->next_pscr];
+    const bool slot_free = !nps.used || cudaEventQuery(nps.done) == cudaSuccess;
+    if (!pl.empty() && (force || head_unparsed || (pl.size() >= e->parse_threshold && slot_free))) {
         if (launch_parse(e, pl)) {
             for (PicBuf *p : pl) p->inst->slot_flags[p->in.cur_slot] |= 4;
         }
@@ -680,7 +686,7 @@ static void be_inst_destroy(h264_backend_t *be, void *inst)
         for (size_t i = 0; i < e->insts.size(); i++) if (e->insts[i] == in) { e->insts.erase(e->insts.begin() + i); break; }
     }
     set_device(e);
-    cudaStreamSynchronize(e->s_parse[0]); cudaStreamSynchronize(e->s_parse[1]);
+    for (int k = 0; k < NPAR; k++) cudaStreamSynchronize(e->s_parse[k]);
     cudaStreamSynchronize(e->s_comp); cudaStreamSynchronize(e->s_d2h);
     if (!keep) { std::lock_guard<std::mutex> lk(e->mu); e->pool.push_back(in); }
 }
@@ -898,8 +904,7 @@ extern "C" h264b200_engine_t *h264b200EngineCreateEx(int device, uint32_t flags)
     CUDA_TRY(cudaStreamCreateWithFlags(&e->s_h2d, cudaStreamNonBlocking), { delete e; return NULL; });
     CUDA_TRY(cudaStreamCreateWithFlags(&e->s_comp, cudaStreamNonBlocking), { delete e; return NULL; });
     CUDA_TRY(cudaStreamCreateWithFlags(&e->s_d2h, cudaStreamNonBlocking), { delete e; return NULL; });
-    CUDA_TRY(cudaStreamCreateWithFlags(&e->s_parse[0], cudaStreamNonBlocking), { delete e; return NULL; });
-    CUDA_TRY(cudaStreamCreateWithFlags(&e->s_parse[1], cudaStreamNonBlocking), { delete e; return NULL; });
+    for (int k = 0; k < NPAR; k++) CUDA_TRY(cudaStreamCreateWithFlags(&e->s_parse[k], cudaStreamNonBlocking), { delete e; return NULL; });
     CUDA_TRY(cudaEventCreateWithFlags(&e->ev_h2d, cudaEventDisableTiming), { delete e; return NULL; });
     CUDA_TRY(cudaEventCreateWithFlags(&e->ev_comp, cudaEventDisableTiming), { delete e; return NULL; });
     CUDA_TRY(cudaEventCreateWithFlags(&e->ev_gate, cudaEventDisableTiming), { delete e; return NULL; });
@@ -960,7 +965,7 @@ extern "C" void h264b200EngineDestroy(h264b200_engine_t *e)
 {
     if (!e) return;
     set_device(e);
-    cudaStreamSynchronize(e->s_h2d); cudaStreamSynchronize(e->s_parse[0]); cudaStreamSynchronize(e->s_parse[1]);
+    cudaStreamSynchronize(e->s_h2d); for (int k = 0; k < NPAR; k++) cudaStreamSynchronize(e->s_parse[k]);
     cudaStreamSynchronize(e->s_comp); cudaStreamSynchronize(e->s_d2h);
     free_retained(e);
     for (Inst *p : e->pool) inst_free(p);
@@ -984,7 +989,7 @@ extern "C" void h264b200EngineDestroy(h264b200_engine_t *e)
     if (e->d_trace) cudaFree(e->d_trace);
     cudaEventDestroy(e->ev_h2d); cudaEventDestroy(e->ev_comp); cudaEventDestroy(e->ev_rep0); cudaEventDestroy(e->ev_rep1); cudaEventDestroy(e->ev_gate);
     cudaStreamDestroy(e->s_h2d); cudaStreamDestroy(e->s_comp); cudaStreamDestroy(e->s_d2h);
-    cudaStreamDestroy(e->s_parse[0]); cudaStreamDestroy(e->s_parse[1]);
+    for (int k = 0; k < NPAR; k++) cudaStreamDestroy(e->s_parse[k]);
     delete e;
 }
 
@@ -1020,10 +1025,11 @@ extern "C" void h264b200EngineSync(h264b200_engine_t *e)
 {
     if (!e) return;
     set_device(e);
-    cudaError_t a = cudaStreamSynchronize(e->s_h2d), p0 = cudaStreamSynchronize(e->s_parse[0]), p1 = cudaStreamSynchronize(e->s_parse[1]);
+    cudaError_t a = cudaStreamSynchronize(e->s_h2d), p0 = cudaSuccess;
+    for (int k = 0; k < NPAR; k++) { cudaError_t pk = cudaStreamSynchronize(e->s_parse[k]); if (pk != cudaSuccess) p0 = pk; }
     cudaError_t b = cudaStreamSynchronize(e->s_comp), c = cudaStreamSynchronize(e->s_d2h);
-    if (a != cudaSuccess || b != cudaSuccess || c != cudaSuccess || p0 != cudaSuccess || p1 != cudaSuccess)
-        fprintf(stderr, "h264b200: engine sync failed: %s\n", cudaGetErrorString(a != cudaSuccess ? a : p0 != cudaSuccess ? p0 : p1 != cudaSuccess ? p1 : b != cudaSuccess ? b : c));
+    if (a != cudaSuccess || b != cudaSuccess || c != cudaSuccess || p0 != cudaSuccess)
+        fprintf(stderr, "h264b200: engine sync failed: %s\n", cudaGetErrorString(a != cudaSuccess ? a : p0 != cudaSuccess ? p0 : b != cudaSuccess ? b : c));
 }
 
 extern "C" void h264b200EngineStats(h264b200_engine_t *e, h264b200_stats_t *out) { if (e && out) { std::lock_guard<std::mutex> lk(e->mu); *out = e->st; } }
@@ -1058,7 +1064,7 @@ extern "C" u32 h264b200EngineReplay(h264b200_engine_t *e, u32 reps, int time_ker
     for (u32 rep = 0; rep < reps; rep++) {
         /* nothing of this repetition starts before the previous one (or the caller's earlier work) has finished */
         cudaEventRecord(e->ev_gate, e->s_comp);
-        cudaStreamWaitEvent(e->s_parse[0], e->ev_gate, 0); cudaStreamWaitEvent(e->s_parse[1], e->ev_gate, 0);
+        for (int k = 0; k < NPAR; k++) cudaStreamWaitEvent(e->s_parse[k], e->ev_gate, 0);
         for (size_t bi = 0; bi < e->retained.size(); bi++) {
             Retained *r = e->retained[bi];
             cudaEvent_t *tev = nullptr;

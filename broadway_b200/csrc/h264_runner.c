@@ -254,8 +254,10 @@ static void *dev_worker_main(void *arg)
         if (round == 0 && s->buf && s->inited) { memcpy(s->buf, s->src, s->len); memset(s->buf + s->len, 0, 16); }
         if (s->inited) {
             activity += dev_consume(w, s, idx);
-            /* fill the look-ahead at once when the stream starts, then keep it topped up */
-            burst = s->pic_id == 0 ? s->depth : 2;
+            /* a quarter of the look-ahead per round: the first Kp launch goes out after one round of scanning, not after
+             * the whole window has been scanned, and in steady state (one picture per stream reconstructed per round)
+             * the window stays full */
+            burst = s->depth >= 4 ? s->depth / 4 : 1;
             while (burst-- && !s->finished && !s->failed && h264b200PicturesPending(&s->st) < s->depth) {
                 double t0 = now_s();
                 activity += (uint32_t)dev_scan_one(s);
@@ -297,7 +299,7 @@ int h264b200DecodeStreams(h264b200_engine_t *e, const h264b200_stream_t *streams
         /* look-ahead per stream: enough pictures in flight for kernel Kp (thousands), within what the engine can hold */
         const char *wenv = getenv("H264B200_WINDOW");
         depth = wenv && atoi(wenv) > 0 ? (uint32_t)atoi(wenv) : 16;
-        h264b200EngineSetWindow(e, depth, n_streams * ((depth + 1) / 2));
+        h264b200EngineSetWindow(e, depth, n_streams * (depth >= 4 ? depth / 4 : 1));
         depth = h264b200EngineWindow(e);
     }
     /* two groups once every thread has a few streams per group; otherwise one (a round is then one batch).  Batches

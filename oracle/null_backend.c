@@ -17,5 +17,11 @@ static int n_grow(h264_backend_t *be, void *i, h264_pic_input_t *p, uint32_t m) 
 static int n_submit(h264_backend_t *be, void *i, h264_pic_input_t *p) { (void)be; (void)i; (void)p; return 0; }
 static uint8_t *n_frame(h264_backend_t *be, void *i, int s, uint32_t *e) { (void)be; (void)s; if (e) *e = 0; return ((null_inst_t *)i)->frame; }
 static void n_del(h264_backend_t *be) { (void)be; }
+#ifdef NULL_DEVICE_PARSE
+/* device-parse flavour: the host only scans NAL units, parses slice headers and copies the slice payloads into the block */
+static int n_block_grow(h264_backend_t *be, void *i, h264_pic_input_t *p, uint32_t m) { (void)be; (void)i; uint8_t *n = realloc(p->block, m + 4096); if (!n) return -1; p->block = n; p->block_cap = m + 4096; return 0; }
+static h264_backend_t g = { n_create, n_destroy, n_begin, n_grow, n_submit, n_frame, n_del, NULL, NULL, NULL, NULL, n_block_grow, NULL, NULL, NULL, 1 };
+#else
 static h264_backend_t g = { n_create, n_destroy, n_begin, n_grow, n_submit, n_frame, n_del, NULL };
+#endif
 h264_backend_t *h264_default_backend(void) { return &g; }

@@ -49,13 +49,14 @@ json.dump(loss, open(os.path.join(ROOT, "tests", "golden", "loss.json"), "w"), i
 
 # bench.py's parity gate: the first streams of its workload (rank 0), decoded by the reference
 from broadway_b200 import bitstream
-bench = {"width_mbs": 120, "height_mbs": 68, "frames": 16, "streams": []}
+BENCH_FRAMES = 64          # bench.py DEFAULT_FRAMES
+bench = {"width_mbs": 120, "height_mbs": 68, "frames": BENCH_FRAMES, "streams": []}
 for i in range(2):
-    data = bitstream.synth(120, 68, 16, seed=1234 + i)
+    data = bitstream.synth(120, 68, BENCH_FRAMES, seed=1234 + i)
     path = "/tmp/golden_bench_%d.264" % i
     open(path, "wb").write(data)
     md5s, summary = ref_md5(path)
-    assert len(md5s) == 16 and summary["err_mbs"] == 0
+    assert len(md5s) == BENCH_FRAMES and summary["err_mbs"] == 0
     bench["streams"].append({"seed": 1234 + i, "stream_md5": hashlib.md5(data).hexdigest(), "frame_md5": md5s})
     os.remove(path)
     print("bench stream", i, "ok")
