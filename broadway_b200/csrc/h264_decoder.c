@@ -25,11 +25,62 @@
 static h264_decoder_t *DEC(storage_t *s) { return s ? (h264_decoder_t *)s->impl : NULL; }
 
 /* ------------------------------------------------------------ NAL extraction */
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
+/* index of the first i < n - 1 with p[i] == 0 && p[i+1] == 0 — the only place a start code prefix or an emulation
+ * prevention sequence can begin — or n when there is none.  16 bytes per step: the scan of a 1080p slice NAL
+ * (~230 KB, a zero byte every 256 bytes in coefficient data) costs a few microseconds instead of one memchr call per
+ * zero byte. */
+static uint32_t find_zero_pair(const uint8_t *p, uint32_t n)
+{
+    uint32_t i = 0;
+#if defined(__SSE2__)
+    const __m128i z = _mm_setzero_si128();
+    while (i + 17 <= n) {
+        const __m128i a = _mm_loadu_si128((const __m128i *)(p + i)), b = _mm_loadu_si128((const __m128i *)(p + i + 1));
+        const int m = _mm_movemask_epi8(_mm_and_si128(_mm_cmpeq_epi8(a, z), _mm_cmpeq_epi8(b, z)));
+        if (m) return i + (uint32_t)__builtin_ctz((unsigned)m);
+        i += 16;
+    }
+#endif
+    while (i + 1 < n) {
+        const uint8_t *q = (const uint8_t *)memchr(p + i, 0, n - 1 - i);
+        if (!q) break;
+        i = (uint32_t)(q - p);
+        if (p[i + 1] == 0) return i;
+        i++;
+    }
+    return n;
+}
+
+/* Copy src[0..n) to dst without its emulation prevention bytes (00 00 03 -> 00 00); returns the RBSP length or
+ * (uint32_t)-1 on a forbidden sequence (h264bsd_byte_stream.c:192-234 reports the same streams as errors). */
+static uint32_t unescape_copy(uint8_t *dst, const uint8_t *src, uint32_t n)
+{
+    uint32_t r = 0, w = 0;
+    while (r < n) {
+        uint32_t k = find_zero_pair(src + r, n - r);
+        if (k >= n - r) { memmove(dst + w, src + r, n - r); w += n - r; break; }
+        k += 2;                                        /* up to and including the two zero bytes */
+        memmove(dst + w, src + r, k); w += k; r += k;
+        if (r < n && src[r] == 0) return (uint32_t)-1;             /* 00 00 00 inside a NAL unit */
+        if (r < n && src[r] == 3) {
+            if (r + 1 == n || src[r + 1] > 3) return (uint32_t)-1;
+            r++;                                       /* drop the emulation prevention byte */
+        } else if (r < n && src[r] <= 2) return (uint32_t)-1;
+    }
+    return w;
+}
+
 /* Find the NAL unit at the head of buf: Annex-B (00 00 01 / 00 00 00 prefix) or a
- * bare NAL.  Removes emulation prevention bytes IN PLACE (the reference does the
- * same to the caller's buffer, h264bsd_byte_stream.c:192-234).  Returns 0 and sets
+ * bare NAL, and remove its emulation prevention bytes: IN PLACE (the reference does the
+ * same to the caller's buffer, h264bsd_byte_stream.c:192-234), or — when `scratch` is given
+ * (read-only input, h264b200SetReadOnlyInput) — by copying a NAL that contains any into
+ * *scratch, so that the caller's bytes are never written.  Returns 0 and sets
  * nal/nal_len/consumed, or -1. */
-static int extract_nal(uint8_t *buf, uint32_t len, uint8_t **nal, uint32_t *nal_len, uint32_t *consumed)
+typedef struct { uint8_t *p; uint32_t cap; } nal_scratch_t;
+static int extract_nal(uint8_t *buf, uint32_t len, uint8_t **nal, uint32_t *nal_len, uint32_t *consumed, nal_scratch_t *scratch)
 {
     uint32_t start = 0, end = len, trailing = 0, i, zeros;
     int has_epb = 0, invalid = 0;
@@ -45,16 +96,18 @@ static int extract_nal(uint8_t *buf, uint32_t len, uint8_t **nal, uint32_t *nal_
         }
         start = i;
         /* the NAL ends at the next start code prefix or at the end of the buffer; trailing
-         * zero bytes are not part of it (runs of zeros are located with memchr) */
+         * zero bytes are not part of it */
         while (i < len) {
-            const uint8_t *z = (const uint8_t *)memchr(buf + i, 0, len - i);
-            uint32_t j;
-            if (!z) break;
-            i = (uint32_t)(z - buf);
+            uint32_t j, k = find_zero_pair(buf + i, len - i);
+            if (k >= len - i) {                        /* no 00 00 any more: at most one trailing zero byte */
+                if (buf[len - 1] == 0 && len - 1 >= i) { end = len - 1; trailing = 1; }
+                break;
+            }
+            i += k;
             for (j = i; j < len && buf[j] == 0; j++) ;
             zeros = j - i;
             if (j == len) { end = i; trailing = zeros; break; }
-            if (zeros >= 2 && buf[j] == 1) { end = i; trailing = zeros > 3 ? zeros - 3 : 0; break; }
+            if (buf[j] == 1) { end = i; trailing = zeros > 3 ? zeros - 3 : 0; break; }
             if (zeros == 2 && buf[j] == 3) has_epb = 1;
             else if (zeros >= 3) invalid = 1;          /* 00 00 00 xx inside a NAL unit */
             i = j + 1;
@@ -65,27 +118,19 @@ static int extract_nal(uint8_t *buf, uint32_t len, uint8_t **nal, uint32_t *nal_
         *nal = buf; *nal_len = len; *consumed = len; has_epb = 1;
     }
     if (has_epb) {
-        uint8_t *p = *nal, *e = p + *nal_len, *r = p, *w;
-        /* locate the first 00 00 03, then compact the rest byte by byte */
-        while (r < e) {
-            uint8_t *z = (uint8_t *)memchr(r, 0, (size_t)(e - r));
-            if (!z || z + 2 >= e) { r = e; break; }
-            if (z[1] == 0 && z[2] == 3) { r = z; break; }
-            r = z + 1;
-        }
-        if (r < e) {
-            w = r; zeros = 0;
-            while (r < e) {
-                if (zeros == 2 && *r == 3) {
-                    if (r + 1 == e || r[1] > 3) return -1;
-                    r++; zeros = 0; continue;
-                }
-                if (zeros == 2 && *r <= 2) return -1;
-                zeros = *r == 0 ? zeros + 1 : 0;
-                *w++ = *r++;
+        uint8_t *dst = *nal;
+        uint32_t n;
+        if (scratch) {
+            if (scratch->cap < *nal_len) {
+                uint8_t *q = (uint8_t *)h264_malloc((size_t)*nal_len + 4096);
+                if (!q) return -1;
+                h264_free(scratch->p); scratch->p = q; scratch->cap = *nal_len + 4096;
             }
-            *nal_len = (uint32_t)(w - p);
+            dst = scratch->p;
         }
+        n = unescape_copy(dst, *nal, *nal_len);        /* in place: the write position never passes the read position */
+        if (n == (uint32_t)-1) return -1;
+        *nal = dst; *nal_len = n;
     }
     return 0;
 }
@@ -478,7 +523,7 @@ u32 h264bsdDecode(storage_t *pStorage, u8 *byteStrm, u32 len, u32 picId, u32 *re
         nal = (uint8_t *)d->nal_data; nal_len = (uint32_t)d->nal_len;
         *readBytes = d->prev_bytes_consumed;
     } else {
-        if (extract_nal(byteStrm, len, &nal, &nal_len, &consumed)) { *readBytes = consumed; return H264BSD_ERROR; }
+        if (extract_nal(byteStrm, len, &nal, &nal_len, &consumed, d->ro_input ? (nal_scratch_t *)&d->nal_scratch : NULL)) { *readBytes = consumed; return H264BSD_ERROR; }
         *readBytes = consumed;
         d->nal_data = nal; d->nal_len = nal_len;
         d->prev_bytes_consumed = consumed; d->prev_buf_ptr = byteStrm;
@@ -681,6 +726,11 @@ u32 h264b200PicturesPending(storage_t *pStorage)
     h264_decoder_t *d = DEC(pStorage);
     return d && d->be_inst && d->be->inst_pending ? d->be->inst_pending(d->be, d->be_inst) : 0;
 }
+/* The decoder stops editing the caller's buffers: a NAL unit that contains emulation prevention bytes is unescaped
+ * into decoder-owned scratch memory instead of in place (the reference always edits in place,
+ * h264bsd_byte_stream.c:192-234; callers that share one read-only copy of a stream between instances need this). */
+void h264b200SetReadOnlyInput(storage_t *pStorage, u32 on) { h264_decoder_t *d = DEC(pStorage); if (d) d->ro_input = on != 0; }
+
 u32 h264b200DeviceParse(storage_t *pStorage) { h264_decoder_t *d = DEC(pStorage); return d ? (u32)d->device_parse : 0; }
 
 void h264bsdShutdown(storage_t *pStorage)
@@ -691,7 +741,7 @@ void h264bsdShutdown(storage_t *pStorage)
     if (d->be_inst) d->be->inst_destroy(d->be, d->be_inst);
     for (i = 0; i < H264_MAX_SPS; i++) h264_free(d->sps[i]);
     for (i = 0; i < H264_MAX_PPS; i++) { if (d->pps[i]) h264_free((void *)d->pps[i]->fmo.group_id); h264_free(d->pps[i]); }
-    h264_free(d->mbctx); h264_free(d->slice_group_map);
+    h264_free(d->mbctx); h264_free(d->slice_group_map); h264_free(d->nal_scratch.p);
     h264_free(d);
     pStorage->impl = NULL;
 }

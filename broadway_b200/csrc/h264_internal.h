@@ -211,7 +211,9 @@ typedef struct h264_decoder {
              int32_t prev_delta_poc_bottom, prev_delta_poc[2]; } aub;
     int pic_started, valid_slice_in_au, skip_redundant;
     uint8_t *prev_buf_ptr; uint32_t prev_bytes_consumed; int prev_buf_not_finished;
-    const uint8_t *nal_data; size_t nal_len;      /* current RBSP (inside the caller's buffer) */
+    const uint8_t *nal_data; size_t nal_len;      /* current RBSP (inside the caller's buffer, or in nal_scratch) */
+    int ro_input;                                 /* h264b200SetReadOnlyInput: never write to the caller's buffer */
+    struct { uint8_t *p; uint32_t cap; } nal_scratch;   /* read-only input: a NAL with emulation prevention bytes is unescaped here */
     uint8_t cur_nal_type, cur_nal_ref_idc;
     uint8_t pic_nal_type, pic_nal_ref_idc;        /* of the last valid slice */
 

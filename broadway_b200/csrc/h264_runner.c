@@ -24,6 +24,7 @@
 #define _GNU_SOURCE
 #include <pthread.h>
 #include <sched.h>
+#include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
@@ -151,8 +152,6 @@ static void *worker_main(void *arg)
             if (__atomic_load_n(&r->stop, __ATOMIC_ACQUIRE)) return NULL;
             sched_yield();
         }
-        /* private copy (the decoder strips emulation prevention bytes in place), made by the first thread to touch the stream */
-        if (round == 0 && s->buf && s->inited) { memcpy(s->buf, s->src, s->len); memset(s->buf + s->len, 0, 16); }
         /* What the previous round popped was launched a whole round ago.  It is consumed BEFORE the next picture is
          * parsed: the DPB may hand that picture the very frame slot whose host mirror the callback is about to read,
          * and the engine holds a picture back while an output of its slot is unreleased. */
@@ -251,7 +250,6 @@ static void *dev_worker_main(void *arg)
             if (__atomic_load_n(&r->stop, __ATOMIC_ACQUIRE)) return NULL;
             sched_yield();
         }
-        if (round == 0 && s->buf && s->inited) { memcpy(s->buf, s->src, s->len); memset(s->buf + s->len, 0, 16); }
         if (s->inited) {
             activity += dev_consume(w, s, idx);
             /* a quarter of the look-ahead per round: the first Kp launch goes out after one round of scanning, not after
@@ -309,9 +307,12 @@ int h264b200DecodeStreams(h264b200_engine_t *e, const h264b200_stream_t *streams
     for (i = 0; i < n_streams; i++) {
         rstream_t *s = &r.s[i];
         s->len = streams[i].len;
-        s->buf = (uint8_t *)malloc(s->len + 16);            /* private copy: the decoder strips emulation prevention bytes in place */
+        /* decoded straight from the caller's bytes: the instance is told never to write to them (a NAL unit with
+         * emulation prevention bytes is unescaped into decoder-owned memory) */
+        s->buf = (uint8_t *)(uintptr_t)streams[i].data;
         s->src = streams[i].data;
         if (!s->buf || h264b200InitOnEngine(&s->st, 0, e) != HANTRO_OK) { s->failed = 1; rc = -1; continue; }
+        h264b200SetReadOnlyInput(&s->st, 1);
         s->inited = 1; s->depth = depth;
     }
     for (i = 0; i < n_threads; i++) { w[i].r = &r; w[i].tid = i; }
@@ -337,7 +338,7 @@ int h264b200DecodeStreams(h264b200_engine_t *e, const h264b200_stream_t *streams
     for (i = 0; i < n_streams; i++) {
         if (r.s[i].failed) rc = -1;
         if (r.s[i].inited) h264bsdShutdown(&r.s[i].st);
-        free(r.s[i].buf); free(r.s[i].outq);
+        free(r.s[i].outq);
     }
     pthread_mutex_destroy(&r.mu);
     free(r.s); free(w);

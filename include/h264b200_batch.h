@@ -52,6 +52,9 @@ u32  h264b200PictureStatus(storage_t *pStorage, u32 ticket, h264b200_picstat_t *
 u32  h264b200PicturesPending(storage_t *pStorage);
 /* 1 if the instance parses slice data on the device */
 u32  h264b200DeviceParse(storage_t *pStorage);
+/* on != 0: h264bsdDecode never writes to byteStrm (NAL units with emulation prevention bytes are unescaped into
+ * decoder-owned memory instead of in place); h264b200DecodeStreams uses it to decode straight from the caller's streams */
+void h264b200SetReadOnlyInput(storage_t *pStorage, u32 on);
 /* One scheduling step of the engine: (1) if enough queued device-parse pictures have accumulated (or a stream would
  * otherwise stall) launch kernel Kp over all of them; (2) launch ONE round of reconstruction: the oldest queued picture
  * of every instance whose output buffer is free.  Returns the number of pictures reconstructed by this call.

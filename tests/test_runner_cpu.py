@@ -86,3 +86,30 @@ def test_many_repeats_of_one_stream(L, golden):
     md5s, _ = run(L, [cases.make_stream(c)] * 24, threads=5)
     for m in md5s:
         assert m == golden[c[0]]["frame_md5"]
+
+
+EPB_HEAVY = [dict(max_level=2000, qp=0, qp_jitter=0, max_coeffs=4, coded_blk_permille=900),
+             dict(max_level=1000, qp=2, qp_jitter=0, max_coeffs=2, coded_blk_permille=950, slices_per_pic=3),
+             dict(first_idr_ipcm=1, max_level=300, qp=1, qp_jitter=0, max_coeffs=3, coded_blk_permille=800)]
+
+
+@pytest.mark.parametrize("flags", [1, 1 | 8], ids=["host_parse", "device_parse"])
+def test_read_only_input_with_emulation_prevention_bytes(L, flags):
+    """h264b200DecodeStreams decodes straight from the caller's bytes (h264b200SetReadOnlyInput): NAL units that
+    contain emulation prevention bytes (dozens per stream here) are unescaped into decoder-owned memory.  The caller's
+    streams must come back untouched — several instances share one copy — and the frames must equal those of the
+    in-place decode (the oracle CLI, h264bsd_byte_stream.c:192-234 semantics) and of the reference where it is built."""
+    import util
+    from broadway_b200 import bitstream
+    streams = [bitstream.synth(20, 12, 5, seed=99, **kw) for kw in EPB_HEAVY]
+    assert all(s.count(b"\x00\x00\x03") >= 9 for s in streams)
+    shared = [streams[0], streams[1], streams[2], streams[0], streams[0], streams[1]]     # the same bytes objects, concurrently
+    before = [hashlib.md5(s).hexdigest() for s in streams]
+    md5s, _ = run(L, shared, threads=3, flags=flags)
+    assert [hashlib.md5(s).hexdigest() for s in streams] == before, "the runner wrote to the caller's streams"
+    want = [util.oracle_md5(s)[0] for s in streams]
+    assert md5s == [want[0], want[1], want[2], want[0], want[0], want[1]]
+    for s, w in zip(streams, want):
+        ref = util.reference_md5(s)
+        if ref is not None:
+            assert ref[0] == w
