@@ -52,6 +52,8 @@
 #endif
 
 #include "kp_types.h"
+#include <stddef.h>
+static_assert(offsetof(KpStage, cc) == offsetof(KpStage, lc) + 40, "lc and cc form one 64-byte TotalCoeff grid (KpTables.step_desc)");
 
 #ifdef __CUDACC__
 typedef uint4 KpU4;
@@ -61,7 +63,10 @@ typedef struct { uint32_t x, y, z, w; } KpU4;
 
 /* lane-0 state of the slice being parsed */
 typedef struct {
-    const uint32_t *words; uint32_t n_words, wpos; uint64_t cache; int bits;
+    /* bit reader: a window of three aligned 32-bit words (big endian in registers): w0 holds the current position,
+     * `sh` bits of it are consumed; w1 follows; w2 is already on its way from memory when w1 becomes w0, so the load
+     * latency never sits on the decoding chain.  32 valid bits are always available to kp_peek32 (one funnel shift). */
+    const uint32_t *words; uint32_t n_words, wpos; uint32_t w0, w1, w2, sh;
     uint32_t rbsp_bits, payload_bits;
     const KpTables *T; KpStage *st;
     const h264b200_slice_t *sl;
@@ -75,33 +80,37 @@ typedef struct {
 } KpS;
 
 /* ------------------------------------------------------------------ bits */
-KP_FN void kp_refill(KpS &s)     /* requires bits <= 32 */
+#ifdef __CUDACC__
+#define KP_FUNNEL(hi, lo, n) __funnelshift_l((lo), (hi), (n))          /* upper 32 bits of hi:lo << (n & 31) */
+#else
+#define KP_FUNNEL(hi, lo, n) (((n) & 31) ? ((hi) << ((n) & 31)) | ((lo) >> (32 - ((n) & 31))) : (hi))
+#endif
+KP_FN uint32_t kp_word(const KpS &s, uint32_t i) { return i < s.n_words ? KP_BSWAP(s.words[i]) : 0u; }   /* zeros behind the RBSP, like the host reader */
+KP_FN void kp_seek(KpS &s, uint32_t bit)
 {
-    uint32_t w = 0;
-    if (s.wpos < s.n_words) w = KP_BSWAP(s.words[s.wpos]);
-    s.wpos++;
-    s.cache |= (uint64_t)w << (32 - s.bits);
-    s.bits += 32;
+    const uint32_t wi = bit >> 5;
+    s.w0 = kp_word(s, wi); s.w1 = kp_word(s, wi + 1); s.w2 = kp_word(s, wi + 2);
+    s.wpos = wi + 3; s.sh = bit & 31;
 }
 KP_FN void kp_bits_init(KpS &s, const uint8_t *rbsp, uint32_t len, uint32_t bit_off, uint32_t payload_bits)
 {
     s.words = (const uint32_t *)rbsp; s.n_words = (len + 3) >> 2;     /* the block pads every RBSP with zeros to 16 bytes */
-    s.wpos = bit_off >> 5; s.cache = 0; s.bits = 0;
     s.rbsp_bits = len * 8; s.payload_bits = payload_bits;
-    kp_refill(s);
-    s.cache <<= (bit_off & 31); s.bits -= (int)(bit_off & 31);
+    kp_seek(s, bit_off);
 }
-KP_FN uint32_t kp_pos(const KpS &s) { return s.wpos * 32u - (uint32_t)s.bits; }
-KP_FN void kp_need32(KpS &s) { if (s.bits < 32) kp_refill(s); }
-KP_FN uint32_t kp_peek(KpS &s, int n) { if (s.bits < n) kp_refill(s); return (uint32_t)(s.cache >> (64 - n)); }   /* 1 <= n <= 32 */
-KP_FN void kp_skip(KpS &s, int n) { s.cache <<= n; s.bits -= n; }
+KP_FN uint32_t kp_pos(const KpS &s) { return (s.wpos - 3) * 32u + s.sh; }
+KP_FN uint32_t kp_peek32(const KpS &s) { return KP_FUNNEL(s.w0, s.w1, s.sh); }
+KP_FN uint32_t kp_peek(const KpS &s, int n) { return kp_peek32(s) >> (32 - n); }   /* 1 <= n <= 32 */
+KP_FN void kp_skip(KpS &s, int n)                                      /* 0 <= n <= 32 */
+{
+    s.sh += (uint32_t)n;
+    if (s.sh >= 32) { s.sh -= 32; s.w0 = s.w1; s.w1 = s.w2; s.w2 = kp_word(s, s.wpos); s.wpos++; }
+}
 KP_FN uint32_t kp_get(KpS &s, int n) { uint32_t v; if (n == 0) return 0; v = kp_peek(s, n); kp_skip(s, n); return v; }
-KP_FN uint32_t kp_get1(KpS &s) { uint32_t v; if (s.bits < 1) kp_refill(s); v = (uint32_t)(s.cache >> 63); s.cache <<= 1; s.bits--; return v; }
+KP_FN uint32_t kp_get1(KpS &s) { const uint32_t v = kp_peek32(s) >> 31; kp_skip(s, 1); return v; }
 KP_FN uint32_t kp_ue(KpS &s)     /* 0xffffffff: malformed (h264_bits.h br_ue) */
 {
-    uint32_t v; int lz;
-    kp_need32(s);
-    v = (uint32_t)(s.cache >> 32);
+    uint32_t v = kp_peek32(s); int lz;
     if (v & 0x80000000u) { kp_skip(s, 1); return 0; }
     if (v == 0) { kp_skip(s, 32); return 0xffffffffu; }
     lz = KP_CLZ(v);
@@ -120,27 +129,26 @@ KP_FN int kp_more_data(const KpS &s) { return kp_pos(s) < s.payload_bits; }
 KP_FN int kp_overrun(const KpS &s) { return kp_pos(s) > s.rbsp_bits; }
 
 /* ------------------------------------------------------------------ CAVLC block (h264_cavlc_inl.h) */
-/* Levels go to out[scan[i]]; `out` is all zero on entry.  Returns TotalCoeff or -1. */
+/* One residual block whose coeff_token is not the single bit of an empty block.  Levels go to out[scan[i]]; `out` is
+ * all zero on entry.  Returns TotalCoeff or -1. */
 KP_HOT int kp_cavlc_block_full(KpS &s, int nc, int max_coeff, int16_t *out, const uint8_t *scan)
 {
     const KpTables *T = s.T;
     int16_t *level = s.st->lvl;
     int tc, t1, i, sl, zeros_left, pos;
-    uint32_t v;
+    uint32_t v = kp_peek32(s);
 
-    v = (uint32_t)(s.cache >> 32);                               /* the caller made sure of 32 valid bits */
     if (nc < 0) {
-        const uint8_t *e = T->ct_cdc[v >> 24];
-        if (!e[0]) return -1;
-        kp_skip(s, e[0]); tc = e[1]; t1 = e[2];
+        const uint32_t e = *(const uint32_t *)T->ct_cdc[v >> 24];
+        if (!(e & 0xff)) return -1;
+        kp_skip(s, (int)(e & 0xff)); tc = (int)((e >> 8) & 0xff); t1 = (int)((e >> 16) & 0xff);
     } else if (nc < 8) {
-        int lz; const uint8_t *e;
-        if (nc < 2 && (v >> 31)) { kp_skip(s, 1); return 0; }
+        int lz; uint32_t e;
         if (v < 0x10000u) return -1;
         lz = KP_CLZ(v);
-        e = T->ct[(0xaa50 >> (2 * nc)) & 3][lz * 8 + ((v >> (28 - lz)) & 7)];
-        if (!e[0]) return -1;
-        kp_skip(s, e[0]); tc = e[1]; t1 = e[2];
+        e = *(const uint32_t *)T->ct[(0xaa50 >> (2 * nc)) & 3][lz * 8 + ((v >> (28 - lz)) & 7)];
+        if (!(e & 0xff)) return -1;
+        kp_skip(s, (int)(e & 0xff)); tc = (int)((e >> 8) & 0xff); t1 = (int)((e >> 16) & 0xff);
     } else {
         v >>= 26; kp_skip(s, 6);
         if (v == 3) { tc = 0; t1 = 0; }
@@ -151,21 +159,20 @@ KP_HOT int kp_cavlc_block_full(KpS &s, int nc, int max_coeff, int16_t *out, cons
 
     sl = (tc > 10 && t1 < 3) ? 1 : 0;
     {
-        const uint32_t sg = (uint32_t)(s.cache >> 61);           /* at least 16 valid bits are left here */
+        const uint32_t sg = kp_peek32(s) >> 29;                  /* the signs of up to three trailing ones */
         level[0] = (int16_t)(1 - (int)((sg >> 1) & 2)); level[1] = (int16_t)(1 - (int)(sg & 2)); level[2] = (int16_t)(1 - (int)((sg << 1) & 2));
         kp_skip(s, t1);
     }
 KP_NOUNROLL
     for (i = t1; i < tc; i++) {
         int lv;
-        const int8_t *q;
-        kp_need32(s);
-        v = (uint32_t)(s.cache >> 32);
-        q = T->lvl[sl][v >> 24];
-        if (q[1] && i != t1) { level[i] = q[0]; kp_skip(s, q[1]); sl = q[2]; continue; }
-        if (q[1]) {
-            lv = q[0];
-            kp_skip(s, q[1]);
+        uint32_t q;                                              /* {level, bits, next suffixLength} */
+        v = kp_peek32(s);
+        q = *(const uint32_t *)T->lvl[sl][v >> 24];
+        if ((q & 0xff00u) && i != t1) { level[i] = (int16_t)(int8_t)q; kp_skip(s, (int)((q >> 8) & 0xff)); sl = (int)((q >> 16) & 0xff); continue; }
+        if (q & 0xff00u) {
+            lv = (int8_t)q;
+            kp_skip(s, (int)((q >> 8) & 0xff));
             if (t1 < 3) lv += lv > 0 ? 1 : -1;
         } else {
             int prefix, code;
@@ -188,8 +195,9 @@ KP_NOUNROLL
 
     if (tc < max_coeff) {
         const uint8_t *e = nc < 0 ? T->tz_cdc[tc - 1][kp_peek(s, 3)] : T->tz[tc - 1][kp_peek(s, 9)];
-        if (!e[0]) return -1;
-        kp_skip(s, e[0]); zeros_left = e[1];
+        const uint32_t ev = *(const uint16_t *)e;
+        if (!(ev & 0xff)) return -1;
+        kp_skip(s, (int)(ev & 0xff)); zeros_left = (int)(ev >> 8);
         if (zeros_left + tc > max_coeff) return -1;
     } else zeros_left = 0;
 
@@ -199,13 +207,13 @@ KP_NOUNROLL
         int run;
         out[scan[pos]] = level[i];
         {
-            const uint8_t *e = T->rb[(zeros_left < 7 ? zeros_left : 7) - 1][kp_peek(s, 3)];
-            if (e[0]) { kp_skip(s, e[0]); run = e[1]; }
+            const uint32_t pk = kp_peek(s, 11);
+            const uint32_t ev = *(const uint16_t *)T->rb[(zeros_left < 7 ? zeros_left : 7) - 1][pk >> 8];
+            if (ev & 0xff) { kp_skip(s, (int)(ev & 0xff)); run = (int)(ev >> 8); }
             else {
                 int lz;
-                v = kp_peek(s, 11);
-                if (!v) return -1;
-                lz = KP_CLZ(v) - 21;
+                if (!pk) return -1;
+                lz = KP_CLZ(pk) - 21;
                 run = lz + 4; kp_skip(s, lz + 1);
             }
         }
@@ -264,60 +272,62 @@ KP_FN int kp_nc_avg(int a, int b)
 }
 
 /* residual( ) of 7.3.5.3 as ONE loop with ONE call of the block decoder (code size: the kernel has to live in the
- * instruction cache): step 0 = Intra16x16 DC, 1..16 = luma4x4BlkIdx 0..15, 17/18 = chroma DC Cb/Cr, 19..26 = chroma AC.
- * Slot order and masks as include/h264b200_records.h says.  Returns 0 / -1. */
+ * instruction cache), over exactly the blocks the syntax holds: bit `step` of `todo` — step 0 = Intra16x16 DC, 1..16 =
+ * luma4x4BlkIdx 0..15 (set by coded_block_pattern per 8x8 quadrant), 17/18 = chroma DC Cb/Cr, 19..26 = chroma AC.  What a
+ * step needs (its cell in the TotalCoeff grids, the distance to the cell above, its kind, its bit in resid_mask) is one
+ * word of KpTables.step_desc.  Slot order and masks as include/h264b200_records.h says.  Returns 0 / -1. */
+#define KP_SD(grid_idx, up, kind, bit) ((uint32_t)(grid_idx) | ((uint32_t)(up) << 8) | ((uint32_t)(kind) << 12) | ((uint32_t)(bit) << 16))
 KP_HOT int kp_parse_residual(KpS &s, int cbp, int i16)
 {
     KpStage *st = s.st;
     h264b200_mb_t *r = &st->rec;
-    const uint8_t *zz = s.T->zigzag;
-    uint32_t slot = 0, mask = 0, nz = 0;
-    int dc_nz = 0, cdc = 0;                                       /* cdc: bit 0 / 1: the Cb / Cr DC block has coefficients */
-    const int last = (cbp & 0x30) ? 27 : 17;
+    const KpTables *T = s.T;
+    uint32_t slot = 0, mask = 0, nz = 0, cdc = 0;                 /* cdc: bit 0 / 1: the Cb / Cr DC block has coefficients */
+    int dc_nz = 0;
+    uint32_t todo = ((uint32_t)T->cbp_luma[cbp & 15] << 1) | (uint32_t)i16;
+    if (cbp & 0x30) todo |= (cbp & 0x20) ? 0x7fe0000u : 0x60000u;
     r->coef_offset = s.coef_used;
 KP_NOUNROLL
-    for (int step = i16 ? 0 : 1; step < last; step++) {
-        int nc, maxc, tc;
-        uint8_t *g;                                               /* where TotalCoeff of this block goes */
+    while (todo) {
+        const int step = KP_CTZ(todo);
+        const uint32_t dsc = T->step_desc[step];
+        const int kind = (int)((dsc >> 12) & 3);
+        uint8_t *g = st->lc + (dsc & 0xff);                        /* lc and cc are one 64-byte grid */
+        int nc, tc, maxc;
         int16_t *out = st->slots + slot * 16;
-        const uint8_t *scan = zz + i16;
-        maxc = 16 - i16;
-        if (step < 17) {
-            const int blk = step ? step - 1 : 0;
-            if (step && !((cbp >> (blk >> 2)) & 1)) {             /* 8x8 quadrant without coefficients */
-                if (dc_nz) { mask |= 15u << blk; slot += 4; }     /* four all-zero slots (staging is zero) */
-                step += 3;
-                continue;
-            }
-            g = st->lc + s.T->lc_idx[blk];
-            nc = kp_nc_avg(g[-1], g[-8]);
-            if (!step) { maxc = 16; scan = zz; g = &st->lvl_dummy; }
-        } else if (step < 19) { nc = -1; maxc = 4; out += 4 * (step - 17); scan = s.T->ident4; g = &st->lvl_dummy; }
+        const uint8_t *scan = T->zigzag + 1;
+        todo &= todo - 1;
+        if (kind == 2) { nc = -1; maxc = 4; scan = T->ident4; out += 4 * (step - 17); }
         else {
-            const int pl = (step - 19) >> 2, k = (step - 19) & 3;
-            if (!(cbp & 0x20)) {                                  /* DC only: a slot per block of a plane whose DC is coded */
-                if ((cdc >> pl) & 1) { mask |= 1u << (step - 3); slot++; }
-                continue;
-            }
-            g = st->cc[pl] + 5 + (k & 1) + 4 * (k >> 1);
-            nc = kp_nc_avg(g[-1], g[-4]); maxc = 15; scan = zz + 1;
+            nc = kp_nc_avg(g[-1], *(g - ((dsc >> 8) & 15)));
+            maxc = 15;
+            if (kind == 0) { maxc = 16; scan = T->zigzag; }
+            else if (kind == 1) { maxc = 16 - i16; scan = T->zigzag + i16; if (dc_nz) out = st->slots + step * 16; }   /* slot 1 + luma4x4BlkIdx */
         }
         /* two blocks out of three are empty, and with sparse neighbours that is the single bit '1' */
-        kp_need32(s);
-        if ((unsigned)nc < 2u && (int64_t)s.cache < 0) { kp_skip(s, 1); tc = 0; }
+        if ((unsigned)nc < 2u && (int32_t)kp_peek32(s) < 0) { kp_skip(s, 1); tc = 0; }
         else {
             tc = kp_cavlc_block_full(s, nc, maxc, out, scan);
             if (tc < 0) return -1;
-            *g = (uint8_t)tc;
         }
-        if (step == 0) { if (tc) { dc_nz = 1; mask |= H264B200_RESID_LUMA_DC; slot++; } }
-        else if (step < 17) {
-            if (tc) { nz |= 1u << (step - 1); mask |= 1u << (step - 1); slot++; }
-            else if (dc_nz) { mask |= 1u << (step - 1); slot++; }
-        } else if (step < 19) {
-            if (tc) cdc |= 1 << (step - 17);
-            if (step == 18 && cdc) { mask |= H264B200_RESID_CHROMA_DC; slot++; }
-        } else if (tc || ((cdc >> ((step - 19) >> 2)) & 1)) { mask |= 1u << (step - 3); slot++; }
+        {
+            const uint32_t bit = 1u << ((dsc >> 16) & 31);
+            if (kind == 1) {
+                if (tc) { nz |= bit; *g = (uint8_t)tc; if (!dc_nz) { mask |= bit; slot++; } }
+            } else if (kind == 3) {
+                if (tc) *g = (uint8_t)tc;
+                if (tc || ((cdc >> ((step - 19) >> 2)) & 1)) { mask |= bit; slot++; }
+            } else if (kind == 2) {
+                if (tc) cdc |= 1u << (step - 17);
+                if (step == 18 && cdc) {
+                    mask |= H264B200_RESID_CHROMA_DC; slot++;
+                    if (!(cbp & 0x20)) {                           /* DC only: an all-zero slot per block of a plane whose DC is coded */
+                        if (cdc & 1) { mask |= 0xfu << 16; slot += 4; }
+                        if (cdc & 2) { mask |= 0xfu << 20; slot += 4; }
+                    }
+                }
+            } else if (tc) { dc_nz = 1; mask |= H264B200_RESID_LUMA_DC | 0xffffu; slot = 17; }   /* every luma block gets a slot (staging is zero) */
+        }
     }
     r->resid_mask = mask; r->nz_mask = (uint16_t)nz;
     s.n_slots = slot;
@@ -544,12 +554,7 @@ KP_FN int kp_parse_mb(KpS &s)
             r->coef_offset = s.coef_used;
             s.ipcm_byte = (int32_t)byte_pos;                       /* the warp copies the samples when the macroblock is stored */
             s.n_slots = 12;
-            {   /* reposition behind the samples */
-                const uint32_t np = byte_pos + 384;
-                s.wpos = np >> 2; s.cache = 0; s.bits = 0;
-                kp_refill(s);
-                s.cache <<= 8 * (np & 3); s.bits -= (int)(8 * (np & 3));
-            }
+            kp_seek(s, (byte_pos + 384) * 8);                     /* reposition behind the samples */
             r->nz_mask = 0xffff;                                   /* TotalCoeff 16 everywhere: kp_stage_out */
             kp_set_qp_fields(s, r);
             r->qp_dbk = 0;                                         /* h264bsd_macroblock_layer.c:1003 */
