@@ -155,6 +155,7 @@ struct ParseScratch {              /* one Kp launch */
 
 struct h264b200_engine {
     int device, sm_count;
+    int kp_on_comp;                /* H264B200_KP_ON_COMP=1: Kp launches go to the reconstruction stream (serialised with K1..K4) instead of overlapping them */
     uint32_t wf_cap;               /* CTAs per SM the wavefront kernels K3 / K4 are launched with at most (tickets hand out the rows); H264B200_WF_CAP, default 16 */
     cudaStream_t s_h2d, s_comp, s_d2h, s_parse[NPAR];
     cudaEvent_t ev_h2d, ev_comp, ev_rep0, ev_rep1, ev_gate;
@@ -275,7 +276,7 @@ static int launch_parse(h264b200_engine *e, std::vector<PicBuf *> &list)
     const uint32_t n = (uint32_t)list.size();
     const bool retain = (e->flags & H264B200_ENGINE_RETAIN) != 0;
     ParseScratch &ps = e->pscr[e->next_pscr];
-    const int stream = e->next_pscr;
+    const int stream = e->kp_on_comp ? -1 : e->next_pscr;
     e->next_pscr = (e->next_pscr + 1) % NPAR;
     if (ps.used) cudaEventSynchronize(ps.done);
     if (ps.cap < n) {
@@ -326,7 +327,7 @@ static int launch_parse(h264b200_engine *e, std::vector<PicBuf *> &list)
         p->parse_seq = e->parse_seq;
     }
     e->st.h2d_bytes += in_bytes;
-    cudaStream_t s = e->s_parse[stream];
+    cudaStream_t s = stream < 0 ? e->s_comp : e->s_parse[stream];
     cudaEventRecord(e->ev_h2d, e->s_h2d);
     cudaStreamWaitEvent(s, e->ev_h2d, 0);
     cudaMemcpyAsync(d_pics, ps.h_pics, n * sizeof(KpPic), cudaMemcpyHostToDevice, s);
@@ -900,6 +901,7 @@ extern "C" h264b200_engine_t *h264b200EngineCreateEx(int device, uint32_t flags)
     CUDA_TRY(cudaGetDeviceProperties(&p, device), { delete e; return NULL; });
     e->sm_count = p.multiProcessorCount;
     e->wf_cap = 16;
+    { const char *c = getenv("H264B200_KP_ON_COMP"); e->kp_on_comp = c && atoi(c) > 0; }
     { const char *c = getenv("H264B200_WF_CAP"); if (c && atoi(c) > 0 && atoi(c) <= 64) e->wf_cap = (uint32_t)atoi(c); }
     CUDA_TRY(cudaStreamCreateWithFlags(&e->s_h2d, cudaStreamNonBlocking), { delete e; return NULL; });
     CUDA_TRY(cudaStreamCreateWithFlags(&e->s_comp, cudaStreamNonBlocking), { delete e; return NULL; });
@@ -1076,7 +1078,7 @@ extern "C" u32 h264b200EngineReplay(h264b200_engine_t *e, u32 reps, int time_ker
                 tev = &e->tev[base];
             }
             if (r->kind == 1) {
-                cudaStream_t s = e->s_parse[r->stream];
+                cudaStream_t s = r->stream < 0 ? e->s_comp : e->s_parse[r->stream];
                 if (r->wait_round >= 0) cudaStreamWaitEvent(s, e->retained[(size_t)r->wait_round]->ev, 0);
                 cudaMemsetAsync(r->kp.ticket, 0, 64, s);
                 if (tev) cudaEventRecord(tev[0], s);

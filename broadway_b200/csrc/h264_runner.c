@@ -49,6 +49,7 @@ typedef struct {
     /* device-parse pipeline: outputs popped while scanning ahead, oldest first */
     pending_t *outq; u32 outq_cap, outq_head, outq_n;
     u32 depth;                  /* look-ahead this stream may use */
+    u32 chunk;                  /* pictures scanned per round at most (= pictures per stream in a Kp launch) */
 } rstream_t;
 
 typedef struct runner runner_t;
@@ -255,7 +256,7 @@ static void *dev_worker_main(void *arg)
             /* a quarter of the look-ahead per round: the first Kp launch goes out after one round of scanning, not after
              * the whole window has been scanned, and in steady state (one picture per stream reconstructed per round)
              * the window stays full */
-            burst = s->depth >= 4 ? s->depth / 4 : 1;
+            burst = s->chunk;
             while (burst-- && !s->finished && !s->failed && h264b200PicturesPending(&s->st) < s->depth) {
                 double t0 = now_s();
                 activity += (uint32_t)dev_scan_one(s);
@@ -282,7 +283,7 @@ static void *dev_worker_main(void *arg)
 int h264b200DecodeStreams(h264b200_engine_t *e, const h264b200_stream_t *streams, uint32_t n_streams,
                           uint32_t n_threads, h264b200_picture_cb cb, void *user, h264b200_run_stats_t *out)
 {
-    runner_t r; worker_t *w; uint32_t i, depth = 1; double t0 = now_s(); int rc = 0, dev;
+    runner_t r; worker_t *w; uint32_t i, depth = 1, chunk = 1; double t0 = now_s(); int rc = 0, dev;
     if (!e || !streams || !n_streams) return -1;
     memset(&r, 0, sizeof r);
     if (!n_threads) { long n = sysconf(_SC_NPROCESSORS_ONLN); n_threads = n > 0 ? (uint32_t)n : 1; }
@@ -297,7 +298,12 @@ int h264b200DecodeStreams(h264b200_engine_t *e, const h264b200_stream_t *streams
         /* look-ahead per stream: enough pictures in flight for kernel Kp (thousands), within what the engine can hold */
         const char *wenv = getenv("H264B200_WINDOW");
         depth = wenv && atoi(wenv) > 0 ? (uint32_t)atoi(wenv) : 16;
-        h264b200EngineSetWindow(e, depth, n_streams * (depth >= 4 ? depth / 4 : 1));
+        {   /* pictures per stream and Kp launch: a quarter of the window unless H264B200_KP_CHUNK says otherwise */
+            const char *cenv = getenv("H264B200_KP_CHUNK");
+            chunk = cenv && atoi(cenv) > 0 ? (uint32_t)atoi(cenv) : (depth >= 4 ? depth / 4 : 1);
+            if (chunk > depth) chunk = depth;
+        }
+        h264b200EngineSetWindow(e, depth, n_streams * chunk);
         depth = h264b200EngineWindow(e);
     }
     /* two groups once every thread has a few streams per group; otherwise one (a round is then one batch).  Batches
@@ -313,7 +319,7 @@ int h264b200DecodeStreams(h264b200_engine_t *e, const h264b200_stream_t *streams
         s->src = streams[i].data;
         if (!s->buf || h264b200InitOnEngine(&s->st, 0, e) != HANTRO_OK) { s->failed = 1; rc = -1; continue; }
         h264b200SetReadOnlyInput(&s->st, 1);
-        s->inited = 1; s->depth = depth;
+        s->inited = 1; s->depth = depth; s->chunk = chunk;
     }
     for (i = 0; i < n_threads; i++) { w[i].r = &r; w[i].tid = i; }
     for (i = 1; i < n_threads; i++) pthread_create(&w[i].th, NULL, dev ? dev_worker_main : worker_main, &w[i]);
