@@ -40,6 +40,7 @@ WORKLOADS = {
     "1080p_ippp": (120, 68, {}, "synthetic 1080p Baseline IPPP, random MVs incl. quarter-pel, ~30% coded blocks, deblocking on (BASELINE.json configs[2]; configs[1] tree.mp4 absent)"),
     "1080p_intra": (120, 68, {"intra_only": 1}, "synthetic 1080p intra-only (I16x16/I4x4 mix) stressing the intra and deblock wavefronts (BASELINE.json configs[3])"),
     "4k_ippp": (240, 135, {"level_idc": 51}, "synthetic 4K (3840x2160) Baseline IPPP multi-stream (BASELINE.json configs[4])"),
+    "4k_gop": (240, 135, {"level_idc": 51, "idr_period": 4}, "synthetic 4K (3840x2160) Baseline, IDR every 4 pictures, IDR-bounded GOP segments sharded over the GPUs (BASELINE.json configs[4])"),
     # not BASELINE.json configurations: the same 1080p IPPP structure at streaming bitrates, to show how the host-parse
     # bound of e2e moves with the bitrate; ~54 Mbit/s at 30 frames/s for the default workload
     "1080p_ippp_17mbps": (120, 68, {"coded_blk_permille": 40, "p_skip_permille": 400}, "synthetic 1080p Baseline IPPP at ~17 Mbit/s (4% coded blocks, 40% P_Skip); illustration, not a BASELINE.json config"),
@@ -239,10 +240,19 @@ def own_arm(args, rank, local_rank, world):
             check = {"streams": n_chk, "pictures": n_chk * args.frames, "against": "reference golden MD5 (tests/golden/bench_streams.json)", "md5_exact": True}
             log("[rank 0] parity gate: %d pictures MD5-exact vs the reference" % check["pictures"])
 
-    # ---- end-to-end leg: host Annex-B -> host I420 frames through the C ABI
+    # ---- end-to-end leg: host Annex-B -> host I420 frames through the C ABI.  The K timed steps are ONE streaming call:
+    # every stream is its 64-picture step repeated K times back to back (each repetition starts with its parameter sets
+    # and an IDR picture, so the concatenation is a valid stream that decodes to K times the same pictures), i.e. the
+    # decoder sees 256 streams of K x 64 pictures and its pipeline (host scan -> Kp -> K1..K4 -> copy-out) is filled and
+    # drained once per timed region, not once per step — a per-step call would measure the 0.3 s pipeline latency
+    # (one picture is ~0.29 s of serial parsing on one warp) K times over.
+    def repeated(k):
+        cache = {}
+        return [cache.setdefault(id(b), b * k) for b in streams]
     eng = capi.Engine(local_rank, capi.ENGINE_BATCHED | pflag)
-    for _ in range(0 if args.skip_e2e else args.warmup):
-        eng.decode_streams(streams, threads)
+    if not args.skip_e2e and args.warmup:
+        eng.decode_streams(repeated(args.warmup), threads)
+    timed = repeated(args.steps)
     barrier()
     s0 = eng.stats()
     sampler = ClockSampler(local_rank)
@@ -250,15 +260,16 @@ def own_arm(args, rank, local_rank, world):
         sampler.start()
     t0 = time.perf_counter()
     parse_s = wait_s = 0.0
-    for _ in range(0 if args.skip_e2e else args.steps):
-        rs = eng.decode_streams(streams, threads)
-        assert rs.pictures == frames_per_step and rs.err_mbs == 0, (rs.pictures, rs.err_mbs)
+    if not args.skip_e2e:
+        rs = eng.decode_streams(timed, threads)
+        assert rs.pictures == frames_per_step * args.steps and rs.err_mbs == 0, (rs.pictures, rs.err_mbs)
         parse_s += rs.parse_seconds
         wait_s += rs.wait_seconds
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     s1 = eng.stats()
     eng.close()
+    del timed
     e2e_fps = world * frames_per_step * args.steps / e2e_s
     h2d = (s1["h2d_bytes"] - s0["h2d_bytes"]) // args.steps
     d2h = (s1["d2h_bytes"] - s0["d2h_bytes"]) // args.steps
@@ -332,12 +343,124 @@ def own_arm(args, rank, local_rank, world):
                        "frames_per_step_per_gpu": frames_per_step, "parser_threads_per_gpu": threads, "host_cores": cores, "slice_data_parse": args.parse,
                        "l2": "inputs larger than L2 (per step: %.0f MB of frame pools + records per GPU)" % (args.streams * 2 * WORKLOADS[args.workload][0] * WORKLOADS[args.workload][1] * 384 / 1e6 + h2d / 1e6)},
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": 1000.0 * e2e_s / args.steps, "timing": "wall clock between barrier+synchronize pairs, max over ranks",
+                    "ms_per_step": 1000.0 * e2e_s / args.steps, "timing": "wall clock between barrier+synchronize pairs around ONE streaming call over the K steps (each stream = its step repeated K times), max over ranks",
                     "host_parse_core_seconds_per_step": parse_s / args.steps, "host_wait_seconds_per_step": wait_s / args.steps,
                     "kernel_launches": launches_e2e},
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
             "parity": check, "device_error_flags": err,
         }))
+    if dist:
+        dist.destroy_process_group()
+
+
+
+# ----------------------------------------------------------------------------- GOP-sharded arm (BASELINE configs[4])
+GOP_DISTINCT, GOP_FRAMES, GOP_REPLICAS = 2, 128, 4          # 2 distinct 4K streams x 128 pictures (32 GOPs of 4), each 4 times: 256 units
+
+
+def gop_streams():
+    from concurrent.futures import ThreadPoolExecutor
+    from broadway_b200 import bitstream
+    w, h, kw, _ = WORKLOADS["4k_gop"]
+    with ThreadPoolExecutor(max_workers=GOP_DISTINCT) as ex:
+        return list(ex.map(lambda i: bitstream.synth(w, h, GOP_FRAMES, seed=4321 + i, **kw), range(GOP_DISTINCT)))
+
+
+def gop_arm(args, rank, local_rank, world):
+    """STRONG scaling: a fixed set of 4K streams is cut at its IDR access units (h264b200SplitGops), the segments are
+    assigned to the ranks by size (broadway_b200/shard.py), every rank decodes its segments as independent streams on
+    its own GPU, the per-picture digests are gathered (all_gather_object: the only cross-rank traffic) and compared
+    with the committed digests of the SEQUENTIAL decode of the whole streams by the unmodified reference
+    (tests/golden/gop_4k.json).  The timed region is the decode alone (host Annex-B segments -> host I420 frames)."""
+    import hashlib
+    import torch
+    from broadway_b200 import capi, shard
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    capi.require_gpu()
+    cores = len(os.sched_getaffinity(0))
+    threads = args.threads or max(1, cores // world)
+    base = gop_streams()
+    segs_of = [capi.split_gops(b) for b in base]
+    units, owner = [], []
+    for rep in range(GOP_REPLICAS):
+        for i, segs in enumerate(segs_of):
+            units += segs
+            owner += [(i, k) for k in range(len(segs))]
+    plan = shard.assign([len(u) for u in units], world)
+    mine = [units[i] for i in plan[rank]]
+    my_pics = sum(GOP_FRAMES // len(segs_of[owner[i][0]]) for i in plan[rank])
+    total_pics = GOP_REPLICAS * GOP_DISTINCT * GOP_FRAMES
+    pflag = capi.ENGINE_DEVICE_PARSE if args.parse == "device" else 0
+    log("[rank %d] %d of %d GOP segments, %d of %d pictures, %d threads" % (rank, len(mine), len(units), my_pics, total_pics, threads))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- parity (untimed): digests of every segment, gathered, against the sequential golden
+    check = {}
+    gpath = os.path.join(ROOT, "tests", "golden", "gop_4k.json")
+    if not args.no_check and os.path.exists(gpath):
+        g = json.load(open(gpath))
+
+        def decode_fn(us):
+            with capi.Engine(local_rank, capi.ENGINE_BATCHED | pflag) as eng:
+                md5s, _ = eng.decode_streams_md5(us, threads=threads)
+            return md5s
+        res = shard.decode_sharded(units, decode_fn, rank, world, dist)
+        if rank == 0:
+            for i, b in enumerate(base):
+                if hashlib.md5(b).hexdigest() != g["streams"][i]["stream_md5"]:
+                    raise SystemExit("4K stream %d is not the stream the golden was made from" % i)
+            for rep in range(GOP_REPLICAS):
+                for i in range(GOP_DISTINCT):
+                    got = [m for (u, (si, k)) in zip(res, owner) if si == i for m in u][rep * GOP_FRAMES:(rep + 1) * GOP_FRAMES]
+                    if got != g["streams"][i]["frame_md5"]:
+                        raise SystemExit("PARITY FAILURE: GOP-sharded decode of 4K stream %d differs from the sequential reference decode" % i)
+            check = {"pictures": total_pics, "units": len(units), "against": "sequential decode by the unmodified reference (tests/golden/gop_4k.json)", "md5_exact": True}
+            log("[rank 0] parity: %d pictures over %d ranks MD5-exact vs the sequential reference decode" % (total_pics, world))
+
+    eng = capi.Engine(local_rank, capi.ENGINE_BATCHED | pflag)
+    for _ in range(args.warmup):
+        if mine:
+            eng.decode_streams(mine, threads)
+    barrier()
+    s0 = eng.stats()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        if mine:
+            rs = eng.decode_streams(mine, threads)
+            assert rs.pictures == my_pics and rs.err_mbs == 0, (rs.pictures, my_pics, rs.err_mbs)
+    barrier()
+    dt = time.perf_counter() - t0
+    if dist:
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    s1 = eng.stats()
+    eng.close()
+    clocks = sampler.stop() if rank == 0 else None
+    fps = total_pics * args.steps / dt
+    if rank == 0:
+        emit({"metric": "4K frames/sec (bit-exact H.264 Baseline decode, IDR-bounded GOP segments sharded over the GPUs)", "value": fps, "unit": "frames/s",
+              "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps, "higher_is_better": True,
+              "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+              "config": {"workload": WORKLOADS["4k_gop"][3], "width": 3840, "height": 2160, "streams": GOP_DISTINCT * GOP_REPLICAS, "frames_per_stream": GOP_FRAMES,
+                         "gop_segments": len(units), "segments_on_rank0": len(mine), "parser_threads_per_gpu": threads, "host_cores": cores, "slice_data_parse": args.parse,
+                         "l2": "inputs larger than L2"},
+              "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": (s1["h2d_bytes"] - s0["h2d_bytes"]) // args.steps,
+                      "d2h_bytes_per_step": (s1["d2h_bytes"] - s0["d2h_bytes"]) // args.steps, "timing": "wall clock between barrier+synchronize pairs, max over ranks; value IS the end-to-end number in this mode (rank 0's byte counts)"},
+              "gpu_launches": s1["kernel_launches"] - s0["kernel_launches"], "clocks": clocks, "parity": check})
     if dist:
         dist.destroy_process_group()
 
@@ -365,11 +488,14 @@ def main():
     ap.add_argument("--threads", type=int, default=0, help="parser threads per GPU (0: host cores / ranks)")
     ap.add_argument("--workload", default="1080p_ippp", choices=sorted(WORKLOADS), help="default: the configuration BASELINE.json's metric is quoted on")
     ap.add_argument("--parse", default="device", choices=["device", "host"], help="where slice data is parsed: kernel Kp (default) or the host cores")
+    ap.add_argument("--shard", default="streams", choices=["streams", "gop"], help="gop: strong scaling over the IDR-bounded GOP segments of a fixed set of 4K streams (SURVEY 8e; implies --workload 4k_gop)")
     ap.add_argument("--no-check", action="store_true")
     ap.add_argument("--e2e-only", action="store_true", help="host-to-host leg only (experiments)")
     ap.add_argument("--skip-e2e", action="store_true", help="kernel-tuning aid: skip the host-to-host leg (the line then carries no valid e2e and is not a bench result)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    if args.shard == "gop":
+        args.workload = "4k_gop"
     _WL["name"] = args.workload
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -387,7 +513,10 @@ def main():
         __graft_entry__.build()
     if args.warmup < 3:
         log("note: fewer than 3 warm-up steps requested")
-    own_arm(args, rank, local_rank, world)
+    if args.shard == "gop":
+        gop_arm(args, rank, local_rank, world)
+    else:
+        own_arm(args, rank, local_rank, world)
 
 
 if __name__ == "__main__":

@@ -39,6 +39,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include <atomic>
 #include <deque>
 #include <mutex>
@@ -56,7 +57,7 @@
 
 #define NBUF 3                 /* input buffers in flight per instance (host-parse; device-parse: look-ahead depth + 2) */
 #define NSCR 4                 /* batch scratch sets in flight per engine */
-#define NPAR 4                 /* Kp launches in flight per engine: one scratch set and one CUDA stream each, so that they overlap —
+#define NPAR 8                 /* Kp launches in flight per engine: one scratch set and one CUDA stream each, so that they overlap —
                                   a launch over a quarter of the look-ahead window does not fill the SMs on its own */
 #define STAT_TAIL 128          /* bytes behind every frame: h264b200_picstat_t of the picture (device-parse), copied out with it */
 #define CTRL_HEAD 16           /* int32 words before the progress counters: [0] K3 ticket, [1] K4 ticket */
@@ -155,6 +156,10 @@ struct ParseScratch {              /* one Kp launch */
 
 struct h264b200_engine {
     int device, sm_count;
+    /* H264B200_TIMELINE=file: device-side start / end of every Kp launch, reconstruction round and copy-out of the live run,
+     * written as CSV when the engine is destroyed (what nsys would show; there is no nsys in the image) */
+    struct TlEntry { int kind; uint32_t n; double host_ms; cudaEvent_t a, b; };
+    std::vector<TlEntry> tl; const char *tl_path; cudaEvent_t tl_base; double tl_host0;
     int kp_on_comp;                /* H264B200_KP_ON_COMP=1: Kp launches go to the reconstruction stream (serialised with K1..K4) instead of overlapping them */
     uint32_t wf_cap;               /* CTAs per SM the wavefront kernels K3 / K4 are launched with at most (tickets hand out the rows); H264B200_WF_CAP, default 16 */
     cudaStream_t s_h2d, s_comp, s_d2h, s_parse[NPAR];
@@ -269,6 +274,33 @@ static uint32_t kp_grid(h264b200_engine *e, uint32_t n_pics)
     return blocks < cap ? blocks : cap;
 }
 
+static double host_ms_now() { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return 1e3 * (double)t.tv_sec + 1e-6 * (double)t.tv_nsec; }
+static void tl_begin(h264b200_engine *e, int kind, uint32_t n, cudaStream_t s)
+{
+    if (!e->tl_path || e->tl.size() >= 20000) return;
+    h264b200_engine::TlEntry t; t.kind = kind; t.n = n; t.host_ms = host_ms_now() - e->tl_host0;
+    cudaEventCreate(&t.a); cudaEventCreate(&t.b);
+    cudaEventRecord(t.a, s);
+    e->tl.push_back(t);
+}
+static void tl_end(h264b200_engine *e, cudaStream_t s) { if (e->tl_path && !e->tl.empty() && e->tl.size() < 20000) cudaEventRecord(e->tl.back().b, s); }
+static void tl_dump(h264b200_engine *e)
+{
+    if (!e->tl_path) return;
+    FILE *f = fopen(e->tl_path, "a");
+    if (f) {
+        fprintf(f, "kind,pictures,host_launch_ms,gpu_start_ms,gpu_end_ms\n");
+        for (auto &t : e->tl) {
+            float a = 0, b = 0;
+            if (cudaEventElapsedTime(&a, e->tl_base, t.a) != cudaSuccess || cudaEventElapsedTime(&b, e->tl_base, t.b) != cudaSuccess) continue;
+            fprintf(f, "%s,%u,%.3f,%.3f,%.3f\n", t.kind == 0 ? "round" : t.kind == 1 ? "kp" : "d2h", t.n, t.host_ms, a, b);
+        }
+        fclose(f);
+    }
+    for (auto &t : e->tl) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+    e->tl.clear();
+}
+
 /* ------------------------------------------------------------------ Kp launch */
 /* engine mutex held.  Copy the blocks of the given queued pictures to the device and parse them all in one launch. */
 static int launch_parse(h264b200_engine *e, std::vector<PicBuf *> &list)
@@ -333,7 +365,9 @@ static int launch_parse(h264b200_engine *e, std::vector<PicBuf *> &list)
     cudaMemcpyAsync(d_pics, ps.h_pics, n * sizeof(KpPic), cudaMemcpyHostToDevice, s);
     cudaMemsetAsync(d_ticket, 0, 64, s);
     KpBatch kb; kb.pics = d_pics; kb.n_pics = n; kb.ticket = d_ticket; kb.tables = e->d_tables;
+    tl_begin(e, 1, n, s);
     kp_parse<<<kp_grid(e, n), KP_WARPS * 32, 0, s>>>(kb);
+    tl_end(e, s);
     e->st.kernel_launches++; e->st.kp_launches++; e->st.kp_pictures += n;
     cudaEventRecord(ps.done, s); ps.used = true;
     if (retain) {
@@ -464,7 +498,9 @@ static uint32_t launch_round(h264b200_engine *e, std::vector<PicBuf *> &list)
     cudaStreamWaitEvent(e->s_comp, e->ev_h2d, 0);
     cudaMemcpyAsync(d_jobs, sc.h_jobs, n * sizeof(PicJob), cudaMemcpyHostToDevice, e->s_comp);
     cudaMemsetAsync(d_ctrl, 0, ctrl_words * sizeof(int32_t), e->s_comp);
+    tl_begin(e, 0, n, e->s_comp);
     launch_kernels(e, b, pl, nullptr);
+    tl_end(e, e->s_comp);
     if (retain) {
         cudaMemsetAsync(ret->d_bytes, 0, 4 * sizeof(unsigned long long), e->s_comp);
         k_count_bytes<<<(mb_base + 255) / 256, 256, 0, e->s_comp>>>(b, ret->d_bytes);
@@ -483,6 +519,7 @@ static uint32_t launch_round(h264b200_engine *e, std::vector<PicBuf *> &list)
     cudaEventRecord(sc.done, e->s_comp); sc.used = true;
     cudaEventRecord(e->ev_comp, e->s_comp);
     cudaStreamWaitEvent(e->s_d2h, e->ev_comp, 0);
+    tl_begin(e, 2, n, e->s_d2h);
     for (uint32_t i = 0; i < n; i++) {
         PicBuf *p = list[i]; Inst *in = p->inst; int slot = p->in.cur_slot;
         uint8_t *d_frame = in->d_frames + (size_t)slot * in->frame_stride, *h_frame = in->h_frames + (size_t)slot * in->frame_stride;
@@ -508,6 +545,7 @@ static uint32_t launch_round(h264b200_engine *e, std::vector<PicBuf *> &list)
         in->slot_flags[slot] = 2; in->slot_lgen[slot]++;
     }
     cudaMemcpyAsync(e->h_err, e->d_err, sizeof(uint32_t), cudaMemcpyDeviceToHost, e->s_d2h);
+    tl_end(e, e->s_d2h);
     cudaEventRecord(sc.d2h_done, e->s_d2h);
     e->st.pictures += n; e->st.batches++;
     if (retain) {
@@ -902,6 +940,9 @@ extern "C" h264b200_engine_t *h264b200EngineCreateEx(int device, uint32_t flags)
     e->sm_count = p.multiProcessorCount;
     e->wf_cap = 16;
     { const char *c = getenv("H264B200_KP_ON_COMP"); e->kp_on_comp = c && atoi(c) > 0; }
+    e->tl_path = getenv("H264B200_TIMELINE");
+    if (e->tl_path && !*e->tl_path) e->tl_path = nullptr;
+    if (e->tl_path) { cudaEventCreate(&e->tl_base); cudaEventRecord(e->tl_base, 0); e->tl_host0 = host_ms_now(); }
     { const char *c = getenv("H264B200_WF_CAP"); if (c && atoi(c) > 0 && atoi(c) <= 64) e->wf_cap = (uint32_t)atoi(c); }
     CUDA_TRY(cudaStreamCreateWithFlags(&e->s_h2d, cudaStreamNonBlocking), { delete e; return NULL; });
     CUDA_TRY(cudaStreamCreateWithFlags(&e->s_comp, cudaStreamNonBlocking), { delete e; return NULL; });
@@ -969,6 +1010,7 @@ extern "C" void h264b200EngineDestroy(h264b200_engine_t *e)
     set_device(e);
     cudaStreamSynchronize(e->s_h2d); for (int k = 0; k < NPAR; k++) cudaStreamSynchronize(e->s_parse[k]);
     cudaStreamSynchronize(e->s_comp); cudaStreamSynchronize(e->s_d2h);
+    tl_dump(e);
     free_retained(e);
     for (Inst *p : e->pool) inst_free(p);
     e->pool.clear();

@@ -53,7 +53,6 @@
 
 #include "kp_types.h"
 #include <stddef.h>
-static_assert(offsetof(KpStage, cc) == offsetof(KpStage, lc) + 40, "lc and cc form one 64-byte TotalCoeff grid (KpTables.step_desc)");
 
 #ifdef __CUDACC__
 typedef uint4 KpU4;
@@ -260,8 +259,8 @@ KP_FN uint32_t kp_predict_mv(const KpStage *st, int x4, int y4, int w4, int ref,
 KP_FN int kp_mv_in_range(int x, int y) { return x >= -8192 && x <= 8191 && y >= -2048 && y <= 2047; }
 
 /* ------------------------------------------------------------------ residual */
-/* nC (9.2.1) from TotalCoeff grids with one guard row above and one guard column to the left (KpStage.lc: luma, 5 rows
- * of 8; KpStage.cc: one 3 x 4 grid per chroma plane), the host parser's own layout (h264_slice.c parse_residual): the
+/* nC (9.2.1) from TotalCoeff grids with one guard row above and one guard column to the left (KpStage.grid: luma, 5 rows
+ * of 8, cells 0..39; one 3 x 4 grid per chroma plane, cells 40..51 and 52..63), the host parser's own layout (h264_slice.c parse_residual): the
  * guards come from macroblocks A and B (64 = not available, so that a + b >= 64 exactly when a neighbour is missing) and
  * are written by the whole warp when the neighbours are staged; the interior starts at zero. */
 KP_FN int kp_nc_avg(int a, int b)
@@ -292,7 +291,7 @@ KP_NOUNROLL
         const int step = KP_CTZ(todo);
         const uint32_t dsc = T->step_desc[step];
         const int kind = (int)((dsc >> 12) & 3);
-        uint8_t *g = st->lc + (dsc & 0xff);                        /* lc and cc are one 64-byte grid */
+        uint8_t *g = st->grid + (dsc & 0xff);
         int nc, tc, maxc;
         int16_t *out = st->slots + slot * 16;
         const uint8_t *scan = T->zigzag + 1;
@@ -608,6 +607,33 @@ KP_FN void kp_stage_in(int lane, const KpPic &p, KpStage *st, uint32_t addr, int
     }
 }
 
+/* Where the border cells of the per-macroblock grids come from is the same for every macroblock: computed once per
+ * picture into KpStage.gsrc / msrc (0: an interior cell; else 1 + neighbour | index << 4 [| vector index << 8]). */
+KP_FN void kp_stage_plan(int lane, KpStage *st)
+{
+    for (int v = lane; v < 64; v += KP_LANES) {
+        uint32_t g = 0, m = 0;
+        if (v < 40) {                                             /* luma: 5 rows of 8, block (x, y) at 9 + x + 8 y */
+            const int rr = v >> 3, c = v & 7;
+            if (rr == 0 && c >= 1 && c <= 4) { const int i = c - 1; g = 2u | (uint32_t)(10 + i + 2 * (i >> 1)) << 4; }       /* B: blocks 10 11 14 15 */
+            else if (rr >= 1 && c == 0) { const int i = rr - 1; g = 1u | (uint32_t)(5 + 2 * i + 4 * (i >> 1)) << 4; }       /* A: blocks 5 7 13 15 */
+        } else {                                                  /* chroma: per plane 3 rows of 4, block (x, y) at 5 + x + 4 y */
+            const int w = v - 40, pl = w >= 12, i = w - 12 * pl, rr = i >> 2, c = i & 3;
+            if (rr == 0 && (c == 1 || c == 2)) g = 2u | (uint32_t)(16 + 4 * pl + 1 + c) << 4;
+            else if (rr >= 1 && c == 0) g = 1u | (uint32_t)(16 + 4 * pl + 2 * rr - 1) << 4;
+        }
+        if (v < 60) {                                             /* motion vector grid, KP_G */
+            const int rr = v / 12, c = v - 12 * rr - 3;
+            if (rr == 0) {
+                if (c == 0) m = 4u | 3u << 4 | 15u << 8;                                           /* D: its bottom right block */
+                else if (c >= 1 && c <= 4) m = 2u | (uint32_t)(2 + ((c - 1) >> 1)) << 4 | (uint32_t)(11 + c) << 8;   /* B: bottom row */
+                else if (c == 5) m = 3u | 2u << 4 | 12u << 8;                                      /* C: bottom left block */
+            } else if (c == 0) m = 1u | (uint32_t)(((rr - 1) >> 1) * 2 + 1) << 4 | (uint32_t)((rr - 1) * 4 + 3) << 8;   /* A: right column */
+        }
+        st->gsrc[v] = (uint16_t)g; st->msrc[v] = (uint16_t)m;
+    }
+}
+
 /* after kp_stage_in (and a warp sync): which neighbours belong to the slice; the guard cells of the TotalCoeff grids
  * (nC) from macroblocks A and B and zeros inside; in P slices the border of the motion vector grid (KP_G) from the
  * neighbour records, "not available" inside.  Every lane computes the same availability word. */
@@ -621,32 +647,22 @@ KP_FN uint32_t kp_stage_derive(int lane, KpStage *st, uint16_t sid, int is_p, in
         if (mbx > 0 && st->nctx[3].slice_id == sid) av |= 8;
     }
     for (int v = lane; v < 64; v += KP_LANES) {
+        const uint32_t d = st->gsrc[v];
         int val = 0;
-        if (v < 40) {                                             /* luma: 5 rows of 8, block (x, y) at 9 + x + 8 y */
-            const int rr = v >> 3, c = v & 7;
-            if (rr == 0 && c >= 1 && c <= 4) { const int i = c - 1; val = (av & 2) ? st->nctx[1].tc[10 + i + 2 * (i >> 1)] : 64; }       /* B: blocks 10 11 14 15 */
-            else if (rr >= 1 && c == 0) { const int i = rr - 1; val = (av & 1) ? st->nctx[0].tc[5 + 2 * i + 4 * (i >> 1)] : 64; }      /* A: blocks 5 7 13 15 */
-            st->lc[v] = (uint8_t)val;
-        } else {                                                  /* chroma: per plane 3 rows of 4, block (x, y) at 5 + x + 4 y */
-            const int w = v - 40, pl = w >= 12, i = w - 12 * pl, rr = i >> 2, c = i & 3;
-            if (rr == 0 && (c == 1 || c == 2)) val = (av & 2) ? st->nctx[1].tc[16 + 4 * pl + 1 + c] : 64;
-            else if (rr >= 1 && c == 0) val = (av & 1) ? st->nctx[0].tc[16 + 4 * pl + 2 * rr - 1] : 64;
-            st->cc[pl][i] = (uint8_t)val;
-        }
+        if (d) { const int nb = (int)(d & 15) - 1; val = ((av >> nb) & 1) ? st->nctx[nb].tc[d >> 4] : 64; }
+        st->grid[v] = (uint8_t)val;
     }
     if (is_p) {
         for (int v = lane; v < 60; v += KP_LANES) {
-            const int rr = v / 12, c = v - 12 * rr - 3;
-            int nb = -1, ri = 0, mi = 0, ref = -2;
+            const uint32_t d = st->msrc[v];
+            int ref = -2;
             uint32_t mv = 0;
-            if (rr == 0) {
-                if (c == 0) { nb = 3; ri = 3; mi = 15; }                                   /* D: its bottom right block */
-                else if (c >= 1 && c <= 4) { nb = 1; ri = 2 + ((c - 1) >> 1); mi = 11 + c; } /* B: bottom row */
-                else if (c == 5) { nb = 2; ri = 2; mi = 12; }                              /* C: bottom left block */
-            } else if (c == 0) { nb = 0; ri = ((rr - 1) >> 1) * 2 + 1; mi = (rr - 1) * 4 + 3; }   /* A: right column */
-            if (nb >= 0 && ((av >> nb) & 1)) {
-                ref = -1;
-                if (st->nctx[nb].kind == H264B200_MB_INTER) { ref = st->nctx[nb].ref_idx[ri]; mv = ((const uint32_t *)st->nrec[nb].mv)[mi]; }
+            if (d) {
+                const int nb = (int)(d & 15) - 1;
+                if ((av >> nb) & 1) {
+                    ref = -1;
+                    if (st->nctx[nb].kind == H264B200_MB_INTER) { ref = st->nctx[nb].ref_idx[(d >> 4) & 15]; mv = ((const uint32_t *)st->nrec[nb].mv)[d >> 8]; }
+                }
             }
             st->refg[v] = (int8_t)ref; st->mvg[v] = mv;
         }
@@ -673,9 +689,9 @@ KP_FN void kp_stage_out(int lane, const KpPic &p, KpStage *st, const KpTables *T
             else if (ipcm_byte >= 0) val = 0x10101010u;
             else if (w < 4) {
                 const uint8_t *ix = T->lc_idx + 4 * w;
-                val = (uint32_t)st->lc[ix[0]] | ((uint32_t)st->lc[ix[1]] << 8) | ((uint32_t)st->lc[ix[2]] << 16) | ((uint32_t)st->lc[ix[3]] << 24);
+                val = (uint32_t)st->grid[ix[0]] | ((uint32_t)st->grid[ix[1]] << 8) | ((uint32_t)st->grid[ix[2]] << 16) | ((uint32_t)st->grid[ix[3]] << 24);
             } else {
-                const uint8_t *g = st->cc[w - 4];
+                const uint8_t *g = st->grid + 40 + 12 * (w - 4);
                 val = (uint32_t)g[5] | ((uint32_t)g[6] << 8) | ((uint32_t)g[9] << 16) | ((uint32_t)g[10] << 24);
             }
             ((uint32_t *)&p.ctx[addr])[w] = val;
@@ -807,6 +823,7 @@ KP_FN void kp_parse_picture(int lane, const KpPic &p, KpStage *st, const KpTable
         for (uint32_t i = (uint32_t)lane; i < 2 * N; i += KP_LANES) ((KpU4 *)p.ctx)[i] = z;
     }
     kp_stage_clear(lane, st);
+    kp_stage_plan(lane, st);
     s.T = T; s.st = st; s.W = W; s.N = N;
     s.coef_used = 0; s.n_intra = s.n_inter = s.any_deblock = 0;
     KP_SYNC();

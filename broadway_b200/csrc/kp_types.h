@@ -46,10 +46,11 @@ typedef struct {
     uint32_t mvg[60];            /* neighbour grid of motion vector prediction, 5 rows of 12 (kp_core.h KP_G); 16-byte aligned */
     int8_t   refg[64];           /* ... and its reference indices: -2 not available, -1 not inter */
     uint16_t part[16];           /* partition list of the macroblock (KP_PART) */
-    uint8_t  lc[40];             /* TotalCoeff grid of the luma blocks with guard row / column (nC), 5 rows of 8 */
-    uint8_t  cc[2][12];          /* ... of the chroma blocks, per plane 3 rows of 4 */
-    uint8_t  lvl_dummy;          /* where TotalCoeff of a DC block goes (it takes part in no nC) */
+    uint8_t  grid[64];           /* TotalCoeff grids with guard row / column (nC): luma 5 rows of 8 (cells 0..39), then per chroma plane 3 rows of 4 */
+    uint8_t  lvl_dummy;
     uint8_t  pad[15];
+    uint16_t gsrc[64];           /* per cell of the TotalCoeff grid / of the vector grid: which neighbour value fills it (kp_core.h kp_stage_plan) */
+    uint16_t msrc[64];
 } KpStage;
 
 typedef struct {                 /* outputs of one picture besides records / slots / contexts */
