@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("H264B200_LIB") or os.path.join(_HERE, "libh264b200.so
 
 H264BSD_RDY, H264BSD_PIC_RDY, H264BSD_HDRS_RDY, H264BSD_ERROR, H264BSD_PARAM_SET_ERROR, H264BSD_MEMALLOC_ERROR = range(6)
 H264SWDEC_OK, H264SWDEC_STRM_PROCESSED, H264SWDEC_PIC_RDY, H264SWDEC_PIC_RDY_BUFF_NOT_EMPTY, H264SWDEC_HDRS_RDY_BUFF_NOT_EMPTY = range(5)
-ENGINE_BATCHED, ENGINE_RETAIN, ENGINE_NO_D2H, ENGINE_DEVICE_PARSE, ENGINE_NO_RECON = 1, 2, 4, 8, 16
+ENGINE_BATCHED, ENGINE_RETAIN, ENGINE_NO_D2H, ENGINE_DEVICE_PARSE, ENGINE_NO_RECON, ENGINE_TAP_PREDEBLOCK = 1, 2, 4, 8, 16, 32
 
 
 class Storage(ctypes.Structure):
@@ -110,6 +110,8 @@ def lib():
     L.h264b200EngineAdvance.argtypes = [vp]; L.h264b200EngineAdvance.restype = u32
     L.h264b200EngineSetWindow.argtypes = [vp, u32, u32]; L.h264b200EngineSetWindow.restype = None
     L.h264b200DeviceParse.argtypes = [sp]; L.h264b200DeviceParse.restype = u32
+    if hasattr(L, "h264b200DebugFetchPredeblock"):
+        L.h264b200DebugFetchPredeblock.argtypes = [sp, vp, ctypes.c_size_t]; L.h264b200DebugFetchPredeblock.restype = ctypes.c_long
     if hasattr(L, "h264b200DebugFetchParse"):
         L.h264b200DebugFetchParse.argtypes = [sp, ctypes.c_int, vp, vp, u32, vp]; L.h264b200DebugFetchParse.restype = ctypes.c_int
     L.h264b200DecodeStreams.argtypes = [vp, ctypes.POINTER(StreamDesc), u32, u32, vp, vp, ctypes.POINTER(RunStats)]
@@ -220,12 +222,14 @@ def decode_annexb(data, keep_frames=False, no_reordering=0, api="swdec"):
     return out, info
 
 
-def decode_on_engine(eng, data, keep_frames=False, fetch_parse=False, no_reordering=0):
+def decode_on_engine(eng, data, keep_frames=False, fetch_parse=False, no_reordering=0, predeblock=None):
     """Decode one Annex-B stream with the h264bsd* loop on an instance attached to `eng` (h264b200InitOnEngine).  On an
     engine that is not batched every finished picture is launched at once, so this is the synchronous API on an engine
     of the caller's choice — in particular a device-parse one (ENGINE_DEVICE_PARSE): slice data parsed by kernel Kp.
     fetch_parse: also return, per picture in decoding order, what Kp produced (h264b200DebugFetchParse):
-    (records bytes, coefficient slot bytes, 12 result words).  Returns (md5s or frames, info[, parses])."""
+    (records bytes, coefficient slot bytes, 12 result words).  predeblock: a list that receives, per picture in decoding
+    order, the MD5 of the picture before deblocking (engine flag ENGINE_TAP_PREDEBLOCK).
+    Returns (md5s or frames, info[, parses])."""
     L = lib()
     buf = ctypes.create_string_buffer(bytes(data), len(data) + 16)
     base = ctypes.addressof(buf)
@@ -247,6 +251,14 @@ def decode_on_engine(eng, data, keep_frames=False, fetch_parse=False, no_reorder
                 out.append(ctypes.string_at(p, nb) if keep_frames else frame_md5(p, nb))
                 info["err_mbs"] += err.value
                 info["pic_ids"].append(pid.value)
+
+        def fetch_pre():
+            nb = info["width"] * info["height"] * 3 // 2
+            buf = ctypes.create_string_buffer(nb)
+            rc = L.h264b200DebugFetchPredeblock(ctypes.byref(st), buf, nb)
+            if rc != nb:
+                raise RuntimeError("h264b200DebugFetchPredeblock failed (%d)" % rc)
+            predeblock.append(hashlib.md5(buf.raw).hexdigest())
 
         def fetch():
             n_mbs = info["width"] * info["height"] // 256
@@ -271,11 +283,15 @@ def decode_on_engine(eng, data, keep_frames=False, fetch_parse=False, no_reorder
                 info["device_parse"] = L.h264b200DeviceParse(ctypes.byref(st))
                 if fetch_parse:
                     fetch()
+                if predeblock is not None:
+                    fetch_pre()
                 drain()
             elif nread.value == 0:
                 break
         before = len(info["pic_ids"])
         L.h264bsdFlushBuffer(ctypes.byref(st))
+        if predeblock is not None and L.h264b200DeviceParse(ctypes.byref(st)) and len(predeblock) < pic_id + 1:
+            fetch_pre()                 # device-parse: the flush ended (and launched) the last picture
         if fetch_parse and L.h264b200DeviceParse(ctypes.byref(st)) and len(parses) < pic_id + 1:
             try:
                 fetch()                 # the picture the flush ended (device-parse: the last one of the stream)

@@ -709,6 +709,18 @@ u32 h264b200PictureWait(storage_t *pStorage, u32 ticket)
     return err;
 }
 
+/* Never blocks: 0 the picture behind `ticket` is complete in its host buffer, 1 launched and in flight, 2 still queued in
+ * the engine, 0xffffffff on an error.  A backend without the query answers 1 for anything launched (h264b200PictureWait decides). */
+u32 h264b200PictureState(storage_t *pStorage, u32 ticket)
+{
+    h264_decoder_t *d = DEC(pStorage);
+    int rc;
+    if (!d || !d->be_inst) return 0xffffffffu;
+    if (!d->be->frame_state) return 1;
+    rc = d->be->frame_state(d->be, d->be_inst, (int)(ticket & 0xff), ticket >> 8);
+    return rc < 0 ? 0xffffffffu : (u32)rc;
+}
+
 /* 0 and the status words of the picture behind `ticket` (after h264b200PictureWait returned 0); 1 if the backend keeps none */
 u32 h264b200PictureStatus(storage_t *pStorage, u32 ticket, h264b200_picstat_t *out)
 {

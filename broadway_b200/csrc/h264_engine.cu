@@ -109,6 +109,7 @@ struct Inst {
     /* optional output formatting (K5): cropped RGBA instead of the I420 frame */
     int out_format; int cl, ct, cw, ch;
     uint8_t *d_rgba, *h_rgba; size_t rgba_bytes;
+    uint8_t *d_pre;                           /* H264B200_ENGINE_TAP_PREDEBLOCK: the last launched picture before K4 */
 };
 
 struct BatchPlan { bool k1, k2, k3, k3c, k4, k0; uint32_t total_mbs; int max_hm; int n_jobs; };
@@ -499,6 +500,19 @@ static uint32_t launch_round(h264b200_engine *e, std::vector<PicBuf *> &list)
     cudaMemcpyAsync(d_jobs, sc.h_jobs, n * sizeof(PicJob), cudaMemcpyHostToDevice, e->s_comp);
     cudaMemsetAsync(d_ctrl, 0, ctrl_words * sizeof(int32_t), e->s_comp);
     tl_begin(e, 0, n, e->s_comp);
+    if (e->flags & H264B200_ENGINE_TAP_PREDEBLOCK) {
+        /* parity aid: K0..K3, the pictures copied aside, then K4 */
+        BatchPlan a = pl, c; memset(&c, 0, sizeof c);
+        a.k4 = false;
+        c.k4 = pl.k4; c.total_mbs = pl.total_mbs; c.max_hm = pl.max_hm; c.n_jobs = pl.n_jobs;
+        launch_kernels(e, b, a, nullptr);
+        for (uint32_t i = 0; i < n; i++) {
+            Inst *in = list[i]->inst;
+            if (!in->d_pre && cudaMalloc((void **)&in->d_pre, in->frame_bytes) != cudaSuccess) { in->d_pre = nullptr; continue; }
+            cudaMemcpyAsync(in->d_pre, in->d_frames + (size_t)list[i]->in.cur_slot * in->frame_stride, in->frame_bytes, cudaMemcpyDeviceToDevice, e->s_comp);
+        }
+        launch_kernels(e, b, c, nullptr);
+    } else
     launch_kernels(e, b, pl, nullptr);
     tl_end(e, e->s_comp);
     if (retain) {
@@ -701,6 +715,7 @@ static void inst_free(Inst *in)
     if (in->d_frames) cudaFree(in->d_frames);
     if (in->h_frames) cudaFreeHost(in->h_frames);
     if (in->d_rgba) { cudaFree(in->d_rgba); cudaFreeHost(in->h_rgba); }
+    if (in->d_pre) cudaFree(in->d_pre);
     delete in->fifo;
     delete in;
 }
@@ -866,6 +881,19 @@ static int be_frame_wait(h264_backend_t *be, void *inst, int slot, uint32_t gen,
     return rc;
 }
 
+static int be_frame_state(h264_backend_t *be, void *inst, int slot, uint32_t gen)
+{
+    h264b200_engine *e = (h264b200_engine *)be->ctx; Inst *in = (Inst *)inst;
+    if (slot < 0 || slot >= (int)in->n_slots) return -1;
+    std::lock_guard<std::mutex> lk(e->mu);             /* slot_lgen / slot_ready are written by the launching thread under the same mutex */
+    const uint32_t g = full_gen(in, slot, gen);
+    if ((int32_t)(in->slot_lgen[slot] - g) < 0) return 2;
+    if (in->slot_lgen[slot] != g) return 0;             /* a later picture was launched into the slot: h264b200PictureWait reports that */
+    if (in->slot_flags[slot] & 4) return -1;
+    if (in->slot_flags[slot] & 2) { set_device(e); return cudaEventQuery(in->slot_ready[slot]) == cudaSuccess ? 0 : 1; }
+    return 0;
+}
+
 static void be_frame_release(h264_backend_t *be, void *inst, int slot, uint32_t gen)
 {
     Inst *in = (Inst *)inst; (void)be;
@@ -987,6 +1015,7 @@ extern "C" h264b200_engine_t *h264b200EngineCreateEx(int device, uint32_t flags)
     e->be.set_output = be_set_output;
     e->be.block_grow = be_block_grow; e->be.frame_status = be_frame_status; e->be.frame_release = be_frame_release;
     e->be.inst_pending = be_inst_pending;
+    e->be.frame_state = be_frame_state;
     e->be.parse_mode = (flags & H264B200_ENGINE_DEVICE_PARSE) != 0;
     e->be.destroy = be_destroy; e->be.ctx = e;
     return e;
@@ -1233,6 +1262,18 @@ extern "C" int h264b200_engine_fetch_parse(h264_backend_t *be, void *inst, int b
         if (n && cudaMemcpy(coef, p->d_coef, (size_t)n * 32, cudaMemcpyDeviceToHost) != cudaSuccess) return -3;
     }
     return 0;
+}
+
+extern "C" long h264b200DebugFetchPredeblock(storage_t *pStorage, uint8_t *out, size_t cap)
+{
+    h264_decoder_t *d = pStorage ? (h264_decoder_t *)pStorage->impl : NULL;
+    if (!d || !d->be || !d->be_inst || d->be->inst_create != be_inst_create || !out) return -1;
+    h264b200_engine *e = (h264b200_engine *)d->be->ctx; Inst *in = (Inst *)d->be_inst;
+    if (!(e->flags & H264B200_ENGINE_TAP_PREDEBLOCK) || !in->d_pre || cap < in->frame_bytes) return -2;
+    h264b200EngineSync(e);
+    set_device(e);
+    if (cudaMemcpy(out, in->d_pre, in->frame_bytes, cudaMemcpyDeviceToHost) != cudaSuccess) return -3;
+    return (long)in->frame_bytes;
 }
 
 extern "C" int h264b200DebugFetchParse(storage_t *pStorage, int back, void *mbs, int16_t *coef, uint32_t coef_cap, uint32_t *res)

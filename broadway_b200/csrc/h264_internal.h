@@ -179,6 +179,8 @@ struct h264_backend {
     uint32_t (*inst_pending)(h264_backend_t *be, void *inst);
     /* 1: instances are to be created in device-parse mode (h264b200_slices.h); read by the decoder at activation */
     int parse_mode;
+    /* optional, never blocks: 0 generation `gen` of `slot` is in its host mirror, 1 launched but still in flight, 2 not launched yet, -1 error */
+    int (*frame_state)(h264_backend_t *be, void *inst, int slot, uint32_t gen);
 };
 
 /* implemented by whichever backend is linked: the CUDA engine in libh264b200.so */

@@ -71,6 +71,7 @@ struct runner {
     uint32_t arrived[MAX_GROUPS], produced[MAX_GROUPS], dead[MAX_GROUPS];   /* under mu: the group's current round */
     uint32_t launched[MAX_GROUPS];            /* rounds of the group that have been handed to the GPU (release / acquire) */
     int stop;                                 /* every group went through a round without producing a picture */
+    int force_wait;                           /* device-parse: the last scheduling step launched nothing: wait for pictures in flight */
     uint32_t rounds;                          /* batches launched */
 };
 
@@ -211,16 +212,28 @@ static int dev_scan_one(rstream_t *s)
     s->finished = 1;
     return 0;
 }
-/* hand over every output whose picture has been launched; returns how many */
-static u32 dev_consume(worker_t *w, rstream_t *s, uint32_t stream_index)
+/* Hand over the outputs whose pictures have been launched, oldest first; returns how many.  The NEWEST launched picture
+ * of the stream is not waited for while it is still in flight (unless `drain`): the round that produced it was launched
+ * one scheduling step ago, and waiting here would put its kernels and its copy-out on the host's critical path —
+ * reconstruction of round r+1 could not be launched before round r has arrived in host memory.  Left alone for one
+ * step, the copy-out of round r overlaps the kernels of round r+1 (the frame slot round r+1 writes was released when
+ * round r-1 was consumed). */
+static u32 dev_consume(worker_t *w, rstream_t *s, uint32_t stream_index, int drain)
 {
     runner_t *r = w->r;
     u32 n = 0;
     while (s->outq_n) {
         pending_t *q = &s->outq[s->outq_head];
         h264b200_picstat_t ps;
-        double t0 = now_s();
-        u32 rc = h264b200PictureWait(&s->st, q->ticket);
+        double t0;
+        u32 rc, state = h264b200PictureState(&s->st, q->ticket);
+        if (state == 2) break;                                    /* still queued in the engine */
+        if (state == 1 && !drain) {
+            /* in flight: wait only if a newer output of this stream has been launched as well */
+            if (s->outq_n < 2 || h264b200PictureState(&s->st, s->outq[(s->outq_head + 1) % s->outq_cap].ticket) == 2) break;
+        }
+        t0 = now_s();
+        rc = h264b200PictureWait(&s->st, q->ticket);
         w->wait_s += now_s() - t0;
         if (rc == H264B200_WAIT_NOT_LAUNCHED) break;
         if (rc == 0xffffffffu || rc == 0xfffffffeu) s->failed = 1;
@@ -252,7 +265,9 @@ static void *dev_worker_main(void *arg)
             sched_yield();
         }
         if (s->inited) {
-            activity += dev_consume(w, s, idx);
+            /* drain: nothing of the stream is left to launch, or the engine could launch nothing last time (a picture may be
+             * held back by an output we have not released) */
+            activity += dev_consume(w, s, idx, (s->finished && !h264b200PicturesPending(&s->st)) || __atomic_load_n(&r->force_wait, __ATOMIC_ACQUIRE));
             /* a quarter of the look-ahead per round: the first Kp launch goes out after one round of scanning, not after
              * the whole window has been scanned, and in steady state (one picture per stream reconstructed per round)
              * the window stays full */
@@ -271,6 +286,7 @@ static void *dev_worker_main(void *arg)
         if (++r->arrived[0] == r->n_streams) {
             const uint32_t launched = h264b200EngineAdvance(r->e);
             if (launched) r->rounds++;
+            __atomic_store_n(&r->force_wait, launched == 0, __ATOMIC_RELEASE);
             if (!r->produced[0] && !launched) __atomic_store_n(&r->stop, 1, __ATOMIC_RELEASE);
             r->produced[0] = 0; r->arrived[0] = 0;
             __atomic_store_n(&r->launched[0], round + 1, __ATOMIC_RELEASE);
@@ -327,7 +343,7 @@ int h264b200DecodeStreams(h264b200_engine_t *e, const h264b200_stream_t *streams
     for (i = 1; i < n_threads; i++) pthread_join(w[i].th, NULL);
     if (dev) {                                                                   /* nothing should be left; be safe */
         for (i = 0; i < n_streams; i++) while (r.s[i].inited && r.s[i].outq_n) {
-            if (!dev_consume(&w[0], &r.s[i], i) && !h264b200EngineSubmit(e)) { r.s[i].failed = 1; break; }
+            if (!dev_consume(&w[0], &r.s[i], i, 1) && !h264b200EngineSubmit(e)) { r.s[i].failed = 1; break; }
         }
     } else
     for (i = 0; i < n_streams; i++) consume_prev(&w[0], &r.s[i], i);           /* what the last round popped */

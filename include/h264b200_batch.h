@@ -26,6 +26,8 @@ extern "C" {
 
 #define H264B200_ENGINE_NO_RECON 16u /* parity aid: reconstruction rounds launch no K1..K4, so that what kernel Kp wrote (levels, not yet
                                        transformed in place by K1) can be read back with h264b200DebugFetchParse; frames are garbage */
+#define H264B200_ENGINE_TAP_PREDEBLOCK 32u /* parity aid: every picture is copied aside between K3 and K4 (the reference's picture at its
+                                       h264bsdFilterPicture call, h264bsd_decoder.c:489-491); read it with h264b200DebugFetchPredeblock */
 
 h264b200_engine_t *h264b200EngineCreateEx(int device, uint32_t flags);
 void h264b200EngineSetFlags(h264b200_engine_t *e, uint32_t flags);
@@ -40,6 +42,8 @@ u8  *h264b200NextOutputPictureAsync(storage_t *pStorage, u32 *picId, u32 *isIdrP
 /* 0: picture complete; otherwise the engine error flags, 0xffffffff on a CUDA failure, or 0xfffffffe when the
  * caller waited so long that a later picture was already reconstructed into the same frame buffer. */
 u32  h264b200PictureWait(storage_t *pStorage, u32 ticket);
+/* never blocks: 0 complete, 1 launched and in flight, 2 still queued in the engine, 0xffffffff error */
+u32  h264b200PictureState(storage_t *pStorage, u32 ticket);
 #define H264B200_WAIT_NOT_LAUNCHED 0xfffffffdu   /* the picture is still queued in the engine (device-parse look-ahead): call h264b200EngineAdvance */
 /* The caller is done with the picture behind `ticket`: its host buffer may be overwritten by a later picture of the
  * same frame slot.  Until then the engine holds that later picture back (it is launched by a later
@@ -98,6 +102,9 @@ void h264b200EngineKernelTimes(h264b200_engine_t *e, h264b200_kernel_times_t *ou
  * any_deblock, n_conceal, conceal_offset, -, -, err_mbs, flags, decoded_mbs, coef_slots}.  Blocks until the engine is idle.
  * Returns 0, or a negative value when the picture is not available. */
 int  h264b200DebugFetchParse(storage_t *pStorage, int back, void *mbs, int16_t *coef, uint32_t coef_cap, uint32_t *res);
+/* the picture most recently launched for this instance as it was BEFORE deblocking (engine flag H264B200_ENGINE_TAP_PREDEBLOCK);
+ * returns the number of bytes written to out (width*height*3/2) or a negative value */
+long h264b200DebugFetchPredeblock(storage_t *pStorage, uint8_t *out, size_t cap);
 
 /* ---- many streams through one engine ---- */
 typedef struct { const uint8_t *data; size_t len; } h264b200_stream_t;   /* Annex-B; not modified (copied internally) */

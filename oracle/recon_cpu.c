@@ -733,6 +733,12 @@ static int cpu_frame_wait(h264_backend_t *be, void *inst, int slot, uint32_t gen
     if (l == (gen & 0xffffffu)) return 0;
     return (int32_t)((l - gen) << 8) < 0 ? 2 : 1;      /* 2: still queued; 1: a later picture already took the slot */
 }
+/* the CPU backend reconstructs at launch: a launched picture is complete */
+static int cpu_frame_state(h264_backend_t *be, void *inst, int slot, uint32_t gen)
+{
+    int rc = cpu_frame_wait(be, inst, slot, gen, NULL);
+    return rc == 2 ? 2 : 0;
+}
 static void cpu_frame_release(h264_backend_t *be, void *inst, int slot, uint32_t gen)
 {
     cpu_inst_t *in = (cpu_inst_t *)inst;
@@ -750,7 +756,7 @@ h264_backend_t recon_cpu_backend(int device_parse)
     b.pic_submit = cpu_pic_submit; b.frame_host = cpu_frame_host; b.destroy = cpu_destroy;
     b.frame_host_async = cpu_frame_host_async; b.frame_wait = cpu_frame_wait;
     b.block_grow = cpu_block_grow; b.frame_status = cpu_frame_status;
-    b.frame_release = cpu_frame_release; b.inst_pending = cpu_inst_pending;
+    b.frame_release = cpu_frame_release; b.inst_pending = cpu_inst_pending; b.frame_state = cpu_frame_state;
     b.parse_mode = device_parse;
     return b;
 }
