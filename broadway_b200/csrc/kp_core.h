@@ -38,6 +38,7 @@
 #define KP_CLZ(x) __clz((int)(x))
 #define KP_CTZ(x) (__ffs((int)(x)) - 1)
 #define KP_BSWAP(x) __byte_perm((x), 0, 0x0123)
+#define KP_COLD() asm volatile("")   /* an opaque statement keeps ptxas from if-converting the block it sits in */
 #else
 #define KP_FN static inline
 #define KP_NOINL static
@@ -49,14 +50,26 @@
 #define KP_CLZ(x) __builtin_clz(x)
 #define KP_CTZ(x) __builtin_ctz(x)
 #define KP_BSWAP(x) __builtin_bswap32(x)
+#define KP_COLD() ((void)0)
 #endif
 
 #include "kp_types.h"
 #include <stddef.h>
 
 #ifdef __CUDACC__
+/* A pointer into shared memory whose 32-bit shared-window address the compiler must keep in a register from here on.
+ * On sm_100 that address contains the CTA's rank in its cluster (S2R SR_CgaCtaId + LEA); inside the divergent lane-0
+ * code ptxas cannot use the uniform datapath for it and, with 64 registers, re-materialised the whole sequence (and the
+ * warp's staging address from SR_TID) at ~35 places per macroblock: 8 % of the instructions of the kernel. */
+template <typename T> __device__ __forceinline__ T *kp_pin_shared(T *p)
+{
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("" : "+r"(a));
+    return (T *)__cvta_shared_to_generic(a);
+}
 typedef uint4 KpU4;
 #else
+#define kp_pin_shared(p) (p)
 typedef struct { uint32_t x, y, z, w; } KpU4;
 #endif
 
@@ -103,7 +116,10 @@ KP_FN uint32_t kp_peek(const KpS &s, int n) { return kp_peek32(s) >> (32 - n); }
 KP_FN void kp_skip(KpS &s, int n)                                      /* 0 <= n <= 32 */
 {
     s.sh += (uint32_t)n;
-    if (s.sh >= 32) { s.sh -= 32; s.w0 = s.w1; s.w1 = s.w2; s.w2 = kp_word(s, s.wpos); s.wpos++; }
+    if (s.sh >= 32) {                                              /* once per 32 bits: a branch, not a predicated block in every skip */
+        KP_COLD();
+        s.sh -= 32; s.w0 = s.w1; s.w1 = s.w2; s.w2 = kp_word(s, s.wpos); s.wpos++;
+    }
 }
 KP_FN uint32_t kp_get(KpS &s, int n) { uint32_t v; if (n == 0) return 0; v = kp_peek(s, n); kp_skip(s, n); return v; }
 KP_FN uint32_t kp_get1(KpS &s) { const uint32_t v = kp_peek32(s) >> 31; kp_skip(s, 1); return v; }
@@ -852,6 +868,7 @@ KP_FN void kp_parse_picture(int lane, const KpPic &p, KpStage *st, const KpTable
             s.avail = kp_stage_derive(lane, st, sl->slice_id, s.is_p, s.mbx, s.mby, W);
             KP_SYNC();
             if (lane == 0) {
+                s.T = kp_pin_shared(T); s.st = kp_pin_shared(st);
                 rc = kp_parse_mb(s);
                 n_slots = s.n_slots; coef_off = s.coef_used; ipcm = s.ipcm_byte;
                 if (rc == KP_MB_OK) {
