@@ -10,6 +10,7 @@
  */
 #include <stdlib.h>
 #include <stdio.h>
+#include <stddef.h>
 #include <string.h>
 #include "h264_internal.h"
 #include "cavlc_tables.h"
@@ -120,9 +121,21 @@ void h264_kp_fill_tables(KpTables *t)
         for (blk = 0; blk < 4; blk++) t->ident4[blk] = (uint8_t)blk;
         for (blk = 0; blk < 16; blk++) t->cbp_luma[blk] = (uint16_t)(((blk & 1) ? 0x000f : 0) | ((blk & 2) ? 0x00f0 : 0) | ((blk & 4) ? 0x0f00 : 0) | ((blk & 8) ? 0xf000 : 0));
         /* residual steps: 0 Intra16x16 DC (nC of block 0), 1..16 luma, 17/18 chroma DC, 19..26 chroma AC (grid cells 40.. = KpStage.cc) */
-        t->step_desc[0] = (uint32_t)t->lc_idx[0] | (8u << 8) | (0u << 12);
-        for (blk = 0; blk < 16; blk++) t->step_desc[1 + blk] = (uint32_t)t->lc_idx[blk] | (8u << 8) | (1u << 12) | ((uint32_t)blk << 16);
-        t->step_desc[17] = t->step_desc[18] = 8u | (4u << 8) | (2u << 12);
-        for (blk = 0; blk < 8; blk++) t->step_desc[19 + blk] = (uint32_t)(40 + 12 * (blk >> 2) + 5 + (blk & 1) + 4 * ((blk >> 1) & 1)) | (4u << 8) | (3u << 12) | ((uint32_t)(16 + blk) << 16);
+        {
+            const uint32_t zz = (uint32_t)offsetof(KpTables, zigzag), id = (uint32_t)offsetof(KpTables, ident4);
+            t->step_desc[0][0] = (uint32_t)t->lc_idx[0] | (8u << 8) | (0u << 12);
+            t->step_desc[0][1] = zz | (16u << 16);
+            for (blk = 0; blk < 16; blk++) {
+                t->step_desc[1 + blk][0] = (uint32_t)t->lc_idx[blk] | (8u << 8) | (1u << 12) | ((uint32_t)blk << 16);
+                t->step_desc[1 + blk][1] = zz | (16u << 16);                       /* Intra16x16: one less, from scan position 1 (kp_parse_residual) */
+            }
+            t->step_desc[17][0] = t->step_desc[18][0] = 8u | (4u << 8) | (2u << 12);
+            t->step_desc[17][1] = id | (4u << 16);
+            t->step_desc[18][1] = id | (4u << 16) | (4u << 24);                    /* Cr DC behind Cb DC in the same slot */
+            for (blk = 0; blk < 8; blk++) {
+                t->step_desc[19 + blk][0] = (uint32_t)(40 + 12 * (blk >> 2) + 5 + (blk & 1) + 4 * ((blk >> 1) & 1)) | (4u << 8) | (3u << 12) | ((uint32_t)(16 + blk) << 16);
+                t->step_desc[19 + blk][1] = (zz + 1u) | (15u << 16);
+            }
+        }
     }
 }

@@ -973,9 +973,18 @@ extern "C" h264b200_engine_t *h264b200EngineCreateEx(int device, uint32_t flags)
     if (e->tl_path) { cudaEventCreate(&e->tl_base); cudaEventRecord(e->tl_base, 0); e->tl_host0 = host_ms_now(); }
     { const char *c = getenv("H264B200_WF_CAP"); if (c && atoi(c) > 0 && atoi(c) <= 64) e->wf_cap = (uint32_t)atoi(c); }
     CUDA_TRY(cudaStreamCreateWithFlags(&e->s_h2d, cudaStreamNonBlocking), { delete e; return NULL; });
-    CUDA_TRY(cudaStreamCreateWithFlags(&e->s_comp, cudaStreamNonBlocking), { delete e; return NULL; });
-    CUDA_TRY(cudaStreamCreateWithFlags(&e->s_d2h, cudaStreamNonBlocking), { delete e; return NULL; });
-    for (int k = 0; k < NPAR; k++) CUDA_TRY(cudaStreamCreateWithFlags(&e->s_parse[k], cudaStreamNonBlocking), { delete e; return NULL; });
+    {   /* The reconstruction stream gets the highest priority, the Kp streams the lowest: a Kp launch lives for ~0.2 s in
+         * persistent CTAs, a reconstruction round for a few milliseconds in thousands of short ones; whenever an SM has room
+         * the block scheduler should give it to the round that a stream's next picture (and the host's next output) waits for.
+         * H264B200_PRIO=0 creates every stream at the default priority. */
+        int lo = 0, hi = 0;
+        const char *pe = getenv("H264B200_PRIO");
+        const bool prio = !(pe && atoi(pe) == 0);
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);         /* lo: numerically largest = least urgent */
+        CUDA_TRY(cudaStreamCreateWithPriority(&e->s_comp, cudaStreamNonBlocking, prio ? hi : 0), { delete e; return NULL; });
+        CUDA_TRY(cudaStreamCreateWithPriority(&e->s_d2h, cudaStreamNonBlocking, prio ? hi : 0), { delete e; return NULL; });
+        for (int k = 0; k < NPAR; k++) CUDA_TRY(cudaStreamCreateWithPriority(&e->s_parse[k], cudaStreamNonBlocking, prio ? lo : 0), { delete e; return NULL; });
+    }
     CUDA_TRY(cudaEventCreateWithFlags(&e->ev_h2d, cudaEventDisableTiming), { delete e; return NULL; });
     CUDA_TRY(cudaEventCreateWithFlags(&e->ev_comp, cudaEventDisableTiming), { delete e; return NULL; });
     CUDA_TRY(cudaEventCreateWithFlags(&e->ev_gate, cudaEventDisableTiming), { delete e; return NULL; });

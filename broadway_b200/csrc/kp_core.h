@@ -289,9 +289,8 @@ KP_FN int kp_nc_avg(int a, int b)
 /* residual( ) of 7.3.5.3 as ONE loop with ONE call of the block decoder (code size: the kernel has to live in the
  * instruction cache), over exactly the blocks the syntax holds: bit `step` of `todo` — step 0 = Intra16x16 DC, 1..16 =
  * luma4x4BlkIdx 0..15 (set by coded_block_pattern per 8x8 quadrant), 17/18 = chroma DC Cb/Cr, 19..26 = chroma AC.  What a
- * step needs (its cell in the TotalCoeff grids, the distance to the cell above, its kind, its bit in resid_mask) is one
- * word of KpTables.step_desc.  Slot order and masks as include/h264b200_records.h says.  Returns 0 / -1. */
-#define KP_SD(grid_idx, up, kind, bit) ((uint32_t)(grid_idx) | ((uint32_t)(up) << 8) | ((uint32_t)(kind) << 12) | ((uint32_t)(bit) << 16))
+ * step needs (its cell in the TotalCoeff grids, the distance to the cell above, its kind, its bit in resid_mask, its scan
+ * table and coefficient count) is one 64-bit entry of KpTables.step_desc, so the loop head has no branches.  Slot order and masks as include/h264b200_records.h says.  Returns 0 / -1. */
 KP_HOT int kp_parse_residual(KpS &s, int cbp, int i16)
 {
     KpStage *st = s.st;
@@ -305,20 +304,16 @@ KP_HOT int kp_parse_residual(KpS &s, int cbp, int i16)
 KP_NOUNROLL
     while (todo) {
         const int step = KP_CTZ(todo);
-        const uint32_t dsc = T->step_desc[step];
+        const uint32_t dsc = T->step_desc[step][0], dsc2 = T->step_desc[step][1];
         const int kind = (int)((dsc >> 12) & 3);
+        const int lum16 = kind == 1 ? i16 : 0;                    /* a luma block of an Intra16x16 macroblock: 15 coefficients from scan position 1 */
         uint8_t *g = st->grid + (dsc & 0xff);
-        int nc, tc, maxc;
-        int16_t *out = st->slots + slot * 16;
-        const uint8_t *scan = T->zigzag + 1;
+        const int maxc = (int)((dsc2 >> 16) & 0xff) - lum16;
+        const uint8_t *scan = (const uint8_t *)T + (dsc2 & 0xffffu) + lum16;
+        int16_t *out = st->slots + (uint32_t)((kind == 1 && dc_nz) ? step : (int)slot) * 16 + (dsc2 >> 24);   /* Intra16x16 with DC: slot 1 + luma4x4BlkIdx */
+        int nc = kp_nc_avg(g[-1], *(g - ((dsc >> 8) & 15))), tc;
+        if (kind == 2) nc = -1;
         todo &= todo - 1;
-        if (kind == 2) { nc = -1; maxc = 4; scan = T->ident4; out += 4 * (step - 17); }
-        else {
-            nc = kp_nc_avg(g[-1], *(g - ((dsc >> 8) & 15)));
-            maxc = 15;
-            if (kind == 0) { maxc = 16; scan = T->zigzag; }
-            else if (kind == 1) { maxc = 16 - i16; scan = T->zigzag + i16; if (dc_nz) out = st->slots + step * 16; }   /* slot 1 + luma4x4BlkIdx */
-        }
         /* two blocks out of three are empty, and with sparse neighbours that is the single bit '1' */
         if ((unsigned)nc < 2u && (int32_t)kp_peek32(s) < 0) { kp_skip(s, 1); tc = 0; }
         else {

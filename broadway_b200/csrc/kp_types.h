@@ -23,7 +23,8 @@ typedef struct {
     uint8_t ident4[4];           /* "scan" of a chroma DC block */
     uint8_t pad[8];
     uint16_t cbp_luma[16];       /* coded_block_pattern & 15 -> the luma4x4BlkIdx set of its 8x8 quadrants */
-    uint32_t step_desc[28];      /* per residual step (kp_core.h kp_parse_residual): grid cell | up distance << 8 | kind << 12 | mask bit << 16 */
+    uint32_t step_desc[28][2];   /* per residual step (kp_core.h kp_parse_residual): [0] grid cell | up distance << 8 | kind << 12 | mask bit << 16;
+                                    [1] byte offset of the scan table in this struct | max coefficients << 16 | offset into the slot << 24 */
 } KpTables;
 
 typedef struct {                 /* == h264_mbctx_t (h264_internal.h) */
