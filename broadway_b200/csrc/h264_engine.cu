@@ -161,6 +161,7 @@ struct h264b200_engine {
      * written as CSV when the engine is destroyed (what nsys would show; there is no nsys in the image) */
     struct TlEntry { int kind; uint32_t n; double host_ms; cudaEvent_t a, b; };
     std::vector<TlEntry> tl; const char *tl_path; cudaEvent_t tl_base; double tl_host0;
+    uint32_t kp_sms;               /* > 0: SMs a Kp launch may take for itself (kp_parse<32, 1>); 0: Kp shares the SMs (kp_parse<8, 4>) */
     int kp_on_comp;                /* H264B200_KP_ON_COMP=1: Kp launches go to the reconstruction stream (serialised with K1..K4) instead of overlapping them */
     uint32_t wf_cap;               /* CTAs per SM the wavefront kernels K3 / K4 are launched with at most (tickets hand out the rows); H264B200_WF_CAP, default 16 */
     cudaStream_t s_h2d, s_comp, s_d2h, s_parse[NPAR];
@@ -177,6 +178,8 @@ struct h264b200_engine {
     uint32_t parse_seq;
     KpTables *d_tables;
     uint32_t window, parse_threshold;
+    uint32_t n_inst_hint; size_t inst_budget;   /* h264b200EngineSetStreams: instances to expect, device bytes each may spend on look-ahead buffers */
+    uint32_t eff_window;           /* the look-ahead the instances created so far can actually hold (<= window) */
     uint32_t *d_err, *h_err;
     unsigned long long *d_trace; int trace_left;
     h264b200_stats_t st;
@@ -269,10 +272,19 @@ static void launch_kernels(h264b200_engine *e, const Batch &b, const BatchPlan &
     if (tev) cudaEventRecord(tev[4], s);
 }
 
-static uint32_t kp_grid(h264b200_engine *e, uint32_t n_pics)
+/* Kp launch: exclusive mode (kp_sms > 0, the default of batched device-parse engines) = CTAs that fill an SM each, at most
+ * kp_sms of them, so the launch owns those SMs and the rest of the device stays with K1..K4 (kp_parse.cuh); shared mode =
+ * 8-warp CTAs on every SM. */
+static void kp_launch(h264b200_engine *e, const KpBatch &kb, cudaStream_t s)
 {
-    uint32_t blocks = (n_pics + KP_WARPS - 1) / KP_WARPS, cap = (uint32_t)e->sm_count * KP_MINB;
-    return blocks < cap ? blocks : cap;
+    if (e->kp_sms > 0) {
+        uint32_t blocks = (kb.n_pics + 31) / 32;
+        if (blocks > e->kp_sms) blocks = e->kp_sms;
+        kp_parse<32, 1><<<blocks, 1024, KP_SMEM_BYTES(32), s>>>(kb);
+    } else {
+        uint32_t blocks = (kb.n_pics + 7) / 8, cap = (uint32_t)e->sm_count * 4;
+        kp_parse<8, 4><<<blocks < cap ? blocks : cap, 256, KP_SMEM_BYTES(8), s>>>(kb);
+    }
 }
 
 static double host_ms_now() { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return 1e3 * (double)t.tv_sec + 1e-6 * (double)t.tv_nsec; }
@@ -309,7 +321,7 @@ static int launch_parse(h264b200_engine *e, std::vector<PicBuf *> &list)
     const uint32_t n = (uint32_t)list.size();
     const bool retain = (e->flags & H264B200_ENGINE_RETAIN) != 0;
     ParseScratch &ps = e->pscr[e->next_pscr];
-    const int stream = e->kp_on_comp ? -1 : e->next_pscr;
+    const int stream = e->kp_on_comp ? -1 : e->kp_sms > 0 ? 0 : e->next_pscr;   /* exclusive mode: one Kp launch at a time (it owns its SMs) */
     e->next_pscr = (e->next_pscr + 1) % NPAR;
     if (ps.used) cudaEventSynchronize(ps.done);
     if (ps.cap < n) {
@@ -367,7 +379,7 @@ static int launch_parse(h264b200_engine *e, std::vector<PicBuf *> &list)
     cudaMemsetAsync(d_ticket, 0, 64, s);
     KpBatch kb; kb.pics = d_pics; kb.n_pics = n; kb.ticket = d_ticket; kb.tables = e->d_tables;
     tl_begin(e, 1, n, s);
-    kp_parse<<<kp_grid(e, n), KP_WARPS * 32, 0, s>>>(kb);
+    kp_launch(e, kb, s);
     tl_end(e, s);
     e->st.kernel_launches++; e->st.kp_launches++; e->st.kp_pictures += n;
     cudaEventRecord(ps.done, s); ps.used = true;
@@ -642,7 +654,20 @@ static void *be_inst_create(h264_backend_t *be, uint32_t wm, uint32_t hm, uint32
     if (n_slots > H264_MAX_SLOTS) return NULL;
     set_device(e);
     const int dev_parse = (e->flags & H264B200_ENGINE_DEVICE_PARSE) != 0;
-    const int n_bufs = dev_parse ? (int)e->window + 2 : NBUF;
+    int n_bufs = dev_parse ? (int)e->window + 2 : NBUF;
+    if (dev_parse && e->inst_budget) {
+        /* the look-ahead window is a wish: 4K pictures cost 35 MB of worst-case parse output each, and hundreds of
+         * instances must fit the device together */
+        const size_t per_buf = parse_bytes_per_buf(wm * hm) + block_cap0(wm * hm);
+        const size_t fit = e->inst_budget / per_buf;
+        if ((size_t)n_bufs > fit) n_bufs = fit < 4 ? 4 : (int)fit;
+        std::lock_guard<std::mutex> lk(e->mu);
+        if ((uint32_t)(n_bufs - 2) < e->eff_window) {
+            e->eff_window = (uint32_t)(n_bufs - 2);
+            const uint32_t thr = e->n_inst_hint * (e->eff_window >= 4 ? e->eff_window / 2 : 1);
+            if (thr < e->parse_threshold) e->parse_threshold = thr;
+        }
+    }
     {   /* reuse a pooled instance of the same geometry */
         std::lock_guard<std::mutex> lk(e->mu);
         for (size_t i = 0; i < e->pool.size(); i++) {
@@ -959,7 +984,7 @@ extern "C" h264b200_engine_t *h264b200EngineCreateEx(int device, uint32_t flags)
     if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
     h264b200_engine *e = new h264b200_engine();
     e->device = device; e->flags = flags; e->next_scr = 0; e->next_pscr = 0; e->parse_seq = 0;
-    e->window = 1; e->parse_threshold = 1;
+    e->window = 1; e->eff_window = 1; e->parse_threshold = 1; e->n_inst_hint = 0; e->inst_budget = 0;
     memset(&e->st, 0, sizeof e->st); memset(e->scr, 0, sizeof e->scr); memset(e->pscr, 0, sizeof e->pscr);
     memset(e->k_ms, 0, sizeof e->k_ms); memset(e->k_bytes, 0, sizeof e->k_bytes); memset(e->k_launches, 0, sizeof e->k_launches);
     CUDA_TRY(cudaSetDevice(device), { delete e; return NULL; });
@@ -968,6 +993,14 @@ extern "C" h264b200_engine_t *h264b200EngineCreateEx(int device, uint32_t flags)
     e->sm_count = p.multiProcessorCount;
     e->wf_cap = 16;
     { const char *c = getenv("H264B200_KP_ON_COMP"); e->kp_on_comp = c && atoi(c) > 0; }
+    {   /* exclusive Kp launches for batched device-parse engines: three quarters of the SMs (112 of 148: the share of Kp in the
+         * device work of the default workload, 16.5 of 22 ms per 256 pictures); H264B200_KP_SMS overrides, 0 = shared mode */
+        const char *c = getenv("H264B200_KP_SMS");
+        e->kp_sms = (flags & H264B200_ENGINE_BATCHED) && (flags & H264B200_ENGINE_DEVICE_PARSE) ? (uint32_t)(e->sm_count * 3 / 4 + 1) : 0;
+        if (c) e->kp_sms = (uint32_t)atoi(c) < (uint32_t)e->sm_count ? (uint32_t)atoi(c) : (uint32_t)e->sm_count;
+        CUDA_TRY(cudaFuncSetAttribute(kp_parse<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KP_SMEM_BYTES(32)), { delete e; return NULL; });
+        CUDA_TRY(cudaFuncSetAttribute(kp_parse<8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KP_SMEM_BYTES(8)), { delete e; return NULL; });
+    }
     e->tl_path = getenv("H264B200_TIMELINE");
     if (e->tl_path && !*e->tl_path) e->tl_path = nullptr;
     if (e->tl_path) { cudaEventCreate(&e->tl_base); cudaEventRecord(e->tl_base, 0); e->tl_host0 = host_ms_now(); }
@@ -1099,9 +1132,24 @@ extern "C" void h264b200EngineSetWindow(h264b200_engine_t *e, uint32_t depth, ui
     if (!e) return;
     std::lock_guard<std::mutex> lk(e->mu);
     e->window = depth ? (depth > 64 ? 64 : depth) : 1;
+    e->eff_window = e->window;
     e->parse_threshold = parse_threshold ? parse_threshold : 1;
 }
-extern "C" uint32_t h264b200EngineWindow(h264b200_engine_t *e) { return e ? e->window : 0; }
+extern "C" uint32_t h264b200EngineWindow(h264b200_engine_t *e) { if (!e) return 0; std::lock_guard<std::mutex> lk(e->mu); return e->eff_window; }
+/* How many instances are going to share the engine: each may spend an equal part of 60 % of the free device memory on its
+ * look-ahead buffers (the rest stays for frame pools and scratch); instances created afterwards shrink their window to that. */
+extern "C" void h264b200EngineSetStreams(h264b200_engine_t *e, uint32_t n_streams)
+{
+    if (!e || !n_streams) return;
+    set_device(e);
+    size_t fr = 0, tot = 0;
+    if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) return;
+    std::lock_guard<std::mutex> lk(e->mu);
+    e->n_inst_hint = n_streams;
+    e->inst_budget = (size_t)((double)fr * 0.6) / n_streams;
+}
+/* pictures one Kp launch parses at full rate: one per warp of the SMs it owns (0: no such limit) */
+extern "C" uint32_t h264b200EngineParseSlots(h264b200_engine_t *e) { return e ? e->kp_sms * 32u : 0; }
 
 extern "C" void h264b200EngineSync(h264b200_engine_t *e)
 {
@@ -1162,7 +1210,7 @@ extern "C" u32 h264b200EngineReplay(h264b200_engine_t *e, u32 reps, int time_ker
                 if (r->wait_round >= 0) cudaStreamWaitEvent(s, e->retained[(size_t)r->wait_round]->ev, 0);
                 cudaMemsetAsync(r->kp.ticket, 0, 64, s);
                 if (tev) cudaEventRecord(tev[0], s);
-                kp_parse<<<kp_grid(e, r->kp.n_pics), KP_WARPS * 32, 0, s>>>(r->kp);
+                kp_launch(e, r->kp, s);
                 if (tev) cudaEventRecord(tev[1], s);
                 cudaEventRecord(r->ev, s);
                 e->st.kernel_launches++; e->st.kp_launches++; e->st.kp_pictures += r->kp.n_pics;

@@ -265,6 +265,10 @@ static void *dev_worker_main(void *arg)
             sched_yield();
         }
         if (s->inited) {
+            if (round < 4) {                                      /* the instances' buffers may hold less than was asked for */
+                const uint32_t wnd = h264b200EngineWindow(r->e);
+                if (wnd < s->depth) { s->depth = wnd; if (s->chunk > (wnd >= 4 ? wnd / 2 : 1)) s->chunk = wnd >= 4 ? wnd / 2 : 1; }
+            }
             /* drain: nothing of the stream is left to launch, or the engine could launch nothing last time (a picture may be
              * held back by an output we have not released) */
             activity += dev_consume(w, s, idx, (s->finished && !h264b200PicturesPending(&s->st)) || __atomic_load_n(&r->force_wait, __ATOMIC_ACQUIRE));
@@ -311,14 +315,21 @@ int h264b200DecodeStreams(h264b200_engine_t *e, const h264b200_stream_t *streams
     pthread_mutex_init(&r.mu, NULL);
     dev = (h264b200EngineFlags(e) & H264B200_ENGINE_DEVICE_PARSE) != 0;
     if (dev) {
-        /* look-ahead per stream: enough pictures in flight for kernel Kp (thousands), within what the engine can hold */
-        const char *wenv = getenv("H264B200_WINDOW");
-        depth = wenv && atoi(wenv) > 0 ? (uint32_t)atoi(wenv) : 16;
-        {   /* pictures per stream and Kp launch: a quarter of the window unless H264B200_KP_CHUNK says otherwise */
-            const char *cenv = getenv("H264B200_KP_CHUNK");
-            chunk = cenv && atoi(cenv) > 0 ? (uint32_t)atoi(cenv) : (depth >= 4 ? depth / 4 : 1);
-            if (chunk > depth) chunk = depth;
-        }
+        /* Look-ahead per stream and pictures per stream in one Kp launch.  A Kp launch that owns SMs (h264b200EngineParseSlots)
+         * parses one picture per warp slot, and a picture takes the same ~0.25 s whether the launch is full or not: the
+         * launches are sized to fill the slots exactly (more pictures than slots would cost a second pass of the same
+         * length), and the window holds one launch being parsed, the next one being scanned, and the pictures parsed
+         * but not yet reconstructed.  H264B200_WINDOW / H264B200_KP_CHUNK override. */
+        const char *wenv = getenv("H264B200_WINDOW"), *cenv = getenv("H264B200_KP_CHUNK");
+        const uint32_t slots = h264b200EngineParseSlots(e);
+        chunk = slots >= n_streams ? slots / n_streams : 0;
+        if (chunk > 16) chunk = 16;
+        depth = chunk ? 2 * chunk + 4 : 16;
+        if (!chunk) chunk = 4;
+        if (wenv && atoi(wenv) > 0) depth = (uint32_t)atoi(wenv);
+        if (cenv && atoi(cenv) > 0) chunk = (uint32_t)atoi(cenv);
+        if (chunk > depth) chunk = depth;
+        h264b200EngineSetStreams(e, n_streams);
         h264b200EngineSetWindow(e, depth, n_streams * chunk);
         depth = h264b200EngineWindow(e);
     }

@@ -2,9 +2,9 @@
  * k0_jobs, which hands Kp's per-picture results (class counts, concealment list, status words) to the job table the
  * reconstruction kernels K1..K4 read.
  *
- * Launch shape: persistent CTAs of KP_WARPS warps; a warp takes pictures from an atomic ticket until none is left, so a
+ * Launch shape: persistent CTAs; a warp takes pictures from an atomic ticket until none is left, so a
  * launch over more pictures than resident warps stays balanced.  Per CTA the host parser's look-up tables (25 KB,
- * KpTables) are copied into shared memory once; per warp 1.8 KB of staging (KpStage).  Only lane 0 walks the syntax —
+ * KpTables) are copied into shared memory once; per warp 2.9 KB of staging (KpStage).  Only lane 0 walks the syntax —
  * the bitstream is serial — so the kernel is bound by dependent-instruction latency, not by HBM: what makes it pay is
  * that thousands of pictures (every picture of the look-ahead window of every stream) are in flight at once, which is
  * parallelism the host cores do not have.
@@ -13,13 +13,13 @@
 #include "k_common.cuh"
 #include "kp_core.h"
 
-#ifndef KP_WARPS
-#define KP_WARPS 8
-#endif
-#ifndef KP_MINB
-#define KP_MINB 4
-#endif
-
+/* Two launch shapes:
+ *   kp_parse<8, 4>   CTAs of 8 warps, 4 per SM: Kp shares every SM with whatever else runs (the synchronous API, small batches);
+ *   kp_parse<32, 1>  CTAs of 32 warps x 64 registers = a whole SM's register file: ONE CTA per SM and nothing else fits beside
+ *                    it.  A launch of n CTAs therefore takes n SMs for itself and leaves the other SMs entirely to the
+ *                    reconstruction kernels — spatial partitioning by resource exhaustion.  Time-sharing the SMs instead
+ *                    costs both sides (measured: K4 runs 5x, K2 3x slower next to Kp's warps, Kp 1.6x), 17 % of the
+ *                    device's throughput; see DESIGN.md section 5. */
 struct KpBatch {
     const KpPic *pics;
     uint32_t n_pics;
@@ -27,10 +27,14 @@ struct KpBatch {
     const KpTables *tables;        /* device copy of the host-built tables */
 };
 
-__global__ void __launch_bounds__(KP_WARPS * 32, KP_MINB) kp_parse(KpBatch b)
+#define KP_SMEM_BYTES(warps) (sizeof(KpTables) + (size_t)(warps) * sizeof(KpStage))
+
+template <int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) kp_parse(KpBatch b)
 {
-    __shared__ __align__(16) KpTables T;
-    __shared__ __align__(16) KpStage stage[KP_WARPS];
+    extern __shared__ __align__(16) unsigned char kp_smem[];
+    KpTables &T = *reinterpret_cast<KpTables *>(kp_smem);
+    KpStage *stage = reinterpret_cast<KpStage *>(kp_smem + sizeof(KpTables));
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(b.tables);
         uint4 *dst = reinterpret_cast<uint4 *>(&T);
@@ -48,6 +52,7 @@ __global__ void __launch_bounds__(KP_WARPS * 32, KP_MINB) kp_parse(KpBatch b)
         kp_parse_picture(lane, p, st, &T);
     }
 }
+static_assert(sizeof(KpTables) % 16 == 0 && sizeof(KpStage) % 16 == 0, "shared memory layout of kernel Kp");
 
 /* After Kp, before K1: copy what the parse found out about each picture into its job, and put the status words behind
  * the frame so that they travel to the host with it. */

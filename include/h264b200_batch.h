@@ -67,7 +67,11 @@ u32  h264b200EngineAdvance(h264b200_engine_t *e);
 /* look-ahead of the device-parse path: how many pictures per instance may be queued (parse buffers are allocated for
  * depth + 2), and how many queued pictures make kernel Kp worth launching.  Call before the instances are created. */
 void h264b200EngineSetWindow(h264b200_engine_t *e, uint32_t depth, uint32_t parse_threshold);
-uint32_t h264b200EngineWindow(h264b200_engine_t *e);
+uint32_t h264b200EngineWindow(h264b200_engine_t *e);   /* the look-ahead the instances can actually hold: <= the depth asked for */
+/* number of instances about to share the engine: bounds the device memory each spends on look-ahead buffers (call before they are created) */
+void h264b200EngineSetStreams(h264b200_engine_t *e, uint32_t n_streams);
+/* pictures one launch of kernel Kp parses at full rate (one per warp of the SMs the launch owns); 0: no such limit */
+uint32_t h264b200EngineParseSlots(h264b200_engine_t *e);
 
 /* ---- output formatting on the device (K5) ----
  * H264B200_OUT_I420 (default): the reference's output, uncropped MB-aligned planar I420.
