@@ -648,6 +648,14 @@ static uint32_t advance_all_locked(h264b200_engine *e)
 
 /* ------------------------------------------------------- backend callbacks */
 static void inst_free(Inst *in);
+/* engine mutex held: the look-ahead the runner may use is what the smallest instance can hold */
+static void note_window(h264b200_engine *e, const Inst *in)
+{
+    if (!in->dev_parse || (uint32_t)(in->n_bufs - 2) >= e->eff_window) return;
+    e->eff_window = (uint32_t)(in->n_bufs - 2);
+    const uint32_t thr = (e->n_inst_hint ? e->n_inst_hint : 1) * (e->eff_window >= 4 ? e->eff_window / 2 : 1);
+    if (thr < e->parse_threshold) e->parse_threshold = thr;
+}
 static void *be_inst_create(h264_backend_t *be, uint32_t wm, uint32_t hm, uint32_t n_slots)
 {
     h264b200_engine *e = (h264b200_engine *)be->ctx;
@@ -661,18 +669,13 @@ static void *be_inst_create(h264_backend_t *be, uint32_t wm, uint32_t hm, uint32
         const size_t per_buf = parse_bytes_per_buf(wm * hm) + block_cap0(wm * hm);
         const size_t fit = e->inst_budget / per_buf;
         if ((size_t)n_bufs > fit) n_bufs = fit < 4 ? 4 : (int)fit;
-        std::lock_guard<std::mutex> lk(e->mu);
-        if ((uint32_t)(n_bufs - 2) < e->eff_window) {
-            e->eff_window = (uint32_t)(n_bufs - 2);
-            const uint32_t thr = e->n_inst_hint * (e->eff_window >= 4 ? e->eff_window / 2 : 1);
-            if (thr < e->parse_threshold) e->parse_threshold = thr;
-        }
     }
     {   /* reuse a pooled instance of the same geometry */
         std::lock_guard<std::mutex> lk(e->mu);
         for (size_t i = 0; i < e->pool.size(); i++) {
             Inst *c = e->pool[i];
-            if (c->wm == wm && c->hm == hm && c->n_slots == n_slots && c->dev_parse == dev_parse && c->n_bufs == n_bufs) {
+            if (c->wm == wm && c->hm == hm && c->n_slots == n_slots && c->dev_parse == dev_parse && (dev_parse ? c->n_bufs >= 4 : c->n_bufs == n_bufs)) {
+                note_window(e, c);
                 e->pool.erase(e->pool.begin() + i);
                 memset(c->slot_flags, 0, sizeof c->slot_flags); memset(c->slot_qgen, 0, sizeof c->slot_qgen); memset(c->slot_lgen, 0, sizeof c->slot_lgen);
                 memset(c->slot_popped, 0, sizeof c->slot_popped);
@@ -727,6 +730,7 @@ static void *be_inst_create(h264_backend_t *be, uint32_t wm, uint32_t hm, uint32
         }
     }
     std::lock_guard<std::mutex> lk(e->mu);
+    note_window(e, in);
     e->insts.push_back(in);
     return in;
 }
@@ -1136,7 +1140,7 @@ extern "C" void h264b200EngineSetWindow(h264b200_engine_t *e, uint32_t depth, ui
     e->parse_threshold = parse_threshold ? parse_threshold : 1;
 }
 extern "C" uint32_t h264b200EngineWindow(h264b200_engine_t *e) { if (!e) return 0; std::lock_guard<std::mutex> lk(e->mu); return e->eff_window; }
-/* How many instances are going to share the engine: each may spend an equal part of 60 % of the free device memory on its
+/* How many instances are going to share the engine: each may spend an equal part of half of the device memory on its
  * look-ahead buffers (the rest stays for frame pools and scratch); instances created afterwards shrink their window to that. */
 extern "C" void h264b200EngineSetStreams(h264b200_engine_t *e, uint32_t n_streams)
 {
@@ -1146,7 +1150,7 @@ extern "C" void h264b200EngineSetStreams(h264b200_engine_t *e, uint32_t n_stream
     if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) return;
     std::lock_guard<std::mutex> lk(e->mu);
     e->n_inst_hint = n_streams;
-    e->inst_budget = (size_t)((double)fr * 0.6) / n_streams;
+    e->inst_budget = (size_t)((double)tot * 0.5) / n_streams;      /* of the TOTAL: pooled instances of an earlier run already hold their share */
 }
 /* pictures one Kp launch parses at full rate: one per warp of the SMs it owns (0: no such limit) */
 extern "C" uint32_t h264b200EngineParseSlots(h264b200_engine_t *e) { return e ? e->kp_sms * 32u : 0; }
