@@ -57,7 +57,7 @@
 
 #define NBUF 3                 /* input buffers in flight per instance (host-parse; device-parse: look-ahead depth + 2) */
 #define NSCR 4                 /* batch scratch sets in flight per engine */
-#define NPAR 8                 /* Kp launches in flight per engine: one scratch set and one CUDA stream each, so that they overlap —
+#define NPAR 16                /* Kp launches in flight per engine: one scratch set and one CUDA stream each, so that they overlap —
                                   a launch over a quarter of the look-ahead window does not fill the SMs on its own */
 #define STAT_TAIL 128          /* bytes behind every frame: h264b200_picstat_t of the picture (device-parse), copied out with it */
 #define CTRL_HEAD 16           /* int32 words before the progress counters: [0] K3 ticket, [1] K4 ticket */
@@ -153,6 +153,7 @@ struct ParseScratch {              /* one Kp launch */
     uint32_t *d_ticket;
     cudaEvent_t done;              /* the launch has finished */
     bool used;
+    uint32_t ctas;                 /* exclusive mode: SMs the launch owns while it runs */
 };
 
 struct h264b200_engine {
@@ -275,12 +276,11 @@ static void launch_kernels(h264b200_engine *e, const Batch &b, const BatchPlan &
 /* Kp launch: exclusive mode (kp_sms > 0, the default of batched device-parse engines) = CTAs that fill an SM each, at most
  * kp_sms of them, so the launch owns those SMs and the rest of the device stays with K1..K4 (kp_parse.cuh); shared mode =
  * 8-warp CTAs on every SM. */
+static uint32_t kp_ctas(const h264b200_engine *e, uint32_t n_pics) { uint32_t b = (n_pics + 31) / 32; return b > e->kp_sms ? e->kp_sms : b; }
 static void kp_launch(h264b200_engine *e, const KpBatch &kb, cudaStream_t s)
 {
     if (e->kp_sms > 0) {
-        uint32_t blocks = (kb.n_pics + 31) / 32;
-        if (blocks > e->kp_sms) blocks = e->kp_sms;
-        kp_parse<32, 1><<<blocks, 1024, KP_SMEM_BYTES(32), s>>>(kb);
+        kp_parse<32, 1><<<kp_ctas(e, kb.n_pics), 1024, KP_SMEM_BYTES(32), s>>>(kb);
     } else {
         uint32_t blocks = (kb.n_pics + 7) / 8, cap = (uint32_t)e->sm_count * 4;
         kp_parse<8, 4><<<blocks < cap ? blocks : cap, 256, KP_SMEM_BYTES(8), s>>>(kb);
@@ -321,7 +321,7 @@ static int launch_parse(h264b200_engine *e, std::vector<PicBuf *> &list)
     const uint32_t n = (uint32_t)list.size();
     const bool retain = (e->flags & H264B200_ENGINE_RETAIN) != 0;
     ParseScratch &ps = e->pscr[e->next_pscr];
-    const int stream = e->kp_on_comp ? -1 : e->kp_sms > 0 ? 0 : e->next_pscr;   /* exclusive mode: one Kp launch at a time (it owns its SMs) */
+    const int stream = e->kp_on_comp ? -1 : e->next_pscr;
     e->next_pscr = (e->next_pscr + 1) % NPAR;
     if (ps.used) cudaEventSynchronize(ps.done);
     if (ps.cap < n) {
@@ -382,7 +382,7 @@ static int launch_parse(h264b200_engine *e, std::vector<PicBuf *> &list)
     kp_launch(e, kb, s);
     tl_end(e, s);
     e->st.kernel_launches++; e->st.kp_launches++; e->st.kp_pictures += n;
-    cudaEventRecord(ps.done, s); ps.used = true;
+    cudaEventRecord(ps.done, s); ps.used = true; ps.ctas = e->kp_sms ? kp_ctas(e, n) : 0;
     if (retain) {
         cudaEventRecord(ret->ev, s);
         ret->kp = kb;
@@ -620,7 +620,14 @@ static uint32_t advance_locked(h264b200_engine *e, bool force)
      * and one of the NPAR launch slots is free: up to NPAR launches overlap on the device, and the reconstruction
      * rounds of pictures parsed earlier run beside them */
     const ParseScratch &nps = e->pscr[e->next_pscr];
-    const bool slot_free = !nps.used || cudaEventQuery(nps.done) == cudaSuccess;
+    bool slot_free = !nps.used || cudaEventQuery(nps.done) == cudaSuccess;
+    if (slot_free && e->kp_sms && pl.size() >= e->parse_threshold) {
+        /* exclusive launches own their SMs: together they must stay within the SMs given to Kp, or the reconstruction
+         * rounds would find no SM until a launch ends */
+        uint32_t busy = 0;
+        for (int k = 0; k < NPAR; k++) if (e->pscr[k].used && e->pscr[k].ctas && cudaEventQuery(e->pscr[k].done) != cudaSuccess) busy += e->pscr[k].ctas;
+        if (busy + kp_ctas(e, (uint32_t)pl.size()) > e->kp_sms) slot_free = false;
+    }
     if (!pl.empty() && (force || head_unparsed || (pl.size() >= e->parse_threshold && slot_free))) {
         if (launch_parse(e, pl)) {
             for (PicBuf *p : pl) p->inst->slot_flags[p->in.cur_slot] |= 4;

@@ -315,17 +315,16 @@ int h264b200DecodeStreams(h264b200_engine_t *e, const h264b200_stream_t *streams
     pthread_mutex_init(&r.mu, NULL);
     dev = (h264b200EngineFlags(e) & H264B200_ENGINE_DEVICE_PARSE) != 0;
     if (dev) {
-        /* Look-ahead per stream and pictures per stream in one Kp launch.  A Kp launch that owns SMs (h264b200EngineParseSlots)
-         * parses one picture per warp slot, and a picture takes the same ~0.25 s whether the launch is full or not: the
-         * launches are sized to fill the slots exactly (more pictures than slots would cost a second pass of the same
-         * length), and the window holds one launch being parsed, the next one being scanned, and the pictures parsed
-         * but not yet reconstructed.  H264B200_WINDOW / H264B200_KP_CHUNK override. */
+        /* Look-ahead per stream and pictures per stream in one Kp launch; H264B200_WINDOW / H264B200_KP_CHUNK override. */
         const char *wenv = getenv("H264B200_WINDOW"), *cenv = getenv("H264B200_KP_CHUNK");
         const uint32_t slots = h264b200EngineParseSlots(e);
-        chunk = slots >= n_streams ? slots / n_streams : 0;
-        if (chunk > 16) chunk = 16;
-        depth = chunk ? 2 * chunk + 4 : 16;
-        if (!chunk) chunk = 4;
+        if (slots >= n_streams) {
+            /* exclusive Kp launches: `slots / n_streams` pictures of every stream are being parsed at any time (a picture
+             * takes ~0.22 s whatever the load); small launches (2 pictures per stream) keep the flow even and the window
+             * small: pictures in Kp + the next launch being scanned + those parsed and waiting for their round */
+            chunk = 2;
+            depth = slots / n_streams + chunk + 4;
+        } else { chunk = 4; depth = 16; }
         if (wenv && atoi(wenv) > 0) depth = (uint32_t)atoi(wenv);
         if (cenv && atoi(cenv) > 0) chunk = (uint32_t)atoi(cenv);
         if (chunk > depth) chunk = depth;
