@@ -27,9 +27,9 @@ static int find_box(span_t in, const char *type, span_t *out)
     while (off + 8 <= in.len) {
         uint64_t size = rd32(in.p + off);
         size_t hdr = 8;
-        if (size == 1) { if (off + 16 > in.len) return -1; size = rd64(in.p + off + 8); hdr = 16; }
+        if (size == 1) { if (in.len - off < 16) return -1; size = rd64(in.p + off + 8); hdr = 16; }
         else if (size == 0) size = in.len - off;
-        if (size < hdr || off + size > in.len) return -1;
+        if (size < hdr || size > in.len - off) return -1;      /* compared without a sum that could wrap (64-bit largesize) */
         if (!memcmp(in.p + off + 4, type, 4)) { out->p = in.p + off + hdr; out->len = (size_t)size - hdr; return 0; }
         off += (size_t)size;
     }
@@ -75,9 +75,9 @@ long h264b200Mp4ToAnnexB(const uint8_t *mp4, size_t len, uint8_t *out, size_t ca
     while (off + 8 <= trak_area.len) {
         uint64_t size = rd32(trak_area.p + off);
         size_t hdr = 8;
-        if (size == 1) { if (off + 16 > trak_area.len) return -1; size = rd64(trak_area.p + off + 8); hdr = 16; }
+        if (size == 1) { if (trak_area.len - off < 16) return -1; size = rd64(trak_area.p + off + 8); hdr = 16; }
         else if (size == 0) size = trak_area.len - off;
-        if (size < hdr || off + size > trak_area.len) return -1;
+        if (size < hdr || size > trak_area.len - off) return -1;
         if (!memcmp(trak_area.p + off + 4, "trak", 4)) {
             span_t trak; trak.p = trak_area.p + off + hdr; trak.len = (size_t)size - hdr;
             if (!open_track(trak, &t)) { found = 1; break; }
@@ -118,12 +118,13 @@ long h264b200Mp4ToAnnexB(const uint8_t *mp4, size_t len, uint8_t *out, size_t ca
         pos = t.stco.p ? rd32(t.stco.p + 8 + (size_t)(chunk - 1) * 4) : rd64(t.co64.p + 8 + (size_t)(chunk - 1) * 8);
         for (i = 0; i < per && sample < n_samples; i++, sample++) {
             uint32_t ssz = fixed_size ? fixed_size : rd32(t.stsz.p + 12 + (size_t)sample * 4);
-            uint64_t end = pos + ssz;
-            if (end > len) return -1;
+            uint64_t end;
+            if (pos > len || ssz > len - pos) return -1;        /* a chunk offset near 2^64 must not wrap pos + ssz */
+            end = pos + ssz;
             while (pos + (uint64_t)lsz <= end) {                /* length-prefixed NAL units (mp4.js:711-723) */
                 uint32_t n = lsz == 4 ? rd32(mp4 + pos) : lsz == 2 ? (((uint32_t)mp4[pos] << 8) | mp4[pos + 1]) : mp4[pos];
                 pos += (uint64_t)lsz;
-                if (pos + n > end) return -1;
+                if (n > end - pos) return -1;
                 if (n) PUT(mp4 + pos, n);
                 pos += n;
             }
