@@ -58,7 +58,7 @@ class RunStats(ctypes.Structure):
     _fields_ = [("pictures", ctypes.c_uint64), ("bytes_in", ctypes.c_uint64), ("bytes_out", ctypes.c_uint64),
                 ("err_mbs", ctypes.c_uint32), ("failed_streams", ctypes.c_uint32), ("rounds", ctypes.c_uint32),
                 ("threads", ctypes.c_uint32), ("seconds", ctypes.c_double), ("parse_seconds", ctypes.c_double),
-                ("wait_seconds", ctypes.c_double)]
+                ("wait_seconds", ctypes.c_double), ("host_streams", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
 
 
 PICTURE_CB = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p,

@@ -258,9 +258,13 @@ static int activate_param_sets(h264_decoder_t *d, uint32_t pps_id, int is_idr)
         if (!d->be) d->be = h264_default_backend();   /* CUDA engine; NULL (reason on stderr) without a usable GPU */
         if (!d->be) return -2;
         if (d->be_inst) { d->be->inst_destroy(d->be, d->be_inst); d->be_inst = NULL; }
-        d->be_inst = d->be->inst_create(d->be, d->width_mbs, d->height_mbs, d->n_slots);
-        if (!d->be_inst) return -2;
-        d->device_parse = d->be->block_grow && d->be->parse_mode;
+        {
+            const int host = d->force_host_parse && d->be->inst_create_ex;
+            d->be_inst = host ? d->be->inst_create_ex(d->be, d->width_mbs, d->height_mbs, d->n_slots, 1)
+                              : d->be->inst_create(d->be, d->width_mbs, d->height_mbs, d->n_slots);
+            if (!d->be_inst) return -2;
+            d->device_parse = d->be->block_grow && d->be->parse_mode && !host;
+        }
         d->pic = NULL;
         if (d->out_format && apply_output_format(d)) return -2;
     } else if ((int)pps_id != d->active_pps_id) {
@@ -742,6 +746,11 @@ u32 h264b200PicturesPending(storage_t *pStorage)
  * into decoder-owned scratch memory instead of in place (the reference always edits in place,
  * h264bsd_byte_stream.c:192-234; callers that share one read-only copy of a stream between instances need this). */
 void h264b200SetReadOnlyInput(storage_t *pStorage, u32 on) { h264_decoder_t *d = DEC(pStorage); if (d) d->ro_input = on != 0; }
+
+/* This instance parses slice data on the host cores even on a device-parse engine (call before the first parameter
+ * sets are activated).  Both parsers write the same records, so the pictures are the same either way; what changes is
+ * who does the work: h264b200DecodeStreams gives the otherwise idle parser threads a share of the streams. */
+void h264b200SetHostParse(storage_t *pStorage, u32 on) { h264_decoder_t *d = DEC(pStorage); if (d) d->force_host_parse = on != 0; }
 
 u32 h264b200DeviceParse(storage_t *pStorage) { h264_decoder_t *d = DEC(pStorage); return d ? (u32)d->device_parse : 0; }
 

@@ -663,13 +663,15 @@ static void note_window(h264b200_engine *e, const Inst *in)
     const uint32_t thr = (e->n_inst_hint ? e->n_inst_hint : 1) * (e->eff_window >= 4 ? e->eff_window / 2 : 1);
     if (thr < e->parse_threshold) e->parse_threshold = thr;
 }
-static void *be_inst_create(h264_backend_t *be, uint32_t wm, uint32_t hm, uint32_t n_slots)
+static void *be_inst_create_ex(h264_backend_t *be, uint32_t wm, uint32_t hm, uint32_t n_slots, int host_parse)
 {
     h264b200_engine *e = (h264b200_engine *)be->ctx;
     if (n_slots > H264_MAX_SLOTS) return NULL;
     set_device(e);
-    const int dev_parse = (e->flags & H264B200_ENGINE_DEVICE_PARSE) != 0;
-    int n_bufs = dev_parse ? (int)e->window + 2 : NBUF;
+    /* host_parse: an instance of a device-parse engine that brings its own records (h264b200SetHostParse); its pictures
+     * join the same reconstruction rounds, they just have nothing for kernel Kp to do */
+    const int dev_parse = (e->flags & H264B200_ENGINE_DEVICE_PARSE) != 0 && !host_parse;
+    int n_bufs = dev_parse ? (int)e->window + 2 : host_parse ? NBUF + 1 : NBUF;   /* host share of a device-parse run: one picture queued ahead of the round in flight */
     if (dev_parse && e->inst_budget) {
         /* the look-ahead window is a wish: 4K pictures cost 35 MB of worst-case parse output each, and hundreds of
          * instances must fit the device together */
@@ -741,6 +743,8 @@ static void *be_inst_create(h264_backend_t *be, uint32_t wm, uint32_t hm, uint32
     e->insts.push_back(in);
     return in;
 }
+
+static void *be_inst_create(h264_backend_t *be, uint32_t wm, uint32_t hm, uint32_t n_slots) { return be_inst_create_ex(be, wm, hm, n_slots, 0); }
 
 static void inst_free(Inst *in)
 {
@@ -1068,7 +1072,7 @@ extern "C" h264b200_engine_t *h264b200EngineCreateEx(int device, uint32_t flags)
     e->be.set_output = be_set_output;
     e->be.block_grow = be_block_grow; e->be.frame_status = be_frame_status; e->be.frame_release = be_frame_release;
     e->be.inst_pending = be_inst_pending;
-    e->be.frame_state = be_frame_state;
+    e->be.frame_state = be_frame_state; e->be.inst_create_ex = be_inst_create_ex;
     e->be.parse_mode = (flags & H264B200_ENGINE_DEVICE_PARSE) != 0;
     e->be.destroy = be_destroy; e->be.ctx = e;
     return e;

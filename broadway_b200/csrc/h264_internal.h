@@ -181,6 +181,9 @@ struct h264_backend {
     int parse_mode;
     /* optional, never blocks: 0 generation `gen` of `slot` is in its host mirror, 1 launched but still in flight, 2 not launched yet, -1 error */
     int (*frame_state)(h264_backend_t *be, void *inst, int slot, uint32_t gen);
+    /* optional: inst_create with the parse mode chosen per instance (host_parse != 0: records come from the host parser
+     * even though parse_mode is set) — h264b200SetHostParse, the host / device split of h264b200DecodeStreams */
+    void *(*inst_create_ex)(h264_backend_t *be, uint32_t width_mbs, uint32_t height_mbs, uint32_t n_slots, int host_parse);
 };
 
 /* implemented by whichever backend is linked: the CUDA engine in libh264b200.so */
@@ -214,6 +217,7 @@ typedef struct h264_decoder {
     int pic_started, valid_slice_in_au, skip_redundant;
     uint8_t *prev_buf_ptr; uint32_t prev_bytes_consumed; int prev_buf_not_finished;
     const uint8_t *nal_data; size_t nal_len;      /* current RBSP (inside the caller's buffer, or in nal_scratch) */
+    int force_host_parse;                         /* h264b200SetHostParse: this instance parses slice data on the host whatever the engine's mode */
     int ro_input;                                 /* h264b200SetReadOnlyInput: never write to the caller's buffer */
     struct { uint8_t *p; uint32_t cap; } nal_scratch;   /* read-only input: a NAL with emulation prevention bytes is unescaped here */
     uint8_t cur_nal_type, cur_nal_ref_idc;

@@ -50,6 +50,7 @@ typedef struct {
     pending_t *outq; u32 outq_cap, outq_head, outq_n;
     u32 depth;                  /* look-ahead this stream may use */
     u32 chunk;                  /* pictures scanned per round at most (= pictures per stream in a Kp launch) */
+    int host_parse;             /* device-parse engine, but this stream's slice data is parsed by the worker threads (the host share) */
 } rstream_t;
 
 typedef struct runner runner_t;
@@ -265,7 +266,7 @@ static void *dev_worker_main(void *arg)
             sched_yield();
         }
         if (s->inited) {
-            if (round < 4) {                                      /* the instances' buffers may hold less than was asked for */
+            if (round < 4 && !s->host_parse) {                    /* the instances' buffers may hold less than was asked for */
                 const uint32_t wnd = h264b200EngineWindow(r->e);
                 if (wnd < s->depth) { s->depth = wnd; if (s->chunk > (wnd >= 4 ? wnd / 2 : 1)) s->chunk = wnd >= 4 ? wnd / 2 : 1; }
             }
@@ -300,10 +301,28 @@ static void *dev_worker_main(void *arg)
     return NULL;
 }
 
+/* How many of the streams of a device-parse run are parsed by the worker threads instead of kernel Kp.  With Kp the
+ * threads have next to nothing to do (0.12 ms of NAL scanning per picture) while the GPU is the bottleneck: Kp costs
+ * it d = 65 us per 1080p picture next to k = 22 us of reconstruction.  Both parsers write the
+ * same records, so a stream can take either; every stream advances one picture per round, and a round costs the GPU
+ * (S - H) d + S k and the T threads (H h + S s) / T with h = 4.1 ms per host-parsed picture and s = 0.24 ms of scanning.
+ * The two are equal at  H = S (d + k - s / T) / (h / T + d);  the ratio h : d is a property of the two parsers (both
+ * scale with the bits of the picture), measured on the bench workload.  H264B200_HOST_STREAMS overrides (0 = all on Kp). */
+static uint32_t host_share(uint32_t n_streams, uint32_t n_threads)
+{
+    const char *env = getenv("H264B200_HOST_STREAMS");
+    const double T = (double)n_threads, d = 65.0, k = 22.0, h = 4100.0, s = 240.0;
+    double H = (double)n_streams * (d + k - s / T) / (h / T + d);
+    if (env) { const long v = atol(env); return v <= 0 ? 0 : (uint32_t)v > n_streams ? n_streams : (uint32_t)v; }
+    if (n_streams < 2 * n_threads) return 0;                       /* few streams: the look-ahead, not the parser, is the limit */
+    if (H < 0) H = 0;
+    return (uint32_t)(0.9 * H);                                     /* stay on the side where the GPU, not the threads, sets the pace */
+}
+
 int h264b200DecodeStreams(h264b200_engine_t *e, const h264b200_stream_t *streams, uint32_t n_streams,
                           uint32_t n_threads, h264b200_picture_cb cb, void *user, h264b200_run_stats_t *out)
 {
-    runner_t r; worker_t *w; uint32_t i, depth = 1, chunk = 1; double t0 = now_s(); int rc = 0, dev;
+    runner_t r; worker_t *w; uint32_t i, depth = 1, chunk = 1, n_host = 0; double t0 = now_s(); int rc = 0, dev;
     if (!e || !streams || !n_streams) return -1;
     memset(&r, 0, sizeof r);
     if (!n_threads) { long n = sysconf(_SC_NPROCESSORS_ONLN); n_threads = n > 0 ? (uint32_t)n : 1; }
@@ -318,18 +337,21 @@ int h264b200DecodeStreams(h264b200_engine_t *e, const h264b200_stream_t *streams
         /* Look-ahead per stream and pictures per stream in one Kp launch; H264B200_WINDOW / H264B200_KP_CHUNK override. */
         const char *wenv = getenv("H264B200_WINDOW"), *cenv = getenv("H264B200_KP_CHUNK");
         const uint32_t slots = h264b200EngineParseSlots(e);
-        if (slots >= n_streams) {
-            /* exclusive Kp launches: `slots / n_streams` pictures of every stream are being parsed at any time (a picture
-             * takes ~0.22 s whatever the load); small launches (2 pictures per stream) keep the flow even and the window
+        uint32_t n_dev;
+        n_host = host_share(n_streams, n_threads);
+        n_dev = n_streams > n_host ? n_streams - n_host : 1;
+        if (slots >= n_dev) {
+            /* exclusive Kp launches: `slots / n_dev` pictures of every device-parsed stream are being parsed at any time (a
+             * picture takes ~0.22 s whatever the load); small launches (2 pictures per stream) keep the flow even and the window
              * small: pictures in Kp + the next launch being scanned + those parsed and waiting for their round */
             chunk = 2;
-            depth = slots / n_streams + chunk + 4;
+            depth = slots / n_dev + chunk + 4;
         } else { chunk = 4; depth = 16; }
         if (wenv && atoi(wenv) > 0) depth = (uint32_t)atoi(wenv);
         if (cenv && atoi(cenv) > 0) chunk = (uint32_t)atoi(cenv);
         if (chunk > depth) chunk = depth;
-        h264b200EngineSetStreams(e, n_streams);
-        h264b200EngineSetWindow(e, depth, n_streams * chunk);
+        h264b200EngineSetStreams(e, n_dev);
+        h264b200EngineSetWindow(e, depth, n_dev * chunk);
         depth = h264b200EngineWindow(e);
     }
     /* two groups once every thread has a few streams per group; otherwise one (a round is then one batch).  Batches
@@ -346,6 +368,12 @@ int h264b200DecodeStreams(h264b200_engine_t *e, const h264b200_stream_t *streams
         if (!s->buf || h264b200InitOnEngine(&s->st, 0, e) != HANTRO_OK) { s->failed = 1; rc = -1; continue; }
         h264b200SetReadOnlyInput(&s->st, 1);
         s->inited = 1; s->depth = depth; s->chunk = chunk;
+        /* the host share, spread evenly over the stream indices (work items are claimed in index order, so the long
+         * items — a host parse is ~30 scans — are interleaved with short ones and the threads finish a round together) */
+        if (dev && (uint32_t)(((uint64_t)(i + 1) * n_host) / n_streams) != (uint32_t)(((uint64_t)i * n_host) / n_streams)) {
+            h264b200SetHostParse(&s->st, 1);
+            s->host_parse = 1; s->depth = 2; s->chunk = 1;     /* one picture per round, one queued ahead (the input ring holds three) */
+        }
     }
     for (i = 0; i < n_threads; i++) { w[i].r = &r; w[i].tid = i; }
     for (i = 1; i < n_threads; i++) pthread_create(&w[i].th, NULL, dev ? dev_worker_main : worker_main, &w[i]);
@@ -366,6 +394,7 @@ int h264b200DecodeStreams(h264b200_engine_t *e, const h264b200_stream_t *streams
         }
         for (i = 0; i < n_streams; i++) { out->bytes_in += r.s[i].len; if (r.s[i].failed) out->failed_streams++; }
         out->rounds = r.rounds; out->threads = n_threads;
+        for (i = 0; i < n_streams; i++) out->host_streams += (uint32_t)r.s[i].host_parse;
     }
     for (i = 0; i < n_streams; i++) {
         if (r.s[i].failed) rc = -1;

@@ -56,6 +56,9 @@ u32  h264b200PictureStatus(storage_t *pStorage, u32 ticket, h264b200_picstat_t *
 u32  h264b200PicturesPending(storage_t *pStorage);
 /* 1 if the instance parses slice data on the device */
 u32  h264b200DeviceParse(storage_t *pStorage);
+/* on != 0: the instance parses slice data on the host (h264_slice.c) even when its engine is a device-parse engine; call
+ * before the first picture.  Host- and device-parsed instances share the reconstruction rounds of the engine. */
+void h264b200SetHostParse(storage_t *pStorage, u32 on);
 /* on != 0: h264bsdDecode never writes to byteStrm (NAL units with emulation prevention bytes are unescaped into
  * decoder-owned memory instead of in place); h264b200DecodeStreams uses it to decode straight from the caller's streams */
 void h264b200SetReadOnlyInput(storage_t *pStorage, u32 on);
@@ -122,6 +125,8 @@ typedef struct {
     double   seconds;            /* wall clock of the whole call */
     double   parse_seconds;      /* summed over threads: time inside h264bsdDecode */
     double   wait_seconds;       /* summed over threads: time blocked on the GPU */
+    uint32_t host_streams;       /* device-parse engines: streams whose slice data the worker threads parsed (the host share) */
+    uint32_t reserved;
 } h264b200_run_stats_t;
 /* Decode n_streams independent streams (or GOP segments) with n_threads parser
  * threads (0: one per online CPU).  Every round parses one picture of every live
@@ -129,6 +134,9 @@ typedef struct {
  * the streams, when there are at least four streams per thread, so that no
  * thread ever waits for a round to end; always one while H264B200_ENGINE_RETAIN is
  * set, so that a retained batch is a whole round) while the next pictures are being parsed.
+ * On a device-parse engine (kernel Kp) the threads only scan NAL units and slice headers, the GPU is the bottleneck, and
+ * a share of the streams — sized from the thread count, H264B200_HOST_STREAMS overrides — is parsed by the threads'
+ * own parser instead (h264b200SetHostParse): same records, same rounds, less work for Kp.
  * `rounds` in the statistics counts the batches.  Returns 0 on success. */
 int h264b200DecodeStreams(h264b200_engine_t *e, const h264b200_stream_t *streams, uint32_t n_streams,
                           uint32_t n_threads, h264b200_picture_cb cb, void *user, h264b200_run_stats_t *out);

@@ -572,7 +572,7 @@ static KpTables *g_kp_tables;
 static recon_cpu_tap_t g_tap;
 void recon_cpu_set_tap(const recon_cpu_tap_t *t) { if (t) g_tap = *t; else memset(&g_tap, 0, sizeof g_tap); }
 
-static void *cpu_inst_create(h264_backend_t *be, uint32_t wm, uint32_t hm, uint32_t n_slots)
+static void *cpu_inst_create_ex(h264_backend_t *be, uint32_t wm, uint32_t hm, uint32_t n_slots, int host_parse)
 {
     cpu_inst_t *in = (cpu_inst_t *)calloc(1, sizeof *in);
     uint32_t i;
@@ -581,7 +581,7 @@ static void *cpu_inst_create(h264_backend_t *be, uint32_t wm, uint32_t hm, uint3
     for (i = 0; i < n_slots; i++) in->frames[i] = (uint8_t *)calloc((size_t)wm * hm, 384);
     in->predeblock = (uint8_t *)calloc((size_t)wm * hm, 384);
     in->pic.mbs = (h264b200_mb_t *)calloc((size_t)wm * hm, sizeof(h264b200_mb_t));
-    in->dev_parse = be->parse_mode;
+    in->dev_parse = be->parse_mode && !host_parse;    /* h264b200SetHostParse: a host-parsed instance on a device-parse engine */
     in->deferred = in->dev_parse && be->ctx != NULL;      /* engine_shim.c sets ctx on batched engines */
     in->ctx = be->ctx;
     if (in->deferred) {
@@ -598,6 +598,7 @@ static void *cpu_inst_create(h264_backend_t *be, uint32_t wm, uint32_t hm, uint3
     }
     return in;
 }
+static void *cpu_inst_create(h264_backend_t *be, uint32_t wm, uint32_t hm, uint32_t n_slots) { return cpu_inst_create_ex(be, wm, hm, n_slots, 0); }
 static void cpu_inst_destroy(h264_backend_t *be, void *inst)
 {
     cpu_inst_t *in = (cpu_inst_t *)inst; uint32_t i;
@@ -757,7 +758,7 @@ h264_backend_t recon_cpu_backend(int device_parse)
     b.frame_host_async = cpu_frame_host_async; b.frame_wait = cpu_frame_wait;
     b.block_grow = cpu_block_grow; b.frame_status = cpu_frame_status;
     b.frame_release = cpu_frame_release; b.inst_pending = cpu_inst_pending; b.frame_state = cpu_frame_state;
-    b.parse_mode = device_parse;
+    b.parse_mode = device_parse; b.inst_create_ex = cpu_inst_create_ex;
     return b;
 }
 static h264_backend_t g_cpu_backend;

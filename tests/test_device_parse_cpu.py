@@ -142,3 +142,26 @@ def test_runner_device_parse_reports_concealed_macroblocks(L):
         g = LOSS_GOLDEN[c[0]]
         assert m == g["frame_md5"], c[0]
         assert e == g["err_mbs"], c[0]
+
+
+@pytest.mark.parametrize("threads,host", [(1, 1), (3, 5), (16, 7), (4, 99)])
+def test_runner_host_share_of_a_device_parse_run(L, golden, threads, host, monkeypatch):
+    """h264b200DecodeStreams gives `host` of the streams of a device-parse run to the worker threads' own parser
+    (h264b200SetHostParse; spread evenly over the stream indices): host- and device-parsed instances share the engine and
+    its rounds, and every picture equals the reference golden whoever parsed it (99: more than there are streams = all)."""
+    monkeypatch.setenv("H264B200_HOST_STREAMS", str(host))
+    sel = cases.SMALL[:12] + [c for c in cases.SMALL if c[0].startswith("dpb_")]
+    md5s, errs, rs = run_streams(L, [cases.make_stream(c) for c in sel], threads, flags=1 | 8)
+    for c, m in zip(sel, md5s):
+        assert m == golden[c[0]]["frame_md5"], (c[0], threads, host)
+    assert rs.pictures == sum(c[3] for c in sel) and sum(errs) == 0
+
+
+def test_runner_host_share_reports_concealed_macroblocks(L, monkeypatch):
+    monkeypatch.setenv("H264B200_HOST_STREAMS", str(len(cases.LOSS) // 2))
+    sel = cases.LOSS
+    md5s, errs, rs = run_streams(L, [cases.make_loss_stream(c) for c in sel], 4, flags=1 | 8)
+    for c, m, e in zip(sel, md5s, errs):
+        g = LOSS_GOLDEN[c[0]]
+        assert m == g["frame_md5"], c[0]
+        assert e == g["err_mbs"], c[0]

@@ -161,3 +161,36 @@ def test_device_parse_thread_count_and_window_do_not_change_results(monkeypatch)
         if ref is None:
             ref = md5s
         assert md5s == ref
+
+
+@pytest.mark.parametrize("threads,host", [(1, 3), (4, 9), (8, 99)])
+def test_host_share_of_a_device_parse_run_matches_golden(golden, monkeypatch, threads, host):
+    """h264b200DecodeStreams gives `host` streams of a device-parse run to the worker threads' parser (h264b200SetHostParse):
+    host- and device-parsed pictures share Kp-less and Kp-fed rounds of one engine, and every picture equals the reference
+    golden whoever parsed it."""
+    monkeypatch.setenv("H264B200_HOST_STREAMS", str(host))
+    sel = cases.SMALL
+    streams = [cases.make_stream(c) for c in sel]
+    with capi.Engine(flags=capi.ENGINE_BATCHED | DEV) as eng:
+        md5s, rs = eng.decode_streams_md5(streams, threads=threads)
+        assert rs.failed_streams == 0 and rs.err_mbs == 0
+        assert rs.host_streams == min(host, len(sel))
+        for c, m in zip(sel, md5s):
+            assert m == golden[c[0]]["frame_md5"], (c[0], threads, host)
+        st = eng.stats()
+        assert st["pictures"] == sum(c[3] for c in sel)
+        assert st["kp_pictures"] < st["pictures"]
+        assert eng.error_flags() == 0
+
+
+def test_host_share_1080p_equals_all_device(monkeypatch):
+    from broadway_b200 import bitstream
+    streams = [bitstream.synth(120, 68, 6, seed=40 + i) for i in range(6)]
+    out = []
+    for host in ("0", "3"):
+        monkeypatch.setenv("H264B200_HOST_STREAMS", host)
+        with capi.Engine(flags=capi.ENGINE_BATCHED | DEV) as eng:
+            md5s, rs = eng.decode_streams_md5(streams, threads=3)
+            assert rs.failed_streams == 0 and rs.host_streams == int(host)
+        out.append(md5s)
+    assert out[0] == out[1]
