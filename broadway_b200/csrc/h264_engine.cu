@@ -56,6 +56,7 @@
 #include "kp_parse.cuh"
 
 #define NBUF 3                 /* input buffers in flight per instance (host-parse; device-parse: look-ahead depth + 2) */
+#define RING_EXTRA 4           /* device-parse input ring = look-ahead + this: the picture being scanned and up to DRIVE_ROUNDS launched ones whose kernels still read their buffers */
 #define NSCR 4                 /* batch scratch sets in flight per engine */
 #define NPAR 16                /* Kp launches in flight per engine: one scratch set and one CUDA stream each, so that they overlap —
                                   a launch over a quarter of the look-ahead window does not fill the SMs on its own */
@@ -83,6 +84,7 @@ struct PicBuf {
     KpMbCtx *d_ctx; KpResult *d_res;
     cudaEvent_t parsed;            /* (not owned) event of the Kp launch that parses this picture */
     uint32_t parse_seq;            /* which Kp launch; 0: not launched yet */
+    int block_on_device;           /* the block was copied to d_block when the picture was submitted (be_pic_submit) */
     uint32_t gate_gen;             /* generation of the frame slot's host mirror that must have been released before this picture is launched */
     int tape_parse, tape_last_round;   /* retained runs: tape index of the Kp launch that fills / of the last round that read this buffer */
 };
@@ -154,6 +156,7 @@ struct ParseScratch {              /* one Kp launch */
     cudaEvent_t done;              /* the launch has finished */
     bool used;
     uint32_t ctas;                 /* exclusive mode: SMs the launch owns while it runs */
+    uint32_t seq;                  /* parse_seq of the launch */
 };
 
 struct h264b200_engine {
@@ -364,7 +367,8 @@ static int launch_parse(h264b200_engine *e, std::vector<PicBuf *> &list)
             CUDA_TRY(cudaMalloc((void **)&p->d_block, p->d_block_cap), return -1);
             d_block = p->d_block;
         }
-        CUDA_TRY(cudaMemcpyAsync(d_block, pic->block, pic->block_used, cudaMemcpyHostToDevice, e->s_h2d), return -1);
+        if (!p->block_on_device || retain)
+            CUDA_TRY(cudaMemcpyAsync(d_block, pic->block, pic->block_used, cudaMemcpyHostToDevice, e->s_h2d), return -1);
         in_bytes += pic->block_used;
         KpPic &kp = ps.h_pics[i];
         kp.block = d_block; kp.mbs = p->d_mbs; kp.coef = p->d_coef; kp.ctx = p->d_ctx; kp.coef_cap = p->d_coef_cap; kp.pad = 0; kp.res = p->d_res;
@@ -382,7 +386,7 @@ static int launch_parse(h264b200_engine *e, std::vector<PicBuf *> &list)
     kp_launch(e, kb, s);
     tl_end(e, s);
     e->st.kernel_launches++; e->st.kp_launches++; e->st.kp_pictures += n;
-    cudaEventRecord(ps.done, s); ps.used = true; ps.ctas = e->kp_sms ? kp_ctas(e, n) : 0;
+    cudaEventRecord(ps.done, s); ps.used = true; ps.ctas = e->kp_sms ? kp_ctas(e, n) : 0; ps.seq = e->parse_seq;
     if (retain) {
         cudaEventRecord(ret->ev, s);
         ret->kp = kb;
@@ -653,13 +657,101 @@ static uint32_t advance_all_locked(h264b200_engine *e)
     return total;
 }
 
+/* engine mutex held.  One step of the FREE-RUNNING schedule (h264b200EngineDrive): what a dedicated scheduling thread
+ * calls every few hundred microseconds while worker threads submit pictures and collect outputs on their own.
+ *   Kp: as soon as `parse_threshold` unparsed pictures are queued (`relaxed` >= 1: any) and SMs of Kp's share are free, a
+ *       launch over as many pictures as fit those SMs — the oldest unparsed picture of every instance first, then the
+ *       second oldest ... so that a truncated launch still serves every stream;
+ *   round: the oldest queued picture of every instance whose Kp launch has finished, once most instances that have anything
+ *       queued are ready (`relaxed` >= 2: any), while fewer than DRIVE_ROUNDS rounds are on the device (launched, copy-out not finished):
+ *       enough to keep kernels and copy-out busy back to back, few enough that a picture's latency stays bounded.
+ * *kp_pics = pictures handed to Kp by this call.  Returns the pictures of the round launched (0: none). */
+#define DRIVE_ROUNDS 3
+static uint32_t drive_locked(h264b200_engine *e, int relaxed, uint32_t *kp_pics)
+{
+    set_device(e);
+    if (kp_pics) *kp_pics = 0;
+    /* ---- Kp ---- */
+    uint32_t unparsed = 0, with_unparsed = 0;
+    for (Inst *in : e->insts) {
+        if (!in->dev_parse) continue;
+        uint32_t k = 0;
+        for (PicBuf *p : *in->fifo) if (!p->parse_seq) k++;
+        unparsed += k; with_unparsed += k != 0;
+    }
+    if (unparsed && (unparsed >= e->parse_threshold || relaxed)) {
+        const ParseScratch &nps = e->pscr[e->next_pscr];
+        bool go = !nps.used || cudaEventQuery(nps.done) == cudaSuccess;
+        uint32_t take = unparsed > 8192 ? 8192 : unparsed;
+        if (go && e->kp_sms) {
+            uint32_t busy = 0;
+            for (int k = 0; k < NPAR; k++) if (e->pscr[k].used && e->pscr[k].ctas && cudaEventQuery(e->pscr[k].done) != cudaSuccess) busy += e->pscr[k].ctas;
+            const uint32_t free_ctas = busy < e->kp_sms ? e->kp_sms - busy : 0;
+            /* a launch worth its latency: all that is queued, or at least the threshold's worth of SMs (anything when nothing runs) */
+            const uint32_t min_ctas = relaxed ? 1 : (e->parse_threshold + 31) / 32;
+            if (free_ctas >= (take + 31) / 32) ;
+            else if (free_ctas >= min_ctas || (busy == 0 && free_ctas)) {
+                take = free_ctas * 32;
+                if (take >= with_unparsed) take -= take % with_unparsed;     /* whole levels: the streams stay in step, rounds stay full */
+            }
+            else go = false;
+        }
+        if (go) {
+            /* the oldest unparsed picture of every instance, then the second oldest ...: a truncated launch serves every stream */
+            std::vector<PicBuf *> &pl = e->tmp_parse; pl.clear();
+            for (uint32_t level = 0; pl.size() < take; level++) {
+                bool any = false;
+                for (Inst *in : e->insts) {
+                    if (!in->dev_parse) continue;
+                    uint32_t k = 0;
+                    for (PicBuf *p : *in->fifo) if (!p->parse_seq) { if (k == level) { if (pl.size() < take) pl.push_back(p); any = true; break; } k++; }
+                }
+                if (!any) break;
+            }
+            const uint32_t n = (uint32_t)pl.size();
+            if (n) {
+                if (launch_parse(e, pl)) { for (PicBuf *p : pl) p->inst->slot_flags[p->in.cur_slot] |= 4; }
+                else if (kp_pics) *kp_pics = n;
+            }
+        }
+    }
+    /* ---- round ---- */
+    uint32_t in_flight = 0;
+    for (int k = 0; k < NSCR; k++) if (e->scr[k].used && cudaEventQuery(e->scr[k].d2h_done) != cudaSuccess) in_flight++;
+    if (in_flight >= DRIVE_ROUNDS) return 0;
+    std::vector<PicBuf *> &rl = e->tmp_round; rl.clear();
+    uint32_t nonempty = 0;
+    /* only pictures whose Kp launch has FINISHED go into a round (strict mode): a round then starts at once, its
+     * buffers come back soon, and no worker ever waits behind a round that itself waits for a 0.2 s parse */
+    uint32_t running[NPAR]; int n_running = 0;
+    for (int k = 0; k < NPAR; k++) if (e->pscr[k].used && cudaEventQuery(e->pscr[k].done) != cudaSuccess) running[n_running++] = e->pscr[k].seq;
+    for (Inst *in : e->insts) {
+        if (in->fifo->empty()) continue;
+        nonempty++;
+        PicBuf *p = in->fifo->front();
+        if (in->dev_parse) {
+            if (!p->parse_seq) continue;
+            bool busy = false;
+            for (int k = 0; k < n_running; k++) if (running[k] == p->parse_seq) busy = true;
+            if (busy) continue;
+        }
+        if (gated(p)) continue;
+        rl.push_back(p);
+    }
+    if (rl.empty()) return 0;
+    if (relaxed < 2 && (uint32_t)rl.size() * 8 < nonempty * 7) return 0;      /* stragglers: their pictures are in the next Kp launch, or their output is about to be released */
+    for (PicBuf *p : rl) { p->inst->fifo->pop_front(); p->inst->n_pending.fetch_sub(1, std::memory_order_release); }
+    launch_round(e, rl);
+    return (uint32_t)rl.size();
+}
+
 /* ------------------------------------------------------- backend callbacks */
 static void inst_free(Inst *in);
 /* engine mutex held: the look-ahead the runner may use is what the smallest instance can hold */
 static void note_window(h264b200_engine *e, const Inst *in)
 {
-    if (!in->dev_parse || (uint32_t)(in->n_bufs - 2) >= e->eff_window) return;
-    e->eff_window = (uint32_t)(in->n_bufs - 2);
+    if (!in->dev_parse || (uint32_t)(in->n_bufs - RING_EXTRA) >= e->eff_window) return;
+    e->eff_window = (uint32_t)(in->n_bufs - RING_EXTRA);
     const uint32_t thr = (e->n_inst_hint ? e->n_inst_hint : 1) * (e->eff_window >= 4 ? e->eff_window / 2 : 1);
     if (thr < e->parse_threshold) e->parse_threshold = thr;
 }
@@ -671,19 +763,19 @@ static void *be_inst_create_ex(h264_backend_t *be, uint32_t wm, uint32_t hm, uin
     /* host_parse: an instance of a device-parse engine that brings its own records (h264b200SetHostParse); its pictures
      * join the same reconstruction rounds, they just have nothing for kernel Kp to do */
     const int dev_parse = (e->flags & H264B200_ENGINE_DEVICE_PARSE) != 0 && !host_parse;
-    int n_bufs = dev_parse ? (int)e->window + 2 : host_parse ? NBUF + 1 : NBUF;   /* host share of a device-parse run: one picture queued ahead of the round in flight */
+    int n_bufs = dev_parse ? (int)e->window + RING_EXTRA : host_parse ? NBUF + 1 : NBUF;   /* host share of a device-parse run: one picture queued ahead of the round in flight */
     if (dev_parse && e->inst_budget) {
         /* the look-ahead window is a wish: 4K pictures cost 35 MB of worst-case parse output each, and hundreds of
          * instances must fit the device together */
         const size_t per_buf = parse_bytes_per_buf(wm * hm) + block_cap0(wm * hm);
         const size_t fit = e->inst_budget / per_buf;
-        if ((size_t)n_bufs > fit) n_bufs = fit < 4 ? 4 : (int)fit;
+        if ((size_t)n_bufs > fit) n_bufs = fit < RING_EXTRA + 2 ? RING_EXTRA + 2 : (int)fit;
     }
     {   /* reuse a pooled instance of the same geometry */
         std::lock_guard<std::mutex> lk(e->mu);
         for (size_t i = 0; i < e->pool.size(); i++) {
             Inst *c = e->pool[i];
-            if (c->wm == wm && c->hm == hm && c->n_slots == n_slots && c->dev_parse == dev_parse && (dev_parse ? c->n_bufs >= 4 : c->n_bufs == n_bufs)) {
+            if (c->wm == wm && c->hm == hm && c->n_slots == n_slots && c->dev_parse == dev_parse && (dev_parse ? c->n_bufs >= RING_EXTRA + 1 : c->n_bufs == n_bufs)) {
                 note_window(e, c);
                 e->pool.erase(e->pool.begin() + i);
                 memset(c->slot_flags, 0, sizeof c->slot_flags); memset(c->slot_qgen, 0, sizeof c->slot_qgen); memset(c->slot_lgen, 0, sizeof c->slot_lgen);
@@ -800,7 +892,7 @@ static h264_pic_input_t *be_pic_begin(h264_backend_t *be, void *inst)
         }
     }
     if (p->state == 3) { set_device(e); cudaEventSynchronize(p->done); }
-    p->state = 1; p->parse_seq = 0;
+    p->state = 1; p->parse_seq = 0; p->block_on_device = 0;
     return &p->in;
 }
 
@@ -841,6 +933,12 @@ static int be_pic_submit(h264_backend_t *be, void *inst, h264_pic_input_t *pic)
     h264b200_engine *e = (h264b200_engine *)be->ctx; Inst *in = (Inst *)inst;
     PicBuf *p = (PicBuf *)pic->priv;
     std::lock_guard<std::mutex> lk(e->mu);
+    if (in->dev_parse && pic->block && !(e->flags & H264B200_ENGINE_RETAIN) && p->d_block_cap >= pic->block_used) {
+        /* the slices travel now, from the thread that scanned them: a Kp launch then finds its input on the device and
+         * the scheduling thread is spared one copy call per picture */
+        set_device(e);
+        if (cudaMemcpyAsync(p->d_block, pic->block, pic->block_used, cudaMemcpyHostToDevice, e->s_h2d) == cudaSuccess) p->block_on_device = 1;
+    }
     p->state = 2;
     in->slot_qgen[pic->cur_slot]++;
     /* whatever the caller still holds of this frame slot (h264b200NextOutputPictureAsync) must be released before the
@@ -1141,6 +1239,12 @@ extern "C" u32 h264b200EngineAdvance(h264b200_engine_t *e)
     if (!e) return 0;
     std::lock_guard<std::mutex> lk(e->mu);
     return advance_locked(e, false);
+}
+extern "C" u32 h264b200EngineDrive(h264b200_engine_t *e, int relaxed, u32 *kp_pictures)
+{
+    if (!e) return 0;
+    std::lock_guard<std::mutex> lk(e->mu);
+    return drive_locked(e, relaxed, kp_pictures);
 }
 extern "C" void h264b200EngineSetWindow(h264b200_engine_t *e, uint32_t depth, uint32_t parse_threshold)
 {

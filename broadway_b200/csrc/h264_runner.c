@@ -50,6 +50,7 @@ typedef struct {
     pending_t *outq; u32 outq_cap, outq_head, outq_n;
     u32 depth;                  /* look-ahead this stream may use */
     u32 chunk;                  /* pictures scanned per round at most (= pictures per stream in a Kp launch) */
+    int done;                   /* device-parse: finished, everything launched and handed out */
     int host_parse;             /* device-parse engine, but this stream's slice data is parsed by the worker threads (the host share) */
 } rstream_t;
 
@@ -72,7 +73,10 @@ struct runner {
     uint32_t arrived[MAX_GROUPS], produced[MAX_GROUPS], dead[MAX_GROUPS];   /* under mu: the group's current round */
     uint32_t launched[MAX_GROUPS];            /* rounds of the group that have been handed to the GPU (release / acquire) */
     int stop;                                 /* every group went through a round without producing a picture */
-    int force_wait;                           /* device-parse: the last scheduling step launched nothing: wait for pictures in flight */
+    uint32_t n_workers;                       /* device-parse: worker threads (the streams are dealt out to them) ... */
+    uint32_t workers_alive;                   /* ... still sweeping */
+    int inline_drive;                         /* device-parse with one thread: the worker takes the scheduling steps itself */
+    uint32_t activity;                        /* device-parse: pictures scanned + outputs collected so far, all workers (progress indicator for the scheduling thread) */
     uint32_t rounds;                          /* batches launched */
 };
 
@@ -173,9 +177,12 @@ static void *worker_main(void *arg)
 /* ------------------------------------------------ device-parse pipeline */
 /* With kernel Kp the host does no slice-data parsing: a picture costs it a NAL scan, a slice header and the DPB
  * bookkeeping.  So every stream SCANS AHEAD of the GPU by up to `depth` pictures (they wait in the engine), which is what
- * gives Kp thousands of independent pictures per launch; every round of the loop below then (1) hands finished
- * pictures to the callback and releases their buffers, (2) tops the look-ahead up, and the last thread of the round
- * calls h264b200EngineAdvance once: a Kp launch when enough pictures are queued, and one reconstruction round. */
+ * gives Kp thousands of independent pictures in flight.  The pipeline is FREE-RUNNING: worker threads sweep over their
+ * own streams — hand completed pictures to the callback, release them, top the look-ahead up — and never block on the
+ * GPU; one scheduling thread polls h264b200EngineDrive, which launches Kp whenever SMs of its share are free and a
+ * reconstruction round whenever the streams' oldest pictures are parsed, a few rounds deep.  (The first version moved
+ * in lock step — all threads swept all streams, then ONE scheduling step — and its ~1000 copy / launch calls per step
+ * were a serial section the whole pipeline waited for: 10.5k frames/s where the device alone replays 13.9k.) */
 static void outq_push(rstream_t *s, const pending_t *q)
 {
     if (s->outq_n == s->outq_cap) {
@@ -213,29 +220,18 @@ static int dev_scan_one(rstream_t *s)
     s->finished = 1;
     return 0;
 }
-/* Hand over the outputs whose pictures have been launched, oldest first; returns how many.  The NEWEST launched picture
- * of the stream is not waited for while it is still in flight (unless `drain`): the round that produced it was launched
- * one scheduling step ago, and waiting here would put its kernels and its copy-out on the host's critical path —
- * reconstruction of round r+1 could not be launched before round r has arrived in host memory.  Left alone for one
- * step, the copy-out of round r overlaps the kernels of round r+1 (the frame slot round r+1 writes was released when
- * round r-1 was consumed). */
-static u32 dev_consume(worker_t *w, rstream_t *s, uint32_t stream_index, int drain)
+/* Hand over the outputs whose pictures are COMPLETE in host memory, oldest first; never blocks.  Returns how many. */
+static u32 dev_consume(worker_t *w, rstream_t *s, uint32_t stream_index)
 {
     runner_t *r = w->r;
     u32 n = 0;
     while (s->outq_n) {
         pending_t *q = &s->outq[s->outq_head];
         h264b200_picstat_t ps;
-        double t0;
-        u32 rc, state = h264b200PictureState(&s->st, q->ticket);
-        if (state == 2) break;                                    /* still queued in the engine */
-        if (state == 1 && !drain) {
-            /* in flight: wait only if a newer output of this stream has been launched as well */
-            if (s->outq_n < 2 || h264b200PictureState(&s->st, s->outq[(s->outq_head + 1) % s->outq_cap].ticket) == 2) break;
-        }
-        t0 = now_s();
-        rc = h264b200PictureWait(&s->st, q->ticket);
-        w->wait_s += now_s() - t0;
+        u32 rc;
+        const u32 state = h264b200PictureState(&s->st, q->ticket);
+        if (state == 1 || state == 2) break;                      /* in flight, or still queued in the engine */
+        rc = state == 0 ? h264b200PictureWait(&s->st, q->ticket) : 0xffffffffu;   /* complete: returns at once */
         if (rc == H264B200_WAIT_NOT_LAUNCHED) break;
         if (rc == 0xffffffffu || rc == 0xfffffffeu) s->failed = 1;
         else if (!h264b200PictureStatus(&s->st, q->ticket, &ps) && (ps.flags & H264B200_PS_DROPPED)) ;   /* incomplete last picture: not output */
@@ -253,70 +249,94 @@ static u32 dev_consume(worker_t *w, rstream_t *s, uint32_t stream_index, int dra
     return n;
 }
 
+static void idle_wait(unsigned us) { struct timespec t; t.tv_sec = 0; t.tv_nsec = (long)us * 1000L; nanosleep(&t, NULL); }
+
+/* A worker owns the streams  tid, tid + n_workers, ...  (a decoder instance is single-threaded) and sweeps over them for
+ * as long as one of them is alive: collect what has arrived, release it, top the look-ahead up.  Nothing in a sweep
+ * blocks on the GPU; a sweep that found nothing to do sleeps for a moment. */
 static void *dev_worker_main(void *arg)
 {
     worker_t *w = (worker_t *)arg; runner_t *r = w->r;
-    while (!__atomic_load_n(&r->stop, __ATOMIC_ACQUIRE)) {
-        const uint64_t item = __atomic_fetch_add(&r->next_item, 1, __ATOMIC_RELAXED);
-        const uint32_t round = (uint32_t)(item / r->n_streams), idx = (uint32_t)(item % r->n_streams);
-        rstream_t *s = &r->s[idx];
-        uint32_t activity = 0, burst;
-        while (__atomic_load_n(&r->launched[0], __ATOMIC_ACQUIRE) < round) {
-            if (__atomic_load_n(&r->stop, __ATOMIC_ACQUIRE)) return NULL;
-            sched_yield();
-        }
-        if (s->inited) {
-            if (round < 4 && !s->host_parse) {                    /* the instances' buffers may hold less than was asked for */
+    uint32_t sweep = 0, quiet = 0;
+    for (;; sweep++) {
+        uint32_t live = 0, activity = 0, idx;
+        for (idx = w->tid; idx < r->n_streams; idx += r->n_workers) {
+            rstream_t *s = &r->s[idx];
+            uint32_t burst;
+            if (!s->inited || s->done) continue;
+            live++;
+            if (sweep < 4 && !s->host_parse) {                    /* the instances' buffers may hold less than was asked for */
                 const uint32_t wnd = h264b200EngineWindow(r->e);
                 if (wnd < s->depth) { s->depth = wnd; if (s->chunk > (wnd >= 4 ? wnd / 2 : 1)) s->chunk = wnd >= 4 ? wnd / 2 : 1; }
             }
-            /* drain: nothing of the stream is left to launch, or the engine could launch nothing last time (a picture may be
-             * held back by an output we have not released) */
-            activity += dev_consume(w, s, idx, (s->finished && !h264b200PicturesPending(&s->st)) || __atomic_load_n(&r->force_wait, __ATOMIC_ACQUIRE));
-            /* a quarter of the look-ahead per round: the first Kp launch goes out after one round of scanning, not after
-             * the whole window has been scanned, and in steady state (one picture per stream reconstructed per round)
-             * the window stays full */
+            activity += dev_consume(w, s, idx);
             burst = s->chunk;
             while (burst-- && !s->finished && !s->failed && h264b200PicturesPending(&s->st) < s->depth) {
                 double t0 = now_s();
-                activity += (uint32_t)dev_scan_one(s);
+                activity += 1 + (uint32_t)dev_scan_one(s);
                 w->parse_s += now_s() - t0;
             }
-            if (!s->finished && !s->failed) activity++;
-            activity += s->outq_n + h264b200PicturesPending(&s->st);
+            if ((s->finished || s->failed) && !s->outq_n && !h264b200PicturesPending(&s->st)) s->done = 1;
         }
-        /* the last stream of the round drives the engine */
-        pthread_mutex_lock(&r->mu);
-        r->produced[0] += activity;
-        if (++r->arrived[0] == r->n_streams) {
-            const uint32_t launched = h264b200EngineAdvance(r->e);
-            if (launched) r->rounds++;
-            __atomic_store_n(&r->force_wait, launched == 0, __ATOMIC_RELEASE);
-            if (!r->produced[0] && !launched) __atomic_store_n(&r->stop, 1, __ATOMIC_RELEASE);
-            r->produced[0] = 0; r->arrived[0] = 0;
-            __atomic_store_n(&r->launched[0], round + 1, __ATOMIC_RELEASE);
+        if (!live) break;
+        if (__atomic_load_n(&r->stop, __ATOMIC_ACQUIRE)) {        /* the scheduling thread saw no progress for seconds: give up on what is left */
+            for (idx = w->tid; idx < r->n_streams; idx += r->n_workers) if (r->s[idx].inited && !r->s[idx].done) { r->s[idx].failed = 1; r->s[idx].done = 1; }
+            break;
         }
-        pthread_mutex_unlock(&r->mu);
+        if (r->inline_drive) {                                    /* one thread for everything: a scheduling step per sweep */
+            u32 kp = 0;
+            const u32 n = h264b200EngineDrive(r->e, activity ? 0 : 2, &kp);
+            if (n) r->rounds++;
+            if (n || kp || activity) quiet = 0;
+            else if (++quiet > 20000) __atomic_store_n(&r->stop, 1, __ATOMIC_RELEASE);
+            if (!n && !kp && !activity) idle_wait(50);
+            continue;
+        }
+        if (activity) __atomic_fetch_add(&r->activity, activity, __ATOMIC_RELEASE);
+        else { double t0 = now_s(); idle_wait(150); w->wait_s += now_s() - t0; }
+    }
+    __atomic_fetch_sub(&r->workers_alive, 1, __ATOMIC_RELEASE);
+    return NULL;
+}
+
+/* The scheduling thread: drives the engine while the workers feed it.  When neither it nor any worker has made progress
+ * for a millisecond — the look-ahead windows are full, or the streams are ending and fewer pictures than a launch is
+ * normally worth are left — it asks for relaxed launches (anything that is ready goes). */
+static void *dev_driver_main(void *arg)
+{
+    runner_t *r = (runner_t *)arg;
+    uint32_t last_activity = 0, quiet = 0;
+    while (__atomic_load_n(&r->workers_alive, __ATOMIC_ACQUIRE) > 0) {
+        u32 kp = 0;
+        u32 n = h264b200EngineDrive(r->e, quiet >= 40 ? 2 : quiet >= 6 ? 1 : 0, &kp);
+        if (n) r->rounds++;
+        if (n || kp) { quiet = 0; continue; }
+        {
+            const uint32_t a = __atomic_load_n(&r->activity, __ATOMIC_ACQUIRE);
+            if (a != last_activity) { last_activity = a; quiet = 0; } else quiet++;
+        }
+        if (quiet > 30000) __atomic_store_n(&r->stop, 1, __ATOMIC_RELEASE);   /* ~5 s without any progress anywhere */
+        idle_wait(150);
     }
     return NULL;
 }
 
-/* How many of the streams of a device-parse run are parsed by the worker threads instead of kernel Kp.  With Kp the
- * threads have next to nothing to do (0.12 ms of NAL scanning per picture) while the GPU is the bottleneck: Kp costs
- * it d = 65 us per 1080p picture next to k = 22 us of reconstruction.  Both parsers write the
- * same records, so a stream can take either; every stream advances one picture per round, and a round costs the GPU
- * (S - H) d + S k and the T threads (H h + S s) / T with h = 4.1 ms per host-parsed picture and s = 0.24 ms of scanning.
- * The two are equal at  H = S (d + k - s / T) / (h / T + d);  the ratio h : d is a property of the two parsers (both
- * scale with the bits of the picture), measured on the bench workload.  H264B200_HOST_STREAMS overrides (0 = all on Kp). */
+/* How many of the streams of a device-parse run are parsed by the worker threads instead of kernel Kp
+ * (h264b200SetHostParse).  Both parsers write the same records, so a stream can take either.  Default: none — on the
+ * development box the copy-out of the finished frames (PCIe, ~16 000 1080p frames/s) is reached before Kp's share of the
+ * SMs is, and a host-parsed picture costs 12x the upload of its slices.  H264B200_HOST_STREAMS=n
+ * gives n streams to the threads; "auto" sizes the share for a box where Kp is the bottleneck: a picture costs the GPU
+ * d = 65 us in Kp next to k = 22 us of reconstruction, a thread h = 4.1 ms, so the two sides finish together at
+ * H = S (d + k) / (h / T + d) for S streams and T worker threads (the ratio h : d is a property of the two parsers, both
+ * scale with the bits of the picture; measured on the bench workload). */
 static uint32_t host_share(uint32_t n_streams, uint32_t n_threads)
 {
     const char *env = getenv("H264B200_HOST_STREAMS");
-    const double T = (double)n_threads, d = 65.0, k = 22.0, h = 4100.0, s = 240.0;
-    double H = (double)n_streams * (d + k - s / T) / (h / T + d);
-    if (env) { const long v = atol(env); return v <= 0 ? 0 : (uint32_t)v > n_streams ? n_streams : (uint32_t)v; }
+    const double T = (double)(n_threads > 1 ? n_threads - 1 : 1), d = 65.0, k = 22.0, h = 4100.0;
+    if (!env) return 0;
+    if (strcmp(env, "auto")) { const long v = atol(env); return v <= 0 ? 0 : (uint32_t)v > n_streams ? n_streams : (uint32_t)v; }
     if (n_streams < 2 * n_threads) return 0;                       /* few streams: the look-ahead, not the parser, is the limit */
-    if (H < 0) H = 0;
-    return (uint32_t)(0.9 * H);                                     /* stay on the side where the GPU, not the threads, sets the pace */
+    return (uint32_t)(0.9 * (double)n_streams * (d + k) / (h / T + d));
 }
 
 int h264b200DecodeStreams(h264b200_engine_t *e, const h264b200_stream_t *streams, uint32_t n_streams,
@@ -376,15 +396,29 @@ int h264b200DecodeStreams(h264b200_engine_t *e, const h264b200_stream_t *streams
         }
     }
     for (i = 0; i < n_threads; i++) { w[i].r = &r; w[i].tid = i; }
-    for (i = 1; i < n_threads; i++) pthread_create(&w[i].th, NULL, dev ? dev_worker_main : worker_main, &w[i]);
-    if (dev) dev_worker_main(&w[0]); else worker_main(&w[0]);
-    for (i = 1; i < n_threads; i++) pthread_join(w[i].th, NULL);
-    if (dev) {                                                                   /* nothing should be left; be safe */
-        for (i = 0; i < n_streams; i++) while (r.s[i].inited && r.s[i].outq_n) {
-            if (!dev_consume(&w[0], &r.s[i], i, 1) && !h264b200EngineSubmit(e)) { r.s[i].failed = 1; break; }
+    if (dev) {
+        /* free-running pipeline: the calling thread schedules the engine, the others are workers over their own streams
+         * (a single thread does both) */
+        pthread_t drv;
+        r.n_workers = n_threads > 1 ? n_threads - 1 : 1;
+        r.inline_drive = n_threads == 1;
+        r.workers_alive = r.n_workers;
+        for (i = 1; i < r.n_workers; i++) pthread_create(&w[i].th, NULL, dev_worker_main, &w[i]);
+        if (r.inline_drive) dev_worker_main(&w[0]);
+        else {
+            pthread_create(&drv, NULL, dev_driver_main, &r);
+            dev_worker_main(&w[0]);
+            pthread_join(drv, NULL);
         }
-    } else
-    for (i = 0; i < n_streams; i++) consume_prev(&w[0], &r.s[i], i);           /* what the last round popped */
+        for (i = 1; i < r.n_workers; i++) pthread_join(w[i].th, NULL);
+        while (h264b200EngineSubmit(e)) ;                                          /* nothing should be left; be safe */
+        for (i = 0; i < n_streams; i++) if (r.s[i].inited && (r.s[i].outq_n || !r.s[i].done)) r.s[i].failed = 1;
+    } else {
+        for (i = 1; i < n_threads; i++) pthread_create(&w[i].th, NULL, worker_main, &w[i]);
+        worker_main(&w[0]);
+        for (i = 1; i < n_threads; i++) pthread_join(w[i].th, NULL);
+        for (i = 0; i < n_streams; i++) consume_prev(&w[0], &r.s[i], i);           /* what the last round popped */
+    }
     h264b200EngineSync(e);
     if (out) {
         memset(out, 0, sizeof *out);

@@ -67,6 +67,14 @@ void h264b200SetReadOnlyInput(storage_t *pStorage, u32 on);
  * of every instance whose output buffer is free.  Returns the number of pictures reconstructed by this call.
  * h264b200EngineSubmit repeats this until nothing is left that can be launched. */
 u32  h264b200EngineAdvance(h264b200_engine_t *e);
+/* One step of the free-running schedule, for a caller that dedicates a thread to the engine (h264b200DecodeStreams does):
+ * call it every few hundred microseconds.  Launches kernel Kp as soon as `parse_threshold` unparsed pictures are queued
+ * and SMs of Kp's share are free (sized to those SMs, oldest picture of every instance first), and ONE reconstruction
+ * round once most instances with queued pictures are ready, while fewer than three rounds are on the device.
+ * relaxed >= 1 drops the "enough to be worth it" condition of the Kp launch, relaxed >= 2 that of the round as well (a
+ * caller that sees no progress elsewhere: end of the streams, look-ahead windows full).  *kp_pictures (may be NULL) = pictures handed to Kp by this call; returns the
+ * pictures of the round it launched, 0 if none. */
+u32  h264b200EngineDrive(h264b200_engine_t *e, int relaxed, u32 *kp_pictures);
 /* look-ahead of the device-parse path: how many pictures per instance may be queued (parse buffers are allocated for
  * depth + 2), and how many queued pictures make kernel Kp worth launching.  Call before the instances are created. */
 void h264b200EngineSetWindow(h264b200_engine_t *e, uint32_t depth, uint32_t parse_threshold);
@@ -134,9 +142,10 @@ typedef struct {
  * the streams, when there are at least four streams per thread, so that no
  * thread ever waits for a round to end; always one while H264B200_ENGINE_RETAIN is
  * set, so that a retained batch is a whole round) while the next pictures are being parsed.
- * On a device-parse engine (kernel Kp) the threads only scan NAL units and slice headers, the GPU is the bottleneck, and
- * a share of the streams — sized from the thread count, H264B200_HOST_STREAMS overrides — is parsed by the threads'
- * own parser instead (h264b200SetHostParse): same records, same rounds, less work for Kp.
+ * On a device-parse engine (kernel Kp) the pipeline is free-running instead: the calling thread schedules the engine
+ * (h264b200EngineDrive), the other threads sweep over their own streams — scan ahead, collect, release — and never
+ * block on the GPU.  H264B200_HOST_STREAMS=n|auto hands a share of the streams to the threads' own parser
+ * (h264b200SetHostParse: same records, same rounds, less work for Kp; off by default).
  * `rounds` in the statistics counts the batches.  Returns 0 on success. */
 int h264b200DecodeStreams(h264b200_engine_t *e, const h264b200_stream_t *streams, uint32_t n_streams,
                           uint32_t n_threads, h264b200_picture_cb cb, void *user, h264b200_run_stats_t *out);

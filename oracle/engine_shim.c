@@ -43,6 +43,7 @@ u32 h264b200EngineSubmit(h264b200_engine_t *e)
 }
 void h264b200EngineSync(h264b200_engine_t *e) { (void)e; }
 u32 h264b200EngineAdvance(h264b200_engine_t *e) { if (!e) return 0; e->submits++; return recon_cpu_advance(e); }
+u32 h264b200EngineDrive(h264b200_engine_t *e, int relaxed, u32 *kp_pictures) { (void)relaxed; if (kp_pictures) *kp_pictures = 0; if (!e) return 0; e->submits++; return recon_cpu_advance(e); }
 void h264b200EngineSetWindow(h264b200_engine_t *e, uint32_t depth, uint32_t parse_threshold) { (void)parse_threshold; if (e) e->window = depth ? depth : 1; }
 uint32_t h264b200EngineWindow(h264b200_engine_t *e) { return e ? e->window : 0; }
 uint32_t h264b200EngineParseSlots(h264b200_engine_t *e) { (void)e; return 0; }

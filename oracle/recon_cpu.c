@@ -28,6 +28,7 @@
  * It plugs in as an `h264_backend_t` (csrc/h264_internal.h), so the very same
  * host decoder sources run above it: oracle/libh264b200_cpuchk.so.
  */
+#include <pthread.h>
 #include <stdlib.h>
 #include <string.h>
 #include <stdio.h>
@@ -558,11 +559,12 @@ typedef struct {
     void *ctx;
     struct cpu_qpic { uint8_t *block; uint32_t used; int cur_slot; uint32_t gate_gen; } *q;
     uint32_t q_cap, q_head, q_n;
+    pthread_mutex_t q_mu;           /* the queue is filled by the stream's parser thread and drained by whichever thread drives the engine */
     uint32_t qgen[H264_MAX_SLOTS], lgen[H264_MAX_SLOTS], popped[H264_MAX_SLOTS], released[H264_MAX_SLOTS];
 } cpu_inst_t;
 
-#include <pthread.h>
 static pthread_mutex_t g_reg_mu = PTHREAD_MUTEX_INITIALIZER;
+static pthread_mutex_t g_adv_mu = PTHREAD_MUTEX_INITIALIZER;   /* held while recon_cpu_advance works on registered instances: an instance is not destroyed under it */
 static cpu_inst_t *g_reg[4096];
 static uint32_t g_reg_n;
 
@@ -584,6 +586,7 @@ static void *cpu_inst_create_ex(h264_backend_t *be, uint32_t wm, uint32_t hm, ui
     in->dev_parse = be->parse_mode && !host_parse;    /* h264b200SetHostParse: a host-parsed instance on a device-parse engine */
     in->deferred = in->dev_parse && be->ctx != NULL;      /* engine_shim.c sets ctx on batched engines */
     in->ctx = be->ctx;
+    pthread_mutex_init(&in->q_mu, NULL);
     if (in->deferred) {
         pthread_mutex_lock(&g_reg_mu);
         if (g_reg_n < 4096) g_reg[g_reg_n++] = in;
@@ -604,9 +607,11 @@ static void cpu_inst_destroy(h264_backend_t *be, void *inst)
     cpu_inst_t *in = (cpu_inst_t *)inst; uint32_t i;
     (void)be;
     if (in->deferred) {
+        pthread_mutex_lock(&g_adv_mu);
         pthread_mutex_lock(&g_reg_mu);
         for (i = 0; i < g_reg_n; i++) if (g_reg[i] == in) { g_reg[i] = g_reg[--g_reg_n]; break; }
         pthread_mutex_unlock(&g_reg_mu);
+        pthread_mutex_unlock(&g_adv_mu);
         for (i = 0; i < in->q_n; i++) free(in->q[(in->q_head + i) % in->q_cap].block);
         free(in->q);
     }
@@ -631,6 +636,7 @@ static int cpu_pic_submit(h264_backend_t *be, void *inst, h264_pic_input_t *pic)
     in->qgen[pic->cur_slot]++;
     if (in->deferred) {             /* keep the block; recon_cpu_advance launches it */
         struct cpu_qpic *e;
+        pthread_mutex_lock(&in->q_mu);
         if (in->q_n == in->q_cap) {
             uint32_t ncap = in->q_cap ? in->q_cap * 2 : 32, k;
             struct cpu_qpic *nq = (struct cpu_qpic *)calloc(ncap, sizeof *nq);
@@ -641,6 +647,7 @@ static int cpu_pic_submit(h264_backend_t *be, void *inst, h264_pic_input_t *pic)
         e->block = (uint8_t *)malloc(pic->block_used); memcpy(e->block, pic->block, pic->block_used);
         e->used = pic->block_used; e->cur_slot = pic->cur_slot; e->gate_gen = in->popped[pic->cur_slot];
         __atomic_fetch_add(&in->q_n, 1, __ATOMIC_RELEASE);
+        pthread_mutex_unlock(&in->q_mu);
         return 0;
     }
     in->lgen[pic->cur_slot]++;
@@ -652,26 +659,32 @@ uint32_t recon_cpu_advance(void *ctx)
 {
     uint32_t i, launched = 0, n;
     cpu_inst_t *list[4096];
+    pthread_mutex_lock(&g_adv_mu);
     pthread_mutex_lock(&g_reg_mu);
     n = g_reg_n; memcpy(list, g_reg, n * sizeof list[0]);
     pthread_mutex_unlock(&g_reg_mu);
     for (i = 0; i < n; i++) {
         cpu_inst_t *in = list[i];
-        struct cpu_qpic *e;
-        uint8_t *saved; uint32_t saved_used;
-        if (in->ctx != ctx || !in->q_n) continue;
-        e = &in->q[in->q_head];
-        if ((int32_t)(__atomic_load_n(&in->released[e->cur_slot], __ATOMIC_ACQUIRE) - e->gate_gen) < 0) continue;
-        saved = in->pic.block; saved_used = in->pic.block_used;
-        in->pic.block = e->block; in->pic.block_used = e->used; in->pic.cur_slot = e->cur_slot;
-        cpu_reconstruct(in, &in->pic);
-        in->pic.block = saved; in->pic.block_used = saved_used;
-        free(e->block);
+        struct cpu_qpic q;
+        h264_pic_input_t tmp;
+        if (in->ctx != ctx || !__atomic_load_n(&in->q_n, __ATOMIC_ACQUIRE)) continue;
+        pthread_mutex_lock(&in->q_mu);
+        q = in->q[in->q_head];
+        if ((int32_t)(__atomic_load_n(&in->released[q.cur_slot], __ATOMIC_ACQUIRE) - q.gate_gen) < 0) { pthread_mutex_unlock(&in->q_mu); continue; }
         in->q_head = (in->q_head + 1) % in->q_cap;
-        __atomic_fetch_add(&in->lgen[e->cur_slot], 1, __ATOMIC_RELEASE);
-        __atomic_fetch_sub(&in->q_n, 1, __ATOMIC_RELEASE);
+        __atomic_fetch_sub(&in->q_n, 1, __ATOMIC_RELEASE);      /* head and count move together: the parser thread appends at head + count */
+        pthread_mutex_unlock(&in->q_mu);
+        /* the instance's own input buffer belongs to its parser thread, which may be filling the next block right now:
+         * reconstruct from a private descriptor (records / slots are only written here) */
+        memset(&tmp, 0, sizeof tmp);
+        tmp.mbs = in->pic.mbs; tmp.coef = in->pic.coef; tmp.coef_cap = in->pic.coef_cap;
+        tmp.block = q.block; tmp.block_used = q.used; tmp.cur_slot = q.cur_slot;
+        cpu_reconstruct(in, &tmp);
+        free(q.block);
+        __atomic_fetch_add(&in->lgen[q.cur_slot], 1, __ATOMIC_RELEASE);
         launched++;
     }
+    pthread_mutex_unlock(&g_adv_mu);
     return launched;
 }
 static int cpu_reconstruct(cpu_inst_t *in, h264_pic_input_t *pic)
