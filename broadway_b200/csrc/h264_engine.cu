@@ -84,6 +84,7 @@ struct PicBuf {
     KpMbCtx *d_ctx; KpResult *d_res;
     cudaEvent_t parsed;            /* (not owned) event of the Kp launch that parses this picture */
     uint32_t parse_seq;            /* which Kp launch; 0: not launched yet */
+    int parse_slot;                /* index of the launch's ParseScratch (its `done` event is re-recorded by later launches of the slot) */
     int block_on_device;           /* the block was copied to d_block when the picture was submitted (be_pic_submit) */
     uint32_t gate_gen;             /* generation of the frame slot's host mirror that must have been released before this picture is launched */
     int tape_parse, tape_last_round;   /* retained runs: tape index of the Kp launch that fills / of the last round that read this buffer */
@@ -157,6 +158,7 @@ struct ParseScratch {              /* one Kp launch */
     bool used;
     uint32_t ctas;                 /* exclusive mode: SMs the launch owns while it runs */
     uint32_t seq;                  /* parse_seq of the launch */
+    bool finished;                 /* the launch has been seen finished (h264b200EngineDrive) */
 };
 
 struct h264b200_engine {
@@ -180,6 +182,7 @@ struct h264b200_engine {
     ParseScratch pscr[NPAR];
     int next_pscr;
     uint32_t parse_seq;
+    uint32_t n_unparsed;           /* device-parse pictures queued and not yet handed to Kp (engine mutex) */
     KpTables *d_tables;
     uint32_t window, parse_threshold;
     uint32_t n_inst_hint; size_t inst_budget;   /* h264b200EngineSetStreams: instances to expect, device bytes each may spend on look-ahead buffers */
@@ -324,9 +327,10 @@ static int launch_parse(h264b200_engine *e, std::vector<PicBuf *> &list)
     const uint32_t n = (uint32_t)list.size();
     const bool retain = (e->flags & H264B200_ENGINE_RETAIN) != 0;
     ParseScratch &ps = e->pscr[e->next_pscr];
+    const int pslot = e->next_pscr;
     const int stream = e->kp_on_comp ? -1 : e->next_pscr;
     e->next_pscr = (e->next_pscr + 1) % NPAR;
-    if (ps.used) cudaEventSynchronize(ps.done);
+    if (ps.used && !ps.finished) cudaEventSynchronize(ps.done);
     if (ps.cap < n) {
         if (ps.h_pics) cudaFreeHost(ps.h_pics);
         if (ps.d_pics) cudaFree(ps.d_pics);
@@ -373,9 +377,10 @@ static int launch_parse(h264b200_engine *e, std::vector<PicBuf *> &list)
         KpPic &kp = ps.h_pics[i];
         kp.block = d_block; kp.mbs = p->d_mbs; kp.coef = p->d_coef; kp.ctx = p->d_ctx; kp.coef_cap = p->d_coef_cap; kp.pad = 0; kp.res = p->d_res;
         p->parsed = retain ? ret->ev : ps.done;
-        p->parse_seq = e->parse_seq;
+        p->parse_seq = e->parse_seq; p->parse_slot = pslot;
     }
     e->st.h2d_bytes += in_bytes;
+    e->n_unparsed = e->n_unparsed > n ? e->n_unparsed - n : 0;
     cudaStream_t s = stream < 0 ? e->s_comp : e->s_parse[stream];
     cudaEventRecord(e->ev_h2d, e->s_h2d);
     cudaStreamWaitEvent(s, e->ev_h2d, 0);
@@ -386,7 +391,7 @@ static int launch_parse(h264b200_engine *e, std::vector<PicBuf *> &list)
     kp_launch(e, kb, s);
     tl_end(e, s);
     e->st.kernel_launches++; e->st.kp_launches++; e->st.kp_pictures += n;
-    cudaEventRecord(ps.done, s); ps.used = true; ps.ctas = e->kp_sms ? kp_ctas(e, n) : 0; ps.seq = e->parse_seq;
+    cudaEventRecord(ps.done, s); ps.used = true; ps.ctas = e->kp_sms ? kp_ctas(e, n) : 0; ps.seq = e->parse_seq; ps.finished = false;
     if (retain) {
         cudaEventRecord(ret->ev, s);
         ret->kp = kb;
@@ -450,7 +455,12 @@ static uint32_t launch_round(h264b200_engine *e, std::vector<PicBuf *> &list)
         memset(&j, 0, sizeof j);
         if (in->dev_parse) {
             /* records and slots are where kernel Kp left them; its launch must have finished */
-            if (p->parse_seq != last_parse_seq) { cudaStreamWaitEvent(e->s_comp, p->parsed, 0); last_parse_seq = p->parse_seq; }
+            if (p->parse_seq != last_parse_seq) {
+                /* the slot's event may have been re-recorded by a LATER launch — then this picture's launch finished long ago
+                 * (a slot is reused only after its launch ended) and waiting on the event would wait for the wrong launch */
+                if (retain || e->pscr[p->parse_slot].seq == p->parse_seq) cudaStreamWaitEvent(e->s_comp, p->parsed, 0);
+                last_parse_seq = p->parse_seq;
+            }
             j.kp_res = p->d_res;
             pl.k0 = pl.k1 = pl.k3 = pl.k3c = pl.k4 = true;
             if (pic->has_p_slice) pl.k2 = true;
@@ -572,7 +582,8 @@ static uint32_t launch_round(h264b200_engine *e, std::vector<PicBuf *> &list)
             e->st.d2h_bytes += in->frame_bytes;
         }
         in->slot_ready[slot] = sc.d2h_done;
-        in->slot_flags[slot] = 2; in->slot_lgen[slot]++;
+        in->slot_flags[slot] = 2;
+        __atomic_store_n(&in->slot_lgen[slot], in->slot_lgen[slot] + 1, __ATOMIC_RELEASE);   /* be_frame_state reads these without the mutex */
     }
     cudaMemcpyAsync(e->h_err, e->d_err, sizeof(uint32_t), cudaMemcpyDeviceToHost, e->s_d2h);
     tl_end(e, e->s_d2h);
@@ -658,46 +669,53 @@ static uint32_t advance_all_locked(h264b200_engine *e)
 }
 
 /* engine mutex held.  One step of the FREE-RUNNING schedule (h264b200EngineDrive): what a dedicated scheduling thread
- * calls every few hundred microseconds while worker threads submit pictures and collect outputs on their own.
- *   Kp: as soon as `parse_threshold` unparsed pictures are queued (`relaxed` >= 1: any) and SMs of Kp's share are free, a
- *       launch over as many pictures as fit those SMs — the oldest unparsed picture of every instance first, then the
- *       second oldest ... so that a truncated launch still serves every stream;
- *   round: the oldest queued picture of every instance whose Kp launch has finished, once most instances that have anything
- *       queued are ready (`relaxed` >= 2: any), while fewer than DRIVE_ROUNDS rounds are on the device (launched, copy-out not finished):
- *       enough to keep kernels and copy-out busy back to back, few enough that a picture's latency stays bounded.
+ * calls a few thousand times per second while worker threads submit pictures and collect outputs on their own.  A call
+ * that finds nothing to launch costs a handful of event queries.
+ *   Kp: as soon as `parse_threshold` unparsed pictures are queued and SMs of Kp's share are free, a launch over as many
+ *       pictures as fit those SMs — the oldest unparsed picture of every instance first, then the second oldest ..., in
+ *       whole levels, so that the streams stay in step and the rounds stay full.  Fewer than the threshold are only
+ *       launched when no Kp launch is running at all and the caller reports that its workers are idle (`idle`): the
+ *       look-ahead windows are full or the streams are ending, so waiting would not bring more.
+ *   round: the oldest queued picture of every instance whose Kp launch has FINISHED (a round then starts at once and its
+ *       buffers come back soon), once at least 7 of 8 instances that have anything queued are ready — under the same
+ *       "nothing else will happen" condition any — while fewer than DRIVE_ROUNDS rounds are on the device (launched,
+ *       copy-out not finished): enough to keep kernels and copy-out busy back to back.
  * *kp_pics = pictures handed to Kp by this call.  Returns the pictures of the round launched (0: none). */
 #define DRIVE_ROUNDS 3
-static uint32_t drive_locked(h264b200_engine *e, int relaxed, uint32_t *kp_pics)
+static uint32_t drive_locked(h264b200_engine *e, int idle, uint32_t *kp_pics)
 {
     set_device(e);
     if (kp_pics) *kp_pics = 0;
-    /* ---- Kp ---- */
-    uint32_t unparsed = 0, with_unparsed = 0;
-    for (Inst *in : e->insts) {
-        if (!in->dev_parse) continue;
-        uint32_t k = 0;
-        for (PicBuf *p : *in->fifo) if (!p->parse_seq) k++;
-        unparsed += k; with_unparsed += k != 0;
+    /* Kp launches still running (a slot once seen finished is not queried again) */
+    uint32_t running[NPAR], busy_ctas = 0; int n_running = 0;
+    for (int k = 0; k < NPAR; k++) {
+        ParseScratch &ps = e->pscr[k];
+        if (!ps.used || ps.finished) continue;
+        if (cudaEventQuery(ps.done) == cudaSuccess) { ps.finished = true; continue; }
+        running[n_running++] = ps.seq; busy_ctas += ps.ctas;
     }
-    if (unparsed && (unparsed >= e->parse_threshold || relaxed)) {
+    /* ---- Kp ---- */
+    const uint32_t unparsed = e->n_unparsed;
+    if (unparsed && (unparsed >= e->parse_threshold || (idle && n_running == 0))) {
         const ParseScratch &nps = e->pscr[e->next_pscr];
-        bool go = !nps.used || cudaEventQuery(nps.done) == cudaSuccess;
+        bool go = !nps.used || nps.finished;
         uint32_t take = unparsed > 8192 ? 8192 : unparsed;
+        uint32_t with_unparsed = 0;
+        if (go) for (Inst *in : e->insts) {
+            if (!in->dev_parse) continue;
+            for (PicBuf *p : *in->fifo) if (!p->parse_seq) { with_unparsed++; break; }
+        }
         if (go && e->kp_sms) {
-            uint32_t busy = 0;
-            for (int k = 0; k < NPAR; k++) if (e->pscr[k].used && e->pscr[k].ctas && cudaEventQuery(e->pscr[k].done) != cudaSuccess) busy += e->pscr[k].ctas;
-            const uint32_t free_ctas = busy < e->kp_sms ? e->kp_sms - busy : 0;
-            /* a launch worth its latency: all that is queued, or at least the threshold's worth of SMs (anything when nothing runs) */
-            const uint32_t min_ctas = relaxed ? 1 : (e->parse_threshold + 31) / 32;
+            const uint32_t free_ctas = busy_ctas < e->kp_sms ? e->kp_sms - busy_ctas : 0;
+            const uint32_t min_ctas = (e->parse_threshold + 31) / 32;     /* a launch worth its latency */
             if (free_ctas >= (take + 31) / 32) ;
-            else if (free_ctas >= min_ctas || (busy == 0 && free_ctas)) {
+            else if (free_ctas >= min_ctas || (n_running == 0 && free_ctas)) {
                 take = free_ctas * 32;
-                if (take >= with_unparsed) take -= take % with_unparsed;     /* whole levels: the streams stay in step, rounds stay full */
+                if (with_unparsed && take >= with_unparsed) take -= take % with_unparsed;   /* whole levels */
             }
             else go = false;
         }
-        if (go) {
-            /* the oldest unparsed picture of every instance, then the second oldest ...: a truncated launch serves every stream */
+        if (go && take) {
             std::vector<PicBuf *> &pl = e->tmp_parse; pl.clear();
             for (uint32_t level = 0; pl.size() < take; level++) {
                 bool any = false;
@@ -711,7 +729,10 @@ static uint32_t drive_locked(h264b200_engine *e, int relaxed, uint32_t *kp_pics)
             const uint32_t n = (uint32_t)pl.size();
             if (n) {
                 if (launch_parse(e, pl)) { for (PicBuf *p : pl) p->inst->slot_flags[p->in.cur_slot] |= 4; }
-                else if (kp_pics) *kp_pics = n;
+                else {
+                    if (kp_pics) *kp_pics = n;
+                    running[n_running < NPAR ? n_running++ : NPAR - 1] = e->parse_seq;
+                }
             }
         }
     }
@@ -721,10 +742,6 @@ static uint32_t drive_locked(h264b200_engine *e, int relaxed, uint32_t *kp_pics)
     if (in_flight >= DRIVE_ROUNDS) return 0;
     std::vector<PicBuf *> &rl = e->tmp_round; rl.clear();
     uint32_t nonempty = 0;
-    /* only pictures whose Kp launch has FINISHED go into a round (strict mode): a round then starts at once, its
-     * buffers come back soon, and no worker ever waits behind a round that itself waits for a 0.2 s parse */
-    uint32_t running[NPAR]; int n_running = 0;
-    for (int k = 0; k < NPAR; k++) if (e->pscr[k].used && cudaEventQuery(e->pscr[k].done) != cudaSuccess) running[n_running++] = e->pscr[k].seq;
     for (Inst *in : e->insts) {
         if (in->fifo->empty()) continue;
         nonempty++;
@@ -739,7 +756,7 @@ static uint32_t drive_locked(h264b200_engine *e, int relaxed, uint32_t *kp_pics)
         rl.push_back(p);
     }
     if (rl.empty()) return 0;
-    if (relaxed < 2 && (uint32_t)rl.size() * 8 < nonempty * 7) return 0;      /* stragglers: their pictures are in the next Kp launch, or their output is about to be released */
+    if ((uint32_t)rl.size() * 8 < nonempty * 7 && !(idle && n_running == 0 && in_flight == 0)) return 0;
     for (PicBuf *p : rl) { p->inst->fifo->pop_front(); p->inst->n_pending.fetch_sub(1, std::memory_order_release); }
     launch_round(e, rl);
     return (uint32_t)rl.size();
@@ -865,7 +882,7 @@ static void be_inst_destroy(h264_backend_t *be, void *inst)
                 if (!advance_all_locked(e)) break;
             }
         }
-        while (!in->fifo->empty()) { in->fifo->front()->state = 0; in->fifo->pop_front(); }
+        while (!in->fifo->empty()) { if (in->dev_parse && !in->fifo->front()->parse_seq && e->n_unparsed) e->n_unparsed--; in->fifo->front()->state = 0; in->fifo->pop_front(); }
         in->n_pending.store(0);
         keep = !e->retained.empty();           /* retained batches name this instance's frame pool and parse buffers */
         if (keep) e->zombies.push_back(in);
@@ -932,13 +949,15 @@ static int be_pic_submit(h264_backend_t *be, void *inst, h264_pic_input_t *pic)
 {
     h264b200_engine *e = (h264b200_engine *)be->ctx; Inst *in = (Inst *)inst;
     PicBuf *p = (PicBuf *)pic->priv;
-    std::lock_guard<std::mutex> lk(e->mu);
     if (in->dev_parse && pic->block && !(e->flags & H264B200_ENGINE_RETAIN) && p->d_block_cap >= pic->block_used) {
-        /* the slices travel now, from the thread that scanned them: a Kp launch then finds its input on the device and
-         * the scheduling thread is spared one copy call per picture */
+        /* the slices travel now, from the thread that scanned them, before the engine mutex is taken: a Kp launch then
+         * finds its input on the device (the copy precedes, in s_h2d, the event the launch will wait for) and the
+         * scheduling thread is spared one copy call per picture */
         set_device(e);
         if (cudaMemcpyAsync(p->d_block, pic->block, pic->block_used, cudaMemcpyHostToDevice, e->s_h2d) == cudaSuccess) p->block_on_device = 1;
     }
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (in->dev_parse) e->n_unparsed++;
     p->state = 2;
     in->slot_qgen[pic->cur_slot]++;
     /* whatever the caller still holds of this frame slot (h264b200NextOutputPictureAsync) must be released before the
@@ -1023,10 +1042,13 @@ static int be_frame_state(h264_backend_t *be, void *inst, int slot, uint32_t gen
 {
     h264b200_engine *e = (h264b200_engine *)be->ctx; Inst *in = (Inst *)inst;
     if (slot < 0 || slot >= (int)in->n_slots) return -1;
-    std::lock_guard<std::mutex> lk(e->mu);             /* slot_lgen / slot_ready are written by the launching thread under the same mutex */
+    /* No mutex: workers poll this for every stream while the scheduling thread holds the mutex to launch.  The launching
+     * thread publishes slot_ready / slot_flags BEFORE it advances slot_lgen (release); a later picture cannot be launched
+     * into the slot before the caller released this one, so what is read behind the acquire belongs to generation g. */
     const uint32_t g = full_gen(in, slot, gen);
-    if ((int32_t)(in->slot_lgen[slot] - g) < 0) return 2;
-    if (in->slot_lgen[slot] != g) return 0;             /* a later picture was launched into the slot: h264b200PictureWait reports that */
+    const uint32_t lg = __atomic_load_n(&in->slot_lgen[slot], __ATOMIC_ACQUIRE);
+    if ((int32_t)(lg - g) < 0) return 2;
+    if (lg != g) return 0;                              /* a later picture was launched into the slot: h264b200PictureWait reports that */
     if (in->slot_flags[slot] & 4) return -1;
     if (in->slot_flags[slot] & 2) { set_device(e); return cudaEventQuery(in->slot_ready[slot]) == cudaSuccess ? 0 : 1; }
     return 0;
@@ -1096,7 +1118,7 @@ extern "C" h264b200_engine_t *h264b200EngineCreateEx(int device, uint32_t flags)
     if (h264b200Probe(msg, sizeof msg)) { fprintf(stderr, "h264b200: %s\n", msg); return NULL; }
     if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
     h264b200_engine *e = new h264b200_engine();
-    e->device = device; e->flags = flags; e->next_scr = 0; e->next_pscr = 0; e->parse_seq = 0;
+    e->device = device; e->flags = flags; e->next_scr = 0; e->next_pscr = 0; e->parse_seq = 0; e->n_unparsed = 0;
     e->window = 1; e->eff_window = 1; e->parse_threshold = 1; e->n_inst_hint = 0; e->inst_budget = 0;
     memset(&e->st, 0, sizeof e->st); memset(e->scr, 0, sizeof e->scr); memset(e->pscr, 0, sizeof e->pscr);
     memset(e->k_ms, 0, sizeof e->k_ms); memset(e->k_bytes, 0, sizeof e->k_bytes); memset(e->k_launches, 0, sizeof e->k_launches);
@@ -1240,11 +1262,11 @@ extern "C" u32 h264b200EngineAdvance(h264b200_engine_t *e)
     std::lock_guard<std::mutex> lk(e->mu);
     return advance_locked(e, false);
 }
-extern "C" u32 h264b200EngineDrive(h264b200_engine_t *e, int relaxed, u32 *kp_pictures)
+extern "C" u32 h264b200EngineDrive(h264b200_engine_t *e, int idle, u32 *kp_pictures)
 {
     if (!e) return 0;
     std::lock_guard<std::mutex> lk(e->mu);
-    return drive_locked(e, relaxed, kp_pictures);
+    return drive_locked(e, idle, kp_pictures);
 }
 extern "C" void h264b200EngineSetWindow(h264b200_engine_t *e, uint32_t depth, uint32_t parse_threshold)
 {

@@ -285,7 +285,7 @@ static void *dev_worker_main(void *arg)
         }
         if (r->inline_drive) {                                    /* one thread for everything: a scheduling step per sweep */
             u32 kp = 0;
-            const u32 n = h264b200EngineDrive(r->e, activity ? 0 : 2, &kp);
+            const u32 n = h264b200EngineDrive(r->e, !activity, &kp);
             if (n) r->rounds++;
             if (n || kp || activity) quiet = 0;
             else if (++quiet > 20000) __atomic_store_n(&r->stop, 1, __ATOMIC_RELEASE);
@@ -293,7 +293,7 @@ static void *dev_worker_main(void *arg)
             continue;
         }
         if (activity) __atomic_fetch_add(&r->activity, activity, __ATOMIC_RELEASE);
-        else { double t0 = now_s(); idle_wait(150); w->wait_s += now_s() - t0; }
+        else { double t0 = now_s(); idle_wait(300); w->wait_s += now_s() - t0; }
     }
     __atomic_fetch_sub(&r->workers_alive, 1, __ATOMIC_RELEASE);
     return NULL;
@@ -308,7 +308,7 @@ static void *dev_driver_main(void *arg)
     uint32_t last_activity = 0, quiet = 0;
     while (__atomic_load_n(&r->workers_alive, __ATOMIC_ACQUIRE) > 0) {
         u32 kp = 0;
-        u32 n = h264b200EngineDrive(r->e, quiet >= 40 ? 2 : quiet >= 6 ? 1 : 0, &kp);
+        u32 n = h264b200EngineDrive(r->e, quiet >= 8, &kp);
         if (n) r->rounds++;
         if (n || kp) { quiet = 0; continue; }
         {
@@ -316,7 +316,7 @@ static void *dev_driver_main(void *arg)
             if (a != last_activity) { last_activity = a; quiet = 0; } else quiet++;
         }
         if (quiet > 30000) __atomic_store_n(&r->stop, 1, __ATOMIC_RELEASE);   /* ~5 s without any progress anywhere */
-        idle_wait(150);
+        idle_wait(250);
     }
     return NULL;
 }

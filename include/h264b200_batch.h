@@ -68,13 +68,14 @@ void h264b200SetReadOnlyInput(storage_t *pStorage, u32 on);
  * h264b200EngineSubmit repeats this until nothing is left that can be launched. */
 u32  h264b200EngineAdvance(h264b200_engine_t *e);
 /* One step of the free-running schedule, for a caller that dedicates a thread to the engine (h264b200DecodeStreams does):
- * call it every few hundred microseconds.  Launches kernel Kp as soon as `parse_threshold` unparsed pictures are queued
- * and SMs of Kp's share are free (sized to those SMs, oldest picture of every instance first), and ONE reconstruction
- * round once most instances with queued pictures are ready, while fewer than three rounds are on the device.
- * relaxed >= 1 drops the "enough to be worth it" condition of the Kp launch, relaxed >= 2 that of the round as well (a
- * caller that sees no progress elsewhere: end of the streams, look-ahead windows full).  *kp_pictures (may be NULL) = pictures handed to Kp by this call; returns the
- * pictures of the round it launched, 0 if none. */
-u32  h264b200EngineDrive(h264b200_engine_t *e, int relaxed, u32 *kp_pictures);
+ * call it a few thousand times per second.  Launches kernel Kp as soon as `parse_threshold` unparsed pictures are queued
+ * and SMs of Kp's share are free (sized to those SMs, oldest picture of every instance first, whole levels), and ONE
+ * reconstruction round over the pictures whose Kp launch has finished once at least 7 of 8 instances with queued pictures
+ * are ready, while fewer than three rounds are on the device.  idle != 0 = the caller's other threads have had nothing to
+ * do for a while (look-ahead windows full, or the streams are ending): when nothing is running on the device either, the
+ * "enough to be worth it" conditions are dropped.  *kp_pictures (may be NULL) = pictures handed to Kp by this call;
+ * returns the pictures of the round it launched, 0 if none. */
+u32  h264b200EngineDrive(h264b200_engine_t *e, int idle, u32 *kp_pictures);
 /* look-ahead of the device-parse path: how many pictures per instance may be queued (parse buffers are allocated for
  * depth + 2), and how many queued pictures make kernel Kp worth launching.  Call before the instances are created. */
 void h264b200EngineSetWindow(h264b200_engine_t *e, uint32_t depth, uint32_t parse_threshold);
