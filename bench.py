@@ -8,16 +8,18 @@ Workload (config.workload): BASELINE.json configs[2], "synthetic 1080p Baseline 
 (random MVs incl. quarter-pel, deblocking on)" — configs[1] (Player/tree.mp4) is absent from the
 reference mount.  Per GPU: S independent 1920x1088 streams of F pictures (1 IDR + F-1 P; all
 partition shapes, quarter-pel vectors, ~30 % coded 4x4 blocks, in-loop deblocking on) from the
-in-repo writer.  One STEP decodes all S*F pictures: F batched launches of S pictures per kernel
-family.  Weak scaling: every rank gets its own S streams.
+in-repo writer.  One STEP decodes all S*F pictures: F reconstruction rounds of S pictures per kernel
+family, fed by Kp launches over the look-ahead window of every stream.  Weak scaling: every rank gets its own S streams.
 
 Own arm prints
-  value       frames/s with records + coefficient levels already resident in HBM (retained batches
-              replayed: K1 transform, K2 inter, K3 intra, K4 deblock only; CUDA events on the
-              engine's compute stream; the replay is checked to rebuild the very same frames)
-  e2e         frames/s through the C ABI (h264b200DecodeStreams -> h264bsdDecode per NAL) from HOST
-              Annex-B bytes to HOST I420 frames: CAVLC parse on the host cores, H2D of records,
-              kernels, D2H of every frame into pinned memory — all inside the timed region
+  value       frames/s with the slices already resident in HBM: the retained tape of one decode — every launch of
+              kernel Kp (CAVLC / macroblock-layer parse on the device) and every reconstruction round (K1 transform,
+              K2 inter, K3 intra, K4 deblock) with the dependencies of the live run — replayed without host<->device
+              copies; CUDA events on the engine's compute stream; the replay is checked to rebuild the very same frames
+  e2e         frames/s through the C ABI (h264b200DecodeStreams -> h264bsdDecode per NAL) from HOST Annex-B bytes to
+              HOST I420 frames: NAL scan + slice headers + DPB on the host threads, H2D of the slices, Kp, K1..K4, D2H
+              of every frame into pinned memory — all inside the timed region (--parse host: round 1's path, slice
+              data parsed on the host cores and records uploaded)
   roofline    the kernel family with the largest share of device time, algorithmic bytes
   cpu_baseline the UNMODIFIED reference decoder (oracle/_ref/refdec, gcc -O3), one process per host core
 Reference arm (--impl reference) times that same reference build on the same streams.
@@ -191,6 +193,47 @@ def reference_arm(args, rank, world):
 
 
 # ----------------------------------------------------------------------------- own arm
+def _cpulist(text):
+    out = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        a, _, b = part.partition("-")
+        out.update(range(int(a), int(b or a) + 1))
+    return out
+
+
+def bind_to_gpu_node(local_rank, world):
+    """Multi-GPU boxes have more than one NUMA node: keep this rank's threads — and with them the pinned frame mirrors they
+    first touch — on the host cores next to its GPU (sysfs local_cpulist of the PCI device), sharing a node's cores evenly
+    between the ranks whose GPUs hang off it.  A no-op when sysfs says nothing (one node, virtual topology).  Returns a
+    note for the JSON line."""
+    try:
+        import torch
+        allowed = os.sched_getaffinity(0)
+        local = {}
+        for lr in range(world):
+            bus = torch.cuda.get_device_properties(lr).pci_bus_id if hasattr(torch.cuda.get_device_properties(lr), "pci_bus_id") else None
+            dom = getattr(torch.cuda.get_device_properties(lr), "pci_domain_id", 0)
+            dev = getattr(torch.cuda.get_device_properties(lr), "pci_device_id", 0)
+            if bus is None:
+                return "no pci id"
+            path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/local_cpulist" % (dom, bus, dev)
+            local[lr] = frozenset(_cpulist(open(path).read()) & allowed)
+        mine = local[local_rank]
+        if not mine or mine == frozenset(allowed) and world == 1:
+            return "single node"
+        peers = sorted(lr for lr in range(world) if local[lr] == mine)
+        cpus = sorted(mine)
+        share = cpus[peers.index(local_rank)::len(peers)]
+        if not share:
+            return "no share"
+        os.sched_setaffinity(0, share)
+        return "rank bound to %d of the %d cores local to its GPU" % (len(share), len(cpus))
+    except Exception as e:                                   # topology not exposed: leave the affinity alone
+        return "unbound (%s)" % type(e).__name__
+
+
 def own_arm(args, rank, local_rank, world):
     import torch
     from broadway_b200 import capi
@@ -204,6 +247,7 @@ def own_arm(args, rank, local_rank, world):
     cores = len(os.sched_getaffinity(0))
     threads = args.threads or max(1, cores // world)
     streams = make_streams(args.streams, args.frames, rank)
+    numa_note = bind_to_gpu_node(local_rank, world) if world > 1 else "single GPU"
     frames_per_step = args.streams * args.frames
     pflag = capi.ENGINE_DEVICE_PARSE if args.parse == "device" else 0
     log("[rank %d] %d streams x %d pictures, %.1f MB of Annex-B, %d parser threads" % (rank, args.streams, args.frames, sum(map(len, streams)) / 1e6, threads))
@@ -349,7 +393,7 @@ def own_arm(args, rank, local_rank, world):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": WORKLOADS[args.workload][3],
                        "width": 16 * WORKLOADS[args.workload][0], "height": 16 * WORKLOADS[args.workload][1], "streams_per_gpu": args.streams, "frames_per_stream": args.frames,
-                       "frames_per_step_per_gpu": frames_per_step, "parser_threads_per_gpu": threads, "host_cores": cores, "slice_data_parse": args.parse,
+                       "frames_per_step_per_gpu": frames_per_step, "parser_threads_per_gpu": threads, "host_cores": cores, "slice_data_parse": args.parse, "numa": numa_note,
                        "l2": "inputs larger than L2 (per step: %.0f MB of frame pools + records per GPU)" % (args.streams * 2 * WORKLOADS[args.workload][0] * WORKLOADS[args.workload][1] * 384 / 1e6 + h2d / 1e6)},
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1000.0 * e2e_s / args.steps, "timing": "wall clock between barrier+synchronize pairs around ONE streaming call over the K steps (each stream = its step repeated K times), max over ranks",

@@ -254,7 +254,7 @@ static int activate_param_sets(h264_decoder_t *d, uint32_t pps_id, int is_idr)
         no_reorder = d->no_reordering_app || sps->poc_type == 2 ||
                      (sps->vui_present && sps->bitstream_restriction && !sps->num_reorder_frames);
         h264_dpb_init(&d->dpb, sps->max_dpb_size, sps->num_ref_frames, sps->max_frame_num, no_reorder);
-        d->n_slots = d->dpb.dpb_size + 1;
+        d->n_slots = d->dpb.dpb_size + 2;        /* the DPB, the picture being decoded, and a spare (h264_dpb_rotate_spare) */
         if (!d->be) d->be = h264_default_backend();   /* CUDA engine; NULL (reason on stderr) without a usable GPU */
         if (!d->be) return -2;
         if (d->be_inst) { d->be->inst_destroy(d->be, d->be_inst); d->be_inst = NULL; }
@@ -472,6 +472,7 @@ static int begin_picture(h264_decoder_t *d)
 {
     d->pic = d->be->pic_begin(d->be, d->be_inst);
     if (!d->pic) return -1;
+    h264_dpb_rotate_spare(&d->dpb);
     d->pic->coef_used = 0; d->pic->n_intra = d->pic->n_inter = 0; d->pic->any_deblock = 0; d->pic->n_conceal = 0; d->pic->conceal_offset = 0;
     memset(d->pic->ref_slots_used, 0, sizeof d->pic->ref_slots_used);
     d->pic->block_used = 0; d->pic->has_p_slice = 0;

@@ -60,10 +60,24 @@ void h264_dpb_init(h264_dpb_t *d, uint32_t dpb_size, uint32_t max_ref_frames, ui
     d->max_frame_num = max_frame_num;
     d->no_reordering = (uint8_t)no_reordering;
     for (i = 0; i <= d->dpb_size; i++) d->buf[i].slot = (int)i;
+    d->spare_slot = (int)d->dpb_size + 1;
     d->allocated = 1;
 }
 
 int h264_dpb_current_slot(h264_dpb_t *d) { return d->buf[d->dpb_size].slot; }
+
+/* Called once per picture before anything names the current slot.  The reference decodes into the buffer the DPB just
+ * freed (dpbSize + 1 buffers, h264bsd_dpb.c:1130-1180), which here would be the frame whose copy-out to the host — or whose
+ * reader, after h264b200NextOutputPictureAsync — may still be busy with it, so the picture would have to wait.  With one
+ * buffer more than the DPB needs the freed slot rests for a picture: the new picture takes the spare, the freed slot
+ * becomes the spare.  Slots are storage identities only; which picture is a reference or waits for output is unchanged. */
+void h264_dpb_rotate_spare(h264_dpb_t *d)
+{
+    const int s = d->buf[d->dpb_size].slot;
+    if (d->spare_slot < 0) return;
+    d->buf[d->dpb_size].slot = d->spare_slot;
+    d->spare_slot = s;
+}
 
 static int output_one(h264_dpb_t *d)
 {

@@ -161,6 +161,12 @@ struct ParseScratch {              /* one Kp launch */
     bool finished;                 /* the launch has been seen finished (h264b200EngineDrive) */
 };
 
+struct CopyList {
+    std::vector<void *> dst, src; std::vector<size_t> size;
+    void clear() { dst.clear(); src.clear(); size.clear(); }
+    void add(void *d, const void *s_, size_t n) { if (n) { dst.push_back(d); src.push_back(const_cast<void *>(s_)); size.push_back(n); } }
+};
+
 struct h264b200_engine {
     int device, sm_count;
     /* H264B200_TIMELINE=file: device-side start / end of every Kp launch, reconstruction round and copy-out of the live run,
@@ -182,6 +188,8 @@ struct h264b200_engine {
     ParseScratch pscr[NPAR];
     int next_pscr;
     uint32_t parse_seq;
+    bool copy_at_submit;           /* H264B200_COPY_AT_SUBMIT=1: slices are uploaded by the thread that scanned them (measured: slower, the copy calls of 15 threads contend) */
+    bool batch_copy; CopyList cl;  /* cudaMemcpyBatchAsync usable; scratch list of the launch being built (engine mutex) */
     uint32_t n_unparsed;           /* device-parse pictures queued and not yet handed to Kp (engine mutex) */
     KpTables *d_tables;
     uint32_t window, parse_threshold;
@@ -320,6 +328,27 @@ static void tl_dump(h264b200_engine *e)
     e->tl.clear();
 }
 
+/* Many independent copies in one call (cudaMemcpyBatchAsync, CUDA 12.8+): a Kp launch uploads hundreds of slice blocks, a
+ * round downloads hundreds of frames, and one cudaMemcpyAsync each kept the scheduling thread — and the engine mutex —
+ * busy for milliseconds per launch.  Falls back to single copies if the runtime refuses the batch. */
+static int copy_list(h264b200_engine *e, CopyList &c, cudaMemcpyKind kind, cudaStream_t s)
+{
+    const size_t n = c.dst.size();
+    if (!n) return 0;
+    if (e->batch_copy && n > 1) {
+        cudaMemcpyAttributes at; memset(&at, 0, sizeof at);
+        at.srcAccessOrder = cudaMemcpySrcAccessOrderStream;
+        size_t idx0 = 0, fail = 0;
+        cudaError_t er = cudaMemcpyBatchAsync(c.dst.data(), c.src.data(), c.size.data(), n, &at, &idx0, 1, &fail, s);
+        if (er == cudaSuccess) return 0;
+        fprintf(stderr, "h264b200: cudaMemcpyBatchAsync -> %s (copy %zu of %zu); using single copies from now on\n", cudaGetErrorString(er), fail, n);
+        cudaGetLastError();
+        e->batch_copy = false;
+    }
+    for (size_t i = 0; i < n; i++) CUDA_TRY(cudaMemcpyAsync(c.dst[i], c.src[i], c.size[i], kind, s), return -1);
+    return 0;
+}
+
 /* ------------------------------------------------------------------ Kp launch */
 /* engine mutex held.  Copy the blocks of the given queued pictures to the device and parse them all in one launch. */
 static int launch_parse(h264b200_engine *e, std::vector<PicBuf *> &list)
@@ -353,6 +382,7 @@ static int launch_parse(h264b200_engine *e, std::vector<PicBuf *> &list)
     e->parse_seq++;
     if (!e->parse_seq) e->parse_seq = 1;
     uint64_t in_bytes = 0;
+    e->cl.clear();
     for (uint32_t i = 0; i < n; i++) {
         PicBuf *p = list[i]; Inst *in = p->inst; h264_pic_input_t *pic = &p->in;
         uint8_t *d_block = p->d_block;
@@ -371,14 +401,14 @@ static int launch_parse(h264b200_engine *e, std::vector<PicBuf *> &list)
             CUDA_TRY(cudaMalloc((void **)&p->d_block, p->d_block_cap), return -1);
             d_block = p->d_block;
         }
-        if (!p->block_on_device || retain)
-            CUDA_TRY(cudaMemcpyAsync(d_block, pic->block, pic->block_used, cudaMemcpyHostToDevice, e->s_h2d), return -1);
+        if (!p->block_on_device || retain) e->cl.add(d_block, pic->block, pic->block_used);
         in_bytes += pic->block_used;
         KpPic &kp = ps.h_pics[i];
         kp.block = d_block; kp.mbs = p->d_mbs; kp.coef = p->d_coef; kp.ctx = p->d_ctx; kp.coef_cap = p->d_coef_cap; kp.pad = 0; kp.res = p->d_res;
         p->parsed = retain ? ret->ev : ps.done;
         p->parse_seq = e->parse_seq; p->parse_slot = pslot;
     }
+    if (copy_list(e, e->cl, cudaMemcpyHostToDevice, e->s_h2d)) return -1;
     e->st.h2d_bytes += in_bytes;
     e->n_unparsed = e->n_unparsed > n ? e->n_unparsed - n : 0;
     cudaStream_t s = stream < 0 ? e->s_comp : e->s_parse[stream];
@@ -560,6 +590,7 @@ static uint32_t launch_round(h264b200_engine *e, std::vector<PicBuf *> &list)
     cudaEventRecord(e->ev_comp, e->s_comp);
     cudaStreamWaitEvent(e->s_d2h, e->ev_comp, 0);
     tl_begin(e, 2, n, e->s_d2h);
+    e->cl.clear();
     for (uint32_t i = 0; i < n; i++) {
         PicBuf *p = list[i]; Inst *in = p->inst; int slot = p->in.cur_slot;
         uint8_t *d_frame = in->d_frames + (size_t)slot * in->frame_stride, *h_frame = in->h_frames + (size_t)slot * in->frame_stride;
@@ -572,22 +603,28 @@ static uint32_t launch_round(h264b200_engine *e, std::vector<PicBuf *> &list)
             const int items = ((rj.cw + 3) / 4) * ((rj.ch + 1) / 2);
             k5_rgba<<<(items + 255) / 256, 256, 0, e->s_d2h>>>(rj); e->st.kernel_launches++;
             if (!(e->flags & H264B200_ENGINE_NO_D2H)) {
-                cudaMemcpyAsync(in->h_rgba + (size_t)slot * in->rgba_bytes, rj.out, in->rgba_bytes, cudaMemcpyDeviceToHost, e->s_d2h);
-                cudaMemcpyAsync(h_frame + in->frame_bytes, d_frame + in->frame_bytes, sizeof(h264b200_picstat_t), cudaMemcpyDeviceToHost, e->s_d2h);
+                e->cl.add(in->h_rgba + (size_t)slot * in->rgba_bytes, rj.out, in->rgba_bytes);
+                e->cl.add(h_frame + in->frame_bytes, d_frame + in->frame_bytes, sizeof(h264b200_picstat_t));
                 e->st.d2h_bytes += in->rgba_bytes;
             }
         } else if (!(e->flags & H264B200_ENGINE_NO_D2H)) {
             /* the frame and the status words behind it: one copy */
-            cudaMemcpyAsync(h_frame, d_frame, in->frame_bytes + sizeof(h264b200_picstat_t), cudaMemcpyDeviceToHost, e->s_d2h);
+            e->cl.add(h_frame, d_frame, in->frame_bytes + sizeof(h264b200_picstat_t));
             e->st.d2h_bytes += in->frame_bytes;
         }
         in->slot_ready[slot] = sc.d2h_done;
         in->slot_flags[slot] = 2;
-        __atomic_store_n(&in->slot_lgen[slot], in->slot_lgen[slot] + 1, __ATOMIC_RELEASE);   /* be_frame_state reads these without the mutex */
     }
-    cudaMemcpyAsync(e->h_err, e->d_err, sizeof(uint32_t), cudaMemcpyDeviceToHost, e->s_d2h);
+    e->cl.add(e->h_err, e->d_err, sizeof(uint32_t));
+    copy_list(e, e->cl, cudaMemcpyDeviceToHost, e->s_d2h);
     tl_end(e, e->s_d2h);
     cudaEventRecord(sc.d2h_done, e->s_d2h);
+    /* only now is the picture "launched" for those who poll without the mutex (be_frame_state): slot_ready names an event
+     * that has been recorded for THIS round */
+    for (uint32_t i = 0; i < n; i++) {
+        Inst *in = list[i]->inst; const int slot = list[i]->in.cur_slot;
+        __atomic_store_n(&in->slot_lgen[slot], in->slot_lgen[slot] + 1, __ATOMIC_RELEASE);
+    }
     e->st.pictures += n; e->st.batches++;
     if (retain) {
         cudaEventRecord(ret->ev, e->s_comp);
@@ -949,7 +986,7 @@ static int be_pic_submit(h264_backend_t *be, void *inst, h264_pic_input_t *pic)
 {
     h264b200_engine *e = (h264b200_engine *)be->ctx; Inst *in = (Inst *)inst;
     PicBuf *p = (PicBuf *)pic->priv;
-    if (in->dev_parse && pic->block && !(e->flags & H264B200_ENGINE_RETAIN) && p->d_block_cap >= pic->block_used) {
+    if (e->copy_at_submit && in->dev_parse && pic->block && !(e->flags & H264B200_ENGINE_RETAIN) && p->d_block_cap >= pic->block_used) {
         /* the slices travel now, from the thread that scanned them, before the engine mutex is taken: a Kp launch then
          * finds its input on the device (the copy precedes, in s_h2d, the event the launch will wait for) and the
          * scheduling thread is spared one copy call per picture */
@@ -1119,6 +1156,8 @@ extern "C" h264b200_engine_t *h264b200EngineCreateEx(int device, uint32_t flags)
     if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
     h264b200_engine *e = new h264b200_engine();
     e->device = device; e->flags = flags; e->next_scr = 0; e->next_pscr = 0; e->parse_seq = 0; e->n_unparsed = 0;
+    { const char *c = getenv("H264B200_COPY_AT_SUBMIT"); e->copy_at_submit = c && atoi(c) > 0; }
+    { const char *c = getenv("H264B200_BATCH_COPY"); e->batch_copy = !(c && atoi(c) == 0); }
     e->window = 1; e->eff_window = 1; e->parse_threshold = 1; e->n_inst_hint = 0; e->inst_budget = 0;
     memset(&e->st, 0, sizeof e->st); memset(e->scr, 0, sizeof e->scr); memset(e->pscr, 0, sizeof e->pscr);
     memset(e->k_ms, 0, sizeof e->k_ms); memset(e->k_bytes, 0, sizeof e->k_bytes); memset(e->k_launches, 0, sizeof e->k_launches);

@@ -111,12 +111,14 @@ typedef struct {
     uint32_t max_ref_frames, dpb_size, max_frame_num, max_long_term_idx;
     uint32_t num_ref_frames, fullness, prev_ref_frame_num;
     uint8_t  no_reordering, flushed, last_has_mmco5, allocated;
+    int      spare_slot;               /* a frame slot beyond dpb_size + 1, rotated in at every picture (h264_dpb_rotate_spare) */
 } h264_dpb_t;
 
 #define H264_NO_LONG_TERM 0xFFFF
 
 void h264_dpb_init(h264_dpb_t *d, uint32_t dpb_size, uint32_t max_ref_frames, uint32_t max_frame_num, int no_reordering);
 int  h264_dpb_current_slot(h264_dpb_t *d);
+void h264_dpb_rotate_spare(h264_dpb_t *d);
 int  h264_dpb_check_gaps(h264_dpb_t *d, uint32_t frame_num, int is_ref, int gaps_allowed);
 void h264_dpb_init_ref_list(h264_dpb_t *d);
 int  h264_dpb_reorder(h264_dpb_t *d, const h264_slice_hdr_t *sh);
