@@ -189,7 +189,8 @@ struct h264b200_engine {
     int next_pscr;
     uint32_t parse_seq;
     bool copy_at_submit;           /* H264B200_COPY_AT_SUBMIT=1: slices are uploaded by the thread that scanned them (measured: slower, the copy calls of 15 threads contend) */
-    bool batch_copy; CopyList cl;  /* cudaMemcpyBatchAsync usable; scratch list of the launch being built (engine mutex) */
+    CopyList cl;                   /* scratch list of the launch being built (engine mutex) */
+    double drv_locked_ms, drv_copy_ms, drv_locked_max; uint64_t drv_polls, drv_launches;   /* H264B200_TIMELINE: host time of the scheduling steps */
     uint32_t n_unparsed;           /* device-parse pictures queued and not yet handed to Kp (engine mutex) */
     KpTables *d_tables;
     uint32_t window, parse_threshold;
@@ -315,6 +316,8 @@ static void tl_dump(h264b200_engine *e)
 {
     if (!e->tl_path) return;
     FILE *f = fopen(e->tl_path, "a");
+    if (e->drv_polls) fprintf(stderr, "h264b200 scheduling thread: %llu steps, %llu launched something: %.1f ms under the mutex (max %.2f), %.1f ms issuing copy-outs\n",
+                              (unsigned long long)e->drv_polls, (unsigned long long)e->drv_launches, e->drv_locked_ms, e->drv_locked_max, e->drv_copy_ms);
     if (f) {
         fprintf(f, "kind,pictures,host_launch_ms,gpu_start_ms,gpu_end_ms\n");
         for (auto &t : e->tl) {
@@ -328,24 +331,10 @@ static void tl_dump(h264b200_engine *e)
     e->tl.clear();
 }
 
-/* Many independent copies in one call (cudaMemcpyBatchAsync, CUDA 12.8+): a Kp launch uploads hundreds of slice blocks, a
- * round downloads hundreds of frames, and one cudaMemcpyAsync each kept the scheduling thread — and the engine mutex —
- * busy for milliseconds per launch.  Falls back to single copies if the runtime refuses the batch. */
-static int copy_list(h264b200_engine *e, CopyList &c, cudaMemcpyKind kind, cudaStream_t s)
+/* issue the copies of a list, one cudaMemcpyAsync each */
+static int copy_list(CopyList &c, cudaMemcpyKind kind, cudaStream_t s)
 {
-    const size_t n = c.dst.size();
-    if (!n) return 0;
-    if (e->batch_copy && n > 1) {
-        cudaMemcpyAttributes at; memset(&at, 0, sizeof at);
-        at.srcAccessOrder = cudaMemcpySrcAccessOrderStream;
-        size_t idx0 = 0, fail = 0;
-        cudaError_t er = cudaMemcpyBatchAsync(c.dst.data(), c.src.data(), c.size.data(), n, &at, &idx0, 1, &fail, s);
-        if (er == cudaSuccess) return 0;
-        fprintf(stderr, "h264b200: cudaMemcpyBatchAsync -> %s (copy %zu of %zu); using single copies from now on\n", cudaGetErrorString(er), fail, n);
-        cudaGetLastError();
-        e->batch_copy = false;
-    }
-    for (size_t i = 0; i < n; i++) CUDA_TRY(cudaMemcpyAsync(c.dst[i], c.src[i], c.size[i], kind, s), return -1);
+    for (size_t i = 0; i < c.dst.size(); i++) CUDA_TRY(cudaMemcpyAsync(c.dst[i], c.src[i], c.size[i], kind, s), return -1);
     return 0;
 }
 
@@ -408,7 +397,7 @@ static int launch_parse(h264b200_engine *e, std::vector<PicBuf *> &list)
         p->parsed = retain ? ret->ev : ps.done;
         p->parse_seq = e->parse_seq; p->parse_slot = pslot;
     }
-    if (copy_list(e, e->cl, cudaMemcpyHostToDevice, e->s_h2d)) return -1;
+    if (copy_list(e->cl, cudaMemcpyHostToDevice, e->s_h2d)) return -1;
     e->st.h2d_bytes += in_bytes;
     e->n_unparsed = e->n_unparsed > n ? e->n_unparsed - n : 0;
     cudaStream_t s = stream < 0 ? e->s_comp : e->s_parse[stream];
@@ -434,7 +423,44 @@ static int launch_parse(h264b200_engine *e, std::vector<PicBuf *> &list)
 
 /* ------------------------------------------------------------------ round launch */
 /* engine mutex held.  Reconstruct the given pictures (at most one per instance) as one batch. */
-static uint32_t launch_round(h264b200_engine *e, std::vector<PicBuf *> &list)
+/* The copy-out half of a round: per picture one copy of the finished frame (and the status words behind it) into its pinned
+ * mirror, then the event that says they have arrived, then — only then — the pictures are published as launched to those
+ * who poll without the mutex (be_frame_state): slot_ready names an event that has been recorded for THIS round.
+ * Touches no engine state, so the free-running schedule runs it outside the engine mutex: hundreds of copy calls per round
+ * would otherwise keep every submitting worker waiting. */
+struct CopyOut { std::vector<PicBuf *> list; cudaEvent_t d2h_done; };
+static void copy_out_issue(h264b200_engine *e, CopyOut &co)
+{
+    const uint32_t n = (uint32_t)co.list.size();
+    tl_begin(e, 2, n, e->s_d2h);
+    for (uint32_t i = 0; i < n; i++) {
+        PicBuf *p = co.list[i]; Inst *in = p->inst; const int slot = p->in.cur_slot;
+        uint8_t *d_frame = in->d_frames + (size_t)slot * in->frame_stride, *h_frame = in->h_frames + (size_t)slot * in->frame_stride;
+        if (in->out_format == H264B200_OUT_RGBA && in->d_rgba) {
+            /* K5 runs on the copy-out stream: it only reads the finished frame */
+            RgbaJob rj; rj.frame = d_frame; rj.out = in->d_rgba + (size_t)slot * in->rgba_bytes;
+            rj.W = (int)in->wm * 16; rj.H = (int)in->hm * 16; rj.cl = in->cl; rj.ct = in->ct; rj.cw = in->cw; rj.ch = in->ch;
+            const int items = ((rj.cw + 3) / 4) * ((rj.ch + 1) / 2);
+            k5_rgba<<<(items + 255) / 256, 256, 0, e->s_d2h>>>(rj);
+            if (!(e->flags & H264B200_ENGINE_NO_D2H)) {
+                cudaMemcpyAsync(in->h_rgba + (size_t)slot * in->rgba_bytes, rj.out, in->rgba_bytes, cudaMemcpyDeviceToHost, e->s_d2h);
+                cudaMemcpyAsync(h_frame + in->frame_bytes, d_frame + in->frame_bytes, sizeof(h264b200_picstat_t), cudaMemcpyDeviceToHost, e->s_d2h);
+            }
+        } else if (!(e->flags & H264B200_ENGINE_NO_D2H)) {
+            /* the frame and the status words behind it: one copy */
+            cudaMemcpyAsync(h_frame, d_frame, in->frame_bytes + sizeof(h264b200_picstat_t), cudaMemcpyDeviceToHost, e->s_d2h);
+        }
+    }
+    cudaMemcpyAsync(e->h_err, e->d_err, sizeof(uint32_t), cudaMemcpyDeviceToHost, e->s_d2h);
+    tl_end(e, e->s_d2h);
+    cudaEventRecord(co.d2h_done, e->s_d2h);
+    for (uint32_t i = 0; i < n; i++) {
+        Inst *in = co.list[i]->inst; const int slot = co.list[i]->in.cur_slot;
+        __atomic_store_n(&in->slot_lgen[slot], in->slot_lgen[slot] + 1, __ATOMIC_RELEASE);
+    }
+}
+
+static uint32_t launch_round(h264b200_engine *e, std::vector<PicBuf *> &list, CopyOut *defer = nullptr)
 {
     uint32_t n = (uint32_t)list.size();
     if (!n) return 0;
@@ -589,42 +615,17 @@ static uint32_t launch_round(h264b200_engine *e, std::vector<PicBuf *> &list)
     cudaEventRecord(sc.done, e->s_comp); sc.used = true;
     cudaEventRecord(e->ev_comp, e->s_comp);
     cudaStreamWaitEvent(e->s_d2h, e->ev_comp, 0);
-    tl_begin(e, 2, n, e->s_d2h);
-    e->cl.clear();
     for (uint32_t i = 0; i < n; i++) {
-        PicBuf *p = list[i]; Inst *in = p->inst; int slot = p->in.cur_slot;
-        uint8_t *d_frame = in->d_frames + (size_t)slot * in->frame_stride, *h_frame = in->h_frames + (size_t)slot * in->frame_stride;
+        PicBuf *p = list[i]; Inst *in = p->inst; const int slot = p->in.cur_slot;
         p->done = sc.done;
         p->state = 3;
-        if (in->out_format == H264B200_OUT_RGBA && in->d_rgba) {
-            /* K5 runs on the copy-out stream: it only reads the finished frame */
-            RgbaJob rj; rj.frame = d_frame; rj.out = in->d_rgba + (size_t)slot * in->rgba_bytes;
-            rj.W = (int)in->wm * 16; rj.H = (int)in->hm * 16; rj.cl = in->cl; rj.ct = in->ct; rj.cw = in->cw; rj.ch = in->ch;
-            const int items = ((rj.cw + 3) / 4) * ((rj.ch + 1) / 2);
-            k5_rgba<<<(items + 255) / 256, 256, 0, e->s_d2h>>>(rj); e->st.kernel_launches++;
-            if (!(e->flags & H264B200_ENGINE_NO_D2H)) {
-                e->cl.add(in->h_rgba + (size_t)slot * in->rgba_bytes, rj.out, in->rgba_bytes);
-                e->cl.add(h_frame + in->frame_bytes, d_frame + in->frame_bytes, sizeof(h264b200_picstat_t));
-                e->st.d2h_bytes += in->rgba_bytes;
-            }
-        } else if (!(e->flags & H264B200_ENGINE_NO_D2H)) {
-            /* the frame and the status words behind it: one copy */
-            e->cl.add(h_frame, d_frame, in->frame_bytes + sizeof(h264b200_picstat_t));
-            e->st.d2h_bytes += in->frame_bytes;
-        }
         in->slot_ready[slot] = sc.d2h_done;
         in->slot_flags[slot] = 2;
+        if (in->out_format == H264B200_OUT_RGBA && in->d_rgba) e->st.kernel_launches++;      /* K5, launched with the copy-out */
+        if (!(e->flags & H264B200_ENGINE_NO_D2H)) e->st.d2h_bytes += (in->out_format == H264B200_OUT_RGBA && in->d_rgba) ? in->rgba_bytes : in->frame_bytes;
     }
-    e->cl.add(e->h_err, e->d_err, sizeof(uint32_t));
-    copy_list(e, e->cl, cudaMemcpyDeviceToHost, e->s_d2h);
-    tl_end(e, e->s_d2h);
-    cudaEventRecord(sc.d2h_done, e->s_d2h);
-    /* only now is the picture "launched" for those who poll without the mutex (be_frame_state): slot_ready names an event
-     * that has been recorded for THIS round */
-    for (uint32_t i = 0; i < n; i++) {
-        Inst *in = list[i]->inst; const int slot = list[i]->in.cur_slot;
-        __atomic_store_n(&in->slot_lgen[slot], in->slot_lgen[slot] + 1, __ATOMIC_RELEASE);
-    }
+    if (defer) { defer->list = list; defer->d2h_done = sc.d2h_done; }      /* h264b200EngineDrive issues the copies after it has let go of the mutex */
+    else { CopyOut co; co.list = list; co.d2h_done = sc.d2h_done; copy_out_issue(e, co); }
     e->st.pictures += n; e->st.batches++;
     if (retain) {
         cudaEventRecord(ret->ev, e->s_comp);
@@ -719,7 +720,7 @@ static uint32_t advance_all_locked(h264b200_engine *e)
  *       copy-out not finished): enough to keep kernels and copy-out busy back to back.
  * *kp_pics = pictures handed to Kp by this call.  Returns the pictures of the round launched (0: none). */
 #define DRIVE_ROUNDS 3
-static uint32_t drive_locked(h264b200_engine *e, int idle, uint32_t *kp_pics)
+static uint32_t drive_locked(h264b200_engine *e, int idle, uint32_t *kp_pics, CopyOut *defer)
 {
     set_device(e);
     if (kp_pics) *kp_pics = 0;
@@ -795,8 +796,7 @@ static uint32_t drive_locked(h264b200_engine *e, int idle, uint32_t *kp_pics)
     if (rl.empty()) return 0;
     if ((uint32_t)rl.size() * 8 < nonempty * 7 && !(idle && n_running == 0 && in_flight == 0)) return 0;
     for (PicBuf *p : rl) { p->inst->fifo->pop_front(); p->inst->n_pending.fetch_sub(1, std::memory_order_release); }
-    launch_round(e, rl);
-    return (uint32_t)rl.size();
+    return launch_round(e, rl, defer);
 }
 
 /* ------------------------------------------------------- backend callbacks */
@@ -1156,8 +1156,8 @@ extern "C" h264b200_engine_t *h264b200EngineCreateEx(int device, uint32_t flags)
     if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
     h264b200_engine *e = new h264b200_engine();
     e->device = device; e->flags = flags; e->next_scr = 0; e->next_pscr = 0; e->parse_seq = 0; e->n_unparsed = 0;
+    e->drv_locked_ms = e->drv_copy_ms = e->drv_locked_max = 0; e->drv_polls = e->drv_launches = 0;
     { const char *c = getenv("H264B200_COPY_AT_SUBMIT"); e->copy_at_submit = c && atoi(c) > 0; }
-    { const char *c = getenv("H264B200_BATCH_COPY"); e->batch_copy = !(c && atoi(c) == 0); }
     e->window = 1; e->eff_window = 1; e->parse_threshold = 1; e->n_inst_hint = 0; e->inst_budget = 0;
     memset(&e->st, 0, sizeof e->st); memset(e->scr, 0, sizeof e->scr); memset(e->pscr, 0, sizeof e->pscr);
     memset(e->k_ms, 0, sizeof e->k_ms); memset(e->k_bytes, 0, sizeof e->k_bytes); memset(e->k_launches, 0, sizeof e->k_launches);
@@ -1304,8 +1304,22 @@ extern "C" u32 h264b200EngineAdvance(h264b200_engine_t *e)
 extern "C" u32 h264b200EngineDrive(h264b200_engine_t *e, int idle, u32 *kp_pictures)
 {
     if (!e) return 0;
-    std::lock_guard<std::mutex> lk(e->mu);
-    return drive_locked(e, idle, kp_pictures);
+    CopyOut co; co.d2h_done = nullptr;
+    u32 n, kp = 0;
+    const double t0 = e->tl_path ? host_ms_now() : 0;
+    {
+        std::lock_guard<std::mutex> lk(e->mu);
+        n = drive_locked(e, idle, &kp, &co);
+    }
+    const double t1 = e->tl_path ? host_ms_now() : 0;
+    if (!co.list.empty()) copy_out_issue(e, co);
+    if (e->tl_path) {
+        const double t2 = host_ms_now();
+        e->drv_polls++;
+        if (n || kp) { e->drv_launches++; e->drv_locked_ms += t1 - t0; if (t1 - t0 > e->drv_locked_max) e->drv_locked_max = t1 - t0; e->drv_copy_ms += t2 - t1; }
+    }
+    if (kp_pictures) *kp_pictures = kp;
+    return n;
 }
 extern "C" void h264b200EngineSetWindow(h264b200_engine_t *e, uint32_t depth, uint32_t parse_threshold)
 {

@@ -194,3 +194,19 @@ def test_host_share_1080p_equals_all_device(monkeypatch):
             assert rs.failed_streams == 0 and rs.host_streams == int(host)
         out.append(md5s)
     assert out[0] == out[1]
+
+
+def test_free_running_pipeline_is_repeatable(golden):
+    """The free-running pipeline has three kinds of threads — workers that poll picture states without the engine mutex, the
+    scheduling thread, the GPU — and the first version handed a worker a frame whose copy-out had not been issued yet
+    (the launch was published before its event was recorded).  Twenty runs at several thread counts, every picture
+    against the reference golden each time."""
+    sel = cases.SMALL
+    streams = [cases.make_stream(c) for c in sel]
+    with capi.Engine(flags=capi.ENGINE_BATCHED | DEV) as eng:
+        for rep in range(20):
+            threads = (2, 3, 4, 8, 16)[rep % 5]
+            md5s, rs = eng.decode_streams_md5(streams, threads=threads)
+            assert rs.failed_streams == 0 and rs.err_mbs == 0
+            for c, m in zip(sel, md5s):
+                assert m == golden[c[0]]["frame_md5"], (c[0], threads, rep)
