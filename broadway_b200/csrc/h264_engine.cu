@@ -352,7 +352,12 @@ static int launch_parse(h264b200_engine *e, std::vector<PicBuf *> &list)
     if (ps.cap < n) {
         if (ps.h_pics) cudaFreeHost(ps.h_pics);
         if (ps.d_pics) cudaFree(ps.d_pics);
+        /* room for the largest launch the engine makes, once: growing it later means cudaFree / cudaMalloc, which wait for
+         * everything on the device — with Kp launches of 0.2 s in flight that stalled the scheduling thread (and the
+         * mutex) for up to a second whenever a launch was a few pictures larger than the last one of its slot */
         ps.cap = n + 64;
+        if (ps.cap < e->kp_sms * 32u + 64u) ps.cap = e->kp_sms * 32u + 64u;
+        if (ps.cap < 1024) ps.cap = 1024;
         CUDA_TRY(cudaHostAlloc((void **)&ps.h_pics, ps.cap * sizeof(KpPic), cudaHostAllocDefault), return -1);
         CUDA_TRY(cudaMalloc((void **)&ps.d_pics, ps.cap * sizeof(KpPic)), return -1);
     }
@@ -476,6 +481,7 @@ static uint32_t launch_round(h264b200_engine *e, std::vector<PicBuf *> &list, Co
         if (sc.d_jobs) cudaFree(sc.d_jobs);
         sc.h_jobs = nullptr; sc.d_jobs = nullptr;
         sc.cap_jobs = n + 16;
+        if (sc.cap_jobs < (uint32_t)e->insts.size() + 16) sc.cap_jobs = (uint32_t)e->insts.size() + 16;      /* once: growing means cudaFree, which waits for the whole device */
         CUDA_TRY(cudaHostAlloc((void **)&sc.h_jobs, sc.cap_jobs * sizeof(PicJob), cudaHostAllocDefault), { sc.cap_jobs = 0; goto fail; });
         CUDA_TRY(cudaMalloc((void **)&sc.d_jobs, sc.cap_jobs * sizeof(PicJob)), { sc.cap_jobs = 0; goto fail; });
     }
@@ -483,6 +489,7 @@ static uint32_t launch_round(h264b200_engine *e, std::vector<PicBuf *> &list, Co
         if (sc.d_ctrl) cudaFree(sc.d_ctrl);
         sc.d_ctrl = nullptr;
         sc.cap_ctrl = ctrl_words + 1024;
+        { size_t all = CTRL_HEAD + 1024; for (Inst *in : e->insts) all += 2 * (size_t)in->hm; if (sc.cap_ctrl < all) sc.cap_ctrl = all; }
         CUDA_TRY(cudaMalloc((void **)&sc.d_ctrl, sc.cap_ctrl * sizeof(int32_t)), { sc.cap_ctrl = 0; goto fail; });
     }
     {

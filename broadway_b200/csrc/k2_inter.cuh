@@ -110,6 +110,14 @@ __global__ void __launch_bounds__(K2_THREADS, 8) k2_inter(Batch b)
         uint32_t r0[9], r1[9], r2[9];
         const int sh = x0 & 3, xa = x0 - sh;
         const bool inside = inter && xa >= 0 && xa + 12 <= W && y0 >= 0 && y0 + 9 <= H;
+#ifdef K2_WHATIF_NO_WINDOW_LOADS
+        /* measurement only (tools/build_cuda_variant.sh, wrong pictures): the luma window costs nothing — no loads, no
+         * alignment shifts — which bounds from below what ANY staging scheme (shared memory, TMA) could make of this kernel */
+        if (inter) {
+#pragma unroll
+            for (int r = 0; r < 9; r++) { r0[r] = mvw * (uint32_t)(r + 1); r1[r] = mvw ^ (uint32_t)(r * 0x01010101); r2[r] = mvw >> r; }
+        } else
+#endif
         if (inside) {
             const uint8_t *p = ref + (size_t)y0 * W + xa;
 #pragma unroll
@@ -134,7 +142,15 @@ __global__ void __launch_bounds__(K2_THREADS, 8) k2_inter(Batch b)
         }
 
         /* ---- interpolation on registers (k2_math.cuh; CPU-checked by tests/test_k2_math_cpu.py) ---- */
+#ifdef K2_WHATIF_NO_MATH
+        /* measurement only: the window is fetched and aligned but the luma interpolation is replaced by a copy of the
+         * integer samples — what the kernel costs as a pure data mover */
+        (void)useG; (void)useB; (void)useH; (void)useJ; (void)n_ops; (void)anyB; (void)anyH; (void)anyJ;
+#pragma unroll
+        for (int py = 0; py < 4; py++) out_rows[py] = __funnelshift_r(r0[py + 2], r1[py + 2], 16) ^ (r2[py] & 0u);
+#else
         k2m_luma4x4(r0, r1, r2, fx, fy, useG, useB, useH, useJ, n_ops, anyB, anyH, anyJ, out_rows);
+#endif
     }
 
     /* ---- luma residual + store ---- */
