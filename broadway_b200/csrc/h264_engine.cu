@@ -188,7 +188,9 @@ struct h264b200_engine {
     ParseScratch pscr[NPAR];
     int next_pscr;
     uint32_t parse_seq;
-    bool copy_at_submit;           /* H264B200_COPY_AT_SUBMIT=1: slices are uploaded by the thread that scanned them (measured: slower, the copy calls of 15 threads contend) */
+    bool copy_at_submit;           /* slices are uploaded by the thread that scanned them, when the picture is submitted (default; H264B200_COPY_AT_SUBMIT=0:
+                                      by the Kp launch, hundreds of ~230 KB copies at once — measured 14 ms per launch next to the copy-out traffic,
+                                      and the launch and the round behind it waited for them) */
     CopyList cl;                   /* scratch list of the launch being built (engine mutex) */
     double drv_locked_ms, drv_copy_ms, drv_locked_max; uint64_t drv_polls, drv_launches;   /* H264B200_TIMELINE: host time of the scheduling steps */
     uint32_t n_unparsed;           /* device-parse pictures queued and not yet handed to Kp (engine mutex) */
@@ -511,6 +513,7 @@ static uint32_t launch_round(h264b200_engine *e, std::vector<PicBuf *> &list, Co
     BatchPlan pl; memset(&pl, 0, sizeof pl);
     uint32_t mb_base = 0; size_t prog_off = CTRL_HEAD;
     uint32_t last_parse_seq = 0;
+    bool uploaded = false;
     for (uint32_t i = 0; i < n; i++) {
         PicBuf *p = list[i]; Inst *in = p->inst; h264_pic_input_t *pic = &p->in;
         h264b200_mb_t *d_mbs = p->d_mbs; int16_t *d_coef_in = p->d_coef, *d_coef = p->d_coef;
@@ -554,6 +557,7 @@ static uint32_t launch_round(h264b200_engine *e, std::vector<PicBuf *> &list, Co
             }
             /* records and coefficient slots are adjacent on both sides: one copy */
             CUDA_TRY(cudaMemcpyAsync(d_mbs, pic->mbs, rec_bytes + coef_bytes, cudaMemcpyHostToDevice, e->s_h2d), goto fail);
+            uploaded = true;
             e->st.h2d_bytes += rec_bytes + coef_bytes;
             j.n_intra = pic->n_intra; j.n_inter = pic->n_inter; j.any_deblock = pic->any_deblock;
             j.n_conceal = pic->n_conceal;
@@ -584,8 +588,10 @@ static uint32_t launch_round(h264b200_engine *e, std::vector<PicBuf *> &list, Co
     for (PicBuf *p : list) if (p->inst->n_mbs != b.uniform_mbs) b.uniform_mbs = 0;
     b.tickets = (uint32_t *)d_ctrl; b.error_flags = e->d_err; b.trace = e->trace_left > 0 ? e->d_trace : nullptr;
 
-    cudaEventRecord(e->ev_h2d, e->s_h2d);
-    cudaStreamWaitEvent(e->s_comp, e->ev_h2d, 0);
+    if (uploaded) {                /* records of host-parsed pictures; device-parsed ones have nothing in the upload stream a round depends on */
+        cudaEventRecord(e->ev_h2d, e->s_h2d);
+        cudaStreamWaitEvent(e->s_comp, e->ev_h2d, 0);
+    }
     cudaMemcpyAsync(d_jobs, sc.h_jobs, n * sizeof(PicJob), cudaMemcpyHostToDevice, e->s_comp);
     cudaMemsetAsync(d_ctrl, 0, ctrl_words * sizeof(int32_t), e->s_comp);
     tl_begin(e, 0, n, e->s_comp);
@@ -1164,7 +1170,7 @@ extern "C" h264b200_engine_t *h264b200EngineCreateEx(int device, uint32_t flags)
     h264b200_engine *e = new h264b200_engine();
     e->device = device; e->flags = flags; e->next_scr = 0; e->next_pscr = 0; e->parse_seq = 0; e->n_unparsed = 0;
     e->drv_locked_ms = e->drv_copy_ms = e->drv_locked_max = 0; e->drv_polls = e->drv_launches = 0;
-    { const char *c = getenv("H264B200_COPY_AT_SUBMIT"); e->copy_at_submit = c && atoi(c) > 0; }
+    { const char *c = getenv("H264B200_COPY_AT_SUBMIT"); e->copy_at_submit = !(c && atoi(c) == 0); }
     e->window = 1; e->eff_window = 1; e->parse_threshold = 1; e->n_inst_hint = 0; e->inst_budget = 0;
     memset(&e->st, 0, sizeof e->st); memset(e->scr, 0, sizeof e->scr); memset(e->pscr, 0, sizeof e->pscr);
     memset(e->k_ms, 0, sizeof e->k_ms); memset(e->k_bytes, 0, sizeof e->k_bytes); memset(e->k_launches, 0, sizeof e->k_launches);
