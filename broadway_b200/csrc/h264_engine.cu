@@ -154,6 +154,7 @@ struct ParseScratch {              /* one Kp launch */
     KpPic *h_pics, *d_pics;
     uint32_t cap;
     uint32_t *d_ticket;
+    uint32_t ticket_val;           /* where the last launch of this slot left d_ticket */
     cudaEvent_t done;              /* the launch has finished */
     bool used;
     uint32_t ctas;                 /* exclusive mode: SMs the launch owns while it runs */
@@ -410,9 +411,18 @@ static int launch_parse(h264b200_engine *e, std::vector<PicBuf *> &list)
     cudaStream_t s = stream < 0 ? e->s_comp : e->s_parse[stream];
     cudaEventRecord(e->ev_h2d, e->s_h2d);
     cudaStreamWaitEvent(s, e->ev_h2d, 0);
-    cudaMemcpyAsync(d_pics, ps.h_pics, n * sizeof(KpPic), cudaMemcpyHostToDevice, s);
-    cudaMemsetAsync(d_ticket, 0, 64, s);
-    KpBatch kb; kb.pics = d_pics; kb.n_pics = n; kb.ticket = d_ticket; kb.tables = e->d_tables;
+    KpBatch kb; kb.pics = d_pics; kb.n_pics = n; kb.ticket = d_ticket; kb.tables = e->d_tables; kb.ticket_base = 0;
+    if (retain) {                  /* the replay needs the table on the device and starts every run from a zeroed counter */
+        cudaMemcpyAsync(d_pics, ps.h_pics, n * sizeof(KpPic), cudaMemcpyHostToDevice, s);
+        cudaMemsetAsync(d_ticket, 0, 64, s);
+    } else {
+        /* no copy-engine work in front of the kernel (it would queue behind the frame copy-out): the warps read their
+         * picture descriptors straight from the pinned table, and the counter continues where the slot's last launch left it */
+        kb.pics = ps.h_pics;
+        kb.ticket_base = ps.ticket_val;
+        const uint32_t warps = e->kp_sms ? kp_ctas(e, n) * 32u : (((n + 7) / 8 < (uint32_t)e->sm_count * 4 ? (n + 7) / 8 : (uint32_t)e->sm_count * 4) * 8u);
+        ps.ticket_val += n + warps;
+    }
     tl_begin(e, 1, n, s);
     kp_launch(e, kb, s);
     tl_end(e, s);
@@ -592,8 +602,8 @@ static uint32_t launch_round(h264b200_engine *e, std::vector<PicBuf *> &list, Co
         cudaEventRecord(e->ev_h2d, e->s_h2d);
         cudaStreamWaitEvent(e->s_comp, e->ev_h2d, 0);
     }
-    cudaMemcpyAsync(d_jobs, sc.h_jobs, n * sizeof(PicJob), cudaMemcpyHostToDevice, e->s_comp);
-    cudaMemsetAsync(d_ctrl, 0, ctrl_words * sizeof(int32_t), e->s_comp);
+    k0_stage<<<32, 256, 0, e->s_comp>>>(d_jobs, sc.h_jobs, (int)n, d_ctrl, (uint32_t)ctrl_words);   /* job table + zeroed control words, without the copy engines */
+    e->st.kernel_launches++;
     tl_begin(e, 0, n, e->s_comp);
     if (e->flags & H264B200_ENGINE_TAP_PREDEBLOCK) {
         /* parity aid: K0..K3, the pictures copied aside, then K4 */
@@ -1217,6 +1227,7 @@ extern "C" h264b200_engine_t *h264b200EngineCreateEx(int device, uint32_t flags)
     for (int i = 0; i < NPAR; i++) {
         CUDA_TRY(cudaEventCreateWithFlags(&e->pscr[i].done, cudaEventDisableTiming), { delete e; return NULL; });
         CUDA_TRY(cudaMalloc((void **)&e->pscr[i].d_ticket, 64), { delete e; return NULL; });
+        CUDA_TRY(cudaMemset(e->pscr[i].d_ticket, 0, 64), { delete e; return NULL; });
     }
     {   /* the host parser's code tables, for kernel Kp */
         KpTables *t = (KpTables *)malloc(sizeof(KpTables));

@@ -59,7 +59,12 @@ __device__ __forceinline__ uint32_t ref_px(const uint8_t *pl, int w, int h, int 
  *     blocks from up to 32 macroblocks, so its window loads no longer share sectors; the two neighbouring
  *     macroblocks of an unsorted warp overlap heavily and that locality is worth more than the instructions;
  *   - the three window words as two 8-byte loads plus selects: 2.31;
- *   - prefetch.global.L1 of the residual slots at the top (ptxas sinks the loads to their use): 2.21, no change. */
+ *   - prefetch.global.L1 of the residual slots at the top (ptxas sinks the loads to their use): 2.21, no change.
+ * Round 2, what-if bounds (profiles/r02_k2_whatif_ab.json; build flags below, wrong pictures, timing only): with the luma
+ * window for free (K2_WHATIF_NO_WINDOW_LOADS) the kernel takes 1.73 ms, with the interpolation replaced by a copy
+ * (K2_WHATIF_NO_MATH) 1.33 ms.  So staging the window through shared memory / TMA can win 21 % at the very most, and
+ * the larger lever is the 1.33 ms this thread-per-4x4 mapping costs as a pure data mover (per-thread record decoding,
+ * 33 narrow loads, 4-byte stores): a warp-per-macroblock-pair mapping with 16-byte row accesses is the next step. */
 __global__ void __launch_bounds__(K2_THREADS, 8) k2_inter(Batch b)
 {
     const unsigned FULL = 0xffffffffu;

@@ -23,7 +23,8 @@
 struct KpBatch {
     const KpPic *pics;
     uint32_t n_pics;
-    uint32_t *ticket;              /* zeroed before the launch */
+    uint32_t *ticket;              /* device counter the warps draw pictures from; holds `ticket_base` when the launch starts */
+    uint32_t ticket_base;          /* the host knows where a launch leaves the counter (n_pics + one failed draw per warp): no memset between launches */
     const KpTables *tables;        /* device copy of the host-built tables */
 };
 
@@ -45,7 +46,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) kp_parse(KpBatch b)
     KpStage *st = &stage[threadIdx.x >> 5];
     for (;;) {
         uint32_t t = 0;
-        if (lane == 0) t = atomicAdd(b.ticket, 1u);
+        if (lane == 0) t = atomicAdd(b.ticket, 1u) - b.ticket_base;
         t = __shfl_sync(0xffffffffu, t, 0);
         if (t >= b.n_pics) break;
         const KpPic p = b.pics[t];
@@ -53,6 +54,20 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) kp_parse(KpBatch b)
     }
 }
 static_assert(sizeof(KpTables) % 16 == 0 && sizeof(KpStage) % 16 == 0, "shared memory layout of kernel Kp");
+
+/* First kernel of a round: fetch the job table from the pinned host memory it was written to (every cudaHostAlloc'ed
+ * byte is device-readable under unified addressing) and zero the round's control words.  This replaces a
+ * cudaMemcpyAsync + cudaMemsetAsync on the compute stream: those are copy-engine work, and behind the ~800 MB of
+ * frame copy-out of the previous round they made a round's kernels wait until that copy-out had finished (the
+ * timeline showed every round starting exactly when the previous copy-out ended). */
+__global__ void k0_stage(PicJob *jobs, const PicJob *host_jobs, int n_jobs, int32_t *ctrl, uint32_t ctrl_words)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+    const uint32_t job_words = (uint32_t)n_jobs * (uint32_t)(sizeof(PicJob) / 4);
+    for (uint32_t w = i; w < job_words; w += stride) reinterpret_cast<uint32_t *>(jobs)[w] = reinterpret_cast<const volatile uint32_t *>(host_jobs)[w];
+    for (uint32_t w = i; w < ctrl_words; w += stride) ctrl[w] = 0;
+}
+static_assert(sizeof(PicJob) % 4 == 0, "PicJob is copied word-wise");
 
 /* After Kp, before K1: copy what the parse found out about each picture into its job, and put the status words behind
  * the frame so that they travel to the host with it. */
