@@ -98,6 +98,9 @@ struct Inst {
     uint8_t *d_frames, *h_frames;
     cudaEvent_t slot_ready[H264_MAX_SLOTS];   /* (not owned) copy-out event of the batch that last wrote the slot's mirror */
     uint8_t slot_flags[H264_MAX_SLOTS];       /* bit 1: a copy-out into the slot's mirror has been issued (slot_ready is valid) */
+    uint8_t slot_scr[H264_MAX_SLOTS];         /* which scratch set's d2h_done slot_ready is ... */
+    uint32_t slot_rseq[H264_MAX_SLOTS];       /* ... and the round it was recorded for: the event is re-recorded when the set serves a later round, and then
+                                                 says nothing about this slot any more — except that its own copy-out ended long ago (slot_copy_pending) */
     uint32_t slot_qgen[H264_MAX_SLOTS];       /* pictures handed over (queued) into the slot so far */
     uint32_t slot_lgen[H264_MAX_SLOTS];       /* generation of the last LAUNCHED picture of the slot */
     uint32_t slot_popped[H264_MAX_SLOTS];     /* newest generation of the slot handed out through frame_host_async */
@@ -148,6 +151,7 @@ struct Scratch {
     cudaEvent_t done;              /* kernels of the batch finished */
     cudaEvent_t d2h_done;          /* copy-out of the batch finished */
     bool used;
+    uint32_t seq;                  /* the round this set currently serves (engine round_seq) */
 };
 
 struct ParseScratch {              /* one Kp launch */
@@ -194,6 +198,7 @@ struct h264b200_engine {
                                       and the launch and the round behind it waited for them) */
     CopyList cl;                   /* scratch list of the launch being built (engine mutex) */
     double drv_locked_ms, drv_copy_ms, drv_locked_max; uint64_t drv_polls, drv_launches;   /* H264B200_TIMELINE: host time of the scheduling steps */
+    uint32_t round_seq;            /* rounds launched so far */
     uint32_t n_unparsed;           /* device-parse pictures queued and not yet handed to Kp (engine mutex) */
     KpTables *d_tables;
     uint32_t window, parse_threshold;
@@ -242,6 +247,16 @@ static void picbuf_free(PicBuf *p)
     if (p->own_dev && p->d_mbs) cudaFree(p->d_mbs);
     if (p->own_dblock && p->d_block) cudaFree(p->d_block);
     memset(p, 0, sizeof *p);
+}
+
+/* Is the copy-out last issued into `slot` possibly still running?  slot_ready is the d2h_done event of a scratch set; once
+ * that set has moved on to a later round the event belongs to THAT round — waiting for it (or polling it) would tie this
+ * slot to a copy-out several rounds younger, which is what serialised every round behind the previous round's copy-out.
+ * A set is reused only after its previous copy-out has finished (launch_round), so "moved on" means "arrived". */
+static bool slot_copy_pending(const h264b200_engine *e, const Inst *in, int slot)
+{
+    if (!(in->slot_flags[slot] & 2)) return false;
+    return __atomic_load_n(&e->scr[in->slot_scr[slot]].seq, __ATOMIC_ACQUIRE) == in->slot_rseq[slot];
 }
 
 /* ------------------------------------------------------------ kernel launch */
@@ -485,7 +500,10 @@ static uint32_t launch_round(h264b200_engine *e, std::vector<PicBuf *> &list, Co
     Retained *ret = nullptr;
     Scratch &sc = e->scr[e->next_scr];
     e->next_scr = (e->next_scr + 1) % NSCR;
-    if (sc.used) cudaEventSynchronize(sc.done);
+    if (sc.used) { cudaEventSynchronize(sc.done); cudaEventSynchronize(sc.d2h_done); }   /* in the free-running schedule both ended long ago */
+    const uint32_t rseq = ++e->round_seq;
+    __atomic_store_n(&sc.seq, rseq, __ATOMIC_RELEASE);      /* from here on the set's events speak for this round only (slot_copy_pending) */
+    const int scr_index = (int)(&sc - e->scr);
     size_t ctrl_words = CTRL_HEAD;
     for (PicBuf *p : list) ctrl_words += 2 * (size_t)p->inst->hm;
     if (sc.cap_jobs < n) {
@@ -587,7 +605,7 @@ static uint32_t launch_round(h264b200_engine *e, std::vector<PicBuf *> &list, Co
         j.mb_base = mb_base; mb_base += in->n_mbs;
         if ((int)in->hm > pl.max_hm) pl.max_hm = (int)in->hm;
         /* the frame being written may still be on its way to the host from an earlier batch */
-        if (in->slot_flags[pic->cur_slot] & 2) cudaStreamWaitEvent(e->s_comp, in->slot_ready[pic->cur_slot], 0);
+        if (slot_copy_pending(e, in, pic->cur_slot)) cudaStreamWaitEvent(e->s_comp, in->slot_ready[pic->cur_slot], 0);
     }
     pl.total_mbs = mb_base; pl.n_jobs = (int)n;
     if (e->flags & H264B200_ENGINE_NO_RECON) pl.k1 = pl.k2 = pl.k3 = pl.k3c = pl.k4 = false;
@@ -643,6 +661,7 @@ static uint32_t launch_round(h264b200_engine *e, std::vector<PicBuf *> &list, Co
         p->done = sc.done;
         p->state = 3;
         in->slot_ready[slot] = sc.d2h_done;
+        in->slot_scr[slot] = (uint8_t)scr_index; in->slot_rseq[slot] = rseq;
         in->slot_flags[slot] = 2;
         if (in->out_format == H264B200_OUT_RGBA && in->d_rgba) e->st.kernel_launches++;      /* K5, launched with the copy-out */
         if (!(e->flags & H264B200_ENGINE_NO_D2H)) e->st.d2h_bytes += (in->out_format == H264B200_OUT_RGBA && in->d_rgba) ? in->rgba_bytes : in->frame_bytes;
@@ -1047,7 +1066,7 @@ static int wait_slot(h264b200_engine *e, Inst *in, int slot, uint32_t gen, bool 
     }
     if (in->slot_lgen[slot] != gen) return (int32_t)(in->slot_lgen[slot] - gen) < 0 ? 2 : 1;
     if (in->slot_flags[slot] & 4) return -1;
-    if (in->slot_flags[slot] & 2) {
+    if (slot_copy_pending(e, in, slot)) {
         set_device(e);
         cudaError_t er = cudaEventSynchronize(in->slot_ready[slot]);
         if (er != cudaSuccess) { fprintf(stderr, "h264b200: reconstruction failed: %s\n", cudaGetErrorString(er)); return -1; }
@@ -1110,7 +1129,7 @@ static int be_frame_state(h264_backend_t *be, void *inst, int slot, uint32_t gen
     if ((int32_t)(lg - g) < 0) return 2;
     if (lg != g) return 0;                              /* a later picture was launched into the slot: h264b200PictureWait reports that */
     if (in->slot_flags[slot] & 4) return -1;
-    if (in->slot_flags[slot] & 2) { set_device(e); return cudaEventQuery(in->slot_ready[slot]) == cudaSuccess ? 0 : 1; }
+    if (slot_copy_pending(e, in, slot)) { set_device(e); return cudaEventQuery(in->slot_ready[slot]) == cudaSuccess ? 0 : 1; }
     return 0;
 }
 
@@ -1178,7 +1197,7 @@ extern "C" h264b200_engine_t *h264b200EngineCreateEx(int device, uint32_t flags)
     if (h264b200Probe(msg, sizeof msg)) { fprintf(stderr, "h264b200: %s\n", msg); return NULL; }
     if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
     h264b200_engine *e = new h264b200_engine();
-    e->device = device; e->flags = flags; e->next_scr = 0; e->next_pscr = 0; e->parse_seq = 0; e->n_unparsed = 0;
+    e->device = device; e->flags = flags; e->next_scr = 0; e->next_pscr = 0; e->parse_seq = 0; e->n_unparsed = 0; e->round_seq = 0;
     e->drv_locked_ms = e->drv_copy_ms = e->drv_locked_max = 0; e->drv_polls = e->drv_launches = 0;
     { const char *c = getenv("H264B200_COPY_AT_SUBMIT"); e->copy_at_submit = !(c && atoi(c) == 0); }
     e->window = 1; e->eff_window = 1; e->parse_threshold = 1; e->n_inst_hint = 0; e->inst_budget = 0;
