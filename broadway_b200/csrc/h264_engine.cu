@@ -152,6 +152,7 @@ struct Scratch {
     cudaEvent_t d2h_done;          /* copy-out of the batch finished */
     bool used;
     uint32_t seq;                  /* the round this set currently serves (engine round_seq) */
+    uint32_t done_seq;             /* the last round of this set whose copy-out the scheduling thread has seen finished */
 };
 
 struct ParseScratch {              /* one Kp launch */
@@ -199,6 +200,7 @@ struct h264b200_engine {
     CopyList cl;                   /* scratch list of the launch being built (engine mutex) */
     double drv_locked_ms, drv_copy_ms, drv_locked_max; uint64_t drv_polls, drv_launches;   /* H264B200_TIMELINE: host time of the scheduling steps */
     uint32_t round_seq;            /* rounds launched so far */
+    double last_drive_ms;          /* host clock of the last h264b200EngineDrive (0: never): while a scheduling thread is polling, picture states come from what IT saw */
     uint32_t n_unparsed;           /* device-parse pictures queued and not yet handed to Kp (engine mutex) */
     KpTables *d_tables;
     uint32_t window, parse_threshold;
@@ -818,7 +820,12 @@ static uint32_t drive_locked(h264b200_engine *e, int idle, uint32_t *kp_pics, Co
     }
     /* ---- round ---- */
     uint32_t in_flight = 0;
-    for (int k = 0; k < NSCR; k++) if (e->scr[k].used && cudaEventQuery(e->scr[k].d2h_done) != cudaSuccess) in_flight++;
+    for (int k = 0; k < NSCR; k++) {
+        Scratch &q = e->scr[k];
+        if (!q.used || q.done_seq == q.seq) continue;
+        if (cudaEventQuery(q.d2h_done) != cudaSuccess) in_flight++;
+        else __atomic_store_n(&q.done_seq, q.seq, __ATOMIC_RELEASE);      /* what be_frame_state reports to the polling workers */
+    }
     if (in_flight >= DRIVE_ROUNDS) return 0;
     std::vector<PicBuf *> &rl = e->tmp_round; rl.clear();
     uint32_t nonempty = 0;
@@ -1129,7 +1136,15 @@ static int be_frame_state(h264_backend_t *be, void *inst, int slot, uint32_t gen
     if ((int32_t)(lg - g) < 0) return 2;
     if (lg != g) return 0;                              /* a later picture was launched into the slot: h264b200PictureWait reports that */
     if (in->slot_flags[slot] & 4) return -1;
-    if (slot_copy_pending(e, in, slot)) { set_device(e); return cudaEventQuery(in->slot_ready[slot]) == cudaSuccess ? 0 : 1; }
+    if (slot_copy_pending(e, in, slot)) {
+        /* While a scheduling thread drives the engine it polls the copy-out events anyway and publishes what it sees;
+         * fifteen workers asking the runtime about every picture of every stream on every sweep (850 000 cudaEventQuery
+         * per second) slowed every other CUDA call of the process down, the launches included. */
+        if (__atomic_load_n(&e->scr[in->slot_scr[slot]].done_seq, __ATOMIC_ACQUIRE) == in->slot_rseq[slot]) return 0;
+        if (e->last_drive_ms > 0 && host_ms_now() - e->last_drive_ms < 20.0) return 1;
+        set_device(e);
+        return cudaEventQuery(in->slot_ready[slot]) == cudaSuccess ? 0 : 1;
+    }
     return 0;
 }
 
@@ -1197,7 +1212,7 @@ extern "C" h264b200_engine_t *h264b200EngineCreateEx(int device, uint32_t flags)
     if (h264b200Probe(msg, sizeof msg)) { fprintf(stderr, "h264b200: %s\n", msg); return NULL; }
     if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
     h264b200_engine *e = new h264b200_engine();
-    e->device = device; e->flags = flags; e->next_scr = 0; e->next_pscr = 0; e->parse_seq = 0; e->n_unparsed = 0; e->round_seq = 0;
+    e->device = device; e->flags = flags; e->next_scr = 0; e->next_pscr = 0; e->parse_seq = 0; e->n_unparsed = 0; e->round_seq = 0; e->last_drive_ms = 0;
     e->drv_locked_ms = e->drv_copy_ms = e->drv_locked_max = 0; e->drv_polls = e->drv_launches = 0;
     { const char *c = getenv("H264B200_COPY_AT_SUBMIT"); e->copy_at_submit = !(c && atoi(c) == 0); }
     e->window = 1; e->eff_window = 1; e->parse_threshold = 1; e->n_inst_hint = 0; e->inst_budget = 0;
@@ -1349,7 +1364,8 @@ extern "C" u32 h264b200EngineDrive(h264b200_engine_t *e, int idle, u32 *kp_pictu
     if (!e) return 0;
     CopyOut co; co.d2h_done = nullptr;
     u32 n, kp = 0;
-    const double t0 = e->tl_path ? host_ms_now() : 0;
+    const double t0 = host_ms_now();
+    e->last_drive_ms = t0;
     {
         std::lock_guard<std::mutex> lk(e->mu);
         n = drive_locked(e, idle, &kp, &co);
