@@ -198,7 +198,8 @@ struct h264b200_engine {
                                       by the Kp launch, hundreds of ~230 KB copies at once — measured 14 ms per launch next to the copy-out traffic,
                                       and the launch and the round behind it waited for them) */
     CopyList cl;                   /* scratch list of the launch being built (engine mutex) */
-    double drv_locked_ms, drv_copy_ms, drv_locked_max; uint64_t drv_polls, drv_launches;   /* H264B200_TIMELINE: host time of the scheduling steps */
+    double drv_locked_ms, drv_copy_ms, drv_locked_max; uint64_t drv_polls, drv_launches;
+    uint64_t drv_miss[4];          /* per launched round: heads not taken because unparsed / in a running Kp launch / held back by an unreleased output; [3] rounds */   /* H264B200_TIMELINE: host time of the scheduling steps */
     uint32_t round_seq;            /* rounds launched so far */
     double last_drive_ms;          /* host clock of the last h264b200EngineDrive (0: never): while a scheduling thread is polling, picture states come from what IT saw */
     uint32_t n_unparsed;           /* device-parse pictures queued and not yet handed to Kp (engine mutex) */
@@ -338,6 +339,8 @@ static void tl_dump(h264b200_engine *e)
     FILE *f = fopen(e->tl_path, "a");
     if (e->drv_polls) fprintf(stderr, "h264b200 scheduling thread: %llu steps, %llu launched something: %.1f ms under the mutex (max %.2f), %.1f ms issuing copy-outs\n",
                               (unsigned long long)e->drv_polls, (unsigned long long)e->drv_launches, e->drv_locked_ms, e->drv_locked_max, e->drv_copy_ms);
+    if (e->drv_miss[3]) fprintf(stderr, "h264b200 rounds: %llu; streams left out per round on average: %.1f head not yet handed to Kp, %.1f in a running Kp launch, %.1f held back by an unreleased output\n",
+                                (unsigned long long)e->drv_miss[3], (double)e->drv_miss[0] / e->drv_miss[3], (double)e->drv_miss[1] / e->drv_miss[3], (double)e->drv_miss[2] / e->drv_miss[3]);
     if (f) {
         fprintf(f, "kind,pictures,host_launch_ms,gpu_start_ms,gpu_end_ms\n");
         for (auto &t : e->tl) {
@@ -828,23 +831,24 @@ static uint32_t drive_locked(h264b200_engine *e, int idle, uint32_t *kp_pics, Co
     }
     if (in_flight >= DRIVE_ROUNDS) return 0;
     std::vector<PicBuf *> &rl = e->tmp_round; rl.clear();
-    uint32_t nonempty = 0;
+    uint32_t nonempty = 0, miss[3] = {0, 0, 0};
     for (Inst *in : e->insts) {
         if (in->fifo->empty()) continue;
         nonempty++;
         PicBuf *p = in->fifo->front();
         if (in->dev_parse) {
-            if (!p->parse_seq) continue;
+            if (!p->parse_seq) { miss[0]++; continue; }
             bool busy = false;
             for (int k = 0; k < n_running; k++) if (running[k] == p->parse_seq) busy = true;
-            if (busy) continue;
+            if (busy) { miss[1]++; continue; }
         }
-        if (gated(p)) continue;
+        if (gated(p)) { miss[2]++; continue; }
         rl.push_back(p);
     }
     if (rl.empty()) return 0;
     if ((uint32_t)rl.size() * 8 < nonempty * 7 && !(idle && n_running == 0 && in_flight == 0)) return 0;
     for (PicBuf *p : rl) { p->inst->fifo->pop_front(); p->inst->n_pending.fetch_sub(1, std::memory_order_release); }
+    e->drv_miss[0] += miss[0]; e->drv_miss[1] += miss[1]; e->drv_miss[2] += miss[2]; e->drv_miss[3]++;
     return launch_round(e, rl, defer);
 }
 
@@ -1213,7 +1217,7 @@ extern "C" h264b200_engine_t *h264b200EngineCreateEx(int device, uint32_t flags)
     if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
     h264b200_engine *e = new h264b200_engine();
     e->device = device; e->flags = flags; e->next_scr = 0; e->next_pscr = 0; e->parse_seq = 0; e->n_unparsed = 0; e->round_seq = 0; e->last_drive_ms = 0;
-    e->drv_locked_ms = e->drv_copy_ms = e->drv_locked_max = 0; e->drv_polls = e->drv_launches = 0;
+    e->drv_locked_ms = e->drv_copy_ms = e->drv_locked_max = 0; e->drv_polls = e->drv_launches = 0; memset(e->drv_miss, 0, sizeof e->drv_miss);
     { const char *c = getenv("H264B200_COPY_AT_SUBMIT"); e->copy_at_submit = !(c && atoi(c) == 0); }
     e->window = 1; e->eff_window = 1; e->parse_threshold = 1; e->n_inst_hint = 0; e->inst_budget = 0;
     memset(&e->st, 0, sizeof e->st); memset(e->scr, 0, sizeof e->scr); memset(e->pscr, 0, sizeof e->pscr);

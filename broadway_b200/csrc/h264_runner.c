@@ -258,6 +258,7 @@ static void *dev_worker_main(void *arg)
 {
     worker_t *w = (worker_t *)arg; runner_t *r = w->r;
     uint32_t sweep = 0, quiet = 0;
+    double last_collect = 0;
     for (;; sweep++) {
         uint32_t live = 0, activity = 0, idx;
         for (idx = w->tid; idx < r->n_streams; idx += r->n_workers) {
@@ -272,9 +273,19 @@ static void *dev_worker_main(void *arg)
             activity += dev_consume(w, s, idx);
             burst = s->chunk;
             while (burst-- && !s->finished && !s->failed && h264b200PicturesPending(&s->st) < s->depth) {
-                double t0 = now_s();
+                double t0 = now_s(), t1;
                 activity += 1 + (uint32_t)dev_scan_one(s);
-                w->parse_s += now_s() - t0;
+                t1 = now_s();
+                w->parse_s += t1 - t0;
+                /* A picture cannot be launched while an older output of its frame slot is unreleased, so collecting must
+                 * not wait for the scanning of a whole sweep (tens of milliseconds: the rounds went out with ~15 % of
+                 * the streams missing): every half millisecond of scanning, a pass over all own streams that only
+                 * collects — a few atomic reads per stream. */
+                if (t1 - last_collect > 0.0005) {
+                    uint32_t j;
+                    for (j = w->tid; j < r->n_streams; j += r->n_workers) if (r->s[j].inited && !r->s[j].done && r->s[j].outq_n) activity += dev_consume(w, &r->s[j], j);
+                    last_collect = now_s();
+                }
             }
             if ((s->finished || s->failed) && !s->outq_n && !h264b200PicturesPending(&s->st)) s->done = 1;
         }
