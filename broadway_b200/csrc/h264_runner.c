@@ -35,6 +35,9 @@
 static double now_s(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return (double)t.tv_sec + 1e-9 * (double)t.tv_nsec; }
 
 #define MAX_PENDING 20
+#ifndef H264B200_HOST_SHARE_DEFAULT
+#define H264B200_HOST_SHARE_DEFAULT "0"      /* "auto" once it has been measured to pay on the box at hand */
+#endif
 
 typedef struct { u8 *ptr; u32 ticket, pic_id, err; } pending_t;
 
@@ -60,6 +63,7 @@ typedef struct {
     pthread_t th;
     uint64_t pictures, bytes_out; uint32_t err_mbs;
     double parse_s, wait_s;
+    uint32_t *own; uint32_t n_own;            /* device-parse: the streams this worker owns (a decoder instance is single-threaded) */
 } worker_t;
 
 #define MAX_GROUPS 2
@@ -251,7 +255,7 @@ static u32 dev_consume(worker_t *w, rstream_t *s, uint32_t stream_index)
 
 static void idle_wait(unsigned us) { struct timespec t; t.tv_sec = 0; t.tv_nsec = (long)us * 1000L; nanosleep(&t, NULL); }
 
-/* A worker owns the streams  tid, tid + n_workers, ...  (a decoder instance is single-threaded) and sweeps over them for
+/* A worker owns a fixed set of streams (a decoder instance is single-threaded) and sweeps over them for
  * as long as one of them is alive: collect what has arrived, release it, top the look-ahead up.  Nothing in a sweep
  * blocks on the GPU; a sweep that found nothing to do sleeps for a moment. */
 static void *dev_worker_main(void *arg)
@@ -261,8 +265,9 @@ static void *dev_worker_main(void *arg)
     double last_collect = 0;
     for (;; sweep++) {
         uint32_t live = 0, activity = 0, idx;
-        for (idx = w->tid; idx < r->n_streams; idx += r->n_workers) {
-            rstream_t *s = &r->s[idx];
+        uint32_t oi;
+        for (oi = 0; oi < w->n_own; oi++) {
+            rstream_t *s = &r->s[(idx = w->own[oi])];
             uint32_t burst;
             if (!s->inited || s->done) continue;
             live++;
@@ -283,7 +288,7 @@ static void *dev_worker_main(void *arg)
                  * collects — a few atomic reads per stream. */
                 if (t1 - last_collect > 0.0005) {
                     uint32_t j;
-                    for (j = w->tid; j < r->n_streams; j += r->n_workers) if (r->s[j].inited && !r->s[j].done && r->s[j].outq_n) activity += dev_consume(w, &r->s[j], j);
+                    for (j = 0; j < w->n_own; j++) { rstream_t *o = &r->s[w->own[j]]; if (o->inited && !o->done && o->outq_n) activity += dev_consume(w, o, w->own[j]); }
                     last_collect = now_s();
                 }
             }
@@ -291,7 +296,7 @@ static void *dev_worker_main(void *arg)
         }
         if (!live) break;
         if (__atomic_load_n(&r->stop, __ATOMIC_ACQUIRE)) {        /* the scheduling thread saw no progress for seconds: give up on what is left */
-            for (idx = w->tid; idx < r->n_streams; idx += r->n_workers) if (r->s[idx].inited && !r->s[idx].done) { r->s[idx].failed = 1; r->s[idx].done = 1; }
+            for (oi = 0; oi < w->n_own; oi++) { rstream_t *o = &r->s[w->own[oi]]; if (o->inited && !o->done) { o->failed = 1; o->done = 1; } }
             break;
         }
         if (r->inline_drive) {                                    /* one thread for everything: a scheduling step per sweep */
@@ -332,22 +337,23 @@ static void *dev_driver_main(void *arg)
     return NULL;
 }
 
-/* How many of the streams of a device-parse run are parsed by the worker threads instead of kernel Kp
- * (h264b200SetHostParse).  Both parsers write the same records, so a stream can take either.  Default: none — on the
- * development box the copy-out of the finished frames (PCIe, ~16 000 1080p frames/s) is reached before Kp's share of the
- * SMs is, and a host-parsed picture costs 12x the upload of its slices.  H264B200_HOST_STREAMS=n
- * gives n streams to the threads; "auto" sizes the share for a box where Kp is the bottleneck: a picture costs the GPU
- * d = 65 us in Kp next to k = 22 us of reconstruction, a thread h = 4.1 ms, so the two sides finish together at
- * H = S (d + k) / (h / T + d) for S streams and T worker threads (the ratio h : d is a property of the two parsers, both
- * scale with the bits of the picture; measured on the bench workload). */
+/* How many of the streams of a device-parse run are parsed by worker threads instead of kernel Kp
+ * (h264b200SetHostParse).  Both parsers write the same records, so a stream can take either; a host-parsed picture
+ * costs a thread h = 4.1 ms (and 12x the upload of its slices), a Kp-parsed one costs the GPU ~45 us of all its SMs next
+ * to 22 us of reconstruction.  The share has workers of its own (all but three, see h264b200DecodeStreams); each of them
+ * keeps up with  round time / h  streams, and the round time on the development box is ~20 ms.  H264B200_HOST_STREAMS=n
+ * sets the share, "auto" sizes it from the worker count (80 % of what the parsing workers can sustain, a third of the
+ * streams at most); default: see host_share_default. */
 static uint32_t host_share(uint32_t n_streams, uint32_t n_threads)
 {
     const char *env = getenv("H264B200_HOST_STREAMS");
-    const double T = (double)(n_threads > 1 ? n_threads - 1 : 1), d = 65.0, k = 22.0, h = 4100.0;
-    if (!env) return 0;
+    const uint32_t n_workers = n_threads > 1 ? n_threads - 1 : 1;
+    uint32_t h;
+    if (!env) env = H264B200_HOST_SHARE_DEFAULT;
     if (strcmp(env, "auto")) { const long v = atol(env); return v <= 0 ? 0 : (uint32_t)v > n_streams ? n_streams : (uint32_t)v; }
-    if (n_streams < 2 * n_threads) return 0;                       /* few streams: the look-ahead, not the parser, is the limit */
-    return (uint32_t)(0.9 * (double)n_streams * (d + k) / (h / T + d));
+    if (n_workers < 6 || n_streams < 4 * n_threads) return 0;      /* too few threads to spare any, or too few streams to need it */
+    h = (uint32_t)(0.8 * (double)(n_workers - 3) * 20.0 / 4.1);
+    return h > n_streams / 3 ? n_streams / 3 : h;
 }
 
 int h264b200DecodeStreams(h264b200_engine_t *e, const h264b200_stream_t *streams, uint32_t n_streams,
@@ -411,9 +417,21 @@ int h264b200DecodeStreams(h264b200_engine_t *e, const h264b200_stream_t *streams
         /* free-running pipeline: the calling thread schedules the engine, the others are workers over their own streams
          * (a single thread does both) */
         pthread_t drv;
+        uint32_t scan_workers, k_dev = 0, k_host = 0;
         r.n_workers = n_threads > 1 ? n_threads - 1 : 1;
         r.inline_drive = n_threads == 1;
         r.workers_alive = r.n_workers;
+        /* Who owns which stream.  Scanning a picture is ~0.2 ms, parsing one on the host ~4 ms: a worker that parses would
+         * serve device-parsed streams of its own late (their outputs uncollected, their rounds short), so the host share has
+         * workers of its own and three workers keep all the device-parsed streams (measured: 3 reach what 15 reach). */
+        scan_workers = (n_host && r.n_workers >= 6) ? 3 : r.n_workers;
+        for (i = 0; i < r.n_workers; i++) { w[i].own = (uint32_t *)malloc((n_streams + 1) * sizeof(uint32_t)); w[i].n_own = 0; if (!w[i].own) { rc = -1; r.n_workers = i; r.workers_alive = i; break; } }
+        for (i = 0; i < n_streams && r.n_workers; i++) {
+            worker_t *o;
+            if (r.s[i].host_parse && scan_workers < r.n_workers) o = &w[scan_workers + k_host++ % (r.n_workers - scan_workers)];
+            else o = &w[k_dev++ % scan_workers];
+            o->own[o->n_own++] = i;
+        }
         for (i = 1; i < r.n_workers; i++) pthread_create(&w[i].th, NULL, dev_worker_main, &w[i]);
         if (r.inline_drive) dev_worker_main(&w[0]);
         else {
@@ -422,6 +440,7 @@ int h264b200DecodeStreams(h264b200_engine_t *e, const h264b200_stream_t *streams
             pthread_join(drv, NULL);
         }
         for (i = 1; i < r.n_workers; i++) pthread_join(w[i].th, NULL);
+        for (i = 0; i < r.n_workers; i++) free(w[i].own);
         while (h264b200EngineSubmit(e)) ;                                          /* nothing should be left; be safe */
         for (i = 0; i < n_streams; i++) if (r.s[i].inited && (r.s[i].outq_n || !r.s[i].done)) r.s[i].failed = 1;
     } else {
