@@ -757,8 +757,8 @@ static uint32_t advance_all_locked(h264b200_engine *e)
  * calls a few thousand times per second while worker threads submit pictures and collect outputs on their own.  A call
  * that finds nothing to launch costs a handful of event queries.
  *   Kp: as soon as `parse_threshold` unparsed pictures are queued and SMs of Kp's share are free, a launch over as many
- *       pictures as fit those SMs — the oldest unparsed picture of every instance first, then the second oldest ..., in
- *       whole levels, so that the streams stay in step and the rounds stay full.  Fewer than the threshold are only
+ *       pictures as fit those SMs — the oldest unparsed picture of every instance first, then the second oldest ..., so
+ *       that a truncated launch still serves every stream — in multiples of 32 (every CTA of the launch full).  Fewer than the threshold are only
  *       launched when no Kp launch is running at all and the caller reports that its workers are idle (`idle`): the
  *       look-ahead windows are full or the streams are ending, so waiting would not bring more.
  *   round: the oldest queued picture of every instance whose Kp launch has FINISHED (a round then starts at once and its
@@ -785,19 +785,14 @@ static uint32_t drive_locked(h264b200_engine *e, int idle, uint32_t *kp_pics, Co
         const ParseScratch &nps = e->pscr[e->next_pscr];
         bool go = !nps.used || nps.finished;
         uint32_t take = unparsed > 8192 ? 8192 : unparsed;
-        uint32_t with_unparsed = 0;
-        if (go) for (Inst *in : e->insts) {
-            if (!in->dev_parse) continue;
-            for (PicBuf *p : *in->fifo) if (!p->parse_seq) { with_unparsed++; break; }
-        }
         if (go && e->kp_sms) {
             const uint32_t free_ctas = busy_ctas < e->kp_sms ? e->kp_sms - busy_ctas : 0;
             const uint32_t min_ctas = (e->parse_threshold + 31) / 32;     /* a launch worth its latency */
-            if (free_ctas >= (take + 31) / 32) ;
-            else if (free_ctas >= min_ctas || (n_running == 0 && free_ctas)) {
-                take = free_ctas * 32;
-                if (with_unparsed && take >= with_unparsed) take -= take % with_unparsed;   /* whole levels */
+            if (free_ctas >= (take + 31) / 32) {
+                /* every CTA full: a launch of 551 pictures would own 18 SMs for what 17.2 can do (the rest joins the next launch) */
+                if (take >= e->parse_threshold && take >= 64 && !idle) take -= take % 32;
             }
+            else if (free_ctas >= min_ctas || (n_running == 0 && free_ctas)) take = free_ctas * 32;
             else go = false;
         }
         if (go && take) {
@@ -1465,6 +1460,19 @@ extern "C" u32 h264b200EngineReplay(h264b200_engine_t *e, u32 reps, int time_ker
             if (r->kind == 1) {
                 cudaStream_t s = r->stream < 0 ? e->s_comp : e->s_parse[r->stream];
                 if (r->wait_round >= 0) cudaStreamWaitEvent(s, e->retained[(size_t)r->wait_round]->ev, 0);
+                if (e->kp_sms) {
+                    /* the live run never has more Kp CTAs in flight than Kp's share of the SMs (h264b200EngineDrive): the
+                     * replay enqueues everything at once, so the same limit becomes a wait for the launch that, counting
+                     * backwards, is the first one that no longer fits — otherwise sixteen launches would take every SM
+                     * and the rounds would run in the gaps */
+                    uint32_t ctas = kp_ctas(e, r->kp.n_pics);
+                    for (size_t k = bi; k-- > 0;) {
+                        const Retained *q = e->retained[k];
+                        if (q->kind != 1) continue;
+                        ctas += kp_ctas(e, q->kp.n_pics);
+                        if (ctas > e->kp_sms) { cudaStreamWaitEvent(s, q->ev, 0); break; }
+                    }
+                }
                 cudaMemsetAsync(r->kp.ticket, 0, 64, s);
                 if (tev) cudaEventRecord(tev[0], s);
                 kp_launch(e, r->kp, s);
