@@ -1460,19 +1460,6 @@ extern "C" u32 h264b200EngineReplay(h264b200_engine_t *e, u32 reps, int time_ker
             if (r->kind == 1) {
                 cudaStream_t s = r->stream < 0 ? e->s_comp : e->s_parse[r->stream];
                 if (r->wait_round >= 0) cudaStreamWaitEvent(s, e->retained[(size_t)r->wait_round]->ev, 0);
-                if (e->kp_sms) {
-                    /* the live run never has more Kp CTAs in flight than Kp's share of the SMs (h264b200EngineDrive): the
-                     * replay enqueues everything at once, so the same limit becomes a wait for the launch that, counting
-                     * backwards, is the first one that no longer fits — otherwise sixteen launches would take every SM
-                     * and the rounds would run in the gaps */
-                    uint32_t ctas = kp_ctas(e, r->kp.n_pics);
-                    for (size_t k = bi; k-- > 0;) {
-                        const Retained *q = e->retained[k];
-                        if (q->kind != 1) continue;
-                        ctas += kp_ctas(e, q->kp.n_pics);
-                        if (ctas > e->kp_sms) { cudaStreamWaitEvent(s, q->ev, 0); break; }
-                    }
-                }
                 cudaMemsetAsync(r->kp.ticket, 0, 64, s);
                 if (tev) cudaEventRecord(tev[0], s);
                 kp_launch(e, r->kp, s);
