@@ -200,6 +200,7 @@ struct h264b200_engine {
     CopyList cl;                   /* scratch list of the launch being built (engine mutex) */
     double drv_locked_ms, drv_copy_ms, drv_locked_max; uint64_t drv_polls, drv_launches;
     uint64_t drv_miss[4];          /* per launched round: heads not taken because unparsed / in a running Kp launch / held back by an unreleased output; [3] rounds */   /* H264B200_TIMELINE: host time of the scheduling steps */
+    std::atomic<uint32_t> copyouts_deferred;   /* rounds whose copy-out h264b200EngineDrive still has to issue (outside the mutex) */
     uint32_t round_seq;            /* rounds launched so far */
     double last_drive_ms;          /* host clock of the last h264b200EngineDrive (0: never): while a scheduling thread is polling, picture states come from what IT saw */
     uint32_t n_unparsed;           /* device-parse pictures queued and not yet handed to Kp (engine mutex) */
@@ -671,7 +672,7 @@ static uint32_t launch_round(h264b200_engine *e, std::vector<PicBuf *> &list, Co
         if (in->out_format == H264B200_OUT_RGBA && in->d_rgba) e->st.kernel_launches++;      /* K5, launched with the copy-out */
         if (!(e->flags & H264B200_ENGINE_NO_D2H)) e->st.d2h_bytes += (in->out_format == H264B200_OUT_RGBA && in->d_rgba) ? in->rgba_bytes : in->frame_bytes;
     }
-    if (defer) { defer->list = list; defer->d2h_done = sc.d2h_done; }      /* h264b200EngineDrive issues the copies after it has let go of the mutex */
+    if (defer) { defer->list = list; defer->d2h_done = sc.d2h_done; e->copyouts_deferred.fetch_add(1); }      /* h264b200EngineDrive issues the copies after it has let go of the mutex */
     else { CopyOut co; co.list = list; co.d2h_done = sc.d2h_done; copy_out_issue(e, co); }
     e->st.pictures += n; e->st.batches++;
     if (retain) {
@@ -974,6 +975,9 @@ static void be_inst_destroy(h264_backend_t *be, void *inst)
         for (size_t i = 0; i < e->insts.size(); i++) if (e->insts[i] == in) { e->insts.erase(e->insts.begin() + i); break; }
     }
     set_device(e);
+    /* a round of this instance may have been launched by the scheduling thread with its copy-out still to be issued: the
+     * stream synchronisation below must see those copies, or they would land in a pooled instance's new life */
+    while (e->copyouts_deferred.load() != 0) { struct timespec ts = {0, 50000}; nanosleep(&ts, NULL); }
     for (int k = 0; k < NPAR; k++) cudaStreamSynchronize(e->s_parse[k]);
     cudaStreamSynchronize(e->s_comp); cudaStreamSynchronize(e->s_d2h);
     if (!keep) { std::lock_guard<std::mutex> lk(e->mu); e->pool.push_back(in); }
@@ -1211,7 +1215,7 @@ extern "C" h264b200_engine_t *h264b200EngineCreateEx(int device, uint32_t flags)
     if (h264b200Probe(msg, sizeof msg)) { fprintf(stderr, "h264b200: %s\n", msg); return NULL; }
     if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
     h264b200_engine *e = new h264b200_engine();
-    e->device = device; e->flags = flags; e->next_scr = 0; e->next_pscr = 0; e->parse_seq = 0; e->n_unparsed = 0; e->round_seq = 0; e->last_drive_ms = 0;
+    e->device = device; e->flags = flags; e->next_scr = 0; e->next_pscr = 0; e->parse_seq = 0; e->n_unparsed = 0; e->round_seq = 0; e->last_drive_ms = 0; e->copyouts_deferred.store(0);
     e->drv_locked_ms = e->drv_copy_ms = e->drv_locked_max = 0; e->drv_polls = e->drv_launches = 0; memset(e->drv_miss, 0, sizeof e->drv_miss);
     { const char *c = getenv("H264B200_COPY_AT_SUBMIT"); e->copy_at_submit = !(c && atoi(c) == 0); }
     e->window = 1; e->eff_window = 1; e->parse_threshold = 1; e->n_inst_hint = 0; e->inst_budget = 0;
@@ -1370,7 +1374,7 @@ extern "C" u32 h264b200EngineDrive(h264b200_engine_t *e, int idle, u32 *kp_pictu
         n = drive_locked(e, idle, &kp, &co);
     }
     const double t1 = e->tl_path ? host_ms_now() : 0;
-    if (!co.list.empty()) copy_out_issue(e, co);
+    if (!co.list.empty()) { copy_out_issue(e, co); e->copyouts_deferred.fetch_sub(1); }
     if (e->tl_path) {
         const double t2 = host_ms_now();
         e->drv_polls++;

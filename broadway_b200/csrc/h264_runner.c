@@ -35,6 +35,8 @@
 static double now_s(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return (double)t.tv_sec + 1e-9 * (double)t.tv_nsec; }
 
 #define MAX_PENDING 20
+#define STALL_SECONDS 300.0   /* device-parse pipeline: no launch, no scan, no collected picture for this long = stuck (a single Kp launch over 4K
+                                 pictures takes ~1 s, under a profiler's kernel replay a hundred times that) */
 #ifndef H264B200_HOST_SHARE_DEFAULT
 #define H264B200_HOST_SHARE_DEFAULT "0"      /* "auto" once it has been measured to pay on the box at hand */
 #endif
@@ -262,7 +264,7 @@ static void *dev_worker_main(void *arg)
 {
     worker_t *w = (worker_t *)arg; runner_t *r = w->r;
     uint32_t sweep = 0, quiet = 0;
-    double last_collect = 0;
+    double last_collect = 0, last_progress = now_s();
     for (;; sweep++) {
         uint32_t live = 0, activity = 0, idx;
         uint32_t oi;
@@ -303,8 +305,8 @@ static void *dev_worker_main(void *arg)
             u32 kp = 0;
             const u32 n = h264b200EngineDrive(r->e, !activity, &kp);
             if (n) r->rounds++;
-            if (n || kp || activity) quiet = 0;
-            else if (++quiet > 20000) __atomic_store_n(&r->stop, 1, __ATOMIC_RELEASE);
+            if (n || kp || activity) { quiet = 0; last_progress = now_s(); }
+            else if (++quiet > 1000 && now_s() - last_progress > STALL_SECONDS) __atomic_store_n(&r->stop, 1, __ATOMIC_RELEASE);
             if (!n && !kp && !activity) idle_wait(50);
             continue;
         }
@@ -322,16 +324,17 @@ static void *dev_driver_main(void *arg)
 {
     runner_t *r = (runner_t *)arg;
     uint32_t last_activity = 0, quiet = 0;
+    double last_progress = now_s();
     while (__atomic_load_n(&r->workers_alive, __ATOMIC_ACQUIRE) > 0) {
         u32 kp = 0;
         u32 n = h264b200EngineDrive(r->e, quiet >= 8, &kp);
         if (n) r->rounds++;
-        if (n || kp) { quiet = 0; continue; }
+        if (n || kp) { quiet = 0; last_progress = now_s(); continue; }
         {
             const uint32_t a = __atomic_load_n(&r->activity, __ATOMIC_ACQUIRE);
-            if (a != last_activity) { last_activity = a; quiet = 0; } else quiet++;
+            if (a != last_activity) { last_activity = a; quiet = 0; last_progress = now_s(); } else quiet++;
         }
-        if (quiet > 30000) __atomic_store_n(&r->stop, 1, __ATOMIC_RELEASE);   /* ~5 s without any progress anywhere */
+        if (quiet > 1000 && now_s() - last_progress > STALL_SECONDS) __atomic_store_n(&r->stop, 1, __ATOMIC_RELEASE);   /* minutes without any progress anywhere: give up instead of hanging */
         idle_wait(250);
     }
     return NULL;
