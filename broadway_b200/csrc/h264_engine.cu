@@ -26,12 +26,15 @@
  * (include/h264b200_slices.h); kernel Kp (kp_core.h, kp_parse.cuh) parses the slice data of every queued
  * picture of every instance in one launch on its own stream — pictures of one stream are independent at
  * that level, so the look-ahead window of all streams is the parallelism — and writes the same records
- * and slots into HBM.  Pictures wait in a FIFO per instance; every h264b200EngineAdvance launches Kp
- * when enough of them are queued and then ONE reconstruction round (the oldest picture of each instance).
+ * and slots into HBM.  Pictures wait in a FIFO per instance; a scheduling thread (h264b200DecodeStreams) polls
+ * h264b200EngineDrive, which launches Kp whenever enough pictures are queued and SMs of Kp's share are free, and ONE
+ * reconstruction round at a time (the oldest picture of each instance whose Kp launch has finished), up to three
+ * rounds deep; h264b200EngineAdvance / h264b200EngineSubmit are the lock-step forms of the same two steps.
  *
- * Streams: s_h2d (records/slots in) -> s_comp (K1..K4) -> s_d2h (frames out),
- * chained with events, so the copy-in of batch n+1 and the copy-out of batch
- * n-1 overlap the kernels of batch n.  There is no CPU reconstruction path in
+ * Streams: s_h2d (records / slice blocks in) -> s_parse[0..15] (Kp launches, overlapping) -> s_comp (K0 staging,
+ * K1..K4) -> s_d2h (frames out), chained with events, so the copy-in of what comes next and the copy-out of what is
+ * finished overlap the kernels; nothing a round or a Kp launch needs goes through a copy engine in front of it
+ * (k0_stage, persistent ticket counters), because behind ~800 MB of frame copy-out it would wait.  There is no CPU reconstruction path in
  * this library: if CUDA is unusable h264_default_backend() returns NULL and
  * h264bsdDecode reports H264BSD_MEMALLOC_ERROR (reason on stderr).
  */

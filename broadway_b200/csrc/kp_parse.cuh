@@ -5,9 +5,10 @@
  * Launch shape: persistent CTAs; a warp takes pictures from an atomic ticket until none is left, so a
  * launch over more pictures than resident warps stays balanced.  Per CTA the host parser's look-up tables (25 KB,
  * KpTables) are copied into shared memory once; per warp 2.9 KB of staging (KpStage).  Only lane 0 walks the syntax —
- * the bitstream is serial — so the kernel is bound by dependent-instruction latency, not by HBM: what makes it pay is
- * that thousands of pictures (every picture of the look-ahead window of every stream) are in flight at once, which is
- * parallelism the host cores do not have.
+ * the bitstream is serial — so the kernel is bound by instruction fetch and dependent-instruction latency, not by HBM
+ * (issue saturates at 2 of 4 warp instructions per clock per SM because the L0 instruction cache
+ * misses on every new 128-byte line): what makes it pay is that thousands of pictures (every picture of the look-ahead
+ * window of every stream) are in flight at once, which is parallelism the host cores do not have.
  */
 #pragma once
 #include "k_common.cuh"
