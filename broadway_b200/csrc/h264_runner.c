@@ -318,8 +318,9 @@ static void *dev_worker_main(void *arg)
 }
 
 /* The scheduling thread: drives the engine while the workers feed it.  When neither it nor any worker has made progress
- * for a millisecond — the look-ahead windows are full, or the streams are ending and fewer pictures than a launch is
- * normally worth are left — it asks for relaxed launches (anything that is ready goes). */
+ * for a couple of milliseconds — the look-ahead windows are full, or the streams are ending and fewer pictures than a
+ * launch is normally worth are left — it tells the engine so (`idle`), which then launches whatever is ready once the
+ * device has nothing else to do. */
 static void *dev_driver_main(void *arg)
 {
     runner_t *r = (runner_t *)arg;
@@ -408,8 +409,7 @@ int h264b200DecodeStreams(h264b200_engine_t *e, const h264b200_stream_t *streams
         if (!s->buf || h264b200InitOnEngine(&s->st, 0, e) != HANTRO_OK) { s->failed = 1; rc = -1; continue; }
         h264b200SetReadOnlyInput(&s->st, 1);
         s->inited = 1; s->depth = depth; s->chunk = chunk;
-        /* the host share, spread evenly over the stream indices (work items are claimed in index order, so the long
-         * items — a host parse is ~30 scans — are interleaved with short ones and the threads finish a round together) */
+        /* the host share (off by default), spread evenly over the stream indices */
         if (dev && (uint32_t)(((uint64_t)(i + 1) * n_host) / n_streams) != (uint32_t)(((uint64_t)i * n_host) / n_streams)) {
             h264b200SetHostParse(&s->st, 1);
             s->host_parse = 1; s->depth = 2; s->chunk = 1;     /* one picture per round, one queued ahead (the input ring holds three) */
@@ -417,8 +417,8 @@ int h264b200DecodeStreams(h264b200_engine_t *e, const h264b200_stream_t *streams
     }
     for (i = 0; i < n_threads; i++) { w[i].r = &r; w[i].tid = i; }
     if (dev) {
-        /* free-running pipeline: the calling thread schedules the engine, the others are workers over their own streams
-         * (a single thread does both) */
+        /* free-running pipeline: one thread schedules the engine (dev_driver_main), the calling thread and the others are
+         * workers over their own streams; with a single thread the worker takes the scheduling steps itself */
         pthread_t drv;
         uint32_t scan_workers, k_dev = 0, k_host = 0;
         r.n_workers = n_threads > 1 ? n_threads - 1 : 1;

@@ -143,9 +143,9 @@ typedef struct {
  * the streams, when there are at least four streams per thread, so that no
  * thread ever waits for a round to end; always one while H264B200_ENGINE_RETAIN is
  * set, so that a retained batch is a whole round) while the next pictures are being parsed.
- * On a device-parse engine (kernel Kp) the pipeline is free-running instead: the calling thread schedules the engine
- * (h264b200EngineDrive), the other threads sweep over their own streams — scan ahead, collect, release — and never
- * block on the GPU.  H264B200_HOST_STREAMS=n|auto hands a share of the streams to the threads' own parser
+ * On a device-parse engine (kernel Kp) the pipeline is free-running instead: one of the n_threads schedules the engine
+ * (h264b200EngineDrive), the others sweep over their own streams — scan ahead, collect, release — and never block on
+ * the GPU (four threads per GPU reach the throughput of sixteen).  H264B200_HOST_STREAMS=n|auto hands a share of the streams to the threads' own parser
  * (h264b200SetHostParse: same records, same rounds, less work for Kp; off by default).
  * `rounds` in the statistics counts the batches.  Returns 0 on success. */
 int h264b200DecodeStreams(h264b200_engine_t *e, const h264b200_stream_t *streams, uint32_t n_streams,
