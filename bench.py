@@ -397,6 +397,7 @@ def own_arm(args, rank, local_rank, world):
                        "l2": "inputs larger than L2 (per step: %.0f MB of frame pools + records per GPU)" % (args.streams * 2 * WORKLOADS[args.workload][0] * WORKLOADS[args.workload][1] * 384 / 1e6 + h2d / 1e6)},
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1000.0 * e2e_s / args.steps, "timing": "wall clock between barrier+synchronize pairs around ONE streaming call over the K steps (each stream = its step repeated K times), max over ranks",
+                    "scaling_note": "weak scaling: every rank decodes its own %d streams on its own GPU with %d host threads, ranks never interact; compare this e2e value across N, not `value`" % (args.streams, threads),
                     "host_parsed_streams": host_streams, "slice_data_parse": ("kernel Kp for %d streams, the %d worker threads' own parser for %d (h264b200DecodeStreams' host share)" % (args.streams - host_streams, threads, host_streams)) if args.parse == "device" else "host",
                     "host_parse_core_seconds_per_step": parse_s / args.steps, "host_wait_seconds_per_step": wait_s / args.steps,
                     "kernel_launches": launches_e2e},
