@@ -60,7 +60,7 @@
 
 #define NBUF 3                 /* input buffers in flight per instance (host-parse; device-parse: look-ahead depth + 2) */
 #define RING_EXTRA 4           /* device-parse input ring = look-ahead + this: the picture being scanned and up to DRIVE_ROUNDS launched ones whose kernels still read their buffers */
-#define NSCR 4                 /* batch scratch sets in flight per engine */
+#define NSCR 8                 /* batch scratch sets in flight per engine */
 #define NPAR 16                /* Kp launches in flight per engine: one scratch set and one CUDA stream each, so that they overlap —
                                   a launch over a quarter of the look-ahead window does not fill the SMs on its own */
 #define STAT_TAIL 128          /* bytes behind every frame: h264b200_picstat_t of the picture (device-parse), copied out with it */
@@ -111,6 +111,8 @@ struct Inst {
     PicBuf *bufs; int n_bufs;
     int next_buf;
     int batched;
+    int lane_pref;                            /* reconstruction lane of this instance's pictures when rounds are split */
+    int last_lane; cudaEvent_t last_done;     /* lane and kernels-finished event of the instance's last launched picture (ordering across lanes) */
     int dev_parse;                            /* slice data parsed by kernel Kp */
     std::deque<PicBuf *> *fifo;               /* pictures handed over, oldest first; one per round is launched (engine mutex) */
     std::atomic<uint32_t> n_pending;          /* == fifo->size(), readable without the mutex */
@@ -187,6 +189,9 @@ struct h264b200_engine {
     uint32_t wf_cap;               /* CTAs per SM the wavefront kernels K3 / K4 are launched with at most (tickets hand out the rows); H264B200_WF_CAP, default 16 */
     cudaStream_t s_h2d, s_comp, s_d2h, s_parse[NPAR];
     cudaEvent_t ev_h2d, ev_comp, ev_rep0, ev_rep1, ev_gate;
+    cudaStream_t s_comp2; cudaEvent_t ev_comp2;   /* second reconstruction lane (H264B200_SPLIT_ROUNDS=1, experiment): a round goes out as two halves over
+                                                     disjoint sets of instances on two streams, so that one half's wavefront tails overlap the other half's K1 / K2 */
+    int split_rounds; uint32_t next_lane;
     std::mutex mu;
     std::vector<Inst *> insts;
     std::vector<Inst *> zombies;   /* shut-down instances whose frame pools retained batches still name */
@@ -288,9 +293,8 @@ __global__ void k_count_bytes(Batch b, unsigned long long *out)
     if ((threadIdx.x & 31) == 0) { atomicAdd(out, k1); atomicAdd(out + 1, k2); atomicAdd(out + 2, k3); atomicAdd(out + 3, k4); }
 }
 
-static void launch_kernels(h264b200_engine *e, const Batch &b, const BatchPlan &pl, cudaEvent_t *tev)
+static void launch_kernels(h264b200_engine *e, const Batch &b, const BatchPlan &pl, cudaEvent_t *tev, cudaStream_t s)
 {
-    cudaStream_t s = e->s_comp;
     if (pl.k0) { k0_jobs<<<(pl.n_jobs + 127) / 128, 128, 0, s>>>(const_cast<PicJob *>(b.jobs), pl.n_jobs); e->st.kernel_launches++; }
     if (tev) cudaEventRecord(tev[0], s);
     if (pl.k1) { uint32_t blocks = (pl.total_mbs * 8 + 255) / 256; k1_transform<<<blocks, 256, 0, s>>>(b); e->st.kernel_launches++; }   /* 8 lanes per macroblock */
@@ -501,8 +505,10 @@ static void copy_out_issue(h264b200_engine *e, CopyOut &co)
     }
 }
 
-static uint32_t launch_round(h264b200_engine *e, std::vector<PicBuf *> &list, CopyOut *defer = nullptr)
+static uint32_t launch_round(h264b200_engine *e, std::vector<PicBuf *> &list, CopyOut *defer = nullptr, int lane = 0)
 {
+    cudaStream_t cs = lane ? e->s_comp2 : e->s_comp;
+    cudaEvent_t evc = lane ? e->ev_comp2 : e->ev_comp;
     uint32_t n = (uint32_t)list.size();
     if (!n) return 0;
     const bool retain = (e->flags & H264B200_ENGINE_RETAIN) != 0;
@@ -561,7 +567,7 @@ static uint32_t launch_round(h264b200_engine *e, std::vector<PicBuf *> &list, Co
             if (p->parse_seq != last_parse_seq) {
                 /* the slot's event may have been re-recorded by a LATER launch — then this picture's launch finished long ago
                  * (a slot is reused only after its launch ended) and waiting on the event would wait for the wrong launch */
-                if (retain || e->pscr[p->parse_slot].seq == p->parse_seq) cudaStreamWaitEvent(e->s_comp, p->parsed, 0);
+                if (retain || e->pscr[p->parse_slot].seq == p->parse_seq) cudaStreamWaitEvent(cs, p->parsed, 0);
                 last_parse_seq = p->parse_seq;
             }
             j.kp_res = p->d_res;
@@ -614,7 +620,10 @@ static uint32_t launch_round(h264b200_engine *e, std::vector<PicBuf *> &list, Co
         j.mb_base = mb_base; mb_base += in->n_mbs;
         if ((int)in->hm > pl.max_hm) pl.max_hm = (int)in->hm;
         /* the frame being written may still be on its way to the host from an earlier batch */
-        if (slot_copy_pending(e, in, pic->cur_slot)) cudaStreamWaitEvent(e->s_comp, in->slot_ready[pic->cur_slot], 0);
+        if (slot_copy_pending(e, in, pic->cur_slot)) cudaStreamWaitEvent(cs, in->slot_ready[pic->cur_slot], 0);
+        /* the instance's previous picture ran on the other lane: its kernels first (a re-recorded event only waits longer) */
+        if (in->last_done && in->last_lane != lane) cudaStreamWaitEvent(cs, in->last_done, 0);
+        in->last_lane = lane; in->last_done = sc.done;
     }
     pl.total_mbs = mb_base; pl.n_jobs = (int)n;
     if (e->flags & H264B200_ENGINE_NO_RECON) pl.k1 = pl.k2 = pl.k3 = pl.k3c = pl.k4 = false;
@@ -627,34 +636,34 @@ static uint32_t launch_round(h264b200_engine *e, std::vector<PicBuf *> &list, Co
 
     if (uploaded) {                /* records of host-parsed pictures; device-parsed ones have nothing in the upload stream a round depends on */
         cudaEventRecord(e->ev_h2d, e->s_h2d);
-        cudaStreamWaitEvent(e->s_comp, e->ev_h2d, 0);
+        cudaStreamWaitEvent(cs, e->ev_h2d, 0);
     }
-    k0_stage<<<32, 256, 0, e->s_comp>>>(d_jobs, sc.h_jobs, (int)n, d_ctrl, (uint32_t)ctrl_words);   /* job table + zeroed control words, without the copy engines */
+    k0_stage<<<32, 256, 0, cs>>>(d_jobs, sc.h_jobs, (int)n, d_ctrl, (uint32_t)ctrl_words);   /* job table + zeroed control words, without the copy engines */
     e->st.kernel_launches++;
-    tl_begin(e, 0, n, e->s_comp);
+    tl_begin(e, 0, n, cs);
     if (e->flags & H264B200_ENGINE_TAP_PREDEBLOCK) {
         /* parity aid: K0..K3, the pictures copied aside, then K4 */
         BatchPlan a = pl, c; memset(&c, 0, sizeof c);
         a.k4 = false;
         c.k4 = pl.k4; c.total_mbs = pl.total_mbs; c.max_hm = pl.max_hm; c.n_jobs = pl.n_jobs;
-        launch_kernels(e, b, a, nullptr);
+        launch_kernels(e, b, a, nullptr, cs);
         for (uint32_t i = 0; i < n; i++) {
             Inst *in = list[i]->inst;
             if (!in->d_pre && cudaMalloc((void **)&in->d_pre, in->frame_bytes) != cudaSuccess) { in->d_pre = nullptr; continue; }
-            cudaMemcpyAsync(in->d_pre, in->d_frames + (size_t)list[i]->in.cur_slot * in->frame_stride, in->frame_bytes, cudaMemcpyDeviceToDevice, e->s_comp);
+            cudaMemcpyAsync(in->d_pre, in->d_frames + (size_t)list[i]->in.cur_slot * in->frame_stride, in->frame_bytes, cudaMemcpyDeviceToDevice, cs);
         }
-        launch_kernels(e, b, c, nullptr);
+        launch_kernels(e, b, c, nullptr, cs);
     } else
-    launch_kernels(e, b, pl, nullptr);
-    tl_end(e, e->s_comp);
+    launch_kernels(e, b, pl, nullptr, cs);
+    tl_end(e, cs);
     if (retain) {
-        cudaMemsetAsync(ret->d_bytes, 0, 4 * sizeof(unsigned long long), e->s_comp);
-        k_count_bytes<<<(mb_base + 255) / 256, 256, 0, e->s_comp>>>(b, ret->d_bytes);
+        cudaMemsetAsync(ret->d_bytes, 0, 4 * sizeof(unsigned long long), cs);
+        k_count_bytes<<<(mb_base + 255) / 256, 256, 0, cs>>>(b, ret->d_bytes);
     }
     if (b.trace) {                 /* debug: dump the wavefront timing of job 0 of this batch */
         const int rows = sc.h_jobs[0].hm < 512 ? sc.h_jobs[0].hm : 512;
         std::vector<unsigned long long> h(256 + 4 * 512);
-        cudaStreamSynchronize(e->s_comp);
+        cudaStreamSynchronize(cs);
         cudaMemcpy(h.data(), e->d_trace, h.size() * 8, cudaMemcpyDeviceToHost);
         fprintf(stderr, "h264b200 trace: batch of %u, job0 %dx%d MBs; per row: start, first-mb, mid, end (us from row 0 start)\n", n, sc.h_jobs[0].wm, sc.h_jobs[0].hm);
         for (int r = 0; r < rows; r++) { const unsigned long long *q = &h[256 + r * 4], t0 = h[256];
@@ -662,9 +671,9 @@ static uint32_t launch_round(h264b200_engine *e, std::vector<PicBuf *> &list, Co
         cudaMemset(e->d_trace, 0, h.size() * 8);
         e->trace_left--;
     }
-    cudaEventRecord(sc.done, e->s_comp); sc.used = true;
-    cudaEventRecord(e->ev_comp, e->s_comp);
-    cudaStreamWaitEvent(e->s_d2h, e->ev_comp, 0);
+    cudaEventRecord(sc.done, cs); sc.used = true;
+    cudaEventRecord(evc, cs);
+    cudaStreamWaitEvent(e->s_d2h, evc, 0);
     for (uint32_t i = 0; i < n; i++) {
         PicBuf *p = list[i]; Inst *in = p->inst; const int slot = p->in.cur_slot;
         p->done = sc.done;
@@ -679,7 +688,7 @@ static uint32_t launch_round(h264b200_engine *e, std::vector<PicBuf *> &list, Co
     else { CopyOut co; co.list = list; co.d2h_done = sc.d2h_done; copy_out_issue(e, co); }
     e->st.pictures += n; e->st.batches++;
     if (retain) {
-        cudaEventRecord(ret->ev, e->s_comp);
+        cudaEventRecord(ret->ev, cs);
         ret->jobs.assign(sc.h_jobs, sc.h_jobs + n);
         ret->batch = b; ret->batch.trace = nullptr; ret->ctrl_words = ctrl_words;
         ret->pl = pl;
@@ -771,7 +780,7 @@ static uint32_t advance_all_locked(h264b200_engine *e)
  *       copy-out not finished): enough to keep kernels and copy-out busy back to back.
  * *kp_pics = pictures handed to Kp by this call.  Returns the pictures of the round launched (0: none). */
 #define DRIVE_ROUNDS 3
-static uint32_t drive_locked(h264b200_engine *e, int idle, uint32_t *kp_pics, CopyOut *defer)
+static uint32_t drive_locked(h264b200_engine *e, int idle, uint32_t *kp_pics, CopyOut *defer, CopyOut *defer2)
 {
     set_device(e);
     if (kp_pics) *kp_pics = 0;
@@ -828,7 +837,7 @@ static uint32_t drive_locked(h264b200_engine *e, int idle, uint32_t *kp_pics, Co
         if (cudaEventQuery(q.d2h_done) != cudaSuccess) in_flight++;
         else __atomic_store_n(&q.done_seq, q.seq, __ATOMIC_RELEASE);      /* what be_frame_state reports to the polling workers */
     }
-    if (in_flight >= DRIVE_ROUNDS) return 0;
+    if (in_flight >= (e->split_rounds ? 2u * DRIVE_ROUNDS : (uint32_t)DRIVE_ROUNDS)) return 0;
     std::vector<PicBuf *> &rl = e->tmp_round; rl.clear();
     uint32_t nonempty = 0, miss[3] = {0, 0, 0};
     for (Inst *in : e->insts) {
@@ -848,6 +857,15 @@ static uint32_t drive_locked(h264b200_engine *e, int idle, uint32_t *kp_pics, Co
     if ((uint32_t)rl.size() * 8 < nonempty * 7 && !(idle && n_running == 0 && in_flight == 0)) return 0;
     for (PicBuf *p : rl) { p->inst->fifo->pop_front(); p->inst->n_pending.fetch_sub(1, std::memory_order_release); }
     e->drv_miss[0] += miss[0]; e->drv_miss[1] += miss[1]; e->drv_miss[2] += miss[2]; e->drv_miss[3]++;
+    if (e->split_rounds && defer2 && rl.size() >= 64 && !(e->flags & (H264B200_ENGINE_RETAIN | H264B200_ENGINE_TAP_PREDEBLOCK))) {
+        /* experiment: the round as two halves over disjoint instances on two streams */
+        std::vector<PicBuf *> a, b2;
+        for (PicBuf *p : rl) (p->inst->lane_pref ? b2 : a).push_back(p);
+        uint32_t n = 0;
+        if (!a.empty()) n += launch_round(e, a, defer, 0);
+        if (!b2.empty()) n += launch_round(e, b2, defer2, 1);
+        return n;
+    }
     return launch_round(e, rl, defer);
 }
 
@@ -895,6 +913,8 @@ static void *be_inst_create_ex(h264_backend_t *be, uint32_t wm, uint32_t hm, uin
                 cudaMemsetAsync(c->d_frames, 0, c->frame_stride * c->n_slots, e->s_comp);
                 memset(c->h_frames, 0, c->frame_stride * c->n_slots);
                 if (c->d_rgba) { cudaMemsetAsync(c->d_rgba, 0, c->rgba_bytes * c->n_slots, e->s_comp); memset(c->h_rgba, 0, c->rgba_bytes * c->n_slots); }
+                if (e->split_rounds) cudaStreamSynchronize(e->s_comp);      /* the instance's first picture may run on the other lane */
+                c->last_done = nullptr; c->last_lane = 0; c->lane_pref = (int)(e->next_lane++ & 1);
                 e->insts.push_back(c);
                 return c;
             }
@@ -906,6 +926,7 @@ static void *be_inst_create_ex(h264_backend_t *be, uint32_t wm, uint32_t hm, uin
     in->frame_stride = in->frame_bytes + STAT_TAIL;
     in->batched = (e->flags & H264B200_ENGINE_BATCHED) != 0;
     in->dev_parse = dev_parse; in->n_bufs = n_bufs;
+    in->last_done = nullptr; in->last_lane = 0; in->lane_pref = 0;
     in->fifo = new std::deque<PicBuf *>();
     in->bufs = (PicBuf *)calloc((size_t)n_bufs, sizeof(PicBuf));
     if (!in->bufs) { inst_free(in); return NULL; }
@@ -938,6 +959,7 @@ static void *be_inst_create_ex(h264_backend_t *be, uint32_t wm, uint32_t hm, uin
     }
     std::lock_guard<std::mutex> lk(e->mu);
     note_window(e, in);
+    in->lane_pref = (int)(e->next_lane++ & 1);
     e->insts.push_back(in);
     return in;
 }
@@ -982,7 +1004,7 @@ static void be_inst_destroy(h264_backend_t *be, void *inst)
      * stream synchronisation below must see those copies, or they would land in a pooled instance's new life */
     while (e->copyouts_deferred.load() != 0) { struct timespec ts = {0, 50000}; nanosleep(&ts, NULL); }
     for (int k = 0; k < NPAR; k++) cudaStreamSynchronize(e->s_parse[k]);
-    cudaStreamSynchronize(e->s_comp); cudaStreamSynchronize(e->s_d2h);
+    cudaStreamSynchronize(e->s_comp); cudaStreamSynchronize(e->s_comp2); cudaStreamSynchronize(e->s_d2h);
     if (!keep) { std::lock_guard<std::mutex> lk(e->mu); e->pool.push_back(in); }
 }
 
@@ -1253,10 +1275,13 @@ extern "C" h264b200_engine_t *h264b200EngineCreateEx(int device, uint32_t flags)
         cudaDeviceGetStreamPriorityRange(&lo, &hi);         /* lo: numerically largest = least urgent */
         CUDA_TRY(cudaStreamCreateWithPriority(&e->s_comp, cudaStreamNonBlocking, prio ? hi : 0), { delete e; return NULL; });
         CUDA_TRY(cudaStreamCreateWithPriority(&e->s_d2h, cudaStreamNonBlocking, prio ? hi : 0), { delete e; return NULL; });
+        CUDA_TRY(cudaStreamCreateWithPriority(&e->s_comp2, cudaStreamNonBlocking, prio ? hi : 0), { delete e; return NULL; });
         for (int k = 0; k < NPAR; k++) CUDA_TRY(cudaStreamCreateWithPriority(&e->s_parse[k], cudaStreamNonBlocking, prio ? lo : 0), { delete e; return NULL; });
     }
     CUDA_TRY(cudaEventCreateWithFlags(&e->ev_h2d, cudaEventDisableTiming), { delete e; return NULL; });
     CUDA_TRY(cudaEventCreateWithFlags(&e->ev_comp, cudaEventDisableTiming), { delete e; return NULL; });
+    CUDA_TRY(cudaEventCreateWithFlags(&e->ev_comp2, cudaEventDisableTiming), { delete e; return NULL; });
+    { const char *c = getenv("H264B200_SPLIT_ROUNDS"); e->split_rounds = c && atoi(c) > 0; e->next_lane = 0; }
     CUDA_TRY(cudaEventCreateWithFlags(&e->ev_gate, cudaEventDisableTiming), { delete e; return NULL; });
     CUDA_TRY(cudaEventCreate(&e->ev_rep0), { delete e; return NULL; });
     CUDA_TRY(cudaEventCreate(&e->ev_rep1), { delete e; return NULL; });
@@ -1318,7 +1343,7 @@ extern "C" void h264b200EngineDestroy(h264b200_engine_t *e)
     if (!e) return;
     set_device(e);
     cudaStreamSynchronize(e->s_h2d); for (int k = 0; k < NPAR; k++) cudaStreamSynchronize(e->s_parse[k]);
-    cudaStreamSynchronize(e->s_comp); cudaStreamSynchronize(e->s_d2h);
+    cudaStreamSynchronize(e->s_comp); cudaStreamSynchronize(e->s_comp2); cudaStreamSynchronize(e->s_d2h);
     tl_dump(e);
     free_retained(e);
     for (Inst *p : e->pool) inst_free(p);
@@ -1341,7 +1366,7 @@ extern "C" void h264b200EngineDestroy(h264b200_engine_t *e)
     cudaFree(e->d_err); cudaFreeHost(e->h_err);
     if (e->d_trace) cudaFree(e->d_trace);
     cudaEventDestroy(e->ev_h2d); cudaEventDestroy(e->ev_comp); cudaEventDestroy(e->ev_rep0); cudaEventDestroy(e->ev_rep1); cudaEventDestroy(e->ev_gate);
-    cudaStreamDestroy(e->s_h2d); cudaStreamDestroy(e->s_comp); cudaStreamDestroy(e->s_d2h);
+    cudaStreamDestroy(e->s_h2d); cudaStreamDestroy(e->s_comp); cudaStreamDestroy(e->s_comp2); cudaStreamDestroy(e->s_d2h); cudaEventDestroy(e->ev_comp2);
     for (int k = 0; k < NPAR; k++) cudaStreamDestroy(e->s_parse[k]);
     delete e;
 }
@@ -1368,16 +1393,17 @@ extern "C" u32 h264b200EngineAdvance(h264b200_engine_t *e)
 extern "C" u32 h264b200EngineDrive(h264b200_engine_t *e, int idle, u32 *kp_pictures)
 {
     if (!e) return 0;
-    CopyOut co; co.d2h_done = nullptr;
+    CopyOut co, co2; co.d2h_done = nullptr; co2.d2h_done = nullptr;
     u32 n, kp = 0;
     const double t0 = host_ms_now();
     e->last_drive_ms = t0;
     {
         std::lock_guard<std::mutex> lk(e->mu);
-        n = drive_locked(e, idle, &kp, &co);
+        n = drive_locked(e, idle, &kp, &co, &co2);
     }
     const double t1 = e->tl_path ? host_ms_now() : 0;
     if (!co.list.empty()) { copy_out_issue(e, co); e->copyouts_deferred.fetch_sub(1); }
+    if (!co2.list.empty()) { copy_out_issue(e, co2); e->copyouts_deferred.fetch_sub(1); }
     if (e->tl_path) {
         const double t2 = host_ms_now();
         e->drv_polls++;
@@ -1416,7 +1442,8 @@ extern "C" void h264b200EngineSync(h264b200_engine_t *e)
     set_device(e);
     cudaError_t a = cudaStreamSynchronize(e->s_h2d), p0 = cudaSuccess;
     for (int k = 0; k < NPAR; k++) { cudaError_t pk = cudaStreamSynchronize(e->s_parse[k]); if (pk != cudaSuccess) p0 = pk; }
-    cudaError_t b = cudaStreamSynchronize(e->s_comp), c = cudaStreamSynchronize(e->s_d2h);
+    cudaError_t b = cudaStreamSynchronize(e->s_comp), b2 = cudaStreamSynchronize(e->s_comp2), c = cudaStreamSynchronize(e->s_d2h);
+    if (b == cudaSuccess) b = b2;
     if (a != cudaSuccess || b != cudaSuccess || c != cudaSuccess || p0 != cudaSuccess)
         fprintf(stderr, "h264b200: engine sync failed: %s\n", cudaGetErrorString(a != cudaSuccess ? a : p0 != cudaSuccess ? p0 : b != cudaSuccess ? b : c));
 }
@@ -1477,7 +1504,7 @@ extern "C" u32 h264b200EngineReplay(h264b200_engine_t *e, u32 reps, int time_ker
                 for (int w : r->wait_parse) cudaStreamWaitEvent(e->s_comp, e->retained[(size_t)w]->ev, 0);
                 /* the round's own control area (tickets + wavefront progress) and job table are part of its retained allocation */
                 cudaMemsetAsync(r->batch.tickets, 0, r->ctrl_words * sizeof(int32_t), e->s_comp);
-                launch_kernels(e, r->batch, r->pl, tev);
+                launch_kernels(e, r->batch, r->pl, tev, e->s_comp);
                 cudaEventRecord(r->ev, e->s_comp);
                 pics += r->n_pics;
                 e->st.batches++;
